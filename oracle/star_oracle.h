@@ -1,0 +1,30 @@
+/*
+ * star_oracle.h — entry points of the CPU restatement (oracle/star_oracle.cpp).
+ * TEST INFRASTRUCTURE ONLY: see the header of star_oracle.cpp.
+ */
+#ifndef STAR_ORACLE_H
+#define STAR_ORACLE_H
+#include "../include/star_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-read intermediate state for unit-level parity tests (the goldens the reference never had) */
+typedef struct star_oracle_dump {
+    uint64_t* pcOff;   /* nReads+1 : first piece of read i */
+    uint64_t* pc;      /* pieces PC[][8] after seeding (IncludeDefine.h:181-189): rStart,Length,Str,Dir,Nrep,SAstart,SAend,iFrag */
+} star_oracle_dump_t;
+
+int star_oracle_init(void** ctx, int device, const star_index_view_t* index, const star_params_t* params, uint32_t maxReads);
+int star_oracle_map_chunk(void* ctx, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats);
+int star_oracle_map_chunk_dump(void* ctx, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats,
+                               star_oracle_dump_t* dump);
+void star_oracle_dump_free(star_oracle_dump_t* d);
+void star_oracle_destroy(void* ctx);
+const char* star_oracle_last_error(void);
+const star_engine_vtbl_t* star_oracle_engine(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,159 @@
+// driver.cpp — the drop-in command line: STAR --runMode alignReads --genomeDir .. --readFilesIn .. (SAM out).
+//
+// Mirrors the run orchestration of reference source/STAR.cpp:58-313 (parameters -> genomeLoad -> SAM header ->
+// map all chunks -> SJ.out.tab -> Log.final.out) with the per-chunk work of
+// ReadAlignChunk::processChunks/mapChunk (ReadAlignChunk_processChunks.cpp:11-282, ReadAlignChunk_mapChunk.cpp:7-128)
+// replaced by one engine call per chunk through the C-ABI (include/star_b200.h).  The engine is passed in as a
+// vtable so that the test-suite can drive the same host code with the CPU oracle; the shipped binary
+// binds the CUDA engine (star_cli_main below) and has no other engine.
+#include <sys/stat.h>
+
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <thread>
+
+#include "host.h"
+
+namespace starhost {
+
+static std::string timeMonthDayTime(time_t t) {
+    char b[100];
+    strftime(b, 80, "%b %d %H:%M:%S", localtime(&t));
+    return b;
+}
+
+static void makeDirs(const std::string& prefix) {  // createDirectory, Parameters.cpp:367
+    size_t p = prefix.rfind('/');
+    if (p == std::string::npos) return;
+    std::string dir = prefix.substr(0, p);
+    std::string cur;
+    for (size_t i = 0; i <= dir.size(); i++) {
+        if (i == dir.size() || dir[i] == '/') {
+            if (!cur.empty()) mkdir(cur.c_str(), 0700);
+        }
+        if (i < dir.size()) cur.push_back(dir[i]);
+    }
+}
+
+static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
+    HostParams P;
+    std::string err;
+    Stats stats;
+    time(&stats.timeStart);
+    int rc = parseCommandLine(argc, argv, P, err);
+    if (rc == -1 && err == "version") { std::cout << "2.7.11b" << std::endl; return 0; }
+    auto exitWithError = [&](const std::string& msg, int code, std::ofstream* logMain) {  // ErrorWarning.cpp:8-23
+        time_t t; time(&t);
+        if (logMain && logMain->is_open()) *logMain << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
+        std::cerr << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
+        return code;
+    };
+    if (rc) return exitWithError(err, rc, nullptr);
+    makeDirs(P.outFileNamePrefix);
+    std::ofstream logMain(P.outFileNamePrefix + "Log.out");
+    if (logMain.fail())
+        return exitWithError("EXITING because of FATAL ERROR: could not create output file: " + P.outFileNamePrefix + "Log.out\nSOLUTION: check if the path " + P.outFileNamePrefix + " exists and you have permissions to write there\n", STAR_EXIT_PARAMETER, nullptr);
+    logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
+    std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
+
+    {
+        time_t t; time(&t);
+        std::cout << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;
+    }
+    LoadedIndex idx;
+    std::string glog;
+    rc = loadIndex(P.genomeDir, &P.hp, idx, err, &glog);
+    logMain << glog << std::flush;
+    if (rc) return exitWithError(err, rc, &logMain);
+
+    void* ectx = nullptr;
+    rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);
+    if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
+
+    ReadsReader reader;
+    rc = reader.open(P, err);
+    if (rc) { eng->destroy(ectx); return exitWithError(err, rc, &logMain); }
+
+    OutputWriter W(P, idx);
+    const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    std::ofstream samOut;
+    if (samYes) {
+        samOut.open(P.outFileNamePrefix + "Aligned.out.sam", std::ios::binary);
+        samOut << W.samHeader();
+    }
+    std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
+    time(&stats.timeStartMap);
+    std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
+
+    std::vector<Junction> allSJ;
+    ReadChunk chunk;
+    std::vector<star_read_result_t> results(P.gpuChunkReads);
+    std::vector<star_align_t> aligns;
+    const int nT = std::max(1, P.runThreadN);
+    star_chunk_stats_t cs;
+    double msEngine = 0;
+    uint64_t nChunks = 0;
+    for (;;) {
+        long long n = reader.next(chunk, P.gpuChunkReads, err);
+        if (n < 0) { eng->destroy(ectx); return exitWithError(err, (int)-n, &logMain); }
+        if (n == 0) break;
+        star_read_batch_t in;
+        in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
+        uint64_t cap = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
+        if (aligns.size() < cap) aligns.resize(cap);
+        star_align_batch_t out;
+        out.reads = results.data(); out.aligns = aligns.data(); out.alignsCapacity = aligns.size(); out.nAligns = 0;
+        memset(&cs, 0, sizeof(cs));
+        rc = eng->map_chunk(ectx, &in, &out, &cs);
+        if (rc) { eng->destroy(ectx); return exitWithError(eng->last_error(), rc, &logMain); }
+        msEngine += cs.ms_total;
+        nChunks++;
+        // format in parallel over contiguous read ranges; concatenate in input order
+        std::vector<std::string> sam(nT);
+        std::vector<std::vector<Junction>> sj(nT);
+        std::vector<Stats> st(nT);
+        auto work = [&](int t) {
+            uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
+            sam[t].reserve((size_t)(hi - lo) * 700);
+            W.formatReads(chunk, out, lo, hi, sam[t], sj[t], st[t]);
+        };
+        if (nT == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nT; t++) th.emplace_back(work, t);
+            for (auto& t : th) t.join();
+        }
+        for (int t = 0; t < nT; t++) {
+            if (samYes) samOut.write(sam[t].data(), sam[t].size());
+            allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
+            stats.add(st[t]);
+        }
+        if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
+            std::string e2;
+            OutputWriter::collapseSJ(allSJ, e2);
+            if (!e2.empty()) { eng->destroy(ectx); return exitWithError(e2, STAR_EXIT_BUG, &logMain); }
+        }
+    }
+    eng->destroy(ectx);
+    if (samYes) samOut.close();
+    time_t tFinishMap; time(&tFinishMap);
+    std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
+    logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
+    logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
+    if (P.outSJyes) {
+        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab");
+        if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
+    }
+    time(&stats.timeFinish);
+    W.writeLogFinal(stats, P.outFileNamePrefix + "Log.final.out");
+    std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished successfully\n" << std::flush;
+    logMain << "ALL DONE!\n" << std::flush;
+    return 0;
+}
+
+}  // namespace starhost
+
+extern "C" int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine) { return starhost::runAlign(argc, argv, engine); }

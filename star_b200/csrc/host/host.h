@@ -1,0 +1,171 @@
+// host.h — internal declarations of the host side (C++) that sits above the C-ABI engine.
+//
+// The host side mirrors the parts of STAR that stay on the CPU around the replaced hot path:
+// parameter parsing (reference source/Parameters.cpp), index loading (Genome_genomeLoad.cpp),
+// FASTQ chunking (ReadAlignChunk_processChunks.cpp), SAM / SJ.out.tab / Log.final.out emission
+// (ReadAlign_outputAlignments.cpp, ReadAlign_outputTranscriptSAM.cpp, outputSJ.cpp, Stats.cpp)
+// and the run driver (STAR.cpp).  It never computes an alignment.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/star_b200.h"
+
+namespace starhost {
+
+struct HostParams {
+    star_params_t hp;                       // what the engine reads
+    // run / IO
+    std::string commandLine, commandLineFull;
+    std::string runMode = "alignReads";
+    int runThreadN = 1;                     // host threads used for FASTQ parsing / SAM formatting
+    std::string genomeDir = "./GenomeDir/";
+    std::string genomeLoad = "NoSharedMemory";
+    std::vector<std::string> readFilesIn = {"Read1", "Read2"};
+    std::vector<std::string> readFilesCommand = {"-"};
+    long long readMapNumber = -1;
+    std::vector<std::string> readNameSeparator = {"/"};
+    std::vector<char> readNameSeparatorChar;
+    std::string outFileNamePrefix = "./";
+    std::string outStd = "Log";
+    std::vector<std::string> outSAMtype = {"SAM"};
+    std::string outSAMmode = "Full";
+    std::string outSAMstrandField = "None";
+    std::vector<std::string> outSAMattributes = {"Standard"};
+    std::vector<int> outSAMattrOrder;       // ATTR_* codes
+    unsigned outSAMattrIHstart = 1;
+    std::vector<std::string> outSAMunmapped = {"None"};
+    bool unmappedWithin = false, unmappedKeepPairs = false;
+    std::string outSAMorder = "Paired";
+    std::string outSAMprimaryFlag = "OneBestScore";
+    std::string outSAMreadID = "Standard";
+    int outSAMmapqUnique = 255;
+    unsigned outSAMflagOR = 0, outSAMflagAND = 65535;
+    std::vector<std::string> outSAMattrRGline = {"-"};
+    std::string outSAMattrRG;               // ID of the single read group (if any)
+    std::string outFilterType = "Normal";
+    std::string outFilterIntronMotifs = "None";
+    std::string outFilterIntronStrands = "RemoveInconsistentStrands";
+    std::vector<std::string> outSJtype = {"Standard"};
+    bool outSJyes = true;
+    std::string outSJfilterReads = "All";
+    std::vector<int32_t> outSJfilterOverhangMin = {30, 12, 12, 12};
+    std::vector<int32_t> outSJfilterCountUniqueMin = {3, 1, 1, 1};
+    std::vector<int32_t> outSJfilterCountTotalMin = {3, 1, 1, 1};
+    std::vector<int32_t> outSJfilterDistToOtherSJmin = {10, 0, 5, 10};
+    std::vector<int32_t> outSJfilterIntronMaxVsReadN = {50000, 100000, 200000};
+    std::string alignEndsType = "Local";
+    std::vector<std::string> alignEndsProtrude = {"0", "ConcordantPair"};
+    std::string alignSoftClipAtReferenceEnds = "Yes";
+    std::string alignInsertionFlush = "None";
+    std::string outMultimapperOrder = "Old_2.4";
+    unsigned readNmates = 1;
+    // star-b200 extensions (not in the reference)
+    int gpuDevice = 0;
+    unsigned gpuChunkReads = 262144;        // reads (pairs) per engine call
+    std::map<std::string, int> userSet;     // parameter name -> input level (for --sjdbOverhang style checks)
+};
+
+// Parses argv exactly like Parameters::inputParameters (Parameters.cpp:310-470) for the supported subset.
+// Returns 0 or a STAR_EXIT_* code with the message in err.
+int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err);
+void paramsDefault(star_params_t* p);
+// derived values that need the other parameters (Parameters.cpp:944-1124)
+int finalizeParams(HostParams& P, std::string& err);
+
+struct LoadedIndex {
+    std::vector<uint8_t> Gstore, SAstore, SAistore;
+    std::vector<uint64_t> genomeSAindexStart, chrStart, chrLength, sjdbStart, sjdbEnd, sjDstart, sjAstart;
+    std::vector<uint8_t> sjdbMotif, sjdbShiftLeft, sjdbShiftRight, sjdbStrand;
+    std::vector<std::string> chrName;
+    std::vector<uint64_t> chrBin;
+    star_index_view_t view;
+    std::string versionGenome;
+};
+int loadIndex(const std::string& genomeDir, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log);
+
+// one chunk of reads in host memory
+struct ReadChunk {
+    uint32_t nReads = 0, nMates = 1;
+    std::string seq, qual;                   // all mates back to back
+    std::vector<uint64_t> seqOff;            // nReads*nMates+1 (same offsets index qual)
+    std::string names;                       // read names (without '@', cut at the separator), '\0'-separated
+    std::vector<uint32_t> nameOff;           // nReads+1
+    std::vector<char> readFilter;            // 'Y'/'N'
+    std::vector<uint64_t> iReadAll;
+    bool fastq = true;
+    void clear() {
+        nReads = 0; seq.clear(); qual.clear(); seqOff.clear(); names.clear(); nameOff.clear(); readFilter.clear(); iReadAll.clear();
+    }
+};
+
+class ReadsReader {
+   public:
+    ~ReadsReader();
+    int open(const HostParams& P, std::string& err);
+    // fills at most maxReads reads; returns number read (0 at EOF) or -STAR_EXIT_* on error
+    long long next(ReadChunk& c, uint32_t maxReads, std::string& err);
+    uint64_t iReadAll = 0;
+
+   private:
+    FILE* f[2] = {nullptr, nullptr};
+    bool piped[2] = {false, false};
+    unsigned nMates = 1;
+    const HostParams* P = nullptr;
+    std::vector<char> buf[2];
+    size_t bpos[2] = {0, 0}, blen[2] = {0, 0};
+    bool getLine(int m, std::string& line);
+    int peekChar(int m);
+};
+
+// Stats.h:11-24
+struct Stats {
+    uint64_t readN = 0, readBases = 0, mappedReadsU = 0, mappedReadsM = 0, mappedBases = 0, mappedMismatchesN = 0, mappedInsN = 0,
+             mappedDelN = 0, mappedInsL = 0, mappedDelL = 0;
+    uint64_t splicesN[STAR_SJ_MOTIF_SIZE] = {0, 0, 0, 0, 0, 0, 0};
+    uint64_t splicesNsjdb = 0;
+    uint64_t unmappedOther = 0, unmappedShort = 0, unmappedMismatch = 0, unmappedMulti = 0, unmappedAll = 0, chimericAll = 0;
+    time_t timeStart = 0, timeStartMap = 0, timeFinish = 0;
+    void add(const Stats& s);
+    // the 24 counters as a flat array (for the multi-GPU allreduce)
+    static const int N_COUNTERS = 24;
+    void toArray(uint64_t* a) const;
+    void fromArray(const uint64_t* a);
+};
+
+// OutSJ.h:9-25 junction record (27 bytes in the reference; plain struct here)
+struct Junction {
+    uint64_t start;
+    uint32_t gap;
+    char strand, motif, annot;
+    uint32_t countUnique, countMultiple;
+    uint16_t overhangLeft, overhangRight;
+};
+
+// Formats everything the reference writes per read: SAM records, junction records, counters.
+class OutputWriter {
+   public:
+    OutputWriter(const HostParams& P, const LoadedIndex& idx) : P(P), idx(idx) {}
+    // appends SAM text for reads [lo,hi) of the chunk to `sam`, junctions to `sj`, counters to `st`
+    void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
+                     std::vector<Junction>& sj, Stats& st) const;
+    std::string samHeader() const;                                   // samHeaders.cpp:5-113
+    // outputSJ.cpp:20-200: collapse + filters + SJ.out.tab text; returns error text (empty = ok)
+    std::string writeSJ(std::vector<Junction>& all, const std::string& path) const;
+    static void collapseSJ(std::vector<Junction>& v, std::string& err);
+    void writeLogFinal(const Stats& st, const std::string& path) const;  // Stats.cpp:99-145
+
+   private:
+    const HostParams& P;
+    const LoadedIndex& idx;
+    void samMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
+                   std::string& sam) const;
+    void samUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trBest, int unmapType,
+                     const bool* mateMap, std::string& sam) const;
+    void recordSJ(const star_align_t& tr, uint64_t nTrOut, std::vector<Junction>& sj, size_t sjReadStartN) const;
+};
+
+}  // namespace starhost

@@ -1,0 +1,509 @@
+// output.cpp — per-read output records built from the engine's POD alignments.
+//
+// Restates (host side, text formatting only):
+//   ReadAlign::outputAlignments / writeSAM / recordSJ   reference source/ReadAlign_outputAlignments.cpp:5-260
+//   ReadAlign::outputTranscriptSAM                       source/ReadAlign_outputTranscriptSAM.cpp:5-359
+//   ReadAlign::outputTranscriptSJ                        source/ReadAlign_outputTranscriptSJ.cpp:4-56
+//   Stats::transcriptStats / reportFinal                 source/Stats.cpp:35-56,99-145
+//   outputSJ + OutSJ::collapseSJ + Junction::outputStream source/outputSJ.cpp:20-200, OutSJ.cpp:34-90
+//   samHeaders                                           source/samHeaders.cpp:5-113
+#include <algorithm>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+
+#include "host.h"
+
+namespace starhost {
+
+enum { ATTR_NH = 1, ATTR_HI, ATTR_AS, ATTR_NM, ATTR_MD, ATTR_nM, ATTR_jM, ATTR_jI, ATTR_XS, ATTR_RG, ATTR_ch = 14, ATTR_MC = 15 };
+
+static inline void putU(std::string& s, uint64_t v) {
+    char b[24];
+    int n = 0;
+    do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(b[--n]);
+}
+static inline void putI(std::string& s, long long v) {
+    if (v < 0) { s.push_back('-'); putU(s, (uint64_t)(-(v + 1)) + 1); } else putU(s, (uint64_t)v);
+}
+
+static void revComplement(const char* in, size_t L, std::string& out) {  // SequenceFuns.cpp:16-54
+    static char tab[256];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 256; i++) tab[i] = (char)i;
+        const char* a = "ACGTNRYKMSWBDVHacgtnrykmswbdvh";
+        const char* b = "TGCANYRMKSWVHBDtgcanyrmkswvhbd";
+        for (int i = 0; a[i]; i++) tab[(unsigned char)a[i]] = b[i];
+        init = true;
+    }
+    out.resize(L);
+    for (size_t j = 0; j < L; j++) out[j] = tab[(unsigned char)in[L - 1 - j]];
+}
+
+void Stats::add(const Stats& s) {
+    readN += s.readN; readBases += s.readBases; mappedReadsU += s.mappedReadsU; mappedReadsM += s.mappedReadsM; mappedBases += s.mappedBases;
+    mappedMismatchesN += s.mappedMismatchesN; mappedInsN += s.mappedInsN; mappedDelN += s.mappedDelN; mappedInsL += s.mappedInsL; mappedDelL += s.mappedDelL;
+    for (int i = 0; i < STAR_SJ_MOTIF_SIZE; i++) splicesN[i] += s.splicesN[i];
+    splicesNsjdb += s.splicesNsjdb;
+    unmappedOther += s.unmappedOther; unmappedShort += s.unmappedShort; unmappedMismatch += s.unmappedMismatch; unmappedMulti += s.unmappedMulti;
+    unmappedAll += s.unmappedAll; chimericAll += s.chimericAll;
+}
+void Stats::toArray(uint64_t* a) const {
+    uint64_t t[N_COUNTERS] = {readN, readBases, mappedReadsU, mappedReadsM, mappedBases, mappedMismatchesN, mappedInsN, mappedDelN, mappedInsL, mappedDelL,
+                              splicesN[0], splicesN[1], splicesN[2], splicesN[3], splicesN[4], splicesN[5], splicesN[6], splicesNsjdb,
+                              unmappedOther, unmappedShort, unmappedMismatch, unmappedMulti, unmappedAll, chimericAll};
+    memcpy(a, t, sizeof(t));
+}
+void Stats::fromArray(const uint64_t* a) {
+    readN = a[0]; readBases = a[1]; mappedReadsU = a[2]; mappedReadsM = a[3]; mappedBases = a[4]; mappedMismatchesN = a[5]; mappedInsN = a[6];
+    mappedDelN = a[7]; mappedInsL = a[8]; mappedDelL = a[9];
+    for (int i = 0; i < 7; i++) splicesN[i] = a[10 + i];
+    splicesNsjdb = a[17]; unmappedOther = a[18]; unmappedShort = a[19]; unmappedMismatch = a[20]; unmappedMulti = a[21]; unmappedAll = a[22]; chimericAll = a[23];
+}
+
+// ReadAlign_outputTranscriptSJ.cpp:4-56
+void OutputWriter::recordSJ(const star_align_t& tr, uint64_t nTrOut, std::vector<Junction>& sj, size_t sjReadStartN) const {
+    if (tr.nExons == 0) return;
+    for (uint32_t iex = 0; iex + 1 < tr.nExons; iex++) {
+        if (tr.canonSJ[iex] >= 0) {
+            Junction j;
+            j.start = tr.exG[iex] + tr.exL[iex];
+            j.gap = (uint32_t)(tr.exG[iex + 1] - j.start);
+            j.overhangLeft = (uint16_t)std::min((uint32_t)tr.exL[iex], (uint32_t)tr.exL[iex + 1]);
+            j.overhangRight = j.overhangLeft;
+            bool dup = false;
+            for (size_t ii = sjReadStartN; ii < sj.size(); ii++) {
+                if (j.start == sj[ii].start && j.gap == sj[ii].gap) {
+                    dup = true;
+                    if (sj[ii].overhangLeft < j.overhangLeft) { sj[ii].overhangLeft = j.overhangLeft; sj[ii].overhangRight = j.overhangLeft; }
+                    break;
+                }
+            }
+            if (dup) continue;
+            j.motif = (char)tr.canonSJ[iex];
+            j.strand = (char)(tr.canonSJ[iex] == 0 ? 0 : (tr.canonSJ[iex] + 1) % 2 + 1);
+            j.annot = (char)tr.sjAnnot[iex];
+            if (nTrOut == 1) { j.countUnique = 1; j.countMultiple = 0; } else { j.countMultiple = 1; j.countUnique = 0; }
+            sj.push_back(j);
+        }
+    }
+}
+
+// ReadAlign_outputTranscriptSAM.cpp:13-53 (unmapType>=0 branch)
+void OutputWriter::samUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* tr, int unmapType,
+                               const bool* mateMap, std::string& s) const {
+    const char* name = c.names.data() + c.nameOff[i];
+    for (unsigned imate = 0; imate < c.nMates; imate++) {
+        if (mateMap[imate]) continue;
+        unsigned flag = 0x4;
+        if (c.nMates == 2) {
+            flag |= 0x1 + (imate == 0 ? 0x40 : 0x80);
+            if (mateMap[1 - imate]) {
+                if (tr->Str != (1 - imate)) flag |= 0x20;
+            } else {
+                flag |= 0x8;
+            }
+        }
+        if (c.readFilter[i] == 'Y') flag |= 0x200;
+        if (mateMap[1 - imate] && tr && !tr->primaryFlag && P.unmappedKeepPairs) flag |= 0x100;
+        s += name; s.push_back('\t'); putU(s, flag);
+        s += "\t*\t0\t0\t*";
+        if (c.nMates == 2 && mateMap[1 - imate]) {
+            s.push_back('\t'); s += idx.chrName[tr->Chr]; s.push_back('\t'); putU(s, tr->exG[0] + 1 - idx.chrStart[tr->Chr]);
+        } else {
+            s += "\t*\t0";
+        }
+        uint64_t a = c.seqOff[(uint64_t)i * c.nMates + imate], b = c.seqOff[(uint64_t)i * c.nMates + imate + 1];
+        s += "\t0\t";
+        s.append(c.seq, a, b - a);
+        s.push_back('\t');
+        if (c.fastq) s.append(c.qual, a, b - a); else s.push_back('*');
+        s += "\tNH:i:0\tHI:i:0\tAS:i:"; putI(s, tr ? tr->maxScore : r.bestScore);
+        s += "\tnM:i:"; putU(s, tr ? tr->nMM : r.bestNMM);
+        s += "\tuT:A:"; putI(s, unmapType);
+        if (!P.outSAMattrRG.empty()) { s += "\tRG:Z:"; s += P.outSAMattrRG; }
+        s.push_back('\n');
+    }
+}
+
+// ReadAlign_outputTranscriptSAM.cpp:56-359 (mapped branch)
+void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
+                             std::string& s) const {
+    const char* name = c.names.data() + c.nameOff[i];
+    const bool flagPaired = c.nMates == 2;
+    const uint64_t Lread = r.Lread;
+    uint64_t readLength[2];
+    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
+    readLength[1] = flagPaired ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    uint32_t iExMate;
+    unsigned nMates = 1;
+    for (iExMate = 0; iExMate + 1 < tr.nExons; iExMate++) {
+        if (tr.canonSJ[iExMate] == -3) { nMates = 2; break; }
+    }
+    unsigned samFlagCommon = 0;
+    if (flagPaired) {
+        samFlagCommon = 0x0001;
+        if (iExMate == tr.nExons - 1) {
+            samFlagCommon += 0x0008;  // mateChr == (uint)-1 > nChrReal
+        } else {
+            if (P.hp.alignEndsProtrudeConcordantPair ||
+                ((tr.exG[0] <= tr.exG[iExMate + 1] + tr.exR[0]) &&
+                 (tr.exG[iExMate] + tr.exL[iExMate] <= tr.exG[tr.nExons - 1] + Lread - tr.exR[tr.nExons - 1]))) {
+                samFlagCommon += 0x0002;
+            }
+        }
+    }
+    if (c.readFilter[i] == 'Y') samFlagCommon += 0x200;
+    const unsigned Str = tr.Str;
+    unsigned leftMate = flagPaired ? Str : 0;
+
+    std::string cigars[2], sjMotif[2], sjIntron[2];
+    unsigned mateOf[2] = {0, 0};
+    uint32_t ex1[2], ex2[2];
+    for (unsigned imate = 0; imate < nMates; imate++) {  // also ReadAlign_calcCIGAR.cpp:3-60 (MC needs both CIGARs first)
+        uint32_t iEx1 = (imate == 0 ? 0 : iExMate + 1);
+        uint32_t iEx2 = (imate == 0 ? iExMate : tr.nExons - 1);
+        ex1[imate] = iEx1; ex2[imate] = iEx2;
+        unsigned Mate = tr.exFrag[iEx1];
+        mateOf[imate] = Mate;
+        std::string& cg = cigars[imate];
+        uint64_t trimL1 = (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
+        if (trimL1 > 0) { putU(cg, trimL1); cg.push_back('S'); }
+        for (uint32_t ii = iEx1; ii <= iEx2; ii++) {
+            if (ii > iEx1) {
+                uint64_t gapG = tr.exG[ii] - (tr.exG[ii - 1] + tr.exL[ii - 1]);
+                uint64_t gapR = (uint64_t)tr.exR[ii] - tr.exR[ii - 1] - tr.exL[ii - 1];
+                if (gapR > 0) { putU(cg, gapR); cg.push_back('I'); }
+                if (tr.canonSJ[ii - 1] >= 0 || tr.sjAnnot[ii - 1] == 1) {
+                    putU(cg, gapG); cg.push_back('N');
+                    sjMotif[imate].push_back(','); putI(sjMotif[imate], tr.canonSJ[ii - 1] + (tr.sjAnnot[ii - 1] == 0 ? 0 : 20));
+                    sjIntron[imate].push_back(','); putU(sjIntron[imate], tr.exG[ii - 1] + tr.exL[ii - 1] + 1 - idx.chrStart[tr.Chr]);
+                    sjIntron[imate].push_back(','); putU(sjIntron[imate], tr.exG[ii] - idx.chrStart[tr.Chr]);
+                } else if (gapG > 0) {
+                    putU(cg, gapG); cg.push_back('D');
+                }
+            }
+            putU(cg, tr.exL[ii]); cg.push_back('M');
+        }
+        if (sjMotif[imate].empty()) { sjMotif[imate] = ",-1"; sjIntron[imate] = ",-1"; }
+        uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLength[leftMate] : readLength[leftMate] + 1 + readLength[Mate]) - tr.exR[iEx2] - tr.exL[iEx2];
+        if (trimR1 > 0) { putU(cg, trimR1); cg.push_back('S'); }
+    }
+
+    std::string rc;
+    for (unsigned imate = 0; imate < nMates; imate++) {
+        unsigned samFLAG = samFlagCommon;
+        uint32_t iEx1 = ex1[imate], iEx2 = ex2[imate];
+        unsigned Mate = mateOf[imate];
+        if (Mate == 0) {
+            samFLAG |= Str * 0x10;
+            if (nMates == 2) samFLAG |= (1 - Str) * 0x20;
+        } else {
+            samFLAG |= (1 - Str) * 0x10;
+            if (nMates == 2) samFLAG |= Str * 0x20;
+        }
+        if (flagPaired) samFLAG |= (Mate == 0 ? 0x0040 : 0x0080);
+        if (!tr.primaryFlag) samFLAG |= 0x100;
+        int MAPQ = P.outSAMmapqUnique;
+        if (nTrOut >= 5) MAPQ = 0; else if (nTrOut >= 3) MAPQ = 1; else if (nTrOut == 2) MAPQ = 3;
+        s += name; s.push_back('\t'); putU(s, (samFLAG & P.outSAMflagAND) | P.outSAMflagOR); s.push_back('\t');
+        s += idx.chrName[tr.Chr]; s.push_back('\t'); putU(s, tr.exG[iEx1] + 1 - idx.chrStart[tr.Chr]); s.push_back('\t');
+        putI(s, MAPQ); s.push_back('\t'); s += cigars[imate];
+        if (nMates > 1) {
+            s += "\t=\t"; putU(s, tr.exG[(imate == 0 ? iExMate + 1 : 0)] + 1 - idx.chrStart[tr.Chr]);
+            s.push_back('\t'); if (imate != 0) s.push_back('-');
+            putU(s, tr.exG[tr.nExons - 1] + tr.exL[tr.nExons - 1] - tr.exG[0]);
+        } else {
+            s += "\t*\t0\t0";
+        }
+        uint64_t a = c.seqOff[(uint64_t)i * c.nMates + Mate], b = c.seqOff[(uint64_t)i * c.nMates + Mate + 1];
+        s.push_back('\t');
+        if (Mate == Str) {
+            s.append(c.seq, a, b - a);
+        } else {
+            revComplement(c.seq.data() + a, b - a, rc);
+            s += rc;
+        }
+        s.push_back('\t');
+        if (c.fastq && P.outSAMmode != "NoQS") {
+            if (Mate == Str) s.append(c.qual, a, b - a);
+            else for (uint64_t k = 0; k < b - a; k++) s.push_back(c.qual[b - 1 - k]);
+        } else {
+            s.push_back('*');
+        }
+        uint64_t tagNM = 0;
+        std::string tagMD;
+        bool needNM = false;
+        for (int code : P.outSAMattrOrder) if (code == ATTR_NM || code == ATTR_MD) needNM = true;
+        if (needNM) {  // :252-288; R = Read1[roStr==0?0:2], built here from the original mates
+            std::string R(Lread, (char)4);
+            auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
+            uint64_t a0 = c.seqOff[(uint64_t)i * c.nMates], a1 = c.seqOff[(uint64_t)i * c.nMates + 1];
+            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[a0 + k]);
+            if (flagPaired) {
+                R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
+                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[a1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+            }
+            if (tr.roStr != 0) {
+                std::string R2(Lread, (char)4);
+                for (uint64_t k = 0; k < Lread; k++) { char ch = R[k]; R2[Lread - 1 - k] = ch < 4 ? 3 - ch : ch; }
+                R.swap(R2);
+            }
+            static const char numToNT[6] = {'A', 'C', 'G', 'T', 'N', 'N'};
+            uint64_t matchN = 0;
+            for (uint32_t iex = iEx1; iex <= iEx2; iex++) {
+                for (uint64_t ii = 0; ii < tr.exL[iex]; ii++) {
+                    char r1 = R[ii + tr.exR[iex]];
+                    char g1 = (char)idx.view.G[ii + tr.exG[iex]];
+                    if (r1 != g1 || r1 == 4 || g1 == 4) {
+                        ++tagNM;
+                        tagMD += std::to_string(matchN);
+                        tagMD.push_back(numToNT[(uint8_t)g1 < 6 ? (uint8_t)g1 : 5]);
+                        matchN = 0;
+                    } else {
+                        matchN++;
+                    }
+                }
+                if (iex < iEx2) {
+                    if (tr.canonSJ[iex] == -1) {
+                        tagNM += tr.exG[iex + 1] - (tr.exG[iex] + tr.exL[iex]);
+                        tagMD += std::to_string(matchN) + "^";
+                        for (uint64_t ii = tr.exG[iex] + tr.exL[iex]; ii < tr.exG[iex + 1]; ii++) tagMD.push_back(numToNT[idx.view.G[ii] < 6 ? idx.view.G[ii] : 5]);
+                        matchN = 0;
+                    } else if (tr.canonSJ[iex] == -2) {
+                        tagNM += (uint64_t)tr.exR[iex + 1] - tr.exR[iex] - tr.exL[iex];
+                    }
+                }
+            }
+            tagMD += std::to_string(matchN);
+        }
+        for (int code : P.outSAMattrOrder) {
+            switch (code) {
+                case ATTR_NH: s += "\tNH:i:"; putU(s, nTrOut); break;
+                case ATTR_HI: s += "\tHI:i:"; putU(s, iTrOut + P.outSAMattrIHstart); break;
+                case ATTR_AS: s += "\tAS:i:"; putI(s, tr.maxScore); break;
+                case ATTR_nM: s += "\tnM:i:"; putU(s, tr.nMM); break;
+                case ATTR_jM: s += "\tjM:B:c"; s += sjMotif[imate]; break;
+                case ATTR_jI: s += "\tjI:B:i"; s += sjIntron[imate]; break;
+                case ATTR_XS:
+                    if (tr.sjMotifStrand == 1) s += "\tXS:A:+";
+                    else if (tr.sjMotifStrand == 2) s += "\tXS:A:-";
+                    break;
+                case ATTR_NM: s += "\tNM:i:"; putU(s, tagNM); break;
+                case ATTR_MD: s += "\tMD:Z:"; s += tagMD; break;
+                case ATTR_RG: s += "\tRG:Z:"; s += P.outSAMattrRG; break;
+                case ATTR_MC: if (nMates > 1) { s += "\tMC:Z:"; s += cigars[1 - imate]; } break;
+                default: break;  // ch: BAM-only
+            }
+        }
+        s.push_back('\n');
+    }
+}
+
+// ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
+void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
+                               std::vector<Junction>& sj, Stats& st) const {
+    const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    for (uint32_t i = lo; i < hi; i++) {
+        const star_read_result_t& r = out.reads[i];
+        uint64_t L0 = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
+        uint64_t L1 = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+        st.readN++;
+        st.readBases += L0 + L1;
+        int unmapType = r.unmapType;
+        switch (unmapType) { case 0: st.unmappedOther++; break; case 1: st.unmappedShort++; break; case 2: st.unmappedMismatch++; break; case 3: st.unmappedMulti++; break; default: break; }
+        const star_align_t* trs = out.aligns + r.trOffset;
+        if (unmapType < 0) {
+            uint64_t nTr = r.nTrOut;
+            if (nTr > 1) {
+                st.mappedReadsM++;
+            } else if (nTr == 1) {
+                st.mappedReadsU++;
+                const star_align_t& T = trs[0];  // Stats::transcriptStats Stats.cpp:35-56
+                st.mappedMismatchesN += T.nMM; st.mappedInsN += T.nIns; st.mappedDelN += T.nDel; st.mappedInsL += T.lIns; st.mappedDelL += T.lDel;
+                if (T.nExons > 0) {
+                    uint64_t mappedL = 0;
+                    for (uint32_t ii = 0; ii < T.nExons; ii++) mappedL += T.exL[ii];
+                    for (uint32_t ii = 0; ii + 1 < T.nExons; ii++) {
+                        if (T.canonSJ[ii] >= 0) st.splicesN[T.canonSJ[ii]]++;
+                        if (T.sjAnnot[ii] == 1) st.splicesNsjdb++;
+                    }
+                    st.mappedBases += mappedL;
+                }
+            }
+            if (P.outSJyes && (P.outSJfilterReads == "All" || nTr == 1)) {  // recordSJ :76-87
+                size_t sjReadStartN = sj.size();
+                for (uint64_t k = 0; k < nTr; k++) recordSJ(trs[k], nTr, sj, sjReadStartN);
+            }
+            // writeSAM :133-230
+            bool mateMapped[2] = {false, false};
+            uint64_t nWrite = std::min<uint64_t>(P.hp.outSAMmultNmax, nTr);
+            for (uint64_t k = 0; k < nWrite; k++) {
+                bool mm1[2] = {false, false};
+                mm1[trs[k].exFrag[0]] = true;
+                mm1[trs[k].exFrag[trs[k].nExons - 1]] = true;
+                if (samYes) {
+                    samMapped(c, i, r, trs[k], nTr, k, sam);
+                    if (P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) samUnmapped(c, i, r, &trs[k], 4, mm1, sam);
+                }
+            }
+            const star_align_t& best = trs[r.bestTr];
+            mateMapped[best.exFrag[0]] = true;
+            mateMapped[best.exFrag[best.nExons - 1]] = true;
+            if (c.nMates > 1 && !(mateMapped[0] && mateMapped[1])) unmapType = 4;
+            if (unmapType == 4 && P.unmappedWithin && samYes && !P.unmappedKeepPairs) samUnmapped(c, i, r, &best, 4, mateMapped, sam);
+        } else if (P.unmappedWithin && samYes) {
+            bool mateMapped[2] = {false, false};
+            samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
+        }
+        if (unmapType >= 0) st.unmappedAll++;
+    }
+}
+
+std::string OutputWriter::samHeader() const {  // samHeaders.cpp:27-113
+    std::ostringstream h;
+    h << "@HD\tVN:1.4\n";
+    for (size_t ii = 0; ii < idx.chrName.size(); ii++) h << "@SQ\tSN:" << idx.chrName[ii] << "\tLN:" << idx.chrLength[ii] << "\n";
+    h << "@PG\tID:STAR\tPN:STAR\tVN:2.7.11b\tCL:" << P.commandLineFull << "\n";
+    if (P.outSAMattrRGline[0] != "-") {
+        h << "@RG";
+        for (auto& w : P.outSAMattrRGline) h << "\t" << w;
+        h << "\n";
+    }
+    h << "@CO\tuser command line: " << P.commandLine << "\n";
+    return h.str();
+}
+
+void OutputWriter::collapseSJ(std::vector<Junction>& v, std::string& err) {  // OutSJ.cpp:34-62,89-125
+    if (v.empty()) return;
+    std::sort(v.begin(), v.end(), [](const Junction& a, const Junction& b) { return a.start != b.start ? a.start < b.start : a.gap < b.gap; });
+    size_t k = 0;
+    for (size_t i = 1; i < v.size(); i++) {
+        if (v[i].start == v[k].start && v[i].gap == v[k].gap) {
+            v[k].countUnique += v[i].countUnique;
+            v[k].countMultiple += v[i].countMultiple;
+            if (v[k].overhangLeft < v[i].overhangLeft) v[k].overhangLeft = v[i].overhangLeft;
+            if (v[k].overhangRight < v[i].overhangRight) v[k].overhangRight = v[i].overhangRight;
+            if (v[k].motif != v[i].motif) err = "EXITING because of BUG: different motifs for the same junction while collapsing junctions\n";
+            if (v[k].annot < v[i].annot) err = "EXITING because  of BUG: different annotation status for the same junction while collapsing junctions:\n";
+        } else {
+            v[++k] = v[i];
+        }
+    }
+    v.resize(k + 1);
+}
+
+std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string& path) const {  // outputSJ.cpp:20-165
+    std::string err;
+    collapseSJ(all, err);
+    if (!err.empty()) return err;
+    std::vector<Junction> kept;
+    for (auto& j : all) {
+        int mi = (j.motif + 1) / 2;
+        uint32_t tot = j.countMultiple + j.countUnique;
+        bool f = j.annot > 0 ||
+                 ((j.countUnique >= (uint32_t)P.outSJfilterCountUniqueMin[mi] || tot >= (uint32_t)P.outSJfilterCountTotalMin[mi]) &&
+                  j.overhangLeft >= (uint32_t)P.outSJfilterOverhangMin[mi] && j.overhangRight >= (uint32_t)P.outSJfilterOverhangMin[mi] &&
+                  (tot > P.outSJfilterIntronMaxVsReadN.size() || j.gap <= (uint32_t)P.outSJfilterIntronMaxVsReadN[tot - 1]));
+        if (f) kept.push_back(j);
+    }
+    size_t N = kept.size();
+    std::vector<char> sjFilter(N, 0);
+    std::vector<uint64_t> sjA(N * 3);
+    for (size_t ii = 0; ii < N; ii++) {
+        uint64_t x1 = 0, x2 = (uint64_t)-1;
+        if (ii > 0) x1 = kept[ii - 1].start;
+        if (ii + 1 < N) x2 = kept[ii + 1].start;
+        uint64_t minDist = std::min(kept[ii].start - x1, x2 - kept[ii].start);
+        sjFilter[ii] = minDist >= (uint64_t)P.outSJfilterDistToOtherSJmin[(kept[ii].motif + 1) / 2];
+        sjA[ii * 3] = kept[ii].start + (uint64_t)kept[ii].gap;
+        sjA[ii * 3 + 1] = ii;
+        sjA[ii * 3 + 2] = kept[ii].annot == 0 ? (uint64_t)kept[ii].motif : STAR_SJ_MOTIF_SIZE + 1;
+    }
+    std::vector<size_t> ord(N);
+    for (size_t i = 0; i < N; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return sjA[a * 3] < sjA[b * 3]; });
+    for (size_t oi = 0; oi < N; oi++) {
+        size_t ii = ord[oi];
+        if (sjA[ii * 3 + 2] == STAR_SJ_MOTIF_SIZE + 1) {
+            sjFilter[sjA[ii * 3 + 1]] = 1;
+        } else {
+            uint64_t x1 = 0, x2 = (uint64_t)-1;
+            if (oi > 0) x1 = sjA[ord[oi - 1] * 3];
+            if (oi + 1 < N) x2 = sjA[ord[oi + 1] * 3];
+            uint64_t minDist = std::min(sjA[ii * 3] - x1, x2 - sjA[ii * 3]);
+            sjFilter[sjA[ii * 3 + 1]] = sjFilter[sjA[ii * 3 + 1]] && (minDist >= (uint64_t)P.outSJfilterDistToOtherSJmin[(sjA[ii * 3 + 2] + 1) / 2]);
+        }
+    }
+    std::string txt;
+    for (size_t ii = 0; ii < N; ii++) {
+        if (!sjFilter[ii]) continue;
+        const Junction& j = kept[ii];  // Junction::outputStream OutSJ.cpp:85-90
+        uint64_t sjChr = idx.chrBin[j.start >> idx.view.gChrBinNbits];
+        txt += idx.chrName.at(sjChr); txt.push_back('\t'); putU(txt, j.start + 1 - idx.chrStart[sjChr]); txt.push_back('\t');
+        putU(txt, j.start + j.gap - idx.chrStart[sjChr]); txt.push_back('\t'); putI(txt, (int)j.strand); txt.push_back('\t'); putI(txt, (int)j.motif);
+        txt.push_back('\t'); putI(txt, (int)j.annot); txt.push_back('\t'); putU(txt, j.countUnique); txt.push_back('\t'); putU(txt, j.countMultiple);
+        txt.push_back('\t'); putU(txt, j.overhangLeft); txt.push_back('\n');
+    }
+    std::ofstream o(path);
+    o << txt;
+    return std::string();
+}
+
+static std::string timeMonthDayTime(time_t t) {  // TimeFunctions.cpp:14-20
+    char b[100];
+    strftime(b, 80, "%b %d %H:%M:%S", localtime(&t));
+    return b;
+}
+
+void OutputWriter::writeLogFinal(const Stats& s, const std::string& path) const {  // Stats.cpp:99-145
+    std::ofstream o(path);
+    const int w1 = 50;
+    auto pct = [&](uint64_t a) { return s.readN > 0 ? double(a) / double(s.readN) * 100 : 0.0; };
+    double dt = difftime(s.timeFinish, s.timeStartMap);
+    o << std::setiosflags(std::ios::fixed) << std::setprecision(2)
+      << std::setw(w1) << "Started job on |\t" << timeMonthDayTime(s.timeStart) << "\n"
+      << std::setw(w1) << "Started mapping on |\t" << timeMonthDayTime(s.timeStartMap) << "\n"
+      << std::setw(w1) << "Finished on |\t" << timeMonthDayTime(s.timeFinish) << "\n"
+      << std::setw(w1) << "Mapping speed, Million of reads per hour |\t" << double(s.readN) / 1e6 / dt * 3600 << "\n"
+      << "\n"
+      << std::setw(w1) << "Number of input reads |\t" << s.readN << "\n"
+      << std::setw(w1) << "Average input read length |\t" << (s.readN > 0 ? s.readBases / s.readN : 0) << "\n"
+      << std::setw(w1) << "UNIQUE READS:\n"
+      << std::setw(w1) << "Uniquely mapped reads number |\t" << s.mappedReadsU << "\n"
+      << std::setw(w1) << "Uniquely mapped reads % |\t" << pct(s.mappedReadsU) << '%' << "\n"
+      << std::setw(w1) << "Average mapped length |\t" << (s.mappedReadsU > 0 ? double(s.mappedBases) / double(s.mappedReadsU) : 0) << "\n";
+    o << std::setw(w1) << "Number of splices: Total |\t" << s.splicesN[0] + s.splicesN[1] + s.splicesN[2] + s.splicesN[3] + s.splicesN[4] + s.splicesN[5] + s.splicesN[6] << "\n"
+      << std::setw(w1) << "Number of splices: Annotated (sjdb) |\t" << s.splicesNsjdb << "\n"
+      << std::setw(w1) << "Number of splices: GT/AG |\t" << s.splicesN[1] + s.splicesN[2] << "\n"
+      << std::setw(w1) << "Number of splices: GC/AG |\t" << s.splicesN[3] + s.splicesN[4] << "\n"
+      << std::setw(w1) << "Number of splices: AT/AC |\t" << s.splicesN[5] + s.splicesN[6] << "\n"
+      << std::setw(w1) << "Number of splices: Non-canonical |\t" << s.splicesN[0] << "\n";
+    o << std::setw(w1) << "Mismatch rate per base, % |\t" << double(s.mappedMismatchesN) / double(s.mappedBases) * 100 << '%' << "\n"
+      << std::setw(w1) << "Deletion rate per base |\t" << (s.mappedBases > 0 ? double(s.mappedDelL) / double(s.mappedBases) * 100 : 0) << '%' << "\n"
+      << std::setw(w1) << "Deletion average length |\t" << (s.mappedDelN > 0 ? double(s.mappedDelL) / double(s.mappedDelN) : 0) << "\n"
+      << std::setw(w1) << "Insertion rate per base |\t" << (s.mappedBases > 0 ? double(s.mappedInsL) / double(s.mappedBases) * 100 : 0) << '%' << "\n"
+      << std::setw(w1) << "Insertion average length |\t" << (s.mappedInsN > 0 ? double(s.mappedInsL) / double(s.mappedInsN) : 0) << "\n"
+      << std::setw(w1) << "MULTI-MAPPING READS:\n"
+      << std::setw(w1) << "Number of reads mapped to multiple loci |\t" << s.mappedReadsM << "\n"
+      << std::setw(w1) << "% of reads mapped to multiple loci |\t" << pct(s.mappedReadsM) << '%' << "\n"
+      << std::setw(w1) << "Number of reads mapped to too many loci |\t" << s.unmappedMulti << "\n"
+      << std::setw(w1) << "% of reads mapped to too many loci |\t" << pct(s.unmappedMulti) << '%' << "\n"
+      << std::setw(w1) << "UNMAPPED READS:\n"
+      << std::setw(w1) << "Number of reads unmapped: too many mismatches |\t" << s.unmappedMismatch << "\n"
+      << std::setw(w1) << "% of reads unmapped: too many mismatches |\t" << pct(s.unmappedMismatch) << '%' << "\n"
+      << std::setw(w1) << "Number of reads unmapped: too short |\t" << s.unmappedShort << "\n"
+      << std::setw(w1) << "% of reads unmapped: too short |\t" << pct(s.unmappedShort) << '%' << "\n"
+      << std::setw(w1) << "Number of reads unmapped: other |\t" << s.unmappedOther << "\n"
+      << std::setw(w1) << "% of reads unmapped: other |\t" << pct(s.unmappedOther) << '%' << "\n"
+      << std::setw(w1) << "CHIMERIC READS:\n"
+      << std::setw(w1) << "Number of chimeric reads |\t" << s.chimericAll << "\n"
+      << std::setw(w1) << "% of chimeric reads |\t" << pct(s.chimericAll) << '%' << "\n"
+      << std::flush;
+}
+
+}  // namespace starhost

@@ -1,0 +1,358 @@
+// params.cpp — command-line parameters of the drop-in CLI.
+//
+// Mirrors the reference's parameter machinery for the subset the alignment path uses
+// (reference source/Parameters.cpp:19-305 registry, :310-470 input levels, :944-1124 derived values,
+// defaults from source/parametersDefault).  Every other STAR parameter is recognised by name and
+// rejected with a clear message when given: config breadth is outside the hot-path scope.
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <sstream>
+
+#include "host.h"
+
+namespace starhost {
+
+void paramsDefault(star_params_t* p) {  // source/parametersDefault
+    memset(p, 0, sizeof(*p));
+    p->seedSearchStartLmax = 50;
+    p->seedSearchStartLmaxOverLread = 1.0;
+    p->seedSearchLmax = 0;
+    p->seedMapMin = 5;
+    p->seedSplitMin = 12;
+    p->seedMultimapNmax = 10000;
+    p->seedPerReadNmax = 1000;
+    p->seedPerWindowNmax = 50;
+    p->maxNsplit = 10;  // Parameters.cpp:473
+    p->winAnchorMultimapNmax = 50;
+    p->winBinNbits = 16;
+    p->winAnchorDistNbins = 9;
+    p->winFlankNbins = 4;
+    p->alignWindowsPerReadNmax = 10000;
+    p->alignTranscriptsPerWindowNmax = 100;
+    p->alignTranscriptsPerReadNmax = 10000;
+    p->alignIntronMin = 21;
+    p->alignIntronMax = 0;
+    p->alignMatesGapMax = 0;
+    p->alignSJoverhangMin = 5;
+    p->alignSJDBoverhangMin = 3;
+    p->alignSJstitchMismatchNmax[0] = 0; p->alignSJstitchMismatchNmax[1] = -1; p->alignSJstitchMismatchNmax[2] = 0; p->alignSJstitchMismatchNmax[3] = 0;
+    p->alignSplicedMateMapLmin = 0;
+    p->alignSplicedMateMapLminOverLmate = 0.66;
+    p->alignEndsProtrudeNbasesMax = 0;
+    p->alignEndsProtrudeConcordantPair = 0;
+    p->alignSoftClipAtReferenceEnds = 1;
+    p->alignInsertionFlushRight = 0;
+    p->scoreGap = 0; p->scoreGapNoncan = -8; p->scoreGapGCAG = -4; p->scoreGapATAC = -8;
+    p->scoreGenomicLengthLog2scale = -0.25;
+    p->scoreDelOpen = -2; p->scoreDelBase = -2; p->scoreInsOpen = -2; p->scoreInsBase = -2; p->scoreStitchSJshift = 1;
+    p->sjdbScore = 2;
+    p->outFilterMismatchNmax = 10;
+    p->outFilterMismatchNoverLmax = 0.3;
+    p->outFilterMismatchNoverReadLmax = 1.0;
+    p->outFilterMultimapScoreRange = 1;
+    p->outFilterMultimapNmax = 10;
+    p->outFilterScoreMin = 0;
+    p->outFilterScoreMinOverLread = 0.66;
+    p->outFilterMatchNmin = 0;
+    p->outFilterMatchNminOverLread = 0.66;
+    p->outFilterIntronMotifs = 0;
+    p->outFilterIntronStrandsRemoveInconsistent = 1;
+    p->outSAMstrandFieldType = 0;
+    p->outSAMprimaryFlagAllBestScore = 0;
+    p->outSAMmultNmax = (uint64_t)-1;
+}
+
+namespace {
+
+typedef std::vector<std::string> Vals;
+struct Setter {
+    std::function<bool(const Vals&)> fn;
+};
+
+template <class T>
+bool parseNum(const std::string& s, T& out) {
+    std::istringstream is(s);
+    is >> out;
+    return !is.fail() && is.eof();
+}
+// the reference reads unsigned parameters through operator>> which accepts "-1" as 2^64-1
+bool parseU64(const std::string& s, uint64_t& out) {
+    if (!s.empty() && s[0] == '-') { long long v; if (!parseNum(s, v)) return false; out = (uint64_t)v; return true; }
+    return parseNum(s, out);
+}
+
+// STAR parameters that exist in the reference but belong to subsystems outside the hot path
+const char* kUnsupported[] = {
+    "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeFastaFiles", "genomeChainFiles", "genomeFileSizes",
+    "genomeTransformOutput", "genomeChrSetMitochondrial", "genomeChrBinNbits", "genomeSAindexNbases", "genomeSAsparseD",
+    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType", "sjdbFileChrStartEnd", "sjdbGTFfile",
+    "sjdbGTFchrPrefix", "sjdbGTFfeatureExon", "sjdbGTFtagExonParentTranscript", "sjdbGTFtagExonParentGene",
+    "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "sjdbInsertSave", "varVCFfile", "readFilesType",
+    "readFilesSAMattrKeep", "readFilesManifest", "readFilesPrefix", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
+    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitGenomeGenerateRAM", "limitIObufferSize",
+    "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitSjdbInsertNsj", "limitNreadsSoft",
+    "outTmpDir", "outTmpKeep", "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
+    "outSAMfilter", "outSAMtlen", "outBAMcompression", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
+    "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
+    "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
+    "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
+    "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", "quantMode",
+    "quantTranscriptomeBAMcompression", "quantTranscriptomeSAMoutput", "twopassMode", "twopass1readsN", "waspOutputMode", "soloType",
+    "soloCBtype", "soloCBwhitelist", "soloCBstart", "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate",
+    "soloCBposition", "soloUMIposition", "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype",
+    "soloInputSAMattrBarcodeSeq", "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup",
+    "soloUMIfiltering", "soloOutFileNames", "soloCellFilter", "soloOutFormatFeaturesGeneField3", "soloCellReadStats", "soloClusterCBfile",
+    "sjdbOverhang", "sjdbScoreX"};
+
+}  // namespace
+
+int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
+    paramsDefault(&P.hp);
+    star_params_t& h = P.hp;
+    std::map<std::string, Setter> tab;
+    auto U64 = [&](const char* name, uint64_t* dst) {
+        tab[name] = Setter{[dst](const Vals& v) { return v.size() == 1 && parseU64(v[0], *dst); }};
+    };
+    auto I32 = [&](const char* name, int32_t* dst) {
+        tab[name] = Setter{[dst](const Vals& v) { return v.size() == 1 && parseNum(v[0], *dst); }};
+    };
+    auto DBL = [&](const char* name, double* dst) {
+        tab[name] = Setter{[dst](const Vals& v) { return v.size() == 1 && parseNum(v[0], *dst); }};
+    };
+    auto STR = [&](const char* name, std::string* dst) {
+        tab[name] = Setter{[dst](const Vals& v) { if (v.size() != 1) return false; *dst = v[0]; return true; }};
+    };
+    auto VSTR = [&](const char* name, std::vector<std::string>* dst) {
+        tab[name] = Setter{[dst](const Vals& v) { if (v.empty()) return false; *dst = v; return true; }};
+    };
+    auto VI32 = [&](const char* name, std::vector<int32_t>* dst) {
+        tab[name] = Setter{[dst](const Vals& v) {
+            if (v.empty()) return false;
+            std::vector<int32_t> t(v.size());
+            for (size_t i = 0; i < v.size(); i++) if (!parseNum(v[i], t[i])) return false;
+            *dst = t;
+            return true;
+        }};
+    };
+    U64("seedSearchStartLmax", &h.seedSearchStartLmax); DBL("seedSearchStartLmaxOverLread", &h.seedSearchStartLmaxOverLread);
+    U64("seedSearchLmax", &h.seedSearchLmax); U64("seedMapMin", &h.seedMapMin); U64("seedSplitMin", &h.seedSplitMin);
+    U64("seedMultimapNmax", &h.seedMultimapNmax); U64("seedPerReadNmax", &h.seedPerReadNmax); U64("seedPerWindowNmax", &h.seedPerWindowNmax);
+    U64("winAnchorMultimapNmax", &h.winAnchorMultimapNmax); U64("winBinNbits", &h.winBinNbits); U64("winAnchorDistNbins", &h.winAnchorDistNbins);
+    U64("winFlankNbins", &h.winFlankNbins); U64("alignWindowsPerReadNmax", &h.alignWindowsPerReadNmax);
+    U64("alignTranscriptsPerWindowNmax", &h.alignTranscriptsPerWindowNmax); U64("alignTranscriptsPerReadNmax", &h.alignTranscriptsPerReadNmax);
+    U64("alignIntronMin", &h.alignIntronMin); U64("alignIntronMax", &h.alignIntronMax); U64("alignMatesGapMax", &h.alignMatesGapMax);
+    U64("alignSJoverhangMin", &h.alignSJoverhangMin); U64("alignSJDBoverhangMin", &h.alignSJDBoverhangMin);
+    U64("alignSplicedMateMapLmin", &h.alignSplicedMateMapLmin); DBL("alignSplicedMateMapLminOverLmate", &h.alignSplicedMateMapLminOverLmate);
+    tab["alignSJstitchMismatchNmax"] = Setter{[&h](const Vals& v) {
+        if (v.size() != 4) return false;
+        for (int i = 0; i < 4; i++) if (!parseNum(v[i], h.alignSJstitchMismatchNmax[i])) return false;
+        return true;
+    }};
+    I32("scoreGap", &h.scoreGap); I32("scoreGapNoncan", &h.scoreGapNoncan); I32("scoreGapGCAG", &h.scoreGapGCAG); I32("scoreGapATAC", &h.scoreGapATAC);
+    DBL("scoreGenomicLengthLog2scale", &h.scoreGenomicLengthLog2scale);
+    I32("scoreDelOpen", &h.scoreDelOpen); I32("scoreDelBase", &h.scoreDelBase); I32("scoreInsOpen", &h.scoreInsOpen); I32("scoreInsBase", &h.scoreInsBase);
+    I32("scoreStitchSJshift", &h.scoreStitchSJshift); I32("sjdbScore", &h.sjdbScore);
+    U64("outFilterMismatchNmax", &h.outFilterMismatchNmax); DBL("outFilterMismatchNoverLmax", &h.outFilterMismatchNoverLmax);
+    DBL("outFilterMismatchNoverReadLmax", &h.outFilterMismatchNoverReadLmax); I32("outFilterMultimapScoreRange", &h.outFilterMultimapScoreRange);
+    U64("outFilterMultimapNmax", &h.outFilterMultimapNmax); I32("outFilterScoreMin", &h.outFilterScoreMin);
+    DBL("outFilterScoreMinOverLread", &h.outFilterScoreMinOverLread); U64("outFilterMatchNmin", &h.outFilterMatchNmin);
+    DBL("outFilterMatchNminOverLread", &h.outFilterMatchNminOverLread); U64("outSAMmultNmax", &h.outSAMmultNmax);
+    STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn);
+    VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
+    STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outSAMorder", &P.outSAMorder);
+    STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
+    STR("outFilterType", &P.outFilterType); STR("outFilterIntronMotifs", &P.outFilterIntronMotifs); STR("outFilterIntronStrands", &P.outFilterIntronStrands);
+    VSTR("outSJtype", &P.outSJtype); STR("outSJfilterReads", &P.outSJfilterReads); VI32("outSJfilterOverhangMin", &P.outSJfilterOverhangMin);
+    VI32("outSJfilterCountUniqueMin", &P.outSJfilterCountUniqueMin); VI32("outSJfilterCountTotalMin", &P.outSJfilterCountTotalMin);
+    VI32("outSJfilterDistToOtherSJmin", &P.outSJfilterDistToOtherSJmin); VI32("outSJfilterIntronMaxVsReadN", &P.outSJfilterIntronMaxVsReadN);
+    STR("alignEndsType", &P.alignEndsType); VSTR("alignEndsProtrude", &P.alignEndsProtrude);
+    STR("alignSoftClipAtReferenceEnds", &P.alignSoftClipAtReferenceEnds); STR("alignInsertionFlush", &P.alignInsertionFlush);
+    STR("outMultimapperOrder", &P.outMultimapperOrder);
+    tab["runThreadN"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.runThreadN) && P.runThreadN > 0; }};
+    tab["readMapNumber"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.readMapNumber); }};
+    tab["outSAMattrIHstart"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMattrIHstart); }};
+    tab["outSAMmapqUnique"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMmapqUnique); }};
+    tab["outSAMflagOR"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagOR); }};
+    tab["outSAMflagAND"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagAND); }};
+    tab["gpuDevice"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuDevice); }};
+    tab["gpuChunkReads"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuChunkReads) && P.gpuChunkReads > 0; }};
+
+    // Parameters.cpp:331-365: "--name v1 v2", "--name=value"
+    std::vector<std::pair<std::string, Vals>> given;
+    P.commandLine = argc > 0 ? argv[0] : "STAR";
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        P.commandLine += " " + a;
+        if (a == "--version") { err = "version"; return -1; }
+        size_t eq = a.find('=');
+        if (a.size() > 2 && a.substr(0, 2) == "--" && eq != std::string::npos) {
+            given.push_back({a.substr(2, eq - 2), Vals{a.substr(eq + 1)}});
+        } else if (a.size() > 2 && a.substr(0, 2) == "--") {
+            given.push_back({a.substr(2), Vals{}});
+        } else {
+            if (given.empty()) { err = "EXITING: FATAL INPUT ERROR: value \"" + a + "\" given before any parameter name\n"; return STAR_EXIT_PARAMETER; }
+            given.back().second.push_back(a);
+        }
+    }
+    std::ostringstream full;
+    full << (argc > 0 ? argv[0] : "STAR");
+    for (auto& g : given) {
+        auto it = tab.find(g.first);
+        if (it == tab.end()) {
+            bool known = false;
+            for (const char* u : kUnsupported) if (g.first == u) known = true;
+            if (known)
+                err = "EXITING: FATAL INPUT ERROR: parameter --" + g.first +
+                      " belongs to a STAR subsystem that is outside the scope of star-b200 (the GPU alignment hot path); remove it\n";
+            else
+                err = "EXITING: FATAL INPUT ERROR: unrecognized parameter name \"" + g.first + "\" in input \"Command-Line\"\n" +
+                      "SOLUTION: use correct parameter name (check the manual)\n";  // Parameters.cpp:1245-1250
+            return STAR_EXIT_PARAMETER;
+        }
+        if (P.userSet.count(g.first)) {
+            err = "EXITING: FATAL INPUT ERROR: duplicate parameter \"" + g.first + "\" in input \"Command-Line\"\nSOLUTION: keep only one definition of input parameters in each input source\n";
+            return STAR_EXIT_PARAMETER;
+        }
+        if (g.second.empty()) {
+            err = "EXITING: FATAL INPUT ERROR: empty value for parameter \"" + g.first + "\" in input \"Command-Line\"\nSOLUTION: use non-empty value for this parameter\n";
+            return STAR_EXIT_PARAMETER;
+        }
+        if (!it->second.fn(g.second)) {
+            err = "EXITING: FATAL INPUT ERROR: could not parse the value of parameter \"" + g.first + "\"\n";
+            return STAR_EXIT_PARAMETER;
+        }
+        P.userSet[g.first] = 2;
+        full << "   --" << g.first;
+        for (auto& v : g.second) full << " " << v;
+    }
+    P.commandLineFull = full.str();
+    return finalizeParams(P, err);
+}
+
+int finalizeParams(HostParams& P, std::string& err) {
+    star_params_t& h = P.hp;
+    auto bad = [&](const std::string& m) { err = m; return STAR_EXIT_PARAMETER; };
+    if (P.runMode != "alignReads")
+        return bad("EXITING because of fatal input ERROR: star-b200 implements --runMode alignReads only (indices are built with the reference STAR --runMode genomeGenerate)\n");
+    if (P.genomeLoad != "NoSharedMemory")
+        return bad("EXITING because of fatal input ERROR: --genomeLoad " + P.genomeLoad + " is not supported: the index is resident in GPU HBM instead of host shared memory\n");
+    if (P.outStd != "Log") return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not supported by star-b200 (only Log)\n");
+    if (P.readFilesIn.size() > 2 || P.readFilesIn.empty() || P.readFilesIn[0] == "Read1")
+        return bad("EXITING: because of fatal input ERROR: --readFilesIn must name 1 or 2 FASTQ/FASTA files\n");
+    for (auto& f : P.readFilesIn)
+        if (f.find(',') != std::string::npos) return bad("EXITING: because of fatal input ERROR: comma-separated lists in --readFilesIn are not supported by star-b200\n");
+    P.readNmates = (unsigned)P.readFilesIn.size();
+    if (h.seedSearchLmax != 0) return bad("EXITING because of fatal PARAMETERS error: --seedSearchLmax >0 is not supported by star-b200\n");
+    if (P.outFilterType != "Normal") return bad("EXITING because of FATAL input ERROR: --outFilterType " + P.outFilterType + " is not supported by star-b200 (only Normal)\n");
+    if (P.outMultimapperOrder != "Old_2.4") return bad("EXITING because of fatal PARAMETERS error: --outMultimapperOrder " + P.outMultimapperOrder + " is not supported by star-b200 (only Old_2.4)\n");
+    // Parameters.cpp:944-955
+    if (P.outSAMstrandField == "None") h.outSAMstrandFieldType = 0;
+    else if (P.outSAMstrandField == "intronMotif") h.outSAMstrandFieldType = 1;
+    else return bad("EXITING because of fatal INPUT error: unrecognized option in outSAMstrandField=" + P.outSAMstrandField + "\nSOLUTION: use one of the allowed values of --outSAMstrandField : None or intronMotif \n");
+    // Parameters.cpp:966-989
+    memset(h.alignEndsTypeExt, 0, sizeof(h.alignEndsTypeExt));
+    if (P.alignEndsType == "EndToEnd") { h.alignEndsTypeExt[0][0] = h.alignEndsTypeExt[0][1] = h.alignEndsTypeExt[1][0] = h.alignEndsTypeExt[1][1] = 1; }
+    else if (P.alignEndsType == "Extend5pOfRead1") { h.alignEndsTypeExt[0][0] = 1; }
+    else if (P.alignEndsType == "Extend5pOfReads12") { h.alignEndsTypeExt[0][0] = 1; h.alignEndsTypeExt[1][0] = 1; }
+    else if (P.alignEndsType == "Extend3pOfRead1") { h.alignEndsTypeExt[0][1] = 1; }
+    else if (P.alignEndsType == "Local") {}
+    else return bad("EXITING because of FATAL INPUT ERROR: unknown/unimplemented value for --alignEndsType: " + P.alignEndsType + "\nSOLUTION: re-run STAR with --alignEndsType Local OR EndToEnd OR Extend5pOfRead1 OR Extend3pOfRead1\n");
+    // Parameters.cpp:1047-1060
+    for (auto& s : P.readNameSeparator) {
+        if (s == "space") P.readNameSeparatorChar.push_back(' ');
+        else if (s == "none") {}
+        else if (s.size() == 1) P.readNameSeparatorChar.push_back(s[0]);
+        else return bad("EXITING because of fatal PARAMETERS error: unrecognized value of --readNameSeparator=" + s + "\nSOLUTION: use allowed values: space OR single characters");
+    }
+    // Parameters.cpp:1062-1082
+    if (P.outSAMunmapped[0] == "None" && P.outSAMunmapped.size() == 1) {}
+    else if (P.outSAMunmapped[0] == "Within" && P.outSAMunmapped.size() == 1) { P.unmappedWithin = true; }
+    else if (P.outSAMunmapped[0] == "Within" && P.outSAMunmapped.size() > 1 && P.outSAMunmapped[1] == "KeepPairs") {
+        P.unmappedWithin = true;
+        if (P.readNmates == 2) P.unmappedKeepPairs = true;
+    } else return bad("EXITING because of fatal PARAMETERS error: unrecognized option for --outSAMunmapped\nSOLUTION: use allowed options: None OR Within OR Within KeepPairs");
+    // Parameters.cpp:1084-1097
+    {
+        int nb = 0;
+        if (!parseNum(P.alignEndsProtrude[0], nb)) return bad("EXITING because of fatal PARAMETERS error: bad --alignEndsProtrude\n");
+        h.alignEndsProtrudeNbasesMax = nb;
+        h.alignEndsProtrudeConcordantPair = 0;
+        if (nb > 0) {
+            if (P.alignEndsProtrude.size() > 1 && P.alignEndsProtrude[1] == "ConcordantPair") h.alignEndsProtrudeConcordantPair = 1;
+            else if (P.alignEndsProtrude.size() > 1 && P.alignEndsProtrude[1] == "DiscordantPair") h.alignEndsProtrudeConcordantPair = 0;
+            else return bad("EXITING because of fatal PARAMETERS error: unrecognized option in of --alignEndsProtrude\nSOLUTION: use allowed options: ConcordantPair or DiscordantPair");
+        }
+    }
+    if (P.alignInsertionFlush == "None") h.alignInsertionFlushRight = 0;
+    else if (P.alignInsertionFlush == "Right") h.alignInsertionFlushRight = 1;
+    else return bad("EXITING because of fatal PARAMETERS error: unrecognized option in of --alignInsertionFlush=" + P.alignInsertionFlush + "\nSOLUTION: use allowed options: None or Right");
+    if (P.alignSoftClipAtReferenceEnds == "Yes") h.alignSoftClipAtReferenceEnds = 1;
+    else if (P.alignSoftClipAtReferenceEnds == "No") h.alignSoftClipAtReferenceEnds = 0;
+    else return bad("EXITING because of fatal PARAMETERS error: unrecognized option in --alignSoftClipAtReferenceEnds   " + P.alignSoftClipAtReferenceEnds + "\nSOLUTION: use allowed options: Yes or No");
+    if (P.outFilterIntronMotifs == "None") h.outFilterIntronMotifs = 0;
+    else if (P.outFilterIntronMotifs == "RemoveNoncanonical") h.outFilterIntronMotifs = 1;
+    else if (P.outFilterIntronMotifs == "RemoveNoncanonicalUnannotated") h.outFilterIntronMotifs = 2;
+    else return bad("EXITING because of FATAL INPUT error: unrecognized value of --outFilterIntronMotifs=" + P.outFilterIntronMotifs + "\nSOLUTION: re-run STAR with --outFilterIntronMotifs = None -OR- RemoveNoncanonical -OR- RemoveNoncanonicalUnannotated\n");
+    h.outFilterIntronStrandsRemoveInconsistent = P.outFilterIntronStrands == "RemoveInconsistentStrands";
+    h.outSAMprimaryFlagAllBestScore = P.outSAMprimaryFlag == "AllBestScore";
+    if (P.outSAMprimaryFlag != "AllBestScore" && P.outSAMprimaryFlag != "OneBestScore")
+        return bad("EXITING because of FATAL INPUT error: unknown value for the option --outSAMprimaryFlag=" + P.outSAMprimaryFlag + "\nSOLUTION: re-run STAR with --outSAMprimaryFlag OneBestScore -OR- AllBestScore\n");
+    // output type
+    if (P.outSAMtype[0] == "None" || P.outSAMmode == "None") {}
+    else if (P.outSAMtype[0] != "SAM")
+        return bad("EXITING because of fatal input ERROR: --outSAMtype " + P.outSAMtype[0] + " is not supported yet by star-b200 (SAM or None; BAM is SURVEY.md §8f N1)\n");
+    if (P.outSAMmode != "Full" && P.outSAMmode != "NoQS" && P.outSAMmode != "None")
+        return bad("EXITING because of FATAL input ERROR: unknown value for the option --outSAMmode=" + P.outSAMmode + "\nSOLUTION: use one of the allowed values: None or Full or NoQS\n");
+    if (P.outSAMorder != "Paired")
+        return bad("EXITING because of fatal input ERROR: --outSAMorder " + P.outSAMorder + ": star-b200 always writes records in input order (the reference's --runThreadN 1 order)\n");
+    // SJ
+    if (P.outSJtype[0] == "None") P.outSJyes = false;
+    else if (P.outSJtype[0] == "Standard") P.outSJyes = true;
+    else return bad("EXITING because of FATAL input ERROR: unrecognized option in --outSJtype   " + P.outSJtype[0] + "\nSOLUTION: use one of the allowed options: --outSJtype   Standard   OR   None\n");
+    if (P.outSJfilterReads != "All" && P.outSJfilterReads != "Unique")
+        return bad("EXITING because of FATAL INPUT error: unknown value for the option --outSJfilterReads=" + P.outSJfilterReads + "\nSOLUTION: re-run STAR with --outSJfilterReads All -OR- Unique\n");
+    for (auto* v : {&P.outSJfilterOverhangMin, &P.outSJfilterCountUniqueMin, &P.outSJfilterCountTotalMin, &P.outSJfilterDistToOtherSJmin}) {
+        if (v->size() != 4) return bad("EXITING because of fatal PARAMETERS error: outSJfilter* parameters need 4 values\n");
+        for (auto& x : *v) if (x < 0) x = std::numeric_limits<int32_t>::max();  // Parameters.cpp:722-728
+    }
+    // SAM attributes: Parameters_samAttributes.cpp:47-60
+    {
+        std::vector<std::string> a;
+        if (P.outSAMattributes[0] == "None") {}
+        else if (P.outSAMattributes[0] == "All") a = {"NH", "HI", "AS", "nM", "NM", "MD", "jM", "jI", "MC", "ch"};
+        else if (P.outSAMattributes[0] == "Standard") a = {"NH", "HI", "AS", "nM"};
+        else a = P.outSAMattributes;
+        static const std::map<std::string, int> code = {{"NH", 1}, {"HI", 2}, {"AS", 3}, {"NM", 4}, {"MD", 5}, {"nM", 6}, {"jM", 7}, {"jI", 8}, {"XS", 9},
+                                                        {"RG", 10}, {"ch", 14}, {"MC", 15}};
+        for (auto& s : a) {
+            auto it = code.find(s);
+            if (it == code.end()) return bad("EXITING because of FATAL INPUT ERROR: unknown/unimplemented SAM atrribute (tag): " + s + "\nSOLUTION: star-b200 supports NH HI AS nM NM MD jM jI XS MC RG ch\n");
+            if (s == "RG" && P.outSAMattrRGline[0] == "-") continue;
+            P.outSAMattrOrder.push_back(it->second);
+        }
+        if (h.outSAMstrandFieldType == 1) {  // Parameters_samAttributes.cpp: XS added for intronMotif
+            bool has = false;
+            for (int c : P.outSAMattrOrder) if (c == 9) has = true;
+            if (!has) P.outSAMattrOrder.push_back(9);
+        }
+    }
+    if (P.outSAMattrRGline[0] != "-") {  // Parameters.cpp: outSAMattrRGline, single read group only
+        for (auto& s : P.outSAMattrRGline) if (s == ",") return bad("EXITING because of fatal input ERROR: multiple read groups are not supported by star-b200\n");
+        if (P.outSAMattrRGline[0].substr(0, 3) != "ID:") return bad("EXITING because of fatal input ERROR: the first word of a line from --outSAMattrRGline=" + P.outSAMattrRGline[0] + " does not start with ID:xxx read group identifier\nSOLUTION: re-run STAR with all lines in --outSAMattrRGline starting with ID:xxx\n");
+        P.outSAMattrRG = P.outSAMattrRGline[0].substr(3);
+        bool has = false;
+        for (int c : P.outSAMattrOrder) if (c == 10) has = true;
+        if (!has) P.outSAMattrOrder.push_back(10);
+    }
+    // geometry the sparse window map of the GPU engine relies on ("windows")
+    if (2 * h.winFlankNbins > h.winAnchorDistNbins && P.userSet.count("winFlankNbins"))
+        return bad("EXITING because of fatal PARAMETERS error: star-b200 requires 2*winFlankNbins <= winAnchorDistNbins (flanks of neighbouring windows must not overlap)\n");
+    return 0;
+}
+
+}  // namespace starhost
+
+extern "C" void star_params_default(star_params_t* p) { starhost::paramsDefault(p); }
