@@ -204,7 +204,7 @@ typedef struct star_align_batch {
 
 /* per-call timing / work counters filled by the engine (all device times from CUDA events) */
 typedef struct star_chunk_stats {
-    float ms_h2d, ms_prep, ms_seed, ms_window, ms_stitch, ms_pack, ms_d2h, ms_total;
+    float ms_h2d, ms_prep, ms_seed, ms_window /* slow-path re-run */, ms_stitch /* fast path */, ms_pack, ms_d2h, ms_total;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_kernel_launches;
     /* algorithmic work counters of the MMP search: */
@@ -237,6 +237,11 @@ int star_gpu_map_resident(star_ctx_t* ctx, star_chunk_stats_t* stats);
 /* Copies the results of the last star_gpu_map_resident to host buffers. */
 int star_gpu_download_results(star_ctx_t* ctx, star_align_batch_t* out);
 
+/* analysis helper: per-read records of the resident chunk (44 bytes each: Lread u32, readLength u16[2], nP u16, pad u16, nA, mapMarker,
+ * multNminL u32, Nsplit u16, split1_0 u16, mmTotal u32, flags u32, then 8 x u32 work counters: searches, saiWords, compareCalls,
+ * basesExamined, saEnumerated, stitchNodes, stitchLeaves, slowPath) */
+int star_gpu_debug_read_info(star_ctx_t* ctx, void* dst, uint64_t bytes);
+
 void star_gpu_destroy(star_ctx_t* ctx);
 const char* star_gpu_last_error(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
@@ -255,6 +260,11 @@ int star_index_load(const char* genomeDir, star_params_t* p, star_index_t** out)
 const star_index_view_t* star_index_get(const star_index_t* idx);
 void star_index_free(star_index_t* idx);
 const char* star_host_last_error(void);
+
+/* sizeof() of the ABI structs, so that foreign-language bindings can verify their layout:
+ * which = 0 star_params_t, 1 star_index_view_t, 2 star_read_batch_t, 3 star_align_t, 4 star_read_result_t,
+ * 5 star_align_batch_t, 6 star_chunk_stats_t */
+size_t star_abi_sizeof(int which);
 
 /* The drop-in command line: `STAR --runMode alignReads --genomeDir .. --readFilesIn ..` (reference
  * source/STAR.cpp:58-313).  Returns the process exit code. */

@@ -1186,7 +1186,7 @@ struct ReadAlign {
             bool aAnchor = (aNrep <= P.winAnchorMultimapNmax);
             for (uint ii = 0; ii < nW; ii++) nWAP[ii] = 0;
             for (uint iSA = PC(iP)[PC_SAstart]; iSA <= PC(iP)[PC_SAend]; iSA++) {
-                cnt.saEnum++;
+                if (mapMarker != STAR_MARKER_TOO_MANY_ANCHORS_PER_WINDOW) cnt.saEnum++;   // after that marker the reference's enumeration is dead work
                 uint a1 = mapGen.SA(iSA);
                 uint aStr = a1 >> mapGen.GstrandBit;
                 a1 &= mapGen.GstrandMask;

@@ -1,0 +1,498 @@
+// engine_api.cu — C-ABI of the CUDA engine (include/star_b200.h): context, HBM residency of the index,
+// per-chunk kernel pipeline, slow-path re-run of reads that exceed a fast-path cap.
+//
+// Replaces (reference): ReadAlignChunk::mapChunk + the ReadAlign::oneRead loop
+// (source/ReadAlignChunk_mapChunk.cpp:7-128, ReadAlign_oneRead.cpp:8-121) and the shared-memory genome
+// residency (Genome_genomeLoad.cpp:177-243).  There is NO CPU fallback: every entry point fails with
+// STAR_EXIT_RUNTIME when no CUDA device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dev.cuh"
+
+namespace starb {
+// kernels (seed.cu, stitch.cu)
+__global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
+__global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
+__global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
+                              star_read_result_t*, star_align_t*, WorkCounters*, u32);
+__global__ void pack_kernel(const star_read_result_t*, const u64*, const star_align_t*, u32, u32, star_align_t*);
+__global__ void scan_kernel(star_read_result_t*, u64*, u32, u64*);
+__global__ void reduce_counters_kernel(const ReadInfo*, u32, WorkCounters*);
+
+// collects the indices of reads whose ReadInfo.flags has `mask` set
+__global__ void collect_flagged_kernel(const ReadInfo* __restrict__ info, u32 nReads, u32 mask, u32* __restrict__ list, u32* __restrict__ count) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nReads && (info[i].flags & mask)) {
+        u32 k = atomicAdd(count, 1u);
+        list[k] = i;
+    }
+}
+}  // namespace starb
+
+using namespace starb;
+
+static thread_local std::string g_err;
+static unsigned long long g_launches = 0;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+            return STAR_EXIT_RUNTIME;                                                                  \
+        }                                                                                              \
+    } while (0)
+
+struct star_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    star_params_t P;
+    DevIndex ix;
+    std::vector<void*> owned;    // device allocations freed in destroy
+    u32 maxReads = 0;
+    int nSM = 0;
+    // per-chunk buffers
+    char* d_seq = nullptr; size_t seqCap = 0;
+    u64* d_seqOff = nullptr;
+    u8* d_reads = nullptr; size_t readsCap = 0;
+    ReadInfo* d_info = nullptr;
+    Piece* d_pieces = nullptr;
+    star_read_result_t* d_results = nullptr;
+    star_align_t* d_staged = nullptr;
+    star_align_t* d_aligns = nullptr;
+    u64* d_offsets = nullptr;
+    u64* d_total = nullptr;
+    u32* d_counter = nullptr;    // [0] ticket, [1] flagged count
+    u32* d_list = nullptr;
+    WorkCounters* d_wc = nullptr;
+    // fast path
+    Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
+    // slow path (allocated on first use)
+    Caps slow; u8* d_arenaSlow = nullptr; Piece* d_piecesSlow = nullptr; u32 slowLanes = 0; u32 slowBatch = 0;
+    // state of the resident chunk
+    u32 nReads = 0, nMates = 1, stride = 0, smemStride = 0;
+    u64 nAligns = 0;
+    cudaEvent_t ev[10];
+    star_chunk_stats_t last;
+};
+
+template <class T>
+static int devAlloc(star_ctx* c, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T) + 64));
+    c->owned.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T>
+static int devUpload(star_ctx* c, const T** dst, const T* src, size_t n, size_t padBytes = 64) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T) + padBytes));
+    c->owned.push_back(q);
+    CK(cudaMemset(q, 0, n * sizeof(T) + padBytes));
+    if (n) CK(cudaMemcpy(q, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)q;
+    return 0;
+}
+
+static u64 arenaSize(const Caps& c) {
+    u64 b = 0;
+    b += (u64)c.maxW * sizeof(Window);
+    b += (u64)c.maxW * c.spw * sizeof(Seed);
+    b += (u64)c.maxTr * sizeof(DevTr);
+    b += 2 * sizeof(DevTr);
+    b += (u64)(c.spw + 2) * 128;     // Frame is 128 bytes (stitch.cu)
+    b += (u64)c.maxTr * 2;
+    b += (u64)c.maxW * 2 * 2;
+    return (b + 255) & ~255ULL;
+}
+
+static u32 envU32(const char* name, u32 dflt) {
+    const char* e = getenv(name);
+    return e ? (u32)strtoul(e, nullptr, 10) : dflt;
+}
+
+extern "C" {
+
+const char* star_gpu_last_error(void) { return g_err.c_str(); }
+uint64_t star_gpu_launch_count(void) { return g_launches; }
+
+void star_gpu_destroy(star_ctx_t* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->owned) cudaFree(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, const star_params_t* params, uint32_t maxReadsPerChunk) {
+    *out = nullptr;
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0) {
+        g_err = std::string("star_b200: no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU fallback";
+        return STAR_EXIT_RUNTIME;
+    }
+    if (device < 0 || device >= nDev) { g_err = "star_b200: bad device ordinal"; return STAR_EXIT_RUNTIME; }
+    if (v->gSAsparseD != 1) { g_err = "star_b200: only genomeSAsparseD 1 indices are supported"; return STAR_EXIT_GENOME_FILES; }
+    if (v->gSAindexNbases > 18) { g_err = "star_b200: genomeSAindexNbases > 18 is not supported"; return STAR_EXIT_GENOME_FILES; }
+    if (params->seedPerWindowNmax > 1000 || params->seedPerReadNmax > 60000 || params->alignTranscriptsPerReadNmax > 60000) {
+        g_err = "star_b200: seedPerWindowNmax/seedPerReadNmax/alignTranscriptsPerReadNmax exceed the engine's 16-bit index range"; return STAR_EXIT_PARAMETER;
+    }
+    CK(cudaSetDevice(device));
+    star_ctx* c = new star_ctx;
+    memset(c->ev, 0, sizeof(c->ev));
+    c->device = device;
+    c->P = *params;
+    c->maxReads = maxReadsPerChunk;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->nSM = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+
+    // ---- index -> HBM (once) ----
+    DevIndex& ix = c->ix;
+    memset(&ix, 0, sizeof(ix));
+    {
+        const size_t PAD = 256;
+        u8* g = nullptr;
+        CK(cudaMalloc((void**)&g, v->nGenome + 2 * PAD + 64));
+        c->owned.push_back(g);
+        CK(cudaMemcpy(g, v->G - PAD, v->nGenome + 2 * PAD, cudaMemcpyHostToDevice));
+        ix.G = g + PAD;
+    }
+    ix.nGenome = v->nGenome;
+    {
+        size_t words = (v->nSAbyte + 7) / 8 + 2;
+        std::vector<u64> tmp;   // copy through a zero-padded word buffer only for the tail
+        u64* d = nullptr;
+        CK(cudaMalloc((void**)&d, words * 8));
+        c->owned.push_back(d);
+        CK(cudaMemset(d, 0, words * 8));
+        CK(cudaMemcpy(d, v->SA, v->nSAbyte, cudaMemcpyHostToDevice));
+        ix.SA = d;
+        size_t wordsI = (v->nSAibyte + 7) / 8 + 2;
+        u64* di = nullptr;
+        CK(cudaMalloc((void**)&di, wordsI * 8));
+        c->owned.push_back(di);
+        CK(cudaMemset(di, 0, wordsI * 8));
+        CK(cudaMemcpy(di, v->SAi, v->nSAibyte, cudaMemcpyHostToDevice));
+        ix.SAi = di;
+    }
+    ix.nSA = v->nSA; ix.nSAi = v->nSAi;
+    ix.GstrandBit = v->GstrandBit; ix.saBits = v->GstrandBit + 1; ix.saiBits = v->GstrandBit + 3;
+    ix.gSAindexNbases = v->gSAindexNbases; ix.gChrBinNbits = v->gChrBinNbits; ix.nChrReal = v->nChrReal;
+    ix.GstrandMask = ~(1ULL << v->GstrandBit);
+    ix.SAiMarkNmaskC = 1ULL << (v->GstrandBit + 1); ix.SAiMarkNmask = ~ix.SAiMarkNmaskC; ix.SAiMarkAbsentMaskC = 1ULL << (v->GstrandBit + 2);
+    for (u32 i = 0; i <= v->gSAindexNbases; i++) ix.genomeSAindexStart[i] = v->genomeSAindexStart[i];
+    {   // Genome::chrBinFill Genome.cpp:209-216
+        u64 nb = 1ULL << v->gChrBinNbits;
+        u64 chrBinN = v->chrStart[v->nChrReal] / nb + 1;
+        std::vector<u32> cb(chrBinN);
+        for (u64 ii = 0, ichr = 1; ii < chrBinN; ++ii) {
+            if (ii * nb >= v->chrStart[ichr]) ichr++;
+            cb[ii] = (u32)(ichr - 1);
+        }
+        if (devUpload(c, &ix.chrBin, cb.data(), chrBinN)) return STAR_EXIT_RUNTIME;
+        ix.chrBinN = chrBinN;
+    }
+    if (devUpload(c, &ix.chrStart, (const u64*)v->chrStart, v->nChrReal + 1)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.chrLength, (const u64*)v->chrLength, v->nChrReal)) return STAR_EXIT_RUNTIME;
+    ix.sjdbN = v->sjdbN; ix.sjdbOverhang = v->sjdbOverhang; ix.sjdbLength = v->sjdbLength; ix.sjGstart = v->sjGstart;
+    if (devUpload(c, &ix.sjdbStart, (const u64*)v->sjdbStart, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjdbEnd, (const u64*)v->sjdbEnd, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjDstart, (const u64*)v->sjDstart, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjAstart, (const u64*)v->sjAstart, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjdbMotif, v->sjdbMotif, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjdbShiftLeft, v->sjdbShiftLeft, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjdbShiftRight, v->sjdbShiftRight, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &ix.sjdbStrand, v->sjdbStrand, v->sjdbN)) return STAR_EXIT_RUNTIME;
+    {   // step table of int(ceil(log2((double)g)*scale-0.5)) evaluated with the HOST libm exactly as the reference writes it
+        // (stitchWindowAligns.cpp:221-225); the function is monotone in g, so change points are found by bisection.
+        std::vector<u64> thr; std::vector<int> val;
+        const double scale = params->scoreGenomicLengthLog2scale;
+        auto f = [&](u64 g) { return int(std::ceil(std::log2((double)g) * scale - 0.5)); };
+        const u64 gMax = 1ULL << 40;
+        u64 pos = 1;
+        thr.push_back(1); val.push_back(f(1));
+        while (pos < gMax && thr.size() < 4096) {
+            int cur = f(pos);
+            if (f(gMax) == cur) break;
+            u64 lo = pos, hi = pos + 1;
+            while (hi < gMax && f(hi) == cur) { lo = hi; hi = hi * 2 < gMax ? hi * 2 : gMax; }
+            if (f(hi) == cur) break;
+            while (lo + 1 < hi) { u64 mid = lo + (hi - lo) / 2; if (f(mid) == cur) lo = mid; else hi = mid; }
+            thr.push_back(hi); val.push_back(f(hi));
+            pos = hi;
+        }
+        if (devUpload(c, &ix.log2Thr, thr.data(), thr.size())) return STAR_EXIT_RUNTIME;
+        if (devUpload(c, &ix.log2Val, val.data(), val.size())) return STAR_EXIT_RUNTIME;
+        ix.log2N = (int)thr.size();
+    }
+    // ---- per-chunk buffers ----
+    const u32 N = maxReadsPerChunk;
+    const u32 nOut = (u32)(params->outFilterMultimapNmax > 0 ? params->outFilterMultimapNmax : 1);
+    c->fast.maxP = envU32("STAR_B200_FAST_MAXP", 128);
+    c->fast.maxW = envU32("STAR_B200_FAST_MAXW", 128);
+    c->fast.maxTr = envU32("STAR_B200_FAST_MAXTR", 128);
+    c->fast.spw = (u32)params->seedPerWindowNmax;
+    c->fast.nOut = nOut;
+    if (c->fast.maxP > params->seedPerReadNmax) c->fast.maxP = (u32)params->seedPerReadNmax;
+    if (c->fast.maxW > params->alignWindowsPerReadNmax) c->fast.maxW = (u32)params->alignWindowsPerReadNmax;
+    c->fast.maxW = (c->fast.maxW + 1) & ~1u;
+    if (c->fast.maxTr > params->alignTranscriptsPerReadNmax) c->fast.maxTr = (u32)params->alignTranscriptsPerReadNmax;
+    c->fast.arenaBytes = arenaSize(c->fast);
+    c->slow.maxP = (u32)params->seedPerReadNmax;
+    c->slow.maxW = ((u32)params->alignWindowsPerReadNmax + 1) & ~1u;
+    c->slow.maxTr = (u32)params->alignTranscriptsPerReadNmax;
+    c->slow.spw = c->fast.spw; c->slow.nOut = nOut;
+    c->slow.arenaBytes = arenaSize(c->slow);
+    if (devAlloc(c, &c->d_seqOff, (size_t)N * 2 + 2)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_info, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_pieces, (size_t)N * c->fast.maxP)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_results, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_staged, (size_t)N * nOut)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_aligns, (size_t)N * nOut)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_offsets, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_total, 2)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_counter, 4)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_list, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_wc, 1)) return STAR_EXIT_RUNTIME;
+    // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
+    c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 4);
+    c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
+    {
+        size_t bytes = (size_t)c->gridStitch * 128 * c->fast.arenaBytes;
+        CK(cudaMalloc((void**)&c->d_arenaFast, bytes));
+        c->owned.push_back(c->d_arenaFast);
+    }
+    CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    *out = c;
+    return 0;
+}
+
+static int ensureSeq(star_ctx* c, size_t bytes) {
+    if (bytes + 64 <= c->seqCap) return 0;
+    if (c->d_seq) cudaFree(c->d_seq);
+    c->seqCap = bytes + bytes / 4 + 4096;
+    CK(cudaMalloc((void**)&c->d_seq, c->seqCap));
+    return 0;
+}
+static int ensureReads(star_ctx* c, size_t bytes) {
+    if (bytes <= c->readsCap) return 0;
+    if (c->d_reads) cudaFree(c->d_reads);
+    c->readsCap = bytes + bytes / 4 + 4096;
+    CK(cudaMalloc((void**)&c->d_reads, c->readsCap));
+    return 0;
+}
+
+int star_gpu_upload_chunk(star_ctx_t* c, const star_read_batch_t* in) {
+    CK(cudaSetDevice(c->device));
+    if (in->nReads > c->maxReads) { g_err = "star_b200: chunk larger than maxReadsPerChunk given to star_gpu_init"; return STAR_EXIT_PARAMETER; }
+    if (in->nMates != 1 && in->nMates != 2) { g_err = "star_b200: nMates must be 1 or 2"; return STAR_EXIT_PARAMETER; }
+    c->nReads = in->nReads; c->nMates = in->nMates;
+    if (in->nReads == 0) return 0;
+    const u64 nOff = (u64)in->nReads * in->nMates + 1;
+    const u64 seqBytes = in->seqOff[nOff - 1];
+    // longest combined read decides the row stride (host scan of the offsets; lengths were validated by the reader)
+    u32 maxL = 0;
+    for (u64 i = 0; i < in->nReads; i++) {
+        const uint64_t* o = in->seqOff + i * in->nMates;
+        u64 l0 = o[1] - o[0], l1 = in->nMates == 2 ? o[2] - o[1] : 0;
+        if (l0 < 1 || (in->nMates == 2 && l1 < 1)) { g_err = "EXITING because of FATAL ERROR in reads input: short read sequence line: 0\n"; return STAR_EXIT_INPUT_FILES; }
+        u64 L = in->nMates == 2 ? l0 + l1 + 1 : l0;
+        if (L > STAR_READ_SEQ_LENGTH_MAX) { g_err = "EXITING because of FATAL ERROR in reads input: Lread of the pair exceeds DEF_readSeqLengthMax\n"; return STAR_EXIT_INPUT_FILES; }
+        if (L > maxL) maxL = (u32)L;
+    }
+    c->stride = (maxL + 16) & ~15u;
+    u32 s = (maxL + 1 + 3) & ~3u;
+    if (((s / 4) & 1) == 0) s += 4;     // odd number of 32-bit words per shared-memory row: conflict-free lane rows
+    c->smemStride = s;
+    if (ensureSeq(c, seqBytes)) return STAR_EXIT_RUNTIME;
+    if (ensureReads(c, (size_t)in->nReads * c->stride)) return STAR_EXIT_RUNTIME;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(cudaMemcpyAsync(c->d_seq, in->seq, seqBytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_seqOff, in->seqOff, nOff * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    c->last.h2d_bytes = seqBytes + nOff * 8;
+    return 0;
+}
+
+int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
+    CK(cudaSetDevice(c->device));
+    star_chunk_stats_t& st = c->last;
+    const u32 n = c->nReads;
+    c->nAligns = 0;
+    if (n == 0) { if (stats) { memset(stats, 0, sizeof(*stats)); } return 0; }
+    const unsigned long long launches0 = g_launches;
+    CK(cudaMemsetAsync(c->d_wc, 0, sizeof(WorkCounters), c->stream));
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    {
+        int grid = c->nSM * 8;
+        prep_reads_kernel<<<grid, 256, 0, c->stream>>>(c->d_seq, c->d_seqOff, n, c->nMates, c->d_reads, c->stride, c->d_info, c->P);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    const u32 smemSeed = 128 * c->smemStride;
+    const u32 smemStitch = 128 * 2 * c->smemStride;
+    if (smemStitch > 200 * 1024) { g_err = "star_b200: read too long for the shared-memory staging"; return STAR_EXIT_RUNTIME; }
+    // ---- fast path over all reads ----
+    CK(cudaMemsetAsync(c->d_counter, 0, 16, c->stream));
+    seed_search_kernel<<<c->gridSeed, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr,
+                                                                   c->d_counter, c->d_wc, c->smemStride);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaMemsetAsync(c->d_counter, 0, 16, c->stream));
+    stitch_kernel<<<c->gridStitch, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, n, nullptr, c->d_counter,
+                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_wc, c->smemStride);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[8], c->stream));
+    // ---- slow path: reads that exceeded a fast-path cap are redone with the reference's own limits ----
+    CK(cudaMemsetAsync(c->d_counter + 1, 0, 4, c->stream));
+    collect_flagged_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, 1u, c->d_list, c->d_counter + 1);
+    g_launches++;
+    u32 nSlow = 0;
+    CK(cudaMemcpyAsync(&nSlow, c->d_counter + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nSlow > 0) {
+        if (!c->d_arenaSlow) {
+            c->slowLanes = envU32("STAR_B200_SLOW_LANES", 256);
+            c->slowBatch = envU32("STAR_B200_SLOW_BATCH", 16384);
+            CK(cudaMalloc((void**)&c->d_arenaSlow, (size_t)c->slowLanes * c->slow.arenaBytes));
+            c->owned.push_back(c->d_arenaSlow);
+            CK(cudaMalloc((void**)&c->d_piecesSlow, (size_t)c->slowBatch * c->slow.maxP * sizeof(Piece)));
+            c->owned.push_back(c->d_piecesSlow);
+        }
+        // the list order is made deterministic (atomics gave an arbitrary order): sort on the host, tiny
+        std::vector<u32> list(nSlow);
+        CK(cudaMemcpy(list.data(), c->d_list, (size_t)nSlow * 4, cudaMemcpyDeviceToHost));
+        std::sort(list.begin(), list.end());
+        CK(cudaMemcpy(c->d_list, list.data(), (size_t)nSlow * 4, cudaMemcpyHostToDevice));
+        int gridSlow = (int)(c->slowLanes / 128);
+        if (gridSlow < 1) gridSlow = 1;
+        for (u32 lo = 0; lo < nSlow; lo += c->slowBatch) {
+            u32 m = nSlow - lo < c->slowBatch ? nSlow - lo : c->slowBatch;
+            CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+            seed_search_kernel<<<gridSlow, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_piecesSlow, c->slow.maxP, m,
+                                                                        c->d_list + lo, c->d_counter, c->d_wc, c->smemStride);
+            g_launches++;
+            CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+            stitch_kernel<<<gridSlow, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_piecesSlow, m, c->d_list + lo,
+                                                                     c->d_counter, c->d_arenaSlow, c->slow, c->d_results, c->d_staged, c->d_wc, c->smemStride);
+            g_launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_results, c->d_offsets, n, c->d_total);
+    pack_kernel<<<c->nSM * 8, 256, 0, c->stream>>>(c->d_results, c->d_offsets, c->d_staged, c->fast.nOut, n, c->d_aligns);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(cudaMemsetAsync(c->d_wc, 0, sizeof(WorkCounters), c->stream));
+    reduce_counters_kernel<<<c->nSM * 4, 256, 0, c->stream>>>(c->d_info, n, c->d_wc);
+    g_launches++;
+    // fatal per-read conditions (reference: exitWithError inside the read loop)
+    CK(cudaMemsetAsync(c->d_counter + 1, 0, 4, c->stream));
+    collect_flagged_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, 3u, c->d_list, c->d_counter + 1);
+    g_launches++;
+    u32 nBad = 0;
+    WorkCounters wc;
+    CK(cudaMemcpyAsync(&nBad, c->d_counter + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&wc, c->d_wc, sizeof(wc), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->nAligns, c->d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nBad > 0) {
+        std::vector<ReadInfo> inf(1);
+        u32 first = 0;
+        CK(cudaMemcpy(&first, c->d_list, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(inf.data(), c->d_info + first, sizeof(ReadInfo), cudaMemcpyDeviceToHost));
+        if (inf[0].flags & 2) {
+            g_err = "EXITING because of FATAL error: too many pieces pere read\nSOLUTION: increase input parameter --seedPerReadNmax";   // ReadAlign_storeAligns.cpp:46-51
+            return STAR_EXIT_RUNTIME;
+        }
+        g_err = "BUG: a read exceeded the slow-path capacities of star_b200";
+        return STAR_EXIT_BUG;
+    }
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); st.ms_prep = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st.ms_seed = ms;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[8]); st.ms_stitch = ms;     // fast path (all reads)
+    cudaEventElapsedTime(&ms, c->ev[8], c->ev[5]); st.ms_window = ms;     // slow path (reads redone with the reference's limits)
+    cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); st.ms_pack = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[6]); st.ms_total = ms;
+    st.n_kernel_launches = g_launches - launches0;
+    st.mmp_searches = wc.searches; st.mmp_sai_words = wc.saiWords; st.mmp_compare_calls = wc.compareCalls; st.mmp_bases_examined = wc.basesExamined;
+    st.sa_enumerated = wc.saEnum; st.stitch_nodes = wc.nodes; st.stitch_leaves = wc.leaves; st.slow_path_reads = wc.slowReads;
+    if (stats) *stats = st;
+    return 0;
+}
+
+int star_gpu_download_results(star_ctx_t* c, star_align_batch_t* out) {
+    CK(cudaSetDevice(c->device));
+    if (c->nAligns > out->alignsCapacity) { g_err = "star_b200: aligns capacity too small"; return STAR_EXIT_RUNTIME; }
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    if (c->nReads) CK(cudaMemcpyAsync(out->reads, c->d_results, (size_t)c->nReads * sizeof(star_read_result_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->nAligns) CK(cudaMemcpyAsync(out->aligns, c->d_aligns, (size_t)c->nAligns * sizeof(star_align_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out->nAligns = c->nAligns;
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]);
+    c->last.ms_d2h = ms;
+    c->last.d2h_bytes = (u64)c->nReads * sizeof(star_read_result_t) + c->nAligns * sizeof(star_align_t);
+    return 0;
+}
+
+int star_gpu_map_chunk(star_ctx_t* c, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats) {
+    memset(&c->last, 0, sizeof(c->last));
+    int rc = star_gpu_upload_chunk(c, in);
+    if (rc) return rc;
+    star_chunk_stats_t s;
+    rc = star_gpu_map_resident(c, &s);
+    if (rc) return rc;
+    float msH2D = 0;
+    if (c->nReads) cudaEventElapsedTime(&msH2D, c->ev[0], c->ev[1]);   // before ev[0] is reused by the download
+    rc = star_gpu_download_results(c, out);
+    if (rc) return rc;
+    c->last.ms_h2d = msH2D;
+    c->last.ms_total += msH2D + c->last.ms_d2h;
+    if (stats) *stats = c->last;
+    return 0;
+}
+
+// debug / analysis: copies the per-read ReadInfo records (work counters, flags) of the resident chunk
+int star_gpu_debug_read_info(star_ctx_t* c, void* dst, uint64_t bytes) {
+    CK(cudaSetDevice(c->device));
+    uint64_t need = (uint64_t)c->nReads * sizeof(ReadInfo);
+    if (bytes < need) { g_err = "star_gpu_debug_read_info: buffer too small"; return STAR_EXIT_RUNTIME; }
+    CK(cudaMemcpy(dst, c->d_info, need, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- engine vtable for the host driver; the shipped CLI binds the CUDA engine and nothing else ----
+static int vt_init(void** ctx, int device, const star_index_view_t* ix, const star_params_t* p, uint32_t maxReads) {
+    return star_gpu_init((star_ctx_t**)ctx, device, ix, p, maxReads);
+}
+static int vt_map(void* ctx, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* st) {
+    return star_gpu_map_chunk((star_ctx_t*)ctx, in, out, st);
+}
+static void vt_destroy(void* ctx) { star_gpu_destroy((star_ctx_t*)ctx); }
+static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error};
+
+int star_cli_main(int argc, char** argv) { return star_cli_main_engine(argc, argv, &g_cuda_engine); }
+
+}  // extern "C"

@@ -1,0 +1,1074 @@
+// stitch.cu — seed -> window assignment, seed stitching, end extension, multimapper selection (sm_100a).
+//
+// What is computed (bit-exact with the reference, proven by tests/ against oracle/):
+//   ReadAlign::stitchPieces                 reference source/ReadAlign_stitchPieces.cpp:12-350
+//   createExtendWindowsWithAlign            source/ReadAlign_createExtendWindowsWithAlign.cpp:7-84
+//   assignAlignToWindow, sjAlignSplit       source/ReadAlign_assignAlignToWindow.cpp:6-130, sjAlignSplit.cpp:3-15
+//   stitchWindowAligns (short-read stitcher) source/stitchWindowAligns.cpp:8-353
+//   stitchAlignToTranscript, binarySearch2   source/stitchAlignToTranscript.cpp:9-415, binarySearch2.cpp:3-43
+//   extendAlign, blocksOverlap               source/extendAlign.cpp:6-92, blocksOverlap.cpp:3-40
+//   multMapSelect, mappedFilter              source/ReadAlign_multMapSelect.cpp:8-95, ReadAlign_mappedFilter.cpp:3-20
+//
+// How (B200-first, NOT the reference's structure):
+//  * persistent lanes (one read per lane at a time, next read from an atomic ticket) with a private arena in HBM;
+//  * the dense per-read winBin[2][nGenome>>16] array (190 KB memset per read in the reference, F8) is replaced by the
+//    window interval list itself: bins owned by a window are exactly [gStart,gEnd] of a live window on that strand,
+//    so "is the bin owned / nearest owned bin within winAnchorDistNbins" are interval queries (DESIGN.md proves the
+//    equivalence, incl. the flank extension and the kill-right-window case);
+//  * the 2^n include/exclude recursion that copies a 1.7 kB Transcript per node (30 % of the reference's CPU time) is an
+//    explicit DFS over ONE shared transcript with a per-level undo record (head + last exon, 104 bytes): stitching only
+//    ever appends an exon and edits the last one.  Leaves materialise a private copy, so visiting order, dedup and
+//    tie-breaks are exactly the reference's;
+//  * log2() of the genomic-length score is an integer threshold table computed by the host libm (CUDA's log2 is not
+//    correctly rounded); every other floating-point expression is a single IEEE multiply/divide and is evaluated
+//    in fp64 as written in the reference.
+#include "dev.cuh"
+
+namespace starb {
+
+#define SJA_NONE 0xFFFFFFFFu
+
+struct Frame {
+    TrHead h;        // head before the include attempt
+    Exon last;       // ex[nExons-1] before the include attempt
+    u64 tG2;
+    u32 tR2;
+    int Score;
+    u16 iA;
+    u8 phase;
+    u8 pad;
+};
+
+static_assert(sizeof(Frame) == 128, "arenaSize() in engine_api.cu assumes 128-byte frames");
+
+struct Lane {
+    const DevIndex* ix;
+    const star_params_t* P;
+    const u8* R0;   // Read1[0] in shared memory
+    const u8* R2;   // Read1[2] (reverse complement)
+    const u8* R;    // orientation of the current window
+    u32 Lread;
+    u16 readLength[2];
+    u32 outFilterMismatchNmaxTotal;
+    int maxScoreMate[2];
+    // arena
+    Window* win;
+    Seed* wa;
+    u16* trPtr;
+    DevTr* pool;
+    u16* winBase;   // per non-empty window iW1: first index into trPtr
+    u16* winN;      // per iW1: nWinTr
+    Frame* stack;
+    DevTr* cur;
+    DevTr* leaf;
+    u32 nW;
+    Caps caps;
+    u32 overflow;
+    u64 saEnum, nodes, leaves;
+};
+
+__device__ __forceinline__ u8 Gat(const Lane& ln, u64 pos) { return __ldg(ln.ix->G + (i64)pos); }
+
+// binarySearch2.cpp:3-43
+__device__ int binarySearch2(u64 x, u64 y, const u64* __restrict__ X, const u64* __restrict__ Y, int N) {
+    if (N == 0 || x > X[N - 1] || x < X[0]) return -1;
+    int i1 = 0, i2 = N - 1, i3 = N / 2;
+    while (i2 > i1 + 1) {
+        i3 = (i1 + i2) / 2;
+        if (X[i3] > x) i2 = i3; else i1 = i3;
+    }
+    if (x == X[i1]) i3 = i1;
+    else if (x == X[i2]) i3 = i2;
+    else return -1;
+    for (int jj = i3; jj >= 0; jj--) {
+        if (x != X[jj]) break;
+        else if (y == Y[jj]) return jj;
+    }
+    for (int jj = i3; jj < N; jj++) {
+        if (x != X[jj]) return -1;
+        else if (y == Y[jj]) return jj;
+    }
+    return -2;
+}
+
+struct ExtRes { u32 extendL; int maxScore; u32 nMatch, nMM; };
+
+// extendAlign.cpp:6-92.  R/G are addressed through the lane (R orientation already selected).
+__device__ bool extendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                            bool extendToEnd, ExtRes& res) {
+    int Score = 0, nMatch = 0, nMM = 0;
+    res.maxScore = 0;
+    const u8* R = ln.R + rStart;
+    const u8* G = ln.ix->G + (i64)gStart;
+    if (extendToEnd) {
+        int iExt;
+        for (iExt = 0; iExt < (int)L; iExt++) {
+            int iS = dR * iExt, iG = dG * iExt;
+            u8 g;
+            if ((gStart + (u64)(i64)iG) == (u64)(-1LL) || (g = __ldg(G + iG)) == 5) {
+                res.extendL = 0; res.maxScore = -999999999; res.nMatch = 0; res.nMM = (u32)(nMMmax + 1);
+                return true;
+            }
+            u8 r = R[iS];
+            if (r == STAR_MARK_FRAG_SPACER_BASE) break;
+            if (r > 3 || g > 3) continue;
+            if (g == r) { nMatch++; Score += 1; } else { nMM++; Score -= 1; }
+        }
+        if (iExt > 0) {
+            res.extendL = (u32)iExt; res.maxScore = Score; res.nMatch = (u32)nMatch; res.nMM = (u32)nMM;
+            return true;
+        }
+        return false;
+    }
+    double capEnd = pMMmax * double(Lprev + L);
+    double nMMmaxD = double(nMMmax);
+    if (nMMmaxD < capEnd) capEnd = nMMmaxD;
+    for (int i = 0; i < (int)L; i++) {
+        int iS = dR * i, iG = dG * i;
+        if ((gStart + (u64)(i64)iG) == (u64)(-1LL)) break;
+        u8 g = __ldg(G + iG);
+        u8 r = R[iS];
+        if (g == 5 || r == STAR_MARK_FRAG_SPACER_BASE) break;
+        if (r > 3 || g > 3) continue;
+        if (g == r) {
+            nMatch++; Score += 1;
+            if (Score > res.maxScore) {
+                double cap = pMMmax * double(Lprev + (u64)i + 1);
+                if (nMMmaxD < cap) cap = nMMmaxD;
+                if (double((u64)nMM + nMMprev) <= cap) {
+                    res.extendL = (u32)(i + 1); res.maxScore = Score; res.nMatch = (u32)nMatch; res.nMM = (u32)nMM;
+                }
+            }
+        } else {
+            if (double((u64)nMM + nMMprev) >= capEnd) break;
+            nMM++; Score -= 1;
+        }
+    }
+    return res.extendL > 0;
+}
+
+// stitchAlignToTranscript.cpp:9-415 operating on the shared DFS transcript `t`
+__device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBstart, u64 gBstart, u64 L, u32 iFragB, u32 sjAB, DevTr* t) {
+    const star_params_t& P = *ln.P;
+    const DevIndex& g = *ln.ix;
+    TrHead& h = t->h;
+    if (h.nExons >= STAR_MAX_N_EXONS) return -1000010;
+    const u8* R = ln.R;
+    int Score = 0;
+    Exon& eA = t->ex[h.nExons - 1];
+    Exon& eB = t->ex[h.nExons];
+    const u64 outFilterMismatchNmaxTotal = ln.outFilterMismatchNmaxTotal;
+
+    if (sjAB != SJA_NONE && eA.sjA == sjAB && eA.iFrag == iFragB && rBstart == rAend + 1 && gAend + 1 < gBstart) {
+        if (g.sjdbMotif[sjAB] == 0 && (L <= g.sjdbShiftRight[sjAB] || eA.L <= g.sjdbShiftLeft[sjAB])) return -1000006;
+        eB.L = (u16)L; eB.R = (u16)rBstart; eB.G = gBstart;
+        eA.canon = (signed char)g.sjdbMotif[sjAB];
+        eA.shL = g.sjdbShiftLeft[sjAB]; eA.shR = g.sjdbShiftRight[sjAB];
+        eA.annot = 1;
+        eA.sjStr = g.sjdbStrand[sjAB];
+        h.nExons++;
+        h.nMatch += (u32)L;
+        Score += (int)L;
+        Score += P.sjdbScore;
+    } else {
+        eA.annot = 0;
+        eA.sjStr = 0;
+        if (eA.iFrag == iFragB) {
+            u64 gBend = gBstart + L - 1;
+            u64 rBend = rBstart + L - 1;
+            if (rBend <= rAend) return -1000001;
+            if (gBend <= gAend) return -1000002;
+            if (rBstart <= rAend) {
+                gBstart += rAend - rBstart + 1;
+                rBstart = rAend + 1;
+                L = rBend - rBstart + 1;
+            }
+            Score += (int)(rBend - rBstart + 1);
+            int gGap = (int)(gBstart - gAend - 1);
+            int rGap = (int)(rBstart - rAend - 1);
+            u64 nMatch = L, nMM = 0, Del = 0, Ins = 0, nIns = 0, nDel = 0;
+            int jR = 0;
+            int jCan = 999;
+            u64 gBstart1 = gBstart - rGap - 1;
+
+            if (gGap == 0 && rGap == 0) {
+            } else if (gGap > 0 && rGap > 0 && rGap == gGap) {
+                for (int ii = 1; ii <= rGap; ii++) {
+                    u8 gv = Gat(ln, gAend + ii), rv = R[rAend + ii];
+                    if (gv < 4 && rv < 4) {
+                        if (rv == gv) { Score += 1; nMatch++; } else { Score -= 1; nMM++; }
+                    }
+                }
+            } else if (gGap > rGap) {
+                nDel = 1;
+                Del = (u64)(gGap - rGap);
+                if (Del > P.alignIntronMax && P.alignIntronMax > 0) return -1000003;
+                int Score1 = 0;
+                int jR1 = 1;
+                do {
+                    jR1--;
+                    u8 rv = R[(i64)rAend + jR1], gb = Gat(ln, gBstart1 + (u64)(i64)jR1), ga = Gat(ln, gAend + (u64)(i64)jR1);
+                    if (rv != gb && gb < 4 && rv == ga) Score1 -= 1;
+                } while (Score1 + P.scoreStitchSJshift >= 0 && int(eA.L) + jR1 > 1);
+
+                int maxScore2 = -999999;
+                Score1 = 0;
+                int jPen = 0;
+                do {
+                    u8 rv = R[(i64)rAend + jR1], ga = Gat(ln, gAend + (u64)(i64)jR1), gb = Gat(ln, gBstart1 + (u64)(i64)jR1);
+                    if (rv == ga && rv != gb) Score1 += 1;
+                    if (rv != ga && rv == gb) Score1 -= 1;
+                    int jCan1 = -1, jPen1 = 0, Score2 = Score1;
+                    if (Del >= P.alignIntronMin) {
+                        u8 d1 = Gat(ln, gAend + (u64)(i64)(jR1 + 1)), d2 = Gat(ln, gAend + (u64)(i64)(jR1 + 2));
+                        u8 a1 = Gat(ln, gBstart1 + (u64)(i64)(jR1 - 1)), a2 = gb;
+                        if (d1 == 2 && d2 == 3 && a1 == 0 && a2 == 2) { jCan1 = 1; }
+                        else if (d1 == 1 && d2 == 3 && a1 == 0 && a2 == 1) { jCan1 = 2; }
+                        else if (d1 == 2 && d2 == 1 && a1 == 0 && a2 == 2) { jCan1 = 3; jPen1 = P.scoreGapGCAG; }
+                        else if (d1 == 1 && d2 == 3 && a1 == 2 && a2 == 1) { jCan1 = 4; jPen1 = P.scoreGapGCAG; }
+                        else if (d1 == 0 && d2 == 3 && a1 == 0 && a2 == 1) { jCan1 = 5; jPen1 = P.scoreGapATAC; }
+                        else if (d1 == 2 && d2 == 3 && a1 == 0 && a2 == 3) { jCan1 = 6; jPen1 = P.scoreGapATAC; }
+                        else { jCan1 = 0; jPen1 = P.scoreGapNoncan; }
+                        Score2 += jPen1;
+                    }
+                    if (maxScore2 < Score2) { maxScore2 = Score2; jR = jR1; jCan = jCan1; jPen = jPen1; }
+                    jR1++;
+                } while (jR1 < int(rBend) - int(rAend));
+
+                u64 jjL = 0, jjR = 0;
+                u64 jRu = (u64)(i64)jR;
+                while (gAend + jRu >= jjL && Gat(ln, gAend - jjL + jRu) == Gat(ln, gBstart1 - jjL + jRu) && Gat(ln, gAend - jjL + jRu) < 4 && jjL <= 255) jjL++;
+                while (gAend + jjR + jRu + 1 < g.nGenome && Gat(ln, gAend + jjR + jRu + 1) == Gat(ln, gBstart1 + jjR + jRu + 1) && Gat(ln, gAend + jjR + jRu + 1) < 4 && jjR <= 255) jjR++;
+
+                if (jCan <= 0) {
+                    jR -= (int)jjL;
+                    if (int(eA.L) + jR < 1) return -1000005;
+                    jjR += jjL;
+                    jjL = 0;
+                }
+                {
+                    int i0 = 1 < jR + 1 ? 1 : jR + 1;
+                    int i1 = rGap > jR ? rGap : jR;
+                    for (int ii = i0; ii <= i1; ii++) {
+                        u64 g1 = (ii <= jR) ? (gAend + (u64)(i64)ii) : (gBstart1 + (u64)(i64)ii);
+                        u8 gv = Gat(ln, g1), rv = R[(i64)rAend + ii];
+                        if (gv < 4 && rv < 4) {
+                            if (rv == gv) {
+                                if (ii >= 1 && ii <= rGap) { Score += 1; nMatch++; }
+                            } else {
+                                Score -= 1; nMM++;
+                                if (ii < 1 || ii > rGap) { Score -= 1; nMatch--; }
+                            }
+                        }
+                    }
+                }
+                bool annotated = false;
+                if (g.sjdbN > 0) {
+                    u64 jS = gAend + (u64)(i64)jR + 1, jE = gBstart1 + (u64)(i64)jR;
+                    int sjdbInd = binarySearch2(jS, jE, g.sjdbStart, g.sjdbEnd, (int)g.sjdbN);
+                    if (sjdbInd >= 0) {
+                        annotated = true;
+                        jCan = g.sjdbMotif[sjdbInd];
+                        if (g.sjdbMotif[sjdbInd] == 0) {
+                            if (L <= g.sjdbShiftLeft[sjdbInd] || eA.L <= g.sjdbShiftLeft[sjdbInd]) return -1000006;
+                            jR += (int)g.sjdbShiftLeft[sjdbInd];
+                            if (rAend + (u64)(i64)jR >= rBend) return -1000006;
+                            jjL = g.sjdbShiftLeft[sjdbInd];
+                            jjR = g.sjdbShiftRight[sjdbInd];
+                        }
+                        eA.annot = 1;
+                        eA.sjStr = g.sjdbStrand[sjdbInd];
+                        Score += P.sjdbScore;
+                    }
+                }
+                if (!annotated) {
+                    if (Del >= P.alignIntronMin) {
+                        Score += P.scoreGap + jPen;
+                    } else {
+                        Score += (int)Del * P.scoreDelBase + P.scoreDelOpen;
+                        jCan = -1;
+                        eA.annot = 0;
+                    }
+                }
+                eA.shL = (u16)jjL; eA.shR = (u16)jjR;
+                eA.canon = (signed char)jCan;
+                if (eA.annot == 0) {
+                    if (jCan > 0) eA.sjStr = (u8)(2 - jCan % 2); else eA.sjStr = 0;
+                }
+            } else if (rGap > gGap) {
+                Ins = (u64)(rGap - gGap);
+                nIns = 1;
+                if (gGap == 0) {
+                    jR = 0;
+                } else if (gGap < 0) {
+                    jR = 0;
+                    Score -= (-gGap);
+                } else {
+                    int Score1 = 0, maxScore1 = 0;
+                    for (int jR1 = 1; jR1 <= gGap; jR1++) {
+                        u8 gv = Gat(ln, gAend + jR1);
+                        if (gv < 4) {
+                            Score1 += (R[rAend + jR1] == gv) ? 1 : -1;
+                            Score1 += (R[rAend + Ins + jR1] == gv) ? -1 : +1;
+                        }
+                        if (Score1 > maxScore1 || (Score1 == maxScore1 && P.alignInsertionFlushRight)) { maxScore1 = Score1; jR = jR1; }
+                    }
+                    for (int ii = 1; ii <= gGap; ii++) {
+                        u64 r1 = rAend + ii + (ii <= jR ? 0 : Ins);
+                        u8 gv = Gat(ln, gAend + ii), rv = R[r1];
+                        if (gv < 4 && rv < 4) {
+                            if (rv == gv) { Score += 1; nMatch++; } else { Score -= 1; nMM++; }
+                        }
+                    }
+                }
+                if (P.alignInsertionFlushRight) {
+                    for (; jR < (int)rBend - (int)rAend - (int)Ins; jR++) {
+                        u8 gv = Gat(ln, gAend + jR + 1);
+                        if (R[rAend + jR + 1] != gv || gv == 4) break;
+                    }
+                    if (jR == (int)rBend - (int)rAend - (int)Ins) return -1000009;
+                }
+                Score += (int)Ins * P.scoreInsBase + P.scoreInsOpen;
+                jCan = -2;
+            }
+
+            if ((h.nMM + nMM) <= outFilterMismatchNmaxTotal
+                && (jCan < 0 || (jCan < 7 && nMM <= (u64)(i64)P.alignSJstitchMismatchNmax[(jCan + 1) / 2]))) {
+                h.nMM += (u32)nMM;
+                h.nMatch += (u32)nMatch;
+                if (Del >= P.alignIntronMin) { h.nGap += (u32)nDel; h.lGap += (u32)Del; }
+                else { h.nDel += (u32)nDel; h.lDel += (u32)Del; }
+                if (Del == 0 && Ins == 0) {
+                    eA.L = (u16)(eA.L + (rBend - rAend));
+                } else if (Del > 0) {
+                    eA.L = (u16)((int)eA.L + jR);
+                    eB.L = (u16)((i64)(rBend - rAend) - jR);
+                    eB.R = (u16)((i64)rAend + jR + 1);
+                    eB.G = gBstart1 + (u64)(i64)jR + 1;
+                    h.nExons++;
+                } else if (Ins > 0) {
+                    h.nIns += (u32)nIns;
+                    h.lIns += (u32)Ins;
+                    eA.L = (u16)((int)eA.L + jR);
+                    eB.L = (u16)((i64)(rBend - rAend) - jR - (i64)Ins);
+                    eB.R = (u16)((i64)rAend + jR + (i64)Ins + 1);
+                    eB.G = gAend + 1 + (u64)(i64)jR;
+                    eA.canon = -2;
+                    eA.annot = 0;
+                    h.nExons++;
+                }
+            } else {
+                return -1000007;
+            }
+        } else if (gBstart + t->ex[0].R + (u64)(i64)P.alignEndsProtrudeNbasesMax >= t->ex[0].G || t->ex[0].G < t->ex[0].R) {
+            if (P.alignMatesGapMax > 0 && gBstart > eA.G + eA.L + P.alignMatesGapMax) return -1000004;
+            Score += (int)L;
+            ExtRes er;
+            er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
+            if (extendAlign(ln, rAend + 1, gAend + 1, 1, 1, STAR_READ_SEQ_LENGTH_MAX, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
+                            P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[eA.iFrag][1], er)) {
+                h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
+                Score += er.maxScore;
+                eA.L = (u16)(eA.L + er.extendL);
+            }
+            eB.R = (u16)rBstart; eB.G = gBstart; eB.L = (u16)L;
+            h.nMatch += (u32)L;
+            er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
+            u64 extlen = P.alignEndsTypeExt[iFragB][1] ? (u64)STAR_READ_SEQ_LENGTH_MAX : gBstart - t->ex[0].G + t->ex[0].R;
+            if (extendAlign(ln, rBstart - 1, gBstart - 1, -1, -1, extlen, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
+                            P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[iFragB][1], er)) {
+                h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
+                Score += er.maxScore;
+                eB.R = (u16)(eB.R - er.extendL);
+                eB.G -= er.extendL;
+                eB.L = (u16)(eB.L + er.extendL);
+            }
+            eA.canon = -3;
+            eA.annot = 0;
+            h.nExons++;
+        } else {
+            return -1000008;
+        }
+    }
+    t->ex[h.nExons - 1].iFrag = (u8)iFragB;
+    t->ex[h.nExons - 1].sjA = sjAB;
+    return Score;
+}
+
+// blocksOverlap.cpp:3-40
+__device__ u64 blocksOverlap(const DevTr& t1, const DevTr& t2) {
+    u32 i1 = 0, i2 = 0;
+    u64 nOverlap = 0;
+    while (i1 < t1.h.nExons && i2 < t2.h.nExons) {
+        u64 rs1 = t1.ex[i1].R, rs2 = t2.ex[i2].R;
+        u64 re1 = rs1 + t1.ex[i1].L, re2 = rs2 + t2.ex[i2].L;
+        u64 gs1 = t1.ex[i1].G, gs2 = t2.ex[i2].G;
+        if (rs1 >= re2) {
+            i2++;
+        } else if (rs2 >= re1) {
+            i1++;
+        } else if (gs1 - rs1 != gs2 - rs2) {
+            if (re1 >= re2) i2++;
+            if (re2 >= re1) i1++;
+        } else {
+            nOverlap += (re1 < re2 ? re1 : re2) - (rs1 > rs2 ? rs1 : rs2);
+            if (re1 >= re2) i2++;
+            if (re2 >= re1) i1++;
+        }
+    }
+    return nOverlap;
+}
+
+__device__ __forceinline__ void copyTr(DevTr* dst, const DevTr* src) {
+    dst->h = src->h;
+    for (u32 i = 0; i < src->h.nExons; i++) dst->ex[i] = src->ex[i];
+}
+
+__device__ int log2Score(const DevIndex& ix, u64 gLen) {
+    // value of int(ceil(log2((double)gLen)*scale-0.5)) from the host-computed step table (stitchWindowAligns.cpp:221-225)
+    int v = ix.log2Val[0];
+    for (int k = 1; k < ix.log2N; k++) {
+        if (gLen >= ix.log2Thr[k]) v = ix.log2Val[k]; else break;
+    }
+    return v;
+}
+
+// leaf of stitchWindowAligns (stitchWindowAligns.cpp:19-306): finalize the transcript held in ln.cur and record it
+__device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str, u32 roStr, u16* wTr, u16* nWinTr) {
+    const star_params_t& P = *ln.P;
+    const DevIndex& g = *ln.ix;
+    DevTr& t = *ln.leaf;
+    copyTr(&t, ln.cur);
+    TrHead& h = t.h;
+    const u64 Lread = ln.Lread;
+    int vOrder[2];
+    if (roStr == 0) { vOrder[0] = 0; vOrder[1] = 1; } else { vOrder[0] = 1; vOrder[1] = 0; }
+    for (int iOrd = 0; iOrd < 2; iOrd++) {
+        ExtRes er;
+        er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
+        if (vOrder[iOrd] == 0) {
+            if (h.rStart > 0) {
+                u32 imate = t.ex[0].iFrag;
+                if (extendAlign(ln, (u64)h.rStart - 1, h.gStart - 1, -1, -1, h.rStart, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
+                                P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[imate][(int)(Str != imate)], er)) {
+                    h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
+                    Score += er.maxScore;
+                    h.rStart -= er.extendL; t.ex[0].R = (u16)h.rStart;
+                    h.gStart -= er.extendL; t.ex[0].G = h.gStart;
+                    t.ex[0].L = (u16)(t.ex[0].L + er.extendL);
+                }
+            }
+        } else {
+            if (tR2 < Lread) {
+                u32 imate = t.ex[h.nExons - 1].iFrag;
+                if (extendAlign(ln, tR2 + 1, tG2 + 1, +1, +1, Lread - tR2 - 1, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
+                                P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[imate][(int)(imate == Str)], er)) {
+                    h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
+                    Score += er.maxScore;
+                    tR2 += er.extendL; tG2 += er.extendL;
+                    t.ex[h.nExons - 1].L = (u16)(t.ex[h.nExons - 1].L + er.extendL);
+                }
+            }
+        }
+    }
+    const u32 nEx = h.nExons;
+    if (!P.alignSoftClipAtReferenceEnds &&
+        ((t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R) > (g.chrStart[Chr] + g.chrLength[Chr]) || t.ex[0].G < (g.chrStart[Chr] + t.ex[0].R))) return;
+    h.rLength = 0;
+    for (u32 i = 0; i < nEx; i++) h.rLength += t.ex[i].L;
+    h.gLength = tG2 + 1 - h.gStart;
+    for (u32 isj = 0; isj + 1 < nEx; isj++) {
+        if (t.ex[isj].canon >= 0) {
+            if (t.ex[isj].annot == 1) {
+                if ((t.ex[isj].L < P.alignSJDBoverhangMin && (isj == 0 || t.ex[isj - 1].canon == -3 || (t.ex[isj - 1].annot == 0 && t.ex[isj - 1].canon >= 0)))
+                    || (t.ex[isj + 1].L < P.alignSJDBoverhangMin && (isj == nEx - 2 || t.ex[isj + 1].canon == -3 || (t.ex[isj + 1].annot == 0 && t.ex[isj + 1].canon >= 0))))
+                    return;
+            } else {
+                if (t.ex[isj].L < P.alignSJoverhangMin + t.ex[isj].shL || t.ex[isj + 1].L < P.alignSJoverhangMin + t.ex[isj].shR) return;
+            }
+        }
+    }
+    if (nEx > 1 && t.ex[nEx - 2].annot == 1 && t.ex[nEx - 1].L < P.alignSJDBoverhangMin) return;
+    u32 sjN = 0, im[3] = {0, 0, 0};
+    for (u32 iex = 0; iex + 1 < nEx; iex++) {
+        if (t.ex[iex].canon >= 0) { sjN++; im[t.ex[iex].sjStr]++; }
+    }
+    if (im[1] > 0 && im[2] == 0) h.sjMotifStrand = 1;
+    else if (im[1] == 0 && im[2] > 0) h.sjMotifStrand = 2;
+    else h.sjMotifStrand = 0;
+    if (im[1] > 0 && im[2] > 0 && P.outFilterIntronStrandsRemoveInconsistent) return;
+    if (sjN > 0 && h.sjMotifStrand == 0 && P.outSAMstrandFieldType == 1) return;
+    if (P.outFilterIntronMotifs == 1) {
+        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0) return;
+    } else if (P.outFilterIntronMotifs == 2) {
+        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0 && t.ex[iex].annot == 0) return;
+    }
+    {
+        u64 nsj = 0, exl = 0;
+        for (u32 iex = 0; iex < nEx; iex++) {
+            exl += t.ex[iex].L;
+            if (iex == nEx - 1 || t.ex[iex].canon == -3) {
+                if (nsj > 0 && (exl < P.alignSplicedMateMapLmin || exl < (u64)(P.alignSplicedMateMapLminOverLmate * (double)ln.readLength[t.ex[iex].iFrag]))) return;
+                exl = 0; nsj = 0;
+            } else if (t.ex[iex].canon >= 0) {
+                nsj++;
+            }
+        }
+    }
+    if (t.ex[0].iFrag != t.ex[nEx - 1].iFrag) {
+        if (t.ex[nEx - 1].G + t.ex[nEx - 1].L <= t.ex[0].G) return;
+        u32 iexM2 = nEx;
+        for (u32 iex = 0; iex + 1 < nEx; iex++) {
+            if (t.ex[iex].canon == -3) { iexM2 = iex + 1; break; }
+        }
+        if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[iexM2].G) {
+            if (t.ex[0].G > t.ex[iexM2].G + t.ex[0].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return;
+            if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return;
+            u32 iex1 = 1, iex2 = iexM2 + 1;
+            for (; iex1 < iexM2; iex1++) {
+                if (t.ex[iex1].G >= t.ex[iex2 - 1].G + t.ex[iex2 - 1].L) break;
+            }
+            while (iex1 < iexM2 && iex2 < nEx) {
+                if (t.ex[iex1 - 1].canon < 0) { iex1++; continue; }
+                if (t.ex[iex2 - 1].canon < 0) { iex2++; continue; }
+                if ((t.ex[iex1].G != t.ex[iex2].G) || ((t.ex[iex1 - 1].G + t.ex[iex1 - 1].L) != (t.ex[iex2 - 1].G + t.ex[iex2 - 1].L))) return;
+                iex1++; iex2++;
+            }
+        }
+    }
+    if (P.scoreGenomicLengthLog2scale != 0) {
+        Score += log2Score(g, t.ex[nEx - 1].G + t.ex[nEx - 1].L - t.ex[0].G);
+        Score = Score > 0 ? Score : 0;
+    }
+    h.maxScore = Score;
+    if (t.ex[0].iFrag == t.ex[nEx - 1].iFrag) {
+        h.iFrag = (signed char)t.ex[0].iFrag;
+        if (ln.maxScoreMate[h.iFrag] < Score) ln.maxScoreMate[h.iFrag] = Score;
+    } else {
+        h.iFrag = -1;
+    }
+    int wBest = ln.pool[wTr[0]].h.maxScore;
+    if (Score + P.outFilterMultimapScoreRange >= wBest || (h.iFrag >= 0 && Score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[h.iFrag])) {
+        u32 iTr = 0;
+        h.mappedLength = 0;
+        for (u32 iex = 0; iex < nEx; iex++) h.mappedLength += t.ex[iex].L;
+        u32 n = *nWinTr;
+        while (iTr < n) {
+            const DevTr& o = ln.pool[wTr[iTr]];
+            u64 nOverlap = blocksOverlap(t, o);
+            u64 uNew = h.mappedLength - nOverlap;
+            u64 uOld = o.h.mappedLength - nOverlap;
+            if (uNew == 0 && Score < o.h.maxScore) {
+                break;
+            } else if (uOld == 0) {
+                u16 p = wTr[iTr];
+                for (u32 ii = iTr + 1; ii < n; ii++) wTr[ii - 1] = wTr[ii];
+                n--;
+                wTr[n] = p;
+            } else if (uOld > 0 && (uNew > 0 || Score >= o.h.maxScore)) {
+                iTr++;
+            }
+        }
+        if (iTr == n) {
+            for (iTr = 0; iTr < n; iTr++) {
+                const DevTr& o = ln.pool[wTr[iTr]];
+                if (Score > o.h.maxScore || (Score == o.h.maxScore && h.gLength < o.h.gLength)) break;
+            }
+            u16 p = wTr[n];
+            for (int ii = (int)n; ii > (int)iTr; ii--) wTr[ii] = wTr[ii - 1];
+            wTr[iTr] = p;
+            copyTr(&ln.pool[p], &t);
+            if (n < P.alignTranscriptsPerWindowNmax) n++;
+        }
+        *nWinTr = (u16)n;
+    }
+}
+
+// stitchWindowAligns.cpp:8-353 as an explicit DFS with undo records (see file header)
+__device__ void stitchWindow(Lane& ln, u32 iW, u32 Chr, u32 Str, u32 roStr, u16* wTr, u16* nWinTr, u32 slotsAvail) {
+    const u32 nA = ln.win[iW].nWA;
+    const Seed* WA = ln.wa + (u64)iW * ln.caps.spw;
+    DevTr* t = ln.cur;
+    Frame* st = ln.stack;
+    // trA = *trInit with Chr/Str set (ReadAlign_stitchPieces.cpp:282-286)
+    TrHead z;
+    z.gStart = 0; z.gLength = 0; z.rStart = 0; z.rLength = 0; z.maxScore = 0; z.nMatch = 0; z.nMM = 0; z.mappedLength = 0;
+    z.nGap = 0; z.lGap = 0; z.nDel = 0; z.lDel = 0; z.nIns = 0; z.lIns = 0; z.nUnique = 0; z.nAnchor = 0; z.nExons = 0; z.iFrag = 0;
+    z.sjMotifStrand = 0; z.primaryFlag = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
+    t->h = z;
+    int sp = 0;
+    st[0].iA = 0; st[0].Score = 0; st[0].tR2 = 0; st[0].tG2 = 0; st[0].phase = 0;
+    while (sp >= 0) {
+        Frame& f = st[sp];
+        if (f.phase == 0) {
+            ln.nodes++;
+            if (f.iA >= nA) {
+                if (f.tR2 != 0) {
+                    ln.leaves++;
+                    if (*nWinTr > slotsAvail) { ln.overflow = 1; return; }   // pool of this lane is full: slow path
+                    finalizeLeaf(ln, f.Score, f.tR2, f.tG2, Chr, Str, roStr, wTr, nWinTr);
+                }
+                sp--;
+                continue;
+            }
+            const Seed s = WA[f.iA];
+            f.h = t->h;
+            if (t->h.nExons > 0) f.last = t->ex[t->h.nExons - 1];
+            int dScore = 0;
+            if (t->h.nExons > 0) {
+                dScore = stitchAlignToTranscript(ln, f.tR2, f.tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+            } else {
+                t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
+                t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
+                t->ex[0].L = s.Length; t->ex[0].iFrag = s.iFrag; t->ex[0].sjA = s.sjA;
+                t->ex[0].canon = 0; t->ex[0].annot = 0; t->ex[0].sjStr = 0; t->ex[0].shL = 0; t->ex[0].shR = 0;
+                t->h.nExons = 1;
+                dScore = s.Length;
+                t->h.nMatch = s.Length;
+            }
+            f.phase = 1;
+            if (dScore > -1000000) {
+                if (s.Nrep == 1) t->h.nUnique++;
+                if (s.Anchor > 0) t->h.nAnchor++;
+                Frame& c = st[sp + 1];
+                c.iA = f.iA + 1; c.Score = f.Score + dScore; c.tR2 = (u32)s.rStart + s.Length - 1; c.tG2 = s.gStart + s.Length - 1; c.phase = 0;
+                sp++;
+            }
+        } else if (f.phase == 1) {
+            // undo the include attempt, then explore the branch without this seed (WA_Anchor==2 never occurs: WlastAnchor is
+            // initialised to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
+            if (f.h.nExons > 0) t->ex[f.h.nExons - 1] = f.last;
+            t->h = f.h;
+            f.phase = 2;
+            Frame& c = st[sp + 1];
+            c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
+            sp++;
+        } else {
+            sp--;
+        }
+    }
+}
+
+// sjAlignSplit.cpp:3-15
+__device__ __forceinline__ bool sjAlignSplit(const DevIndex& g, u64 a1, u64 aLength, u64& a1D, u64& aLengthD, u64& a1A, u64& aLengthA, u32& isj) {
+    u64 sj1 = (a1 - g.sjGstart) % g.sjdbLength;
+    if (sj1 < g.sjdbOverhang && sj1 + aLength > g.sjdbOverhang) {
+        u64 j = (a1 - g.sjGstart) / g.sjdbLength;
+        isj = (u32)j;
+        aLengthD = g.sjdbOverhang - sj1;
+        aLengthA = aLength - aLengthD;
+        a1D = g.sjDstart[j] + sj1;
+        a1A = g.sjAstart[j];
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ u32 chrOfBin(const Lane& ln, u64 bin) {
+    u64 cb = bin >> ln.P->winBinChrNbits;
+    return cb < ln.ix->chrBinN ? ln.ix->chrBin[cb] : 0xFFFFFFFFu;
+}
+
+// ReadAlign_createExtendWindowsWithAlign.cpp:7-84 on the interval list (see file header)
+__device__ int createExtendWindowsWithAlign(Lane& ln, u64 a1, u32 aStr) {
+    const star_params_t& P = *ln.P;
+    u64 aBin = a1 >> P.winBinNbits;
+    Window* W = ln.win;
+    const u32 nW = ln.nW;
+    int left = -1, right = -1;
+    u64 lo = aBin > P.winAnchorDistNbins ? aBin - P.winAnchorDistNbins : 0;
+    u64 hiX = aBin + P.winAnchorDistNbins + 1 < P.winBinN ? aBin + P.winAnchorDistNbins + 1 : P.winBinN;   // exclusive
+    u64 bestL = 0, bestR = 0;
+    for (u32 w = 0; w < nW; w++) {
+        if (W[w].Str != aStr || W[w].gStart > W[w].gEnd) continue;
+        u64 s = W[w].gStart, e = W[w].gEnd;
+        if (s <= aBin && aBin <= e) return 0;   // the bin already belongs to a window
+        if (aBin > 0 && e < aBin && e >= lo) { if (left < 0 || e > bestL) { left = (int)w; bestL = e; } }
+        if (aBin + 1 < P.winBinN && s > aBin && s < hiX) { if (right < 0 || s < bestR) { right = (int)w; bestR = s; } }
+    }
+    bool flagMergeLeft = left >= 0 && chrOfBin(ln, bestL) == chrOfBin(ln, aBin);
+    bool flagMergeRight = right >= 0 && chrOfBin(ln, bestR) == chrOfBin(ln, aBin);
+    u64 iBinLeft = aBin, iBinRight = aBin;
+    int iWin = -1;
+    if (flagMergeLeft) { iWin = left; iBinLeft = W[left].gStart; }
+    if (flagMergeRight) { iBinRight = W[right].gEnd; if (!flagMergeLeft) iWin = right; }
+    if (!flagMergeLeft && !flagMergeRight) {
+        if (nW >= ln.caps.maxW) { ln.overflow = 1; return 101; }
+        Window nw;
+        nw.gStart = (u32)aBin; nw.gEnd = (u32)aBin; nw.Chr = chrOfBin(ln, aBin); nw.nWA = 0; nw.WALrec = 0; nw.Str = (u8)aStr;
+        nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
+        W[nW] = nw;
+        ln.nW = nW + 1;
+        if (ln.nW >= P.alignWindowsPerReadNmax) {
+            ln.nW = (u32)P.alignWindowsPerReadNmax - 1;
+            return 101;   // EXIT_createExtendWindowsWithAlign_TOO_MANY_WINDOWS
+        }
+    } else {
+        W[iWin].gStart = (u32)iBinLeft;
+        W[iWin].gEnd = (u32)iBinRight;
+        if (flagMergeLeft && flagMergeRight) { W[right].gStart = 1; W[right].gEnd = 0; }
+    }
+    return 0;
+}
+
+__device__ __forceinline__ void setSeed(Seed& d, u64 a1, u64 aLength, u64 aNrep, u32 aFrag, u64 aRstart, bool aAnchor, u32 sjA) {
+    d.gStart = a1; d.sjA = sjA; d.rStart = (u16)aRstart; d.Length = (u16)aLength; d.Nrep = (u16)aNrep; d.Anchor = aAnchor ? 1 : 0; d.iFrag = (u8)aFrag;
+}
+
+// ReadAlign_assignAlignToWindow.cpp:6-130.  Returns false when the read hit MARKER_TOO_MANY_ANCHORS_PER_WINDOW.
+__device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64 aNrep, u32 aFrag, u64 aRstart, bool aAnchor, u32 sjA) {
+    const star_params_t& P = *ln.P;
+    u64 bin = a1 >> P.winBinNbits;
+    int iW = -1;
+    for (u32 w = 0; w < ln.nW; w++) {
+        if (ln.win[w].Str == aStr && ln.win[w].gStart <= bin && bin <= ln.win[w].gEnd) { iW = (int)w; break; }
+    }
+    if (iW < 0) return true;
+    Window& W = ln.win[iW];
+    if (!aAnchor && aLength < W.WALrec) return true;
+    Seed* WA = ln.wa + (u64)iW * ln.caps.spw;
+    u32 nWA = W.nWA;
+    {
+        u32 iA;
+        for (iA = 0; iA < nWA; iA++) {
+            const Seed& s = WA[iA];
+            if (aFrag == s.iFrag && s.sjA == sjA && a1 + s.rStart == s.gStart + aRstart
+                && ((aRstart >= s.rStart && aRstart < (u64)s.rStart + s.Length) || (aRstart + aLength >= s.rStart && aRstart + aLength < (u64)s.rStart + s.Length))) break;
+        }
+        if (iA < nWA) {
+            if (aLength > WA[iA].Length) {
+                u32 iA0;
+                for (iA0 = 0; iA0 < nWA; iA0++) {
+                    if (iA0 != iA && aRstart < WA[iA0].rStart) break;
+                }
+                if (iA0 > iA) --iA0;
+                if (iA0 < iA) {
+                    for (u32 iA1 = iA; iA1 > iA0; iA1--) WA[iA1] = WA[iA1 - 1];
+                } else if (iA0 > iA) {
+                    for (u32 iA1 = iA; iA1 < iA0; iA1++) WA[iA1] = WA[iA1 + 1];
+                }
+                setSeed(WA[iA0], a1, aLength, aNrep, aFrag, aRstart, aAnchor, sjA);
+            }
+            return true;
+        }
+    }
+    if (nWA == P.seedPerWindowNmax) {
+        u32 rec = ln.Lread + 1;
+        for (u32 iA = 0; iA < nWA; iA++) if (WA[iA].Anchor != 1 && WA[iA].Length < rec) rec = WA[iA].Length;
+        W.WALrec = (u16)rec;
+        if (rec == ln.Lread + 1) return false;   // mapMarker=MARKER_TOO_MANY_ANCHORS_PER_WINDOW; nW=0
+        if (!aAnchor && aLength < rec) return true;
+        u32 iA1 = 0;
+        for (u32 iA = 0; iA < nWA; iA++) {
+            if (WA[iA].Anchor == 1 || WA[iA].Length > rec) { WA[iA1] = WA[iA]; iA1++; }
+        }
+        nWA = iA1;
+        W.nWA = (u16)nWA;
+    }
+    if (aAnchor || aLength > W.WALrec) {
+        u32 iA;
+        for (iA = 0; iA < nWA; iA++) if (aRstart < WA[iA].rStart) break;
+        for (u32 iA1 = nWA; iA1 > iA; iA1--) WA[iA1] = WA[iA1 - 1];
+        setSeed(WA[iA], a1, aLength, aNrep, aFrag, aRstart, aAnchor, sjA);
+        W.nWA = (u16)(nWA + 1);
+    }
+    return true;
+}
+
+__device__ void exportAlign(const DevTr& t, u32 Chr, u32 Str, u32 roStr, u32 Lread, const DevIndex& g, star_align_t* o) {
+    const u32 n = t.h.nExons;
+    for (u32 i = 0; i < STAR_MAX_N_EXONS; i++) {
+        bool v = i < n;
+        bool j = i + 1 < n;
+        o->exG[i] = v ? t.ex[i].G : 0; o->exR[i] = v ? t.ex[i].R : 0; o->exL[i] = v ? t.ex[i].L : 0; o->exFrag[i] = v ? t.ex[i].iFrag : 0;
+        o->canonSJ[i] = j ? t.ex[i].canon : 0; o->sjAnnot[i] = j ? t.ex[i].annot : 0; o->sjStr[i] = j ? t.ex[i].sjStr : 0;
+        bool sh = j && t.ex[i].canon >= -1;
+        o->shiftSJ[i][0] = sh ? t.ex[i].shL : 0; o->shiftSJ[i][1] = sh ? t.ex[i].shR : 0;
+    }
+    o->nExons = n; o->Chr = Chr; o->Str = (u8)Str; o->roStr = (u8)roStr; o->primaryFlag = t.h.primaryFlag; o->sjMotifStrand = t.h.sjMotifStrand;
+    o->iFrag = t.h.iFrag; o->maxScore = t.h.maxScore; o->nMatch = t.h.nMatch; o->nMM = t.h.nMM; o->nGap = t.h.nGap; o->lGap = t.h.lGap;
+    o->nDel = t.h.nDel; o->lDel = t.h.lDel; o->nIns = t.h.nIns; o->lIns = t.h.lIns; o->nUnique = t.h.nUnique; o->nAnchor = t.h.nAnchor;
+    o->rStart = t.h.rStart; o->rLength = t.h.rLength;
+    o->roStart = roStr == 0 ? t.h.rStart : Lread - t.h.rStart - t.h.rLength;   // ReadAlign_multMapSelect.cpp:52
+    o->gStart = t.h.gStart; o->gLength = t.h.gLength; o->cStart = t.h.gStart - g.chrStart[Chr];
+}
+
+__global__ void __launch_bounds__(128) stitch_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+                                                     ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nReads,
+                                                     const u32* __restrict__ readList, u32* __restrict__ counter, u8* __restrict__ arenas,
+                                                     Caps caps, star_read_result_t* __restrict__ results, star_align_t* __restrict__ staged,
+                                                     WorkCounters* __restrict__ /*wc*/, u32 smemStride) {
+    extern __shared__ u8 smem[];
+    u8* R0 = smem + (size_t)threadIdx.x * 2 * smemStride;
+    u8* R2 = R0 + smemStride;
+    Lane ln;
+    ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.caps = caps;
+    {
+        u8* a = arenas + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * caps.arenaBytes;
+        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+        ln.wa = (Seed*)a; a += (u64)caps.maxW * caps.spw * sizeof(Seed);
+        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+        ln.cur = (DevTr*)a; a += sizeof(DevTr);
+        ln.leaf = (DevTr*)a; a += sizeof(DevTr);
+        ln.stack = (Frame*)a; a += (u64)(caps.spw + 2) * sizeof(Frame);
+        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+        ln.winN = (u16*)a;
+    }
+    for (;;) {
+        u32 k = atomicAdd(counter, 1u);
+        if (k >= nReads) break;
+        u32 i = readList ? readList[k] : k;
+        ReadInfo ri = info[i];
+        ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0;
+        star_read_result_t res;
+        res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+        res.bestRLength = 0; res.Lread = ri.Lread; res.bestTr = 0;
+        if (ri.flags) {   // seed kernel overflowed (bit0) or hit the fatal piece limit (bit1): nothing to do here
+            results[i] = res;
+            continue;
+        }
+        const u32 Lread = ri.Lread;
+        ln.Lread = Lread; ln.readLength[0] = ri.readLength[0]; ln.readLength[1] = ri.readLength[1];
+        ln.outFilterMismatchNmaxTotal = ri.outFilterMismatchNmaxTotal;
+        ln.maxScoreMate[0] = 0; ln.maxScoreMate[1] = 0;
+        ln.overflow = 0;
+        u32 mapMarker = 0;
+        u32 nWfinal = 0;
+        int bestPool = -1;       // trBest: pool index (or -1 = trInit)
+        int bestScore = 0; u64 bestGLength = 0; u32 bestNMM = 0, bestNMatch = 0, bestRLength = 0;
+        u32 nW1 = 0;             // number of windows with transcripts
+        // ReadAlign_mapOneRead.cpp:100-115
+        if (Lread < P.outFilterMatchNmin) {
+            mapMarker = STAR_MARKER_READ_TOO_SHORT; bestRLength = 0;
+        } else if (ri.Nsplit == 0) {
+            mapMarker = STAR_MARKER_NO_GOOD_PIECES; bestRLength = ri.split1_0;
+        } else if (ri.nA == 0) {
+            mapMarker = STAR_MARKER_ALL_PIECES_EXCEED_seedMultimapNmax; bestRLength = ri.multNminL;
+        } else {
+            // ---------------- stitchPieces ----------------
+            const u8* src = reads + (u64)i * stride;
+            for (u32 b = 0; b < Lread; b++) {
+                u8 c = src[b];
+                R0[b] = c;
+                R2[Lread - 1 - b] = c < 4 ? 3 - c : c;
+            }
+            const Piece* PC = pieces + (u64)k * caps.maxP;
+            const u32 nP = ri.nP;
+            ln.nW = 0;
+            for (u32 iP = 0; iP < nP && !ln.overflow; iP++) {   // :41-93
+                const Piece p = PC[iP];
+                if (p.Nrep <= P.winAnchorMultimapNmax) {
+                    u64 aLength = p.Length;
+                    for (u64 iSA = p.SAstart; iSA < p.SAstart + p.Nrep; iSA++) {
+                        ln.saEnum++;
+                        u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
+                        u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                        a1 &= ix.GstrandMask;
+                        if (p.Dir == 1 && aStr == 0) { aStr = 1; }
+                        else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
+                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                        if (a1 >= ix.sjGstart) {
+                            u64 a1D, aLengthD, a1A, aLengthA; u32 sj1;
+                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) {
+                                if (createExtendWindowsWithAlign(ln, a1D, aStr) == 101) break;
+                                if (createExtendWindowsWithAlign(ln, a1A, aStr) == 101) break;
+                            }
+                        } else {
+                            if (createExtendWindowsWithAlign(ln, a1, aStr) == 101) break;
+                        }
+                    }
+                }
+            }
+            for (u32 iWin = 0; iWin < ln.nW; iWin++) {   // flanks :96-118
+                Window& W = ln.win[iWin];
+                if (W.gStart <= W.gEnd) {
+                    u64 wb = W.gStart;
+                    for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
+                    W.gStart = (u32)wb;
+                    wb = W.gEnd;
+                    for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
+                    W.gEnd = (u32)wb;
+                }
+                W.nWA = 0; W.WALrec = 0;
+            }
+            bool tooManyAnchors = false;
+            for (u32 iP = 0; iP < nP && !ln.overflow && !tooManyAnchors; iP++) {   // :129-185
+                const Piece p = PC[iP];
+                u64 aNrep = p.Nrep, aLength = p.Length;
+                u32 aFrag = p.iFrag;
+                bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
+                for (u64 iSA = p.SAstart; iSA < p.SAstart + p.Nrep; iSA++) {
+                    ln.saEnum++;
+                    u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
+                    u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                    a1 &= ix.GstrandMask;
+                    u64 aRstart = p.rStart;
+                    if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
+                    else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
+                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                    if (a1 >= ix.sjGstart) {
+                        u64 a1D, aLengthD, a1A, aLengthA; u32 isj1;
+                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj1)) {
+                            if (!assignAlignToWindow(ln, a1D, aLengthD, aStr, aNrep, aFrag, aRstart, aAnchor, isj1)) { tooManyAnchors = true; break; }
+                            if (!assignAlignToWindow(ln, a1A, aLengthA, aStr, aNrep, aFrag, aRstart + aLengthD, aAnchor, isj1)) { tooManyAnchors = true; break; }
+                        }
+                    } else {
+                        if (!assignAlignToWindow(ln, a1, aLength, aStr, aNrep, aFrag, aRstart, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
+                    }
+                }
+            }
+            if (tooManyAnchors) ln.nW = 0;   // assignAlignToWindow.cpp:77-81; ends as MARKER_NO_GOOD_WINDOW below
+            // ---------------- per-window stitching :262-350 ----------------
+            for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+            u32 trNtotal = 0;
+            for (u32 iW = 0; iW < ln.nW && !ln.overflow; iW++) {
+                if (ln.win[iW].nWA == 0) continue;
+                u32 Chr = ln.win[iW].Chr, Str = ln.win[iW].Str, roStr = Str;
+                if (trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) break;
+                if (trNtotal + 1 > caps.maxTr) { ln.overflow = 1; break; }
+                u16* wTr = ln.trPtr + trNtotal;
+                u16 nWinTr = 0;
+                // *(trAll[iW1][0]) = trA : the window-best comparison starts from maxScore 0 (:293)
+                ln.pool[wTr[0]].h.maxScore = 0;
+                ln.pool[wTr[0]].h.nExons = 0;
+                ln.R = roStr == 0 ? R0 : R2;
+                stitchWindow(ln, iW, Chr, Str, roStr, wTr, &nWinTr, caps.maxTr - trNtotal - 1);
+                if (ln.overflow) break;
+                if (nWinTr == 0) continue;
+                const TrHead& b = ln.pool[wTr[0]].h;
+                if (b.maxScore > bestScore || (b.maxScore == bestScore && b.gLength < bestGLength)) {
+                    bestPool = wTr[0]; bestScore = b.maxScore; bestGLength = b.gLength;
+                }
+                ln.winBase[nW1] = (u16)trNtotal;
+                ln.winN[nW1] = nWinTr;
+                ln.win[nW1].Chr = Chr;      // compact windows (iW1 <= iW): keep Chr/Str of the windows that have transcripts
+                ln.win[nW1].Str = (u8)Str;
+                trNtotal += nWinTr;
+                nW1++;
+            }
+            nWfinal = nW1;
+            if (bestScore == 0) { mapMarker = STAR_MARKER_NO_GOOD_WINDOW; nWfinal = 0; }
+            if (bestPool >= 0) {
+                const TrHead& b = ln.pool[bestPool].h;
+                bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
+            }
+        }
+        ri.cSaEnum = (u32)ln.saEnum; ri.cNodes = (u32)ln.nodes; ri.cLeaves = (u32)ln.leaves;
+        if (ln.overflow) {   // a fast-path cap was hit: flag the read for the slow path
+            ri.flags |= 1;
+            info[i] = ri;
+            results[i] = res;
+            continue;
+        }
+        // ---------------- multMapSelect :8-95 ----------------
+        u32 nTr = 0;
+        if (nWfinal > 0) {
+            for (u32 iW = 0; iW < nWfinal; iW++) {
+                const u16* wTr = ln.trPtr + ln.winBase[iW];
+                for (u32 iTr = 0; iTr < ln.winN[iW]; iTr++) {
+                    if (ln.pool[wTr[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
+                }
+            }
+        }
+        // ---------------- mappedFilter :3-20 ----------------
+        int unmapType = -1;
+        if (nWfinal == 0) {
+            unmapType = 0;
+        } else if ((bestScore < P.outFilterScoreMin) || (bestScore < (int)(P.outFilterScoreMinOverLread * (double)(Lread - 1)))
+                   || (bestNMatch < P.outFilterMatchNmin) || (bestNMatch < (u64)(P.outFilterMatchNminOverLread * (double)(Lread - 1)))) {
+            unmapType = 1;
+        } else if ((bestNMM > ri.outFilterMismatchNmaxTotal) || (double(bestNMM) / double(bestRLength) > P.outFilterMismatchNoverLmax)) {
+            unmapType = 2;
+        } else if (nTr > P.outFilterMultimapNmax) {
+            unmapType = 3;
+        }
+        res.unmapType = unmapType; res.nTr = nTr; res.mapMarker = mapMarker; res.bestScore = bestScore; res.bestNMM = bestNMM; res.bestRLength = bestRLength;
+        if (unmapType < 0) {
+            // trMult order = window order then in-window rank (:26-44); primary flag rules (:56-91)
+            star_align_t* o = staged + (u64)i * caps.nOut;
+            u32 kOut = 0;
+            u32 bestK = 0;
+            for (u32 iW = 0; iW < nWfinal; iW++) {
+                const u16* wTr = ln.trPtr + ln.winBase[iW];
+                for (u32 iTr = 0; iTr < ln.winN[iW]; iTr++) {
+                    DevTr& t = ln.pool[wTr[iTr]];
+                    if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
+                        t.h.primaryFlag = 0;
+                        exportAlign(t, ln.win[iW].Chr, ln.win[iW].Str, ln.win[iW].Str, Lread, ix, o + kOut);
+                        if ((int)wTr[iTr] == bestPool) bestK = kOut;
+                        kOut++;
+                    }
+                }
+            }
+            if (nTr == 1) {
+                o[0].primaryFlag = 1;
+            } else {
+                u32 nbest = 0;
+                if (P.outSAMmultNmax != (u64)-1) {   // bring the best alignments to the top (:60-67)
+                    for (u32 itr = 0; itr < nTr; itr++) {
+                        if (o[itr].maxScore == bestScore) {
+                            if (itr != nbest) { star_align_t tmp = o[itr]; o[itr] = o[nbest]; o[nbest] = tmp; }
+                            if (bestK == itr) bestK = nbest; else if (bestK == nbest) bestK = itr;
+                            ++nbest;
+                        }
+                    }
+                }
+                if (P.outSAMprimaryFlagAllBestScore) {
+                    for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
+                } else if (P.outSAMmultNmax != (u64)-1) {
+                    o[0].primaryFlag = 1;
+                } else {
+                    o[bestK].primaryFlag = 1;
+                }
+            }
+            res.nTrOut = nTr;
+            res.bestTr = bestK;
+        }
+        results[i] = res;
+        info[i] = ri;
+    }
+}
+
+// Compaction: results[i].trOffset = exclusive prefix sum of nTrOut; aligns[trOffset+k] = staged[i*nOut+k].
+// One warp per read copies its alignments with coalesced 16-byte words.
+__global__ void pack_kernel(const star_read_result_t* __restrict__ results, const u64* __restrict__ offsets, const star_align_t* __restrict__ staged,
+                            u32 nOut, u32 nReads, star_align_t* __restrict__ aligns) {
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    u32 nWarps = (gridDim.x * blockDim.x) >> 5;
+    const u32 words = sizeof(star_align_t) / 16;
+    for (u32 i = warp; i < nReads; i += nWarps) {
+        u32 n = results[i].nTrOut;
+        if (n == 0) continue;
+        const uint4* s = (const uint4*)(staged + (u64)i * nOut);
+        uint4* d = (uint4*)(aligns + offsets[i]);
+        for (u32 w = lane; w < n * words; w += 32) d[w] = s[w];
+    }
+}
+
+// single-block exclusive scan of nTrOut (nReads <= a few million: one pass of 1024 threads with a serial carry)
+__global__ void scan_kernel(star_read_result_t* __restrict__ results, u64* __restrict__ offsets, u32 nReads, u64* __restrict__ total) {
+    __shared__ u64 part[1024];
+    u32 t = threadIdx.x;
+    u32 per = (nReads + blockDim.x - 1) / blockDim.x;
+    u32 lo = t * per, hi = lo + per < nReads ? lo + per : nReads;
+    u64 s = 0;
+    for (u32 i = lo; i < hi; i++) s += results[i].nTrOut;
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        u64 run = 0;
+        for (u32 k = 0; k < blockDim.x; k++) { u64 v = part[k]; part[k] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    u64 run = part[t];
+    for (u32 i = lo; i < hi; i++) {
+        offsets[i] = run;
+        results[i].trOffset = run;
+        run += results[i].nTrOut;
+    }
+}
+
+}  // namespace starb

@@ -356,3 +356,16 @@ int finalizeParams(HostParams& P, std::string& err) {
 }  // namespace starhost
 
 extern "C" void star_params_default(star_params_t* p) { starhost::paramsDefault(p); }
+
+extern "C" size_t star_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(star_params_t);
+        case 1: return sizeof(star_index_view_t);
+        case 2: return sizeof(star_read_batch_t);
+        case 3: return sizeof(star_align_t);
+        case 4: return sizeof(star_read_result_t);
+        case 5: return sizeof(star_align_batch_t);
+        case 6: return sizeof(star_chunk_stats_t);
+        default: return 0;
+    }
+}

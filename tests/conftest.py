@@ -1,0 +1,66 @@
+import os
+import subprocess
+import sys
+import tarfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden(tmp_path_factory):
+    """Unpacked tests/golden/tiny.tar.gz (inputs + outputs of the unmodified reference binary)."""
+    d = tmp_path_factory.mktemp("golden")
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", "tiny.tar.gz")) as t:
+        t.extractall(d)
+    return str(d / "tiny")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The product library (built by __graft_entry__.build() / make)."""
+    import star_b200
+    if not os.path.exists(star_b200.capi.LIB_PATH):
+        subprocess.check_call(["make", "-s", "-j8"], cwd=ROOT)
+    return star_b200.load_library()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_capi
+    oracle_capi.build_oracle()
+    return oracle_capi.load_oracle()
+
+
+def read_fastq_seqs(path):
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    return lines[1::4]
+
+
+def sam_body(path):
+    with open(path, "rb") as f:
+        return [l for l in f.read().split(b"\n") if l and not l.startswith(b"@")]
+
+
+def log_counters(path):
+    """Integer / percentage lines of Log.final.out (times and speed excluded)."""
+    out = []
+    with open(path) as f:
+        for i, l in enumerate(f):
+            if "|" not in l:
+                continue
+            k, v = l.split("|", 1)
+            k = k.strip()
+            if k.startswith("Started") or k.startswith("Finished") or k.startswith("Mapping speed"):
+                continue
+            out.append((k, v.strip()))
+    return out

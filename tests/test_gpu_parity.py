@@ -1,0 +1,72 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI, against the CPU oracle and the reference goldens.
+
+Bar: bit-exact (integer/index work).  Every field of every returned alignment and read result must be equal.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import conftest as cf
+
+pytestmark = pytest.mark.gpu
+
+ROOT = cf.ROOT
+
+
+def _sets(golden):
+    return {
+        "std": [os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq")],
+        "hard": [os.path.join(golden, "hard_1.fq"), os.path.join(golden, "hard_2.fq")],
+        "se": [os.path.join(golden, "se_1.fq")],
+    }
+
+
+@pytest.fixture(scope="module")
+def tiny_index(lib, golden):
+    import star_b200 as sb
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    yield idx
+    idx.close()
+
+
+@pytest.mark.parametrize("name", ["std", "hard", "se"])
+def test_engine_matches_oracle_tiny(lib, oracle, golden, tiny_index, name):
+    import oracle_capi as oc
+    import star_b200 as sb
+    files = _sets(golden)[name]
+    mates = [cf.read_fastq_seqs(f) for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    oe = oc.OracleEngine(oracle, tiny_index)
+    res_o, al_o, st_o = oe.map_chunk(seq, off, n, nm)
+    oe.close()
+    eng = sb.Engine(lib, tiny_index, max_reads=n)
+    res_g, al_g, st_g = eng.map_chunk(seq, off, n, nm)
+    eng.close()
+    diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
+    assert not diffs, "\n".join(diffs[:20])
+    # the algorithmic work counters of the MMP search must agree with the instrumented oracle
+    for k in ("mmp_searches", "mmp_sai_words", "mmp_compare_calls", "mmp_bases_examined", "sa_enumerated"):
+        assert getattr(st_g, k) == getattr(st_o, k), k
+
+
+@pytest.mark.parametrize("name,extra", [("std", []), ("hard", []), ("se", []), ("std_opts", None)])
+def test_cli_matches_reference_golden(lib, golden, tmp_path, name, extra):
+    """Drop-in CLI on the GPU vs outputs of the unmodified reference binary (committed goldens)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    if extra is None:
+        mg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mg)
+        extra = mg.OPTS
+    base = "std" if name == "std_opts" else name
+    files = _sets(golden)[base]
+    out = str(tmp_path) + "/"
+    cmd = [os.path.join(ROOT, "star_b200", "bin", "STAR"), "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn"] + files + \
+          ["--outFileNamePrefix", out, "--runThreadN", "2"] + list(extra)
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    ref = os.path.join(golden, "ref_" + name)
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Per-read work analysis of one chunk on the GPU (uses star_gpu_debug_read_info). Usage: analyze_chunk.py [pairs] [mm] [readlen]"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import bench
+import star_b200 as sb
+import synth
+
+INFO = np.dtype({"names": ["Lread", "rl0", "rl1", "nP", "nA", "mapMarker", "multNminL", "Nsplit", "split1_0", "mmTotal", "flags",
+                           "searches", "saiWords", "compare", "bases", "saEnum", "nodes", "leaves", "slow"],
+                 "formats": ["<u4", "<u2", "<u2", "<u2", "<u4", "<u4", "<u4", "<u2", "<u2", "<u4", "<u4"] + ["<u4"] * 8,
+                 "offsets": [0, 4, 6, 8, 12, 16, 20, 24, 26, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64], "itemsize": 68})
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+mm = float(sys.argv[2]) if len(sys.argv) > 2 else 0.005
+rl = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+workdir = "/tmp/star_b200_bench/chr21"
+os.makedirs(workdir, exist_ok=True)
+chrs, trs, idx = bench.prepare_genome(workdir, "chr21")
+lib = sb.load_library()
+lib.star_gpu_debug_read_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+index = sb.Index(lib, idx)
+m1, m2 = synth.make_reads(chrs, trs, n, read_len=rl, mm=mm, seed=1000)
+seq, off, _, nm = sb.pack_reads([m1, m2])
+eng = sb.Engine(lib, index, max_reads=n)
+eng.upload(seq, off, n, nm)
+for k in range(3):
+    st = eng.map_resident()
+    print("run", k, {k2: round(v, 2) if isinstance(v, float) else v for k2, v in st.as_dict().items()})
+info = np.zeros(n, dtype=INFO)
+rc = lib.star_gpu_debug_read_info(eng.ctx, info.ctypes.data, info.nbytes)
+assert rc == 0
+slow = info["slow"] > 0
+print("pairs/s total %.0f ; fast-only stitch %.0f ; seed %.0f" % (n / st.ms_total * 1e3, n / max(st.ms_stitch, 1e-3) * 1e3, n / st.ms_seed * 1e3))
+for name in ["nP", "saEnum", "nodes", "leaves", "compare"]:
+    x = info[name].astype(np.float64)
+    q = np.percentile(x, [50, 90, 99, 99.9, 100])
+    print("%8s mean %.1f  p50 %.0f p90 %.0f p99 %.0f p99.9 %.0f max %.0f | slow-path reads mean %.1f (n=%d) | share of total work in slow reads %.3f"
+          % (name, x.mean(), q[0], q[1], q[2], q[3], q[4], x[slow].mean() if slow.any() else 0, slow.sum(), x[slow].sum() / max(1, x.sum())))
+eng.close()
