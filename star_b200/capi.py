@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstar_b200.so")
+LIB_PATH = os.environ.get("STAR_B200_LIB", os.path.join(_HERE, "lib", "libstar_b200.so"))   # the override is for A/B builds of the same ABI
 
 MAX_EX = 20
 

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "dev.cuh"
 
 namespace starb {
@@ -20,7 +22,8 @@ namespace starb {
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
 __global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
-                              star_read_result_t*, star_align_t*, WorkCounters*, u32);
+                              star_read_result_t*, star_align_t*, const u32*, u32);
+__global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void pack_kernel(const star_read_result_t*, const u64*, const star_align_t*, u32, u32, star_align_t*);
 __global__ void scan_kernel(star_read_result_t*, u64*, u32, u64*);
 __global__ void reduce_counters_kernel(const ReadInfo*, u32, WorkCounters*);
@@ -70,11 +73,14 @@ struct star_ctx {
     u64* d_total = nullptr;
     u32* d_counter = nullptr;    // [0] ticket, [1] flagged count
     u32* d_list = nullptr;
+    u32 *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_order = nullptr;
+    void* d_sortTmp = nullptr; size_t sortTmpBytes = 0;
     WorkCounters* d_wc = nullptr;
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
-    // slow path (allocated on first use)
-    Caps slow; u8* d_arenaSlow = nullptr; Piece* d_piecesSlow = nullptr; u32 slowLanes = 0; u32 slowBatch = 0;
+    // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
+    struct Tier { Caps caps; u8* arena = nullptr; Piece* pieces = nullptr; u32 lanes = 0, batch = 0; };
+    Tier tiers[2];
     // state of the resident chunk
     u32 nReads = 0, nMates = 1, stride = 0, smemStride = 0;
     u64 nAligns = 0;
@@ -144,6 +150,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     if (device < 0 || device >= nDev) { g_err = "star_b200: bad device ordinal"; return STAR_EXIT_RUNTIME; }
     if (v->gSAsparseD != 1) { g_err = "star_b200: only genomeSAsparseD 1 indices are supported"; return STAR_EXIT_GENOME_FILES; }
     if (v->gSAindexNbases > 18) { g_err = "star_b200: genomeSAindexNbases > 18 is not supported"; return STAR_EXIT_GENOME_FILES; }
+    if (params->seedPerWindowNmax > 50) { g_err = "star_b200: seedPerWindowNmax > 50 is not supported by this build (DFS depth)"; return STAR_EXIT_PARAMETER; }
     if (params->seedPerWindowNmax > 1000 || params->seedPerReadNmax > 60000 || params->alignTranscriptsPerReadNmax > 60000) {
         g_err = "star_b200: seedPerWindowNmax/seedPerReadNmax/alignTranscriptsPerReadNmax exceed the engine's 16-bit index range"; return STAR_EXIT_PARAMETER;
     }
@@ -251,11 +258,22 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     c->fast.maxW = (c->fast.maxW + 1) & ~1u;
     if (c->fast.maxTr > params->alignTranscriptsPerReadNmax) c->fast.maxTr = (u32)params->alignTranscriptsPerReadNmax;
     c->fast.arenaBytes = arenaSize(c->fast);
-    c->slow.maxP = (u32)params->seedPerReadNmax;
-    c->slow.maxW = ((u32)params->alignWindowsPerReadNmax + 1) & ~1u;
-    c->slow.maxTr = (u32)params->alignTranscriptsPerReadNmax;
-    c->slow.spw = c->fast.spw; c->slow.nOut = nOut;
-    c->slow.arenaBytes = arenaSize(c->slow);
+    {
+        star_ctx::Tier& M = c->tiers[0];
+        M.caps.maxP = std::min<u32>((u32)params->seedPerReadNmax, envU32("STAR_B200_MID_MAXP", 512));
+        M.caps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_MID_MAXW", 1024)) + 1) & ~1u;
+        M.caps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_MID_MAXTR", 1024));
+        M.caps.spw = c->fast.spw; M.caps.nOut = nOut;
+        M.caps.arenaBytes = arenaSize(M.caps);
+        M.lanes = envU32("STAR_B200_MID_LANES", 8192); M.batch = envU32("STAR_B200_MID_BATCH", 65536);
+        star_ctx::Tier& S = c->tiers[1];
+        S.caps.maxP = (u32)params->seedPerReadNmax;
+        S.caps.maxW = ((u32)params->alignWindowsPerReadNmax + 1) & ~1u;
+        S.caps.maxTr = (u32)params->alignTranscriptsPerReadNmax;
+        S.caps.spw = c->fast.spw; S.caps.nOut = nOut;
+        S.caps.arenaBytes = arenaSize(S.caps);
+        S.lanes = envU32("STAR_B200_SLOW_LANES", 128); S.batch = envU32("STAR_B200_SLOW_BATCH", 4096);
+    }
     if (devAlloc(c, &c->d_seqOff, (size_t)N * 2 + 2)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_info, N)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_pieces, (size_t)N * c->fast.maxP)) return STAR_EXIT_RUNTIME;
@@ -267,6 +285,13 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     if (devAlloc(c, &c->d_counter, 4)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_list, N)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_wc, 1)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_keys, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_keys2, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_vals, N)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_order, N)) return STAR_EXIT_RUNTIME;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, c->sortTmpBytes, c->d_keys, c->d_keys2, c->d_vals, c->d_order, (int)N));
+    CK(cudaMalloc(&c->d_sortTmp, c->sortTmpBytes + 64));
+    c->owned.push_back(c->d_sortTmp);
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
     c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 4);
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
@@ -355,43 +380,46 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaMemsetAsync(c->d_counter, 0, 16, c->stream));
+    order_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, c->d_keys, c->d_vals);
+    CK(cub::DeviceRadixSort::SortPairs(c->d_sortTmp, c->sortTmpBytes, c->d_keys, c->d_keys2, c->d_vals, c->d_order, (int)n, 0, 32, c->stream));
+    g_launches += 4;   // key kernel + cub's histogram/onesweep passes (library kernels, not counted as ours beyond the launch)
     stitch_kernel<<<c->gridStitch, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, n, nullptr, c->d_counter,
-                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_wc, c->smemStride);
+                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_order, c->smemStride);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[8], c->stream));
-    // ---- slow path: reads that exceeded a fast-path cap are redone with the reference's own limits ----
-    CK(cudaMemsetAsync(c->d_counter + 1, 0, 4, c->stream));
-    collect_flagged_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, 1u, c->d_list, c->d_counter + 1);
-    g_launches++;
-    u32 nSlow = 0;
-    CK(cudaMemcpyAsync(&nSlow, c->d_counter + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (nSlow > 0) {
-        if (!c->d_arenaSlow) {
-            c->slowLanes = envU32("STAR_B200_SLOW_LANES", 256);
-            c->slowBatch = envU32("STAR_B200_SLOW_BATCH", 16384);
-            CK(cudaMalloc((void**)&c->d_arenaSlow, (size_t)c->slowLanes * c->slow.arenaBytes));
-            c->owned.push_back(c->d_arenaSlow);
-            CK(cudaMalloc((void**)&c->d_piecesSlow, (size_t)c->slowBatch * c->slow.maxP * sizeof(Piece)));
-            c->owned.push_back(c->d_piecesSlow);
+    // ---- overflow tiers: reads that exceeded the caps of a tier are redone in the next one; the last tier has the reference's own limits ----
+    for (int tier = 0; tier < 2; tier++) {
+        CK(cudaMemsetAsync(c->d_counter + 1, 0, 4, c->stream));
+        collect_flagged_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, 1u, c->d_list, c->d_counter + 1);
+        g_launches++;
+        u32 nSlow = 0;
+        CK(cudaMemcpyAsync(&nSlow, c->d_counter + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (nSlow == 0) break;
+        star_ctx::Tier& T = c->tiers[tier];
+        if (!T.arena) {
+            CK(cudaMalloc((void**)&T.arena, (size_t)T.lanes * T.caps.arenaBytes));
+            c->owned.push_back(T.arena);
+            CK(cudaMalloc((void**)&T.pieces, (size_t)T.batch * T.caps.maxP * sizeof(Piece)));
+            c->owned.push_back(T.pieces);
         }
-        // the list order is made deterministic (atomics gave an arbitrary order): sort on the host, tiny
+        // heaviest first inside the tier too, deterministic order: sort (nA desc, index) on the host (the list is small)
         std::vector<u32> list(nSlow);
         CK(cudaMemcpy(list.data(), c->d_list, (size_t)nSlow * 4, cudaMemcpyDeviceToHost));
         std::sort(list.begin(), list.end());
         CK(cudaMemcpy(c->d_list, list.data(), (size_t)nSlow * 4, cudaMemcpyHostToDevice));
-        int gridSlow = (int)(c->slowLanes / 128);
-        if (gridSlow < 1) gridSlow = 1;
-        for (u32 lo = 0; lo < nSlow; lo += c->slowBatch) {
-            u32 m = nSlow - lo < c->slowBatch ? nSlow - lo : c->slowBatch;
+        int grid = (int)(T.lanes / 128);
+        if (grid < 1) grid = 1;
+        for (u32 lo = 0; lo < nSlow; lo += T.batch) {
+            u32 m = nSlow - lo < T.batch ? nSlow - lo : T.batch;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-            seed_search_kernel<<<gridSlow, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_piecesSlow, c->slow.maxP, m,
-                                                                        c->d_list + lo, c->d_counter, c->d_wc, c->smemStride);
+            seed_search_kernel<<<grid, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, T.caps.maxP, m,
+                                                                    c->d_list + lo, c->d_counter, c->d_wc, c->smemStride);
             g_launches++;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-            stitch_kernel<<<gridSlow, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_piecesSlow, m, c->d_list + lo,
-                                                                     c->d_counter, c->d_arenaSlow, c->slow, c->d_results, c->d_staged, c->d_wc, c->smemStride);
+            stitch_kernel<<<grid, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, m, c->d_list + lo,
+                                                                 c->d_counter, T.arena, T.caps, c->d_results, c->d_staged, nullptr, c->smemStride);
             g_launches++;
             CK(cudaGetLastError());
         }

@@ -27,6 +27,7 @@
 namespace starb {
 
 #define SJA_NONE 0xFFFFFFFFu
+#define STAR_DFS_MAX_DEPTH 52   // seedPerWindowNmax (<=50 on the local-memory fast build) + 2
 
 struct Frame {
     TrHead h;        // head before the include attempt
@@ -65,6 +66,10 @@ struct Lane {
     Caps caps;
     u32 overflow;
     u64 saEnum, nodes, leaves;
+    int sp;              // DFS stack pointer
+    int leafScore;       // pending leaf (set by dfsStep)
+    u32 leafR2;
+    u64 leafG2;
 };
 
 __device__ __forceinline__ u8 Gat(const Lane& ln, u64 pos) { return __ldg(ln.ix->G + (i64)pos); }
@@ -584,31 +589,38 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
     }
 }
 
-// stitchWindowAligns.cpp:8-353 as an explicit DFS with undo records (see file header)
-__device__ void stitchWindow(Lane& ln, u32 iW, u32 Chr, u32 Str, u32 roStr, u16* wTr, u16* nWinTr, u32 slotsAvail) {
-    const u32 nA = ln.win[iW].nWA;
-    const Seed* WA = ln.wa + (u64)iW * ln.caps.spw;
-    DevTr* t = ln.cur;
-    Frame* st = ln.stack;
+// stitchWindowAligns.cpp:8-353 as an explicit DFS with undo records (see file header).
+// dfsInit starts a window; dfsStep runs the cheap bookkeeping transitions (undo, pop) until it has executed ONE seed-include
+// attempt (one stitchAlignToTranscript call), reached a leaf, or emptied the stack.  One call = one unit of work of the
+// warp-lockstep state machine in stitch_kernel: all lanes of a warp that are inside a window execute their stitch call together.
+__device__ __forceinline__ void dfsInit(Lane& ln) {
     // trA = *trInit with Chr/Str set (ReadAlign_stitchPieces.cpp:282-286)
     TrHead z;
     z.gStart = 0; z.gLength = 0; z.rStart = 0; z.rLength = 0; z.maxScore = 0; z.nMatch = 0; z.nMM = 0; z.mappedLength = 0;
     z.nGap = 0; z.lGap = 0; z.nDel = 0; z.lDel = 0; z.nIns = 0; z.lIns = 0; z.nUnique = 0; z.nAnchor = 0; z.nExons = 0; z.iFrag = 0;
     z.sjMotifStrand = 0; z.primaryFlag = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
-    t->h = z;
-    int sp = 0;
-    st[0].iA = 0; st[0].Score = 0; st[0].tR2 = 0; st[0].tG2 = 0; st[0].phase = 0;
-    while (sp >= 0) {
-        Frame& f = st[sp];
+    ln.cur->h = z;
+    ln.sp = 0;
+    Frame& f = ln.stack[0];
+    f.iA = 0; f.Score = 0; f.tR2 = 0; f.tG2 = 0; f.phase = 0;
+}
+
+#define DFS_CONTINUE 0
+#define DFS_LEAF 1
+#define DFS_DONE 2
+__device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
+    DevTr* t = ln.cur;
+    Frame* st = ln.stack;
+    for (;;) {
+        if (ln.sp < 0) return DFS_DONE;
+        Frame& f = st[ln.sp];
         if (f.phase == 0) {
             ln.nodes++;
             if (f.iA >= nA) {
-                if (f.tR2 != 0) {
-                    ln.leaves++;
-                    if (*nWinTr > slotsAvail) { ln.overflow = 1; return; }   // pool of this lane is full: slow path
-                    finalizeLeaf(ln, f.Score, f.tR2, f.tG2, Chr, Str, roStr, wTr, nWinTr);
-                }
-                sp--;
+                bool isLeaf = f.tR2 != 0;   // "iA>=nA && tR2==0: no aligns in the transcript" (:14)
+                if (isLeaf) { ln.leafScore = f.Score; ln.leafR2 = f.tR2; ln.leafG2 = f.tG2; }
+                ln.sp--;
+                if (isLeaf) return DFS_LEAF;
                 continue;
             }
             const Seed s = WA[f.iA];
@@ -630,21 +642,22 @@ __device__ void stitchWindow(Lane& ln, u32 iW, u32 Chr, u32 Str, u32 roStr, u16*
             if (dScore > -1000000) {
                 if (s.Nrep == 1) t->h.nUnique++;
                 if (s.Anchor > 0) t->h.nAnchor++;
-                Frame& c = st[sp + 1];
+                Frame& c = st[ln.sp + 1];
                 c.iA = f.iA + 1; c.Score = f.Score + dScore; c.tR2 = (u32)s.rStart + s.Length - 1; c.tG2 = s.gStart + s.Length - 1; c.phase = 0;
-                sp++;
+                ln.sp++;
             }
+            return DFS_CONTINUE;
         } else if (f.phase == 1) {
             // undo the include attempt, then explore the branch without this seed (WA_Anchor==2 never occurs: WlastAnchor is
             // initialised to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
             if (f.h.nExons > 0) t->ex[f.h.nExons - 1] = f.last;
             t->h = f.h;
             f.phase = 2;
-            Frame& c = st[sp + 1];
+            Frame& c = st[ln.sp + 1];
             c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
-            sp++;
+            ln.sp++;
         } else {
-            sp--;
+            ln.sp--;
         }
     }
 }
@@ -793,94 +806,149 @@ __device__ void exportAlign(const DevTr& t, u32 Chr, u32 Str, u32 roStr, u32 Lre
     o->gStart = t.h.gStart; o->gLength = t.h.gLength; o->cStart = t.h.gStart - g.chrStart[Chr];
 }
 
-__global__ void __launch_bounds__(128) stitch_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+// Warp-lockstep state machine.  Every lane owns one read at a time (persistent lanes, ticket counter) and advances it one
+// unit of work per loop iteration; lanes of a warp that are in the same phase execute that phase's step together, so the
+// dominant units (one stitchAlignToTranscript call per DFS node, one leaf finalisation) run with many active lanes even though
+// the per-read work is heavy-tailed (1 % of the reads hold most of the DFS nodes).  A read never waits for its warp neighbours.
+enum { PH_FETCH = 0, PH_WIN, PH_FLANK, PH_ASSIGN, PH_NEXTWIN, PH_NODE, PH_LEAF, PH_SELECT, PH_DONE };
+
+#ifndef STITCH_MIN_BLOCKS
+#define STITCH_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                      ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nReads,
                                                      const u32* __restrict__ readList, u32* __restrict__ counter, u8* __restrict__ arenas,
                                                      Caps caps, star_read_result_t* __restrict__ results, star_align_t* __restrict__ staged,
-                                                     WorkCounters* __restrict__ /*wc*/, u32 smemStride) {
+                                                     const u32* __restrict__ order, u32 smemStride) {
+    // readList != NULL : slow path, ticket k -> read readList[k], piece slab k
+    // order    != NULL : fast path, ticket k -> read order[k] (heaviest reads first), piece slab = read id
     extern __shared__ u8 smem[];
     u8* R0 = smem + (size_t)threadIdx.x * 2 * smemStride;
     u8* R2 = R0 + smemStride;
+    const u32 lane = threadIdx.x & 31;
+    const u32 warpBase = threadIdx.x & ~31u;
     Lane ln;
-    ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.caps = caps;
+    // DFS state in per-thread local memory (L1-resident, interleaved across lanes) instead of the HBM arena
+    DevTr curL, leafL;
+    Frame stackL[STAR_DFS_MAX_DEPTH];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL;
+    ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
     {
         u8* a = arenas + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * caps.arenaBytes;
         ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
         ln.wa = (Seed*)a; a += (u64)caps.maxW * caps.spw * sizeof(Seed);
         ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
-        ln.cur = (DevTr*)a; a += sizeof(DevTr);
-        ln.leaf = (DevTr*)a; a += sizeof(DevTr);
-        ln.stack = (Frame*)a; a += (u64)(caps.spw + 2) * sizeof(Frame);
+        a += 2 * sizeof(DevTr) + (u64)(caps.spw + 2) * sizeof(Frame);   // (layout kept; DFS state lives in local memory)
         ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
         ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
         ln.winN = (u16*)a;
     }
+    u32 phase = PH_FETCH;
+    u32 k = 0, i = 0;
+    ReadInfo ri;
+    const Piece* PC = nullptr;
+    u32 nP = 0, iP = 0;
+    u64 iSA = 0, iSAend = 0;
+    Piece p;
+    p.SAstart = 0; p.rStart = 0; p.Length = 0; p.Nrep = 0; p.Dir = 0; p.iFrag = 0;
+    bool tooManyAnchors = false;
+    u32 mapMarker = 0, nWfinal = 0, nW1 = 0, iW = 0, trNtotal = 0, Chr = 0, Str = 0, bestRLength = 0;
+    int bestPool = -1, bestScore = 0;
+    u64 bestGLength = 0;
+    u16* wTr = nullptr;
+    u16 nWinTr = 0;
+
     for (;;) {
-        u32 k = atomicAdd(counter, 1u);
-        if (k >= nReads) break;
-        u32 i = readList ? readList[k] : k;
-        ReadInfo ri = info[i];
-        ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0;
-        star_read_result_t res;
-        res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
-        res.bestRLength = 0; res.Lread = ri.Lread; res.bestTr = 0;
-        if (ri.flags) {   // seed kernel overflowed (bit0) or hit the fatal piece limit (bit1): nothing to do here
-            results[i] = res;
-            continue;
-        }
-        const u32 Lread = ri.Lread;
-        ln.Lread = Lread; ln.readLength[0] = ri.readLength[0]; ln.readLength[1] = ri.readLength[1];
-        ln.outFilterMismatchNmaxTotal = ri.outFilterMismatchNmaxTotal;
-        ln.maxScoreMate[0] = 0; ln.maxScoreMate[1] = 0;
-        ln.overflow = 0;
-        u32 mapMarker = 0;
-        u32 nWfinal = 0;
-        int bestPool = -1;       // trBest: pool index (or -1 = trInit)
-        int bestScore = 0; u64 bestGLength = 0; u32 bestNMM = 0, bestNMatch = 0, bestRLength = 0;
-        u32 nW1 = 0;             // number of windows with transcripts
-        // ReadAlign_mapOneRead.cpp:100-115
-        if (Lread < P.outFilterMatchNmin) {
-            mapMarker = STAR_MARKER_READ_TOO_SHORT; bestRLength = 0;
-        } else if (ri.Nsplit == 0) {
-            mapMarker = STAR_MARKER_NO_GOOD_PIECES; bestRLength = ri.split1_0;
-        } else if (ri.nA == 0) {
-            mapMarker = STAR_MARKER_ALL_PIECES_EXCEED_seedMultimapNmax; bestRLength = ri.multNminL;
-        } else {
-            // ---------------- stitchPieces ----------------
-            const u8* src = reads + (u64)i * stride;
-            for (u32 b = 0; b < Lread; b++) {
-                u8 c = src[b];
-                R0[b] = c;
-                R2[Lread - 1 - b] = c < 4 ? 3 - c : c;
-            }
-            const Piece* PC = pieces + (u64)k * caps.maxP;
-            const u32 nP = ri.nP;
-            ln.nW = 0;
-            for (u32 iP = 0; iP < nP && !ln.overflow; iP++) {   // :41-93
-                const Piece p = PC[iP];
-                if (p.Nrep <= P.winAnchorMultimapNmax) {
-                    u64 aLength = p.Length;
-                    for (u64 iSA = p.SAstart; iSA < p.SAstart + p.Nrep; iSA++) {
-                        ln.saEnum++;
-                        u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
-                        u32 aStr = (u32)(a1 >> ix.GstrandBit);
-                        a1 &= ix.GstrandMask;
-                        if (p.Dir == 1 && aStr == 0) { aStr = 1; }
-                        else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
-                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                        if (a1 >= ix.sjGstart) {
-                            u64 a1D, aLengthD, a1A, aLengthA; u32 sj1;
-                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) {
-                                if (createExtendWindowsWithAlign(ln, a1D, aStr) == 101) break;
-                                if (createExtendWindowsWithAlign(ln, a1A, aStr) == 101) break;
-                            }
-                        } else {
-                            if (createExtendWindowsWithAlign(ln, a1, aStr) == 101) break;
-                        }
-                    }
+        // ------------------------------------------------------------------ fetch the next read
+        bool needCopy = false;
+        if (phase == PH_FETCH) {
+            k = atomicAdd(counter, 1u);
+            if (k >= nReads) {
+                phase = PH_DONE;
+            } else {
+                i = readList ? readList[k] : (order ? order[k] : k);
+                ri = info[i];
+                ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.overflow = 0;
+                ln.Lread = ri.Lread; ln.readLength[0] = ri.readLength[0]; ln.readLength[1] = ri.readLength[1];
+                ln.outFilterMismatchNmaxTotal = ri.outFilterMismatchNmaxTotal;
+                ln.maxScoreMate[0] = 0; ln.maxScoreMate[1] = 0;
+                mapMarker = 0; nWfinal = 0; nW1 = 0; bestPool = -1; bestScore = 0; bestGLength = 0; bestRLength = 0;
+                tooManyAnchors = false;
+                if (ri.flags) {   // seed kernel overflowed (bit0) or hit the fatal piece limit (bit1): the read is redone / reported elsewhere
+                    star_read_result_t res;
+                    res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+                    res.bestRLength = 0; res.Lread = ri.Lread; res.bestTr = 0;
+                    results[i] = res;
+                } else if (ri.Lread < P.outFilterMatchNmin) {   // ReadAlign_mapOneRead.cpp:100-115
+                    mapMarker = STAR_MARKER_READ_TOO_SHORT; bestRLength = 0; phase = PH_SELECT;
+                } else if (ri.Nsplit == 0) {
+                    mapMarker = STAR_MARKER_NO_GOOD_PIECES; bestRLength = ri.split1_0; phase = PH_SELECT;
+                } else if (ri.nA == 0) {
+                    mapMarker = STAR_MARKER_ALL_PIECES_EXCEED_seedMultimapNmax; bestRLength = ri.multNminL; phase = PH_SELECT;
+                } else {
+                    needCopy = true;
+                    PC = pieces + (u64)(readList ? k : i) * caps.maxP;
+                    nP = ri.nP; iP = 0; iSA = 0; iSAend = 0;
+                    ln.nW = 0;
+                    phase = PH_WIN;
                 }
             }
-            for (u32 iWin = 0; iWin < ln.nW; iWin++) {   // flanks :96-118
+        }
+        {   // the whole warp copies the reads of the lanes that just fetched one (coalesced) into their shared-memory rows
+            u32 m = __ballot_sync(0xffffffffu, needCopy);
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                u32 ri_i = __shfl_sync(0xffffffffu, i, src);
+                u32 L = __shfl_sync(0xffffffffu, ln.Lread, src);
+                const u8* g = reads + (u64)ri_i * stride;
+                u8* d0 = smem + (size_t)(warpBase + src) * 2 * smemStride;
+                u8* d2 = d0 + smemStride;
+                for (u32 b = lane; b < L; b += 32) {
+                    u8 c = g[b];
+                    d0[b] = c;
+                    d2[L - 1 - b] = c < 4 ? 3 - c : c;
+                }
+            }
+            __syncwarp();
+        }
+        // ------------------------------------------------------------------ window creation, one SA locus per step (:41-93)
+        if (phase == PH_WIN) {
+            if (iSA >= iSAend) {
+                while (iP < nP) {
+                    p = PC[iP];
+                    iP++;
+                    if (p.Nrep <= P.winAnchorMultimapNmax) { iSA = p.SAstart; iSAend = p.SAstart + p.Nrep; break; }
+                }
+                if (iSA >= iSAend) phase = PH_FLANK;
+            }
+            if (phase == PH_WIN) {
+                ln.saEnum++;
+                u64 aLength = p.Length;
+                u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
+                iSA++;
+                u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                a1 &= ix.GstrandMask;
+                if (p.Dir == 1 && aStr == 0) { aStr = 1; }
+                else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
+                else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                bool stopPiece = false;
+                if (a1 >= ix.sjGstart) {
+                    u64 a1D, aLengthD, a1A, aLengthA; u32 sj1;
+                    if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) {
+                        if (createExtendWindowsWithAlign(ln, a1D, aStr) == 101) stopPiece = true;
+                        else if (createExtendWindowsWithAlign(ln, a1A, aStr) == 101) stopPiece = true;
+                    }
+                } else {
+                    if (createExtendWindowsWithAlign(ln, a1, aStr) == 101) stopPiece = true;
+                }
+                if (stopPiece) iSA = iSAend;   // EXIT_createExtendWindowsWithAlign_TOO_MANY_WINDOWS breaks the loop of this piece only
+                if (ln.overflow) phase = PH_SELECT;
+            }
+        }
+        // ------------------------------------------------------------------ flanks (:96-118)
+        if (phase == PH_FLANK) {
+            for (u32 iWin = 0; iWin < ln.nW; iWin++) {
                 Window& W = ln.win[iWin];
                 if (W.gStart <= W.gEnd) {
                     u64 wb = W.gStart;
@@ -892,142 +960,202 @@ __global__ void __launch_bounds__(128) stitch_kernel(DevIndex ix, star_params_t 
                 }
                 W.nWA = 0; W.WALrec = 0;
             }
-            bool tooManyAnchors = false;
-            for (u32 iP = 0; iP < nP && !ln.overflow && !tooManyAnchors; iP++) {   // :129-185
-                const Piece p = PC[iP];
+            iP = 0; iSA = 0; iSAend = 0;
+            phase = PH_ASSIGN;
+        }
+        // ------------------------------------------------------------------ seed -> window assignment, one SA locus per step (:129-185)
+        if (phase == PH_ASSIGN) {
+            if (iSA >= iSAend) {
+                if (iP < nP) { p = PC[iP]; iP++; iSA = p.SAstart; iSAend = p.SAstart + p.Nrep; }
+                else {
+                    // init per-window stitching (:262-270)
+                    if (tooManyAnchors) ln.nW = 0;   // assignAlignToWindow.cpp:77-81; ends as MARKER_NO_GOOD_WINDOW
+                    for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+                    trNtotal = 0; iW = 0; nW1 = 0;
+                    phase = PH_NEXTWIN;
+                }
+            }
+            if (phase == PH_ASSIGN) {
+                ln.saEnum++;
                 u64 aNrep = p.Nrep, aLength = p.Length;
                 u32 aFrag = p.iFrag;
                 bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
-                for (u64 iSA = p.SAstart; iSA < p.SAstart + p.Nrep; iSA++) {
-                    ln.saEnum++;
-                    u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
-                    u32 aStr = (u32)(a1 >> ix.GstrandBit);
-                    a1 &= ix.GstrandMask;
-                    u64 aRstart = p.rStart;
-                    if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
-                    else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
-                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                    if (a1 >= ix.sjGstart) {
-                        u64 a1D, aLengthD, a1A, aLengthA; u32 isj1;
-                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj1)) {
-                            if (!assignAlignToWindow(ln, a1D, aLengthD, aStr, aNrep, aFrag, aRstart, aAnchor, isj1)) { tooManyAnchors = true; break; }
-                            if (!assignAlignToWindow(ln, a1A, aLengthA, aStr, aNrep, aFrag, aRstart + aLengthD, aAnchor, isj1)) { tooManyAnchors = true; break; }
-                        }
-                    } else {
-                        if (!assignAlignToWindow(ln, a1, aLength, aStr, aNrep, aFrag, aRstart, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
+                u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
+                iSA++;
+                u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                a1 &= ix.GstrandMask;
+                u64 aRstart = p.rStart;
+                const u32 Lread = ln.Lread;
+                if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
+                else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
+                else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                if (a1 >= ix.sjGstart) {
+                    u64 a1D, aLengthD, a1A, aLengthA; u32 isj1;
+                    if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj1)) {
+                        if (!assignAlignToWindow(ln, a1D, aLengthD, aStr, aNrep, aFrag, aRstart, aAnchor, isj1)) tooManyAnchors = true;
+                        else if (!assignAlignToWindow(ln, a1A, aLengthA, aStr, aNrep, aFrag, aRstart + aLengthD, aAnchor, isj1)) tooManyAnchors = true;
                     }
+                } else {
+                    if (!assignAlignToWindow(ln, a1, aLength, aStr, aNrep, aFrag, aRstart, aAnchor, SJA_NONE)) tooManyAnchors = true;
                 }
+                if (tooManyAnchors) { iSA = iSAend; iP = nP; }   // the rest of the reference's enumeration is dead work (nW=0)
             }
-            if (tooManyAnchors) ln.nW = 0;   // assignAlignToWindow.cpp:77-81; ends as MARKER_NO_GOOD_WINDOW below
-            // ---------------- per-window stitching :262-350 ----------------
-            for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
-            u32 trNtotal = 0;
-            for (u32 iW = 0; iW < ln.nW && !ln.overflow; iW++) {
-                if (ln.win[iW].nWA == 0) continue;
-                u32 Chr = ln.win[iW].Chr, Str = ln.win[iW].Str, roStr = Str;
-                if (trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) break;
+        }
+        // ------------------------------------------------------------------ next window with seeds (:268-299)
+        if (phase == PH_NEXTWIN) {
+            bool found = false;
+            while (iW < ln.nW) {
+                if (ln.win[iW].nWA == 0) { iW++; continue; }
+                if (trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) { iW = ln.nW; break; }   // logs a warning in the reference (:288-292)
                 if (trNtotal + 1 > caps.maxTr) { ln.overflow = 1; break; }
-                u16* wTr = ln.trPtr + trNtotal;
-                u16 nWinTr = 0;
+                found = true;
+                break;
+            }
+            if (ln.overflow) {
+                phase = PH_SELECT;
+            } else if (!found) {
+                nWfinal = nW1;
+                if (bestScore == 0) { mapMarker = STAR_MARKER_NO_GOOD_WINDOW; nWfinal = 0; }
+                phase = PH_SELECT;
+            } else {
+                Chr = ln.win[iW].Chr; Str = ln.win[iW].Str;
+                wTr = ln.trPtr + trNtotal;
+                nWinTr = 0;
                 // *(trAll[iW1][0]) = trA : the window-best comparison starts from maxScore 0 (:293)
                 ln.pool[wTr[0]].h.maxScore = 0;
                 ln.pool[wTr[0]].h.nExons = 0;
-                ln.R = roStr == 0 ? R0 : R2;
-                stitchWindow(ln, iW, Chr, Str, roStr, wTr, &nWinTr, caps.maxTr - trNtotal - 1);
-                if (ln.overflow) break;
-                if (nWinTr == 0) continue;
-                const TrHead& b = ln.pool[wTr[0]].h;
-                if (b.maxScore > bestScore || (b.maxScore == bestScore && b.gLength < bestGLength)) {
-                    bestPool = wTr[0]; bestScore = b.maxScore; bestGLength = b.gLength;
+                ln.R = Str == 0 ? R0 : R2;
+                dfsInit(ln);
+                phase = PH_NODE;
+            }
+        }
+        // ------------------------------------------------------------------ one DFS unit: one seed-include attempt
+        if (phase == PH_NODE) {
+            int r = dfsStep(ln, ln.wa + (u64)iW * caps.spw, ln.win[iW].nWA);
+            if (r == DFS_LEAF) {
+                phase = PH_LEAF;
+            } else if (r == DFS_DONE) {   // window finished (:324-331)
+                if (nWinTr > 0) {
+                    const TrHead& b = ln.pool[wTr[0]].h;
+                    if (b.maxScore > bestScore || (b.maxScore == bestScore && b.gLength < bestGLength)) {
+                        bestPool = wTr[0]; bestScore = b.maxScore; bestGLength = b.gLength;
+                    }
+                    ln.winBase[nW1] = (u16)trNtotal;
+                    ln.winN[nW1] = nWinTr;
+                    ln.win[nW1].Chr = Chr;      // compact windows (iW1 <= iW): keep Chr/Str of the windows that have transcripts
+                    ln.win[nW1].Str = (u8)Str;
+                    trNtotal += nWinTr;
+                    nW1++;
                 }
-                ln.winBase[nW1] = (u16)trNtotal;
-                ln.winN[nW1] = nWinTr;
-                ln.win[nW1].Chr = Chr;      // compact windows (iW1 <= iW): keep Chr/Str of the windows that have transcripts
-                ln.win[nW1].Str = (u8)Str;
-                trNtotal += nWinTr;
-                nW1++;
-            }
-            nWfinal = nW1;
-            if (bestScore == 0) { mapMarker = STAR_MARKER_NO_GOOD_WINDOW; nWfinal = 0; }
-            if (bestPool >= 0) {
-                const TrHead& b = ln.pool[bestPool].h;
-                bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
+                iW++;
+                phase = PH_NEXTWIN;
             }
         }
-        ri.cSaEnum = (u32)ln.saEnum; ri.cNodes = (u32)ln.nodes; ri.cLeaves = (u32)ln.leaves;
-        if (ln.overflow) {   // a fast-path cap was hit: flag the read for the slow path
-            ri.flags |= 1;
-            info[i] = ri;
-            results[i] = res;
-            continue;
+        // ------------------------------------------------------------------ leaf: extend, filter, score, record (:19-306)
+        if (phase == PH_LEAF) {
+            ln.leaves++;
+            if (nWinTr > caps.maxTr - trNtotal - 1) {   // pool of this lane is full: slow path
+                ln.overflow = 1;
+                phase = PH_SELECT;
+            } else {
+                finalizeLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str, wTr, &nWinTr);
+                phase = PH_NODE;
+            }
         }
-        // ---------------- multMapSelect :8-95 ----------------
-        u32 nTr = 0;
-        if (nWfinal > 0) {
-            for (u32 iW = 0; iW < nWfinal; iW++) {
-                const u16* wTr = ln.trPtr + ln.winBase[iW];
-                for (u32 iTr = 0; iTr < ln.winN[iW]; iTr++) {
-                    if (ln.pool[wTr[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
+        // ------------------------------------------------------------------ multMapSelect, mappedFilter, export
+        if (phase == PH_SELECT) {
+            const u32 Lread = ri.Lread;
+            star_read_result_t res;
+            res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+            res.bestRLength = 0; res.Lread = Lread; res.bestTr = 0;
+            ri.cSaEnum = (u32)ln.saEnum; ri.cNodes = (u32)ln.nodes; ri.cLeaves = (u32)ln.leaves;
+            if (ln.overflow) {   // a fast-path cap was hit: flag the read for the slow path
+                ri.flags |= 1;
+                info[i] = ri;
+                results[i] = res;
+            } else {
+                u32 bestNMM = 0, bestNMatch = 0;
+                if (bestPool >= 0) {
+                    const TrHead& b = ln.pool[bestPool].h;
+                    bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
                 }
-            }
-        }
-        // ---------------- mappedFilter :3-20 ----------------
-        int unmapType = -1;
-        if (nWfinal == 0) {
-            unmapType = 0;
-        } else if ((bestScore < P.outFilterScoreMin) || (bestScore < (int)(P.outFilterScoreMinOverLread * (double)(Lread - 1)))
-                   || (bestNMatch < P.outFilterMatchNmin) || (bestNMatch < (u64)(P.outFilterMatchNminOverLread * (double)(Lread - 1)))) {
-            unmapType = 1;
-        } else if ((bestNMM > ri.outFilterMismatchNmaxTotal) || (double(bestNMM) / double(bestRLength) > P.outFilterMismatchNoverLmax)) {
-            unmapType = 2;
-        } else if (nTr > P.outFilterMultimapNmax) {
-            unmapType = 3;
-        }
-        res.unmapType = unmapType; res.nTr = nTr; res.mapMarker = mapMarker; res.bestScore = bestScore; res.bestNMM = bestNMM; res.bestRLength = bestRLength;
-        if (unmapType < 0) {
-            // trMult order = window order then in-window rank (:26-44); primary flag rules (:56-91)
-            star_align_t* o = staged + (u64)i * caps.nOut;
-            u32 kOut = 0;
-            u32 bestK = 0;
-            for (u32 iW = 0; iW < nWfinal; iW++) {
-                const u16* wTr = ln.trPtr + ln.winBase[iW];
-                for (u32 iTr = 0; iTr < ln.winN[iW]; iTr++) {
-                    DevTr& t = ln.pool[wTr[iTr]];
-                    if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
-                        t.h.primaryFlag = 0;
-                        exportAlign(t, ln.win[iW].Chr, ln.win[iW].Str, ln.win[iW].Str, Lread, ix, o + kOut);
-                        if ((int)wTr[iTr] == bestPool) bestK = kOut;
-                        kOut++;
+                // ---------------- multMapSelect :8-95 ----------------
+                u32 nTr = 0;
+                for (u32 w = 0; w < nWfinal; w++) {
+                    const u16* wt = ln.trPtr + ln.winBase[w];
+                    for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
+                        if (ln.pool[wt[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
                     }
                 }
-            }
-            if (nTr == 1) {
-                o[0].primaryFlag = 1;
-            } else {
-                u32 nbest = 0;
-                if (P.outSAMmultNmax != (u64)-1) {   // bring the best alignments to the top (:60-67)
-                    for (u32 itr = 0; itr < nTr; itr++) {
-                        if (o[itr].maxScore == bestScore) {
-                            if (itr != nbest) { star_align_t tmp = o[itr]; o[itr] = o[nbest]; o[nbest] = tmp; }
-                            if (bestK == itr) bestK = nbest; else if (bestK == nbest) bestK = itr;
-                            ++nbest;
+                // ---------------- mappedFilter :3-20 ----------------
+                int unmapType = -1;
+                if (nWfinal == 0) {
+                    unmapType = 0;
+                } else if ((bestScore < P.outFilterScoreMin) || (bestScore < (int)(P.outFilterScoreMinOverLread * (double)(Lread - 1)))
+                           || (bestNMatch < P.outFilterMatchNmin) || (bestNMatch < (u64)(P.outFilterMatchNminOverLread * (double)(Lread - 1)))) {
+                    unmapType = 1;
+                } else if ((bestNMM > ri.outFilterMismatchNmaxTotal) || (double(bestNMM) / double(bestRLength) > P.outFilterMismatchNoverLmax)) {
+                    unmapType = 2;
+                } else if (nTr > P.outFilterMultimapNmax) {
+                    unmapType = 3;
+                }
+                res.unmapType = unmapType; res.nTr = nTr; res.mapMarker = mapMarker; res.bestScore = bestScore; res.bestNMM = bestNMM; res.bestRLength = bestRLength;
+                if (unmapType < 0) {
+                    // trMult order = window order then in-window rank (:26-44); primary flag rules (:56-91)
+                    star_align_t* o = staged + (u64)i * caps.nOut;
+                    u32 kOut = 0;
+                    u32 bestK = 0;
+                    for (u32 w = 0; w < nWfinal; w++) {
+                        const u16* wt = ln.trPtr + ln.winBase[w];
+                        for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
+                            DevTr& t = ln.pool[wt[iTr]];
+                            if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
+                                t.h.primaryFlag = 0;
+                                exportAlign(t, ln.win[w].Chr, ln.win[w].Str, ln.win[w].Str, Lread, ix, o + kOut);
+                                if ((int)wt[iTr] == bestPool) bestK = kOut;
+                                kOut++;
+                            }
                         }
                     }
+                    if (nTr == 1) {
+                        o[0].primaryFlag = 1;
+                    } else {
+                        u32 nbest = 0;
+                        if (P.outSAMmultNmax != (u64)-1) {   // bring the best alignments to the top (:60-67)
+                            for (u32 itr = 0; itr < nTr; itr++) {
+                                if (o[itr].maxScore == bestScore) {
+                                    if (itr != nbest) { star_align_t tmp = o[itr]; o[itr] = o[nbest]; o[nbest] = tmp; }
+                                    if (bestK == itr) bestK = nbest; else if (bestK == nbest) bestK = itr;
+                                    ++nbest;
+                                }
+                            }
+                        }
+                        if (P.outSAMprimaryFlagAllBestScore) {
+                            for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
+                        } else if (P.outSAMmultNmax != (u64)-1) {
+                            o[0].primaryFlag = 1;
+                        } else {
+                            o[bestK].primaryFlag = 1;
+                        }
+                    }
+                    res.nTrOut = nTr;
+                    res.bestTr = bestK;
                 }
-                if (P.outSAMprimaryFlagAllBestScore) {
-                    for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
-                } else if (P.outSAMmultNmax != (u64)-1) {
-                    o[0].primaryFlag = 1;
-                } else {
-                    o[bestK].primaryFlag = 1;
-                }
+                results[i] = res;
+                info[i] = ri;
             }
-            res.nTrOut = nTr;
-            res.bestTr = bestK;
+            phase = PH_FETCH;
         }
-        results[i] = res;
-        info[i] = ri;
+        if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
     }
+}
+
+// Heaviest-first schedule of the fast path: key = ~nA (number of genomic loci of the stored pieces, known after seeding).
+// The per-read work is heavy-tailed (a read inside a repeat family costs 1000x the median); starting those reads first keeps
+// the tail of the persistent kernel short.
+__global__ void order_keys_kernel(const ReadInfo* __restrict__ info, u32 nReads, u32* __restrict__ keys, u32* __restrict__ vals) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nReads) { keys[i] = 0xFFFFFFFFu - info[i].nA; vals[i] = i; }
 }
 
 // Compaction: results[i].trOffset = exclusive prefix sum of nTrOut; aligns[trOffset+k] = staged[i*nOut+k].

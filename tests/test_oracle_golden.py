@@ -1,0 +1,68 @@
+"""CPU tests (no GPU): the oracle restatement + the repository's host code against outputs of the UNMODIFIED reference.
+
+test_oracle_cli_matches_golden   committed goldens (tests/golden/tiny.tar.gz, produced by oracle/_ref/STAR; see make_golden.py)
+test_oracle_vs_live_reference    fresh seeded reads through oracle/_ref/STAR (when it was built in this container) and the oracle
+"""
+import os
+import subprocess
+
+import pytest
+
+import conftest as cf
+import oracle_capi as oc
+
+ROOT = cf.ROOT
+
+
+def _run_cli(binary, genome_dir, files, out, extra=(), threads=2, env=None):
+    cmd = [binary, "--genomeDir", genome_dir, "--readFilesIn"] + files + ["--outFileNamePrefix", out, "--runThreadN", str(threads)] + list(extra)
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, env=env)
+
+
+def _opts():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.OPTS
+
+
+@pytest.mark.parametrize("name", ["std", "hard", "se", "std_opts"])
+def test_oracle_cli_matches_golden(oracle, golden, tmp_path, name):
+    base = "std" if name == "std_opts" else name
+    files = [os.path.join(golden, base + "_1.fq")] + ([os.path.join(golden, base + "_2.fq")] if base != "se" else [])
+    out = str(tmp_path) + "/"
+    _run_cli(oc.ORACLE_CLI, os.path.join(golden, "idx"), files, out, extra=_opts() if name == "std_opts" else ())
+    ref = os.path.join(golden, "ref_" + name)
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+
+
+def test_sam_header_sq_lines(oracle, golden, tmp_path):
+    out = str(tmp_path) + "/"
+    _run_cli(oc.ORACLE_CLI, os.path.join(golden, "idx"), [os.path.join(golden, "se_1.fq")], out)
+    ours = [l for l in open(out + "Aligned.out.sam") if l.startswith("@HD") or l.startswith("@SQ")]
+    ref = [l for l in open(os.path.join(golden, "ref_se", "Aligned.out.sam")) if l.startswith("@HD") or l.startswith("@SQ")]
+    assert ours == ref
+
+
+@pytest.mark.skipif(not os.path.exists(oc.REF_STAR), reason="oracle/_ref/STAR not built (needs /root/reference)")
+@pytest.mark.parametrize("kw", [dict(n_pairs=3000, read_len=100, mm=0.01, seed=77, indel=0.002, nrate=0.002, junk=0.02),
+                                dict(n_pairs=800, read_len=125, mm=0.04, seed=78, indel=0.003, nrate=0.003, junk=0.0)])
+def test_oracle_vs_live_reference(oracle, golden, tmp_path, kw):
+    """Fresh seeded reads (not in the goldens): unmodified reference binary vs oracle, byte-identical outputs."""
+    import synth
+    chrs = synth.make_genome("tiny")
+    trs = synth.make_annotation(chrs, "tiny")
+    m1, m2 = synth.make_reads(chrs, trs, **kw)
+    f1, f2 = str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq")
+    synth.write_fastq(m1, f1)
+    synth.write_fastq(m2, f2)
+    os.makedirs(str(tmp_path / "ref"))
+    os.makedirs(str(tmp_path / "ora"))
+    _run_cli(oc.REF_STAR, os.path.join(golden, "idx"), [f1, f2], str(tmp_path / "ref") + "/", threads=1)
+    _run_cli(oc.ORACLE_CLI, os.path.join(golden, "idx"), [f1, f2], str(tmp_path / "ora") + "/", threads=2)
+    assert cf.sam_body(str(tmp_path / "ora" / "Aligned.out.sam")) == cf.sam_body(str(tmp_path / "ref" / "Aligned.out.sam"))
+    assert open(str(tmp_path / "ora" / "SJ.out.tab"), "rb").read() == open(str(tmp_path / "ref" / "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(str(tmp_path / "ora" / "Log.final.out")) == cf.log_counters(str(tmp_path / "ref" / "Log.final.out"))

@@ -46,4 +46,19 @@ for name in ["nP", "saEnum", "nodes", "leaves", "compare"]:
     q = np.percentile(x, [50, 90, 99, 99.9, 100])
     print("%8s mean %.1f  p50 %.0f p90 %.0f p99 %.0f p99.9 %.0f max %.0f | slow-path reads mean %.1f (n=%d) | share of total work in slow reads %.3f"
           % (name, x.mean(), q[0], q[1], q[2], q[3], q[4], x[slow].mean() if slow.any() else 0, slow.sum(), x[slow].sum() / max(1, x.sum())))
-eng.close()
+eng.close() if not os.environ.get("ANALYZE_LIGHT") else eng.close()
+
+# ---- throughput of the light reads alone (tail excluded): keeps only reads below the p-th percentile of nA
+if os.environ.get("ANALYZE_LIGHT"):
+    for pct in (90, 98, 99.5):
+        thr = np.percentile(info["nA"], pct)
+        keep = np.nonzero(info["nA"] <= thr)[0]
+        m1k, m2k = m1[keep], m2[keep]
+        seq2, off2, n2, _ = sb.pack_reads([m1k, m2k])
+        eng = sb.Engine(lib, index, max_reads=n2)
+        eng.upload(seq2, off2, n2, nm)
+        for k in range(2):
+            st = eng.map_resident()
+        print("light reads <= p%.1f of nA (nA<=%d): n=%d  seed %.1f ms  fast stitch %.1f ms  tiers %.1f ms -> %.0f pairs/s (fast stitch only %.0f); nodes %d slow %d"
+              % (pct, thr, n2, st.ms_seed, st.ms_stitch, st.ms_window, n2 / st.ms_total * 1e3, n2 / st.ms_stitch * 1e3, st.stitch_nodes, st.slow_path_reads))
+        eng.close()
