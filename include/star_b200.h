@@ -212,6 +212,9 @@ typedef struct star_chunk_stats {
     uint64_t sa_enumerated;
     uint64_t stitch_nodes, stitch_leaves;
     uint64_t slow_path_reads;
+    uint64_t heavy_reads;   /* reads stitched by the warp-per-read kernel */
+    float ms_heavy;         /* time of that kernel inside ms_stitch */
+    float pad_;
 } star_chunk_stats_t;
 
 typedef struct star_ctx star_ctx_t;
@@ -241,6 +244,8 @@ int star_gpu_download_results(star_ctx_t* ctx, star_align_batch_t* out);
  * multNminL u32, Nsplit u16, split1_0 u16, mmTotal u32, flags u32, then 8 x u32 work counters: searches, saiWords, compareCalls,
  * basesExamined, saEnumerated, stitchNodes, stitchLeaves, slowPath) */
 int star_gpu_debug_read_info(star_ctx_t* ctx, void* dst, uint64_t bytes);
+/* analysis helper: per-phase cycle sums of the stitch kernels (32 x uint64), reset on read */
+int star_gpu_debug_prof(star_ctx_t* ctx, uint64_t* out32);
 
 void star_gpu_destroy(star_ctx_t* ctx);
 const char* star_gpu_last_error(void);

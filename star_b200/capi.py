@@ -61,7 +61,8 @@ class AlignBatch(C.Structure):
 class ChunkStats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_prep", "ms_seed", "ms_window", "ms_stitch", "ms_pack", "ms_d2h", "ms_total")] + \
                [(n, C.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "n_kernel_launches", "mmp_searches", "mmp_sai_words", "mmp_compare_calls",
-                                          "mmp_bases_examined", "sa_enumerated", "stitch_nodes", "stitch_leaves", "slow_path_reads")]
+                                          "mmp_bases_examined", "sa_enumerated", "stitch_nodes", "stitch_leaves", "slow_path_reads", "heavy_reads")] + \
+               [("ms_heavy", C.c_float), ("pad_", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -21,9 +21,22 @@ namespace starb {
 // kernels (seed.cu, stitch.cu)
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
 __global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
+struct HeavyArgs {
+    u8* pool; u64 poolBytes; unsigned long long* bump;
+    u64* readOff;
+    u32* list; u32* count;
+    u32 estLimit;
+};
+struct HeavyScratch {
+    u32 maxTasks, maxBlocks, maxWin;
+    u64 bytesPerWarp;
+};
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
-                              star_read_result_t*, star_align_t*, const u32*, u32);
+                              star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
+__global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
+                                    star_read_result_t*, star_align_t*, u32, u8*, HeavyScratch);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
+__global__ void prof_read_kernel(unsigned long long*, int);
 __global__ void pack_kernel(const star_read_result_t*, const u64*, const star_align_t*, u32, u32, star_align_t*);
 __global__ void scan_kernel(star_read_result_t*, u64*, u32, u64*);
 __global__ void reduce_counters_kernel(const ReadInfo*, u32, WorkCounters*);
@@ -76,6 +89,14 @@ struct star_ctx {
     u32 *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_order = nullptr;
     void* d_sortTmp = nullptr; size_t sortTmpBytes = 0;
     WorkCounters* d_wc = nullptr;
+    // heavy-read path (warp per read)
+    u8* d_heavyPool = nullptr; u64 heavyPoolBytes = 0;
+    unsigned long long* d_heavyBump = nullptr;     // [0] pool bump, [1] (u32) heavy count
+    u64* d_heavyOff = nullptr;
+    u32* d_heavyList = nullptr;
+    u8* d_heavyScratch = nullptr;
+    u32 heavyEst = 1024; u32 heavyMaxTasks = 8192, heavyMaxBlocks = 4096;
+    u64 heavyScratchBytes = 0; u64 lastHeavy = 0;
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
     // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
@@ -84,7 +105,7 @@ struct star_ctx {
     // state of the resident chunk
     u32 nReads = 0, nMates = 1, stride = 0, smemStride = 0;
     u64 nAligns = 0;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[12];
     star_chunk_stats_t last;
 };
 
@@ -292,6 +313,18 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     CK(cub::DeviceRadixSort::SortPairs(nullptr, c->sortTmpBytes, c->d_keys, c->d_keys2, c->d_vals, c->d_order, (int)N));
     CK(cudaMalloc(&c->d_sortTmp, c->sortTmpBytes + 64));
     c->owned.push_back(c->d_sortTmp);
+    c->heavyEst = envU32("STAR_B200_HEAVY_EST", 1024);
+    c->heavyMaxTasks = envU32("STAR_B200_HEAVY_TASKS", 8192);
+    c->heavyMaxBlocks = envU32("STAR_B200_HEAVY_BLOCKS", 4096);
+    if (c->heavyEst) {
+        c->heavyPoolBytes = (u64)envU32("STAR_B200_HEAVY_POOL_MB", 0) << 20;
+        if (!c->heavyPoolBytes) c->heavyPoolBytes = std::min<u64>(8ULL << 30, std::max<u64>(64ULL << 20, (u64)N * 4096));
+        CK(cudaMalloc((void**)&c->d_heavyPool, c->heavyPoolBytes));
+        c->owned.push_back(c->d_heavyPool);
+        if (devAlloc(c, &c->d_heavyBump, 4)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &c->d_heavyOff, N)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &c->d_heavyList, N)) return STAR_EXIT_RUNTIME;
+    }
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
     c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 4);
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
@@ -302,6 +335,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     }
     CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(stitch_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = c;
     return 0;
 }
@@ -353,6 +387,46 @@ int star_gpu_upload_chunk(star_ctx_t* c, const star_read_batch_t* in) {
     return 0;
 }
 
+// Runs the warp-per-read heavy kernel over the reads the preceding stitch_kernel pass exported (if any).
+static int runHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, u32 smemStride) {
+    if (!c->heavyEst) return 0;
+    u32 nHeavy = 0;
+    CK(cudaMemcpyAsync(&nHeavy, (u32*)(c->d_heavyBump + 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->lastHeavy += nHeavy;
+    if (nHeavy == 0) return 0;
+    HeavyScratch hs;
+    hs.maxTasks = c->heavyMaxTasks; hs.maxBlocks = c->heavyMaxBlocks; hs.maxWin = caps.maxW;
+    const u32 W1 = (hs.maxWin + 2) & ~1u;
+    hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + 255) & ~255ULL;
+    const u32 warps = (u32)gridBlocks * 4;
+    const u64 need = (u64)warps * hs.bytesPerWarp;
+    if (need > c->heavyScratchBytes) {
+        if (c->d_heavyScratch) cudaFree(c->d_heavyScratch);
+        CK(cudaMalloc((void**)&c->d_heavyScratch, need));
+        c->heavyScratchBytes = need;
+    }
+    // deterministic, heaviest-first order is not needed for exactness; sort the list so that runs are reproducible
+    std::vector<u32> list(nHeavy);
+    CK(cudaMemcpy(list.data(), c->d_heavyList, (size_t)nHeavy * 4, cudaMemcpyDeviceToHost));
+    std::sort(list.begin(), list.end());
+    CK(cudaMemcpy(c->d_heavyList, list.data(), (size_t)nHeavy * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    const u32 smem = 4 * (2 * smemStride + 16);
+    stitch_heavy_kernel<<<gridBlocks, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, nHeavy, c->d_heavyList, c->d_heavyOff,
+                                                            c->d_heavyPool, c->d_counter, arenas, caps, c->d_results, c->d_staged, smemStride,
+                                                            c->d_heavyScratch, hs);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static HeavyArgs heavyArgs(star_ctx* c) {
+    HeavyArgs hv;
+    hv.pool = c->d_heavyPool; hv.poolBytes = c->heavyPoolBytes; hv.bump = c->d_heavyBump; hv.readOff = c->d_heavyOff;
+    hv.list = c->d_heavyList; hv.count = (u32*)(c->d_heavyBump + 1); hv.estLimit = c->heavyEst;
+    return hv;
+}
+
 int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     CK(cudaSetDevice(c->device));
     star_chunk_stats_t& st = c->last;
@@ -383,10 +457,14 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     order_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, c->d_keys, c->d_vals);
     CK(cub::DeviceRadixSort::SortPairs(c->d_sortTmp, c->sortTmpBytes, c->d_keys, c->d_keys2, c->d_vals, c->d_order, (int)n, 0, 32, c->stream));
     g_launches += 4;   // key kernel + cub's histogram/onesweep passes (library kernels, not counted as ours beyond the launch)
+    c->lastHeavy = 0;
+    if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
     stitch_kernel<<<c->gridStitch, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, n, nullptr, c->d_counter,
-                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_order, c->smemStride);
+                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_order, c->smemStride, heavyArgs(c));
     g_launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[9], c->stream));
+    if (runHeavy(c, c->fast, c->d_arenaFast, c->gridStitch, c->smemStride)) return STAR_EXIT_RUNTIME;
     CK(cudaEventRecord(c->ev[8], c->stream));
     // ---- overflow tiers: reads that exceeded the caps of a tier are redone in the next one; the last tier has the reference's own limits ----
     for (int tier = 0; tier < 2; tier++) {
@@ -418,10 +496,12 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
                                                                     c->d_list + lo, c->d_counter, c->d_wc, c->smemStride);
             g_launches++;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+            if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
             stitch_kernel<<<grid, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, m, c->d_list + lo,
-                                                                 c->d_counter, T.arena, T.caps, c->d_results, c->d_staged, nullptr, c->smemStride);
+                                                                 c->d_counter, T.arena, T.caps, c->d_results, c->d_staged, nullptr, c->smemStride, heavyArgs(c));
             g_launches++;
             CK(cudaGetLastError());
+            if (runHeavy(c, T.caps, T.arena, grid, c->smemStride)) return STAR_EXIT_RUNTIME;
         }
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
@@ -458,7 +538,9 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     float ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); st.ms_prep = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st.ms_seed = ms;
-    cudaEventElapsedTime(&ms, c->ev[4], c->ev[8]); st.ms_stitch = ms;     // fast path (all reads)
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[8]); st.ms_stitch = ms;     // first tier: light kernel + heavy (warp-per-read) kernel
+    cudaEventElapsedTime(&ms, c->ev[9], c->ev[8]); st.ms_heavy = ms;      // of which: heavy kernel
+    st.heavy_reads = c->lastHeavy;
     cudaEventElapsedTime(&ms, c->ev[8], c->ev[5]); st.ms_window = ms;     // slow path (reads redone with the reference's limits)
     cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); st.ms_pack = ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[6]); st.ms_total = ms;
@@ -508,6 +590,18 @@ int star_gpu_debug_read_info(star_ctx_t* c, void* dst, uint64_t bytes) {
     uint64_t need = (uint64_t)c->nReads * sizeof(ReadInfo);
     if (bytes < need) { g_err = "star_gpu_debug_read_info: buffer too small"; return STAR_EXIT_RUNTIME; }
     CK(cudaMemcpy(dst, c->d_info, need, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// debug / analysis: cycle accounting of the stitch kernels (32 x u64; see stitch.cu g_prof); resets the counters
+int star_gpu_debug_prof(star_ctx_t* c, uint64_t* out32) {
+    CK(cudaSetDevice(c->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 32 * 8));
+    prof_read_kernel<<<1, 32, 0, c->stream>>>(d, 1);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out32, d, 32 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return 0;
 }
 

@@ -27,6 +27,12 @@
 namespace starb {
 
 #define SJA_NONE 0xFFFFFFFFu
+
+// optional cycle accounting (per warp, lane 0 adds at kernel end): light kernel phases [0..8], heavy kernel [16..]
+__device__ unsigned long long g_prof[32];
+#define PROF_ADD(slot, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
+
+#define LOCI_PER_STEP 1          // SA loci handled per lockstep step (their SA words are loaded back to back, latency overlapped)
 #define STAR_DFS_MAX_DEPTH 52   // seedPerWindowNmax (<=50 on the local-memory fast build) + 2
 
 struct Frame {
@@ -70,6 +76,13 @@ struct Lane {
     int leafScore;       // pending leaf (set by dfsStep)
     u32 leafR2;
     u64 leafG2;
+    u64 inclMask;        // bit k set <=> seed k of the window is included on the current DFS path
+    u32 forceDepth;      // heavy path: the first forceDepth include/exclude decisions are fixed (prefix sub-tree task)
+    u32 forceBits;       // bit (forceDepth-1-k) set <=> seed k is EXCLUDED (so that ascending task id = DFS order, include first)
+    // per-read stitching state (ReadAlign_stitchPieces.cpp:262-350)
+    u32 trNtotal, nW1;
+    int bestPool, bestScore;
+    u64 bestGLength;
 };
 
 __device__ __forceinline__ u8 Gat(const Lane& ln, u64 pos) { return __ldg(ln.ix->G + (i64)pos); }
@@ -438,8 +451,10 @@ __device__ int log2Score(const DevIndex& ix, u64 gLen) {
     return v;
 }
 
-// leaf of stitchWindowAligns (stitchWindowAligns.cpp:19-306): finalize the transcript held in ln.cur and record it
-__device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str, u32 roStr, u16* wTr, u16* nWinTr) {
+// Leaf of stitchWindowAligns, part 1 (stitchWindowAligns.cpp:19-243): extend both ends, apply the filters, compute the final score.
+// Pure function of the DFS path (reads no per-read mutable state), so the heavy path can evaluate leaves of different sub-trees
+// in parallel.  Result in ln.leaf (h.maxScore, h.iFrag set).  Returns false when a filter drops the transcript.
+__device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str, u32 roStr) {
     const star_params_t& P = *ln.P;
     const DevIndex& g = *ln.ix;
     DevTr& t = *ln.leaf;
@@ -478,7 +493,7 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
     }
     const u32 nEx = h.nExons;
     if (!P.alignSoftClipAtReferenceEnds &&
-        ((t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R) > (g.chrStart[Chr] + g.chrLength[Chr]) || t.ex[0].G < (g.chrStart[Chr] + t.ex[0].R))) return;
+        ((t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R) > (g.chrStart[Chr] + g.chrLength[Chr]) || t.ex[0].G < (g.chrStart[Chr] + t.ex[0].R))) return false;
     h.rLength = 0;
     for (u32 i = 0; i < nEx; i++) h.rLength += t.ex[i].L;
     h.gLength = tG2 + 1 - h.gStart;
@@ -487,13 +502,13 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
             if (t.ex[isj].annot == 1) {
                 if ((t.ex[isj].L < P.alignSJDBoverhangMin && (isj == 0 || t.ex[isj - 1].canon == -3 || (t.ex[isj - 1].annot == 0 && t.ex[isj - 1].canon >= 0)))
                     || (t.ex[isj + 1].L < P.alignSJDBoverhangMin && (isj == nEx - 2 || t.ex[isj + 1].canon == -3 || (t.ex[isj + 1].annot == 0 && t.ex[isj + 1].canon >= 0))))
-                    return;
+                    return false;
             } else {
-                if (t.ex[isj].L < P.alignSJoverhangMin + t.ex[isj].shL || t.ex[isj + 1].L < P.alignSJoverhangMin + t.ex[isj].shR) return;
+                if (t.ex[isj].L < P.alignSJoverhangMin + t.ex[isj].shL || t.ex[isj + 1].L < P.alignSJoverhangMin + t.ex[isj].shR) return false;
             }
         }
     }
-    if (nEx > 1 && t.ex[nEx - 2].annot == 1 && t.ex[nEx - 1].L < P.alignSJDBoverhangMin) return;
+    if (nEx > 1 && t.ex[nEx - 2].annot == 1 && t.ex[nEx - 1].L < P.alignSJDBoverhangMin) return false;
     u32 sjN = 0, im[3] = {0, 0, 0};
     for (u32 iex = 0; iex + 1 < nEx; iex++) {
         if (t.ex[iex].canon >= 0) { sjN++; im[t.ex[iex].sjStr]++; }
@@ -501,19 +516,19 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
     if (im[1] > 0 && im[2] == 0) h.sjMotifStrand = 1;
     else if (im[1] == 0 && im[2] > 0) h.sjMotifStrand = 2;
     else h.sjMotifStrand = 0;
-    if (im[1] > 0 && im[2] > 0 && P.outFilterIntronStrandsRemoveInconsistent) return;
-    if (sjN > 0 && h.sjMotifStrand == 0 && P.outSAMstrandFieldType == 1) return;
+    if (im[1] > 0 && im[2] > 0 && P.outFilterIntronStrandsRemoveInconsistent) return false;
+    if (sjN > 0 && h.sjMotifStrand == 0 && P.outSAMstrandFieldType == 1) return false;
     if (P.outFilterIntronMotifs == 1) {
-        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0) return;
+        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0) return false;
     } else if (P.outFilterIntronMotifs == 2) {
-        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0 && t.ex[iex].annot == 0) return;
+        for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0 && t.ex[iex].annot == 0) return false;
     }
     {
         u64 nsj = 0, exl = 0;
         for (u32 iex = 0; iex < nEx; iex++) {
             exl += t.ex[iex].L;
             if (iex == nEx - 1 || t.ex[iex].canon == -3) {
-                if (nsj > 0 && (exl < P.alignSplicedMateMapLmin || exl < (u64)(P.alignSplicedMateMapLminOverLmate * (double)ln.readLength[t.ex[iex].iFrag]))) return;
+                if (nsj > 0 && (exl < P.alignSplicedMateMapLmin || exl < (u64)(P.alignSplicedMateMapLminOverLmate * (double)ln.readLength[t.ex[iex].iFrag]))) return false;
                 exl = 0; nsj = 0;
             } else if (t.ex[iex].canon >= 0) {
                 nsj++;
@@ -521,14 +536,14 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
         }
     }
     if (t.ex[0].iFrag != t.ex[nEx - 1].iFrag) {
-        if (t.ex[nEx - 1].G + t.ex[nEx - 1].L <= t.ex[0].G) return;
+        if (t.ex[nEx - 1].G + t.ex[nEx - 1].L <= t.ex[0].G) return false;
         u32 iexM2 = nEx;
         for (u32 iex = 0; iex + 1 < nEx; iex++) {
             if (t.ex[iex].canon == -3) { iexM2 = iex + 1; break; }
         }
         if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[iexM2].G) {
-            if (t.ex[0].G > t.ex[iexM2].G + t.ex[0].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return;
-            if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return;
+            if (t.ex[0].G > t.ex[iexM2].G + t.ex[0].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return false;
+            if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return false;
             u32 iex1 = 1, iex2 = iexM2 + 1;
             for (; iex1 < iexM2; iex1++) {
                 if (t.ex[iex1].G >= t.ex[iex2 - 1].G + t.ex[iex2 - 1].L) break;
@@ -536,7 +551,7 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
             while (iex1 < iexM2 && iex2 < nEx) {
                 if (t.ex[iex1 - 1].canon < 0) { iex1++; continue; }
                 if (t.ex[iex2 - 1].canon < 0) { iex2++; continue; }
-                if ((t.ex[iex1].G != t.ex[iex2].G) || ((t.ex[iex1 - 1].G + t.ex[iex1 - 1].L) != (t.ex[iex2 - 1].G + t.ex[iex2 - 1].L))) return;
+                if ((t.ex[iex1].G != t.ex[iex2].G) || ((t.ex[iex1 - 1].G + t.ex[iex1 - 1].L) != (t.ex[iex2 - 1].G + t.ex[iex2 - 1].L))) return false;
                 iex1++; iex2++;
             }
         }
@@ -546,11 +561,20 @@ __device__ void finalizeLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32
         Score = Score > 0 ? Score : 0;
     }
     h.maxScore = Score;
-    if (t.ex[0].iFrag == t.ex[nEx - 1].iFrag) {
-        h.iFrag = (signed char)t.ex[0].iFrag;
+    h.iFrag = (t.ex[0].iFrag == t.ex[nEx - 1].iFrag) ? (signed char)t.ex[0].iFrag : (signed char)-1;
+    return true;
+}
+
+// Leaf, part 2 (stitchWindowAligns.cpp:228-304): maxScoreMate update, record test, dedup by blocksOverlap, ordered insert.
+// Strictly sequential in DFS order within a window and in window order within a read.
+__device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
+    const star_params_t& P = *ln.P;
+    DevTr& t = *ln.leaf;
+    TrHead& h = t.h;
+    const u32 nEx = h.nExons;
+    const int Score = h.maxScore;
+    if (h.iFrag >= 0) {
         if (ln.maxScoreMate[h.iFrag] < Score) ln.maxScoreMate[h.iFrag] = Score;
-    } else {
-        h.iFrag = -1;
     }
     int wBest = ln.pool[wTr[0]].h.maxScore;
     if (Score + P.outFilterMultimapScoreRange >= wBest || (h.iFrag >= 0 && Score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[h.iFrag])) {
@@ -601,6 +625,7 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
     z.sjMotifStrand = 0; z.primaryFlag = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
     ln.cur->h = z;
     ln.sp = 0;
+    ln.inclMask = 0;
     Frame& f = ln.stack[0];
     f.iA = 0; f.Score = 0; f.tR2 = 0; f.tG2 = 0; f.phase = 0;
 }
@@ -623,6 +648,14 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
                 if (isLeaf) return DFS_LEAF;
                 continue;
             }
+            const bool forced = f.iA < ln.forceDepth;
+            if (forced && ((ln.forceBits >> (ln.forceDepth - 1 - f.iA)) & 1u)) {   // this level is fixed to "exclude"
+                f.phase = 2;
+                Frame& c = st[ln.sp + 1];
+                c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
+                ln.sp++;
+                continue;
+            }
             const Seed s = WA[f.iA];
             f.h = t->h;
             if (t->h.nExons > 0) f.last = t->ex[t->h.nExons - 1];
@@ -638,13 +671,17 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
                 dScore = s.Length;
                 t->h.nMatch = s.Length;
             }
-            f.phase = 1;
+            f.phase = forced ? 2 : 1;   // a forced include never explores its exclude branch
             if (dScore > -1000000) {
                 if (s.Nrep == 1) t->h.nUnique++;
                 if (s.Anchor > 0) t->h.nAnchor++;
+                ln.inclMask |= 1ULL << f.iA;
                 Frame& c = st[ln.sp + 1];
                 c.iA = f.iA + 1; c.Score = f.Score + dScore; c.tR2 = (u32)s.rStart + s.Length - 1; c.tG2 = s.gStart + s.Length - 1; c.phase = 0;
                 ln.sp++;
+            } else if (forced) {
+                ln.sp = -1;             // the fixed prefix is not a valid path: this sub-tree is empty
+                return DFS_DONE;
             }
             return DFS_CONTINUE;
         } else if (f.phase == 1) {
@@ -652,6 +689,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             // initialised to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
             if (f.h.nExons > 0) t->ex[f.h.nExons - 1] = f.last;
             t->h = f.h;
+            ln.inclMask &= ~(1ULL << f.iA);
             f.phase = 2;
             Frame& c = st[ln.sp + 1];
             c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
@@ -706,7 +744,7 @@ __device__ int createExtendWindowsWithAlign(Lane& ln, u64 a1, u32 aStr) {
     if (flagMergeLeft) { iWin = left; iBinLeft = W[left].gStart; }
     if (flagMergeRight) { iBinRight = W[right].gEnd; if (!flagMergeLeft) iWin = right; }
     if (!flagMergeLeft && !flagMergeRight) {
-        if (nW >= ln.caps.maxW) { ln.overflow = 1; return 101; }
+        if (nW >= ln.caps.maxW) { ln.overflow = 1; return 101; }   // reason 1: windows
         Window nw;
         nw.gStart = (u32)aBin; nw.gEnd = (u32)aBin; nw.Chr = chrOfBin(ln, aBin); nw.nWA = 0; nw.WALrec = 0; nw.Str = (u8)aStr;
         nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
@@ -806,11 +844,180 @@ __device__ void exportAlign(const DevTr& t, u32 Chr, u32 Str, u32 roStr, u32 Lre
     o->gStart = t.h.gStart; o->gLength = t.h.gLength; o->cStart = t.h.gStart - g.chrStart[Chr];
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Per-read stitching bookkeeping shared by the light kernel (one lane per read) and the heavy kernel (one warp per read).
+
+__device__ __forceinline__ void readBegin(Lane& ln, const ReadInfo& ri) {
+    ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.overflow = 0;
+    ln.Lread = ri.Lread; ln.readLength[0] = ri.readLength[0]; ln.readLength[1] = ri.readLength[1];
+    ln.outFilterMismatchNmaxTotal = ri.outFilterMismatchNmaxTotal;
+    ln.maxScoreMate[0] = 0; ln.maxScoreMate[1] = 0;
+    ln.trNtotal = 0; ln.nW1 = 0; ln.bestPool = -1; ln.bestScore = 0; ln.bestGLength = 0;
+    ln.forceDepth = 0; ln.forceBits = 0;
+}
+
+// start of a window's stitching (ReadAlign_stitchPieces.cpp:281-294).  Returns 0 ok, 1 reference's per-read transcript budget reached
+// (:288-292, remaining windows are skipped), 2 this lane's pool is full (overflow tier).
+__device__ __forceinline__ int windowBegin(Lane& ln, u16*& wTr, u16& nWinTr) {
+    const star_params_t& P = *ln.P;
+    if (ln.trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) return 1;
+    if (ln.trNtotal + 1 > ln.caps.maxTr) return 2;
+    wTr = ln.trPtr + ln.trNtotal;
+    nWinTr = 0;
+    // *(trAll[iW1][0]) = trA : the window-best comparison starts from maxScore 0 (:293)
+    ln.pool[wTr[0]].h.maxScore = 0;
+    ln.pool[wTr[0]].h.nExons = 0;
+    return 0;
+}
+
+// end of a window (:324-331)
+__device__ __forceinline__ void windowEnd(Lane& ln, u32 Chr, u32 Str, const u16* wTr, u16 nWinTr) {
+    if (nWinTr == 0) return;
+    const TrHead& b = ln.pool[wTr[0]].h;
+    if (b.maxScore > ln.bestScore || (b.maxScore == ln.bestScore && b.gLength < ln.bestGLength)) {
+        ln.bestPool = wTr[0]; ln.bestScore = b.maxScore; ln.bestGLength = b.gLength;
+    }
+    ln.winBase[ln.nW1] = (u16)ln.trNtotal;
+    ln.winN[ln.nW1] = nWinTr;
+    ln.win[ln.nW1].Chr = Chr;      // compact (iW1 <= iW): Chr/Str of the windows that have transcripts
+    ln.win[ln.nW1].Str = (u8)Str;
+    ln.trNtotal += nWinTr;
+    ln.nW1++;
+}
+
+// multMapSelect (ReadAlign_multMapSelect.cpp:8-95) + mappedFilter (ReadAlign_mappedFilter.cpp:3-20) + export of the selected alignments
+__device__ void selectExport(Lane& ln, ReadInfo& ri, u32 i, u32 mapMarker, u32 bestRLength, star_read_result_t* __restrict__ results,
+                             star_align_t* __restrict__ staged, ReadInfo* __restrict__ info) {
+    const star_params_t& P = *ln.P;
+    const DevIndex& ix = *ln.ix;
+    const u32 Lread = ri.Lread;
+    star_read_result_t res;
+    res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+    res.bestRLength = 0; res.Lread = Lread; res.bestTr = 0;
+    ri.cSaEnum += (u32)ln.saEnum; ri.cNodes += (u32)ln.nodes; ri.cLeaves += (u32)ln.leaves;
+    if (ln.overflow) {   // a cap of this tier was hit: flag the read for the next tier
+        ri.flags |= 1 | (ln.overflow << 8);   // bits 8..: reason (analysis only)
+        ri.cSaEnum = 0; ri.cNodes = 0; ri.cLeaves = 0;
+        info[i] = ri;
+        results[i] = res;
+        return;
+    }
+    u32 nWfinal = ln.nW1;
+    const int bestScore = ln.bestScore;
+    if (mapMarker == 0 && bestScore == 0) { mapMarker = STAR_MARKER_NO_GOOD_WINDOW; }   // stitchPieces.cpp:344-348
+    if (bestScore == 0) nWfinal = 0;
+    u32 bestNMM = 0, bestNMatch = 0;
+    if (ln.bestPool >= 0) {
+        const TrHead& b = ln.pool[ln.bestPool].h;
+        bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
+    }
+    u32 nTr = 0;
+    for (u32 w = 0; w < nWfinal; w++) {
+        const u16* wt = ln.trPtr + ln.winBase[w];
+        for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
+            if (ln.pool[wt[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
+        }
+    }
+    int unmapType = -1;
+    if (nWfinal == 0) {
+        unmapType = 0;
+    } else if ((bestScore < P.outFilterScoreMin) || (bestScore < (int)(P.outFilterScoreMinOverLread * (double)(Lread - 1)))
+               || (bestNMatch < P.outFilterMatchNmin) || (bestNMatch < (u64)(P.outFilterMatchNminOverLread * (double)(Lread - 1)))) {
+        unmapType = 1;
+    } else if ((bestNMM > ri.outFilterMismatchNmaxTotal) || (double(bestNMM) / double(bestRLength) > P.outFilterMismatchNoverLmax)) {
+        unmapType = 2;
+    } else if (nTr > P.outFilterMultimapNmax) {
+        unmapType = 3;
+    }
+    res.unmapType = unmapType; res.nTr = nTr; res.mapMarker = mapMarker; res.bestScore = bestScore; res.bestNMM = bestNMM; res.bestRLength = bestRLength;
+    if (unmapType < 0) {
+        // trMult order = window order then in-window rank (:26-44); primary flag rules (:56-91)
+        star_align_t* o = staged + (u64)i * ln.caps.nOut;
+        u32 kOut = 0;
+        u32 bestK = 0;
+        for (u32 w = 0; w < nWfinal; w++) {
+            const u16* wt = ln.trPtr + ln.winBase[w];
+            for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
+                DevTr& t = ln.pool[wt[iTr]];
+                if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
+                    t.h.primaryFlag = 0;
+                    exportAlign(t, ln.win[w].Chr, ln.win[w].Str, ln.win[w].Str, Lread, ix, o + kOut);
+                    if ((int)wt[iTr] == ln.bestPool) bestK = kOut;
+                    kOut++;
+                }
+            }
+        }
+        if (nTr == 1) {
+            o[0].primaryFlag = 1;
+        } else {
+            u32 nbest = 0;
+            if (P.outSAMmultNmax != (u64)-1) {   // bring the best alignments to the top (:60-67)
+                for (u32 itr = 0; itr < nTr; itr++) {
+                    if (o[itr].maxScore == bestScore) {
+                        if (itr != nbest) { star_align_t tmp = o[itr]; o[itr] = o[nbest]; o[nbest] = tmp; }
+                        if (bestK == itr) bestK = nbest; else if (bestK == nbest) bestK = itr;
+                        ++nbest;
+                    }
+                }
+            }
+            if (P.outSAMprimaryFlagAllBestScore) {
+                for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
+            } else if (P.outSAMmultNmax != (u64)-1) {
+                o[0].primaryFlag = 1;
+            } else {
+                o[bestK].primaryFlag = 1;
+            }
+        }
+        res.nTrOut = nTr;
+        res.bestTr = bestK;
+    }
+    results[i] = res;
+    info[i] = ri;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Heavy-read hand-over.  A read whose windows hold many seeds (an upper bound of its DFS size is sum_w 2^nWA_w) is not
+// stitched by its lane: the lane exports the windows + seeds to a pool in HBM and the read is stitched by a whole warp in
+// stitch_heavy_kernel.  Record layout (8-byte aligned): u32 nWin, u32 nSeedsTotal, then nWin x {u32 Chr, u16 nWA, u8 Str, u8 pad},
+// then the seeds of the windows back to back (24 B each).
+struct HeavyWin { u32 Chr; u16 nWA; u8 Str; u8 pad; };
+
+__device__ bool exportHeavy(Lane& ln, u8* __restrict__ heavyPool, u64 heavyPoolBytes, unsigned long long* __restrict__ heavyBump, u64& offOut) {
+    u32 nWin = 0, nSeeds = 0;
+    for (u32 w = 0; w < ln.nW; w++) if (ln.win[w].nWA > 0) { nWin++; nSeeds += ln.win[w].nWA; }
+    u64 bytes = 8 + (u64)nWin * sizeof(HeavyWin) + (u64)nSeeds * sizeof(Seed);
+    bytes = (bytes + 15) & ~15ULL;
+    u64 off = atomicAdd(heavyBump, (unsigned long long)bytes);
+    if (off + bytes > heavyPoolBytes) return false;
+    u8* p = heavyPool + off;
+    ((u32*)p)[0] = nWin; ((u32*)p)[1] = nSeeds;
+    HeavyWin* hw = (HeavyWin*)(p + 8);
+    Seed* sd = (Seed*)(p + 8 + (u64)nWin * sizeof(HeavyWin));
+    u32 k = 0, q = 0;
+    for (u32 w = 0; w < ln.nW; w++) {
+        const Window& W = ln.win[w];
+        if (W.nWA == 0) continue;
+        HeavyWin h; h.Chr = W.Chr; h.nWA = W.nWA; h.Str = W.Str; h.pad = 0;
+        hw[k++] = h;
+        const Seed* src = ln.wa + (u64)w * ln.caps.spw;
+        for (u32 a = 0; a < W.nWA; a++) sd[q++] = src[a];
+    }
+    offOut = off;
+    return true;
+}
+
 // Warp-lockstep state machine.  Every lane owns one read at a time (persistent lanes, ticket counter) and advances it one
 // unit of work per loop iteration; lanes of a warp that are in the same phase execute that phase's step together, so the
-// dominant units (one stitchAlignToTranscript call per DFS node, one leaf finalisation) run with many active lanes even though
-// the per-read work is heavy-tailed (1 % of the reads hold most of the DFS nodes).  A read never waits for its warp neighbours.
+// dominant units (one stitchAlignToTranscript call per DFS node, one leaf finalisation) run with many active lanes.
+// A read never waits for its warp neighbours.
 enum { PH_FETCH = 0, PH_WIN, PH_FLANK, PH_ASSIGN, PH_NEXTWIN, PH_NODE, PH_LEAF, PH_SELECT, PH_DONE };
+
+struct HeavyArgs {
+    u8* pool; u64 poolBytes; unsigned long long* bump;   // export pool
+    u64* readOff;                                         // per read: offset of its record in the pool
+    u32* list; u32* count;                                // heavy read list (read ids) and its length
+    u32 estLimit;                                         // a read is heavy when sum_w 2^min(nWA_w,20) exceeds this (0 = heavy path off)
+};
 
 #ifndef STITCH_MIN_BLOCKS
 #define STITCH_MIN_BLOCKS 2
@@ -819,9 +1026,9 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
                                                      ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nReads,
                                                      const u32* __restrict__ readList, u32* __restrict__ counter, u8* __restrict__ arenas,
                                                      Caps caps, star_read_result_t* __restrict__ results, star_align_t* __restrict__ staged,
-                                                     const u32* __restrict__ order, u32 smemStride) {
-    // readList != NULL : slow path, ticket k -> read readList[k], piece slab k
-    // order    != NULL : fast path, ticket k -> read order[k] (heaviest reads first), piece slab = read id
+                                                     const u32* __restrict__ order, u32 smemStride, HeavyArgs hv) {
+    // readList != NULL : overflow tier, ticket k -> read readList[k], piece slab k
+    // order    != NULL : first tier, ticket k -> read order[k] (heaviest reads first), piece slab = read id
     extern __shared__ u8 smem[];
     u8* R0 = smem + (size_t)threadIdx.x * 2 * smemStride;
     u8* R2 = R0 + smemStride;
@@ -852,12 +1059,13 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
     Piece p;
     p.SAstart = 0; p.rStart = 0; p.Length = 0; p.Nrep = 0; p.Dir = 0; p.iFrag = 0;
     bool tooManyAnchors = false;
-    u32 mapMarker = 0, nWfinal = 0, nW1 = 0, iW = 0, trNtotal = 0, Chr = 0, Str = 0, bestRLength = 0;
-    int bestPool = -1, bestScore = 0;
-    u64 bestGLength = 0;
+    u32 mapMarker = 0, iW = 0, Chr = 0, Str = 0, bestRLength = 0;
     u16* wTr = nullptr;
     u16 nWinTr = 0;
 
+    long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tPrev = clock64();
+#define PHASE_TICK(slot) do { long long tn_ = clock64(); pc[slot] += tn_ - tPrev; tPrev = tn_; } while (0)
     for (;;) {
         // ------------------------------------------------------------------ fetch the next read
         bool needCopy = false;
@@ -868,11 +1076,8 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
             } else {
                 i = readList ? readList[k] : (order ? order[k] : k);
                 ri = info[i];
-                ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.overflow = 0;
-                ln.Lread = ri.Lread; ln.readLength[0] = ri.readLength[0]; ln.readLength[1] = ri.readLength[1];
-                ln.outFilterMismatchNmaxTotal = ri.outFilterMismatchNmaxTotal;
-                ln.maxScoreMate[0] = 0; ln.maxScoreMate[1] = 0;
-                mapMarker = 0; nWfinal = 0; nW1 = 0; bestPool = -1; bestScore = 0; bestGLength = 0; bestRLength = 0;
+                readBegin(ln, ri);
+                mapMarker = 0; bestRLength = 0;
                 tooManyAnchors = false;
                 if (ri.flags) {   // seed kernel overflowed (bit0) or hit the fatal piece limit (bit1): the read is redone / reported elsewhere
                     star_read_result_t res;
@@ -912,6 +1117,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
             }
             __syncwarp();
         }
+        PHASE_TICK(0);
         // ------------------------------------------------------------------ window creation, one SA locus per step (:41-93)
         if (phase == PH_WIN) {
             if (iSA >= iSAend) {
@@ -923,29 +1129,38 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
                 if (iSA >= iSAend) phase = PH_FLANK;
             }
             if (phase == PH_WIN) {
-                ln.saEnum++;
-                u64 aLength = p.Length;
-                u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
-                iSA++;
-                u32 aStr = (u32)(a1 >> ix.GstrandBit);
-                a1 &= ix.GstrandMask;
-                if (p.Dir == 1 && aStr == 0) { aStr = 1; }
-                else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
-                else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                bool stopPiece = false;
-                if (a1 >= ix.sjGstart) {
-                    u64 a1D, aLengthD, a1A, aLengthA; u32 sj1;
-                    if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) {
-                        if (createExtendWindowsWithAlign(ln, a1D, aStr) == 101) stopPiece = true;
-                        else if (createExtendWindowsWithAlign(ln, a1A, aStr) == 101) stopPiece = true;
+                u64 raw[LOCI_PER_STEP];
+                u32 nl = (u32)(iSAend - iSA < LOCI_PER_STEP ? iSAend - iSA : LOCI_PER_STEP);
+#pragma unroll
+                for (u32 q = 0; q < LOCI_PER_STEP; q++) if (q < nl) raw[q] = packedGet(ix.SA, ix.saBits, iSA + q);
+                const u64 aLength = p.Length;
+#pragma unroll
+                for (u32 q = 0; q < LOCI_PER_STEP; q++) {
+                    if (q >= nl || ln.overflow) break;
+                    ln.saEnum++;
+                    iSA++;
+                    u64 a1 = raw[q];
+                    u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                    a1 &= ix.GstrandMask;
+                    if (p.Dir == 1 && aStr == 0) { aStr = 1; }
+                    else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
+                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                    bool stopPiece = false;
+                    if (a1 >= ix.sjGstart) {
+                        u64 a1D, aLengthD, a1A, aLengthA; u32 sj1;
+                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) {
+                            if (createExtendWindowsWithAlign(ln, a1D, aStr) == 101) stopPiece = true;
+                            else if (createExtendWindowsWithAlign(ln, a1A, aStr) == 101) stopPiece = true;
+                        }
+                    } else {
+                        if (createExtendWindowsWithAlign(ln, a1, aStr) == 101) stopPiece = true;
                     }
-                } else {
-                    if (createExtendWindowsWithAlign(ln, a1, aStr) == 101) stopPiece = true;
+                    if (stopPiece) { iSA = iSAend; break; }   // EXIT_createExtendWindowsWithAlign_TOO_MANY_WINDOWS breaks the loop of this piece only
                 }
-                if (stopPiece) iSA = iSAend;   // EXIT_createExtendWindowsWithAlign_TOO_MANY_WINDOWS breaks the loop of this piece only
                 if (ln.overflow) phase = PH_SELECT;
             }
         }
+        PHASE_TICK(1);
         // ------------------------------------------------------------------ flanks (:96-118)
         if (phase == PH_FLANK) {
             for (u32 iWin = 0; iWin < ln.nW; iWin++) {
@@ -963,6 +1178,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
             iP = 0; iSA = 0; iSAend = 0;
             phase = PH_ASSIGN;
         }
+        PHASE_TICK(2);
         // ------------------------------------------------------------------ seed -> window assignment, one SA locus per step (:129-185)
         if (phase == PH_ASSIGN) {
             if (iSA >= iSAend) {
@@ -970,184 +1186,363 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
                 else {
                     // init per-window stitching (:262-270)
                     if (tooManyAnchors) ln.nW = 0;   // assignAlignToWindow.cpp:77-81; ends as MARKER_NO_GOOD_WINDOW
-                    for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
-                    trNtotal = 0; iW = 0; nW1 = 0;
-                    phase = PH_NEXTWIN;
+                    bool heavy = false;
+                    if (hv.estLimit) {
+                        u64 est = 0;
+                        for (u32 w = 0; w < ln.nW; w++) { u32 a = ln.win[w].nWA; if (a) est += 1ULL << (a < 20 ? a : 20); }
+                        heavy = est > hv.estLimit;
+                    }
+                    if (heavy) {
+                        u64 off;
+                        if (exportHeavy(ln, hv.pool, hv.poolBytes, hv.bump, off)) {
+                            hv.readOff[i] = off;
+                            u32 q = atomicAdd(hv.count, 1u);
+                            hv.list[q] = i;
+                            ri.cSaEnum = (u32)ln.saEnum; ri.cNodes = 0; ri.cLeaves = 0;   // the heavy kernel adds its DFS work
+                            info[i] = ri;
+                            phase = PH_FETCH;
+                        } else {
+                            ln.overflow = 4;      // reason 4: export pool exhausted: next tier
+                            phase = PH_SELECT;
+                        }
+                    } else {
+                        for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+                        iW = 0;
+                        phase = PH_NEXTWIN;
+                    }
                 }
             }
             if (phase == PH_ASSIGN) {
-                ln.saEnum++;
-                u64 aNrep = p.Nrep, aLength = p.Length;
-                u32 aFrag = p.iFrag;
-                bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
-                u64 a1 = packedGet(ix.SA, ix.saBits, iSA);
-                iSA++;
-                u32 aStr = (u32)(a1 >> ix.GstrandBit);
-                a1 &= ix.GstrandMask;
-                u64 aRstart = p.rStart;
+                u64 raw[LOCI_PER_STEP];
+                u32 nl = (u32)(iSAend - iSA < LOCI_PER_STEP ? iSAend - iSA : LOCI_PER_STEP);
+#pragma unroll
+                for (u32 q = 0; q < LOCI_PER_STEP; q++) if (q < nl) raw[q] = packedGet(ix.SA, ix.saBits, iSA + q);
+                const u64 aNrep = p.Nrep, aLength = p.Length;
+                const u32 aFrag = p.iFrag;
+                const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
                 const u32 Lread = ln.Lread;
-                if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
-                else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
-                else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                if (a1 >= ix.sjGstart) {
-                    u64 a1D, aLengthD, a1A, aLengthA; u32 isj1;
-                    if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj1)) {
-                        if (!assignAlignToWindow(ln, a1D, aLengthD, aStr, aNrep, aFrag, aRstart, aAnchor, isj1)) tooManyAnchors = true;
-                        else if (!assignAlignToWindow(ln, a1A, aLengthA, aStr, aNrep, aFrag, aRstart + aLengthD, aAnchor, isj1)) tooManyAnchors = true;
+#pragma unroll
+                for (u32 q = 0; q < LOCI_PER_STEP; q++) {
+                    if (q >= nl) break;
+                    ln.saEnum++;
+                    iSA++;
+                    u64 a1 = raw[q];
+                    u32 aStr = (u32)(a1 >> ix.GstrandBit);
+                    a1 &= ix.GstrandMask;
+                    u64 aRstart = p.rStart;
+                    if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
+                    else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
+                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                    if (a1 >= ix.sjGstart) {
+                        u64 a1D, aLengthD, a1A, aLengthA; u32 isj1;
+                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj1)) {
+                            if (!assignAlignToWindow(ln, a1D, aLengthD, aStr, aNrep, aFrag, aRstart, aAnchor, isj1)) tooManyAnchors = true;
+                            else if (!assignAlignToWindow(ln, a1A, aLengthA, aStr, aNrep, aFrag, aRstart + aLengthD, aAnchor, isj1)) tooManyAnchors = true;
+                        }
+                    } else {
+                        if (!assignAlignToWindow(ln, a1, aLength, aStr, aNrep, aFrag, aRstart, aAnchor, SJA_NONE)) tooManyAnchors = true;
                     }
-                } else {
-                    if (!assignAlignToWindow(ln, a1, aLength, aStr, aNrep, aFrag, aRstart, aAnchor, SJA_NONE)) tooManyAnchors = true;
+                    if (tooManyAnchors) { iSA = iSAend; iP = nP; break; }   // the rest of the reference's enumeration is dead work (nW=0)
                 }
-                if (tooManyAnchors) { iSA = iSAend; iP = nP; }   // the rest of the reference's enumeration is dead work (nW=0)
             }
         }
+        PHASE_TICK(3);
         // ------------------------------------------------------------------ next window with seeds (:268-299)
         if (phase == PH_NEXTWIN) {
-            bool found = false;
-            while (iW < ln.nW) {
-                if (ln.win[iW].nWA == 0) { iW++; continue; }
-                if (trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) { iW = ln.nW; break; }   // logs a warning in the reference (:288-292)
-                if (trNtotal + 1 > caps.maxTr) { ln.overflow = 1; break; }
-                found = true;
-                break;
-            }
-            if (ln.overflow) {
-                phase = PH_SELECT;
-            } else if (!found) {
-                nWfinal = nW1;
-                if (bestScore == 0) { mapMarker = STAR_MARKER_NO_GOOD_WINDOW; nWfinal = 0; }
-                phase = PH_SELECT;
-            } else {
+            while (iW < ln.nW && ln.win[iW].nWA == 0) iW++;
+            int rc = iW < ln.nW ? windowBegin(ln, wTr, nWinTr) : 1;
+            if (rc == 2) { ln.overflow = 3; phase = PH_SELECT; }   // reason 3: transcript pool
+            else if (rc == 1) { phase = PH_SELECT; }
+            else {
                 Chr = ln.win[iW].Chr; Str = ln.win[iW].Str;
-                wTr = ln.trPtr + trNtotal;
-                nWinTr = 0;
-                // *(trAll[iW1][0]) = trA : the window-best comparison starts from maxScore 0 (:293)
-                ln.pool[wTr[0]].h.maxScore = 0;
-                ln.pool[wTr[0]].h.nExons = 0;
                 ln.R = Str == 0 ? R0 : R2;
                 dfsInit(ln);
                 phase = PH_NODE;
             }
         }
+        PHASE_TICK(4);
         // ------------------------------------------------------------------ one DFS unit: one seed-include attempt
         if (phase == PH_NODE) {
             int r = dfsStep(ln, ln.wa + (u64)iW * caps.spw, ln.win[iW].nWA);
             if (r == DFS_LEAF) {
                 phase = PH_LEAF;
-            } else if (r == DFS_DONE) {   // window finished (:324-331)
-                if (nWinTr > 0) {
-                    const TrHead& b = ln.pool[wTr[0]].h;
-                    if (b.maxScore > bestScore || (b.maxScore == bestScore && b.gLength < bestGLength)) {
-                        bestPool = wTr[0]; bestScore = b.maxScore; bestGLength = b.gLength;
-                    }
-                    ln.winBase[nW1] = (u16)trNtotal;
-                    ln.winN[nW1] = nWinTr;
-                    ln.win[nW1].Chr = Chr;      // compact windows (iW1 <= iW): keep Chr/Str of the windows that have transcripts
-                    ln.win[nW1].Str = (u8)Str;
-                    trNtotal += nWinTr;
-                    nW1++;
-                }
+            } else if (r == DFS_DONE) {
+                windowEnd(ln, Chr, Str, wTr, nWinTr);
                 iW++;
                 phase = PH_NEXTWIN;
             }
         }
+        PHASE_TICK(5);
         // ------------------------------------------------------------------ leaf: extend, filter, score, record (:19-306)
         if (phase == PH_LEAF) {
             ln.leaves++;
-            if (nWinTr > caps.maxTr - trNtotal - 1) {   // pool of this lane is full: slow path
-                ln.overflow = 1;
+            if (nWinTr > caps.maxTr - ln.trNtotal - 1) {   // pool of this lane is full: next tier
+                ln.overflow = 3;
                 phase = PH_SELECT;
             } else {
-                finalizeLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str, wTr, &nWinTr);
+                if (evalLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str)) recordLeaf(ln, wTr, &nWinTr);
                 phase = PH_NODE;
             }
         }
+        PHASE_TICK(6);
         // ------------------------------------------------------------------ multMapSelect, mappedFilter, export
         if (phase == PH_SELECT) {
-            const u32 Lread = ri.Lread;
-            star_read_result_t res;
-            res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
-            res.bestRLength = 0; res.Lread = Lread; res.bestTr = 0;
-            ri.cSaEnum = (u32)ln.saEnum; ri.cNodes = (u32)ln.nodes; ri.cLeaves = (u32)ln.leaves;
-            if (ln.overflow) {   // a fast-path cap was hit: flag the read for the slow path
-                ri.flags |= 1;
-                info[i] = ri;
-                results[i] = res;
-            } else {
-                u32 bestNMM = 0, bestNMatch = 0;
-                if (bestPool >= 0) {
-                    const TrHead& b = ln.pool[bestPool].h;
-                    bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
-                }
-                // ---------------- multMapSelect :8-95 ----------------
-                u32 nTr = 0;
-                for (u32 w = 0; w < nWfinal; w++) {
-                    const u16* wt = ln.trPtr + ln.winBase[w];
-                    for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
-                        if (ln.pool[wt[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
-                    }
-                }
-                // ---------------- mappedFilter :3-20 ----------------
-                int unmapType = -1;
-                if (nWfinal == 0) {
-                    unmapType = 0;
-                } else if ((bestScore < P.outFilterScoreMin) || (bestScore < (int)(P.outFilterScoreMinOverLread * (double)(Lread - 1)))
-                           || (bestNMatch < P.outFilterMatchNmin) || (bestNMatch < (u64)(P.outFilterMatchNminOverLread * (double)(Lread - 1)))) {
-                    unmapType = 1;
-                } else if ((bestNMM > ri.outFilterMismatchNmaxTotal) || (double(bestNMM) / double(bestRLength) > P.outFilterMismatchNoverLmax)) {
-                    unmapType = 2;
-                } else if (nTr > P.outFilterMultimapNmax) {
-                    unmapType = 3;
-                }
-                res.unmapType = unmapType; res.nTr = nTr; res.mapMarker = mapMarker; res.bestScore = bestScore; res.bestNMM = bestNMM; res.bestRLength = bestRLength;
-                if (unmapType < 0) {
-                    // trMult order = window order then in-window rank (:26-44); primary flag rules (:56-91)
-                    star_align_t* o = staged + (u64)i * caps.nOut;
-                    u32 kOut = 0;
-                    u32 bestK = 0;
-                    for (u32 w = 0; w < nWfinal; w++) {
-                        const u16* wt = ln.trPtr + ln.winBase[w];
-                        for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
-                            DevTr& t = ln.pool[wt[iTr]];
-                            if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
-                                t.h.primaryFlag = 0;
-                                exportAlign(t, ln.win[w].Chr, ln.win[w].Str, ln.win[w].Str, Lread, ix, o + kOut);
-                                if ((int)wt[iTr] == bestPool) bestK = kOut;
-                                kOut++;
-                            }
-                        }
-                    }
-                    if (nTr == 1) {
-                        o[0].primaryFlag = 1;
-                    } else {
-                        u32 nbest = 0;
-                        if (P.outSAMmultNmax != (u64)-1) {   // bring the best alignments to the top (:60-67)
-                            for (u32 itr = 0; itr < nTr; itr++) {
-                                if (o[itr].maxScore == bestScore) {
-                                    if (itr != nbest) { star_align_t tmp = o[itr]; o[itr] = o[nbest]; o[nbest] = tmp; }
-                                    if (bestK == itr) bestK = nbest; else if (bestK == nbest) bestK = itr;
-                                    ++nbest;
-                                }
-                            }
-                        }
-                        if (P.outSAMprimaryFlagAllBestScore) {
-                            for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
-                        } else if (P.outSAMmultNmax != (u64)-1) {
-                            o[0].primaryFlag = 1;
-                        } else {
-                            o[bestK].primaryFlag = 1;
-                        }
-                    }
-                    res.nTrOut = nTr;
-                    res.bestTr = bestK;
-                }
-                results[i] = res;
-                info[i] = ri;
-            }
+            selectExport(ln, ri, i, mapMarker, bestRLength, results, staged, info);
             phase = PH_FETCH;
         }
+        PHASE_TICK(7);
         if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
     }
+    for (int q = 0; q < 8; q++) PROF_ADD(q, pc[q]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Heavy reads: ONE WARP per read.  The DFS of every window is cut into prefix sub-trees (the first d include/exclude decisions
+// fixed; task id ascending = the reference's DFS order, include before exclude).  Lanes pull tasks from a warp-wide ticket and
+// evaluate them independently: the expensive part of a leaf (stitch chain, end extension, filters, score: evalLeaf) is a pure
+// function of the path, so it parallelises exactly.  Each surviving leaf is stored as a 16-byte candidate {include mask, score,
+// iFrag}.  Then lane 0 replays the reference's order-dependent part (recordLeaf: maxScoreMate, record test, blocksOverlap dedup,
+// ordered insert) over the candidates in window order / task order / leaf order, re-materialising the transcript (replayPath +
+// evalLeaf) only for the few candidates that pass the record test.  Result: identical to the sequential recursion.
+struct Cand { u64 mask; int score; signed char iFrag; u8 pad[3]; };
+#define CAND_PER_BLOCK 31
+struct CandBlock { u32 next; u32 count; Cand c[CAND_PER_BLOCK]; };   // 8 + 31*16 = 504 bytes
+struct TaskOut { u32 first, last; };                                 // candidate blocks of a task (0xFFFFFFFF = none)
+
+struct HeavyScratch {     // per warp, in HBM
+    u32 maxTasks, maxBlocks, maxWin;
+    u64 bytesPerWarp;
+};
+
+__device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 mask, int& Score, u32& tR2, u64& tG2) {
+    DevTr* t = ln.cur;
+    dfsInit(ln);
+    Score = 0; tR2 = 0; tG2 = 0;
+    for (u32 iA = 0; iA < nA; iA++) {
+        if (!((mask >> iA) & 1ULL)) continue;
+        const Seed s = WA[iA];
+        int dScore;
+        if (t->h.nExons > 0) {
+            dScore = stitchAlignToTranscript(ln, tR2, tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+        } else {
+            t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
+            t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
+            t->ex[0].L = s.Length; t->ex[0].iFrag = s.iFrag; t->ex[0].sjA = s.sjA;
+            t->ex[0].canon = 0; t->ex[0].annot = 0; t->ex[0].sjStr = 0; t->ex[0].shL = 0; t->ex[0].shR = 0;
+            t->h.nExons = 1;
+            dScore = s.Length;
+            t->h.nMatch = s.Length;
+        }
+        if (dScore <= -1000000) return false;
+        if (s.Nrep == 1) t->h.nUnique++;
+        if (s.Anchor > 0) t->h.nAnchor++;
+        Score += dScore;
+        tR2 = (u32)s.rStart + s.Length - 1;
+        tG2 = s.gStart + s.Length - 1;
+    }
+    return tR2 != 0;
+}
+
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+                                                     ReadInfo* __restrict__ info, u32 nHeavy, const u32* __restrict__ heavyList,
+                                                     const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
+                                                     u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
+                                                     star_align_t* __restrict__ staged, u32 smemStride, u8* __restrict__ scratch, HeavyScratch hs) {
+    extern __shared__ u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warpInBlock = threadIdx.x >> 5;
+    const u32 warpsPerBlock = blockDim.x >> 5;
+    const u32 gwarp = blockIdx.x * warpsPerBlock + warpInBlock;
+    // shared memory per warp: R0 | R2 | ticket counters
+    u8* R0 = smem + (size_t)warpInBlock * (2 * smemStride + 16);
+    u8* R2 = R0 + smemStride;
+    u32* sh = (u32*)(R0 + 2 * smemStride);   // [0] task ticket, [1] block bump, [2] overflow flag
+    Lane ln;
+    DevTr curL, leafL;
+    Frame stackL[STAR_DFS_MAX_DEPTH];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL;
+    ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
+    {   // lane 0's arena of this warp holds the recording state (pool, pointer arrays, compacted window Chr/Str)
+        u8* a = arenas + (u64)(blockIdx.x * blockDim.x + warpInBlock * 32) * caps.arenaBytes;
+        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+        ln.wa = (Seed*)a; a += (u64)caps.maxW * caps.spw * sizeof(Seed);
+        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+        a += 2 * sizeof(DevTr) + (u64)(caps.spw + 2) * sizeof(Frame);
+        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+        ln.winN = (u16*)a;
+    }
+    u8* ws = scratch + (u64)gwarp * hs.bytesPerWarp;
+    const u32 W1 = (hs.maxWin + 2) & ~1u;                                   // even, >= maxWin+1
+    u32* taskStart = (u32*)ws;                                              // W1
+    u32* seedStart = taskStart + W1;                                        // W1
+    u8* depthOf = (u8*)(seedStart + W1);                                    // W1 rounded to 8
+    TaskOut* taskOut = (TaskOut*)(depthOf + ((W1 + 7) & ~7u));              // maxTasks (8-byte aligned)
+    CandBlock* blocks = (CandBlock*)(taskOut + hs.maxTasks);                // maxBlocks
+
+    long long hc[6] = {0, 0, 0, 0, 0, 0};
+    for (;;) {
+        long long t0 = clock64();
+        u32 k = 0;
+        if (lane == 0) k = atomicAdd(counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nHeavy) break;
+        const u32 i = heavyList[k];
+        ReadInfo ri = info[i];
+        readBegin(ln, ri);
+        const u8* rec = heavyPool + heavyOff[i];
+        const u32 nWin = ((const u32*)rec)[0];
+        const HeavyWin* hw = (const HeavyWin*)(rec + 8);
+        const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
+        {   // read into shared memory (both orientations)
+            const u8* g = reads + (u64)i * stride;
+            const u32 L = ri.Lread;
+            for (u32 b = lane; b < L; b += 32) {
+                u8 c = g[b];
+                R0[b] = c;
+                R2[L - 1 - b] = c < 4 ? 3 - c : c;
+            }
+        }
+        // ---- task table (lane 0): split depth per window, prefix sums
+        u32 nTasks = 0;
+        if (lane == 0) {
+            sh[0] = 0; sh[1] = 0; sh[2] = 0;
+            if (nWin > hs.maxWin) { sh[2] = 1; }
+            else {
+                u32 shift = 0;
+                for (;;) {
+                    u32 tot = 0, sd = 0;
+                    for (u32 w = 0; w < nWin; w++) {
+                        u32 a = hw[w].nWA;
+                        u32 d = a <= 6 ? 0 : (a - 6 > 8 ? 8 : a - 6);
+                        d = d > shift ? d - shift : 0;
+                        taskStart[w] = tot; depthOf[w] = (u8)d; seedStart[w] = sd;
+                        tot += 1u << d; sd += a;
+                    }
+                    taskStart[nWin] = tot; seedStart[nWin] = sd;
+                    if (tot <= hs.maxTasks) { nTasks = tot; break; }
+                    shift++;
+                }
+            }
+        }
+        __syncwarp();
+        nTasks = __shfl_sync(0xffffffffu, nTasks, 0);
+        bool over = sh[2] != 0;
+        long long t1 = clock64(); hc[0] += t1 - t0;
+        // ---- E phase: lanes evaluate prefix sub-trees, lockstep over {fetch task, DFS node, leaf}
+        if (!over) {
+            u32 ph = 0;   // 0 fetch, 1 node, 2 leaf, 3 idle
+            u32 tsk = 0, w = 0, Chr = 0, Str = 0, curBlock = 0xFFFFFFFFu;
+            const Seed* WA = seeds;
+            u32 nA = 0;
+            for (;;) {
+                if (ph == 0) {
+                    tsk = atomicAdd(&sh[0], 1u);
+                    if (tsk >= nTasks || sh[2]) { ph = 3; }
+                    else {
+                        // window of the task: last w with taskStart[w] <= tsk
+                        u32 lo = 0, hi = nWin;
+                        while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (taskStart[mid] <= tsk) lo = mid; else hi = mid; }
+                        w = lo;
+                        Chr = hw[w].Chr; Str = hw[w].Str; nA = hw[w].nWA;
+                        WA = seeds + seedStart[w];
+                        ln.R = Str == 0 ? R0 : R2;
+                        dfsInit(ln);
+                        ln.forceDepth = depthOf[w];
+                        ln.forceBits = tsk - taskStart[w];
+                        taskOut[tsk].first = 0xFFFFFFFFu; taskOut[tsk].last = 0xFFFFFFFFu;
+                        curBlock = 0xFFFFFFFFu;
+                        ph = 1;
+                    }
+                }
+                if (ph == 1) {
+                    int r = dfsStep(ln, WA, nA);
+                    if (r == DFS_LEAF) ph = 2;
+                    else if (r == DFS_DONE) ph = 0;
+                }
+                if (ph == 2) {
+                    ln.leaves++;
+                    if (evalLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str)) {
+                        if (curBlock == 0xFFFFFFFFu || blocks[curBlock].count == CAND_PER_BLOCK) {
+                            u32 nb = atomicAdd(&sh[1], 1u);
+                            if (nb >= hs.maxBlocks) { sh[2] = 1; nb = 0xFFFFFFFFu; }
+                            else {
+                                blocks[nb].next = 0xFFFFFFFFu; blocks[nb].count = 0;
+                                if (curBlock == 0xFFFFFFFFu) taskOut[tsk].first = nb; else blocks[curBlock].next = nb;
+                                taskOut[tsk].last = nb;
+                            }
+                            curBlock = nb;
+                        }
+                        if (curBlock != 0xFFFFFFFFu) {
+                            Cand c; c.mask = ln.inclMask; c.score = ln.leaf->h.maxScore; c.iFrag = ln.leaf->h.iFrag; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+                            CandBlock& B = blocks[curBlock];
+                            B.c[B.count] = c;
+                            B.count++;
+                        }
+                    }
+                    ph = sh[2] ? 3 : 1;
+                }
+                if (__all_sync(0xffffffffu, ph == 3)) break;
+            }
+        }
+        __syncwarp();
+        // work counters of the E phase (nodes, leaves) summed over the lanes
+        {
+            u64 nd = ln.nodes, lv = ln.leaves;
+            for (int o = 16; o > 0; o >>= 1) { nd += __shfl_down_sync(0xffffffffu, nd, o); lv += __shfl_down_sync(0xffffffffu, lv, o); }
+            ln.nodes = nd; ln.leaves = lv;   // meaningful on lane 0
+        }
+        over = sh[2] != 0;
+        long long t2 = clock64(); hc[1] += t2 - t1; hc[3] += nTasks;
+        // ---- R phase: lane 0 replays the order-dependent recording
+        if (lane == 0) {
+            ln.forceDepth = 0; ln.forceBits = 0;
+            if (over) {
+                ln.overflow = 5;   // reason 5: heavy-kernel scratch (tasks / candidate blocks / windows)
+            } else {
+                for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+                for (u32 w = 0; w < nWin && !ln.overflow; w++) {
+                    u16* wTr = nullptr; u16 nWinTr = 0;
+                    int rc = windowBegin(ln, wTr, nWinTr);
+                    if (rc == 2) { ln.overflow = 3; break; }
+                    if (rc == 1) break;
+                    const u32 Chr = hw[w].Chr, Str = hw[w].Str, nA = hw[w].nWA;
+                    const Seed* WA = seeds + seedStart[w];
+                    ln.R = Str == 0 ? R0 : R2;
+                    for (u32 t = taskStart[w]; t < taskStart[w + 1] && !ln.overflow; t++) {
+                        u32 b = taskOut[t].first;
+                        while (b != 0xFFFFFFFFu && !ln.overflow) {
+                            const CandBlock& B = blocks[b];
+                            for (u32 q = 0; q < B.count; q++) {
+                                const Cand c = B.c[q];
+                                if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
+                                int wBest = ln.pool[wTr[0]].h.maxScore;
+                                if (c.score + P.outFilterMultimapScoreRange >= wBest ||
+                                    (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
+                                    if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; break; }
+                                    int Score; u32 tR2; u64 tG2;
+                                    hc[4]++;
+                                    bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                    if (ok) recordLeaf(ln, wTr, &nWinTr);
+                                }
+                            }
+                            b = B.next;
+                        }
+                    }
+                    windowEnd(ln, Chr, Str, wTr, nWinTr);
+                }
+            }
+            selectExport(ln, ri, i, 0, 0, results, staged, info);
+        }
+        __syncwarp();
+        hc[2] += clock64() - t2;
+    }
+    for (int q = 0; q < 5; q++) PROF_ADD(16 + q, hc[q]);
+}
+
+__global__ void prof_read_kernel(unsigned long long* out, int reset) {
+    int t = threadIdx.x;
+    if (t < 32) { out[t] = g_prof[t]; if (reset) g_prof[t] = 0; }
 }
 
 // Heaviest-first schedule of the fast path: key = ~nA (number of genomic loci of the stored pieces, known after seeding).

@@ -33,8 +33,15 @@ m1, m2 = synth.make_reads(chrs, trs, n, read_len=rl, mm=mm, seed=1000)
 seq, off, _, nm = sb.pack_reads([m1, m2])
 eng = sb.Engine(lib, index, max_reads=n)
 eng.upload(seq, off, n, nm)
+lib.star_gpu_debug_prof.argtypes = [C.c_void_p, C.c_void_p]
 for k in range(3):
     st = eng.map_resident()
+    prof = np.zeros(32, dtype=np.uint64)
+    lib.star_gpu_debug_prof(eng.ctx, prof.ctypes.data)
+    tot = float(prof[:8].sum()) or 1.0
+    print("light kernel warp-cycles by phase [fetch+copy, win, flank, assign, nextwin, node, leaf, select]: " + " ".join("%.1f%%" % (100.0 * float(x) / tot) for x in prof[:8]) + "  total %.3g" % tot)
+    th = float(prof[16:19].sum()) or 1.0
+    print("heavy kernel warp-cycles [setup, E, R]: " + " ".join("%.1f%%" % (100.0 * float(x) / th) for x in prof[16:19]) + "  total %.3g; tasks %d replays %d" % (th, prof[19], prof[20]))
     print("run", k, {k2: round(v, 2) if isinstance(v, float) else v for k2, v in st.as_dict().items()})
 info = np.zeros(n, dtype=INFO)
 rc = lib.star_gpu_debug_read_info(eng.ctx, info.ctypes.data, info.nbytes)
@@ -62,3 +69,5 @@ if os.environ.get("ANALYZE_LIGHT"):
         print("light reads <= p%.1f of nA (nA<=%d): n=%d  seed %.1f ms  fast stitch %.1f ms  tiers %.1f ms -> %.0f pairs/s (fast stitch only %.0f); nodes %d slow %d"
               % (pct, thr, n2, st.ms_seed, st.ms_stitch, st.ms_window, n2 / st.ms_total * 1e3, n2 / st.ms_stitch * 1e3, st.stitch_nodes, st.slow_path_reads))
         eng.close()
+rs = (info["flags"] >> 8) & 0xff
+print("overflow reasons (1 windows, 3 transcripts, 4 pool, 5 heavy scratch):", {int(r): int((rs == r).sum()) for r in np.unique(rs) if r})

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+for n in 1048576; do timeout 900 python tools/analyze_chunk.py $n > gpurun_out/analyze7_$n.log 2>&1; grep -E "^run 2|pairs/s|kernel warp" gpurun_out/analyze7_$n.log | tail -5; done
