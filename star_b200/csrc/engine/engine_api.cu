@@ -33,8 +33,9 @@ struct HeavyScratch {
 };
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
                               star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
-__global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
+__global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
                                     star_read_result_t*, star_align_t*, u32, u8*, HeavyScratch);
+__global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void prof_read_kernel(unsigned long long*, int);
 __global__ void pack_kernel(const star_read_result_t*, const u64*, const star_align_t*, u32, u32, star_align_t*);
@@ -95,7 +96,8 @@ struct star_ctx {
     u64* d_heavyOff = nullptr;
     u32* d_heavyList = nullptr;
     u8* d_heavyScratch = nullptr;
-    u32 heavyEst = 1024; u32 heavyMaxTasks = 8192, heavyMaxBlocks = 4096;
+    u32 heavyEst = 1024; u32 heavyNA = 64; u32 heavyMaxTasks = 8192, heavyMaxBlocks = 4096;
+    Caps heavyCaps; u8* d_arenaHeavy = nullptr;   // per-WARP arenas of the warp-per-read kernel (bigger caps than the per-lane fast arenas)
     u64 heavyScratchBytes = 0; u64 lastHeavy = 0;
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -314,6 +316,8 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     CK(cudaMalloc(&c->d_sortTmp, c->sortTmpBytes + 64));
     c->owned.push_back(c->d_sortTmp);
     c->heavyEst = envU32("STAR_B200_HEAVY_EST", 1024);
+    c->heavyNA = envU32("STAR_B200_HEAVY_NA", 64);
+    if (!c->heavyEst) c->heavyNA = 0;
     c->heavyMaxTasks = envU32("STAR_B200_HEAVY_TASKS", 8192);
     c->heavyMaxBlocks = envU32("STAR_B200_HEAVY_BLOCKS", 4096);
     if (c->heavyEst) {
@@ -325,6 +329,12 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         if (devAlloc(c, &c->d_heavyOff, N)) return STAR_EXIT_RUNTIME;
         if (devAlloc(c, &c->d_heavyList, N)) return STAR_EXIT_RUNTIME;
     }
+    if (c->heavyEst) {
+        c->heavyCaps = c->fast;
+        c->heavyCaps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_HEAVY_MAXW", 1024)) + 1) & ~1u;
+        c->heavyCaps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_HEAVY_MAXTR", 1024));
+        c->heavyCaps.arenaBytes = arenaSize(c->heavyCaps);
+    }
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
     c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 4);
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
@@ -332,6 +342,11 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         size_t bytes = (size_t)c->gridStitch * 128 * c->fast.arenaBytes;
         CK(cudaMalloc((void**)&c->d_arenaFast, bytes));
         c->owned.push_back(c->d_arenaFast);
+    }
+    if (c->heavyEst) {   // one arena per warp: the kernel indexes arenas by (first thread of the warp) * arenaBytes, so allocate with a stride of 32 arenas... no: use a dedicated stride
+        size_t bytes = (size_t)c->gridStitch * 4 * c->heavyCaps.arenaBytes;
+        CK(cudaMalloc((void**)&c->d_arenaHeavy, bytes));
+        c->owned.push_back(c->d_arenaHeavy);
     }
     CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -387,13 +402,9 @@ int star_gpu_upload_chunk(star_ctx_t* c, const star_read_batch_t* in) {
     return 0;
 }
 
-// Runs the warp-per-read heavy kernel over the reads the preceding stitch_kernel pass exported (if any).
-static int runHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, u32 smemStride) {
-    if (!c->heavyEst) return 0;
-    u32 nHeavy = 0;
-    CK(cudaMemcpyAsync(&nHeavy, (u32*)(c->d_heavyBump + 1), 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    c->lastHeavy += nHeavy;
+// Launches the warp-per-read kernel over `nHeavy` reads of `list` (device pointer).  pool==true: reads exported by stitch_kernel
+// (windows + seeds in the heavy pool); pool==false: reads routed here right after seeding (the warp does the window phases too).
+static int launchHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, const u32* list, u32 nHeavy, bool pool, const Piece* pieces) {
     if (nHeavy == 0) return 0;
     HeavyScratch hs;
     hs.maxTasks = c->heavyMaxTasks; hs.maxBlocks = c->heavyMaxBlocks; hs.maxWin = caps.maxW;
@@ -406,19 +417,32 @@ static int runHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, u
         CK(cudaMalloc((void**)&c->d_heavyScratch, need));
         c->heavyScratchBytes = need;
     }
-    // deterministic, heaviest-first order is not needed for exactness; sort the list so that runs are reproducible
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    const u32 perWarp = (2 * c->smemStride + 32 + caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+    const u32 smem = 4 * perWarp;
+    if (smem > 200 * 1024) { g_err = "star_b200: heavy kernel shared memory exceeds the limit for this tier"; return STAR_EXIT_RUNTIME; }
+    stitch_heavy_kernel<<<gridBlocks, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, pieces, nHeavy, list, c->d_heavyOff,
+                                                            pool ? c->d_heavyPool : nullptr, c->d_counter, arenas, caps, c->d_results, c->d_staged,
+                                                            c->smemStride, c->d_heavyScratch, hs);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Runs the heavy kernel over the reads the preceding stitch_kernel pass exported (if any).
+static int runHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, u32 /*smemStride*/) {
+    if (!c->heavyEst) return 0;
+    u32 nHeavy = 0;
+    CK(cudaMemcpyAsync(&nHeavy, (u32*)(c->d_heavyBump + 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->lastHeavy += nHeavy;
+    if (nHeavy == 0) return 0;
+    // sort the exported list so that runs are reproducible (atomics produced an arbitrary order)
     std::vector<u32> list(nHeavy);
     CK(cudaMemcpy(list.data(), c->d_heavyList, (size_t)nHeavy * 4, cudaMemcpyDeviceToHost));
     std::sort(list.begin(), list.end());
     CK(cudaMemcpy(c->d_heavyList, list.data(), (size_t)nHeavy * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-    const u32 smem = 4 * (2 * smemStride + 16);
-    stitch_heavy_kernel<<<gridBlocks, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, nHeavy, c->d_heavyList, c->d_heavyOff,
-                                                            c->d_heavyPool, c->d_counter, arenas, caps, c->d_results, c->d_staged, smemStride,
-                                                            c->d_heavyScratch, hs);
-    g_launches++;
-    CK(cudaGetLastError());
-    return 0;
+    return launchHeavy(c, caps, arenas, gridBlocks, c->d_heavyList, nHeavy, true, nullptr);
 }
 static HeavyArgs heavyArgs(star_ctx* c) {
     HeavyArgs hv;
@@ -459,12 +483,26 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     g_launches += 4;   // key kernel + cub's histogram/onesweep passes (library kernels, not counted as ours beyond the launch)
     c->lastHeavy = 0;
     if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
-    stitch_kernel<<<c->gridStitch, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, n, nullptr, c->d_counter,
-                                                                  c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_order, c->smemStride, heavyArgs(c));
-    g_launches++;
-    CK(cudaGetLastError());
+    // reads with many genomic loci (nA) go straight to the warp-per-read kernel: they are the head of the nA-descending order
+    u32 nHeavyA = 0;
+    if (c->heavyNA) {
+        CK(cudaMemsetAsync(c->d_counter + 2, 0, 4, c->stream));
+        count_heavy_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, c->heavyNA, c->d_counter + 2);
+        g_launches++;
+        CK(cudaMemcpyAsync(&nHeavyA, c->d_counter + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->lastHeavy += nHeavyA;
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    if (n > nHeavyA) {
+        stitch_kernel<<<c->gridStitch, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, n - nHeavyA, nullptr, c->d_counter,
+                                                                      c->d_arenaFast, c->fast, c->d_results, c->d_staged, c->d_order + nHeavyA, c->smemStride, heavyArgs(c));
+        g_launches++;
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(c->ev[9], c->stream));
-    if (runHeavy(c, c->fast, c->d_arenaFast, c->gridStitch, c->smemStride)) return STAR_EXIT_RUNTIME;
+    if (launchHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->d_order, nHeavyA, false, c->d_pieces)) return STAR_EXIT_RUNTIME;
+    if (runHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->smemStride)) return STAR_EXIT_RUNTIME;
     CK(cudaEventRecord(c->ev[8], c->stream));
     // ---- overflow tiers: reads that exceeded the caps of a tier are redone in the next one; the last tier has the reference's own limits ----
     for (int tier = 0; tier < 2; tier++) {
@@ -497,11 +535,15 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
             g_launches++;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
+            HeavyArgs hv = heavyArgs(c);
+            const u32 perWarpH = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+            const bool heavyOk = c->heavyEst && 4 * perWarpH <= 200 * 1024;   // the last tier (reference limits) has no shared-memory window table
+            if (!heavyOk) hv.estLimit = 0;
             stitch_kernel<<<grid, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, m, c->d_list + lo,
-                                                                 c->d_counter, T.arena, T.caps, c->d_results, c->d_staged, nullptr, c->smemStride, heavyArgs(c));
+                                                                 c->d_counter, T.arena, T.caps, c->d_results, c->d_staged, nullptr, c->smemStride, hv);
             g_launches++;
             CK(cudaGetLastError());
-            if (runHeavy(c, T.caps, T.arena, grid, c->smemStride)) return STAR_EXIT_RUNTIME;
+            if (heavyOk && runHeavy(c, T.caps, T.arena, grid, c->smemStride)) return STAR_EXIT_RUNTIME;
         }
     }
     CK(cudaEventRecord(c->ev[5], c->stream));

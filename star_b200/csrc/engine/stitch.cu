@@ -35,18 +35,19 @@ __device__ unsigned long long g_prof[32];
 #define LOCI_PER_STEP 1          // SA loci handled per lockstep step (their SA words are loaded back to back, latency overlapped)
 #define STAR_DFS_MAX_DEPTH 52   // seedPerWindowNmax (<=50 on the local-memory fast build) + 2
 
+// Undo record of one successful (or attempted) seed include: the transcript head and the last exon before the include, and the
+// DFS cursor (Score, tR2, tG2).  Only include levels need one (<= MAX_N_EXONS+1 deep); exclude levels change nothing.
 struct Frame {
-    TrHead h;        // head before the include attempt
-    Exon last;       // ex[nExons-1] before the include attempt
+    TrHead h;
+    Exon last;
     u64 tG2;
     u32 tR2;
     int Score;
-    u16 iA;
-    u8 phase;
-    u8 pad;
+    u32 pad[2];
 };
 
 static_assert(sizeof(Frame) == 128, "arenaSize() in engine_api.cu assumes 128-byte frames");
+#define STAR_UNDO_DEPTH (STAR_MAX_N_EXONS + 2)
 
 struct Lane {
     const DevIndex* ix;
@@ -72,7 +73,12 @@ struct Lane {
     Caps caps;
     u32 overflow;
     u64 saEnum, nodes, leaves;
-    int sp;              // DFS stack pointer
+    u8* ph;              // per DFS level: 0 new, 1 include branch taken, 2 exclude branch taken, 3 forced include
+    int level;           // current DFS level (= seed index iA); -1 when the window is finished
+    int nInc;            // number of live undo records
+    int Score;           // DFS cursor
+    u32 tR2;
+    u64 tG2;
     int leafScore;       // pending leaf (set by dfsStep)
     u32 leafR2;
     u64 leafG2;
@@ -624,10 +630,33 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
     z.nGap = 0; z.lGap = 0; z.nDel = 0; z.lDel = 0; z.nIns = 0; z.lIns = 0; z.nUnique = 0; z.nAnchor = 0; z.nExons = 0; z.iFrag = 0;
     z.sjMotifStrand = 0; z.primaryFlag = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
     ln.cur->h = z;
-    ln.sp = 0;
     ln.inclMask = 0;
-    Frame& f = ln.stack[0];
-    f.iA = 0; f.Score = 0; f.tR2 = 0; f.tG2 = 0; f.phase = 0;
+    ln.level = 0; ln.nInc = 0; ln.Score = 0; ln.tR2 = 0; ln.tG2 = 0;
+    ln.ph[0] = 0;
+}
+
+// after a sub-tree is exhausted: unwind to the deepest level whose exclude branch is still unexplored (undoing its include)
+__device__ __forceinline__ void dfsBacktrack(Lane& ln) {
+    DevTr* t = ln.cur;
+    int L = ln.level - 1;
+    while (L >= 0) {
+        const u8 p = ln.ph[L];
+        if (p == 1) {
+            // undo the include of seed L, then explore the branch without it (WA_Anchor==2 never occurs: WlastAnchor is initialised
+            // to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
+            const Frame& u = ln.stack[--ln.nInc];
+            if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
+            t->h = u.h;
+            ln.Score = u.Score; ln.tR2 = u.tR2; ln.tG2 = u.tG2;
+            ln.inclMask &= ~(1ULL << L);
+            ln.ph[L] = 2;
+            ln.level = L + 1;
+            ln.ph[L + 1] = 0;
+            return;
+        }
+        L--;
+    }
+    ln.level = -1;
 }
 
 #define DFS_CONTINUE 0
@@ -635,68 +664,66 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
 #define DFS_DONE 2
 __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
     DevTr* t = ln.cur;
-    Frame* st = ln.stack;
     for (;;) {
-        if (ln.sp < 0) return DFS_DONE;
-        Frame& f = st[ln.sp];
-        if (f.phase == 0) {
-            ln.nodes++;
-            if (f.iA >= nA) {
-                bool isLeaf = f.tR2 != 0;   // "iA>=nA && tR2==0: no aligns in the transcript" (:14)
-                if (isLeaf) { ln.leafScore = f.Score; ln.leafR2 = f.tR2; ln.leafG2 = f.tG2; }
-                ln.sp--;
-                if (isLeaf) return DFS_LEAF;
+        if (ln.level < 0) return DFS_DONE;
+        const u32 L = (u32)ln.level;
+        ln.nodes++;
+        if (L >= nA) {
+            if (ln.ph[L] == 9) {               // the leaf at this position was already handed out: now unwind
+                dfsBacktrack(ln);
                 continue;
             }
-            const bool forced = f.iA < ln.forceDepth;
-            if (forced && ((ln.forceBits >> (ln.forceDepth - 1 - f.iA)) & 1u)) {   // this level is fixed to "exclude"
-                f.phase = 2;
-                Frame& c = st[ln.sp + 1];
-                c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
-                ln.sp++;
-                continue;
+            const bool isLeaf = ln.tR2 != 0;   // "iA>=nA && tR2==0: no aligns in the transcript" (:14)
+            if (isLeaf) {
+                // the caller evaluates the leaf from ln.cur, so the undo of the last include has to wait for the next call
+                ln.leafScore = ln.Score; ln.leafR2 = ln.tR2; ln.leafG2 = ln.tG2;
+                ln.ph[L] = 9;
+                ln.nodes--;                    // (this level is visited twice)
+                return DFS_LEAF;
             }
-            const Seed s = WA[f.iA];
-            f.h = t->h;
-            if (t->h.nExons > 0) f.last = t->ex[t->h.nExons - 1];
-            int dScore = 0;
-            if (t->h.nExons > 0) {
-                dScore = stitchAlignToTranscript(ln, f.tR2, f.tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
-            } else {
-                t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
-                t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
-                t->ex[0].L = s.Length; t->ex[0].iFrag = s.iFrag; t->ex[0].sjA = s.sjA;
-                t->ex[0].canon = 0; t->ex[0].annot = 0; t->ex[0].sjStr = 0; t->ex[0].shL = 0; t->ex[0].shR = 0;
-                t->h.nExons = 1;
-                dScore = s.Length;
-                t->h.nMatch = s.Length;
-            }
-            f.phase = forced ? 2 : 1;   // a forced include never explores its exclude branch
-            if (dScore > -1000000) {
-                if (s.Nrep == 1) t->h.nUnique++;
-                if (s.Anchor > 0) t->h.nAnchor++;
-                ln.inclMask |= 1ULL << f.iA;
-                Frame& c = st[ln.sp + 1];
-                c.iA = f.iA + 1; c.Score = f.Score + dScore; c.tR2 = (u32)s.rStart + s.Length - 1; c.tG2 = s.gStart + s.Length - 1; c.phase = 0;
-                ln.sp++;
-            } else if (forced) {
-                ln.sp = -1;             // the fixed prefix is not a valid path: this sub-tree is empty
-                return DFS_DONE;
-            }
-            return DFS_CONTINUE;
-        } else if (f.phase == 1) {
-            // undo the include attempt, then explore the branch without this seed (WA_Anchor==2 never occurs: WlastAnchor is
-            // initialised to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
-            if (f.h.nExons > 0) t->ex[f.h.nExons - 1] = f.last;
-            t->h = f.h;
-            ln.inclMask &= ~(1ULL << f.iA);
-            f.phase = 2;
-            Frame& c = st[ln.sp + 1];
-            c.iA = f.iA + 1; c.Score = f.Score; c.tR2 = f.tR2; c.tG2 = f.tG2; c.phase = 0;
-            ln.sp++;
-        } else {
-            ln.sp--;
+            dfsBacktrack(ln);
+            continue;
         }
+        const bool forced = L < ln.forceDepth;
+        if (forced && ((ln.forceBits >> (ln.forceDepth - 1 - L)) & 1u)) {   // this level is fixed to "exclude"
+            ln.ph[L] = 2;
+            ln.level = (int)L + 1;
+            ln.ph[L + 1] = 0;
+            continue;
+        }
+        const Seed s = WA[L];
+        Frame& u = ln.stack[ln.nInc];
+        u.h = t->h;
+        if (t->h.nExons > 0) u.last = t->ex[t->h.nExons - 1];
+        u.Score = ln.Score; u.tR2 = ln.tR2; u.tG2 = ln.tG2;
+        int dScore = 0;
+        if (t->h.nExons > 0) {
+            dScore = stitchAlignToTranscript(ln, ln.tR2, ln.tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+        } else {
+            t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
+            t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
+            t->ex[0].L = s.Length; t->ex[0].iFrag = s.iFrag; t->ex[0].sjA = s.sjA;
+            t->ex[0].canon = 0; t->ex[0].annot = 0; t->ex[0].sjStr = 0; t->ex[0].shL = 0; t->ex[0].shR = 0;
+            t->h.nExons = 1;
+            dScore = s.Length;
+            t->h.nMatch = s.Length;
+        }
+        if (dScore > -1000000) {
+            if (s.Nrep == 1) t->h.nUnique++;
+            if (s.Anchor > 0) t->h.nAnchor++;
+            ln.inclMask |= 1ULL << L;
+            ln.nInc++;
+            ln.ph[L] = forced ? 3 : 1;   // a forced include never explores its exclude branch
+            ln.Score += dScore; ln.tR2 = (u32)s.rStart + s.Length - 1; ln.tG2 = s.gStart + s.Length - 1;
+        } else {
+            if (forced) { ln.level = -1; return DFS_DONE; }   // the fixed prefix is not a valid path: this sub-tree is empty
+            if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;   // the failed attempt may have touched the last exon / head
+            t->h = u.h;
+            ln.ph[L] = 2;
+        }
+        ln.level = (int)L + 1;
+        ln.ph[L + 1] = 0;
+        return DFS_CONTINUE;
     }
 }
 
@@ -1037,8 +1064,9 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
     Lane ln;
     // DFS state in per-thread local memory (L1-resident, interleaved across lanes) instead of the HBM arena
     DevTr curL, leafL;
-    Frame stackL[STAR_DFS_MAX_DEPTH];
-    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL;
+    Frame stackL[STAR_UNDO_DEPTH];
+    u8 phL[STAR_DFS_MAX_DEPTH + 4];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
     ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
     {
         u8* a = arenas + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * caps.arenaBytes;
@@ -1343,8 +1371,169 @@ __device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 ma
     return tR2 != 0;
 }
 
+// ---- warp-cooperative window creation / seed assignment (same semantics as createExtendWindowsWithAlign / assignAlignToWindow
+// above; all 32 lanes call these with IDENTICAL arguments, the window table lives in shared memory, the seeds of window w at
+// wa[w*spw ..] in the warp's arena).  Lanes scan windows / seeds 32 at a time and agree through ballots and shuffles.
+struct WarpWin {
+    Window* swin;     // shared memory, caps.maxW entries
+    Seed* wa;         // arena of the warp
+    u32 nW;
+    u32 spw;
+    u32 lane;
+};
+
+__device__ __forceinline__ u64 warpMaxU64(u64 v) {
+    for (int o = 16; o > 0; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
+    return v;
+}
+__device__ __forceinline__ u64 warpMinU64(u64 v) {
+    for (int o = 16; o > 0; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+    return v;
+}
+
+// ReadAlign_createExtendWindowsWithAlign.cpp:7-84, cooperative.  Returns 0, 101 (TOO_MANY_WINDOWS) or 102 (tier cap: overflow).
+__device__ int coopCreateWindow(const Lane& ln, WarpWin& ww, u64 a1, u32 aStr) {
+    const star_params_t& P = *ln.P;
+    const u64 aBin = a1 >> P.winBinNbits;
+    const u64 lo = aBin > P.winAnchorDistNbins ? aBin - P.winAnchorDistNbins : 0;
+    const u64 hiX = aBin + P.winAnchorDistNbins + 1 < P.winBinN ? aBin + P.winAnchorDistNbins + 1 : P.winBinN;
+    bool owned = false;
+    u64 candL = 0;                      // (gEnd+1)<<16 | w   (0 = none); max wins
+    u64 candR = ~0ULL;                  // gStart<<16 | w     (~0 = none); min wins
+    for (u32 w = ww.lane; w < ww.nW; w += 32) {
+        const Window W = ww.swin[w];
+        if (W.Str != aStr || W.gStart > W.gEnd) continue;
+        const u64 s0 = W.gStart, e0 = W.gEnd;
+        if (s0 <= aBin && aBin <= e0) owned = true;
+        if (aBin > 0 && e0 < aBin && e0 >= lo) { u64 c = ((e0 + 1) << 16) | w; if (c > candL) candL = c; }
+        if (aBin + 1 < P.winBinN && s0 > aBin && s0 < hiX) { u64 c = (s0 << 16) | w; if (c < candR) candR = c; }
+    }
+    if (__any_sync(0xffffffffu, owned)) return 0;
+    candL = warpMaxU64(candL);
+    candR = warpMinU64(candR);
+    const int left = candL ? (int)(candL & 0xffff) : -1;
+    const int right = candR != ~0ULL ? (int)(candR & 0xffff) : -1;
+    const u64 bestL = candL ? (candL >> 16) - 1 : 0, bestR = candR != ~0ULL ? candR >> 16 : 0;
+    const bool flagMergeLeft = left >= 0 && chrOfBin(ln, bestL) == chrOfBin(ln, aBin);
+    const bool flagMergeRight = right >= 0 && chrOfBin(ln, bestR) == chrOfBin(ln, aBin);
+    int rc = 0;
+    if (!flagMergeLeft && !flagMergeRight) {
+        if (ww.nW >= ln.caps.maxW) return 102;
+        if (ww.lane == 0) {
+            Window nw;
+            nw.gStart = (u32)aBin; nw.gEnd = (u32)aBin; nw.Chr = chrOfBin(ln, aBin); nw.nWA = 0; nw.WALrec = 0; nw.Str = (u8)aStr;
+            nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
+            ww.swin[ww.nW] = nw;
+        }
+        ww.nW++;
+        if (ww.nW >= P.alignWindowsPerReadNmax) { ww.nW = (u32)P.alignWindowsPerReadNmax - 1; rc = 101; }
+    } else {
+        if (ww.lane == 0) {
+            u64 iBinLeft = aBin, iBinRight = aBin;
+            int iWin = -1;
+            if (flagMergeLeft) { iWin = left; iBinLeft = ww.swin[left].gStart; }
+            if (flagMergeRight) { iBinRight = ww.swin[right].gEnd; if (!flagMergeLeft) iWin = right; }
+            ww.swin[iWin].gStart = (u32)iBinLeft;
+            ww.swin[iWin].gEnd = (u32)iBinRight;
+            if (flagMergeLeft && flagMergeRight) { ww.swin[right].gStart = 1; ww.swin[right].gEnd = 0; }
+        }
+    }
+    __syncwarp();
+    return rc;
+}
+
+// ReadAlign_assignAlignToWindow.cpp:6-130, cooperative, window iW already looked up.  Returns false on MARKER_TOO_MANY_ANCHORS.
+__device__ bool coopAssign(const Lane& ln, WarpWin& ww, int iW, u64 a1, u64 aLength, u64 aNrep, u32 aFrag, u64 aRstart, bool aAnchor, u32 sjA) {
+    const star_params_t& P = *ln.P;
+    if (iW < 0) return true;
+    Window* Wp = &ww.swin[iW];
+    const u32 WALrec0 = Wp->WALrec;
+    if (!aAnchor && aLength < WALrec0) return true;
+    Seed* WA = ww.wa + (u64)iW * ww.spw;
+    u32 nWA = Wp->nWA;
+    const u32 lane = ww.lane;
+    // my (up to two) seeds: j0 = lane, j1 = lane + 32
+    Seed e0, e1;
+    const bool v0 = lane < nWA, v1 = lane + 32 < nWA;
+    if (v0) e0 = WA[lane];
+    if (v1) e1 = WA[lane + 32];
+    auto overlaps = [&](const Seed& s0) {
+        return aFrag == s0.iFrag && s0.sjA == sjA && a1 + s0.rStart == s0.gStart + aRstart
+               && ((aRstart >= s0.rStart && aRstart < (u64)s0.rStart + s0.Length) || (aRstart + aLength >= s0.rStart && aRstart + aLength < (u64)s0.rStart + s0.Length));
+    };
+    Seed nsd;
+    setSeed(nsd, a1, aLength, aNrep, aFrag, aRstart, aAnchor, sjA);
+    {
+        u32 m0 = __ballot_sync(0xffffffffu, v0 && overlaps(e0));
+        u32 m1 = __ballot_sync(0xffffffffu, v1 && overlaps(e1));
+        int iA = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
+        if (iA >= 0) {
+            u32 LiA = __shfl_sync(0xffffffffu, iA < 32 ? (u32)e0.Length : (u32)e1.Length, iA & 31);
+            if (aLength > LiA) {
+                // insertion point: first iA0 != iA with aRstart < rStart, else nWA
+                u32 b0 = __ballot_sync(0xffffffffu, v0 && (int)lane != iA && aRstart < e0.rStart);
+                u32 b1 = __ballot_sync(0xffffffffu, v1 && (int)(lane + 32) != iA && aRstart < e1.rStart);
+                int iA0 = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : (int)nWA);
+                if (iA0 > iA) --iA0;
+                __syncwarp();
+                if (iA0 < iA) {   // elements iA0..iA-1 move up by one
+                    if (v0 && (int)lane >= iA0 && (int)lane < iA) WA[lane + 1] = e0;
+                    if (v1 && (int)(lane + 32) >= iA0 && (int)(lane + 32) < iA) WA[lane + 33] = e1;
+                } else if (iA0 > iA) {   // elements iA+1..iA0 move down by one
+                    if (v0 && (int)lane > iA && (int)lane <= iA0) WA[lane - 1] = e0;
+                    if (v1 && (int)(lane + 32) > iA && (int)(lane + 32) <= iA0) WA[lane + 31] = e1;
+                }
+                __syncwarp();
+                if (lane == 0) WA[iA0] = nsd;
+                __syncwarp();
+            }
+            return true;
+        }
+    }
+    if (nWA == P.seedPerWindowNmax) {
+        u32 rec = ln.Lread + 1;
+        if (v0 && e0.Anchor != 1 && e0.Length < rec) rec = e0.Length;
+        if (v1 && e1.Anchor != 1 && e1.Length < rec) rec = e1.Length;
+        rec = (u32)warpMinU64(rec);
+        if (lane == 0) Wp->WALrec = (u16)rec;
+        __syncwarp();
+        if (rec == ln.Lread + 1) return false;
+        if (!aAnchor && aLength < rec) return true;
+        const bool k0 = v0 && (e0.Anchor == 1 || e0.Length > rec), k1 = v1 && (e1.Anchor == 1 || e1.Length > rec);
+        const u32 km0 = __ballot_sync(0xffffffffu, k0), km1 = __ballot_sync(0xffffffffu, k1);
+        const u32 below = (1u << lane) - 1;
+        __syncwarp();
+        if (k0) WA[__popc(km0 & below)] = e0;
+        if (k1) WA[__popc(km0) + __popc(km1 & below)] = e1;
+        __syncwarp();
+        nWA = __popc(km0) + __popc(km1);
+        if (lane == 0) Wp->nWA = (u16)nWA;
+        __syncwarp();
+    }
+    const u32 WALrec = Wp->WALrec;
+    if (aAnchor || aLength > WALrec) {
+        // reload (the purge may have moved the seeds)
+        const bool w0 = lane < nWA, w1 = lane + 32 < nWA;
+        if (w0) e0 = WA[lane];
+        if (w1) e1 = WA[lane + 32];
+        u32 b0 = __ballot_sync(0xffffffffu, w0 && aRstart < e0.rStart);
+        u32 b1 = __ballot_sync(0xffffffffu, w1 && aRstart < e1.rStart);
+        int iA = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : (int)nWA);
+        __syncwarp();
+        if (w0 && (int)lane >= iA) WA[lane + 1] = e0;
+        if (w1 && (int)(lane + 32) >= iA) WA[lane + 33] = e1;
+        __syncwarp();
+        if (lane == 0) { WA[iA] = nsd; Wp->nWA = (u16)(nWA + 1); }
+        __syncwarp();
+    }
+    return true;
+}
+
+// Modes: heavyPool != NULL : the lane of stitch_kernel that owned the read exported its windows + seeds (DFS-heavy read);
+//        heavyPool == NULL : the read was routed here right after seeding because it has many loci (nA): the warp also does the
+//                            window creation / seed assignment cooperatively (coalesced SA loads, 32-wide scans).
 __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
-                                                     ReadInfo* __restrict__ info, u32 nHeavy, const u32* __restrict__ heavyList,
+                                                     ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nHeavy, const u32* __restrict__ heavyList,
                                                      const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
                                                      u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
                                                      star_align_t* __restrict__ staged, u32 smemStride, u8* __restrict__ scratch, HeavyScratch hs) {
@@ -1353,17 +1542,20 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     const u32 warpInBlock = threadIdx.x >> 5;
     const u32 warpsPerBlock = blockDim.x >> 5;
     const u32 gwarp = blockIdx.x * warpsPerBlock + warpInBlock;
-    // shared memory per warp: R0 | R2 | ticket counters
-    u8* R0 = smem + (size_t)warpInBlock * (2 * smemStride + 16);
+    // shared memory per warp: R0 | R2 | counters (32 B) | window table
+    const u32 perWarp = (2 * smemStride + 32 + caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+    u8* R0 = smem + (size_t)warpInBlock * perWarp;
     u8* R2 = R0 + smemStride;
     u32* sh = (u32*)(R0 + 2 * smemStride);   // [0] task ticket, [1] block bump, [2] overflow flag
+    Window* swin = (Window*)(R0 + 2 * smemStride + 32);
     Lane ln;
     DevTr curL, leafL;
-    Frame stackL[STAR_DFS_MAX_DEPTH];
-    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL;
+    Frame stackL[STAR_UNDO_DEPTH];
+    u8 phL[STAR_DFS_MAX_DEPTH + 4];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
     ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
-    {   // lane 0's arena of this warp holds the recording state (pool, pointer arrays, compacted window Chr/Str)
-        u8* a = arenas + (u64)(blockIdx.x * blockDim.x + warpInBlock * 32) * caps.arenaBytes;
+    {   // one arena per WARP: seeds of the windows + the recording state (pool, pointer arrays, compacted window Chr/Str)
+        u8* a = arenas + (u64)gwarp * caps.arenaBytes;
         ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
         ln.wa = (Seed*)a; a += (u64)caps.maxW * caps.spw * sizeof(Seed);
         ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
@@ -1374,11 +1566,13 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     }
     u8* ws = scratch + (u64)gwarp * hs.bytesPerWarp;
     const u32 W1 = (hs.maxWin + 2) & ~1u;                                   // even, >= maxWin+1
-    u32* taskStart = (u32*)ws;                                              // W1
-    u32* seedStart = taskStart + W1;                                        // W1
+    u32* taskStart = (u32*)ws;                                              // W1 : first task of window w (windows without seeds: empty range)
+    u32* seedStart = taskStart + W1;                                        // (unused slot kept for layout)
     u8* depthOf = (u8*)(seedStart + W1);                                    // W1 rounded to 8
     TaskOut* taskOut = (TaskOut*)(depthOf + ((W1 + 7) & ~7u));              // maxTasks (8-byte aligned)
     CandBlock* blocks = (CandBlock*)(taskOut + hs.maxTasks);                // maxBlocks
+    WarpWin ww;
+    ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
 
     long long hc[6] = {0, 0, 0, 0, 0, 0};
     for (;;) {
@@ -1390,62 +1584,206 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         const u32 i = heavyList[k];
         ReadInfo ri = info[i];
         readBegin(ln, ri);
-        const u8* rec = heavyPool + heavyOff[i];
-        const u32 nWin = ((const u32*)rec)[0];
-        const HeavyWin* hw = (const HeavyWin*)(rec + 8);
-        const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
+        const u32 Lread = ri.Lread;
+        if (ri.flags || ri.Lread < P.outFilterMatchNmin || ri.Nsplit == 0 || ri.nA == 0) {   // same early exits as stitch_kernel's fetch
+            if (lane == 0) {
+                if (ri.flags) {
+                    star_read_result_t res;
+                    res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+                    res.bestRLength = 0; res.Lread = ri.Lread; res.bestTr = 0;
+                    results[i] = res;
+                } else if (ri.Lread < P.outFilterMatchNmin) selectExport(ln, ri, i, STAR_MARKER_READ_TOO_SHORT, 0, results, staged, info);
+                else if (ri.Nsplit == 0) selectExport(ln, ri, i, STAR_MARKER_NO_GOOD_PIECES, ri.split1_0, results, staged, info);
+                else selectExport(ln, ri, i, STAR_MARKER_ALL_PIECES_EXCEED_seedMultimapNmax, ri.multNminL, results, staged, info);
+            }
+            __syncwarp();
+            continue;
+        }
         {   // read into shared memory (both orientations)
             const u8* g = reads + (u64)i * stride;
-            const u32 L = ri.Lread;
-            for (u32 b = lane; b < L; b += 32) {
+            for (u32 b = lane; b < Lread; b += 32) {
                 u8 c = g[b];
                 R0[b] = c;
-                R2[L - 1 - b] = c < 4 ? 3 - c : c;
+                R2[Lread - 1 - b] = c < 4 ? 3 - c : c;
             }
         }
-        // ---- task table (lane 0): split depth per window, prefix sums
-        u32 nTasks = 0;
-        if (lane == 0) {
-            sh[0] = 0; sh[1] = 0; sh[2] = 0;
-            if (nWin > hs.maxWin) { sh[2] = 1; }
-            else {
-                u32 shift = 0;
-                for (;;) {
-                    u32 tot = 0, sd = 0;
-                    for (u32 w = 0; w < nWin; w++) {
-                        u32 a = hw[w].nWA;
-                        u32 d = a <= 6 ? 0 : (a - 6 > 8 ? 8 : a - 6);
-                        d = d > shift ? d - shift : 0;
-                        taskStart[w] = tot; depthOf[w] = (u8)d; seedStart[w] = sd;
-                        tot += 1u << d; sd += a;
-                    }
-                    taskStart[nWin] = tot; seedStart[nWin] = sd;
-                    if (tot <= hs.maxTasks) { nTasks = tot; break; }
-                    shift++;
+        if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; }
+        __syncwarp();
+        u32 nWin = 0;
+        u32 overReason = 0;
+        bool tooManyAnchors = false;
+        u64 saEnum = 0;
+        if (heavyPool) {
+            // ---- mode A: import the exported windows + seeds
+            const u8* rec = heavyPool + heavyOff[i];
+            nWin = ((const u32*)rec)[0];
+            const HeavyWin* hw = (const HeavyWin*)(rec + 8);
+            const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
+            if (nWin > caps.maxW) { overReason = 5; nWin = 0; }
+            u32 sd = 0;
+            for (u32 w = 0; w < nWin; w++) {   // uniform loop; lanes copy the seeds of window w
+                const HeavyWin h = hw[w];
+                if (lane == 0) {
+                    Window nw; nw.gStart = 0; nw.gEnd = 0; nw.Chr = h.Chr; nw.nWA = h.nWA; nw.WALrec = 0; nw.Str = h.Str; nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
+                    swin[w] = nw;
                 }
+                for (u32 a = lane; a < h.nWA; a += 32) ln.wa[(u64)w * caps.spw + a] = seeds[sd + a];
+                sd += h.nWA;
+            }
+            ww.nW = nWin;
+        } else {
+            // ---- mode B: cooperative window creation and seed assignment (ReadAlign_stitchPieces.cpp:41-185)
+            const Piece* PC = pieces + (u64)i * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier
+            const u32 nP = ri.nP;
+            ww.nW = 0;
+            for (u32 iP = 0; iP < nP && !overReason; iP++) {
+                const Piece p = PC[iP];
+                if (p.Nrep > P.winAnchorMultimapNmax) continue;
+                const u64 aLength = p.Length;
+                bool stopPiece = false;
+                for (u64 base = 0; base < p.Nrep && !stopPiece && !overReason; base += 32) {
+                    const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
+                    u64 a1 = 0, a1A = 0; u32 aStr = 0; u32 kind = 0;   // kind: 0 skip, 1 genomic, 2 sjdb (donor a1, acceptor a1A)
+                    if (lane < nl) {
+                        a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
+                        aStr = (u32)(a1 >> ix.GstrandBit);
+                        a1 &= ix.GstrandMask;
+                        if (p.Dir == 1 && aStr == 0) { aStr = 1; }
+                        else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
+                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                        kind = 1;
+                        if (a1 >= ix.sjGstart) {
+                            u64 a1D, aLengthD, aLengthA; u32 sj1;
+                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) { a1 = a1D; kind = 2; } else kind = 0;
+                        }
+                    }
+                    for (u32 q = 0; q < nl; q++) {
+                        saEnum++;
+                        const u32 kq = __shfl_sync(0xffffffffu, kind, q);
+                        const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
+                        const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
+                        const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
+                        if (kq == 0) continue;
+                        int rc = coopCreateWindow(ln, ww, a1q, sq);
+                        if (rc == 0 && kq == 2) rc = coopCreateWindow(ln, ww, a1Aq, sq);
+                        if (rc == 102) { overReason = 1; break; }
+                        if (rc == 101) { stopPiece = true; break; }
+                    }
+                }
+            }
+            // flanks :96-118 (one window per lane)
+            for (u32 w = lane; w < ww.nW; w += 32) {
+                Window W = swin[w];
+                if (W.gStart <= W.gEnd) {
+                    u64 wb = W.gStart;
+                    for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
+                    W.gStart = (u32)wb;
+                    wb = W.gEnd;
+                    for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
+                    W.gEnd = (u32)wb;
+                }
+                W.nWA = 0; W.WALrec = 0;
+                swin[w] = W;
+            }
+            __syncwarp();
+            // assignment :129-185
+            for (u32 iP = 0; iP < nP && !overReason && !tooManyAnchors; iP++) {
+                const Piece p = PC[iP];
+                const u64 aNrep = p.Nrep, aLength = p.Length;
+                const u32 aFrag = p.iFrag;
+                const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
+                for (u64 base = 0; base < p.Nrep && !tooManyAnchors; base += 32) {
+                    const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
+                    u64 a1 = 0, a1A = 0, aRstart = 0, aLengthD = 0, aLengthA = 0; u32 aStr = 0, kind = 0, isj = SJA_NONE;
+                    int wD = -1, wA = -1;
+                    if (lane < nl) {
+                        a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
+                        aStr = (u32)(a1 >> ix.GstrandBit);
+                        a1 &= ix.GstrandMask;
+                        aRstart = p.rStart;
+                        if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
+                        else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
+                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                        kind = 1;
+                        if (a1 >= ix.sjGstart) {
+                            u64 a1D;
+                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj)) { a1 = a1D; kind = 2; } else { kind = 0; isj = SJA_NONE; }
+                        }
+                        if (kind) {   // window lookup: windows do not change during the assignment phase
+                            const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
+                            for (u32 w = 0; w < ww.nW; w++) {
+                                const Window W = swin[w];
+                                if (W.Str != aStr) continue;
+                                if (wD < 0 && W.gStart <= binD && binD <= W.gEnd) wD = (int)w;
+                                if (kind == 2 && wA < 0 && W.gStart <= binA && binA <= W.gEnd) wA = (int)w;
+                            }
+                        }
+                    }
+                    for (u32 q = 0; q < nl; q++) {
+                        saEnum++;
+                        const u32 kq = __shfl_sync(0xffffffffu, kind, q);
+                        if (kq == 0) continue;
+                        const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
+                        const u64 rq = __shfl_sync(0xffffffffu, aRstart, q);
+                        const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
+                        const int wDq = __shfl_sync(0xffffffffu, wD, q);
+                        if (kq == 1) {
+                            if (!coopAssign(ln, ww, wDq, a1q, aLength, aNrep, aFrag, rq, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
+                        } else {
+                            const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
+                            const u64 lDq = __shfl_sync(0xffffffffu, aLengthD, q), lAq = __shfl_sync(0xffffffffu, aLengthA, q);
+                            const u32 isjq = __shfl_sync(0xffffffffu, isj, q);
+                            const int wAq = __shfl_sync(0xffffffffu, wA, q);
+                            if (!coopAssign(ln, ww, wDq, a1q, lDq, aNrep, aFrag, rq, aAnchor, isjq)) { tooManyAnchors = true; break; }
+                            if (!coopAssign(ln, ww, wAq, a1Aq, lAq, aNrep, aFrag, rq + lDq, aAnchor, isjq)) { tooManyAnchors = true; break; }
+                        }
+                    }
+                }
+            }
+            if (tooManyAnchors) ww.nW = 0;
+            nWin = ww.nW;
+            ln.saEnum = saEnum;
+        }
+        __syncwarp();
+        // ---- task table (lane 0): split depth per window, prefix sums (windows without seeds get an empty task range)
+        u32 nTasks = 0;
+        if (lane == 0 && !overReason) {
+            u32 shift = 0;
+            for (;;) {
+                u32 tot = 0;
+                for (u32 w = 0; w < nWin; w++) {
+                    u32 a = swin[w].nWA;
+                    u32 d = a <= 6 ? 0 : (a - 6 > 8 ? 8 : a - 6);
+                    d = d > shift ? d - shift : 0;
+                    taskStart[w] = tot; depthOf[w] = (u8)d;
+                    if (a) tot += 1u << d;
+                }
+                taskStart[nWin] = tot;
+                if (tot <= hs.maxTasks) { nTasks = tot; break; }
+                shift++;
             }
         }
         __syncwarp();
         nTasks = __shfl_sync(0xffffffffu, nTasks, 0);
-        bool over = sh[2] != 0;
         long long t1 = clock64(); hc[0] += t1 - t0;
         // ---- E phase: lanes evaluate prefix sub-trees, lockstep over {fetch task, DFS node, leaf}
-        if (!over) {
+        if (!overReason) {
             u32 ph = 0;   // 0 fetch, 1 node, 2 leaf, 3 idle
             u32 tsk = 0, w = 0, Chr = 0, Str = 0, curBlock = 0xFFFFFFFFu;
-            const Seed* WA = seeds;
+            const Seed* WA = ln.wa;
             u32 nA = 0;
             for (;;) {
                 if (ph == 0) {
                     tsk = atomicAdd(&sh[0], 1u);
                     if (tsk >= nTasks || sh[2]) { ph = 3; }
                     else {
-                        // window of the task: last w with taskStart[w] <= tsk
+                        // window of the task: last w with taskStart[w] <= tsk (skipping empty ranges is automatic: taskStart[w+1] > tsk)
                         u32 lo = 0, hi = nWin;
                         while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (taskStart[mid] <= tsk) lo = mid; else hi = mid; }
                         w = lo;
-                        Chr = hw[w].Chr; Str = hw[w].Str; nA = hw[w].nWA;
-                        WA = seeds + seedStart[w];
+                        const Window W = swin[w];
+                        Chr = W.Chr; Str = W.Str; nA = W.nWA;
+                        WA = ln.wa + (u64)w * caps.spw;
                         ln.R = Str == 0 ? R0 : R2;
                         dfsInit(ln);
                         ln.forceDepth = depthOf[w];
@@ -1486,28 +1824,29 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
             }
         }
         __syncwarp();
-        // work counters of the E phase (nodes, leaves) summed over the lanes
-        {
+        {   // work counters of the E phase (nodes, leaves) summed over the lanes
             u64 nd = ln.nodes, lv = ln.leaves;
             for (int o = 16; o > 0; o >>= 1) { nd += __shfl_down_sync(0xffffffffu, nd, o); lv += __shfl_down_sync(0xffffffffu, lv, o); }
             ln.nodes = nd; ln.leaves = lv;   // meaningful on lane 0
         }
-        over = sh[2] != 0;
+        if (sh[2] != 0 && !overReason) overReason = 5;
         long long t2 = clock64(); hc[1] += t2 - t1; hc[3] += nTasks;
         // ---- R phase: lane 0 replays the order-dependent recording
         if (lane == 0) {
             ln.forceDepth = 0; ln.forceBits = 0;
-            if (over) {
-                ln.overflow = 5;   // reason 5: heavy-kernel scratch (tasks / candidate blocks / windows)
+            if (overReason) {
+                ln.overflow = overReason;
             } else {
                 for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
                 for (u32 w = 0; w < nWin && !ln.overflow; w++) {
+                    const Window W = swin[w];
+                    if (W.nWA == 0) continue;
                     u16* wTr = nullptr; u16 nWinTr = 0;
                     int rc = windowBegin(ln, wTr, nWinTr);
                     if (rc == 2) { ln.overflow = 3; break; }
                     if (rc == 1) break;
-                    const u32 Chr = hw[w].Chr, Str = hw[w].Str, nA = hw[w].nWA;
-                    const Seed* WA = seeds + seedStart[w];
+                    const u32 Chr = W.Chr, Str = W.Str, nA = W.nWA;
+                    const Seed* WA = ln.wa + (u64)w * caps.spw;
                     ln.R = Str == 0 ? R0 : R2;
                     for (u32 t = taskStart[w]; t < taskStart[w + 1] && !ln.overflow; t++) {
                         u32 b = taskOut[t].first;
@@ -1529,6 +1868,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                             b = B.next;
                         }
                     }
+                    // windowEnd compacts Chr/Str into ln.win[] (global arena), independent of the shared-memory table
                     windowEnd(ln, Chr, Str, wTr, nWinTr);
                 }
             }
@@ -1551,6 +1891,14 @@ __global__ void prof_read_kernel(unsigned long long* out, int reset) {
 __global__ void order_keys_kernel(const ReadInfo* __restrict__ info, u32 nReads, u32* __restrict__ keys, u32* __restrict__ vals) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nReads) { keys[i] = 0xFFFFFFFFu - info[i].nA; vals[i] = i; }
+}
+
+// number of reads routed to the warp-per-read kernel right after seeding (many genomic loci)
+__global__ void count_heavy_kernel(const ReadInfo* __restrict__ info, u32 nReads, u32 naLimit, u32* __restrict__ count) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool h = i < nReads && info[i].nA > naLimit;
+    u32 m = __ballot_sync(0xffffffffu, h);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
 
 // Compaction: results[i].trOffset = exclusive prefix sum of nTrOut; aligns[trOffset+k] = staged[i*nOut+k].

@@ -51,6 +51,42 @@ def test_engine_matches_oracle_tiny(lib, oracle, golden, tiny_index, name):
         assert getattr(st_g, k) == getattr(st_o, k), k
 
 
+@pytest.mark.parametrize("env", [
+    {"STAR_B200_HEAVY_EST": "0"},                                   # heavy path off: everything on the one-lane-per-read path
+    {"STAR_B200_HEAVY_NA": "0x7fffffff", "STAR_B200_HEAVY_EST": "1"},   # every read exported to the warp-per-read kernel (mode A)
+    {"STAR_B200_HEAVY_NA": "1"},                                    # every read with >1 locus: cooperative windows + DFS tasks (mode B)
+    {"STAR_B200_FAST_MAXW": "4", "STAR_B200_FAST_MAXTR": "4", "STAR_B200_FAST_MAXP": "8", "STAR_B200_MID_MAXW": "16", "STAR_B200_MID_MAXTR": "8"},  # tiny caps: overflow tiers
+])
+@pytest.mark.parametrize("name", ["std", "hard"])
+def test_engine_paths_are_all_exact(lib, oracle, golden, tiny_index, name, env):
+    """Every execution path of the engine (light lanes, both heavy-kernel modes, overflow tiers) must give the oracle's result."""
+    import oracle_capi as oc
+    import star_b200 as sb
+    files = _sets(golden)[name]
+    mates = [cf.read_fastq_seqs(f) for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    oe = oc.OracleEngine(oracle, tiny_index)
+    res_o, al_o, st_o = oe.map_chunk(seq, off, n, nm)
+    oe.close()
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            os.environ[k] = str(int(v, 0))
+        eng = sb.Engine(lib, tiny_index, max_reads=n)
+        res_g, al_g, st_g = eng.map_chunk(seq, off, n, nm)
+        eng.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
+    assert not diffs, "\n".join(diffs[:20])
+    for k in ("mmp_searches", "mmp_sai_words", "mmp_compare_calls", "mmp_bases_examined", "sa_enumerated"):
+        assert getattr(st_g, k) == getattr(st_o, k), k
+
+
 @pytest.mark.parametrize("name,extra", [("std", []), ("hard", []), ("se", []), ("std_opts", None)])
 def test_cli_matches_reference_golden(lib, golden, tmp_path, name, extra):
     """Drop-in CLI on the GPU vs outputs of the unmodified reference binary (committed goldens)."""
