@@ -29,6 +29,7 @@ struct HeavyArgs {
 };
 struct HeavyScratch {
     u32 maxTasks, maxBlocks, maxWin;
+    u32 trWords;
     u64 bytesPerWarp;
 };
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
@@ -409,7 +410,8 @@ static int launchHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks
     HeavyScratch hs;
     hs.maxTasks = c->heavyMaxTasks; hs.maxBlocks = c->heavyMaxBlocks; hs.maxWin = caps.maxW;
     const u32 W1 = (hs.maxWin + 2) & ~1u;
-    hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + 255) & ~255ULL;
+    hs.trWords = envU32("STAR_B200_HEAVY_TRWORDS", 1u << 17);   // 1 MB of stored transcripts per warp
+    hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + (u64)hs.trWords * 8 + 255) & ~255ULL;
     const u32 warps = (u32)gridBlocks * 4;
     const u64 need = (u64)warps * hs.bytesPerWarp;
     if (need > c->heavyScratchBytes) {

@@ -1332,13 +1332,16 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
 // iFrag}.  Then lane 0 replays the reference's order-dependent part (recordLeaf: maxScoreMate, record test, blocksOverlap dedup,
 // ordered insert) over the candidates in window order / task order / leaf order, re-materialising the transcript (replayPath +
 // evalLeaf) only for the few candidates that pass the record test.  Result: identical to the sequential recursion.
-struct Cand { u64 mask; int score; signed char iFrag; u8 pad[3]; };
+// trOff: offset (in 8-byte words) of the evaluated transcript stored by the lane for candidates that are likely to pass the record
+// test (saves the replay in the R phase); 0xFFFFFFFF = not stored, the R phase replays the path.
+struct Cand { u64 mask; u32 trOff; short score; signed char iFrag; u8 pad; };
 #define CAND_PER_BLOCK 31
 struct CandBlock { u32 next; u32 count; Cand c[CAND_PER_BLOCK]; };   // 8 + 31*16 = 504 bytes
 struct TaskOut { u32 first, last; };                                 // candidate blocks of a task (0xFFFFFFFF = none)
 
 struct HeavyScratch {     // per warp, in HBM
     u32 maxTasks, maxBlocks, maxWin;
+    u32 trWords;              // capacity (8-byte words) of the per-warp stored-transcript buffer
     u64 bytesPerWarp;
 };
 
@@ -1571,10 +1574,12 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     u8* depthOf = (u8*)(seedStart + W1);                                    // W1 rounded to 8
     TaskOut* taskOut = (TaskOut*)(depthOf + ((W1 + 7) & ~7u));              // maxTasks (8-byte aligned)
     CandBlock* blocks = (CandBlock*)(taskOut + hs.maxTasks);                // maxBlocks
+    u64* trBuf = (u64*)(blocks + hs.maxBlocks);                              // trWords
     WarpWin ww;
     ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
 
     long long hc[6] = {0, 0, 0, 0, 0, 0};
+    long long eU[3] = {0, 0, 0};
     for (;;) {
         long long t0 = clock64();
         u32 k = 0;
@@ -1607,7 +1612,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                 R2[Lread - 1 - b] = c < 4 ? 3 - c : c;
             }
         }
-        if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; }
+        if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
@@ -1770,9 +1775,14 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         if (!overReason) {
             u32 ph = 0;   // 0 fetch, 1 node, 2 leaf, 3 idle
             u32 tsk = 0, w = 0, Chr = 0, Str = 0, curBlock = 0xFFFFFFFFu;
+            int taskBest = 0;
             const Seed* WA = ln.wa;
             u32 nA = 0;
             for (;;) {
+                {   // lane-utilisation accounting of the E phase
+                    u32 mF = __ballot_sync(0xffffffffu, ph == 0), mN = __ballot_sync(0xffffffffu, ph == 1), mL = __ballot_sync(0xffffffffu, ph == 2);
+                    hc[5]++; eU[0] += __popc(mF); eU[1] += __popc(mN); eU[2] += __popc(mL);
+                }
                 if (ph == 0) {
                     tsk = atomicAdd(&sh[0], 1u);
                     if (tsk >= nTasks || sh[2]) { ph = 3; }
@@ -1790,6 +1800,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                         ln.forceBits = tsk - taskStart[w];
                         taskOut[tsk].first = 0xFFFFFFFFu; taskOut[tsk].last = 0xFFFFFFFFu;
                         curBlock = 0xFFFFFFFFu;
+                        taskBest = 0;
                         ph = 1;
                     }
                 }
@@ -1812,7 +1823,22 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                             curBlock = nb;
                         }
                         if (curBlock != 0xFFFFFFFFu) {
-                            Cand c; c.mask = ln.inclMask; c.score = ln.leaf->h.maxScore; c.iFrag = ln.leaf->h.iFrag; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+                            const int sc = ln.leaf->h.maxScore;
+                            Cand c; c.mask = ln.inclMask; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = 0xFFFFFFFFu;
+                            if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
+                                if (sc > taskBest) taskBest = sc;
+                                const u32 nEx = ln.leaf->h.nExons;
+                                const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
+                                u32 off = atomicAdd(&sh[3], words);
+                                if (off + words <= hs.trWords) {
+                                    u64* dst = trBuf + off;
+                                    const u64* sh8 = (const u64*)&ln.leaf->h;
+                                    for (u32 q = 0; q < sizeof(TrHead) / 8; q++) dst[q] = sh8[q];
+                                    const u64* se = (const u64*)ln.leaf->ex;
+                                    for (u32 q = 0; q < nEx * (sizeof(Exon) / 8); q++) dst[sizeof(TrHead) / 8 + q] = se[q];
+                                    c.trOff = off;
+                                }
+                            }
                             CandBlock& B = blocks[curBlock];
                             B.c[B.count] = c;
                             B.count++;
@@ -1859,10 +1885,20 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                                 if (c.score + P.outFilterMultimapScoreRange >= wBest ||
                                     (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
                                     if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; break; }
-                                    int Score; u32 tR2; u64 tG2;
-                                    hc[4]++;
-                                    bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
-                                    if (ok) recordLeaf(ln, wTr, &nWinTr);
+                                    if (c.trOff != 0xFFFFFFFFu) {   // transcript stored by the lane that evaluated the leaf
+                                        const u64* src = trBuf + c.trOff;
+                                        u64* dh = (u64*)&ln.leaf->h;
+                                        for (u32 z = 0; z < sizeof(TrHead) / 8; z++) dh[z] = src[z];
+                                        const u32 nEx = ln.leaf->h.nExons;
+                                        u64* de = (u64*)ln.leaf->ex;
+                                        for (u32 z = 0; z < nEx * (sizeof(Exon) / 8); z++) de[z] = src[sizeof(TrHead) / 8 + z];
+                                        recordLeaf(ln, wTr, &nWinTr);
+                                    } else {
+                                        int Score; u32 tR2; u64 tG2;
+                                        hc[4]++;
+                                        bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                        if (ok) recordLeaf(ln, wTr, &nWinTr);
+                                    }
                                 }
                             }
                             b = B.next;
@@ -1877,7 +1913,8 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         __syncwarp();
         hc[2] += clock64() - t2;
     }
-    for (int q = 0; q < 5; q++) PROF_ADD(16 + q, hc[q]);
+    for (int q = 0; q < 6; q++) PROF_ADD(16 + q, hc[q]);
+    for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
 }
 
 __global__ void prof_read_kernel(unsigned long long* out, int reset) {
