@@ -30,6 +30,7 @@ struct HeavyArgs {
 struct HeavyScratch {
     u32 maxTasks, maxBlocks, maxWin;
     u32 trWords;
+    u32 memoSlots;
     u64 bytesPerWarp;
 };
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
@@ -99,7 +100,7 @@ struct star_ctx {
     u8* d_heavyScratch = nullptr;
     u32 heavyEst = 1024; u32 heavyNA = 64; u32 heavyMaxTasks = 8192, heavyMaxBlocks = 4096;
     Caps heavyCaps; u8* d_arenaHeavy = nullptr;   // per-WARP arenas of the warp-per-read kernel (bigger caps than the per-lane fast arenas)
-    u64 heavyScratchBytes = 0; u64 lastHeavy = 0;
+    u64 heavyScratchBytes = 0; u64 heavyScratchStride = 0; u64 lastHeavy = 0;
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
     // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
@@ -332,7 +333,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     }
     if (c->heavyEst) {
         c->heavyCaps = c->fast;
-        c->heavyCaps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_HEAVY_MAXW", 1024)) + 1) & ~1u;
+        c->heavyCaps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_HEAVY_MAXW", 256)) + 1) & ~1u;
         c->heavyCaps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_HEAVY_MAXTR", 1024));
         c->heavyCaps.arenaBytes = arenaSize(c->heavyCaps);
     }
@@ -411,16 +412,24 @@ static int launchHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks
     hs.maxTasks = c->heavyMaxTasks; hs.maxBlocks = c->heavyMaxBlocks; hs.maxWin = caps.maxW;
     const u32 W1 = (hs.maxWin + 2) & ~1u;
     hs.trWords = envU32("STAR_B200_HEAVY_TRWORDS", 1u << 17);   // 1 MB of stored transcripts per warp
-    hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + (u64)hs.trWords * 8 + 255) & ~255ULL;
+    hs.memoSlots = envU32("STAR_B200_HEAVY_MEMO", 0);   // measured: most stitches live in windows with <10 seeds where pairs rarely repeat; off by default          // stitch memo entries per warp (power of two, 0 = off)
+    if (hs.memoSlots & (hs.memoSlots - 1)) { g_err = "STAR_B200_HEAVY_MEMO must be a power of two"; return STAR_EXIT_PARAMETER; }
+    hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + (u64)hs.trWords * 8 + 8 + (u64)hs.memoSlots * 72 + 255) & ~255ULL;
     const u32 warps = (u32)gridBlocks * 4;
     const u64 need = (u64)warps * hs.bytesPerWarp;
+    if (need <= c->heavyScratchBytes && hs.bytesPerWarp != c->heavyScratchStride) {
+        CK(cudaMemsetAsync(c->d_heavyScratch, 0, c->heavyScratchBytes, c->stream));   // layout changed (other tier): forget memo / epochs
+        c->heavyScratchStride = hs.bytesPerWarp;
+    }
     if (need > c->heavyScratchBytes) {
         if (c->d_heavyScratch) cudaFree(c->d_heavyScratch);
         CK(cudaMalloc((void**)&c->d_heavyScratch, need));
+        CK(cudaMemsetAsync(c->d_heavyScratch, 0, need, c->stream));   // memo keys / epochs start at zero
         c->heavyScratchBytes = need;
+        c->heavyScratchStride = hs.bytesPerWarp;
     }
     CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-    const u32 perWarp = (2 * c->smemStride + 32 + caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+    const u32 perWarp = (2 * c->smemStride + 32 + caps.maxW * (u32)sizeof(Window) + (caps.maxW + 4) * 4 + ((caps.maxW + 3) & ~3u) + 15) & ~15u;
     const u32 smem = 4 * perWarp;
     if (smem > 200 * 1024) { g_err = "star_b200: heavy kernel shared memory exceeds the limit for this tier"; return STAR_EXIT_RUNTIME; }
     stitch_heavy_kernel<<<gridBlocks, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, pieces, nHeavy, list, c->d_heavyOff,
@@ -538,7 +547,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
             HeavyArgs hv = heavyArgs(c);
-            const u32 perWarpH = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+            const u32 perWarpH = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + (T.caps.maxW + 4) * 4 + ((T.caps.maxW + 3) & ~3u) + 15) & ~15u;
             const bool heavyOk = c->heavyEst && 4 * perWarpH <= 200 * 1024;   // the last tier (reference limits) has no shared-memory window table
             if (!heavyOk) hv.estLimit = 0;
             stitch_kernel<<<grid, 128, smemStitch, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, m, c->d_list + lo,

@@ -32,6 +32,7 @@ namespace starb {
 __device__ unsigned long long g_prof[32];
 #define PROF_ADD(slot, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
 
+#define HEAVY_SPLIT_MIN 6        // heavy kernel: windows with more seeds than this are cut into 2^(nWA-6) (max 256) prefix sub-trees
 #define LOCI_PER_STEP 1          // SA loci handled per lockstep step (their SA words are loaded back to back, latency overlapped)
 #define STAR_DFS_MAX_DEPTH 52   // seedPerWindowNmax (<=50 on the local-memory fast build) + 2
 
@@ -83,6 +84,12 @@ struct Lane {
     u32 leafR2;
     u64 leafG2;
     u64 inclMask;        // bit k set <=> seed k of the window is included on the current DFS path
+    u32 memoNMM; bool memoMotifOk;   // set by stitchAlignToTranscript: mismatches of this stitch / junction-motif rule
+    struct StitchMemo* memo;         // heavy kernel: per-warp table of same-fragment stitch results (NULL = off)
+    u32 memoMask;                    // slots-1
+    u64 memoBase;                    // (epoch, window) part of the key
+    int lastSeed;                    // index of the last included seed on the current path (-1 = none)
+    u64 memoHit, memoMiss;
     u32 forceDepth;      // heavy path: the first forceDepth include/exclude decisions are fixed (prefix sub-tree task)
     u32 forceBits;       // bit (forceDepth-1-k) set <=> seed k is EXCLUDED (so that ascending task id = DFS order, include first)
     // per-read stitching state (ReadAlign_stitchPieces.cpp:262-350)
@@ -356,8 +363,9 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                 jCan = -2;
             }
 
-            if ((h.nMM + nMM) <= outFilterMismatchNmaxTotal
-                && (jCan < 0 || (jCan < 7 && nMM <= (u64)(i64)P.alignSJstitchMismatchNmax[(jCan + 1) / 2]))) {
+            const bool motifOk = (jCan < 0 || (jCan < 7 && nMM <= (u64)(i64)P.alignSJstitchMismatchNmax[(jCan + 1) / 2]));
+            ln.memoNMM = (u32)nMM; ln.memoMotifOk = motifOk;   // (for the stitch memo of the heavy kernel)
+            if ((h.nMM + nMM) <= outFilterMismatchNmaxTotal && motifOk) {
                 h.nMM += (u32)nMM;
                 h.nMatch += (u32)nMatch;
                 if (Del >= P.alignIntronMin) { h.nGap += (u32)nDel; h.lGap += (u32)Del; }
@@ -619,6 +627,85 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
     }
 }
 
+// ---- stitch memo (heavy kernel).  Inside one window the include/exclude enumeration stitches the same ordered pair of seeds
+// (A = last included seed, B = candidate) over and over under different earlier choices.  For seeds of the same mate the result of
+// stitchAlignToTranscript is a pure function of (A, B, current length of A's exon) except for the final test on the TOTAL number
+// of mismatches, which is re-evaluated on every use.  Entries are published with a seqlock-style key so that lanes of the warp
+// can share the table without locks; a lost race only costs a recomputation.
+struct StitchMemo {
+    volatile u64 key;     // 0 = empty / being written
+    int dScore;           // <= -1000000: the pair never stitches (independent of the path)
+    u32 nMM, nMatch;
+    u32 dGapN, dGapL, dDelN, dDelL, dInsN, dInsL;
+    u64 eB_G;
+    u16 eB_R, eB_L, eA_L, shL, shR;
+    signed char canon;
+    u8 annot, sjStr;
+};
+
+static_assert(sizeof(StitchMemo) == 72, "engine_api.cu sizes the memo table with 72-byte entries");
+
+__device__ int stitchMemoized(Lane& ln, u64 rAend, u64 gAend, const Seed& s, u32 bIdx, DevTr* t, bool& wasHit) {
+    wasHit = false;
+    TrHead& h = t->h;
+    if (!ln.memo || ln.lastSeed < 0 || h.nExons >= STAR_MAX_N_EXONS || t->ex[h.nExons - 1].iFrag != s.iFrag)
+        return stitchAlignToTranscript(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+    Exon& eA = t->ex[h.nExons - 1];
+    {   // the two cheapest outcomes are not worth a table access: B ends inside A in read or genome space (:53-54).  The sjdb shortcut
+        // (:18) is tested first by the reference, so it must not apply here.
+        const bool sjdbDirect = s.sjA != SJA_NONE && eA.sjA == s.sjA && (u64)s.rStart == rAend + 1 && gAend + 1 < s.gStart;
+        if (!sjdbDirect) {
+            if ((u64)s.rStart + s.Length - 1 <= rAend) { eA.annot = 0; eA.sjStr = 0; return -1000001; }
+            if (s.gStart + s.Length - 1 <= gAend) { eA.annot = 0; eA.sjStr = 0; return -1000002; }
+        }
+    }
+    const u64 key = ln.memoBase | ((u64)(u32)ln.lastSeed << 22) | ((u64)bIdx << 16) | (u64)eA.L;
+    StitchMemo* m = ln.memo + (u32)((key * 0x9E3779B97F4A7C15ULL) >> 40 & ln.memoMask);
+    if (m->key == key) {
+        const int dScore = m->dScore;
+        const u32 nMM = m->nMM, nMatch = m->nMatch, dGapN = m->dGapN, dGapL = m->dGapL, dDelN = m->dDelN, dDelL = m->dDelL, dInsN = m->dInsN, dInsL = m->dInsL;
+        const u64 eB_G = m->eB_G;
+        const u16 eB_R = m->eB_R, eB_L = m->eB_L, eA_L = m->eA_L, shL = m->shL, shR = m->shR;
+        const signed char canon = m->canon; const u8 annot = m->annot, sjStr = m->sjStr;
+        __threadfence_block();
+        if (m->key == key) {   // the entry was not replaced while it was read
+            wasHit = true;
+            ln.memoHit++;
+            if (dScore <= -1000000) return dScore;
+            if (h.nMM + nMM > ln.outFilterMismatchNmaxTotal) return -1000007;   // the only path-dependent test (stitchAlignToTranscript.cpp:314)
+            Exon& eB = t->ex[h.nExons];
+            eA.L = eA_L; eA.canon = canon; eA.annot = annot; eA.sjStr = sjStr; eA.shL = shL; eA.shR = shR;
+            eB.R = eB_R; eB.G = eB_G; eB.L = eB_L; eB.iFrag = s.iFrag; eB.sjA = s.sjA;
+            h.nMM += nMM; h.nMatch += nMatch; h.nGap += dGapN; h.lGap += dGapL; h.nDel += dDelN; h.lDel += dDelL; h.nIns += dInsN; h.lIns += dInsL;
+            h.nExons++;
+            return dScore;
+        }
+    }
+    // miss: compute, then publish
+    ln.memoMiss++;
+    const TrHead h0 = h;
+    ln.memoMotifOk = true; ln.memoNMM = 0;
+    const int dScore = stitchAlignToTranscript(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+    bool cache = true;
+    if (dScore == -1000007 && ln.memoMotifOk) cache = false;   // failed only because of the total mismatch count of THIS path
+    if (cache && atomicExch((unsigned long long*)&m->key, 1ULL) != 1ULL) {   // 1 = slot locked by another lane: skip publishing
+        __threadfence_block();
+        m->dScore = dScore;
+        if (dScore > -1000000) {
+            const Exon& a = t->ex[h0.nExons - 1];
+            const Exon& b = t->ex[h0.nExons];
+            m->nMM = h.nMM - h0.nMM; m->nMatch = h.nMatch - h0.nMatch;
+            m->dGapN = h.nGap - h0.nGap; m->dGapL = h.lGap - h0.lGap; m->dDelN = h.nDel - h0.nDel; m->dDelL = h.lDel - h0.lDel;
+            m->dInsN = h.nIns - h0.nIns; m->dInsL = h.lIns - h0.lIns;
+            m->eB_G = b.G; m->eB_R = b.R; m->eB_L = b.L; m->eA_L = a.L; m->shL = a.shL; m->shR = a.shR;
+            m->canon = a.canon; m->annot = a.annot; m->sjStr = a.sjStr;
+        }
+        __threadfence_block();
+        m->key = key;
+    }
+    return dScore;
+}
+
 // stitchWindowAligns.cpp:8-353 as an explicit DFS with undo records (see file header).
 // dfsInit starts a window; dfsStep runs the cheap bookkeeping transitions (undo, pop) until it has executed ONE seed-include
 // attempt (one stitchAlignToTranscript call), reached a leaf, or emptied the stack.  One call = one unit of work of the
@@ -632,6 +719,7 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
     ln.cur->h = z;
     ln.inclMask = 0;
     ln.level = 0; ln.nInc = 0; ln.Score = 0; ln.tR2 = 0; ln.tG2 = 0;
+    ln.lastSeed = -1;
     ln.ph[0] = 0;
 }
 
@@ -648,6 +736,7 @@ __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
             if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
             t->h = u.h;
             ln.Score = u.Score; ln.tR2 = u.tR2; ln.tG2 = u.tG2;
+            ln.lastSeed = (int)u.pad[0] - 1;
             ln.inclMask &= ~(1ULL << L);
             ln.ph[L] = 2;
             ln.level = L + 1;
@@ -664,6 +753,7 @@ __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
 #define DFS_DONE 2
 __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
     DevTr* t = ln.cur;
+    int runAhead = 0;
     for (;;) {
         if (ln.level < 0) return DFS_DONE;
         const u32 L = (u32)ln.level;
@@ -696,9 +786,11 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
         u.h = t->h;
         if (t->h.nExons > 0) u.last = t->ex[t->h.nExons - 1];
         u.Score = ln.Score; u.tR2 = ln.tR2; u.tG2 = ln.tG2;
+        u.pad[0] = (u32)(ln.lastSeed + 1);
         int dScore = 0;
+        bool cheap = false;
         if (t->h.nExons > 0) {
-            dScore = stitchAlignToTranscript(ln, ln.tR2, ln.tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+            dScore = stitchMemoized(ln, ln.tR2, ln.tG2, s, L, t, cheap);
         } else {
             t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
             t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
@@ -707,12 +799,14 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             t->h.nExons = 1;
             dScore = s.Length;
             t->h.nMatch = s.Length;
+            cheap = true;
         }
         if (dScore > -1000000) {
             if (s.Nrep == 1) t->h.nUnique++;
             if (s.Anchor > 0) t->h.nAnchor++;
             ln.inclMask |= 1ULL << L;
             ln.nInc++;
+            ln.lastSeed = (int)L;
             ln.ph[L] = forced ? 3 : 1;   // a forced include never explores its exclude branch
             ln.Score += dScore; ln.tR2 = (u32)s.rStart + s.Length - 1; ln.tG2 = s.gStart + s.Length - 1;
         } else {
@@ -723,6 +817,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
         }
         ln.level = (int)L + 1;
         ln.ph[L + 1] = 0;
+        if (cheap && ++runAhead < 24) continue;   // memo hits / first seeds cost nothing: keep going inside this step
         return DFS_CONTINUE;
     }
 }
@@ -1068,6 +1163,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
     u8 phL[STAR_DFS_MAX_DEPTH + 4];
     ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
     ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1;
     {
         u8* a = arenas + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * caps.arenaBytes;
         ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
@@ -1342,6 +1438,7 @@ struct TaskOut { u32 first, last; };                                 // candidat
 struct HeavyScratch {     // per warp, in HBM
     u32 maxTasks, maxBlocks, maxWin;
     u32 trWords;              // capacity (8-byte words) of the per-warp stored-transcript buffer
+    u32 memoSlots;            // stitch memo entries per warp (power of two; 0 = off)
     u64 bytesPerWarp;
 };
 
@@ -1354,7 +1451,8 @@ __device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 ma
         const Seed s = WA[iA];
         int dScore;
         if (t->h.nExons > 0) {
-            dScore = stitchAlignToTranscript(ln, tR2, tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+            bool hit;
+            dScore = stitchMemoized(ln, tR2, tG2, s, iA, t, hit);
         } else {
             t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
             t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
@@ -1365,6 +1463,7 @@ __device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 ma
             t->h.nMatch = s.Length;
         }
         if (dScore <= -1000000) return false;
+        ln.lastSeed = (int)iA;
         if (s.Nrep == 1) t->h.nUnique++;
         if (s.Anchor > 0) t->h.nAnchor++;
         Score += dScore;
@@ -1546,11 +1645,13 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     const u32 warpsPerBlock = blockDim.x >> 5;
     const u32 gwarp = blockIdx.x * warpsPerBlock + warpInBlock;
     // shared memory per warp: R0 | R2 | counters (32 B) | window table
-    const u32 perWarp = (2 * smemStride + 32 + caps.maxW * (u32)sizeof(Window) + 15) & ~15u;
+    const u32 perWarp = (2 * smemStride + 32 + caps.maxW * (u32)sizeof(Window) + (caps.maxW + 4) * 4 + ((caps.maxW + 3) & ~3u) + 15) & ~15u;
     u8* R0 = smem + (size_t)warpInBlock * perWarp;
     u8* R2 = R0 + smemStride;
-    u32* sh = (u32*)(R0 + 2 * smemStride);   // [0] task ticket, [1] block bump, [2] overflow flag
+    u32* sh = (u32*)(R0 + 2 * smemStride);   // [0] task ticket, [1] block bump, [2] overflow flag, [3] stored-transcript bump
     Window* swin = (Window*)(R0 + 2 * smemStride + 32);
+    u32* taskStart = (u32*)(swin + caps.maxW);            // maxW+1 (+pad): first task of window w (windows without seeds: empty range)
+    u8* depthOf = (u8*)(taskStart + caps.maxW + 4);       // maxW
     Lane ln;
     DevTr curL, leafL;
     Frame stackL[STAR_UNDO_DEPTH];
@@ -1569,12 +1670,14 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     }
     u8* ws = scratch + (u64)gwarp * hs.bytesPerWarp;
     const u32 W1 = (hs.maxWin + 2) & ~1u;                                   // even, >= maxWin+1
-    u32* taskStart = (u32*)ws;                                              // W1 : first task of window w (windows without seeds: empty range)
-    u32* seedStart = taskStart + W1;                                        // (unused slot kept for layout)
-    u8* depthOf = (u8*)(seedStart + W1);                                    // W1 rounded to 8
-    TaskOut* taskOut = (TaskOut*)(depthOf + ((W1 + 7) & ~7u));              // maxTasks (8-byte aligned)
+    TaskOut* taskOut = (TaskOut*)(ws + (u64)W1 * 8 + ((W1 + 7) & ~7u));     // maxTasks (8-byte aligned; the leading area is unused now)
     CandBlock* blocks = (CandBlock*)(taskOut + hs.maxTasks);                // maxBlocks
     u64* trBuf = (u64*)(blocks + hs.maxBlocks);                              // trWords
+    u64* epochPtr = trBuf + hs.trWords;                                      // persistent per-warp epoch of the stitch memo
+    StitchMemo* memoTab = (StitchMemo*)(epochPtr + 1);                       // memoSlots (zeroed once at allocation)
+    const bool memoOn = hs.memoSlots != 0 && caps.maxW <= 4096;
+    ln.memo = memoOn ? memoTab : nullptr; ln.memoMask = hs.memoSlots - 1; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1;
+    u64 epoch = *epochPtr;
     WarpWin ww;
     ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
 
@@ -1613,6 +1716,11 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
             }
         }
         if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
+        epoch++;
+        if (memoOn && (epoch & 0xFFFFFFULL) == 0) {   // 24-bit epoch wrapped: forget everything
+            for (u32 q = lane; q < hs.memoSlots; q += 32) memoTab[q].key = 0;
+            epoch++;
+        }
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
@@ -1758,7 +1866,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                 u32 tot = 0;
                 for (u32 w = 0; w < nWin; w++) {
                     u32 a = swin[w].nWA;
-                    u32 d = a <= 6 ? 0 : (a - 6 > 8 ? 8 : a - 6);
+                    u32 d = a <= HEAVY_SPLIT_MIN ? 0 : (a - HEAVY_SPLIT_MIN > 8 ? 8 : a - HEAVY_SPLIT_MIN);
                     d = d > shift ? d - shift : 0;
                     taskStart[w] = tot; depthOf[w] = (u8)d;
                     if (a) tot += 1u << d;
@@ -1798,6 +1906,8 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                         dfsInit(ln);
                         ln.forceDepth = depthOf[w];
                         ln.forceBits = tsk - taskStart[w];
+                        ln.memoBase = ((epoch & 0xFFFFFFULL) << 40) | ((u64)w << 28);
+                        ln.memo = (memoOn && nA >= 10) ? memoTab : nullptr;   // repetition only pays in windows with many seeds
                         taskOut[tsk].first = 0xFFFFFFFFu; taskOut[tsk].last = 0xFFFFFFFFu;
                         curBlock = 0xFFFFFFFFu;
                         taskBest = 0;
@@ -1874,6 +1984,8 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                     const u32 Chr = W.Chr, Str = W.Str, nA = W.nWA;
                     const Seed* WA = ln.wa + (u64)w * caps.spw;
                     ln.R = Str == 0 ? R0 : R2;
+                    ln.memoBase = ((epoch & 0xFFFFFFULL) << 40) | ((u64)w << 28);
+                    ln.memo = (memoOn && nA >= 10) ? memoTab : nullptr;
                     for (u32 t = taskStart[w]; t < taskStart[w + 1] && !ln.overflow; t++) {
                         u32 b = taskOut[t].first;
                         while (b != 0xFFFFFFFFu && !ln.overflow) {
@@ -1913,8 +2025,14 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         __syncwarp();
         hc[2] += clock64() - t2;
     }
+    if (lane == 0) *epochPtr = epoch;
     for (int q = 0; q < 6; q++) PROF_ADD(16 + q, hc[q]);
     for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
+    {
+        u64 hsum = ln.memoHit, msum = ln.memoMiss;
+        for (int o = 16; o > 0; o >>= 1) { hsum += __shfl_down_sync(0xffffffffu, hsum, o); msum += __shfl_down_sync(0xffffffffu, msum, o); }
+        PROF_ADD(25, hsum); PROF_ADD(26, msum);
+    }
 }
 
 __global__ void prof_read_kernel(unsigned long long* out, int reset) {

@@ -55,6 +55,7 @@ def test_engine_matches_oracle_tiny(lib, oracle, golden, tiny_index, name):
     {"STAR_B200_HEAVY_EST": "0"},                                   # heavy path off: everything on the one-lane-per-read path
     {"STAR_B200_HEAVY_NA": "0x7fffffff", "STAR_B200_HEAVY_EST": "1"},   # every read exported to the warp-per-read kernel (mode A)
     {"STAR_B200_HEAVY_NA": "1"},                                    # every read with >1 locus: cooperative windows + DFS tasks (mode B)
+    {"STAR_B200_HEAVY_NA": "1", "STAR_B200_HEAVY_MEMO": "256"},     # the same with the (optional) shared stitch memo switched on
     {"STAR_B200_FAST_MAXW": "4", "STAR_B200_FAST_MAXTR": "4", "STAR_B200_FAST_MAXP": "8", "STAR_B200_MID_MAXW": "16", "STAR_B200_MID_MAXTR": "8"},  # tiny caps: overflow tiers
 ])
 @pytest.mark.parametrize("name", ["std", "hard"])

@@ -44,6 +44,7 @@ for k in range(3):
     print("heavy kernel warp-cycles [setup, E, R]: " + " ".join("%.1f%%" % (100.0 * float(x) / th) for x in prof[16:19]) + "  total %.3g; tasks %d replays %d" % (th, prof[19], prof[20]))
     it = float(prof[21]) or 1.0
     print("heavy E-phase: iterations/warp-sum %.3g, avg active lanes: fetch %.2f node %.2f leaf %.2f" % (it, prof[22] / it, prof[23] / it, prof[24] / it))
+    print("stitch memo: hits %d misses %d" % (prof[25], prof[26]))
     print("run", k, {k2: round(v, 2) if isinstance(v, float) else v for k2, v in st.as_dict().items()})
 info = np.zeros(n, dtype=INFO)
 rc = lib.star_gpu_debug_read_info(eng.ctx, info.ctypes.data, info.nbytes)
