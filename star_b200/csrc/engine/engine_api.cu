@@ -31,6 +31,7 @@ struct HeavyScratch {
     u32 maxTasks, maxBlocks, maxWin;
     u32 trWords;
     u32 memoSlots;
+    u32 splitMin;
     u64 bytesPerWarp;
 };
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
@@ -412,6 +413,7 @@ static int launchHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks
     hs.maxTasks = c->heavyMaxTasks; hs.maxBlocks = c->heavyMaxBlocks; hs.maxWin = caps.maxW;
     const u32 W1 = (hs.maxWin + 2) & ~1u;
     hs.trWords = envU32("STAR_B200_HEAVY_TRWORDS", 1u << 17);   // 1 MB of stored transcripts per warp
+    hs.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 6);
     hs.memoSlots = envU32("STAR_B200_HEAVY_MEMO", 0);   // measured: most stitches live in windows with <10 seeds where pairs rarely repeat; off by default          // stitch memo entries per warp (power of two, 0 = off)
     if (hs.memoSlots & (hs.memoSlots - 1)) { g_err = "STAR_B200_HEAVY_MEMO must be a power of two"; return STAR_EXIT_PARAMETER; }
     hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + (u64)hs.trWords * 8 + 8 + (u64)hs.memoSlots * 72 + 255) & ~255ULL;

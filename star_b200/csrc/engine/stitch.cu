@@ -782,6 +782,24 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             continue;
         }
         const Seed s = WA[L];
+        if (t->h.nExons > 0) {
+            // The most frequent outcomes of an include attempt change nothing: the transcript is full (:13) or seed B ends inside the
+            // last included seed in read or genome space (:53-54; tested after the sjdb shortcut :18).  Decide them before any state is saved.
+            const Exon& eA = t->ex[t->h.nExons - 1];
+            bool quickFail = t->h.nExons >= STAR_MAX_N_EXONS;
+            if (!quickFail && eA.iFrag == s.iFrag) {
+                const bool sjdbDirect = s.sjA != SJA_NONE && eA.sjA == s.sjA && (u64)s.rStart == (u64)ln.tR2 + 1 && ln.tG2 + 1 < s.gStart;
+                quickFail = !sjdbDirect && ((u64)s.rStart + s.Length - 1 <= ln.tR2 || s.gStart + s.Length - 1 <= ln.tG2);
+            }
+            if (quickFail) {
+                if (forced) { ln.level = -1; return DFS_DONE; }
+                ln.ph[L] = 2;
+                ln.level = (int)L + 1;
+                ln.ph[L + 1] = 0;
+                if (++runAhead < 64) continue;
+                return DFS_CONTINUE;
+            }
+        }
         Frame& u = ln.stack[ln.nInc];
         u.h = t->h;
         if (t->h.nExons > 0) u.last = t->ex[t->h.nExons - 1];
@@ -817,7 +835,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
         }
         ln.level = (int)L + 1;
         ln.ph[L + 1] = 0;
-        if (cheap && ++runAhead < 24) continue;   // memo hits / first seeds cost nothing: keep going inside this step
+        if (cheap && ++runAhead < 64) continue;   // memo hits / first seeds cost nothing: keep going inside this step
         return DFS_CONTINUE;
     }
 }
@@ -1439,6 +1457,7 @@ struct HeavyScratch {     // per warp, in HBM
     u32 maxTasks, maxBlocks, maxWin;
     u32 trWords;              // capacity (8-byte words) of the per-warp stored-transcript buffer
     u32 memoSlots;            // stitch memo entries per warp (power of two; 0 = off)
+    u32 splitMin;             // windows with more seeds than this are cut into 2^(nWA-splitMin) (max 256) prefix sub-trees
     u64 bytesPerWarp;
 };
 
@@ -1866,7 +1885,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
                 u32 tot = 0;
                 for (u32 w = 0; w < nWin; w++) {
                     u32 a = swin[w].nWA;
-                    u32 d = a <= HEAVY_SPLIT_MIN ? 0 : (a - HEAVY_SPLIT_MIN > 8 ? 8 : a - HEAVY_SPLIT_MIN);
+                    u32 d = a <= hs.splitMin ? 0 : (a - hs.splitMin > 8 ? 8 : a - hs.splitMin);
                     d = d > shift ? d - shift : 0;
                     taskStart[w] = tot; depthOf[w] = (u8)d;
                     if (a) tot += 1u << d;
