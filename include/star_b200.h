@@ -275,6 +275,13 @@ size_t star_abi_sizeof(int which);
  * source/STAR.cpp:58-313).  Returns the process exit code. */
 int star_cli_main(int argc, char** argv);
 
+/* Multi-GPU: every rank runs the command line with --gpuShardIndex r --gpuShardCount R --outFileNamePrefix <prefix>shard<r>.
+ * and maps a contiguous slice of the reads; after an allreduce(sum) of the 24 Log.final.out counters (Stats.h:11-24) rank 0 calls
+ * this with the ORIGINAL command line (prefix <prefix>) to concatenate the SAM shards in order, run the reference's global junction
+ * collapse + filters (outputSJ.cpp:20-200) over all shards' junction records and write SJ.out.tab / Log.final.out.
+ * counters24 may be NULL (then the shard files are summed). */
+int star_host_merge_shards(int argc, char** argv, int nShards, const uint64_t* counters24);
+
 /* Engine indirection used by star_cli_main; tests drive the same host code with the CPU oracle. */
 typedef struct star_engine_vtbl {
     int (*init)(void** ctx, int device, const star_index_view_t*, const star_params_t*, uint32_t maxReads);

@@ -81,7 +81,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     std::ofstream samOut;
     if (samYes) {
         samOut.open(P.outFileNamePrefix + "Aligned.out.sam", std::ios::binary);
-        samOut << W.samHeader();
+        if (P.gpuShardIndex == 0) samOut << W.samHeader();   // shards > 0 write records only; the merge concatenates in shard order
     }
     std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
     time(&stats.timeStartMap);
@@ -143,17 +143,86 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
     logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
+    time(&stats.timeFinish);
+    if (P.gpuShardCount > 1) {
+        // one shard of a multi-GPU run: leave the counters and the (collapsed) junction records for the merge
+        // (the neighbour-distance filter of outputSJ needs the GLOBAL sorted junction list)
+        std::string e2;
+        OutputWriter::collapseSJ(allSJ, e2);
+        if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
+        std::ofstream sb(P.outFileNamePrefix + "shard.bin", std::ios::binary);
+        uint64_t cnt[Stats::N_COUNTERS];
+        stats.toArray(cnt);
+        int64_t tm[3] = {(int64_t)stats.timeStart, (int64_t)stats.timeStartMap, (int64_t)stats.timeFinish};
+        uint64_t nsj = allSJ.size();
+        sb.write((const char*)cnt, sizeof(cnt));
+        sb.write((const char*)tm, sizeof(tm));
+        sb.write((const char*)&nsj, 8);
+        if (nsj) sb.write((const char*)allSJ.data(), nsj * sizeof(Junction));
+        std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+        logMain << "ALL DONE!\n" << std::flush;
+        return 0;
+    }
     if (P.outSJyes) {
         std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab");
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
     }
-    time(&stats.timeFinish);
     W.writeLogFinal(stats, P.outFileNamePrefix + "Log.final.out");
     std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished successfully\n" << std::flush;
     logMain << "ALL DONE!\n" << std::flush;
     return 0;
 }
 
+// Merge of a sharded (multi-GPU) run: shard r wrote <prefix>shard<r>.{Aligned.out.sam,shard.bin}.  counters = the 24 Log.final.out
+// counters after the allreduce over ranks (NULL: sum the shard files).  Writes <prefix>Aligned.out.sam, SJ.out.tab, Log.final.out.
+static int mergeShards(int argc, char** argv, int nShards, const uint64_t* counters) {
+    HostParams P;
+    std::string err;
+    int rc = parseCommandLine(argc, argv, P, err);
+    if (rc) { std::cerr << err << std::endl; return rc; }
+    LoadedIndex idx;
+    rc = loadIndex(P.genomeDir, &P.hp, idx, err, nullptr, true);
+    if (rc) { std::cerr << err << std::endl; return rc; }
+    OutputWriter W(P, idx);
+    Stats total;
+    std::vector<Junction> allSJ;
+    int64_t tStart = 0, tStartMap = 0, tFinish = 0;
+    const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    std::ofstream samOut;
+    if (samYes) samOut.open(P.outFileNamePrefix + "Aligned.out.sam", std::ios::binary);
+    for (int r = 0; r < nShards; r++) {
+        std::string sp = P.outFileNamePrefix + "shard" + std::to_string(r) + ".";
+        std::ifstream sb(sp + "shard.bin", std::ios::binary);
+        if (!sb.good()) { std::cerr << "EXITING because of FATAL ERROR: missing shard output " << sp << "shard.bin\n"; return STAR_EXIT_RUNTIME; }
+        uint64_t cnt[Stats::N_COUNTERS]; int64_t tm[3]; uint64_t nsj = 0;
+        sb.read((char*)cnt, sizeof(cnt)); sb.read((char*)tm, sizeof(tm)); sb.read((char*)&nsj, 8);
+        Stats s1; s1.fromArray(cnt); total.add(s1);
+        if (r == 0 || tm[0] < tStart) tStart = tm[0];
+        if (r == 0 || tm[1] < tStartMap) tStartMap = tm[1];
+        if (tm[2] > tFinish) tFinish = tm[2];
+        size_t old = allSJ.size();
+        allSJ.resize(old + nsj);
+        if (nsj) sb.read((char*)(allSJ.data() + old), nsj * sizeof(Junction));
+        if (samYes) {
+            std::ifstream in(sp + "Aligned.out.sam", std::ios::binary);
+            samOut << in.rdbuf();
+            samOut.clear();   // an empty shard sets failbit on operator<<
+        }
+    }
+    if (counters) total.fromArray(counters);
+    total.timeStart = (time_t)tStart; total.timeStartMap = (time_t)tStartMap; total.timeFinish = (time_t)tFinish;
+    if (P.outSJyes) {
+        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab");
+        if (!e2.empty()) { std::cerr << e2 << std::endl; return STAR_EXIT_BUG; }
+    }
+    W.writeLogFinal(total, P.outFileNamePrefix + "Log.final.out");
+    return 0;
+}
+
 }  // namespace starhost
+
+extern "C" int star_host_merge_shards(int argc, char** argv, int nShards, const uint64_t* counters24) {
+    return starhost::mergeShards(argc, argv, nShards, counters24);
+}
 
 extern "C" int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine) { return starhost::runAlign(argc, argv, engine); }

@@ -31,7 +31,7 @@ static bool readWhole(const std::string& path, std::vector<uint8_t>& dst, size_t
     return got == nBytes;
 }
 
-int loadIndex(const std::string& gDirIn, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log) {
+int loadIndex(const std::string& gDirIn, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log, bool chrInfoOnly) {
     std::string gDir = gDirIn;
     std::ostringstream lg;
     auto fail = [&](int code, const std::string& m) { err = m; if (log) *log = lg.str(); return code; };
@@ -88,6 +88,21 @@ int loadIndex(const std::string& gDirIn, star_params_t* p, LoadedIndex& L, std::
         if (cs.fail()) return fail(STAR_EXIT_INPUT_FILES, "EXITING because of FATAL error, could not open file " + gDir + "/chrStart.txt\nSOLUTION: re-generate genome files with STAR --runMode genomeGenerate\n");
         for (uint32_t i = 0; i <= n; i++) cs >> L.chrStart[i];
         lg << "Number of real (reference) chromosomes= " << n << "\n";
+    }
+    if (chrInfoOnly) {   // enough for SAM headers / SJ.out.tab of a shard merge: names, starts, lengths, chrBin
+        star_index_view_t& v0 = L.view;
+        memset(&v0, 0, sizeof(v0));
+        uint32_t nChr = (uint32_t)L.chrName.size();
+        uint64_t nb = 1ULL << gChrBinNbits;
+        uint64_t chrBinN = L.chrStart[nChr] / nb + 1;
+        L.chrBin.resize(chrBinN);
+        for (uint64_t ii = 0, ichr = 1; ii < chrBinN; ++ii) {
+            if (ii * nb >= L.chrStart[ichr]) ichr++;
+            L.chrBin[ii] = ichr - 1;
+        }
+        v0.gChrBinNbits = gChrBinNbits; v0.nChrReal = nChr; v0.chrStart = L.chrStart.data(); v0.chrLength = L.chrLength.data();
+        if (log) *log = lg.str();
+        return 0;
     }
     // ---- Genome / SA / SAindex :303-345
     uint64_t nGenome = 0, nSAbyte = 0, nSAiFile = 0;

@@ -66,6 +66,7 @@ struct HostParams {
     // star-b200 extensions (not in the reference)
     int gpuDevice = 0;
     unsigned gpuChunkReads = 262144;        // reads (pairs) per engine call
+    unsigned gpuShardIndex = 0, gpuShardCount = 1;   // multi-GPU: this process maps reads [n*i/N, n*(i+1)/N) (contiguous slices keep input order)
     std::map<std::string, int> userSet;     // parameter name -> input level (for --sjdbOverhang style checks)
 };
 
@@ -85,7 +86,7 @@ struct LoadedIndex {
     star_index_view_t view;
     std::string versionGenome;
 };
-int loadIndex(const std::string& genomeDir, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log);
+int loadIndex(const std::string& genomeDir, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log, bool chrInfoOnly = false);
 
 // one chunk of reads in host memory
 struct ReadChunk {
@@ -109,6 +110,7 @@ class ReadsReader {
     // fills at most maxReads reads; returns number read (0 at EOF) or -STAR_EXIT_* on error
     long long next(ReadChunk& c, uint32_t maxReads, std::string& err);
     uint64_t iReadAll = 0;
+    uint64_t shardLo = 0, shardHi = ~0ULL;   // reads (0-based) this process maps
 
    private:
     FILE* f[2] = {nullptr, nullptr};

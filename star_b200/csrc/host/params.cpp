@@ -178,6 +178,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     tab["outSAMflagOR"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagOR); }};
     tab["outSAMflagAND"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagAND); }};
     tab["gpuDevice"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuDevice); }};
+    tab["gpuShardIndex"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardIndex); }};
+    tab["gpuShardCount"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardCount) && P.gpuShardCount > 0; }};
     tab["gpuChunkReads"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuChunkReads) && P.gpuChunkReads > 0; }};
 
     // Parameters.cpp:331-365: "--name v1 v2", "--name=value"
@@ -347,6 +349,7 @@ int finalizeParams(HostParams& P, std::string& err) {
         for (int c : P.outSAMattrOrder) if (c == 10) has = true;
         if (!has) P.outSAMattrOrder.push_back(10);
     }
+    if (P.gpuShardIndex >= P.gpuShardCount) return bad("EXITING because of fatal PARAMETERS error: --gpuShardIndex must be < --gpuShardCount\n");
     // geometry the sparse window map of the GPU engine relies on ("windows")
     if (2 * h.winFlankNbins > h.winAnchorDistNbins && P.userSet.count("winFlankNbins"))
         return bad("EXITING because of fatal PARAMETERS error: star-b200 requires 2*winFlankNbins <= winAnchorDistNbins (flanks of neighbouring windows must not overlap)\n");

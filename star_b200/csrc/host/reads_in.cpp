@@ -36,6 +36,39 @@ int ReadsReader::open(const HostParams& Pin, std::string& err) {
         buf[m].resize(1 << 22);
         bpos[m] = blen[m] = 0;
     }
+    if (Pin.gpuShardCount > 1) {
+        // contiguous slice of the input by read index: count the records of mate 1 first (one pass over the text), then reopen
+        uint64_t nRec = 0;
+        {
+            std::string line;
+            int ch = peekChar(0);
+            bool fq = ch == '@';
+            uint64_t lines = 0;
+            while (getLine(0, line)) { if (fq) lines++; else if (!line.empty() && line[0] == '>') nRec++; }
+            if (fq) nRec = lines / 4;
+        }
+        for (unsigned m = 0; m < nMates; m++) { if (piped[m]) pclose(f[m]); else fclose(f[m]); f[m] = nullptr; }
+        HostParams P1 = Pin;
+        P1.gpuShardCount = 1;
+        int rc = open(P1, err);
+        P = &Pin;
+        if (rc) return rc;
+        shardLo = nRec * Pin.gpuShardIndex / Pin.gpuShardCount;
+        shardHi = nRec * (Pin.gpuShardIndex + 1) / Pin.gpuShardCount;
+        // skip the records before the slice (both mates), keeping the global read numbering
+        std::string tmp;
+        while (iReadAll < shardLo) {
+            int ch = peekChar(0);
+            if (ch != '@' && ch != '>') break;
+            bool fq = ch == '@';
+            for (unsigned m = 0; m < nMates; m++) {
+                getLine(m, tmp);
+                if (fq) { getLine(m, tmp); getLine(m, tmp); getLine(m, tmp); }
+                else { for (;;) { int c2 = peekChar(m); if (c2 == '@' || c2 == '>' || c2 == ' ' || c2 == '\n' || c2 < 0) break; getLine(m, tmp); } }
+            }
+            iReadAll++;
+        }
+    }
     return 0;
 }
 
@@ -82,6 +115,7 @@ long long ReadsReader::next(ReadChunk& c, uint32_t maxReads, std::string& err) {
     std::string l1, seq[2], qual[2], tmp;
     while (c.nReads < maxReads) {
         if (P->readMapNumber >= 0 && (long long)iReadAll >= P->readMapNumber) break;  // processChunks.cpp:25
+        if (iReadAll >= shardHi) break;                                               // end of this process' slice (multi-GPU)
         int ch = peekChar(0);
         if (ch != '@' && ch != '>') break;  // end of stream (:198-200)
         bool fastq = ch == '@';

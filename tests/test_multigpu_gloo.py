@@ -1,0 +1,38 @@
+"""N>1 path on CPU: world_size 2 over gloo.  Each rank maps a contiguous slice of the reads (with the oracle-driven test CLI,
+there is no GPU here), the counters are allreduced, rank 0 merges; the merged outputs must equal the single-process reference
+goldens byte for byte (SAM order = input order, global junction collapse + filters, summed Log.final.out counters)."""
+import os
+import subprocess
+import sys
+
+import conftest as cf
+import oracle_capi as oc
+
+ROOT = cf.ROOT
+
+
+def test_two_rank_sharded_run_equals_reference(oracle, lib, golden, tmp_path):
+    out = str(tmp_path) + "/"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
+           "-m", "star_b200.dist", "--cli", oc.ORACLE_CLI, "--",
+           "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
+           "--outFileNamePrefix", out, "--runThreadN", "2"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = os.path.join(golden, "ref_std")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+    # both shards really mapped a slice
+    n0 = len(cf.sam_body(out + "shard0.Aligned.out.sam"))
+    n1 = len(cf.sam_body(out + "shard1.Aligned.out.sam"))
+    assert n0 > 0 and n1 > 0 and n0 + n1 == len(cf.sam_body(out + "Aligned.out.sam"))
+
+
+def test_shard_arguments():
+    from star_b200 import dist
+    a = dist.shard_args(["--genomeDir", "g", "--outFileNamePrefix", "o/x_"], 3, 8, device=3)
+    assert a[a.index("--outFileNamePrefix") + 1] == "o/x_shard3."
+    assert a[a.index("--gpuShardIndex") + 1] == "3" and a[a.index("--gpuShardCount") + 1] == "8" and a[a.index("--gpuDevice") + 1] == "3"
