@@ -38,6 +38,19 @@ __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*
                               star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
 __global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
                                     star_read_result_t*, star_align_t*, u32, u8*, HeavyScratch);
+struct FlatArgs {   // stitch_flat.cuh
+    void* recs;
+    u8* pool; u64 poolBytes;
+    unsigned long long* bumps;
+    void* tasks; void* outs; u64 maxTasks;
+    void* blocks; u32 maxBlocks;
+    u64* trStore; u64 trWords;
+    u32 maxTasksPerRead, splitMin;
+};
+__global__ void flat_setup_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
+                                  star_read_result_t*, star_align_t*, u32, FlatArgs, u32);
+void launch_flat_dfs(int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, const FlatArgs&, u32*, const Caps&, u8*, u32);
+__global__ void flat_record_kernel(DevIndex, star_params_t, ReadInfo*, u32, u32*, u8*, Caps, star_read_result_t*, star_align_t*, FlatArgs);
 __global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void prof_read_kernel(unsigned long long*, int);
@@ -102,6 +115,12 @@ struct star_ctx {
     u32 heavyEst = 1024; u32 heavyNA = 64; u32 heavyMaxTasks = 8192, heavyMaxBlocks = 4096;
     Caps heavyCaps; u8* d_arenaHeavy = nullptr;   // per-WARP arenas of the warp-per-read kernel (bigger caps than the per-lane fast arenas)
     u64 heavyScratchBytes = 0; u64 heavyScratchStride = 0; u64 lastHeavy = 0;
+    // flattened heavy path (stitch_flat.cuh): setup -> sub-tree tasks -> ordered recording, each over all heavy reads of the chunk
+    bool flat = false;
+    FlatArgs fa{};
+    Caps recCaps; u8* d_arenaRec = nullptr; int gridRec = 0;
+    int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
+    unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
     // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
@@ -351,6 +370,46 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         CK(cudaMalloc((void**)&c->d_arenaHeavy, bytes));
         c->owned.push_back(c->d_arenaHeavy);
     }
+    c->flat = c->heavyEst && envU32("STAR_B200_HEAVY_FLAT", 1) != 0;
+    if (c->flat) {
+        FlatArgs& fa = c->fa;
+        const u64 perRead = envU32("STAR_B200_FLAT_POOL_KB", 16) * 1024ULL;
+        fa.poolBytes = std::min<u64>(48ULL << 30, std::max<u64>(256ULL << 20, (u64)N * perRead));
+        fa.maxTasks = std::max<u64>(4ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TASKS_PER_READ", 192));
+        if (fa.maxTasks > 0xFFFF0000ULL) fa.maxTasks = 0xFFFF0000ULL;
+        fa.maxBlocks = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(1ULL << 20, (u64)N * envU32("STAR_B200_FLAT_BLOCKS_PER_READ", 8)));
+        fa.trWords = std::min<u64>(0xFFFF0000ULL, std::max<u64>(16ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TRWORDS_PER_READ", 2048)));
+        // absolute overrides (tests exercise the exhaustion paths with tiny pools)
+        if (getenv("STAR_B200_FLAT_POOL_BYTES")) fa.poolBytes = strtoull(getenv("STAR_B200_FLAT_POOL_BYTES"), nullptr, 10);
+        if (getenv("STAR_B200_FLAT_MAXTASKS")) fa.maxTasks = strtoull(getenv("STAR_B200_FLAT_MAXTASKS"), nullptr, 10);
+        if (getenv("STAR_B200_FLAT_MAXBLOCKS")) fa.maxBlocks = (u32)strtoull(getenv("STAR_B200_FLAT_MAXBLOCKS"), nullptr, 10);
+        if (getenv("STAR_B200_FLAT_TRWORDS")) fa.trWords = strtoull(getenv("STAR_B200_FLAT_TRWORDS"), nullptr, 10);
+        fa.maxTasksPerRead = c->heavyMaxTasks;
+        fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 6);
+        void* p = nullptr;
+        CK(cudaMalloc(&p, (size_t)N * 48)); fa.recs = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.poolBytes)); fa.pool = (u8*)p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, 64)); fa.bumps = (unsigned long long*)p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.maxTasks * 8)); fa.tasks = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.maxTasks * 32)); fa.outs = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, (size_t)fa.maxBlocks * 128)); fa.blocks = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.trWords * 8)); fa.trStore = (u64*)p; c->owned.push_back(p);
+        // recording kernel: one lane per read, each lane with its own transcript pool
+        c->recCaps = c->heavyCaps;
+        c->recCaps.arenaBytes = ((u64)c->recCaps.maxW * sizeof(Window) + (u64)c->recCaps.maxTr * sizeof(DevTr) + (u64)c->recCaps.maxTr * 2
+                                 + (u64)c->recCaps.maxW * 4 + 255) & ~255ULL;
+        int recGrid = c->nSM * (int)envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", 2);
+        const int needGrid = (int)std::max<u64>(1, ((u64)N + 127) / 128);
+        c->gridRec = std::min(recGrid, needGrid);
+        CK(cudaMalloc(&p, (size_t)c->gridRec * 128 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
+        CK(cudaFuncSetAttribute(flat_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->dfsMode = (int)envU32("STAR_B200_FLAT_DFS_MODE", 1);   // 1: one task per warp (uniform execution); 0: one task per lane
+        c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", c->dfsMode ? 4 : 4)));
+        c->fetchMin = envU32("STAR_B200_FLAT_FETCH_MIN", 1);
+        if (envU32("STAR_B200_FLAT_LANE_SCRATCH", 0)) {
+            CK(cudaMalloc(&p, (size_t)c->nSM * c->dfsCtas * 128 * 4096)); c->d_laneScratch = (u8*)p; c->owned.push_back(p);
+        }
+    }
     CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -457,6 +516,50 @@ static int runHeavy(star_ctx* c, const Caps& caps, u8* arenas, int gridBlocks, u
     CK(cudaMemcpy(c->d_heavyList, list.data(), (size_t)nHeavy * 4, cudaMemcpyHostToDevice));
     return launchHeavy(c, caps, arenas, gridBlocks, c->d_heavyList, nHeavy, true, nullptr);
 }
+// Flattened heavy path, first tier.  listB = reads routed here right after seeding (head of the nA-descending order), then the
+// reads stitch_kernel exported (known after a sync).  One setup launch per list, then ONE task kernel and ONE recording kernel.
+static int runFlat(star_ctx* c, u32 nHeavyB) {
+    const Caps& caps = c->heavyCaps;
+    const u32 perWarp = (2 * c->smemStride + 32 + caps.maxW * (u32)sizeof(Window) + (caps.maxW + 4) * 4 + ((caps.maxW + 3) & ~3u) + 15) & ~15u;
+    const u32 smem = 4 * perWarp;
+    if (smem > 200 * 1024) { g_err = "star_b200: flat setup kernel shared memory exceeds the limit"; return STAR_EXIT_RUNTIME; }
+    CK(cudaMemsetAsync(c->fa.bumps, 0, 64, c->stream));
+    if (nHeavyB) {
+        CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+        flat_setup_kernel<<<c->gridStitch, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, nHeavyB, c->d_order, c->d_heavyOff,
+                                                                  nullptr, c->d_counter, c->d_arenaHeavy, caps, c->d_results, c->d_staged, c->smemStride, c->fa, 0);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    u32 nHeavyX = 0;   // exported by stitch_kernel
+    CK(cudaMemcpyAsync(&nHeavyX, (u32*)(c->d_heavyBump + 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->lastHeavy += nHeavyX;
+    if (nHeavyX) {
+        std::vector<u32> list(nHeavyX);   // deterministic order (the export order came from atomics)
+        CK(cudaMemcpy(list.data(), c->d_heavyList, (size_t)nHeavyX * 4, cudaMemcpyDeviceToHost));
+        std::sort(list.begin(), list.end());
+        CK(cudaMemcpy(c->d_heavyList, list.data(), (size_t)nHeavyX * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+        flat_setup_kernel<<<c->gridStitch, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, nullptr, nHeavyX, c->d_heavyList, c->d_heavyOff,
+                                                                  c->d_heavyPool, c->d_counter, c->d_arenaHeavy, caps, c->d_results, c->d_staged, c->smemStride, c->fa, nHeavyB);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    const u32 nRecs = nHeavyB + nHeavyX;
+    if (nRecs == 0) return 0;
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    launch_flat_dfs(c->dfsMode, c->dfsCtas, c->nSM, c->stream, c->ix, c->P, c->fa, c->d_counter, caps, c->d_laneScratch, c->fetchMin);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    flat_record_kernel<<<c->gridRec, 128, 0, c->stream>>>(c->ix, c->P, c->d_info, nRecs, c->d_counter, c->d_arenaRec, c->recCaps, c->d_results, c->d_staged, c->fa);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->flatUse, c->fa.bumps, 32, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
 static HeavyArgs heavyArgs(star_ctx* c) {
     HeavyArgs hv;
     hv.pool = c->d_heavyPool; hv.poolBytes = c->heavyPoolBytes; hv.bump = c->d_heavyBump; hv.readOff = c->d_heavyOff;
@@ -514,8 +617,12 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev[9], c->stream));
-    if (launchHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->d_order, nHeavyA, false, c->d_pieces)) return STAR_EXIT_RUNTIME;
-    if (runHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->smemStride)) return STAR_EXIT_RUNTIME;
+    if (c->flat) {
+        if (runFlat(c, nHeavyA)) return STAR_EXIT_RUNTIME;
+    } else {
+        if (launchHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->d_order, nHeavyA, false, c->d_pieces)) return STAR_EXIT_RUNTIME;
+        if (runHeavy(c, c->heavyCaps, c->d_arenaHeavy, c->gridStitch, c->smemStride)) return STAR_EXIT_RUNTIME;
+    }
     CK(cudaEventRecord(c->ev[8], c->stream));
     // ---- overflow tiers: reads that exceeded the caps of a tier are redone in the next one; the last tier has the reference's own limits ----
     for (int tier = 0; tier < 2; tier++) {
@@ -578,6 +685,9 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     CK(cudaMemcpyAsync(&wc, c->d_wc, sizeof(wc), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->nAligns, c->d_total, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->flat && getenv("STAR_B200_FLAT_DEBUG"))
+        fprintf(stderr, "star_b200 flat path: pool %.1f/%.1f MB, tasks %llu/%llu, blocks %llu/%u, stored words %llu/%llu\n", c->flatUse[0] / 1048576.0,
+                c->fa.poolBytes / 1048576.0, c->flatUse[1], (unsigned long long)c->fa.maxTasks, c->flatUse[2], c->fa.maxBlocks, c->flatUse[3], (unsigned long long)c->fa.trWords);
     if (nBad > 0) {
         std::vector<ReadInfo> inf(1);
         u32 first = 0;

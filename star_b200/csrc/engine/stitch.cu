@@ -90,6 +90,7 @@ struct Lane {
     u64 memoBase;                    // (epoch, window) part of the key
     int lastSeed;                    // index of the last included seed on the current path (-1 = none)
     u64 memoHit, memoMiss;
+    u32 coop;            // 1: all 32 lanes of the warp run this Lane with identical state (flat_dfs_warp_kernel): byte loops are cooperative
     u32 forceDepth;      // heavy path: the first forceDepth include/exclude decisions are fixed (prefix sub-tree task)
     u32 forceBits;       // bit (forceDepth-1-k) set <=> seed k is EXCLUDED (so that ascending task id = DFS order, include first)
     // per-read stitching state (ReadAlign_stitchPieces.cpp:262-350)
@@ -124,9 +125,89 @@ __device__ int binarySearch2(u64 x, u64 y, const u64* __restrict__ X, const u64*
 
 struct ExtRes { u32 extendL; int maxScore; u32 nMatch, nMM; };
 
+// extendAlign.cpp:6-92 (local extension, extendToEnd==false) executed by a whole warp: all 32 lanes call with IDENTICAL arguments and
+// get identical results; lane j examines base 32*c+j of chunk c.  Equivalence with the sequential loop:
+//  * the loop ends at the first base that is a stop (genome edge / padding, mate spacer, i==L) or at the first mismatch whose
+//    running mismatch count already reaches capEnd — both are "first lane with the property" (ballot + ffs);
+//  * Score/nMatch/nMM at a base are prefix counts of matches / mismatches (popc of ballot masks below the lane);
+//  * a base is recorded when it is a match, its cap test holds and its Score exceeds every previously recorded Score, so the final
+//    record is the FIRST base that attains the maximum Score among the matches passing the cap test (if that maximum is > 0).
+__device__ __noinline__ bool coopExtendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax, ExtRes& res) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 below = (1u << lane) - 1;
+    const u8* R = ln.R;
+    const u8* G = ln.ix->G;
+    const u64 nG = ln.ix->nGenome;
+    const u64 Lread = ln.Lread;
+    res.maxScore = 0;
+    double capEnd = pMMmax * double(Lprev + L);
+    const double nMMmaxD = double(nMMmax);
+    if (nMMmaxD < capEnd) capEnd = nMMmaxD;
+    int Score = 0, nMatch = 0, nMM = 0;   // state after the bases of the previous chunks
+    for (u64 base = 0; base < L; base += 32) {
+        const u64 i = base + lane;
+        bool stop = i >= L;
+        u8 g = 0, r = 0;
+        if (!stop) {
+            const u64 gpos = gStart + (u64)((i64)dG * (i64)i);
+            const u64 rpos = rStart + (u64)((i64)dR * (i64)i);
+            if (gpos >= nG || rpos >= Lread) stop = true;   // (u64)-1 = before the genome start; beyond the end the padding (5) stops the loop
+            else {
+                g = __ldg(G + gpos); r = R[rpos];
+                if (g == 5 || r == STAR_MARK_FRAG_SPACER_BASE) stop = true;
+            }
+        }
+        const u32 stopMask = __ballot_sync(0xffffffffu, stop);
+        u32 nValid = stopMask ? (u32)__ffs(stopMask) - 1 : 32;
+        bool ended = stopMask != 0;
+        const bool notN = !(r > 3 || g > 3);
+        const bool isX = lane < nValid && notN && g != r;
+        u32 xMask = __ballot_sync(0xffffffffu, isX);
+        const bool brk = isX && double((u64)(nMM + __popc(xMask & below)) + nMMprev) >= capEnd;
+        const u32 brkMask = __ballot_sync(0xffffffffu, brk);
+        if (brkMask) { nValid = (u32)__ffs(brkMask) - 1; ended = true; }
+        const u32 vm = nValid >= 32 ? 0xffffffffu : ((1u << nValid) - 1);
+        const u32 mMask = __ballot_sync(0xffffffffu, notN && g == r) & vm;
+        xMask &= vm;
+        const int mIncl = __popc(mMask & (below | (1u << lane)));
+        const int xB = __popc(xMask & below);
+        const int Score_i = Score + mIncl - xB, nMM_i = nMM + xB, nMatch_i = nMatch + mIncl;
+        bool cand = (mMask >> lane) & 1u;
+        if (cand) {
+            double cap = pMMmax * double(Lprev + i + 1);
+            if (nMMmaxD < cap) cap = nMMmaxD;
+            cand = double((u64)nMM_i + nMMprev) <= cap;
+        }
+        const int best = __reduce_max_sync(0xffffffffu, cand ? Score_i : (int)0x80000000);
+        if (best > res.maxScore) {
+            const u32 src = (u32)__ffs(__ballot_sync(0xffffffffu, cand && Score_i == best)) - 1;
+            res.maxScore = best;
+            res.extendL = (u32)base + src + 1;
+            res.nMatch = (u32)__shfl_sync(0xffffffffu, nMatch_i, src);
+            res.nMM = (u32)__shfl_sync(0xffffffffu, nMM_i, src);
+        }
+        Score += __popc(mMask) - __popc(xMask); nMatch += __popc(mMask); nMM += __popc(xMask);
+        if (ended) break;
+    }
+    return res.extendL > 0;
+}
+
 // extendAlign.cpp:6-92.  R/G are addressed through the lane (R orientation already selected).
-__device__ bool extendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+// COOP: the caller is a warp executing one Lane uniformly (flat_dfs_warp_kernel).
+template <bool COOP>
+__device__ __noinline__ bool extendAlignShared(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                               bool extendToEnd, ExtRes& res);
+template <bool COOP = false>
+__device__ __forceinline__ bool extendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                            bool extendToEnd, ExtRes& res) {
+    return extendAlignShared<COOP>(ln, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd, res);   // one copy per kernel
+}
+template <bool COOP>
+__device__ __noinline__ bool extendAlignShared(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
                             bool extendToEnd, ExtRes& res) {
+    if constexpr (COOP) {
+        if (!extendToEnd) return coopExtendAlign(ln, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, res);
+    }
     int Score = 0, nMatch = 0, nMM = 0;
     res.maxScore = 0;
     const u8* R = ln.R + rStart;
@@ -179,6 +260,9 @@ __device__ bool extendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int 
 }
 
 // stitchAlignToTranscript.cpp:9-415 operating on the shared DFS transcript `t`
+// COOP: executed by a whole warp with identical arguments; the byte loops run 32 positions per step (same results, see the
+// comments at each loop).
+template <bool COOP = false>
 __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBstart, u64 gBstart, u64 L, u32 iFragB, u32 sjAB, DevTr* t) {
     const star_params_t& P = *ln.P;
     const DevIndex& g = *ln.ix;
@@ -224,16 +308,123 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
 
             if (gGap == 0 && rGap == 0) {
             } else if (gGap > 0 && rGap > 0 && rGap == gGap) {
+                if constexpr (COOP) {   // matches / mismatches of the gap: two popcounts per 32 bases
+                    const u32 lane = threadIdx.x & 31;
+                    for (int base = 1; base <= rGap; base += 32) {
+                        const int ii = base + (int)lane;
+                        bool m = false, x = false;
+                        if (ii <= rGap) {
+                            u8 gv = Gat(ln, gAend + ii), rv = R[rAend + ii];
+                            if (gv < 4 && rv < 4) { m = rv == gv; x = !m; }
+                        }
+                        const int nm = __popc(__ballot_sync(0xffffffffu, m)), nx = __popc(__ballot_sync(0xffffffffu, x));
+                        Score += nm - nx; nMatch += (u64)nm; nMM += (u64)nx;
+                    }
+                } else {
                 for (int ii = 1; ii <= rGap; ii++) {
                     u8 gv = Gat(ln, gAend + ii), rv = R[rAend + ii];
                     if (gv < 4 && rv < 4) {
                         if (rv == gv) { Score += 1; nMatch++; } else { Score -= 1; nMM++; }
                     }
                 }
+                }
             } else if (gGap > rGap) {
                 nDel = 1;
                 Del = (u64)(gGap - rGap);
                 if (Del > P.alignIntronMax && P.alignIntronMax > 0) return -1000003;
+                int jPen = 0;
+                u64 jjL = 0, jjR = 0;
+                if constexpr (COOP) {
+                    const u32 lane = threadIdx.x & 31;
+                    const u32 below = (1u << lane) - 1;
+                    // (1) backward scan for the start of the junction search: the sequential loop visits jR1 = 0,-1,.. and ends at the
+                    // (scoreStitchSJshift+1)-th position where the read matches the donor side but not the acceptor side, or at 1-eA.L.
+                    int jR1 = 0;
+                    {
+                        const int jMin = 1 - (int)eA.L;
+                        const int need = P.scoreStitchSJshift + 1;
+                        int cnt = 0;
+                        for (int base = 0;; base -= 32) {
+                            const int pz = base - (int)lane;
+                            bool pen = false;
+                            if (pz >= jMin) {
+                                u8 rv = R[(i64)rAend + pz], gb = Gat(ln, gBstart1 + (u64)(i64)pz), ga = Gat(ln, gAend + (u64)(i64)pz);
+                                pen = rv != gb && gb < 4 && rv == ga;
+                            }
+                            u32 pm = __ballot_sync(0xffffffffu, pen);
+                            const int lastLane = base - jMin;          // lane holding position jMin (may be > 31)
+                            int hit = -1;
+                            if (need <= 0) hit = 0;
+                            else if (cnt + __popc(pm) >= need) {
+                                for (int q = 1; q < need - cnt; q++) pm &= pm - 1;
+                                hit = __ffs(pm) - 1;
+                            }
+                            if (hit >= 0 && hit <= lastLane) { jR1 = base - hit; break; }
+                            if (lastLane <= 31) { jR1 = jMin; break; }
+                            cnt += __popc(pm);
+                        }
+                    }
+                    // (2) forward scan: Score1 is a prefix sum of {+1,-1,0}; the junction is the FIRST position with the maximum of
+                    // Score1 + motif penalty (the sequential loop updates on strict improvement only).
+                    {
+                        const int jEnd = int(rBend) - int(rAend);
+                        const bool withMotif = Del >= P.alignIntronMin;
+                        int maxScore2 = -999999;
+                        int Score1 = 0;
+                        for (int base = jR1; base < jEnd; base += 32) {
+                            const int pz = base + (int)lane;
+                            const bool v = pz < jEnd;
+                            bool up = false, dn = false;
+                            int jCan1 = -1, jPen1 = 0;
+                            if (v) {
+                                u8 rv = R[(i64)rAend + pz], ga = Gat(ln, gAend + (u64)(i64)pz), gb = Gat(ln, gBstart1 + (u64)(i64)pz);
+                                up = rv == ga && rv != gb;
+                                dn = rv != ga && rv == gb;
+                                if (withMotif) {
+                                    u8 d1 = Gat(ln, gAend + (u64)(i64)(pz + 1)), d2 = Gat(ln, gAend + (u64)(i64)(pz + 2));
+                                    u8 a1 = Gat(ln, gBstart1 + (u64)(i64)(pz - 1)), a2 = gb;
+                                    if (d1 == 2 && d2 == 3 && a1 == 0 && a2 == 2) { jCan1 = 1; }
+                                    else if (d1 == 1 && d2 == 3 && a1 == 0 && a2 == 1) { jCan1 = 2; }
+                                    else if (d1 == 2 && d2 == 1 && a1 == 0 && a2 == 2) { jCan1 = 3; jPen1 = P.scoreGapGCAG; }
+                                    else if (d1 == 1 && d2 == 3 && a1 == 2 && a2 == 1) { jCan1 = 4; jPen1 = P.scoreGapGCAG; }
+                                    else if (d1 == 0 && d2 == 3 && a1 == 0 && a2 == 1) { jCan1 = 5; jPen1 = P.scoreGapATAC; }
+                                    else if (d1 == 2 && d2 == 3 && a1 == 0 && a2 == 3) { jCan1 = 6; jPen1 = P.scoreGapATAC; }
+                                    else { jCan1 = 0; jPen1 = P.scoreGapNoncan; }
+                                }
+                            }
+                            const u32 upM = __ballot_sync(0xffffffffu, up), dnM = __ballot_sync(0xffffffffu, dn);
+                            const u32 incl = below | (1u << lane);
+                            const int S2 = Score1 + __popc(upM & incl) - __popc(dnM & incl) + jPen1;
+                            const int best = __reduce_max_sync(0xffffffffu, v ? S2 : (int)0x80000000);
+                            if (best > maxScore2) {
+                                const u32 src = (u32)__ffs(__ballot_sync(0xffffffffu, v && S2 == best)) - 1;
+                                maxScore2 = best;
+                                jR = base + (int)src;
+                                jCan = __shfl_sync(0xffffffffu, jCan1, src);
+                                jPen = __shfl_sync(0xffffffffu, jPen1, src);
+                            }
+                            Score1 += __popc(upM) - __popc(dnM);
+                        }
+                    }
+                    // (3) repeat lengths around the junction: first position where the flanks differ (or an N, or 256)
+                    const u64 jRu = (u64)(i64)jR;
+                    for (;;) {
+                        const u64 q = jjL + lane;
+                        bool ok = gAend + jRu >= q && q <= 255;
+                        if (ok) { u8 x = Gat(ln, gAend - q + jRu), y = Gat(ln, gBstart1 - q + jRu); ok = x == y && x < 4; }
+                        const u32 fail = __ballot_sync(0xffffffffu, !ok);
+                        if (fail) { jjL += (u32)__ffs(fail) - 1; break; }
+                        jjL += 32;
+                    }
+                    for (;;) {
+                        const u64 q = jjR + lane;
+                        bool ok = gAend + q + jRu + 1 < g.nGenome && gBstart1 + q + jRu + 1 < g.nGenome && q <= 255;   // (beyond the genome the padding (5) ends the loop)
+                        if (ok) { u8 x = Gat(ln, gAend + q + jRu + 1), y = Gat(ln, gBstart1 + q + jRu + 1); ok = x == y && x < 4; }
+                        const u32 fail = __ballot_sync(0xffffffffu, !ok);
+                        if (fail) { jjR += (u32)__ffs(fail) - 1; break; }
+                        jjR += 32;
+                    }
+                } else {
                 int Score1 = 0;
                 int jR1 = 1;
                 do {
@@ -244,7 +435,6 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
 
                 int maxScore2 = -999999;
                 Score1 = 0;
-                int jPen = 0;
                 do {
                     u8 rv = R[(i64)rAend + jR1], ga = Gat(ln, gAend + (u64)(i64)jR1), gb = Gat(ln, gBstart1 + (u64)(i64)jR1);
                     if (rv == ga && rv != gb) Score1 += 1;
@@ -266,11 +456,11 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                     jR1++;
                 } while (jR1 < int(rBend) - int(rAend));
 
-                u64 jjL = 0, jjR = 0;
                 u64 jRu = (u64)(i64)jR;
                 while (gAend + jRu >= jjL && Gat(ln, gAend - jjL + jRu) == Gat(ln, gBstart1 - jjL + jRu) && Gat(ln, gAend - jjL + jRu) < 4 && jjL <= 255) jjL++;
                 while (gAend + jjR + jRu + 1 < g.nGenome && Gat(ln, gAend + jjR + jRu + 1) == Gat(ln, gBstart1 + jjR + jRu + 1) && Gat(ln, gAend + jjR + jRu + 1) < 4 && jjR <= 255) jjR++;
 
+                }
                 if (jCan <= 0) {
                     jR -= (int)jjL;
                     if (int(eA.L) + jR < 1) return -1000005;
@@ -280,6 +470,23 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                 {
                     int i0 = 1 < jR + 1 ? 1 : jR + 1;
                     int i1 = rGap > jR ? rGap : jR;
+                    if constexpr (COOP) {
+                        const u32 lane = threadIdx.x & 31;
+                        for (int base = i0; base <= i1; base += 32) {
+                            const int ii = base + (int)lane;
+                            bool a = false, b = false, c = false;
+                            if (ii <= i1) {
+                                u64 g1 = (ii <= jR) ? (gAend + (u64)(i64)ii) : (gBstart1 + (u64)(i64)ii);
+                                u8 gv = Gat(ln, g1), rv = R[(i64)rAend + ii];
+                                if (gv < 4 && rv < 4) {
+                                    const bool inGap = ii >= 1 && ii <= rGap;
+                                    if (rv == gv) a = inGap; else { b = true; c = !inGap; }
+                                }
+                            }
+                            const int na = __popc(__ballot_sync(0xffffffffu, a)), nb = __popc(__ballot_sync(0xffffffffu, b)), nc = __popc(__ballot_sync(0xffffffffu, c));
+                            Score += na - nb - nc; nMatch += (u64)(i64)(na - nc); nMM += (u64)nb;
+                        }
+                    } else {
                     for (int ii = i0; ii <= i1; ii++) {
                         u64 g1 = (ii <= jR) ? (gAend + (u64)(i64)ii) : (gBstart1 + (u64)(i64)ii);
                         u8 gv = Gat(ln, g1), rv = R[(i64)rAend + ii];
@@ -291,6 +498,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                                 if (ii < 1 || ii > rGap) { Score -= 1; nMatch--; }
                             }
                         }
+                    }
                     }
                 }
                 bool annotated = false;
@@ -397,7 +605,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
             Score += (int)L;
             ExtRes er;
             er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
-            if (extendAlign(ln, rAend + 1, gAend + 1, 1, 1, STAR_READ_SEQ_LENGTH_MAX, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
+            if (extendAlign<COOP>(ln, rAend + 1, gAend + 1, 1, 1, STAR_READ_SEQ_LENGTH_MAX, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
                             P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[eA.iFrag][1], er)) {
                 h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                 Score += er.maxScore;
@@ -407,7 +615,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
             h.nMatch += (u32)L;
             er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
             u64 extlen = P.alignEndsTypeExt[iFragB][1] ? (u64)STAR_READ_SEQ_LENGTH_MAX : gBstart - t->ex[0].G + t->ex[0].R;
-            if (extendAlign(ln, rBstart - 1, gBstart - 1, -1, -1, extlen, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
+            if (extendAlign<COOP>(ln, rBstart - 1, gBstart - 1, -1, -1, extlen, h.nMatch, h.nMM, outFilterMismatchNmaxTotal,
                             P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[iFragB][1], er)) {
                 h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                 Score += er.maxScore;
@@ -451,6 +659,15 @@ __device__ u64 blocksOverlap(const DevTr& t1, const DevTr& t2) {
     return nOverlap;
 }
 
+// warp-uniform mode (flat_dfs_warp_kernel): 32-bit words [0,nWords) copied one per lane instead of 32 times by every lane
+__device__ __forceinline__ void warpCopyWords(void* dst, const void* src, u32 nWords) {
+    const u32 lane = threadIdx.x & 31;
+    __syncwarp();
+    for (u32 q = lane; q < nWords; q += 32) ((u32*)dst)[q] = ((const u32*)src)[q];
+    __syncwarp();
+}
+static_assert(sizeof(TrHead) == 80 && sizeof(Exon) == 24, "warpCopyWords call sites assume 20-word heads and 6-word exons");
+
 __device__ __forceinline__ void copyTr(DevTr* dst, const DevTr* src) {
     dst->h = src->h;
     for (u32 i = 0; i < src->h.nExons; i++) dst->ex[i] = src->ex[i];
@@ -468,11 +685,13 @@ __device__ int log2Score(const DevIndex& ix, u64 gLen) {
 // Leaf of stitchWindowAligns, part 1 (stitchWindowAligns.cpp:19-243): extend both ends, apply the filters, compute the final score.
 // Pure function of the DFS path (reads no per-read mutable state), so the heavy path can evaluate leaves of different sub-trees
 // in parallel.  Result in ln.leaf (h.maxScore, h.iFrag set).  Returns false when a filter drops the transcript.
+template <bool COOP = false>
 __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str, u32 roStr) {
     const star_params_t& P = *ln.P;
     const DevIndex& g = *ln.ix;
     DevTr& t = *ln.leaf;
-    copyTr(&t, ln.cur);
+    if constexpr (COOP) warpCopyWords(&t, ln.cur, 20 + 6 * (u32)ln.cur->h.nExons);   // head and exons are contiguous
+    else copyTr(&t, ln.cur);
     TrHead& h = t.h;
     const u64 Lread = ln.Lread;
     int vOrder[2];
@@ -483,7 +702,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
         if (vOrder[iOrd] == 0) {
             if (h.rStart > 0) {
                 u32 imate = t.ex[0].iFrag;
-                if (extendAlign(ln, (u64)h.rStart - 1, h.gStart - 1, -1, -1, h.rStart, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
+                if (extendAlign<COOP>(ln, (u64)h.rStart - 1, h.gStart - 1, -1, -1, h.rStart, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
                                 P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[imate][(int)(Str != imate)], er)) {
                     h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                     Score += er.maxScore;
@@ -495,7 +714,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
         } else {
             if (tR2 < Lread) {
                 u32 imate = t.ex[h.nExons - 1].iFrag;
-                if (extendAlign(ln, tR2 + 1, tG2 + 1, +1, +1, Lread - tR2 - 1, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
+                if (extendAlign<COOP>(ln, tR2 + 1, tG2 + 1, +1, +1, Lread - tR2 - 1, tR2 - h.rStart + 1, h.nMM, ln.outFilterMismatchNmaxTotal,
                                 P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[imate][(int)(imate == Str)], er)) {
                     h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                     Score += er.maxScore;
@@ -645,11 +864,12 @@ struct StitchMemo {
 
 static_assert(sizeof(StitchMemo) == 72, "engine_api.cu sizes the memo table with 72-byte entries");
 
+template <bool COOP = false>
 __device__ int stitchMemoized(Lane& ln, u64 rAend, u64 gAend, const Seed& s, u32 bIdx, DevTr* t, bool& wasHit) {
     wasHit = false;
     TrHead& h = t->h;
     if (!ln.memo || ln.lastSeed < 0 || h.nExons >= STAR_MAX_N_EXONS || t->ex[h.nExons - 1].iFrag != s.iFrag)
-        return stitchAlignToTranscript(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+        return stitchAlignToTranscript<COOP>(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
     Exon& eA = t->ex[h.nExons - 1];
     {   // the two cheapest outcomes are not worth a table access: B ends inside A in read or genome space (:53-54).  The sjdb shortcut
         // (:18) is tested first by the reference, so it must not apply here.
@@ -685,7 +905,7 @@ __device__ int stitchMemoized(Lane& ln, u64 rAend, u64 gAend, const Seed& s, u32
     ln.memoMiss++;
     const TrHead h0 = h;
     ln.memoMotifOk = true; ln.memoNMM = 0;
-    const int dScore = stitchAlignToTranscript(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
+    const int dScore = stitchAlignToTranscript<COOP>(ln, rAend, gAend, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);
     bool cache = true;
     if (dScore == -1000007 && ln.memoMotifOk) cache = false;   // failed only because of the total mismatch count of THIS path
     if (cache && atomicExch((unsigned long long*)&m->key, 1ULL) != 1ULL) {   // 1 = slot locked by another lane: skip publishing
@@ -710,8 +930,19 @@ __device__ int stitchMemoized(Lane& ln, u64 rAend, u64 gAend, const Seed& s, u32
 // dfsInit starts a window; dfsStep runs the cheap bookkeeping transitions (undo, pop) until it has executed ONE seed-include
 // attempt (one stitchAlignToTranscript call), reached a leaf, or emptied the stack.  One call = one unit of work of the
 // warp-lockstep state machine in stitch_kernel: all lanes of a warp that are inside a window execute their stitch call together.
+template <bool COOP = false>
 __device__ __forceinline__ void dfsInit(Lane& ln) {
     // trA = *trInit with Chr/Str set (ReadAlign_stitchPieces.cpp:282-286)
+    if constexpr (COOP) {
+        __syncwarp();
+        if ((threadIdx.x & 31) < 20) ((u32*)&ln.cur->h)[threadIdx.x & 31] = 0;   // every field of the initial head is zero
+        __syncwarp();
+        ln.inclMask = 0;
+        ln.level = 0; ln.nInc = 0; ln.Score = 0; ln.tR2 = 0; ln.tG2 = 0;
+        ln.lastSeed = -1;
+        ln.ph[0] = 0;
+        return;
+    }
     TrHead z;
     z.gStart = 0; z.gLength = 0; z.rStart = 0; z.rLength = 0; z.maxScore = 0; z.nMatch = 0; z.nMM = 0; z.mappedLength = 0;
     z.nGap = 0; z.lGap = 0; z.nDel = 0; z.lDel = 0; z.nIns = 0; z.lIns = 0; z.nUnique = 0; z.nAnchor = 0; z.nExons = 0; z.iFrag = 0;
@@ -724,6 +955,7 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
 }
 
 // after a sub-tree is exhausted: unwind to the deepest level whose exclude branch is still unexplored (undoing its include)
+template <bool COOP = false>
 __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
     DevTr* t = ln.cur;
     int L = ln.level - 1;
@@ -733,8 +965,13 @@ __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
             // undo the include of seed L, then explore the branch without it (WA_Anchor==2 never occurs: WlastAnchor is initialised
             // to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
             const Frame& u = ln.stack[--ln.nInc];
-            if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
-            t->h = u.h;
+            if constexpr (COOP) {
+                if (u.h.nExons > 0) warpCopyWords(&t->ex[u.h.nExons - 1], &u.last, 6);
+                warpCopyWords(&t->h, &u.h, 20);
+            } else {
+                if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
+                t->h = u.h;
+            }
             ln.Score = u.Score; ln.tR2 = u.tR2; ln.tG2 = u.tG2;
             ln.lastSeed = (int)u.pad[0] - 1;
             ln.inclMask &= ~(1ULL << L);
@@ -751,6 +988,7 @@ __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
 #define DFS_CONTINUE 0
 #define DFS_LEAF 1
 #define DFS_DONE 2
+template <bool COOP = false>
 __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
     DevTr* t = ln.cur;
     int runAhead = 0;
@@ -760,7 +998,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
         ln.nodes++;
         if (L >= nA) {
             if (ln.ph[L] == 9) {               // the leaf at this position was already handed out: now unwind
-                dfsBacktrack(ln);
+                dfsBacktrack<COOP>(ln);
                 continue;
             }
             const bool isLeaf = ln.tR2 != 0;   // "iA>=nA && tR2==0: no aligns in the transcript" (:14)
@@ -771,7 +1009,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
                 ln.nodes--;                    // (this level is visited twice)
                 return DFS_LEAF;
             }
-            dfsBacktrack(ln);
+            dfsBacktrack<COOP>(ln);
             continue;
         }
         const bool forced = L < ln.forceDepth;
@@ -801,14 +1039,20 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             }
         }
         Frame& u = ln.stack[ln.nInc];
-        u.h = t->h;
-        if (t->h.nExons > 0) u.last = t->ex[t->h.nExons - 1];
+        if constexpr (COOP) {
+            warpCopyWords(&u.h, &t->h, 20);
+            if (t->h.nExons > 0) warpCopyWords(&u.last, &t->ex[t->h.nExons - 1], 6);
+        } else {
+            u.h = t->h;
+            if (t->h.nExons > 0) u.last = t->ex[t->h.nExons - 1];
+        }
         u.Score = ln.Score; u.tR2 = ln.tR2; u.tG2 = ln.tG2;
         u.pad[0] = (u32)(ln.lastSeed + 1);
         int dScore = 0;
         bool cheap = false;
         if (t->h.nExons > 0) {
-            dScore = stitchMemoized(ln, ln.tR2, ln.tG2, s, L, t, cheap);
+            if constexpr (COOP) dScore = stitchAlignToTranscript<true>(ln, ln.tR2, ln.tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, t);   // (no stitch memo on this path)
+            else dScore = stitchMemoized<COOP>(ln, ln.tR2, ln.tG2, s, L, t, cheap);
         } else {
             t->ex[0].R = s.rStart; t->h.rStart = s.rStart;
             t->ex[0].G = s.gStart; t->h.gStart = s.gStart;
@@ -829,8 +1073,13 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             ln.Score += dScore; ln.tR2 = (u32)s.rStart + s.Length - 1; ln.tG2 = s.gStart + s.Length - 1;
         } else {
             if (forced) { ln.level = -1; return DFS_DONE; }   // the fixed prefix is not a valid path: this sub-tree is empty
+            if constexpr (COOP) {
+                if (u.h.nExons > 0) warpCopyWords(&t->ex[u.h.nExons - 1], &u.last, 6);
+                warpCopyWords(&t->h, &u.h, 20);
+            } else {
             if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;   // the failed attempt may have touched the last exon / head
             t->h = u.h;
+            }
             ln.ph[L] = 2;
         }
         ln.level = (int)L + 1;
@@ -1181,7 +1430,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex
     u8 phL[STAR_DFS_MAX_DEPTH + 4];
     ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
     ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
-    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1;
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
     {
         u8* a = arenas + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * caps.arenaBytes;
         ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
@@ -1650,6 +1899,148 @@ __device__ bool coopAssign(const Lane& ln, WarpWin& ww, int iW, u64 a1, u64 aLen
     return true;
 }
 
+// Window phases of a heavy read, executed by the whole warp (all lanes call with identical arguments): mode A imports the windows +
+// seeds a lane of stitch_kernel exported, mode B builds them cooperatively from the stored pieces.  Result: window table in shared
+// memory (swin[0..nWin)), seeds of window w at ln.wa[w*caps.spw ..].
+__device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const DevIndex& ix, const star_params_t& P, const ReadInfo& ri, u32 i,
+                                                 const Piece* __restrict__ pieces, const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool,
+                                                 const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason) {
+    const u32 Lread = ri.Lread;
+    bool tooManyAnchors = false;
+    u64 saEnum = 0;
+    if (heavyPool) {
+        // ---- mode A: import the exported windows + seeds
+        const u8* rec = heavyPool + heavyOff[i];
+        nWin = ((const u32*)rec)[0];
+        const HeavyWin* hw = (const HeavyWin*)(rec + 8);
+        const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
+        if (nWin > caps.maxW) { overReason = 5; nWin = 0; }
+        u32 sd = 0;
+        for (u32 w = 0; w < nWin; w++) {   // uniform loop; lanes copy the seeds of window w
+            const HeavyWin h = hw[w];
+            if (lane == 0) {
+                Window nw; nw.gStart = 0; nw.gEnd = 0; nw.Chr = h.Chr; nw.nWA = h.nWA; nw.WALrec = 0; nw.Str = h.Str; nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
+                swin[w] = nw;
+            }
+            for (u32 a = lane; a < h.nWA; a += 32) ln.wa[(u64)w * caps.spw + a] = seeds[sd + a];
+            sd += h.nWA;
+        }
+        ww.nW = nWin;
+    } else {
+        // ---- mode B: cooperative window creation and seed assignment (ReadAlign_stitchPieces.cpp:41-185)
+        const Piece* PC = pieces + (u64)i * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier
+        const u32 nP = ri.nP;
+        ww.nW = 0;
+        for (u32 iP = 0; iP < nP && !overReason; iP++) {
+            const Piece p = PC[iP];
+            if (p.Nrep > P.winAnchorMultimapNmax) continue;
+            const u64 aLength = p.Length;
+            bool stopPiece = false;
+            for (u64 base = 0; base < p.Nrep && !stopPiece && !overReason; base += 32) {
+                const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
+                u64 a1 = 0, a1A = 0; u32 aStr = 0; u32 kind = 0;   // kind: 0 skip, 1 genomic, 2 sjdb (donor a1, acceptor a1A)
+                if (lane < nl) {
+                    a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
+                    aStr = (u32)(a1 >> ix.GstrandBit);
+                    a1 &= ix.GstrandMask;
+                    if (p.Dir == 1 && aStr == 0) { aStr = 1; }
+                    else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
+                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                    kind = 1;
+                    if (a1 >= ix.sjGstart) {
+                        u64 a1D, aLengthD, aLengthA; u32 sj1;
+                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) { a1 = a1D; kind = 2; } else kind = 0;
+                    }
+                }
+                for (u32 q = 0; q < nl; q++) {
+                    saEnum++;
+                    const u32 kq = __shfl_sync(0xffffffffu, kind, q);
+                    const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
+                    const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
+                    const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
+                    if (kq == 0) continue;
+                    int rc = coopCreateWindow(ln, ww, a1q, sq);
+                    if (rc == 0 && kq == 2) rc = coopCreateWindow(ln, ww, a1Aq, sq);
+                    if (rc == 102) { overReason = 1; break; }
+                    if (rc == 101) { stopPiece = true; break; }
+                }
+            }
+        }
+        // flanks :96-118 (one window per lane)
+        for (u32 w = lane; w < ww.nW; w += 32) {
+            Window W = swin[w];
+            if (W.gStart <= W.gEnd) {
+                u64 wb = W.gStart;
+                for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
+                W.gStart = (u32)wb;
+                wb = W.gEnd;
+                for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
+                W.gEnd = (u32)wb;
+            }
+            W.nWA = 0; W.WALrec = 0;
+            swin[w] = W;
+        }
+        __syncwarp();
+        // assignment :129-185
+        for (u32 iP = 0; iP < nP && !overReason && !tooManyAnchors; iP++) {
+            const Piece p = PC[iP];
+            const u64 aNrep = p.Nrep, aLength = p.Length;
+            const u32 aFrag = p.iFrag;
+            const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
+            for (u64 base = 0; base < p.Nrep && !tooManyAnchors; base += 32) {
+                const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
+                u64 a1 = 0, a1A = 0, aRstart = 0, aLengthD = 0, aLengthA = 0; u32 aStr = 0, kind = 0, isj = SJA_NONE;
+                int wD = -1, wA = -1;
+                if (lane < nl) {
+                    a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
+                    aStr = (u32)(a1 >> ix.GstrandBit);
+                    a1 &= ix.GstrandMask;
+                    aRstart = p.rStart;
+                    if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
+                    else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
+                    else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
+                    kind = 1;
+                    if (a1 >= ix.sjGstart) {
+                        u64 a1D;
+                        if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj)) { a1 = a1D; kind = 2; } else { kind = 0; isj = SJA_NONE; }
+                    }
+                    if (kind) {   // window lookup: windows do not change during the assignment phase
+                        const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
+                        for (u32 w = 0; w < ww.nW; w++) {
+                            const Window W = swin[w];
+                            if (W.Str != aStr) continue;
+                            if (wD < 0 && W.gStart <= binD && binD <= W.gEnd) wD = (int)w;
+                            if (kind == 2 && wA < 0 && W.gStart <= binA && binA <= W.gEnd) wA = (int)w;
+                        }
+                    }
+                }
+                for (u32 q = 0; q < nl; q++) {
+                    saEnum++;
+                    const u32 kq = __shfl_sync(0xffffffffu, kind, q);
+                    if (kq == 0) continue;
+                    const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
+                    const u64 rq = __shfl_sync(0xffffffffu, aRstart, q);
+                    const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
+                    const int wDq = __shfl_sync(0xffffffffu, wD, q);
+                    if (kq == 1) {
+                        if (!coopAssign(ln, ww, wDq, a1q, aLength, aNrep, aFrag, rq, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
+                    } else {
+                        const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
+                        const u64 lDq = __shfl_sync(0xffffffffu, aLengthD, q), lAq = __shfl_sync(0xffffffffu, aLengthA, q);
+                        const u32 isjq = __shfl_sync(0xffffffffu, isj, q);
+                        const int wAq = __shfl_sync(0xffffffffu, wA, q);
+                        if (!coopAssign(ln, ww, wDq, a1q, lDq, aNrep, aFrag, rq, aAnchor, isjq)) { tooManyAnchors = true; break; }
+                        if (!coopAssign(ln, ww, wAq, a1Aq, lAq, aNrep, aFrag, rq + lDq, aAnchor, isjq)) { tooManyAnchors = true; break; }
+                    }
+                }
+            }
+        }
+        if (tooManyAnchors) ww.nW = 0;
+        nWin = ww.nW;
+        ln.saEnum = saEnum;
+    }
+}
+
 // Modes: heavyPool != NULL : the lane of stitch_kernel that owned the read exported its windows + seeds (DFS-heavy read);
 //        heavyPool == NULL : the read was routed here right after seeding because it has many loci (nA): the warp also does the
 //                            window creation / seed assignment cooperatively (coalesced SA loads, 32-wide scans).
@@ -1695,7 +2086,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
     u64* epochPtr = trBuf + hs.trWords;                                      // persistent per-warp epoch of the stitch memo
     StitchMemo* memoTab = (StitchMemo*)(epochPtr + 1);                       // memoSlots (zeroed once at allocation)
     const bool memoOn = hs.memoSlots != 0 && caps.maxW <= 4096;
-    ln.memo = memoOn ? memoTab : nullptr; ln.memoMask = hs.memoSlots - 1; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1;
+    ln.memo = memoOn ? memoTab : nullptr; ln.memoMask = hs.memoSlots - 1; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
     u64 epoch = *epochPtr;
     WarpWin ww;
     ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
@@ -1743,139 +2134,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
-        bool tooManyAnchors = false;
-        u64 saEnum = 0;
-        if (heavyPool) {
-            // ---- mode A: import the exported windows + seeds
-            const u8* rec = heavyPool + heavyOff[i];
-            nWin = ((const u32*)rec)[0];
-            const HeavyWin* hw = (const HeavyWin*)(rec + 8);
-            const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
-            if (nWin > caps.maxW) { overReason = 5; nWin = 0; }
-            u32 sd = 0;
-            for (u32 w = 0; w < nWin; w++) {   // uniform loop; lanes copy the seeds of window w
-                const HeavyWin h = hw[w];
-                if (lane == 0) {
-                    Window nw; nw.gStart = 0; nw.gEnd = 0; nw.Chr = h.Chr; nw.nWA = h.nWA; nw.WALrec = 0; nw.Str = h.Str; nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
-                    swin[w] = nw;
-                }
-                for (u32 a = lane; a < h.nWA; a += 32) ln.wa[(u64)w * caps.spw + a] = seeds[sd + a];
-                sd += h.nWA;
-            }
-            ww.nW = nWin;
-        } else {
-            // ---- mode B: cooperative window creation and seed assignment (ReadAlign_stitchPieces.cpp:41-185)
-            const Piece* PC = pieces + (u64)i * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier
-            const u32 nP = ri.nP;
-            ww.nW = 0;
-            for (u32 iP = 0; iP < nP && !overReason; iP++) {
-                const Piece p = PC[iP];
-                if (p.Nrep > P.winAnchorMultimapNmax) continue;
-                const u64 aLength = p.Length;
-                bool stopPiece = false;
-                for (u64 base = 0; base < p.Nrep && !stopPiece && !overReason; base += 32) {
-                    const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
-                    u64 a1 = 0, a1A = 0; u32 aStr = 0; u32 kind = 0;   // kind: 0 skip, 1 genomic, 2 sjdb (donor a1, acceptor a1A)
-                    if (lane < nl) {
-                        a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
-                        aStr = (u32)(a1 >> ix.GstrandBit);
-                        a1 &= ix.GstrandMask;
-                        if (p.Dir == 1 && aStr == 0) { aStr = 1; }
-                        else if (p.Dir == 0 && aStr == 1) { a1 = ix.nGenome - (aLength + a1); }
-                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                        kind = 1;
-                        if (a1 >= ix.sjGstart) {
-                            u64 a1D, aLengthD, aLengthA; u32 sj1;
-                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) { a1 = a1D; kind = 2; } else kind = 0;
-                        }
-                    }
-                    for (u32 q = 0; q < nl; q++) {
-                        saEnum++;
-                        const u32 kq = __shfl_sync(0xffffffffu, kind, q);
-                        const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
-                        const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
-                        const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
-                        if (kq == 0) continue;
-                        int rc = coopCreateWindow(ln, ww, a1q, sq);
-                        if (rc == 0 && kq == 2) rc = coopCreateWindow(ln, ww, a1Aq, sq);
-                        if (rc == 102) { overReason = 1; break; }
-                        if (rc == 101) { stopPiece = true; break; }
-                    }
-                }
-            }
-            // flanks :96-118 (one window per lane)
-            for (u32 w = lane; w < ww.nW; w += 32) {
-                Window W = swin[w];
-                if (W.gStart <= W.gEnd) {
-                    u64 wb = W.gStart;
-                    for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
-                    W.gStart = (u32)wb;
-                    wb = W.gEnd;
-                    for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
-                    W.gEnd = (u32)wb;
-                }
-                W.nWA = 0; W.WALrec = 0;
-                swin[w] = W;
-            }
-            __syncwarp();
-            // assignment :129-185
-            for (u32 iP = 0; iP < nP && !overReason && !tooManyAnchors; iP++) {
-                const Piece p = PC[iP];
-                const u64 aNrep = p.Nrep, aLength = p.Length;
-                const u32 aFrag = p.iFrag;
-                const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
-                for (u64 base = 0; base < p.Nrep && !tooManyAnchors; base += 32) {
-                    const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
-                    u64 a1 = 0, a1A = 0, aRstart = 0, aLengthD = 0, aLengthA = 0; u32 aStr = 0, kind = 0, isj = SJA_NONE;
-                    int wD = -1, wA = -1;
-                    if (lane < nl) {
-                        a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
-                        aStr = (u32)(a1 >> ix.GstrandBit);
-                        a1 &= ix.GstrandMask;
-                        aRstart = p.rStart;
-                        if (p.Dir == 1 && aStr == 0) { aStr = 1; aRstart = Lread - (aLength + aRstart); }
-                        else if (p.Dir == 0 && aStr == 1) { aRstart = Lread - (aLength + aRstart); a1 = ix.nGenome - (aLength + a1); }
-                        else if (p.Dir == 1 && aStr == 1) { aStr = 0; a1 = ix.nGenome - (aLength + a1); }
-                        kind = 1;
-                        if (a1 >= ix.sjGstart) {
-                            u64 a1D;
-                            if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj)) { a1 = a1D; kind = 2; } else { kind = 0; isj = SJA_NONE; }
-                        }
-                        if (kind) {   // window lookup: windows do not change during the assignment phase
-                            const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
-                            for (u32 w = 0; w < ww.nW; w++) {
-                                const Window W = swin[w];
-                                if (W.Str != aStr) continue;
-                                if (wD < 0 && W.gStart <= binD && binD <= W.gEnd) wD = (int)w;
-                                if (kind == 2 && wA < 0 && W.gStart <= binA && binA <= W.gEnd) wA = (int)w;
-                            }
-                        }
-                    }
-                    for (u32 q = 0; q < nl; q++) {
-                        saEnum++;
-                        const u32 kq = __shfl_sync(0xffffffffu, kind, q);
-                        if (kq == 0) continue;
-                        const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
-                        const u64 rq = __shfl_sync(0xffffffffu, aRstart, q);
-                        const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
-                        const int wDq = __shfl_sync(0xffffffffu, wD, q);
-                        if (kq == 1) {
-                            if (!coopAssign(ln, ww, wDq, a1q, aLength, aNrep, aFrag, rq, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
-                        } else {
-                            const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
-                            const u64 lDq = __shfl_sync(0xffffffffu, aLengthD, q), lAq = __shfl_sync(0xffffffffu, aLengthA, q);
-                            const u32 isjq = __shfl_sync(0xffffffffu, isj, q);
-                            const int wAq = __shfl_sync(0xffffffffu, wA, q);
-                            if (!coopAssign(ln, ww, wDq, a1q, lDq, aNrep, aFrag, rq, aAnchor, isjq)) { tooManyAnchors = true; break; }
-                            if (!coopAssign(ln, ww, wAq, a1Aq, lAq, aNrep, aFrag, rq + lDq, aAnchor, isjq)) { tooManyAnchors = true; break; }
-                        }
-                    }
-                }
-            }
-            if (tooManyAnchors) ww.nW = 0;
-            nWin = ww.nW;
-            ln.saEnum = saEnum;
-        }
+        warpBuildWindows(ln, ww, ix, P, ri, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason);
         __syncwarp();
         // ---- task table (lane 0): split depth per window, prefix sums (windows without seeds get an empty task range)
         u32 nTasks = 0;
@@ -2053,6 +2312,8 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(De
         PROF_ADD(25, hsum); PROF_ADD(26, msum);
     }
 }
+
+#include "stitch_flat.cuh"
 
 __global__ void prof_read_kernel(unsigned long long* out, int reset) {
     int t = threadIdx.x;

@@ -1,0 +1,611 @@
+// stitch_flat.cuh — heavy reads, flattened over the whole chunk (included at the end of stitch.cu, namespace starb).
+//
+// stitch_heavy_kernel gives one warp to one read and keeps the read's three phases inside that warp: windows (cooperative),
+// sub-tree evaluation (lanes pull tasks), ordered recording (lane 0).  Measured on B200 (profiles/r01_summary.md): the lanes of a
+// warp wait for the longest sub-tree of THEIR read and for lane 0's recording, 5.7 of 32 lanes execute on average, and the
+// per-lane DFS state in local memory (interleaved by lane) is cached with a handful of useful bytes per 32-byte sector.
+// Here the three phases are three kernels over ALL heavy reads of the chunk, so that no lane ever waits for a read:
+//
+//   flat_setup_kernel   one warp per read: window creation / seed assignment (same cooperative code as the heavy kernel), then
+//                       the read is exported to the flat pool in HBM: R0 | R2 | FlatWin[nWin] | Seed[nSeeds], plus one FlatTask
+//                       per prefix sub-tree of every window (task ids of a read are contiguous and ascending = the reference's
+//                       DFS order, windows in window order);
+//   flat_dfs_kernel     one LANE per task, persistent lanes, warp-aggregated global ticket: the pure part of the recursion
+//                       (stitch chain, end extension, filters, score) for every leaf of the sub-tree; surviving leaves become
+//                       16-byte candidates in the task's FlatOut (first candidate inline, more in 128-byte blocks);
+//   flat_record_kernel  one LANE per read: the reference's order-dependent part (maxScoreMate, record test, blocksOverlap dedup,
+//                       ordered insert, multMapSelect) over the candidates in window / task / leaf order.
+//
+// Results are identical to the sequential recursion for the same reason as in the heavy kernel (evalLeaf is a pure function of
+// the path; recordLeaf sees the leaves in DFS order).
+
+struct FlatRec {          // one per heavy read of the chunk
+    u64 poolOff;          // record in the flat pool
+    u32 read;             // read index in the chunk
+    u32 nWin;             // windows with seeds (only those are exported)
+    u32 taskBase, nTasks; // tasks [taskBase, taskBase+nTasks) of the global task array
+    u32 over;             // overflow reason (0 = ok); also set by flat_dfs_kernel when the candidate pool is exhausted
+    u32 done;             // 1: the read was finished by the setup kernel (early exits)
+    u32 saEnum;
+    u32 Lread;
+    u32 mmMax;            // outFilterMismatchNmaxTotal of the read
+    u16 readLength[2];
+};
+static_assert(sizeof(FlatRec) == 48, "engine_api.cu sizes the record array with 48-byte entries");
+
+struct FlatWin { u32 Chr; u16 nWA; u8 Str; u8 depth; u32 seedOff; u32 taskStart; };   // 16 B
+struct FlatTask { u32 k; u16 w; u16 bits; };                                           // k = 0xFFFFFFFF: hole (never written)
+struct FlatOut { Cand c0; u32 count; u32 first; u32 nodes; u32 leaves; };              // 32 B per task
+#define FLAT_CAND_PER_BLOCK 7
+struct FlatBlock { u32 next; u32 count; Cand c[FLAT_CAND_PER_BLOCK]; u64 pad; };       // 128 B
+static_assert(sizeof(FlatOut) == 32 && sizeof(FlatBlock) == 128 && sizeof(FlatTask) == 8 && sizeof(FlatWin) == 16, "flat layouts");
+#define FLAT_NONE 0xFFFFFFFFu
+#define FLAT_TR_CHUNK 512   // 8-byte words a lane reserves at a time in the stored-transcript buffer
+
+struct FlatArgs {
+    FlatRec* recs;
+    u8* pool; u64 poolBytes;
+    unsigned long long* bumps;     // [0] pool bytes, [1] tasks, [2] candidate blocks, [3] stored-transcript words
+    FlatTask* tasks; FlatOut* outs; u64 maxTasks;
+    FlatBlock* blocks; u32 maxBlocks;
+    u64* trStore; u64 trWords;
+    u32 maxTasksPerRead, splitMin;
+};
+
+__device__ __forceinline__ u32 flatReadStride(u32 Lread) { return (Lread + 16) & ~15u; }
+
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+                                                   ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nHeavy, const u32* __restrict__ heavyList,
+                                                   const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
+                                                   u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
+                                                   star_align_t* __restrict__ staged, u32 smemStride, FlatArgs fa, u32 kBase) {
+    extern __shared__ u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warpInBlock = threadIdx.x >> 5;
+    const u32 warpsPerBlock = blockDim.x >> 5;
+    const u32 gwarp = blockIdx.x * warpsPerBlock + warpInBlock;
+    const u32 perWarp = (2 * smemStride + 32 + caps.maxW * (u32)sizeof(Window) + (caps.maxW + 4) * 4 + ((caps.maxW + 3) & ~3u) + 15) & ~15u;
+    u8* R0 = smem + (size_t)warpInBlock * perWarp;
+    u8* R2 = R0 + smemStride;
+    u32* sh = (u32*)(R0 + 2 * smemStride);
+    Window* swin = (Window*)(R0 + 2 * smemStride + 32);
+    u32* taskStart = (u32*)(swin + caps.maxW);
+    u8* depthOf = (u8*)(taskStart + caps.maxW + 4);
+    Lane ln;
+    ln.cur = nullptr; ln.leaf = nullptr; ln.stack = nullptr; ln.ph = nullptr;   // this kernel never stitches
+    ln.ix = &ix; ln.P = &P; ln.R0 = R0; ln.R2 = R2; ln.R = R0; ln.caps = caps;
+    {
+        u8* a = arenas + (u64)gwarp * caps.arenaBytes;
+        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+        ln.wa = (Seed*)a; a += (u64)caps.maxW * caps.spw * sizeof(Seed);
+        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+        a += 2 * sizeof(DevTr) + (u64)(caps.spw + 2) * sizeof(Frame);
+        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+        ln.winN = (u16*)a;
+    }
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
+    WarpWin ww;
+    ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
+    long long tSetup = 0;
+    for (;;) {
+        long long t0 = clock64();
+        u32 k = 0;
+        if (lane == 0) k = atomicAdd(counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nHeavy) break;
+        const u32 i = heavyList[k];
+        ReadInfo ri = info[i];
+        readBegin(ln, ri);
+        const u32 Lread = ri.Lread;
+        FlatRec rec;
+        rec.poolOff = 0; rec.read = i; rec.nWin = 0; rec.taskBase = 0; rec.nTasks = 0; rec.over = 0; rec.done = 0; rec.saEnum = 0;
+        rec.Lread = Lread; rec.mmMax = ri.outFilterMismatchNmaxTotal; rec.readLength[0] = ri.readLength[0]; rec.readLength[1] = ri.readLength[1];
+        if (ri.flags || ri.Lread < P.outFilterMatchNmin || ri.Nsplit == 0 || ri.nA == 0) {   // same early exits as stitch_kernel's fetch
+            if (lane == 0) {
+                if (ri.flags) {
+                    star_read_result_t res;
+                    res.unmapType = 0; res.nTr = 0; res.nTrOut = 0; res.mapMarker = 0; res.trOffset = 0; res.bestScore = 0; res.bestNMM = 0;
+                    res.bestRLength = 0; res.Lread = ri.Lread; res.bestTr = 0;
+                    results[i] = res;
+                } else if (ri.Lread < P.outFilterMatchNmin) selectExport(ln, ri, i, STAR_MARKER_READ_TOO_SHORT, 0, results, staged, info);
+                else if (ri.Nsplit == 0) selectExport(ln, ri, i, STAR_MARKER_NO_GOOD_PIECES, ri.split1_0, results, staged, info);
+                else selectExport(ln, ri, i, STAR_MARKER_ALL_PIECES_EXCEED_seedMultimapNmax, ri.multNminL, results, staged, info);
+                rec.done = 1;
+                fa.recs[kBase + k] = rec;
+            }
+            __syncwarp();
+            continue;
+        }
+        {   // read into shared memory (both orientations)
+            const u8* g = reads + (u64)i * stride;
+            for (u32 b = lane; b < Lread; b += 32) {
+                u8 c = g[b];
+                R0[b] = c;
+                R2[Lread - 1 - b] = c < 4 ? 3 - c : c;
+            }
+        }
+        if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
+        __syncwarp();
+        u32 nWin = 0;
+        u32 overReason = 0;
+        warpBuildWindows(ln, ww, ix, P, ri, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason);
+        __syncwarp();
+        // ---- task table (lane 0), allocation in the flat pool / task array
+        u32 nTasks = 0, nWinC = 0, nSeeds = 0, taskBase = 0;
+        u64 poolOff = 0;
+        const u32 rs = flatReadStride(Lread);
+        if (lane == 0) {
+            if (!overReason) {
+                u32 shift = 0;
+                for (;;) {
+                    u32 tot = 0;
+                    nWinC = 0; nSeeds = 0;
+                    for (u32 w = 0; w < nWin; w++) {
+                        u32 a = swin[w].nWA;
+                        u32 d = a <= fa.splitMin ? 0 : (a - fa.splitMin > 8 ? 8 : a - fa.splitMin);
+                        d = d > shift ? d - shift : 0;
+                        taskStart[w] = tot; depthOf[w] = (u8)d;
+                        if (a) { tot += 1u << d; nWinC++; nSeeds += a; }
+                    }
+                    taskStart[nWin] = tot;
+                    if (tot <= fa.maxTasksPerRead) { nTasks = tot; break; }
+                    shift++;
+                }
+                const u64 bytes = ((u64)2 * rs + (u64)nWinC * sizeof(FlatWin) + (u64)nSeeds * sizeof(Seed) + 15) & ~15ULL;
+                poolOff = atomicAdd(&fa.bumps[0], (unsigned long long)bytes);
+                if (poolOff + bytes > fa.poolBytes) overReason = 5;
+                if (nTasks) {
+                    const u64 tb = atomicAdd(&fa.bumps[1], (unsigned long long)nTasks);
+                    if (tb + nTasks > fa.maxTasks) {
+                        overReason = 5;
+                        for (u64 t = tb; t < tb + nTasks && t < fa.maxTasks; t++) { FlatTask h; h.k = FLAT_NONE; h.w = 0; h.bits = 0; fa.tasks[t] = h; }
+                    }
+                    taskBase = (u32)tb;
+                }
+            }
+            rec.over = overReason;
+            rec.saEnum = (u32)ln.saEnum;
+            if (!overReason) { rec.poolOff = poolOff; rec.nWin = nWinC; rec.taskBase = taskBase; rec.nTasks = nTasks; }
+            fa.recs[kBase + k] = rec;
+        }
+        overReason = __shfl_sync(0xffffffffu, overReason, 0);
+        poolOff = __shfl_sync(0xffffffffu, poolOff, 0);
+        taskBase = __shfl_sync(0xffffffffu, taskBase, 0);
+        nWinC = __shfl_sync(0xffffffffu, nWinC, 0);
+        if (!overReason) {
+            u8* rp = fa.pool + poolOff;
+            for (u32 b = lane * 4; b < rs; b += 128) {   // both orientations (32-bit copies; rs and smemStride are multiples of 4)
+                u32 v0 = 0, v2 = 0;
+                if (b + 4 <= smemStride) { v0 = *(const u32*)(R0 + b); v2 = *(const u32*)(R2 + b); }
+                *(u32*)(rp + b) = v0;
+                *(u32*)(rp + rs + b) = v2;
+            }
+            FlatWin* fw = (FlatWin*)(rp + 2 * (u64)rs);
+            Seed* fs = (Seed*)(fw + nWinC);
+            u32 wc = 0, so = 0;
+            const u32 kk = kBase + k;
+            for (u32 w = 0; w < nWin; w++) {   // uniform loop
+                const u32 a = swin[w].nWA;
+                if (a == 0) continue;
+                const u32 d = depthOf[w], ts = taskStart[w];
+                if (lane == 0) {
+                    FlatWin f; f.Chr = swin[w].Chr; f.nWA = (u16)a; f.Str = swin[w].Str; f.depth = (u8)d; f.seedOff = so; f.taskStart = ts;
+                    fw[wc] = f;
+                }
+                const Seed* src = ln.wa + (u64)w * caps.spw;
+                for (u32 q = lane; q < a; q += 32) fs[so + q] = src[q];
+                for (u32 q = lane; q < (1u << d); q += 32) { FlatTask h; h.k = kk; h.w = (u16)wc; h.bits = (u16)q; fa.tasks[(u64)taskBase + ts + q] = h; }
+                wc++; so += a;
+            }
+        }
+        __syncwarp();
+        tSetup += clock64() - t0;
+    }
+    PROF_ADD(16, tSetup);
+}
+
+// laneScratch != NULL: the DFS transcript, the leaf copy and the undo records of a lane live in a lane-contiguous 4 KB slice of HBM
+// (whole 128-byte lines belong to one lane) instead of lane-interleaved local memory; fetchMin: lanes fetch new tasks only when at
+// least that many lanes of the warp are waiting (or none is working), which keeps neighbouring lanes on neighbouring tasks.
+#define FLAT_LANE_SCRATCH 4096
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(DevIndex ix, star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps,
+                                                             u8* __restrict__ laneScratch, u32 fetchMin) {
+    const u32 lane = threadIdx.x & 31;
+    u64 nT = fa.bumps[1];
+    if (nT > fa.maxTasks) nT = fa.maxTasks;
+    Lane ln;
+    DevTr curL, leafL;
+    Frame stackL[STAR_UNDO_DEPTH];
+    u8 phL[STAR_DFS_MAX_DEPTH + 4];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
+    if (laneScratch) {
+        u8* a = laneScratch + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * FLAT_LANE_SCRATCH;
+        static_assert(2 * sizeof(DevTr) + STAR_UNDO_DEPTH * sizeof(Frame) <= FLAT_LANE_SCRATCH, "lane scratch too small");
+        ln.stack = (Frame*)a; a += STAR_UNDO_DEPTH * sizeof(Frame);
+        ln.cur = (DevTr*)a; a += sizeof(DevTr);
+        ln.leaf = (DevTr*)a;
+    }
+    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
+    ln.win = nullptr; ln.wa = nullptr; ln.pool = nullptr; ln.trPtr = nullptr; ln.winBase = nullptr; ln.winN = nullptr;
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
+    ln.overflow = 0; ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.maxScoreMate[0] = ln.maxScoreMate[1] = 0;
+    ln.Lread = 0; ln.readLength[0] = ln.readLength[1] = 0; ln.outFilterMismatchNmaxTotal = 0;
+    ln.forceDepth = 0; ln.forceBits = 0;
+    u32 ph = 0;   // 0 fetch, 1 node, 2 leaf, 3 idle
+    u64 t = 0;
+    u32 k = FLAT_NONE, lastK = FLAT_NONE;
+    u32 Chr = 0, Str = 0, nA = 0;
+    const Seed* WA = nullptr;
+    const u8* rp = nullptr;
+    u32 rs = 0, nWinK = 0;
+    u32 curBlock = FLAT_NONE, firstBlock = FLAT_NONE, nCand = 0;
+    int taskBest = 0;
+    Cand c0; c0.mask = 0; c0.trOff = FLAT_NONE; c0.score = 0; c0.iFrag = 0; c0.pad = 0;
+    u64 trCur = 0, trEnd = 0;
+    long long hc = 0, eU[3] = {0, 0, 0};
+    long long tStart = clock64();
+    for (;;) {
+        {
+            u32 mF = __ballot_sync(0xffffffffu, ph == 0), mN = __ballot_sync(0xffffffffu, ph == 1), mL = __ballot_sync(0xffffffffu, ph == 2);
+            hc++; eU[0] += __popc(mF); eU[1] += __popc(mN); eU[2] += __popc(mL);
+            if (mF && ((u32)__popc(mF) >= fetchMin || (mN | mL) == 0)) {   // warp-aggregated ticket
+                const u32 leader = __ffs(mF) - 1;
+                u32 base = 0;
+                if (lane == leader) base = atomicAdd(counter, (u32)__popc(mF));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (ph == 0) { t = (u64)base + __popc(mF & ((1u << lane) - 1)); ph = 4; }
+            }
+        }
+        if (ph == 4) {
+            ph = 0;
+            if (t >= nT) { ph = 3; }
+            else {
+                const FlatTask tk = fa.tasks[t];
+                if (tk.k != FLAT_NONE) {
+                    k = tk.k;
+                    if (k != lastK) {
+                        const FlatRec rec = fa.recs[k];
+                        ln.Lread = rec.Lread; ln.readLength[0] = rec.readLength[0]; ln.readLength[1] = rec.readLength[1];
+                        ln.outFilterMismatchNmaxTotal = rec.mmMax;
+                        rp = fa.pool + rec.poolOff;
+                        rs = flatReadStride(rec.Lread);
+                        nWinK = rec.nWin;
+                        lastK = k;
+                    }
+                    const FlatWin W = ((const FlatWin*)(rp + 2 * (u64)rs))[tk.w];
+                    Chr = W.Chr; Str = W.Str; nA = W.nWA;
+                    WA = (const Seed*)(rp + 2 * (u64)rs + (u64)nWinK * sizeof(FlatWin)) + W.seedOff;
+                    ln.R0 = rp; ln.R2 = rp + rs;
+                    ln.R = Str == 0 ? ln.R0 : ln.R2;
+                    ln.nodes = 0; ln.leaves = 0;
+                    dfsInit(ln);
+                    ln.forceDepth = W.depth;
+                    ln.forceBits = tk.bits;
+                    curBlock = FLAT_NONE; firstBlock = FLAT_NONE; nCand = 0; taskBest = 0;
+                    ph = 1;
+                }
+                // a hole (task range of a read that did not fit): fetch again in the next iteration
+            }
+        }
+        if (ph == 1) {
+            int r = dfsStep(ln, WA, nA);
+            if (r == DFS_LEAF) ph = 2;
+            else if (r == DFS_DONE) {
+                FlatOut o;
+                o.c0 = c0; o.count = nCand; o.first = firstBlock; o.nodes = (u32)ln.nodes; o.leaves = (u32)ln.leaves;
+                fa.outs[t] = o;
+                ph = 0;
+            }
+        }
+        if (ph == 2) {
+            ln.leaves++;
+            if (evalLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str)) {
+                const int sc = ln.leaf->h.maxScore;
+                Cand c; c.mask = ln.inclMask; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
+                if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
+                    if (sc > taskBest) taskBest = sc;
+                    const u32 nEx = ln.leaf->h.nExons;
+                    const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
+                    if (trCur + words > trEnd) {
+                        const u64 off = atomicAdd(&fa.bumps[3], (unsigned long long)FLAT_TR_CHUNK);
+                        if (off + FLAT_TR_CHUNK <= fa.trWords && off + FLAT_TR_CHUNK < 0xFFFFFFFFULL) { trCur = off; trEnd = off + FLAT_TR_CHUNK; }
+                        else { trCur = 0; trEnd = 0; }
+                    }
+                    if (trCur + words <= trEnd) {
+                        u64* dst = fa.trStore + trCur;
+                        const u64* sh8 = (const u64*)&ln.leaf->h;
+                        for (u32 q = 0; q < sizeof(TrHead) / 8; q++) dst[q] = sh8[q];
+                        const u64* se = (const u64*)ln.leaf->ex;
+                        for (u32 q = 0; q < nEx * (sizeof(Exon) / 8); q++) dst[sizeof(TrHead) / 8 + q] = se[q];
+                        c.trOff = (u32)trCur;
+                        trCur += words;
+                    }
+                }
+                if (nCand == 0) {
+                    c0 = c;
+                    nCand = 1;
+                } else {
+                    bool ok = true;
+                    if (curBlock == FLAT_NONE || fa.blocks[curBlock].count == FLAT_CAND_PER_BLOCK) {
+                        const u64 nb = atomicAdd(&fa.bumps[2], 1ULL);
+                        if (nb >= fa.maxBlocks) { fa.recs[k].over = 5; ok = false; }
+                        else {
+                            fa.blocks[nb].next = FLAT_NONE; fa.blocks[nb].count = 0;
+                            if (curBlock == FLAT_NONE) firstBlock = (u32)nb; else fa.blocks[curBlock].next = (u32)nb;
+                            curBlock = (u32)nb;
+                        }
+                    }
+                    if (ok) {
+                        FlatBlock& B = fa.blocks[curBlock];
+                        B.c[B.count] = c;
+                        B.count++;
+                        nCand++;
+                    }
+                }
+            }
+            ph = 1;
+        }
+        if (__all_sync(0xffffffffu, ph == 3)) break;
+    }
+    PROF_ADD(17, clock64() - tStart);
+    PROF_ADD(21, hc);
+    for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
+}
+
+// ---- warp-uniform variant.  Measured on B200: in flat_dfs_kernel the lanes of a warp do not overlap at all (32-task batches with 1.7
+// lanes working on average take the same time as 12 lanes working): every lane walks its own branchy path, SIMT serialises them.
+// Here a WARP owns one task at a time and all 32 lanes execute the same scalar path (no divergence, every local-memory access is
+// one full 128-byte line); the DFS transcript, leaf copy and undo records are ONE copy per warp in shared memory; the byte loops
+// (end extension, junction scan, gap mismatches) are done cooperatively, 32 bases per step (coop* functions in stitch.cu).
+// Tasks are fetched 32 at a time (lane j prefetches the descriptor, read header and window of task base+j).
+#define FLAT_WARP_SMEM (2 * (u32)sizeof(DevTr) + STAR_UNDO_DEPTH * (u32)sizeof(Frame) + 64)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(DevIndex ix, star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps) {
+    extern __shared__ u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warpInBlock = threadIdx.x >> 5;
+    u64 nT = fa.bumps[1];
+    if (nT > fa.maxTasks) nT = fa.maxTasks;
+    u8* ws = smem + (size_t)warpInBlock * FLAT_WARP_SMEM;
+    Lane ln;
+    ln.stack = (Frame*)ws;
+    ln.cur = (DevTr*)(ws + STAR_UNDO_DEPTH * sizeof(Frame));
+    ln.leaf = ln.cur + 1;
+    ln.ph = (u8*)(ln.leaf + 1);
+    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
+    ln.win = nullptr; ln.wa = nullptr; ln.pool = nullptr; ln.trPtr = nullptr; ln.winBase = nullptr; ln.winN = nullptr;
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
+    ln.overflow = 0; ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.maxScoreMate[0] = ln.maxScoreMate[1] = 0;
+    ln.Lread = 0; ln.readLength[0] = ln.readLength[1] = 0; ln.outFilterMismatchNmaxTotal = 0;
+    ln.forceDepth = 0; ln.forceBits = 0;
+    ln.coop = 1;
+    u64 trCur = 0, trEnd = 0;
+    long long tStart = clock64();
+    for (;;) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((u64)base >= nT) break;
+        // lane j prefetches task base+j
+        const u64 tMine = (u64)base + lane;
+        FlatTask tk; tk.k = FLAT_NONE; tk.w = 0; tk.bits = 0;
+        if (tMine < nT) tk = fa.tasks[tMine];
+        u64 poolOffM = 0; u32 LreadM = 0, mmM = 0, rlM = 0, nWinM = 0;
+        FlatWin WM; WM.Chr = 0; WM.nWA = 0; WM.Str = 0; WM.depth = 0; WM.seedOff = 0; WM.taskStart = 0;
+        if (tk.k != FLAT_NONE) {
+            const FlatRec* r = &fa.recs[tk.k];
+            poolOffM = r->poolOff; LreadM = r->Lread; mmM = r->mmMax; rlM = (u32)r->readLength[0] | ((u32)r->readLength[1] << 16); nWinM = r->nWin;
+            WM = ((const FlatWin*)(fa.pool + poolOffM + 2 * (u64)flatReadStride(LreadM)))[tk.w];
+        }
+        const u32 vmask = __ballot_sync(0xffffffffu, tk.k != FLAT_NONE);
+        for (u32 j = 0; j < 32; j++) {
+            if (!((vmask >> j) & 1u)) continue;
+            const u32 k = __shfl_sync(0xffffffffu, tk.k, j);
+            const u32 bits = __shfl_sync(0xffffffffu, (u32)tk.bits, j);
+            const u64 poolOff = __shfl_sync(0xffffffffu, poolOffM, j);
+            const u32 Lread = __shfl_sync(0xffffffffu, LreadM, j);
+            const u32 rl = __shfl_sync(0xffffffffu, rlM, j);
+            const u32 nWinK = __shfl_sync(0xffffffffu, nWinM, j);
+            const u32 Chr = __shfl_sync(0xffffffffu, WM.Chr, j);
+            const u32 wpk = __shfl_sync(0xffffffffu, (u32)WM.nWA | ((u32)WM.Str << 16) | ((u32)WM.depth << 24), j);
+            const u32 seedOff = __shfl_sync(0xffffffffu, WM.seedOff, j);
+            ln.outFilterMismatchNmaxTotal = __shfl_sync(0xffffffffu, mmM, j);
+            const u32 nA = wpk & 0xffffu, Str = (wpk >> 16) & 0xffu, depth = wpk >> 24;
+            const u64 t = (u64)base + j;
+            const u32 rs = flatReadStride(Lread);
+            const u8* rp = fa.pool + poolOff;
+            const Seed* WA = (const Seed*)(rp + 2 * (u64)rs + (u64)nWinK * sizeof(FlatWin)) + seedOff;
+            ln.Lread = Lread; ln.readLength[0] = (u16)(rl & 0xffffu); ln.readLength[1] = (u16)(rl >> 16);
+            ln.R0 = rp; ln.R2 = rp + rs;
+            ln.R = Str == 0 ? ln.R0 : ln.R2;
+            ln.nodes = 0; ln.leaves = 0;
+            dfsInit<true>(ln);
+            ln.forceDepth = depth;
+            ln.forceBits = bits;
+            u32 curBlock = FLAT_NONE, firstBlock = FLAT_NONE, nCand = 0, inBlock = 0;
+            int taskBest = 0;
+            Cand c0; c0.mask = 0; c0.trOff = FLAT_NONE; c0.score = 0; c0.iFrag = 0; c0.pad = 0;
+            for (;;) {
+                __syncwarp();
+                const int r = dfsStep<true>(ln, WA, nA);
+                __syncwarp();
+                if (r == DFS_DONE) break;
+                if (r != DFS_LEAF) continue;
+                ln.leaves++;
+                const bool keep = evalLeaf<true>(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str);
+                __syncwarp();
+                if (!keep) continue;
+                const int sc = ln.leaf->h.maxScore;
+                Cand c; c.mask = ln.inclMask; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
+                if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
+                    if (sc > taskBest) taskBest = sc;
+                    const u32 nEx = ln.leaf->h.nExons;
+                    const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
+                    if (trCur + words > trEnd) {
+                        u64 off = 0;
+                        if (lane == 0) off = atomicAdd(&fa.bumps[3], (unsigned long long)(4 * FLAT_TR_CHUNK));
+                        off = __shfl_sync(0xffffffffu, off, 0);
+                        if (off + 4 * FLAT_TR_CHUNK <= fa.trWords && off + 4 * FLAT_TR_CHUNK < 0xFFFFFFFFULL) { trCur = off; trEnd = off + 4 * FLAT_TR_CHUNK; }
+                        else { trCur = 0; trEnd = 0; }
+                    }
+                    if (trCur + words <= trEnd) {
+                        u64* dst = fa.trStore + trCur;
+                        const u64* src = (const u64*)ln.leaf;   // head and exons are contiguous in DevTr
+                        for (u32 q = lane; q < words; q += 32) dst[q] = src[q];
+                        c.trOff = (u32)trCur;
+                        trCur += words;
+                    }
+                }
+                if (nCand == 0) {
+                    c0 = c;
+                    nCand = 1;
+                } else {
+                    bool ok = true;
+                    if (curBlock == FLAT_NONE || inBlock == FLAT_CAND_PER_BLOCK) {
+                        u64 nb = 0;
+                        if (lane == 0) nb = atomicAdd(&fa.bumps[2], 1ULL);
+                        nb = __shfl_sync(0xffffffffu, nb, 0);
+                        if (nb >= fa.maxBlocks) { if (lane == 0) fa.recs[k].over = 5; ok = false; }
+                        else {
+                            if (lane == 0) {
+                                fa.blocks[nb].next = FLAT_NONE; fa.blocks[nb].count = 0;
+                                if (curBlock != FLAT_NONE) fa.blocks[curBlock].next = (u32)nb;
+                            }
+                            if (curBlock == FLAT_NONE) firstBlock = (u32)nb;
+                            curBlock = (u32)nb;
+                            inBlock = 0;
+                        }
+                    }
+                    if (ok) {
+                        if (lane == 0) { FlatBlock& B = fa.blocks[curBlock]; B.c[inBlock] = c; B.count = inBlock + 1; }
+                        inBlock++;
+                        nCand++;
+                    }
+                }
+            }
+            if (lane == 0) {
+                FlatOut o;
+                o.c0 = c0; o.count = nCand; o.first = firstBlock; o.nodes = (u32)ln.nodes; o.leaves = (u32)ln.leaves;
+                fa.outs[t] = o;
+            }
+        }
+    }
+    PROF_ADD(17, clock64() - tStart);
+}
+
+// host-side launcher (the kernels are templates over the occupancy target; engine_api.cu is another translation unit)
+void launch_flat_dfs(int mode, int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps,
+                     u8* laneScratch, u32 fetchMin) {
+    if (mode == 1) {
+        const u32 smem = 4 * FLAT_WARP_SMEM;
+        if (ctasPerSM <= 4) flat_dfs_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, fa, counter, caps);
+        else if (ctasPerSM <= 6) flat_dfs_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, fa, counter, caps);
+        else flat_dfs_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, fa, counter, caps);
+        return;
+    }
+    if (ctasPerSM <= 2) flat_dfs_kernel<2><<<nSM * 2, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
+    else if (ctasPerSM == 3) flat_dfs_kernel<3><<<nSM * 3, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
+    else flat_dfs_kernel<4><<<nSM * 4, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
+}
+
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(DevIndex ix, star_params_t P, ReadInfo* __restrict__ info, u32 nRecs, u32* __restrict__ counter,
+                                                    u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
+                                                    star_align_t* __restrict__ staged, FlatArgs fa) {
+    const u32 gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    Lane ln;
+    DevTr curL, leafL;
+    Frame stackL[2];
+    u8 phL[4];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
+    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
+    {   // per-lane arena: compacted window Chr/Str | transcript pool | pointer arrays
+        u8* a = arenas + (u64)gthread * caps.arenaBytes;
+        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+        ln.winN = (u16*)a;
+        ln.wa = nullptr;
+    }
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
+    long long tStart = clock64();
+    long long nReplay = 0;
+    for (;;) {
+        const u32 k = atomicAdd(counter, 1u);
+        if (k >= nRecs) break;
+        const FlatRec rec = fa.recs[k];
+        if (rec.done) continue;
+        const u32 i = rec.read;
+        ReadInfo ri = info[i];
+        readBegin(ln, ri);
+        ln.saEnum = rec.saEnum;
+        if (rec.over) {
+            ln.overflow = rec.over;
+        } else {
+            const u8* rp = fa.pool + rec.poolOff;
+            const u32 rs = flatReadStride(rec.Lread);
+            ln.R0 = rp; ln.R2 = rp + rs;
+            const FlatWin* fw = (const FlatWin*)(rp + 2 * (u64)rs);
+            const Seed* fs = (const Seed*)(fw + rec.nWin);
+            {   // work counters of the sub-tree evaluation
+                u64 nd = 0, lv = 0;
+                for (u32 t = 0; t < rec.nTasks; t++) { const FlatOut& o = fa.outs[(u64)rec.taskBase + t]; nd += o.nodes; lv += o.leaves; }
+                ln.nodes = nd; ln.leaves = lv;
+            }
+            for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+            for (u32 w = 0; w < rec.nWin && !ln.overflow; w++) {
+                const FlatWin W = fw[w];
+                u16* wTr = nullptr; u16 nWinTr = 0;
+                int rc = windowBegin(ln, wTr, nWinTr);
+                if (rc == 2) { ln.overflow = 3; break; }
+                if (rc == 1) break;
+                const u32 Chr = W.Chr, Str = W.Str, nA = W.nWA;
+                const Seed* WA = fs + W.seedOff;
+                ln.R = Str == 0 ? ln.R0 : ln.R2;
+                const u64 tb = (u64)rec.taskBase + W.taskStart;
+                for (u32 tq = 0; tq < (1u << W.depth) && !ln.overflow; tq++) {
+                    const FlatOut o = fa.outs[tb + tq];
+                    u32 b = o.first, inBlock = 0;
+                    for (u32 q = 0; q < o.count; q++) {
+                        Cand c;
+                        if (q == 0) c = o.c0;
+                        else {
+                            if (inBlock == FLAT_CAND_PER_BLOCK) { b = fa.blocks[b].next; inBlock = 0; }
+                            c = fa.blocks[b].c[inBlock++];
+                        }
+                        if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
+                        int wBest = ln.pool[wTr[0]].h.maxScore;
+                        if (c.score + P.outFilterMultimapScoreRange >= wBest ||
+                            (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
+                            if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; break; }
+                            if (c.trOff != FLAT_NONE) {   // transcript stored by the lane that evaluated the leaf
+                                const u64* src = fa.trStore + c.trOff;
+                                u64* dh = (u64*)&ln.leaf->h;
+                                for (u32 z = 0; z < sizeof(TrHead) / 8; z++) dh[z] = src[z];
+                                const u32 nEx = ln.leaf->h.nExons;
+                                u64* de = (u64*)ln.leaf->ex;
+                                for (u32 z = 0; z < nEx * (sizeof(Exon) / 8); z++) de[z] = src[sizeof(TrHead) / 8 + z];
+                                recordLeaf(ln, wTr, &nWinTr);
+                            } else {
+                                int Score; u32 tR2; u64 tG2;
+                                nReplay++;
+                                bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                if (ok) recordLeaf(ln, wTr, &nWinTr);
+                            }
+                        }
+                    }
+                }
+                windowEnd(ln, Chr, Str, wTr, nWinTr);
+            }
+        }
+        selectExport(ln, ri, i, 0, 0, results, staged, info);
+    }
+    PROF_ADD(18, clock64() - tStart);
+    {
+        long long r = nReplay;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+        PROF_ADD(20, r);
+    }
+}

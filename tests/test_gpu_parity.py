@@ -53,14 +53,19 @@ def test_engine_matches_oracle_tiny(lib, oracle, golden, tiny_index, name):
 
 @pytest.mark.parametrize("env", [
     {"STAR_B200_HEAVY_EST": "0"},                                   # heavy path off: everything on the one-lane-per-read path
-    {"STAR_B200_HEAVY_NA": "0x7fffffff", "STAR_B200_HEAVY_EST": "1"},   # every read exported to the warp-per-read kernel (mode A)
-    {"STAR_B200_HEAVY_NA": "1"},                                    # every read with >1 locus: cooperative windows + DFS tasks (mode B)
-    {"STAR_B200_HEAVY_NA": "1", "STAR_B200_HEAVY_MEMO": "256"},     # the same with the (optional) shared stitch memo switched on
+    {"STAR_B200_HEAVY_NA": "0x7fffffff", "STAR_B200_HEAVY_EST": "1"},   # every read exported by its lane (mode A) -> flattened heavy path
+    {"STAR_B200_HEAVY_NA": "1"},                                    # every read with >1 locus: cooperative windows (mode B) -> flattened heavy path
+    {"STAR_B200_HEAVY_NA": "1", "STAR_B200_HEAVY_SPLIT": "2"},      # the same with windows cut into many prefix sub-trees
+    {"STAR_B200_HEAVY_NA": "1", "STAR_B200_FLAT_MAXTASKS": "3000", "STAR_B200_FLAT_MAXBLOCKS": "40", "STAR_B200_FLAT_TRWORDS": "4096",
+     "STAR_B200_FLAT_POOL_BYTES": "2000000"},                       # flat pools exhausted: reads fall to the overflow tiers / replay their leaves
+    {"STAR_B200_HEAVY_FLAT": "0", "STAR_B200_HEAVY_NA": "0x7fffffff", "STAR_B200_HEAVY_EST": "1"},   # warp-per-read kernel, mode A
+    {"STAR_B200_HEAVY_FLAT": "0", "STAR_B200_HEAVY_NA": "1"},       # warp-per-read kernel, mode B
+    {"STAR_B200_HEAVY_FLAT": "0", "STAR_B200_HEAVY_NA": "1", "STAR_B200_HEAVY_MEMO": "256"},     # the same with the (optional) shared stitch memo switched on
     {"STAR_B200_FAST_MAXW": "4", "STAR_B200_FAST_MAXTR": "4", "STAR_B200_FAST_MAXP": "8", "STAR_B200_MID_MAXW": "16", "STAR_B200_MID_MAXTR": "8"},  # tiny caps: overflow tiers
 ])
 @pytest.mark.parametrize("name", ["std", "hard"])
 def test_engine_paths_are_all_exact(lib, oracle, golden, tiny_index, name, env):
-    """Every execution path of the engine (light lanes, both heavy-kernel modes, overflow tiers) must give the oracle's result."""
+    """Every execution path of the engine (light lanes, flattened heavy path, warp-per-read kernel, overflow tiers) must give the oracle's result."""
     import oracle_capi as oc
     import star_b200 as sb
     files = _sets(golden)[name]

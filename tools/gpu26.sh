@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+STAR_B200_FLAT_DFS_MODE=0 STAR_B200_FLAT_DFS_CTAS_PER_SM=4 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:flat_dfs_kernel -c 1 -o gpurun_out/prof_flat_lane -f python tools/analyze_chunk.py 262144 > gpurun_out/ncu_flat_lane.log 2>&1; tail -1 gpurun_out/ncu_flat_lane.log
+STAR_B200_FLAT_DFS_MODE=1 STAR_B200_FLAT_DFS_CTAS_PER_SM=4 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:flat_dfs_warp_kernel -c 1 -o gpurun_out/prof_flat_warp -f python tools/analyze_chunk.py 262144 > gpurun_out/ncu_flat_warp.log 2>&1; tail -1 gpurun_out/ncu_flat_warp.log
+ls -la gpurun_out/*.ncu-rep
