@@ -258,7 +258,7 @@ __device__ void maxMappableLength2strands(SeedCtx& c, StoreState& st, const star
 }
 
 // Persistent lanes: each lane takes the next read from `counter` (or from readList on the slow path).
-__global__ void __launch_bounds__(128) seed_search_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+__global__ void __launch_bounds__(128) seed_search_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                           ReadInfo* __restrict__ info, Piece* __restrict__ pieces, u32 maxP, u32 nReads,
                                                           const u32* __restrict__ readList, u32* __restrict__ counter,
                                                           WorkCounters* __restrict__ /*wc*/, u32 smemStride) {

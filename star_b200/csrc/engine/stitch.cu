@@ -132,13 +132,9 @@ struct ExtRes { u32 extendL; int maxScore; u32 nMatch, nMM; };
 //  * Score/nMatch/nMM at a base are prefix counts of matches / mismatches (popc of ballot masks below the lane);
 //  * a base is recorded when it is a match, its cap test holds and its Score exceeds every previously recorded Score, so the final
 //    record is the FIRST base that attains the maximum Score among the matches passing the cap test (if that maximum is > 0).
-__device__ __noinline__ bool coopExtendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax, ExtRes& res) {
+__device__ __forceinline__ bool coopExtendAlign(const u8* R, const u8* G, const u64 nG, const u64 Lread, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax, ExtRes& res) {
     const u32 lane = threadIdx.x & 31;
     const u32 below = (1u << lane) - 1;
-    const u8* R = ln.R;
-    const u8* G = ln.ix->G;
-    const u64 nG = ln.ix->nGenome;
-    const u64 Lread = ln.Lread;
     res.maxScore = 0;
     double capEnd = pMMmax * double(Lprev + L);
     const double nMMmaxD = double(nMMmax);
@@ -194,24 +190,38 @@ __device__ __noinline__ bool coopExtendAlign(const Lane& ln, u64 rStart, u64 gSt
 
 // extendAlign.cpp:6-92.  R/G are addressed through the lane (R orientation already selected).
 // COOP: the caller is a warp executing one Lane uniformly (flat_dfs_warp_kernel).
+struct ExtOut { ExtRes r; bool ok; };
+// One copy per kernel (four call sites).  Takes the sequence pointers instead of the Lane so that the caller's Lane never escapes
+// (its fields can then live in registers).
 template <bool COOP>
-__device__ __noinline__ bool extendAlignShared(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
-                                               bool extendToEnd, ExtRes& res);
+__device__ __noinline__ ExtOut extendAlignShared(const u8* Rbase, const u8* Gbase, u64 nG, u64 Lread, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev,
+                                                 u64 nMMmax, double pMMmax, bool extendToEnd);
 template <bool COOP = false>
 __device__ __forceinline__ bool extendAlign(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
                                             bool extendToEnd, ExtRes& res) {
-    return extendAlignShared<COOP>(ln, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd, res);   // one copy per kernel
+    const ExtOut o = extendAlignShared<COOP>(ln.R, ln.ix->G, ln.ix->nGenome, ln.Lread, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd);
+    res = o.r;
+    return o.ok;
 }
+__device__ __forceinline__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                                bool extendToEnd, ExtRes& res);
 template <bool COOP>
-__device__ __noinline__ bool extendAlignShared(const Lane& ln, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
-                            bool extendToEnd, ExtRes& res) {
+__device__ __noinline__ ExtOut extendAlignShared(const u8* Rbase, const u8* Gbase, u64 nG, u64 Lread, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev,
+                                                 u64 nMMmax, double pMMmax, bool extendToEnd) {
+    ExtOut o;
+    o.r.extendL = 0; o.r.maxScore = 0; o.r.nMatch = 0; o.r.nMM = 0;   // (every caller passes a zeroed result)
     if constexpr (COOP) {
-        if (!extendToEnd) return coopExtendAlign(ln, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, res);
+        if (!extendToEnd) { o.ok = coopExtendAlign(Rbase, Gbase, nG, Lread, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, o.r); return o; }
     }
+    o.ok = extendAlignBody(Rbase, Gbase, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd, o.r);
+    return o;
+}
+__device__ __forceinline__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                                bool extendToEnd, ExtRes& res) {
     int Score = 0, nMatch = 0, nMM = 0;
     res.maxScore = 0;
-    const u8* R = ln.R + rStart;
-    const u8* G = ln.ix->G + (i64)gStart;
+    const u8* R = Rbase + rStart;
+    const u8* G = Gbase + (i64)gStart;
     if (extendToEnd) {
         int iExt;
         for (iExt = 0; iExt < (int)L; iExt++) {
@@ -958,29 +968,27 @@ __device__ __forceinline__ void dfsInit(Lane& ln) {
 template <bool COOP = false>
 __device__ __forceinline__ void dfsBacktrack(Lane& ln) {
     DevTr* t = ln.cur;
-    int L = ln.level - 1;
-    while (L >= 0) {
-        const u8 p = ln.ph[L];
-        if (p == 1) {
-            // undo the include of seed L, then explore the branch without it (WA_Anchor==2 never occurs: WlastAnchor is initialised
-            // to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
-            const Frame& u = ln.stack[--ln.nInc];
-            if constexpr (COOP) {
-                if (u.h.nExons > 0) warpCopyWords(&t->ex[u.h.nExons - 1], &u.last, 6);
-                warpCopyWords(&t->h, &u.h, 20);
-            } else {
-                if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
-                t->h = u.h;
-            }
-            ln.Score = u.Score; ln.tR2 = u.tR2; ln.tG2 = u.tG2;
-            ln.lastSeed = (int)u.pad[0] - 1;
-            ln.inclMask &= ~(1ULL << L);
-            ln.ph[L] = 2;
-            ln.level = L + 1;
-            ln.ph[L + 1] = 0;
-            return;
+    // The deepest level whose exclude branch is still open is the last included seed of the path (levels above it were excluded on
+    // the way down), unless that include was forced by the task prefix (ph 3): then the sub-tree is exhausted.
+    const int L = ln.lastSeed;
+    if (L >= 0 && ln.ph[L] == 1) {
+        // undo the include of seed L, then explore the branch without it (WA_Anchor==2 never occurs: WlastAnchor is initialised
+        // to (uint)-1 and only updated when WlastAnchor<iA, ReadAlign_stitchPieces.cpp:117, assignAlignToWindow.cpp:128)
+        const Frame& u = ln.stack[--ln.nInc];
+        if constexpr (COOP) {
+            if (u.h.nExons > 0) warpCopyWords(&t->ex[u.h.nExons - 1], &u.last, 6);
+            warpCopyWords(&t->h, &u.h, 20);
+        } else {
+            if (u.h.nExons > 0) t->ex[u.h.nExons - 1] = u.last;
+            t->h = u.h;
         }
-        L--;
+        ln.Score = u.Score; ln.tR2 = u.tR2; ln.tG2 = u.tG2;
+        ln.lastSeed = (int)u.pad[0] - 1;
+        ln.inclMask &= ~(1ULL << L);
+        ln.ph[L] = 2;
+        ln.level = L + 1;
+        ln.ph[L + 1] = 0;
+        return;
     }
     ln.level = -1;
 }
@@ -1018,6 +1026,43 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
             ln.level = (int)L + 1;
             ln.ph[L + 1] = 0;
             continue;
+        }
+        if constexpr (COOP) {
+            // warp-uniform mode: the quick-fail test below for seeds L, L+1, .. is independent of the outcome for the earlier ones (nothing
+            // is included in between), so 32 seeds are tested at once and the DFS jumps to the first seed that needs a real attempt.
+            if (t->h.nExons > 0 && !forced) {
+                const u32 lane = threadIdx.x & 31;
+                const Exon& eA = t->ex[t->h.nExons - 1];
+                const bool full = t->h.nExons >= STAR_MAX_N_EXONS;
+                const u32 eFrag = eA.iFrag, eSj = eA.sjA;
+                u32 j = L;
+                for (;;) {
+                    const u32 idx = j + lane;
+                    bool real = false;
+                    if (idx < nA) {
+                        const Seed q = WA[idx];
+                        bool qf = full;
+                        if (!qf && eFrag == q.iFrag) {
+                            const bool sjdbDirect = q.sjA != SJA_NONE && eSj == q.sjA && (u64)q.rStart == (u64)ln.tR2 + 1 && ln.tG2 + 1 < q.gStart;
+                            qf = !sjdbDirect && ((u64)q.rStart + q.Length - 1 <= ln.tR2 || q.gStart + q.Length - 1 <= ln.tG2);
+                        }
+                        real = !qf;
+                    }
+                    const u32 realMask = __ballot_sync(0xffffffffu, real);
+                    const u32 span = nA - j < 32 ? nA - j : 32;
+                    const u32 skipped = realMask ? (u32)__ffs(realMask) - 1 : span;
+                    if (lane < skipped) ln.ph[j + lane] = 2;
+                    j += skipped;
+                    if (realMask || j >= nA) break;
+                }
+                __syncwarp();
+                if (j > L) {
+                    ln.nodes += (u64)(j - L - 1);   // (the skipped levels are visited one by one in the sequential order; this one is counted above)
+                    ln.level = (int)j;
+                    ln.ph[j] = 0;
+                    continue;
+                }
+            }
         }
         const Seed s = WA[L];
         if (t->h.nExons > 0) {
@@ -1411,7 +1456,7 @@ struct HeavyArgs {
 #ifndef STITCH_MIN_BLOCKS
 #define STITCH_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                      ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nReads,
                                                      const u32* __restrict__ readList, u32* __restrict__ counter, u8* __restrict__ arenas,
                                                      Caps caps, star_read_result_t* __restrict__ results, star_align_t* __restrict__ staged,
@@ -2044,7 +2089,7 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
 // Modes: heavyPool != NULL : the lane of stitch_kernel that owned the read exported its windows + seeds (DFS-heavy read);
 //        heavyPool == NULL : the read was routed here right after seeding because it has many loci (nA): the warp also does the
 //                            window creation / seed assignment cooperatively (coalesced SA loads, 32-wide scans).
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                      ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nHeavy, const u32* __restrict__ heavyList,
                                                      const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
                                                      u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,

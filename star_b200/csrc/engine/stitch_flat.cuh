@@ -54,7 +54,7 @@ struct FlatArgs {
 
 __device__ __forceinline__ u32 flatReadStride(u32 Lread) { return (Lread + 16) & ~15u; }
 
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(DevIndex ix, star_params_t P, const u8* __restrict__ reads, u32 stride,
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                    ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nHeavy, const u32* __restrict__ heavyList,
                                                    const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
                                                    u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(DevI
 // least that many lanes of the warp are waiting (or none is working), which keeps neighbouring lanes on neighbouring tasks.
 #define FLAT_LANE_SCRATCH 4096
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(DevIndex ix, star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps,
+__global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps,
                                                              u8* __restrict__ laneScratch, u32 fetchMin) {
     const u32 lane = threadIdx.x & 31;
     u64 nT = fa.bumps[1];
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(DevIndex ix, star_p
 // Tasks are fetched 32 at a time (lane j prefetches the descriptor, read header and window of task base+j).
 #define FLAT_WARP_SMEM (2 * (u32)sizeof(DevTr) + STAR_UNDO_DEPTH * (u32)sizeof(Frame) + 64)
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(DevIndex ix, star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps) {
+__global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps) {
     extern __shared__ u8 smem[];
     const u32 lane = threadIdx.x & 31;
     const u32 warpInBlock = threadIdx.x >> 5;
@@ -420,74 +420,167 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(DevIndex ix, s
             ln.Lread = Lread; ln.readLength[0] = (u16)(rl & 0xffffu); ln.readLength[1] = (u16)(rl >> 16);
             ln.R0 = rp; ln.R2 = rp + rs;
             ln.R = Str == 0 ? ln.R0 : ln.R2;
-            ln.nodes = 0; ln.leaves = 0;
-            dfsInit<true>(ln);
-            ln.forceDepth = depth;
-            ln.forceBits = bits;
+            // ---- the include/exclude recursion of stitchWindowAligns.cpp:8-353 for this sub-tree, warp-uniform, DFS cursor in registers.
+            // Same visiting order and node accounting as dfsStep/dfsBacktrack (stitch.cu); the per-level phase array is replaced by two
+            // bit masks: incl (seeds on the path) and open (included seeds whose exclude branch is still unexplored, i.e. not forced).
+            DevTr* const tcur = ln.cur;
+            Frame* const stack = ln.stack;
+            __syncwarp();
+            if (lane < 20) ((u32*)&tcur->h)[lane] = 0;   // trA = *trInit (ReadAlign_stitchPieces.cpp:282-286): every field zero
+            __syncwarp();
+            u32 level = 0, nInc = 0;
+            int Score = 0;
+            u32 tR2 = 0;
+            u64 tG2 = 0, incl = 0, open = 0;
+            u32 nodes = 0, leaves = 0;
             u32 curBlock = FLAT_NONE, firstBlock = FLAT_NONE, nCand = 0, inBlock = 0;
             int taskBest = 0;
             Cand c0; c0.mask = 0; c0.trOff = FLAT_NONE; c0.score = 0; c0.iFrag = 0; c0.pad = 0;
             for (;;) {
-                __syncwarp();
-                const int r = dfsStep<true>(ln, WA, nA);
-                __syncwarp();
-                if (r == DFS_DONE) break;
-                if (r != DFS_LEAF) continue;
-                ln.leaves++;
-                const bool keep = evalLeaf<true>(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str);
-                __syncwarp();
-                if (!keep) continue;
-                const int sc = ln.leaf->h.maxScore;
-                Cand c; c.mask = ln.inclMask; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
-                if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
-                    if (sc > taskBest) taskBest = sc;
-                    const u32 nEx = ln.leaf->h.nExons;
-                    const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
-                    if (trCur + words > trEnd) {
-                        u64 off = 0;
-                        if (lane == 0) off = atomicAdd(&fa.bumps[3], (unsigned long long)(4 * FLAT_TR_CHUNK));
-                        off = __shfl_sync(0xffffffffu, off, 0);
-                        if (off + 4 * FLAT_TR_CHUNK <= fa.trWords && off + 4 * FLAT_TR_CHUNK < 0xFFFFFFFFULL) { trCur = off; trEnd = off + 4 * FLAT_TR_CHUNK; }
-                        else { trCur = 0; trEnd = 0; }
-                    }
-                    if (trCur + words <= trEnd) {
-                        u64* dst = fa.trStore + trCur;
-                        const u64* src = (const u64*)ln.leaf;   // head and exons are contiguous in DevTr
-                        for (u32 q = lane; q < words; q += 32) dst[q] = src[q];
-                        c.trOff = (u32)trCur;
-                        trCur += words;
-                    }
-                }
-                if (nCand == 0) {
-                    c0 = c;
-                    nCand = 1;
-                } else {
-                    bool ok = true;
-                    if (curBlock == FLAT_NONE || inBlock == FLAT_CAND_PER_BLOCK) {
-                        u64 nb = 0;
-                        if (lane == 0) nb = atomicAdd(&fa.bumps[2], 1ULL);
-                        nb = __shfl_sync(0xffffffffu, nb, 0);
-                        if (nb >= fa.maxBlocks) { if (lane == 0) fa.recs[k].over = 5; ok = false; }
-                        else {
-                            if (lane == 0) {
-                                fa.blocks[nb].next = FLAT_NONE; fa.blocks[nb].count = 0;
-                                if (curBlock != FLAT_NONE) fa.blocks[curBlock].next = (u32)nb;
+                const u32 L = level;
+                nodes++;
+                if (L >= nA) {
+                    if (tR2 != 0) {   // "iA>=nA && tR2==0: no aligns in the transcript" (:14)
+                        leaves++;
+                        const bool keep = evalLeaf<true>(ln, Score, tR2, tG2, Chr, Str, Str);
+                        __syncwarp();
+                        if (keep) {
+                            const int sc = ln.leaf->h.maxScore;
+                            Cand c; c.mask = incl; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
+                            if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
+                                if (sc > taskBest) taskBest = sc;
+                                const u32 nEx = ln.leaf->h.nExons;
+                                const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
+                                if (trCur + words > trEnd) {
+                                    u64 off = 0;
+                                    if (lane == 0) off = atomicAdd(&fa.bumps[3], (unsigned long long)(4 * FLAT_TR_CHUNK));
+                                    off = __shfl_sync(0xffffffffu, off, 0);
+                                    if (off + 4 * FLAT_TR_CHUNK <= fa.trWords && off + 4 * FLAT_TR_CHUNK < 0xFFFFFFFFULL) { trCur = off; trEnd = off + 4 * FLAT_TR_CHUNK; }
+                                    else { trCur = 0; trEnd = 0; }
+                                }
+                                if (trCur + words <= trEnd) {
+                                    u64* dst = fa.trStore + trCur;
+                                    const u64* src = (const u64*)ln.leaf;   // head and exons are contiguous in DevTr
+                                    #pragma unroll 1
+                                    for (u32 q = lane; q < words; q += 32) dst[q] = src[q];
+                                    c.trOff = (u32)trCur;
+                                    trCur += words;
+                                }
                             }
-                            if (curBlock == FLAT_NONE) firstBlock = (u32)nb;
-                            curBlock = (u32)nb;
-                            inBlock = 0;
+                            if (nCand == 0) {
+                                c0 = c;
+                                nCand = 1;
+                            } else {
+                                bool ok = true;
+                                if (curBlock == FLAT_NONE || inBlock == FLAT_CAND_PER_BLOCK) {
+                                    u64 nb = 0;
+                                    if (lane == 0) nb = atomicAdd(&fa.bumps[2], 1ULL);
+                                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                                    if (nb >= fa.maxBlocks) { if (lane == 0) fa.recs[k].over = 5; ok = false; }
+                                    else {
+                                        if (lane == 0) {
+                                            fa.blocks[nb].next = FLAT_NONE; fa.blocks[nb].count = 0;
+                                            if (curBlock != FLAT_NONE) fa.blocks[curBlock].next = (u32)nb;
+                                        }
+                                        if (curBlock == FLAT_NONE) firstBlock = (u32)nb;
+                                        curBlock = (u32)nb;
+                                        inBlock = 0;
+                                    }
+                                }
+                                if (ok) {
+                                    if (lane == 0) { FlatBlock& B = fa.blocks[curBlock]; B.c[inBlock] = c; B.count = inBlock + 1; }
+                                    inBlock++;
+                                    nCand++;
+                                }
+                            }
                         }
                     }
-                    if (ok) {
-                        if (lane == 0) { FlatBlock& B = fa.blocks[curBlock]; B.c[inBlock] = c; B.count = inBlock + 1; }
-                        inBlock++;
-                        nCand++;
-                    }
+                    // unwind to the deepest included seed whose exclude branch is unexplored (undoing its include)
+                    if (open == 0) break;
+                    const u32 Bk = 63u - (u32)__clzll((long long)open);
+                    const Frame& u = stack[--nInc];
+                    if (u.h.nExons > 0) warpCopyWords(&tcur->ex[u.h.nExons - 1], &u.last, 6);
+                    warpCopyWords(&tcur->h, &u.h, 20);
+                    Score = u.Score; tR2 = u.tR2; tG2 = u.tG2;
+                    open &= ~(1ULL << Bk); incl &= ~(1ULL << Bk);
+                    level = Bk + 1;
+                    continue;
                 }
+                const bool forced = L < depth;
+                if (forced && ((bits >> (depth - 1 - L)) & 1u)) { level = L + 1; continue; }   // this level is fixed to "exclude"
+                const u32 nEx0 = tcur->h.nExons;
+                if (nEx0 > 0 && !forced) {
+                    // The most frequent outcomes of an include attempt change nothing: the transcript is full (:13) or seed B ends inside
+                    // the last included seed in read or genome space (:53-54, after the sjdb shortcut :18).  The test for seeds L, L+1, ..
+                    // does not depend on the outcome for the earlier ones, so 32 seeds are tested at once.
+                    const Exon& eA = tcur->ex[nEx0 - 1];
+                    const bool full = nEx0 >= STAR_MAX_N_EXONS;
+                    const u32 eFrag = eA.iFrag, eSj = eA.sjA;
+                    u32 j = L;
+                    for (;;) {
+                        const u32 idx = j + lane;
+                        bool real = false;
+                        if (idx < nA) {
+                            const Seed q = WA[idx];
+                            bool qf = full;
+                            if (!qf && eFrag == q.iFrag) {
+                                const bool sjdbDirect = q.sjA != SJA_NONE && eSj == q.sjA && (u64)q.rStart == (u64)tR2 + 1 && tG2 + 1 < q.gStart;
+                                qf = !sjdbDirect && ((u64)q.rStart + q.Length - 1 <= tR2 || q.gStart + q.Length - 1 <= tG2);
+                            }
+                            real = !qf;
+                        }
+                        const u32 realMask = __ballot_sync(0xffffffffu, real);
+                        const u32 span = nA - j < 32 ? nA - j : 32;
+                        j += realMask ? (u32)__ffs(realMask) - 1 : span;
+                        if (realMask || j >= nA) break;
+                    }
+                    if (j > L) { nodes += j - L - 1; level = j; continue; }
+                }
+                const Seed s = WA[L];
+                if (nEx0 > 0 && forced) {   // a forced include that cannot succeed: the fixed prefix is not a valid path, the sub-tree is empty
+                    const Exon& eA = tcur->ex[nEx0 - 1];
+                    bool qf = nEx0 >= STAR_MAX_N_EXONS;
+                    if (!qf && eA.iFrag == s.iFrag) {
+                        const bool sjdbDirect = s.sjA != SJA_NONE && eA.sjA == s.sjA && (u64)s.rStart == (u64)tR2 + 1 && tG2 + 1 < s.gStart;
+                        qf = !sjdbDirect && ((u64)s.rStart + s.Length - 1 <= tR2 || s.gStart + s.Length - 1 <= tG2);
+                    }
+                    if (qf) break;
+                }
+                Frame& u = stack[nInc];
+                warpCopyWords(&u.h, &tcur->h, 20);
+                if (nEx0 > 0) warpCopyWords(&u.last, &tcur->ex[nEx0 - 1], 6);
+                u.Score = Score; u.tR2 = tR2; u.tG2 = tG2;
+                int dScore;
+                if (nEx0 > 0) {
+                    dScore = stitchAlignToTranscript<true>(ln, tR2, tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, tcur);
+                } else {
+                    tcur->ex[0].R = s.rStart; tcur->h.rStart = s.rStart;
+                    tcur->ex[0].G = s.gStart; tcur->h.gStart = s.gStart;
+                    tcur->ex[0].L = s.Length; tcur->ex[0].iFrag = s.iFrag; tcur->ex[0].sjA = s.sjA;
+                    tcur->ex[0].canon = 0; tcur->ex[0].annot = 0; tcur->ex[0].sjStr = 0; tcur->ex[0].shL = 0; tcur->ex[0].shR = 0;
+                    tcur->h.nExons = 1;
+                    dScore = s.Length;
+                    tcur->h.nMatch = s.Length;
+                }
+                __syncwarp();
+                if (dScore > -1000000) {
+                    if (s.Nrep == 1) tcur->h.nUnique++;
+                    if (s.Anchor > 0) tcur->h.nAnchor++;
+                    __syncwarp();
+                    incl |= 1ULL << L;
+                    if (!forced) open |= 1ULL << L;   // a forced include never explores its exclude branch
+                    nInc++;
+                    Score += dScore; tR2 = (u32)s.rStart + s.Length - 1; tG2 = s.gStart + s.Length - 1;
+                } else {
+                    if (forced) break;
+                    if (u.h.nExons > 0) warpCopyWords(&tcur->ex[u.h.nExons - 1], &u.last, 6);   // the failed attempt may have touched the last exon / head
+                    warpCopyWords(&tcur->h, &u.h, 20);
+                }
+                level = L + 1;
             }
             if (lane == 0) {
                 FlatOut o;
-                o.c0 = c0; o.count = nCand; o.first = firstBlock; o.nodes = (u32)ln.nodes; o.leaves = (u32)ln.leaves;
+                o.c0 = c0; o.count = nCand; o.first = firstBlock; o.nodes = nodes; o.leaves = leaves;
                 fa.outs[t] = o;
             }
         }
@@ -510,7 +603,7 @@ void launch_flat_dfs(int mode, int ctasPerSM, int nSM, cudaStream_t stream, cons
     else flat_dfs_kernel<4><<<nSM * 4, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
 }
 
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(DevIndex ix, star_params_t P, ReadInfo* __restrict__ info, u32 nRecs, u32* __restrict__ counter,
+__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, ReadInfo* __restrict__ info, u32 nRecs, u32* __restrict__ counter,
                                                     u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
                                                     star_align_t* __restrict__ staged, FlatArgs fa) {
     const u32 gthread = blockIdx.x * blockDim.x + threadIdx.x;
