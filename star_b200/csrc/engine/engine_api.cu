@@ -338,7 +338,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     CK(cudaMalloc(&c->d_sortTmp, c->sortTmpBytes + 64));
     c->owned.push_back(c->d_sortTmp);
     c->heavyEst = envU32("STAR_B200_HEAVY_EST", 1024);
-    c->heavyNA = envU32("STAR_B200_HEAVY_NA", 64);
+    c->heavyNA = envU32("STAR_B200_HEAVY_NA", 4);
     if (!c->heavyEst) c->heavyNA = 0;
     c->heavyMaxTasks = envU32("STAR_B200_HEAVY_TASKS", 8192);
     c->heavyMaxBlocks = envU32("STAR_B200_HEAVY_BLOCKS", 4096);
@@ -385,7 +385,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         if (getenv("STAR_B200_FLAT_MAXBLOCKS")) fa.maxBlocks = (u32)strtoull(getenv("STAR_B200_FLAT_MAXBLOCKS"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_TRWORDS")) fa.trWords = strtoull(getenv("STAR_B200_FLAT_TRWORDS"), nullptr, 10);
         fa.maxTasksPerRead = c->heavyMaxTasks;
-        fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 6);
+        fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
         void* p = nullptr;
         CK(cudaMalloc(&p, (size_t)N * 48)); fa.recs = p; c->owned.push_back(p);
         CK(cudaMalloc(&p, fa.poolBytes)); fa.pool = (u8*)p; c->owned.push_back(p);

@@ -105,6 +105,7 @@ __device__ __forceinline__ u8 Gat(const Lane& ln, u64 pos) { return __ldg(ln.ix-
 __device__ int binarySearch2(u64 x, u64 y, const u64* __restrict__ X, const u64* __restrict__ Y, int N) {
     if (N == 0 || x > X[N - 1] || x < X[0]) return -1;
     int i1 = 0, i2 = N - 1, i3 = N / 2;
+    #pragma unroll 1
     while (i2 > i1 + 1) {
         i3 = (i1 + i2) / 2;
         if (X[i3] > x) i2 = i3; else i1 = i3;
@@ -112,10 +113,12 @@ __device__ int binarySearch2(u64 x, u64 y, const u64* __restrict__ X, const u64*
     if (x == X[i1]) i3 = i1;
     else if (x == X[i2]) i3 = i2;
     else return -1;
+    #pragma unroll 1
     for (int jj = i3; jj >= 0; jj--) {
         if (x != X[jj]) break;
         else if (y == Y[jj]) return jj;
     }
+    #pragma unroll 1
     for (int jj = i3; jj < N; jj++) {
         if (x != X[jj]) return -1;
         else if (y == Y[jj]) return jj;
@@ -140,6 +143,7 @@ __device__ __forceinline__ bool coopExtendAlign(const u8* R, const u8* G, const 
     const double nMMmaxD = double(nMMmax);
     if (nMMmaxD < capEnd) capEnd = nMMmaxD;
     int Score = 0, nMatch = 0, nMM = 0;   // state after the bases of the previous chunks
+    #pragma unroll 1
     for (u64 base = 0; base < L; base += 32) {
         const u64 i = base + lane;
         bool stop = i >= L;
@@ -203,8 +207,9 @@ __device__ __forceinline__ bool extendAlign(const Lane& ln, u64 rStart, u64 gSta
     res = o.r;
     return o.ok;
 }
-__device__ __forceinline__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
-                                                bool extendToEnd, ExtRes& res);
+template <bool COOP>
+__device__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                bool extendToEnd, ExtRes& res);
 template <bool COOP>
 __device__ __noinline__ ExtOut extendAlignShared(const u8* Rbase, const u8* Gbase, u64 nG, u64 Lread, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev,
                                                  u64 nMMmax, double pMMmax, bool extendToEnd) {
@@ -213,17 +218,20 @@ __device__ __noinline__ ExtOut extendAlignShared(const u8* Rbase, const u8* Gbas
     if constexpr (COOP) {
         if (!extendToEnd) { o.ok = coopExtendAlign(Rbase, Gbase, nG, Lread, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, o.r); return o; }
     }
-    o.ok = extendAlignBody(Rbase, Gbase, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd, o.r);
+    o.ok = extendAlignBody<COOP>(Rbase, Gbase, rStart, gStart, dR, dG, L, Lprev, nMMprev, nMMmax, pMMmax, extendToEnd, o.r);
     return o;
 }
-__device__ __forceinline__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
-                                                bool extendToEnd, ExtRes& res) {
+// (COOP: only reached for extendToEnd, a cold path there: kept out of line)
+template <bool COOP>
+__device__ bool extendAlignBody(const u8* Rbase, const u8* Gbase, u64 rStart, u64 gStart, int dR, int dG, u64 L, u64 Lprev, u64 nMMprev, u64 nMMmax, double pMMmax,
+                                bool extendToEnd, ExtRes& res) {
     int Score = 0, nMatch = 0, nMM = 0;
     res.maxScore = 0;
     const u8* R = Rbase + rStart;
     const u8* G = Gbase + (i64)gStart;
     if (extendToEnd) {
         int iExt;
+        #pragma unroll 1
         for (iExt = 0; iExt < (int)L; iExt++) {
             int iS = dR * iExt, iG = dG * iExt;
             u8 g;
@@ -245,6 +253,7 @@ __device__ __forceinline__ bool extendAlignBody(const u8* Rbase, const u8* Gbase
     double capEnd = pMMmax * double(Lprev + L);
     double nMMmaxD = double(nMMmax);
     if (nMMmaxD < capEnd) capEnd = nMMmaxD;
+    #pragma unroll 1
     for (int i = 0; i < (int)L; i++) {
         int iS = dR * i, iG = dG * i;
         if ((gStart + (u64)(i64)iG) == (u64)(-1LL)) break;
@@ -284,7 +293,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
     Exon& eB = t->ex[h.nExons];
     const u64 outFilterMismatchNmaxTotal = ln.outFilterMismatchNmaxTotal;
 
-    if (sjAB != SJA_NONE && eA.sjA == sjAB && eA.iFrag == iFragB && rBstart == rAend + 1 && gAend + 1 < gBstart) {
+    if (__builtin_expect(sjAB != SJA_NONE && eA.sjA == sjAB && eA.iFrag == iFragB && rBstart == rAend + 1 && gAend + 1 < gBstart, 0)) {
         if (g.sjdbMotif[sjAB] == 0 && (L <= g.sjdbShiftRight[sjAB] || eA.L <= g.sjdbShiftLeft[sjAB])) return -1000006;
         eB.L = (u16)L; eB.R = (u16)rBstart; eB.G = gBstart;
         eA.canon = (signed char)g.sjdbMotif[sjAB];
@@ -320,6 +329,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
             } else if (gGap > 0 && rGap > 0 && rGap == gGap) {
                 if constexpr (COOP) {   // matches / mismatches of the gap: two popcounts per 32 bases
                     const u32 lane = threadIdx.x & 31;
+                    #pragma unroll 1
                     for (int base = 1; base <= rGap; base += 32) {
                         const int ii = base + (int)lane;
                         bool m = false, x = false;
@@ -331,6 +341,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                         Score += nm - nx; nMatch += (u64)nm; nMM += (u64)nx;
                     }
                 } else {
+                #pragma unroll 1
                 for (int ii = 1; ii <= rGap; ii++) {
                     u8 gv = Gat(ln, gAend + ii), rv = R[rAend + ii];
                     if (gv < 4 && rv < 4) {
@@ -354,6 +365,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                         const int jMin = 1 - (int)eA.L;
                         const int need = P.scoreStitchSJshift + 1;
                         int cnt = 0;
+                        #pragma unroll 1
                         for (int base = 0;; base -= 32) {
                             const int pz = base - (int)lane;
                             bool pen = false;
@@ -366,6 +378,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                             int hit = -1;
                             if (need <= 0) hit = 0;
                             else if (cnt + __popc(pm) >= need) {
+                                #pragma unroll 1
                                 for (int q = 1; q < need - cnt; q++) pm &= pm - 1;
                                 hit = __ffs(pm) - 1;
                             }
@@ -381,6 +394,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                         const bool withMotif = Del >= P.alignIntronMin;
                         int maxScore2 = -999999;
                         int Score1 = 0;
+                        #pragma unroll 1
                         for (int base = jR1; base < jEnd; base += 32) {
                             const int pz = base + (int)lane;
                             const bool v = pz < jEnd;
@@ -418,6 +432,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                     }
                     // (3) repeat lengths around the junction: first position where the flanks differ (or an N, or 256)
                     const u64 jRu = (u64)(i64)jR;
+                    #pragma unroll 1
                     for (;;) {
                         const u64 q = jjL + lane;
                         bool ok = gAend + jRu >= q && q <= 255;
@@ -426,6 +441,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                         if (fail) { jjL += (u32)__ffs(fail) - 1; break; }
                         jjL += 32;
                     }
+                    #pragma unroll 1
                     for (;;) {
                         const u64 q = jjR + lane;
                         bool ok = gAend + q + jRu + 1 < g.nGenome && gBstart1 + q + jRu + 1 < g.nGenome && q <= 255;   // (beyond the genome the padding (5) ends the loop)
@@ -437,6 +453,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                 } else {
                 int Score1 = 0;
                 int jR1 = 1;
+                #pragma unroll 1
                 do {
                     jR1--;
                     u8 rv = R[(i64)rAend + jR1], gb = Gat(ln, gBstart1 + (u64)(i64)jR1), ga = Gat(ln, gAend + (u64)(i64)jR1);
@@ -445,6 +462,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
 
                 int maxScore2 = -999999;
                 Score1 = 0;
+                #pragma unroll 1
                 do {
                     u8 rv = R[(i64)rAend + jR1], ga = Gat(ln, gAend + (u64)(i64)jR1), gb = Gat(ln, gBstart1 + (u64)(i64)jR1);
                     if (rv == ga && rv != gb) Score1 += 1;
@@ -467,7 +485,9 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                 } while (jR1 < int(rBend) - int(rAend));
 
                 u64 jRu = (u64)(i64)jR;
+                #pragma unroll 1
                 while (gAend + jRu >= jjL && Gat(ln, gAend - jjL + jRu) == Gat(ln, gBstart1 - jjL + jRu) && Gat(ln, gAend - jjL + jRu) < 4 && jjL <= 255) jjL++;
+                #pragma unroll 1
                 while (gAend + jjR + jRu + 1 < g.nGenome && Gat(ln, gAend + jjR + jRu + 1) == Gat(ln, gBstart1 + jjR + jRu + 1) && Gat(ln, gAend + jjR + jRu + 1) < 4 && jjR <= 255) jjR++;
 
                 }
@@ -482,6 +502,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                     int i1 = rGap > jR ? rGap : jR;
                     if constexpr (COOP) {
                         const u32 lane = threadIdx.x & 31;
+                        #pragma unroll 1
                         for (int base = i0; base <= i1; base += 32) {
                             const int ii = base + (int)lane;
                             bool a = false, b = false, c = false;
@@ -497,6 +518,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                             Score += na - nb - nc; nMatch += (u64)(i64)(na - nc); nMM += (u64)nb;
                         }
                     } else {
+                    #pragma unroll 1
                     for (int ii = i0; ii <= i1; ii++) {
                         u64 g1 = (ii <= jR) ? (gAend + (u64)(i64)ii) : (gBstart1 + (u64)(i64)ii);
                         u8 gv = Gat(ln, g1), rv = R[(i64)rAend + ii];
@@ -544,7 +566,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                 if (eA.annot == 0) {
                     if (jCan > 0) eA.sjStr = (u8)(2 - jCan % 2); else eA.sjStr = 0;
                 }
-            } else if (rGap > gGap) {
+            } else if (__builtin_expect(rGap > gGap, 0)) {
                 Ins = (u64)(rGap - gGap);
                 nIns = 1;
                 if (gGap == 0) {
@@ -554,6 +576,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                     Score -= (-gGap);
                 } else {
                     int Score1 = 0, maxScore1 = 0;
+                    #pragma unroll 1
                     for (int jR1 = 1; jR1 <= gGap; jR1++) {
                         u8 gv = Gat(ln, gAend + jR1);
                         if (gv < 4) {
@@ -562,6 +585,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                         }
                         if (Score1 > maxScore1 || (Score1 == maxScore1 && P.alignInsertionFlushRight)) { maxScore1 = Score1; jR = jR1; }
                     }
+                    #pragma unroll 1
                     for (int ii = 1; ii <= gGap; ii++) {
                         u64 r1 = rAend + ii + (ii <= jR ? 0 : Ins);
                         u8 gv = Gat(ln, gAend + ii), rv = R[r1];
@@ -571,6 +595,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
                     }
                 }
                 if (P.alignInsertionFlushRight) {
+                    #pragma unroll 1
                     for (; jR < (int)rBend - (int)rAend - (int)Ins; jR++) {
                         u8 gv = Gat(ln, gAend + jR + 1);
                         if (R[rAend + jR + 1] != gv || gv == 4) break;
@@ -649,6 +674,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
 __device__ u64 blocksOverlap(const DevTr& t1, const DevTr& t2) {
     u32 i1 = 0, i2 = 0;
     u64 nOverlap = 0;
+    #pragma unroll 1
     while (i1 < t1.h.nExons && i2 < t2.h.nExons) {
         u64 rs1 = t1.ex[i1].R, rs2 = t2.ex[i2].R;
         u64 re1 = rs1 + t1.ex[i1].L, re2 = rs2 + t2.ex[i2].L;
@@ -673,6 +699,7 @@ __device__ u64 blocksOverlap(const DevTr& t1, const DevTr& t2) {
 __device__ __forceinline__ void warpCopyWords(void* dst, const void* src, u32 nWords) {
     const u32 lane = threadIdx.x & 31;
     __syncwarp();
+    #pragma unroll 1
     for (u32 q = lane; q < nWords; q += 32) ((u32*)dst)[q] = ((const u32*)src)[q];
     __syncwarp();
 }
@@ -680,12 +707,14 @@ static_assert(sizeof(TrHead) == 80 && sizeof(Exon) == 24, "warpCopyWords call si
 
 __device__ __forceinline__ void copyTr(DevTr* dst, const DevTr* src) {
     dst->h = src->h;
+    #pragma unroll 1
     for (u32 i = 0; i < src->h.nExons; i++) dst->ex[i] = src->ex[i];
 }
 
 __device__ int log2Score(const DevIndex& ix, u64 gLen) {
     // value of int(ceil(log2((double)gLen)*scale-0.5)) from the host-computed step table (stitchWindowAligns.cpp:221-225)
     int v = ix.log2Val[0];
+    #pragma unroll 1
     for (int k = 1; k < ix.log2N; k++) {
         if (gLen >= ix.log2Thr[k]) v = ix.log2Val[k]; else break;
     }
@@ -706,6 +735,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     const u64 Lread = ln.Lread;
     int vOrder[2];
     if (roStr == 0) { vOrder[0] = 0; vOrder[1] = 1; } else { vOrder[0] = 1; vOrder[1] = 0; }
+    #pragma unroll 1
     for (int iOrd = 0; iOrd < 2; iOrd++) {
         ExtRes er;
         er.extendL = 0; er.maxScore = 0; er.nMatch = 0; er.nMM = 0;
@@ -738,8 +768,10 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     if (!P.alignSoftClipAtReferenceEnds &&
         ((t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R) > (g.chrStart[Chr] + g.chrLength[Chr]) || t.ex[0].G < (g.chrStart[Chr] + t.ex[0].R))) return false;
     h.rLength = 0;
+    #pragma unroll 1
     for (u32 i = 0; i < nEx; i++) h.rLength += t.ex[i].L;
     h.gLength = tG2 + 1 - h.gStart;
+    #pragma unroll 1
     for (u32 isj = 0; isj + 1 < nEx; isj++) {
         if (t.ex[isj].canon >= 0) {
             if (t.ex[isj].annot == 1) {
@@ -753,6 +785,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     }
     if (nEx > 1 && t.ex[nEx - 2].annot == 1 && t.ex[nEx - 1].L < P.alignSJDBoverhangMin) return false;
     u32 sjN = 0, im[3] = {0, 0, 0};
+    #pragma unroll 1
     for (u32 iex = 0; iex + 1 < nEx; iex++) {
         if (t.ex[iex].canon >= 0) { sjN++; im[t.ex[iex].sjStr]++; }
     }
@@ -762,12 +795,15 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     if (im[1] > 0 && im[2] > 0 && P.outFilterIntronStrandsRemoveInconsistent) return false;
     if (sjN > 0 && h.sjMotifStrand == 0 && P.outSAMstrandFieldType == 1) return false;
     if (P.outFilterIntronMotifs == 1) {
+        #pragma unroll 1
         for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0) return false;
     } else if (P.outFilterIntronMotifs == 2) {
+        #pragma unroll 1
         for (u32 iex = 0; iex + 1 < nEx; iex++) if (t.ex[iex].canon == 0 && t.ex[iex].annot == 0) return false;
     }
     {
         u64 nsj = 0, exl = 0;
+        #pragma unroll 1
         for (u32 iex = 0; iex < nEx; iex++) {
             exl += t.ex[iex].L;
             if (iex == nEx - 1 || t.ex[iex].canon == -3) {
@@ -781,6 +817,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     if (t.ex[0].iFrag != t.ex[nEx - 1].iFrag) {
         if (t.ex[nEx - 1].G + t.ex[nEx - 1].L <= t.ex[0].G) return false;
         u32 iexM2 = nEx;
+        #pragma unroll 1
         for (u32 iex = 0; iex + 1 < nEx; iex++) {
             if (t.ex[iex].canon == -3) { iexM2 = iex + 1; break; }
         }
@@ -788,9 +825,11 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
             if (t.ex[0].G > t.ex[iexM2].G + t.ex[0].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return false;
             if (t.ex[iexM2 - 1].G + t.ex[iexM2 - 1].L > t.ex[nEx - 1].G + Lread - t.ex[nEx - 1].R + (u64)(i64)P.alignEndsProtrudeNbasesMax) return false;
             u32 iex1 = 1, iex2 = iexM2 + 1;
+            #pragma unroll 1
             for (; iex1 < iexM2; iex1++) {
                 if (t.ex[iex1].G >= t.ex[iex2 - 1].G + t.ex[iex2 - 1].L) break;
             }
+            #pragma unroll 1
             while (iex1 < iexM2 && iex2 < nEx) {
                 if (t.ex[iex1 - 1].canon < 0) { iex1++; continue; }
                 if (t.ex[iex2 - 1].canon < 0) { iex2++; continue; }
@@ -823,8 +862,10 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
     if (Score + P.outFilterMultimapScoreRange >= wBest || (h.iFrag >= 0 && Score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[h.iFrag])) {
         u32 iTr = 0;
         h.mappedLength = 0;
+        #pragma unroll 1
         for (u32 iex = 0; iex < nEx; iex++) h.mappedLength += t.ex[iex].L;
         u32 n = *nWinTr;
+        #pragma unroll 1
         while (iTr < n) {
             const DevTr& o = ln.pool[wTr[iTr]];
             u64 nOverlap = blocksOverlap(t, o);
@@ -834,6 +875,7 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
                 break;
             } else if (uOld == 0) {
                 u16 p = wTr[iTr];
+                #pragma unroll 1
                 for (u32 ii = iTr + 1; ii < n; ii++) wTr[ii - 1] = wTr[ii];
                 n--;
                 wTr[n] = p;
@@ -842,11 +884,13 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
             }
         }
         if (iTr == n) {
+            #pragma unroll 1
             for (iTr = 0; iTr < n; iTr++) {
                 const DevTr& o = ln.pool[wTr[iTr]];
                 if (Score > o.h.maxScore || (Score == o.h.maxScore && h.gLength < o.h.gLength)) break;
             }
             u16 p = wTr[n];
+            #pragma unroll 1
             for (int ii = (int)n; ii > (int)iTr; ii--) wTr[ii] = wTr[ii - 1];
             wTr[iTr] = p;
             copyTr(&ln.pool[p], &t);
@@ -1000,6 +1044,7 @@ template <bool COOP = false>
 __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
     DevTr* t = ln.cur;
     int runAhead = 0;
+    #pragma unroll 1
     for (;;) {
         if (ln.level < 0) return DFS_DONE;
         const u32 L = (u32)ln.level;
@@ -1036,6 +1081,7 @@ __device__ int dfsStep(Lane& ln, const Seed* __restrict__ WA, u32 nA) {
                 const bool full = t->h.nExons >= STAR_MAX_N_EXONS;
                 const u32 eFrag = eA.iFrag, eSj = eA.sjA;
                 u32 j = L;
+                #pragma unroll 1
                 for (;;) {
                     const u32 idx = j + lane;
                     bool real = false;
@@ -1164,6 +1210,7 @@ __device__ int createExtendWindowsWithAlign(Lane& ln, u64 a1, u32 aStr) {
     u64 lo = aBin > P.winAnchorDistNbins ? aBin - P.winAnchorDistNbins : 0;
     u64 hiX = aBin + P.winAnchorDistNbins + 1 < P.winBinN ? aBin + P.winAnchorDistNbins + 1 : P.winBinN;   // exclusive
     u64 bestL = 0, bestR = 0;
+    #pragma unroll 1
     for (u32 w = 0; w < nW; w++) {
         if (W[w].Str != aStr || W[w].gStart > W[w].gEnd) continue;
         u64 s = W[w].gStart, e = W[w].gEnd;
@@ -1205,6 +1252,7 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
     const star_params_t& P = *ln.P;
     u64 bin = a1 >> P.winBinNbits;
     int iW = -1;
+    #pragma unroll 1
     for (u32 w = 0; w < ln.nW; w++) {
         if (ln.win[w].Str == aStr && ln.win[w].gStart <= bin && bin <= ln.win[w].gEnd) { iW = (int)w; break; }
     }
@@ -1215,6 +1263,7 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
     u32 nWA = W.nWA;
     {
         u32 iA;
+        #pragma unroll 1
         for (iA = 0; iA < nWA; iA++) {
             const Seed& s = WA[iA];
             if (aFrag == s.iFrag && s.sjA == sjA && a1 + s.rStart == s.gStart + aRstart
@@ -1223,13 +1272,16 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
         if (iA < nWA) {
             if (aLength > WA[iA].Length) {
                 u32 iA0;
+                #pragma unroll 1
                 for (iA0 = 0; iA0 < nWA; iA0++) {
                     if (iA0 != iA && aRstart < WA[iA0].rStart) break;
                 }
                 if (iA0 > iA) --iA0;
                 if (iA0 < iA) {
+                    #pragma unroll 1
                     for (u32 iA1 = iA; iA1 > iA0; iA1--) WA[iA1] = WA[iA1 - 1];
                 } else if (iA0 > iA) {
+                    #pragma unroll 1
                     for (u32 iA1 = iA; iA1 < iA0; iA1++) WA[iA1] = WA[iA1 + 1];
                 }
                 setSeed(WA[iA0], a1, aLength, aNrep, aFrag, aRstart, aAnchor, sjA);
@@ -1239,11 +1291,13 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
     }
     if (nWA == P.seedPerWindowNmax) {
         u32 rec = ln.Lread + 1;
+        #pragma unroll 1
         for (u32 iA = 0; iA < nWA; iA++) if (WA[iA].Anchor != 1 && WA[iA].Length < rec) rec = WA[iA].Length;
         W.WALrec = (u16)rec;
         if (rec == ln.Lread + 1) return false;   // mapMarker=MARKER_TOO_MANY_ANCHORS_PER_WINDOW; nW=0
         if (!aAnchor && aLength < rec) return true;
         u32 iA1 = 0;
+        #pragma unroll 1
         for (u32 iA = 0; iA < nWA; iA++) {
             if (WA[iA].Anchor == 1 || WA[iA].Length > rec) { WA[iA1] = WA[iA]; iA1++; }
         }
@@ -1252,7 +1306,9 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
     }
     if (aAnchor || aLength > W.WALrec) {
         u32 iA;
+        #pragma unroll 1
         for (iA = 0; iA < nWA; iA++) if (aRstart < WA[iA].rStart) break;
+        #pragma unroll 1
         for (u32 iA1 = nWA; iA1 > iA; iA1--) WA[iA1] = WA[iA1 - 1];
         setSeed(WA[iA], a1, aLength, aNrep, aFrag, aRstart, aAnchor, sjA);
         W.nWA = (u16)(nWA + 1);
@@ -1262,6 +1318,7 @@ __device__ bool assignAlignToWindow(Lane& ln, u64 a1, u64 aLength, u32 aStr, u64
 
 __device__ void exportAlign(const DevTr& t, u32 Chr, u32 Str, u32 roStr, u32 Lread, const DevIndex& g, star_align_t* o) {
     const u32 n = t.h.nExons;
+    #pragma unroll 1
     for (u32 i = 0; i < STAR_MAX_N_EXONS; i++) {
         bool v = i < n;
         bool j = i + 1 < n;
@@ -1346,8 +1403,10 @@ __device__ void selectExport(Lane& ln, ReadInfo& ri, u32 i, u32 mapMarker, u32 b
         bestNMM = b.nMM; bestNMatch = b.nMatch; bestRLength = b.rLength;
     }
     u32 nTr = 0;
+    #pragma unroll 1
     for (u32 w = 0; w < nWfinal; w++) {
         const u16* wt = ln.trPtr + ln.winBase[w];
+        #pragma unroll 1
         for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
             if (ln.pool[wt[iTr]].h.maxScore + P.outFilterMultimapScoreRange >= bestScore) nTr++;
         }
@@ -1369,8 +1428,10 @@ __device__ void selectExport(Lane& ln, ReadInfo& ri, u32 i, u32 mapMarker, u32 b
         star_align_t* o = staged + (u64)i * ln.caps.nOut;
         u32 kOut = 0;
         u32 bestK = 0;
+        #pragma unroll 1
         for (u32 w = 0; w < nWfinal; w++) {
             const u16* wt = ln.trPtr + ln.winBase[w];
+            #pragma unroll 1
             for (u32 iTr = 0; iTr < ln.winN[w]; iTr++) {
                 DevTr& t = ln.pool[wt[iTr]];
                 if (t.h.maxScore + P.outFilterMultimapScoreRange >= bestScore) {
@@ -1395,6 +1456,7 @@ __device__ void selectExport(Lane& ln, ReadInfo& ri, u32 i, u32 mapMarker, u32 b
                 }
             }
             if (P.outSAMprimaryFlagAllBestScore) {
+                #pragma unroll 1
                 for (u32 itr = 0; itr < nTr; itr++) if (o[itr].maxScore == bestScore) o[itr].primaryFlag = 1;
             } else if (P.outSAMmultNmax != (u64)-1) {
                 o[0].primaryFlag = 1;
@@ -1418,6 +1480,7 @@ struct HeavyWin { u32 Chr; u16 nWA; u8 Str; u8 pad; };
 
 __device__ bool exportHeavy(Lane& ln, u8* __restrict__ heavyPool, u64 heavyPoolBytes, unsigned long long* __restrict__ heavyBump, u64& offOut) {
     u32 nWin = 0, nSeeds = 0;
+    #pragma unroll 1
     for (u32 w = 0; w < ln.nW; w++) if (ln.win[w].nWA > 0) { nWin++; nSeeds += ln.win[w].nWA; }
     u64 bytes = 8 + (u64)nWin * sizeof(HeavyWin) + (u64)nSeeds * sizeof(Seed);
     bytes = (bytes + 15) & ~15ULL;
@@ -1428,12 +1491,14 @@ __device__ bool exportHeavy(Lane& ln, u8* __restrict__ heavyPool, u64 heavyPoolB
     HeavyWin* hw = (HeavyWin*)(p + 8);
     Seed* sd = (Seed*)(p + 8 + (u64)nWin * sizeof(HeavyWin));
     u32 k = 0, q = 0;
+    #pragma unroll 1
     for (u32 w = 0; w < ln.nW; w++) {
         const Window& W = ln.win[w];
         if (W.nWA == 0) continue;
         HeavyWin h; h.Chr = W.Chr; h.nWA = W.nWA; h.Str = W.Str; h.pad = 0;
         hw[k++] = h;
         const Seed* src = ln.wa + (u64)w * ln.caps.spw;
+        #pragma unroll 1
         for (u32 a = 0; a < W.nWA; a++) sd[q++] = src[a];
     }
     offOut = off;
@@ -1537,6 +1602,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
         }
         {   // the whole warp copies the reads of the lanes that just fetched one (coalesced) into their shared-memory rows
             u32 m = __ballot_sync(0xffffffffu, needCopy);
+            #pragma unroll 1
             while (m) {
                 int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -1545,6 +1611,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
                 const u8* g = reads + (u64)ri_i * stride;
                 u8* d0 = smem + (size_t)(warpBase + src) * 2 * smemStride;
                 u8* d2 = d0 + smemStride;
+                #pragma unroll 1
                 for (u32 b = lane; b < L; b += 32) {
                     u8 c = g[b];
                     d0[b] = c;
@@ -1557,6 +1624,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
         // ------------------------------------------------------------------ window creation, one SA locus per step (:41-93)
         if (phase == PH_WIN) {
             if (iSA >= iSAend) {
+                #pragma unroll 1
                 while (iP < nP) {
                     p = PC[iP];
                     iP++;
@@ -1599,13 +1667,16 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
         PHASE_TICK(1);
         // ------------------------------------------------------------------ flanks (:96-118)
         if (phase == PH_FLANK) {
+            #pragma unroll 1
             for (u32 iWin = 0; iWin < ln.nW; iWin++) {
                 Window& W = ln.win[iWin];
                 if (W.gStart <= W.gEnd) {
                     u64 wb = W.gStart;
+                    #pragma unroll 1
                     for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
                     W.gStart = (u32)wb;
                     wb = W.gEnd;
+                    #pragma unroll 1
                     for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
                     W.gEnd = (u32)wb;
                 }
@@ -1625,6 +1696,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
                     bool heavy = false;
                     if (hv.estLimit) {
                         u64 est = 0;
+                        #pragma unroll 1
                         for (u32 w = 0; w < ln.nW; w++) { u32 a = ln.win[w].nWA; if (a) est += 1ULL << (a < 20 ? a : 20); }
                         heavy = est > hv.estLimit;
                     }
@@ -1642,6 +1714,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
                             phase = PH_SELECT;
                         }
                     } else {
+                        #pragma unroll 1
                         for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
                         iW = 0;
                         phase = PH_NEXTWIN;
@@ -1685,6 +1758,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
         PHASE_TICK(3);
         // ------------------------------------------------------------------ next window with seeds (:268-299)
         if (phase == PH_NEXTWIN) {
+            #pragma unroll 1
             while (iW < ln.nW && ln.win[iW].nWA == 0) iW++;
             int rc = iW < ln.nW ? windowBegin(ln, wTr, nWinTr) : 1;
             if (rc == 2) { ln.overflow = 3; phase = PH_SELECT; }   // reason 3: transcript pool
@@ -1729,6 +1803,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
         PHASE_TICK(7);
         if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
     }
+    #pragma unroll 1
     for (int q = 0; q < 8; q++) PROF_ADD(q, pc[q]);
 }
 
@@ -1759,6 +1834,7 @@ __device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 ma
     DevTr* t = ln.cur;
     dfsInit(ln);
     Score = 0; tR2 = 0; tG2 = 0;
+    #pragma unroll 1
     for (u32 iA = 0; iA < nA; iA++) {
         if (!((mask >> iA) & 1ULL)) continue;
         const Seed s = WA[iA];
@@ -1798,10 +1874,12 @@ struct WarpWin {
 };
 
 __device__ __forceinline__ u64 warpMaxU64(u64 v) {
+    #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
     return v;
 }
 __device__ __forceinline__ u64 warpMinU64(u64 v) {
+    #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) { u64 x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
     return v;
 }
@@ -1815,6 +1893,7 @@ __device__ int coopCreateWindow(const Lane& ln, WarpWin& ww, u64 a1, u32 aStr) {
     bool owned = false;
     u64 candL = 0;                      // (gEnd+1)<<16 | w   (0 = none); max wins
     u64 candR = ~0ULL;                  // gStart<<16 | w     (~0 = none); min wins
+    #pragma unroll 1
     for (u32 w = ww.lane; w < ww.nW; w += 32) {
         const Window W = ww.swin[w];
         if (W.Str != aStr || W.gStart > W.gEnd) continue;
@@ -1961,12 +2040,14 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
         const Seed* seeds = (const Seed*)(rec + 8 + (u64)nWin * sizeof(HeavyWin));
         if (nWin > caps.maxW) { overReason = 5; nWin = 0; }
         u32 sd = 0;
+        #pragma unroll 1
         for (u32 w = 0; w < nWin; w++) {   // uniform loop; lanes copy the seeds of window w
             const HeavyWin h = hw[w];
             if (lane == 0) {
                 Window nw; nw.gStart = 0; nw.gEnd = 0; nw.Chr = h.Chr; nw.nWA = h.nWA; nw.WALrec = 0; nw.Str = h.Str; nw.pad[0] = nw.pad[1] = nw.pad[2] = 0;
                 swin[w] = nw;
             }
+            #pragma unroll 1
             for (u32 a = lane; a < h.nWA; a += 32) ln.wa[(u64)w * caps.spw + a] = seeds[sd + a];
             sd += h.nWA;
         }
@@ -1976,11 +2057,13 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
         const Piece* PC = pieces + (u64)i * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier
         const u32 nP = ri.nP;
         ww.nW = 0;
+        #pragma unroll 1
         for (u32 iP = 0; iP < nP && !overReason; iP++) {
             const Piece p = PC[iP];
             if (p.Nrep > P.winAnchorMultimapNmax) continue;
             const u64 aLength = p.Length;
             bool stopPiece = false;
+            #pragma unroll 1
             for (u64 base = 0; base < p.Nrep && !stopPiece && !overReason; base += 32) {
                 const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
                 u64 a1 = 0, a1A = 0; u32 aStr = 0; u32 kind = 0;   // kind: 0 skip, 1 genomic, 2 sjdb (donor a1, acceptor a1A)
@@ -1997,6 +2080,7 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                         if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, sj1)) { a1 = a1D; kind = 2; } else kind = 0;
                     }
                 }
+                #pragma unroll 1
                 for (u32 q = 0; q < nl; q++) {
                     saEnum++;
                     const u32 kq = __shfl_sync(0xffffffffu, kind, q);
@@ -2016,9 +2100,11 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
             Window W = swin[w];
             if (W.gStart <= W.gEnd) {
                 u64 wb = W.gStart;
+                #pragma unroll 1
                 for (u64 ii = 0; ii < P.winFlankNbins && wb > 0 && chrOfBin(ln, wb - 1) == W.Chr; ii++) wb--;
                 W.gStart = (u32)wb;
                 wb = W.gEnd;
+                #pragma unroll 1
                 for (u64 ii = 0; ii < P.winFlankNbins && wb + 1 < P.winBinN && chrOfBin(ln, wb + 1) == W.Chr; ii++) wb++;
                 W.gEnd = (u32)wb;
             }
@@ -2027,11 +2113,13 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
         }
         __syncwarp();
         // assignment :129-185
+        #pragma unroll 1
         for (u32 iP = 0; iP < nP && !overReason && !tooManyAnchors; iP++) {
             const Piece p = PC[iP];
             const u64 aNrep = p.Nrep, aLength = p.Length;
             const u32 aFrag = p.iFrag;
             const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
+            #pragma unroll 1
             for (u64 base = 0; base < p.Nrep && !tooManyAnchors; base += 32) {
                 const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
                 u64 a1 = 0, a1A = 0, aRstart = 0, aLengthD = 0, aLengthA = 0; u32 aStr = 0, kind = 0, isj = SJA_NONE;
@@ -2051,6 +2139,7 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                     }
                     if (kind) {   // window lookup: windows do not change during the assignment phase
                         const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
+                        #pragma unroll 1
                         for (u32 w = 0; w < ww.nW; w++) {
                             const Window W = swin[w];
                             if (W.Str != aStr) continue;
@@ -2059,6 +2148,7 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                         }
                     }
                 }
+                #pragma unroll 1
                 for (u32 q = 0; q < nl; q++) {
                     saEnum++;
                     const u32 kq = __shfl_sync(0xffffffffu, kind, q);
@@ -2138,6 +2228,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
 
     long long hc[6] = {0, 0, 0, 0, 0, 0};
     long long eU[3] = {0, 0, 0};
+    #pragma unroll 1
     for (;;) {
         long long t0 = clock64();
         u32 k = 0;
@@ -2164,6 +2255,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         }
         {   // read into shared memory (both orientations)
             const u8* g = reads + (u64)i * stride;
+            #pragma unroll 1
             for (u32 b = lane; b < Lread; b += 32) {
                 u8 c = g[b];
                 R0[b] = c;
@@ -2173,6 +2265,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         if (lane == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
         epoch++;
         if (memoOn && (epoch & 0xFFFFFFULL) == 0) {   // 24-bit epoch wrapped: forget everything
+            #pragma unroll 1
             for (u32 q = lane; q < hs.memoSlots; q += 32) memoTab[q].key = 0;
             epoch++;
         }
@@ -2185,8 +2278,10 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         u32 nTasks = 0;
         if (lane == 0 && !overReason) {
             u32 shift = 0;
+            #pragma unroll 1
             for (;;) {
                 u32 tot = 0;
+                #pragma unroll 1
                 for (u32 w = 0; w < nWin; w++) {
                     u32 a = swin[w].nWA;
                     u32 d = a <= hs.splitMin ? 0 : (a - hs.splitMin > 8 ? 8 : a - hs.splitMin);
@@ -2209,6 +2304,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
             int taskBest = 0;
             const Seed* WA = ln.wa;
             u32 nA = 0;
+            #pragma unroll 1
             for (;;) {
                 {   // lane-utilisation accounting of the E phase
                     u32 mF = __ballot_sync(0xffffffffu, ph == 0), mN = __ballot_sync(0xffffffffu, ph == 1), mL = __ballot_sync(0xffffffffu, ph == 2);
@@ -2220,6 +2316,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
                     else {
                         // window of the task: last w with taskStart[w] <= tsk (skipping empty ranges is automatic: taskStart[w+1] > tsk)
                         u32 lo = 0, hi = nWin;
+                        #pragma unroll 1
                         while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (taskStart[mid] <= tsk) lo = mid; else hi = mid; }
                         w = lo;
                         const Window W = swin[w];
@@ -2266,8 +2363,10 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
                                 if (off + words <= hs.trWords) {
                                     u64* dst = trBuf + off;
                                     const u64* sh8 = (const u64*)&ln.leaf->h;
+                                    #pragma unroll 1
                                     for (u32 q = 0; q < sizeof(TrHead) / 8; q++) dst[q] = sh8[q];
                                     const u64* se = (const u64*)ln.leaf->ex;
+                                    #pragma unroll 1
                                     for (u32 q = 0; q < nEx * (sizeof(Exon) / 8); q++) dst[sizeof(TrHead) / 8 + q] = se[q];
                                     c.trOff = off;
                                 }
@@ -2285,6 +2384,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         __syncwarp();
         {   // work counters of the E phase (nodes, leaves) summed over the lanes
             u64 nd = ln.nodes, lv = ln.leaves;
+            #pragma unroll 1
             for (int o = 16; o > 0; o >>= 1) { nd += __shfl_down_sync(0xffffffffu, nd, o); lv += __shfl_down_sync(0xffffffffu, lv, o); }
             ln.nodes = nd; ln.leaves = lv;   // meaningful on lane 0
         }
@@ -2296,7 +2396,9 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
             if (overReason) {
                 ln.overflow = overReason;
             } else {
+                #pragma unroll 1
                 for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+                #pragma unroll 1
                 for (u32 w = 0; w < nWin && !ln.overflow; w++) {
                     const Window W = swin[w];
                     if (W.nWA == 0) continue;
@@ -2309,10 +2411,13 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
                     ln.R = Str == 0 ? R0 : R2;
                     ln.memoBase = ((epoch & 0xFFFFFFULL) << 40) | ((u64)w << 28);
                     ln.memo = (memoOn && nA >= 10) ? memoTab : nullptr;
+                    #pragma unroll 1
                     for (u32 t = taskStart[w]; t < taskStart[w + 1] && !ln.overflow; t++) {
                         u32 b = taskOut[t].first;
+                        #pragma unroll 1
                         while (b != 0xFFFFFFFFu && !ln.overflow) {
                             const CandBlock& B = blocks[b];
+                            #pragma unroll 1
                             for (u32 q = 0; q < B.count; q++) {
                                 const Cand c = B.c[q];
                                 if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
@@ -2323,9 +2428,11 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
                                     if (c.trOff != 0xFFFFFFFFu) {   // transcript stored by the lane that evaluated the leaf
                                         const u64* src = trBuf + c.trOff;
                                         u64* dh = (u64*)&ln.leaf->h;
+                                        #pragma unroll 1
                                         for (u32 z = 0; z < sizeof(TrHead) / 8; z++) dh[z] = src[z];
                                         const u32 nEx = ln.leaf->h.nExons;
                                         u64* de = (u64*)ln.leaf->ex;
+                                        #pragma unroll 1
                                         for (u32 z = 0; z < nEx * (sizeof(Exon) / 8); z++) de[z] = src[sizeof(TrHead) / 8 + z];
                                         recordLeaf(ln, wTr, &nWinTr);
                                     } else {
@@ -2349,10 +2456,13 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         hc[2] += clock64() - t2;
     }
     if (lane == 0) *epochPtr = epoch;
+    #pragma unroll 1
     for (int q = 0; q < 6; q++) PROF_ADD(16 + q, hc[q]);
+    #pragma unroll 1
     for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
     {
         u64 hsum = ln.memoHit, msum = ln.memoMiss;
+        #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) { hsum += __shfl_down_sync(0xffffffffu, hsum, o); msum += __shfl_down_sync(0xffffffffu, msum, o); }
         PROF_ADD(25, hsum); PROF_ADD(26, msum);
     }
@@ -2389,11 +2499,13 @@ __global__ void pack_kernel(const star_read_result_t* __restrict__ results, cons
     u32 lane = threadIdx.x & 31;
     u32 nWarps = (gridDim.x * blockDim.x) >> 5;
     const u32 words = sizeof(star_align_t) / 16;
+    #pragma unroll 1
     for (u32 i = warp; i < nReads; i += nWarps) {
         u32 n = results[i].nTrOut;
         if (n == 0) continue;
         const uint4* s = (const uint4*)(staged + (u64)i * nOut);
         uint4* d = (uint4*)(aligns + offsets[i]);
+        #pragma unroll 1
         for (u32 w = lane; w < n * words; w += 32) d[w] = s[w];
     }
 }
@@ -2405,16 +2517,19 @@ __global__ void scan_kernel(star_read_result_t* __restrict__ results, u64* __res
     u32 per = (nReads + blockDim.x - 1) / blockDim.x;
     u32 lo = t * per, hi = lo + per < nReads ? lo + per : nReads;
     u64 s = 0;
+    #pragma unroll 1
     for (u32 i = lo; i < hi; i++) s += results[i].nTrOut;
     part[t] = s;
     __syncthreads();
     if (t == 0) {
         u64 run = 0;
+        #pragma unroll 1
         for (u32 k = 0; k < blockDim.x; k++) { u64 v = part[k]; part[k] = run; run += v; }
         *total = run;
     }
     __syncthreads();
     u64 run = part[t];
+    #pragma unroll 1
     for (u32 i = lo; i < hi; i++) {
         offsets[i] = run;
         results[i].trOffset = run;

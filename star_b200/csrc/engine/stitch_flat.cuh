@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
     WarpWin ww;
     ww.swin = swin; ww.wa = ln.wa; ww.spw = caps.spw; ww.lane = lane; ww.nW = 0;
     long long tSetup = 0;
+    #pragma unroll 1
     for (;;) {
         long long t0 = clock64();
         u32 k = 0;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
         }
         {   // read into shared memory (both orientations)
             const u8* g = reads + (u64)i * stride;
+            #pragma unroll 1
             for (u32 b = lane; b < Lread; b += 32) {
                 u8 c = g[b];
                 R0[b] = c;
@@ -138,9 +140,11 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
         if (lane == 0) {
             if (!overReason) {
                 u32 shift = 0;
+                #pragma unroll 1
                 for (;;) {
                     u32 tot = 0;
                     nWinC = 0; nSeeds = 0;
+                    #pragma unroll 1
                     for (u32 w = 0; w < nWin; w++) {
                         u32 a = swin[w].nWA;
                         u32 d = a <= fa.splitMin ? 0 : (a - fa.splitMin > 8 ? 8 : a - fa.splitMin);
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
                     const u64 tb = atomicAdd(&fa.bumps[1], (unsigned long long)nTasks);
                     if (tb + nTasks > fa.maxTasks) {
                         overReason = 5;
+                        #pragma unroll 1
                         for (u64 t = tb; t < tb + nTasks && t < fa.maxTasks; t++) { FlatTask h; h.k = FLAT_NONE; h.w = 0; h.bits = 0; fa.tasks[t] = h; }
                     }
                     taskBase = (u32)tb;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
         nWinC = __shfl_sync(0xffffffffu, nWinC, 0);
         if (!overReason) {
             u8* rp = fa.pool + poolOff;
+            #pragma unroll 1
             for (u32 b = lane * 4; b < rs; b += 128) {   // both orientations (32-bit copies; rs and smemStride are multiples of 4)
                 u32 v0 = 0, v2 = 0;
                 if (b + 4 <= smemStride) { v0 = *(const u32*)(R0 + b); v2 = *(const u32*)(R2 + b); }
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
             Seed* fs = (Seed*)(fw + nWinC);
             u32 wc = 0, so = 0;
             const u32 kk = kBase + k;
+            #pragma unroll 1
             for (u32 w = 0; w < nWin; w++) {   // uniform loop
                 const u32 a = swin[w].nWA;
                 if (a == 0) continue;
@@ -194,7 +201,9 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(cons
                     fw[wc] = f;
                 }
                 const Seed* src = ln.wa + (u64)w * caps.spw;
+                #pragma unroll 1
                 for (u32 q = lane; q < a; q += 32) fs[so + q] = src[q];
+                #pragma unroll 1
                 for (u32 q = lane; q < (1u << d); q += 32) { FlatTask h; h.k = kk; h.w = (u16)wc; h.bits = (u16)q; fa.tasks[(u64)taskBase + ts + q] = h; }
                 wc++; so += a;
             }
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(const __grid_consta
     u64 trCur = 0, trEnd = 0;
     long long hc = 0, eU[3] = {0, 0, 0};
     long long tStart = clock64();
+    #pragma unroll 1
     for (;;) {
         {
             u32 mF = __ballot_sync(0xffffffffu, ph == 0), mN = __ballot_sync(0xffffffffu, ph == 1), mL = __ballot_sync(0xffffffffu, ph == 2);
@@ -316,8 +326,10 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(const __grid_consta
                     if (trCur + words <= trEnd) {
                         u64* dst = fa.trStore + trCur;
                         const u64* sh8 = (const u64*)&ln.leaf->h;
+                        #pragma unroll 1
                         for (u32 q = 0; q < sizeof(TrHead) / 8; q++) dst[q] = sh8[q];
                         const u64* se = (const u64*)ln.leaf->ex;
+                        #pragma unroll 1
                         for (u32 q = 0; q < nEx * (sizeof(Exon) / 8); q++) dst[sizeof(TrHead) / 8 + q] = se[q];
                         c.trOff = (u32)trCur;
                         trCur += words;
@@ -351,6 +363,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(const __grid_consta
     }
     PROF_ADD(17, clock64() - tStart);
     PROF_ADD(21, hc);
+    #pragma unroll 1
     for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
 }
 
@@ -383,6 +396,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
     ln.coop = 1;
     u64 trCur = 0, trEnd = 0;
     long long tStart = clock64();
+    #pragma unroll 1
     for (;;) {
         u32 base = 0;
         if (lane == 0) base = atomicAdd(counter, 32u);
@@ -400,6 +414,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
             WM = ((const FlatWin*)(fa.pool + poolOffM + 2 * (u64)flatReadStride(LreadM)))[tk.w];
         }
         const u32 vmask = __ballot_sync(0xffffffffu, tk.k != FLAT_NONE);
+        #pragma unroll 1
         for (u32 j = 0; j < 32; j++) {
             if (!((vmask >> j) & 1u)) continue;
             const u32 k = __shfl_sync(0xffffffffu, tk.k, j);
@@ -436,6 +451,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
             u32 curBlock = FLAT_NONE, firstBlock = FLAT_NONE, nCand = 0, inBlock = 0;
             int taskBest = 0;
             Cand c0; c0.mask = 0; c0.trOff = FLAT_NONE; c0.score = 0; c0.iFrag = 0; c0.pad = 0;
+            #pragma unroll 1
             for (;;) {
                 const u32 L = level;
                 nodes++;
@@ -517,6 +533,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
                     const bool full = nEx0 >= STAR_MAX_N_EXONS;
                     const u32 eFrag = eA.iFrag, eSj = eA.sjA;
                     u32 j = L;
+                    #pragma unroll 1
                     for (;;) {
                         const u32 idx = j + lane;
                         bool real = false;
@@ -625,6 +642,11 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
     ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
     long long tStart = clock64();
     long long nReplay = 0;
+    // slot table of the transcript pool: recordLeaf only ever permutes it, and which physical slot holds a transcript is irrelevant,
+    // so it is initialised once per lane and not per read
+    #pragma unroll 1
+    for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+    #pragma unroll 1
     for (;;) {
         const u32 k = atomicAdd(counter, 1u);
         if (k >= nRecs) break;
@@ -642,12 +664,9 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
             ln.R0 = rp; ln.R2 = rp + rs;
             const FlatWin* fw = (const FlatWin*)(rp + 2 * (u64)rs);
             const Seed* fs = (const Seed*)(fw + rec.nWin);
-            {   // work counters of the sub-tree evaluation
-                u64 nd = 0, lv = 0;
-                for (u32 t = 0; t < rec.nTasks; t++) { const FlatOut& o = fa.outs[(u64)rec.taskBase + t]; nd += o.nodes; lv += o.leaves; }
-                ln.nodes = nd; ln.leaves = lv;
-            }
-            for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+            u64 nd = 0, lv = 0;   // work counters of the sub-tree evaluation
+            u32 tSeen = 0;        // tasks [0,tSeen) are already counted
+            #pragma unroll 1
             for (u32 w = 0; w < rec.nWin && !ln.overflow; w++) {
                 const FlatWin W = fw[w];
                 u16* wTr = nullptr; u16 nWinTr = 0;
@@ -658,9 +677,12 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
                 const Seed* WA = fs + W.seedOff;
                 ln.R = Str == 0 ? ln.R0 : ln.R2;
                 const u64 tb = (u64)rec.taskBase + W.taskStart;
+                #pragma unroll 1
                 for (u32 tq = 0; tq < (1u << W.depth) && !ln.overflow; tq++) {
                     const FlatOut o = fa.outs[tb + tq];
+                    nd += o.nodes; lv += o.leaves; tSeen = W.taskStart + tq + 1;
                     u32 b = o.first, inBlock = 0;
+                    #pragma unroll 1
                     for (u32 q = 0; q < o.count; q++) {
                         Cand c;
                         if (q == 0) c = o.c0;
@@ -676,9 +698,11 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
                             if (c.trOff != FLAT_NONE) {   // transcript stored by the lane that evaluated the leaf
                                 const u64* src = fa.trStore + c.trOff;
                                 u64* dh = (u64*)&ln.leaf->h;
+                                #pragma unroll 1
                                 for (u32 z = 0; z < sizeof(TrHead) / 8; z++) dh[z] = src[z];
                                 const u32 nEx = ln.leaf->h.nExons;
                                 u64* de = (u64*)ln.leaf->ex;
+                                #pragma unroll 1
                                 for (u32 z = 0; z < nEx * (sizeof(Exon) / 8); z++) de[z] = src[sizeof(TrHead) / 8 + z];
                                 recordLeaf(ln, wTr, &nWinTr);
                             } else {
@@ -692,12 +716,16 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
                 }
                 windowEnd(ln, Chr, Str, wTr, nWinTr);
             }
+            #pragma unroll 1
+            for (u32 t = tSeen; t < rec.nTasks; t++) { const FlatOut& o = fa.outs[(u64)rec.taskBase + t]; nd += o.nodes; lv += o.leaves; }   // (windows skipped by an early exit)
+            ln.nodes = nd; ln.leaves = lv;
         }
         selectExport(ln, ri, i, 0, 0, results, staged, info);
     }
     PROF_ADD(18, clock64() - tStart);
     {
         long long r = nReplay;
+        #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
         PROF_ADD(20, r);
     }
