@@ -49,8 +49,8 @@ struct FlatArgs {   // stitch_flat.cuh
 };
 __global__ void flat_setup_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
                                   star_read_result_t*, star_align_t*, u32, FlatArgs, u32);
+void launch_flat_record(int, int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, ReadInfo*, u32, u32*, u8*, const Caps&, star_read_result_t*, star_align_t*, const FlatArgs&);
 void launch_flat_dfs(int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, const FlatArgs&, u32*, const Caps&, u8*, u32);
-__global__ void flat_record_kernel(DevIndex, star_params_t, ReadInfo*, u32, u32*, u8*, Caps, star_read_result_t*, star_align_t*, FlatArgs);
 __global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void prof_read_kernel(unsigned long long*, int);
@@ -119,7 +119,7 @@ struct star_ctx {
     bool flat = false;
     FlatArgs fa{};
     Caps recCaps; u8* d_arenaRec = nullptr; int gridRec = 0;
-    int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
+    int recMode = 1; int recCtas = 4; int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -398,13 +398,19 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         c->recCaps = c->heavyCaps;
         c->recCaps.arenaBytes = ((u64)c->recCaps.maxW * sizeof(Window) + (u64)c->recCaps.maxTr * sizeof(DevTr) + (u64)c->recCaps.maxTr * 2
                                  + (u64)c->recCaps.maxW * 4 + 255) & ~255ULL;
-        int recGrid = c->nSM * (int)envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", 2);
-        const int needGrid = (int)std::max<u64>(1, ((u64)N + 127) / 128);
-        c->gridRec = std::min(recGrid, needGrid);
-        CK(cudaMalloc(&p, (size_t)c->gridRec * 128 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
+        c->recMode = (int)envU32("STAR_B200_FLAT_REC_MODE", 1);   // 1: one read per warp (uniform execution); 0: one read per lane
+        c->recCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", c->recMode ? 4 : 2)));
+        if (c->recMode) {
+            CK(cudaMalloc(&p, (size_t)c->nSM * c->recCtas * 4 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
+        } else {
+            int recGrid = c->nSM * c->recCtas;
+            const int needGrid = (int)std::max<u64>(1, ((u64)N + 127) / 128);
+            c->gridRec = std::min(recGrid, needGrid);
+            CK(cudaMalloc(&p, (size_t)c->gridRec * 128 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
+        }
         CK(cudaFuncSetAttribute(flat_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->dfsMode = (int)envU32("STAR_B200_FLAT_DFS_MODE", 1);   // 1: one task per warp (uniform execution); 0: one task per lane
-        c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", c->dfsMode ? 4 : 4)));
+        c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", 4)));
         c->fetchMin = envU32("STAR_B200_FLAT_FETCH_MIN", 1);
         if (envU32("STAR_B200_FLAT_LANE_SCRATCH", 0)) {
             CK(cudaMalloc(&p, (size_t)c->nSM * c->dfsCtas * 128 * 4096)); c->d_laneScratch = (u8*)p; c->owned.push_back(p);
@@ -553,7 +559,7 @@ static int runFlat(star_ctx* c, u32 nHeavyB) {
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-    flat_record_kernel<<<c->gridRec, 128, 0, c->stream>>>(c->ix, c->P, c->d_info, nRecs, c->d_counter, c->d_arenaRec, c->recCaps, c->d_results, c->d_staged, c->fa);
+    launch_flat_record(c->recMode, c->recCtas, c->nSM, c->gridRec, c->stream, c->ix, c->P, c->d_info, nRecs, c->d_counter, c->d_arenaRec, c->recCaps, c->d_results, c->d_staged, c->fa);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->flatUse, c->fa.bumps, 32, cudaMemcpyDeviceToHost, c->stream));

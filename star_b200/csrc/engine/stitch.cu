@@ -849,6 +849,7 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
 
 // Leaf, part 2 (stitchWindowAligns.cpp:228-304): maxScoreMate update, record test, dedup by blocksOverlap, ordered insert.
 // Strictly sequential in DFS order within a window and in window order within a read.
+template <bool COOP = false>
 __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
     const star_params_t& P = *ln.P;
     DevTr& t = *ln.leaf;
@@ -893,7 +894,8 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
             #pragma unroll 1
             for (int ii = (int)n; ii > (int)iTr; ii--) wTr[ii] = wTr[ii - 1];
             wTr[iTr] = p;
-            copyTr(&ln.pool[p], &t);
+            if constexpr (COOP) warpCopyWords(&ln.pool[p], &t, 20 + 6 * nEx);   // (warp-uniform caller)
+            else copyTr(&ln.pool[p], &t);
             if (n < P.alignTranscriptsPerWindowNmax) n++;
         }
         *nWinTr = (u16)n;

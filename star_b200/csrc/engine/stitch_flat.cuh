@@ -611,6 +611,7 @@ void launch_flat_dfs(int mode, int ctasPerSM, int nSM, cudaStream_t stream, cons
     if (mode == 1) {
         const u32 smem = 4 * FLAT_WARP_SMEM;
         if (ctasPerSM <= 4) flat_dfs_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, fa, counter, caps);
+        else if (ctasPerSM == 5) flat_dfs_warp_kernel<5><<<nSM * 5, 128, smem, stream>>>(ix, P, fa, counter, caps);
         else if (ctasPerSM <= 6) flat_dfs_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, fa, counter, caps);
         else flat_dfs_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, fa, counter, caps);
         return;
@@ -729,4 +730,159 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(con
         for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
         PROF_ADD(20, r);
     }
+}
+
+// ---- warp-uniform recording kernel: one WARP per read.  All 32 lanes execute the order-dependent recording with identical state
+// (no divergence: one instruction stream per warp instead of 32); the scan over the read's tasks is cooperative: 32 FlatOut records
+// per step, only tasks that produced candidates are visited.  Windows without candidates are skipped: windowBegin has no lasting
+// effect for them and its exit conditions only depend on the number of transcripts recorded so far, which they do not change.
+#define FLAT_REC_SMEM (2 * (u32)sizeof(DevTr) + 2 * (u32)sizeof(Frame) + 64)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, ReadInfo* __restrict__ info,
+                                                                    u32 nRecs, u32* __restrict__ counter, u8* __restrict__ arenas, Caps caps,
+                                                                    star_read_result_t* __restrict__ results, star_align_t* __restrict__ staged, FlatArgs fa) {
+    extern __shared__ u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warpInBlock = threadIdx.x >> 5;
+    const u32 gwarp = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+    u8* ws = smem + (size_t)warpInBlock * FLAT_REC_SMEM;
+    Lane ln;
+    ln.leaf = (DevTr*)ws;
+    ln.cur = ln.leaf + 1;
+    ln.stack = (Frame*)(ln.cur + 1);
+    ln.ph = (u8*)(ln.stack + 2);
+    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
+    {   // per-WARP arena: compacted window Chr/Str | transcript pool | pointer arrays
+        u8* a = arenas + (u64)gwarp * caps.arenaBytes;
+        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+        ln.winN = (u16*)a;
+        ln.wa = nullptr;
+    }
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 1;
+    long long tStart = clock64();
+    long long nReplay = 0;
+    #pragma unroll 1
+    for (u32 q = lane; q < caps.maxTr; q += 32) ln.trPtr[q] = (u16)q;   // slot table: only ever permuted, initialised once
+    __syncwarp();
+    #pragma unroll 1
+    for (;;) {
+        u32 k = 0;
+        if (lane == 0) k = atomicAdd(counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nRecs) break;
+        const FlatRec rec = fa.recs[k];
+        if (rec.done) continue;
+        const u32 i = rec.read;
+        ReadInfo ri = info[i];
+        readBegin(ln, ri);
+        ln.saEnum = rec.saEnum;
+        if (rec.over) {
+            ln.overflow = rec.over;
+        } else {
+            const u8* rp = fa.pool + rec.poolOff;
+            const u32 rs = flatReadStride(rec.Lread);
+            ln.R0 = rp; ln.R2 = rp + rs;
+            const FlatWin* fw = (const FlatWin*)(rp + 2 * (u64)rs);
+            const Seed* fs = (const Seed*)(fw + rec.nWin);
+            u64 ndP = 0, lvP = 0;          // per-lane partial sums of the sub-tree work counters
+            u32 curW = FLAT_NONE;
+            bool openWin = false, stop = false;
+            u16* wTr = nullptr; u16 nWinTr = 0;
+            u32 Chr = 0, Str = 0, nA = 0;
+            const Seed* WA = nullptr;
+            #pragma unroll 1
+            for (u32 t0 = 0; t0 < rec.nTasks; t0 += 32) {
+                const u32 idx = t0 + lane;
+                FlatOut o; o.count = 0; o.first = FLAT_NONE; o.nodes = 0; o.leaves = 0; o.c0.mask = 0; o.c0.trOff = FLAT_NONE; o.c0.score = 0; o.c0.iFrag = 0; o.c0.pad = 0;
+                u32 wv = 0;
+                if (idx < rec.nTasks) {
+                    o = fa.outs[(u64)rec.taskBase + idx];
+                    wv = fa.tasks[(u64)rec.taskBase + idx].w;
+                    ndP += o.nodes; lvP += o.leaves;
+                }
+                u32 m = stop ? 0u : __ballot_sync(0xffffffffu, o.count > 0);
+                #pragma unroll 1
+                while (m && !stop) {
+                    const u32 j = (u32)__ffs(m) - 1;
+                    m &= m - 1;
+                    const u32 w = __shfl_sync(0xffffffffu, wv, j);
+                    const u32 cnt = __shfl_sync(0xffffffffu, o.count, j);
+                    const u32 first = __shfl_sync(0xffffffffu, o.first, j);
+                    Cand c0;
+                    c0.mask = __shfl_sync(0xffffffffu, o.c0.mask, j);
+                    c0.trOff = __shfl_sync(0xffffffffu, o.c0.trOff, j);
+                    {
+                        const u32 pk = __shfl_sync(0xffffffffu, (u32)(unsigned short)o.c0.score | ((u32)(u8)o.c0.iFrag << 16), j);
+                        c0.score = (short)(pk & 0xffffu); c0.iFrag = (signed char)(pk >> 16); c0.pad = 0;
+                    }
+                    if (w != curW) {
+                        if (openWin) { windowEnd(ln, Chr, Str, wTr, nWinTr); openWin = false; }
+                        const int rc = windowBegin(ln, wTr, nWinTr);
+                        if (rc == 2) { ln.overflow = 3; stop = true; break; }
+                        if (rc == 1) { stop = true; break; }
+                        const FlatWin W = fw[w];
+                        Chr = W.Chr; Str = W.Str; nA = W.nWA;
+                        WA = fs + W.seedOff;
+                        ln.R = Str == 0 ? ln.R0 : ln.R2;
+                        curW = w; openWin = true;
+                    }
+                    u32 b = first, inBlock = 0;
+                    #pragma unroll 1
+                    for (u32 q = 0; q < cnt; q++) {
+                        Cand c;
+                        if (q == 0) c = c0;
+                        else {
+                            if (inBlock == FLAT_CAND_PER_BLOCK) { b = fa.blocks[b].next; inBlock = 0; }
+                            c = fa.blocks[b].c[inBlock++];
+                        }
+                        if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
+                        const int wBest = ln.pool[wTr[0]].h.maxScore;
+                        if (c.score + P.outFilterMultimapScoreRange >= wBest ||
+                            (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
+                            if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; stop = true; break; }
+                            if (c.trOff != FLAT_NONE) {   // transcript stored by the warp that evaluated the leaf
+                                const u32 nEx = ((const TrHead*)(fa.trStore + c.trOff))->nExons;
+                                warpCopyWords(ln.leaf, fa.trStore + c.trOff, 20 + 6 * nEx);
+                                recordLeaf<true>(ln, wTr, &nWinTr);
+                            } else {
+                                int Score; u32 tR2; u64 tG2;
+                                nReplay++;
+                                __syncwarp();
+                                bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2);
+                                __syncwarp();
+                                ok = ok && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                __syncwarp();
+                                if (ok) recordLeaf<true>(ln, wTr, &nWinTr);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            if (openWin) windowEnd(ln, Chr, Str, wTr, nWinTr);
+            #pragma unroll 1
+            for (int off = 16; off > 0; off >>= 1) { ndP += __shfl_xor_sync(0xffffffffu, ndP, off); lvP += __shfl_xor_sync(0xffffffffu, lvP, off); }
+            ln.nodes = ndP; ln.leaves = lvP;
+        }
+        __syncwarp();
+        selectExport(ln, ri, i, 0, 0, results, staged, info);
+        __syncwarp();
+    }
+    PROF_ADD(18, clock64() - tStart);
+    PROF_ADD(20, nReplay);
+}
+
+void launch_flat_record(int mode, int ctasPerSM, int nSM, int gridLane, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
+                        u8* arenas, const Caps& caps, star_read_result_t* results, star_align_t* staged, const FlatArgs& fa) {
+    if (mode == 1) {
+        const u32 smem = 4 * FLAT_REC_SMEM;
+        if (ctasPerSM <= 2) flat_record_warp_kernel<2><<<nSM * 2, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+        else if (ctasPerSM == 3) flat_record_warp_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+        else flat_record_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+        return;
+    }
+    flat_record_kernel<<<gridLane, 128, 0, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
 }
