@@ -326,7 +326,7 @@ def main():
                            "l2_policy": "inputs larger than L2 (SA 392 MB + reads %d MB per step, L2 126 MB)" % (seq.nbytes >> 20),
                            "parallelism": "reads sharded across %d GPU(s), index replicated, one NCCL allreduce of the counters" % world,
                            "mapped_fraction": float((res_np["unmapType"] < 0).mean()), "overflow_tier_reads_per_step": int(last.slow_path_reads),
-                           "warp_per_read_kernel_reads_per_step": int(last.heavy_reads), "warp_per_read_kernel_ms": float(last.ms_heavy),
+                           "flat_path_reads_per_step": int(last.heavy_reads), "flat_path_ms": float(last.ms_heavy),
                            "wall_s_value_leg": wall},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e / a.steps * 1e3},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

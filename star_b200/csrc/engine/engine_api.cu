@@ -46,9 +46,10 @@ struct FlatArgs {   // stitch_flat.cuh
     void* blocks; u32 maxBlocks;
     u64* trStore; u64 trWords;
     u32 maxTasksPerRead, splitMin;
+    u32 storeAll, pad_;
 };
-__global__ void flat_setup_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
-                                  star_read_result_t*, star_align_t*, u32, FlatArgs, u32);
+void launch_flat_setup(int, int, u32, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*,
+                       const Caps&, star_read_result_t*, star_align_t*, u32, const FlatArgs&, u32);
 void launch_flat_record(int, int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, ReadInfo*, u32, u32*, u8*, const Caps&, star_read_result_t*, star_align_t*, const FlatArgs&);
 void launch_flat_dfs(int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, const FlatArgs&, u32*, const Caps&, u8*, u32);
 __global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
@@ -119,7 +120,7 @@ struct star_ctx {
     bool flat = false;
     FlatArgs fa{};
     Caps recCaps; u8* d_arenaRec = nullptr; int gridRec = 0;
-    int recMode = 1; int recCtas = 4; int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
+    int setupCtas = 2; u8* d_arenaSetup = nullptr; int recMode = 1; int recCtas = 4; int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -358,7 +359,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         c->heavyCaps.arenaBytes = arenaSize(c->heavyCaps);
     }
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
-    c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 4);
+    c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 6);
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
     {
         size_t bytes = (size_t)c->gridStitch * 128 * c->fast.arenaBytes;
@@ -377,13 +378,14 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         fa.poolBytes = std::min<u64>(48ULL << 30, std::max<u64>(256ULL << 20, (u64)N * perRead));
         fa.maxTasks = std::max<u64>(4ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TASKS_PER_READ", 192));
         if (fa.maxTasks > 0xFFFF0000ULL) fa.maxTasks = 0xFFFF0000ULL;
-        fa.maxBlocks = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(1ULL << 20, (u64)N * envU32("STAR_B200_FLAT_BLOCKS_PER_READ", 8)));
+        fa.maxBlocks = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(1ULL << 20, (u64)N * envU32("STAR_B200_FLAT_BLOCKS_PER_READ", 16)));
         fa.trWords = std::min<u64>(0xFFFF0000ULL, std::max<u64>(16ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TRWORDS_PER_READ", 2048)));
         // absolute overrides (tests exercise the exhaustion paths with tiny pools)
         if (getenv("STAR_B200_FLAT_POOL_BYTES")) fa.poolBytes = strtoull(getenv("STAR_B200_FLAT_POOL_BYTES"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_MAXTASKS")) fa.maxTasks = strtoull(getenv("STAR_B200_FLAT_MAXTASKS"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_MAXBLOCKS")) fa.maxBlocks = (u32)strtoull(getenv("STAR_B200_FLAT_MAXBLOCKS"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_TRWORDS")) fa.trWords = strtoull(getenv("STAR_B200_FLAT_TRWORDS"), nullptr, 10);
+        fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1); fa.pad_ = 0;
         fa.maxTasksPerRead = c->heavyMaxTasks;
         fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
         void* p = nullptr;
@@ -398,6 +400,8 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         c->recCaps = c->heavyCaps;
         c->recCaps.arenaBytes = ((u64)c->recCaps.maxW * sizeof(Window) + (u64)c->recCaps.maxTr * sizeof(DevTr) + (u64)c->recCaps.maxTr * 2
                                  + (u64)c->recCaps.maxW * 4 + 255) & ~255ULL;
+        c->setupCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_SETUP_CTAS_PER_SM", 3)));
+        CK(cudaMalloc(&p, (size_t)c->nSM * c->setupCtas * 4 * c->heavyCaps.arenaBytes)); c->d_arenaSetup = (u8*)p; c->owned.push_back(p);
         c->recMode = (int)envU32("STAR_B200_FLAT_REC_MODE", 1);   // 1: one read per warp (uniform execution); 0: one read per lane
         c->recCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", c->recMode ? 4 : 2)));
         if (c->recMode) {
@@ -408,7 +412,6 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
             c->gridRec = std::min(recGrid, needGrid);
             CK(cudaMalloc(&p, (size_t)c->gridRec * 128 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
         }
-        CK(cudaFuncSetAttribute(flat_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->dfsMode = (int)envU32("STAR_B200_FLAT_DFS_MODE", 1);   // 1: one task per warp (uniform execution); 0: one task per lane
         c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", 4)));
         c->fetchMin = envU32("STAR_B200_FLAT_FETCH_MIN", 1);
@@ -532,8 +535,8 @@ static int runFlat(star_ctx* c, u32 nHeavyB) {
     CK(cudaMemsetAsync(c->fa.bumps, 0, 64, c->stream));
     if (nHeavyB) {
         CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-        flat_setup_kernel<<<c->gridStitch, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, nHeavyB, c->d_order, c->d_heavyOff,
-                                                                  nullptr, c->d_counter, c->d_arenaHeavy, caps, c->d_results, c->d_staged, c->smemStride, c->fa, 0);
+        launch_flat_setup(c->setupCtas, c->nSM, smem, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, nHeavyB, c->d_order, c->d_heavyOff,
+                          nullptr, c->d_counter, c->d_arenaSetup, caps, c->d_results, c->d_staged, c->smemStride, c->fa, 0);
         g_launches++;
         CK(cudaGetLastError());
     }
@@ -547,8 +550,8 @@ static int runFlat(star_ctx* c, u32 nHeavyB) {
         std::sort(list.begin(), list.end());
         CK(cudaMemcpy(c->d_heavyList, list.data(), (size_t)nHeavyX * 4, cudaMemcpyHostToDevice));
         CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-        flat_setup_kernel<<<c->gridStitch, 128, smem, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, nullptr, nHeavyX, c->d_heavyList, c->d_heavyOff,
-                                                                  c->d_heavyPool, c->d_counter, c->d_arenaHeavy, caps, c->d_results, c->d_staged, c->smemStride, c->fa, nHeavyB);
+        launch_flat_setup(c->setupCtas, c->nSM, smem, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, nullptr, nHeavyX, c->d_heavyList, c->d_heavyOff,
+                          c->d_heavyPool, c->d_counter, c->d_arenaSetup, caps, c->d_results, c->d_staged, c->smemStride, c->fa, nHeavyB);
         g_launches++;
         CK(cudaGetLastError());
     }

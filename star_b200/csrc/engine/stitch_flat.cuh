@@ -50,11 +50,13 @@ struct FlatArgs {
     FlatBlock* blocks; u32 maxBlocks;
     u64* trStore; u64 trWords;
     u32 maxTasksPerRead, splitMin;
+    u32 storeAll, pad_;            // storeAll: keep the evaluated transcript of EVERY surviving leaf (no replays in the recording kernel)
 };
 
 __device__ __forceinline__ u32 flatReadStride(u32 Lread) { return (Lread + 16) & ~15u; }
 
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_setup_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) flat_setup_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                    ReadInfo* __restrict__ info, const Piece* __restrict__ pieces, u32 nHeavy, const u32* __restrict__ heavyList,
                                                    const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool, u32* __restrict__ counter,
                                                    u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
                         if (keep) {
                             const int sc = ln.leaf->h.maxScore;
                             Cand c; c.mask = incl; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
-                            if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
+                            if (fa.storeAll || sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
                                 if (sc > taskBest) taskBest = sc;
                                 const u32 nEx = ln.leaf->h.nExons;
                                 const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
@@ -885,4 +887,19 @@ void launch_flat_record(int mode, int ctasPerSM, int nSM, int gridLane, cudaStre
         return;
     }
     flat_record_kernel<<<gridLane, 128, 0, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+}
+
+void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
+                       const Piece* pieces, u32 nHeavy, const u32* heavyList, const u64* heavyOff, const u8* heavyPool, u32* counter, u8* arenas, const Caps& caps,
+                       star_read_result_t* results, star_align_t* staged, u32 smemStride, const FlatArgs& fa, u32 kBase) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(flat_setup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(flat_setup_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(flat_setup_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    if (ctasPerSM <= 2) flat_setup_kernel<2><<<nSM * 2, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, nHeavy, heavyList, heavyOff, heavyPool, counter, arenas, caps, results, staged, smemStride, fa, kBase);
+    else if (ctasPerSM == 3) flat_setup_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, nHeavy, heavyList, heavyOff, heavyPool, counter, arenas, caps, results, staged, smemStride, fa, kBase);
+    else flat_setup_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, nHeavy, heavyList, heavyOff, heavyPool, counter, arenas, caps, results, staged, smemStride, fa, kBase);
 }
