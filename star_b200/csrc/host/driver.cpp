@@ -12,6 +12,11 @@
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "host.h"
@@ -87,62 +92,134 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     time(&stats.timeStartMap);
     std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
 
+    // ---- three overlapped stages, chunks flow in input order through bounded queues (3 chunk buffers in flight):
+    //   reader thread   : FASTQ/FASTA text -> ReadChunk                      (ReadAlignChunk_processChunks.cpp:11-282)
+    //   this thread     : one engine call per chunk through the C-ABI        (ReadAlignChunk_mapChunk.cpp:7-128)
+    //   output thread   : SAM / junction / counter formatting on runThreadN threads, ordered writes
+    struct Work {
+        ReadChunk chunk;
+        std::vector<star_read_result_t> results;
+        std::vector<star_align_t> aligns;
+        star_align_batch_t out;
+        long long n = 0;          // reads in the chunk; 0 = end of input; < 0 = -STAR_EXIT_* (err holds the message)
+        std::string err;
+    };
+    struct Queue {
+        std::mutex m; std::condition_variable cv; std::deque<Work*> q;
+        void push(Work* w) { { std::lock_guard<std::mutex> l(m); q.push_back(w); } cv.notify_one(); }
+        Work* pop() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty(); }); Work* w = q.front(); q.pop_front(); return w; }
+    };
+    const int NBUF = 3;
+    std::vector<Work> bufs(NBUF);
+    Queue freeQ, mapQ, outQ;
+    for (auto& wk : bufs) freeQ.push(&wk);
     std::vector<Junction> allSJ;
-    ReadChunk chunk;
-    std::vector<star_read_result_t> results(P.gpuChunkReads);
-    std::vector<star_align_t> aligns;
     const int nT = std::max(1, P.runThreadN);
-    star_chunk_stats_t cs;
-    double msEngine = 0;
+    double msEngine = 0, msRead = 0, msFormat = 0, msWrite = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto msSince = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
     uint64_t nChunks = 0;
+    std::atomic<bool> abortRun(false);
+    std::string outErr;   // set by the output thread (junction buffer bug check)
+
+    std::thread readerThread([&] {
+        for (;;) {
+            Work* wk = freeQ.pop();
+            if (abortRun.load()) { wk->n = 0; mapQ.push(wk); return; }
+            auto t0 = now();
+            wk->err.clear();
+            wk->n = reader.next(wk->chunk, P.gpuChunkReads, wk->err);
+            msRead += msSince(t0);
+            const long long n = wk->n;
+            mapQ.push(wk);
+            if (n <= 0) return;
+        }
+    });
+    std::thread outputThread([&] {
+        for (;;) {
+            Work* wk = outQ.pop();
+            if (wk->n <= 0) return;
+            if (!abortRun.load()) {
+                const ReadChunk& chunk = wk->chunk;
+                auto tf0 = now();
+                std::vector<std::string> sam(nT);
+                std::vector<std::vector<Junction>> sj(nT);
+                std::vector<Stats> st(nT);
+                auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
+                    uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
+                    sam[t].reserve((size_t)(hi - lo) * 700);
+                    W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t]);
+                };
+                if (nT == 1) {
+                    work(0);
+                } else {
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nT; t++) th.emplace_back(work, t);
+                    for (auto& t : th) t.join();
+                }
+                msFormat += msSince(tf0);
+                auto tw0 = now();
+                for (int t = 0; t < nT; t++) {
+                    if (samYes) samOut.write(sam[t].data(), sam[t].size());
+                    allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
+                    stats.add(st[t]);
+                }
+                msWrite += msSince(tw0);
+                if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
+                    std::string e2;
+                    OutputWriter::collapseSJ(allSJ, e2);
+                    if (!e2.empty()) { outErr = e2; abortRun.store(true); }
+                }
+            }
+            freeQ.push(wk);
+        }
+    });
+    int runRc = 0;
+    std::string runErr;
     for (;;) {
-        long long n = reader.next(chunk, P.gpuChunkReads, err);
-        if (n < 0) { eng->destroy(ectx); return exitWithError(err, (int)-n, &logMain); }
-        if (n == 0) break;
+        Work* wk = mapQ.pop();
+        if (wk->n <= 0 || abortRun.load()) {
+            if (wk->n < 0 && !runRc) { runRc = (int)-wk->n; runErr = wk->err; }
+            abortRun.store(abortRun.load() || wk->n < 0);
+            wk->n = 0;
+            outQ.push(wk);      // end marker for the output thread
+            break;
+        }
+        const ReadChunk& chunk = wk->chunk;
         star_read_batch_t in;
         in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
         uint64_t cap = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
-        if (aligns.size() < cap) aligns.resize(cap);
-        star_align_batch_t out;
-        out.reads = results.data(); out.aligns = aligns.data(); out.alignsCapacity = aligns.size(); out.nAligns = 0;
+        if (wk->aligns.size() < cap) wk->aligns.resize(cap);
+        if (wk->results.size() < chunk.nReads) wk->results.resize(chunk.nReads);
+        wk->out.reads = wk->results.data(); wk->out.aligns = wk->aligns.data(); wk->out.alignsCapacity = wk->aligns.size(); wk->out.nAligns = 0;
+        star_chunk_stats_t cs;
         memset(&cs, 0, sizeof(cs));
-        rc = eng->map_chunk(ectx, &in, &out, &cs);
-        if (rc) { eng->destroy(ectx); return exitWithError(eng->last_error(), rc, &logMain); }
+        rc = eng->map_chunk(ectx, &in, &wk->out, &cs);
+        if (rc) {
+            runRc = rc; runErr = eng->last_error();
+            abortRun.store(true);
+            wk->n = 0;
+            outQ.push(wk);
+            break;
+        }
         msEngine += cs.ms_total;
         nChunks++;
-        // format in parallel over contiguous read ranges; concatenate in input order
-        std::vector<std::string> sam(nT);
-        std::vector<std::vector<Junction>> sj(nT);
-        std::vector<Stats> st(nT);
-        auto work = [&](int t) {
-            uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
-            sam[t].reserve((size_t)(hi - lo) * 700);
-            W.formatReads(chunk, out, lo, hi, sam[t], sj[t], st[t]);
-        };
-        if (nT == 1) {
-            work(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nT; t++) th.emplace_back(work, t);
-            for (auto& t : th) t.join();
-        }
-        for (int t = 0; t < nT; t++) {
-            if (samYes) samOut.write(sam[t].data(), sam[t].size());
-            allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
-            stats.add(st[t]);
-        }
-        if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
-            std::string e2;
-            OutputWriter::collapseSJ(allSJ, e2);
-            if (!e2.empty()) { eng->destroy(ectx); return exitWithError(e2, STAR_EXIT_BUG, &logMain); }
-        }
+        outQ.push(wk);
     }
+    outputThread.join();
+    if (abortRun.load()) {   // release a reader that may be waiting for a free buffer
+        for (auto& wk : bufs) freeQ.push(&wk);
+    }
+    readerThread.join();
+    if (runRc) { eng->destroy(ectx); return exitWithError(runErr, runRc, &logMain); }
+    if (!outErr.empty()) { eng->destroy(ectx); return exitWithError(outErr, STAR_EXIT_BUG, &logMain); }
     eng->destroy(ectx);
     if (samYes) samOut.close();
     time_t tFinishMap; time(&tFinishMap);
     std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
     logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
+    logMain << "star-b200: host time: reads input " << msRead << " ms, SAM/SJ formatting " << msFormat << " ms, output writes " << msWrite << " ms\n";
     time(&stats.timeFinish);
     if (P.gpuShardCount > 1) {
         // one shard of a multi-GPU run: leave the counters and the (collapsed) junction records for the merge
