@@ -16,6 +16,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -99,7 +100,9 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     struct Work {
         ReadChunk chunk;
         std::vector<star_read_result_t> results;
-        std::vector<star_align_t> aligns;
+        // worst case nReads x outFilterMultimapNmax records of 496 B: allocated once, NOT value-initialised (only the part the
+        // engine fills is ever touched, so the untouched pages are never faulted in)
+        std::unique_ptr<star_align_t[]> aligns; uint64_t alignsCap = 0;
         star_align_batch_t out;
         long long n = 0;          // reads in the chunk; 0 = end of input; < 0 = -STAR_EXIT_* (err holds the message)
         std::string err;
@@ -189,9 +192,9 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         star_read_batch_t in;
         in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
         uint64_t cap = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
-        if (wk->aligns.size() < cap) wk->aligns.resize(cap);
+        if (wk->alignsCap < cap) { wk->aligns.reset(new star_align_t[cap]); wk->alignsCap = cap; }
         if (wk->results.size() < chunk.nReads) wk->results.resize(chunk.nReads);
-        wk->out.reads = wk->results.data(); wk->out.aligns = wk->aligns.data(); wk->out.alignsCapacity = wk->aligns.size(); wk->out.nAligns = 0;
+        wk->out.reads = wk->results.data(); wk->out.aligns = wk->aligns.get(); wk->out.alignsCapacity = wk->alignsCap; wk->out.nAligns = 0;
         star_chunk_stats_t cs;
         memset(&cs, 0, sizeof(cs));
         rc = eng->map_chunk(ectx, &in, &wk->out, &cs);
