@@ -16,42 +16,16 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "dev.cuh"
+#include "stitch_types.cuh"
 
 namespace starb {
 // kernels (seed.cu, stitch.cu)
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
 __global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
-struct HeavyArgs {
-    u8* pool; u64 poolBytes; unsigned long long* bump;
-    u64* readOff;
-    u32* list; u32* count;
-    u32 estLimit;
-};
-struct HeavyScratch {
-    u32 maxTasks, maxBlocks, maxWin;
-    u32 trWords;
-    u32 memoSlots;
-    u32 splitMin;
-    u64 bytesPerWarp;
-};
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
                               star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
 __global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
                                     star_read_result_t*, star_align_t*, u32, u8*, HeavyScratch);
-struct FlatArgs {   // stitch_flat.cuh
-    void* recs;
-    u8* pool; u64 poolBytes;
-    unsigned long long* bumps;
-    void* tasks; void* outs; u64 maxTasks;
-    void* blocks; u32 maxBlocks;
-    u64* trStore; u64 trWords;
-    u32 maxTasksPerRead, splitMin;
-    u32 storeAll, pad_;
-};
-void launch_flat_setup(int, int, u32, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*,
-                       const Caps&, star_read_result_t*, star_align_t*, u32, const FlatArgs&, u32);
-void launch_flat_record(int, int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, ReadInfo*, u32, u32*, u8*, const Caps&, star_read_result_t*, star_align_t*, const FlatArgs&);
-void launch_flat_dfs(int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, const FlatArgs&, u32*, const Caps&, u8*, u32);
 __global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void prof_read_kernel(unsigned long long*, int);
@@ -389,12 +363,12 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
         fa.maxTasksPerRead = c->heavyMaxTasks;
         fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
         void* p = nullptr;
-        CK(cudaMalloc(&p, (size_t)N * 48)); fa.recs = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, (size_t)N * sizeof(FlatRec))); fa.recs = (FlatRec*)p; c->owned.push_back(p);
         CK(cudaMalloc(&p, fa.poolBytes)); fa.pool = (u8*)p; c->owned.push_back(p);
         CK(cudaMalloc(&p, 64)); fa.bumps = (unsigned long long*)p; c->owned.push_back(p);
-        CK(cudaMalloc(&p, fa.maxTasks * 8)); fa.tasks = p; c->owned.push_back(p);
-        CK(cudaMalloc(&p, fa.maxTasks * 32)); fa.outs = p; c->owned.push_back(p);
-        CK(cudaMalloc(&p, (size_t)fa.maxBlocks * 128)); fa.blocks = p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.maxTasks * sizeof(FlatTask))); fa.tasks = (FlatTask*)p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, fa.maxTasks * sizeof(FlatOut))); fa.outs = (FlatOut*)p; c->owned.push_back(p);
+        CK(cudaMalloc(&p, (size_t)fa.maxBlocks * sizeof(FlatBlock))); fa.blocks = (FlatBlock*)p; c->owned.push_back(p);
         CK(cudaMalloc(&p, fa.trWords * 8)); fa.trStore = (u64*)p; c->owned.push_back(p);
         // recording kernel: one lane per read, each lane with its own transcript pool
         c->recCaps = c->heavyCaps;

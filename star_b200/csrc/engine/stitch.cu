@@ -23,6 +23,7 @@
 //    correctly rounded); every other floating-point expression is a single IEEE multiply/divide and is evaluated
 //    in fp64 as written in the reference.
 #include "dev.cuh"
+#include "stitch_types.cuh"
 
 namespace starb {
 
@@ -1513,12 +1514,6 @@ __device__ bool exportHeavy(Lane& ln, u8* __restrict__ heavyPool, u64 heavyPoolB
 // A read never waits for its warp neighbours.
 enum { PH_FETCH = 0, PH_WIN, PH_FLANK, PH_ASSIGN, PH_NEXTWIN, PH_NODE, PH_LEAF, PH_SELECT, PH_DONE };
 
-struct HeavyArgs {
-    u8* pool; u64 poolBytes; unsigned long long* bump;   // export pool
-    u64* readOff;                                         // per read: offset of its record in the pool
-    u32* list; u32* count;                                // heavy read list (read ids) and its length
-    u32 estLimit;                                         // a read is heavy when sum_w 2^min(nWA_w,20) exceeds this (0 = heavy path off)
-};
 
 #ifndef STITCH_MIN_BLOCKS
 #define STITCH_MIN_BLOCKS 2
@@ -1819,18 +1814,10 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_kernel(const __
 // evalLeaf) only for the few candidates that pass the record test.  Result: identical to the sequential recursion.
 // trOff: offset (in 8-byte words) of the evaluated transcript stored by the lane for candidates that are likely to pass the record
 // test (saves the replay in the R phase); 0xFFFFFFFF = not stored, the R phase replays the path.
-struct Cand { u64 mask; u32 trOff; short score; signed char iFrag; u8 pad; };
 #define CAND_PER_BLOCK 31
 struct CandBlock { u32 next; u32 count; Cand c[CAND_PER_BLOCK]; };   // 8 + 31*16 = 504 bytes
 struct TaskOut { u32 first, last; };                                 // candidate blocks of a task (0xFFFFFFFF = none)
 
-struct HeavyScratch {     // per warp, in HBM
-    u32 maxTasks, maxBlocks, maxWin;
-    u32 trWords;              // capacity (8-byte words) of the per-warp stored-transcript buffer
-    u32 memoSlots;            // stitch memo entries per warp (power of two; 0 = off)
-    u32 splitMin;             // windows with more seeds than this are cut into 2^(nWA-splitMin) (max 256) prefix sub-trees
-    u64 bytesPerWarp;
-};
 
 __device__ bool replayPath(Lane& ln, const Seed* __restrict__ WA, u32 nA, u64 mask, int& Score, u32& tR2, u64& tG2) {
     DevTr* t = ln.cur;

@@ -19,40 +19,6 @@
 // Results are identical to the sequential recursion for the same reason as in the heavy kernel (evalLeaf is a pure function of
 // the path; recordLeaf sees the leaves in DFS order).
 
-struct FlatRec {          // one per heavy read of the chunk
-    u64 poolOff;          // record in the flat pool
-    u32 read;             // read index in the chunk
-    u32 nWin;             // windows with seeds (only those are exported)
-    u32 taskBase, nTasks; // tasks [taskBase, taskBase+nTasks) of the global task array
-    u32 over;             // overflow reason (0 = ok); also set by flat_dfs_kernel when the candidate pool is exhausted
-    u32 done;             // 1: the read was finished by the setup kernel (early exits)
-    u32 saEnum;
-    u32 Lread;
-    u32 mmMax;            // outFilterMismatchNmaxTotal of the read
-    u16 readLength[2];
-};
-static_assert(sizeof(FlatRec) == 48, "engine_api.cu sizes the record array with 48-byte entries");
-
-struct FlatWin { u32 Chr; u16 nWA; u8 Str; u8 depth; u32 seedOff; u32 taskStart; };   // 16 B
-struct FlatTask { u32 k; u16 w; u16 bits; };                                           // k = 0xFFFFFFFF: hole (never written)
-struct FlatOut { Cand c0; u32 count; u32 first; u32 nodes; u32 leaves; };              // 32 B per task
-#define FLAT_CAND_PER_BLOCK 7
-struct FlatBlock { u32 next; u32 count; Cand c[FLAT_CAND_PER_BLOCK]; u64 pad; };       // 128 B
-static_assert(sizeof(FlatOut) == 32 && sizeof(FlatBlock) == 128 && sizeof(FlatTask) == 8 && sizeof(FlatWin) == 16, "flat layouts");
-#define FLAT_NONE 0xFFFFFFFFu
-#define FLAT_TR_CHUNK 512   // 8-byte words a lane reserves at a time in the stored-transcript buffer
-
-struct FlatArgs {
-    FlatRec* recs;
-    u8* pool; u64 poolBytes;
-    unsigned long long* bumps;     // [0] pool bytes, [1] tasks, [2] candidate blocks, [3] stored-transcript words
-    FlatTask* tasks; FlatOut* outs; u64 maxTasks;
-    FlatBlock* blocks; u32 maxBlocks;
-    u64* trStore; u64 trWords;
-    u32 maxTasksPerRead, splitMin;
-    u32 storeAll, pad_;            // storeAll: keep the evaluated transcript of EVERY surviving leaf (no replays in the recording kernel)
-};
-
 __device__ __forceinline__ u32 flatReadStride(u32 Lread) { return (Lread + 16) & ~15u; }
 
 template <int MINB>
