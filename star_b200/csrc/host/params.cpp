@@ -334,6 +334,7 @@ int finalizeParams(HostParams& P, std::string& err) {
             if (it == code.end()) return bad("EXITING because of FATAL INPUT ERROR: unknown/unimplemented SAM atrribute (tag): " + s + "\nSOLUTION: star-b200 supports NH HI AS nM NM MD jM jI XS MC RG ch\n");
             if (s == "RG" && P.outSAMattrRGline[0] == "-") continue;
             P.outSAMattrOrder.push_back(it->second);
+            if (s == "XS") h.outSAMstrandFieldType = 1;   // Parameters_samAttributes.cpp:172-179: XS implies --outSAMstrandField intronMotif
         }
         if (h.outSAMstrandFieldType == 1) {  // Parameters_samAttributes.cpp: XS added for intronMotif
             bool has = false;

@@ -112,3 +112,27 @@ def test_cli_matches_reference_golden(lib, golden, tmp_path, name, extra):
     assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
     assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
     assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+
+
+@pytest.mark.parametrize("base,extra", [
+    ("std", ["--outSAMattributes", "NH", "HI", "AS", "nM", "XS"]),
+    ("std", ["--outSAMstrandField", "intronMotif", "--outFilterIntronMotifs", "RemoveNoncanonical"]),
+    ("std", ["--alignEndsType", "Extend5pOfRead1", "--outSAMprimaryFlag", "AllBestScore"]),
+    ("std", ["--outFilterMultimapNmax", "3", "--winAnchorMultimapNmax", "100", "--outSAMmultNmax", "2"]),
+    ("hard", ["--outFilterMismatchNoverLmax", "0.1", "--scoreGenomicLengthLog2scale", "0", "--alignSJoverhangMin", "8"]),
+])
+def test_cli_option_sets_match_oracle_cli(lib, oracle, golden, tmp_path, base, extra):
+    """Option sets without committed goldens: the drop-in CLI on the GPU vs the same host code driven by the oracle engine
+    (the oracle itself is pinned to the unmodified reference for these option sets by tests/test_oracle_golden.py)."""
+    import oracle_capi as oc
+    files = _sets(golden)[base]
+    outs = []
+    for tag, binary in (("gpu", os.path.join(ROOT, "star_b200", "bin", "STAR")), ("ora", oc.ORACLE_CLI)):
+        out = str(tmp_path / tag) + "/"
+        os.makedirs(out)
+        cmd = [binary, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn"] + files + ["--outFileNamePrefix", out, "--runThreadN", "2"] + list(extra)
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        outs.append(out)
+    assert cf.sam_body(outs[0] + "Aligned.out.sam") == cf.sam_body(outs[1] + "Aligned.out.sam")
+    assert open(outs[0] + "SJ.out.tab", "rb").read() == open(outs[1] + "SJ.out.tab", "rb").read()
+    assert cf.log_counters(outs[0] + "Log.final.out") == cf.log_counters(outs[1] + "Log.final.out")

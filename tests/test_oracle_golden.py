@@ -66,3 +66,23 @@ def test_oracle_vs_live_reference(oracle, golden, tmp_path, kw):
     assert cf.sam_body(str(tmp_path / "ora" / "Aligned.out.sam")) == cf.sam_body(str(tmp_path / "ref" / "Aligned.out.sam"))
     assert open(str(tmp_path / "ora" / "SJ.out.tab"), "rb").read() == open(str(tmp_path / "ref" / "SJ.out.tab"), "rb").read()
     assert cf.log_counters(str(tmp_path / "ora" / "Log.final.out")) == cf.log_counters(str(tmp_path / "ref" / "Log.final.out"))
+
+
+@pytest.mark.skipif(not os.path.exists(oc.REF_STAR), reason="oracle/_ref/STAR not built (needs /root/reference)")
+@pytest.mark.parametrize("base,extra", [
+    ("hard", ["--outFilterMismatchNoverLmax", "0.1", "--scoreGenomicLengthLog2scale", "0", "--alignSJoverhangMin", "8"]),
+    ("std", ["--outSAMattributes", "NH", "HI", "AS", "nM", "XS"]),                      # XS implies --outSAMstrandField intronMotif (Parameters_samAttributes.cpp:172-179)
+    ("std", ["--outSAMstrandField", "intronMotif", "--outFilterIntronMotifs", "RemoveNoncanonical"]),
+    ("std", ["--alignEndsType", "Extend5pOfRead1", "--outSAMprimaryFlag", "AllBestScore"]),
+    ("std", ["--outFilterMultimapNmax", "3", "--winAnchorMultimapNmax", "100", "--outSAMmultNmax", "2"]),
+])
+def test_option_sets_vs_live_reference(oracle, golden, tmp_path, base, extra):
+    """Non-default option sets that are not in the committed goldens: unmodified reference binary vs oracle-driven host code."""
+    files = [os.path.join(golden, base + "_1.fq"), os.path.join(golden, base + "_2.fq")]
+    os.makedirs(str(tmp_path / "ref"))
+    os.makedirs(str(tmp_path / "ora"))
+    _run_cli(oc.REF_STAR, os.path.join(golden, "idx"), files, str(tmp_path / "ref") + "/", extra=extra, threads=1)
+    _run_cli(oc.ORACLE_CLI, os.path.join(golden, "idx"), files, str(tmp_path / "ora") + "/", extra=extra, threads=2)
+    assert cf.sam_body(str(tmp_path / "ora" / "Aligned.out.sam")) == cf.sam_body(str(tmp_path / "ref" / "Aligned.out.sam"))
+    assert open(str(tmp_path / "ora" / "SJ.out.tab"), "rb").read() == open(str(tmp_path / "ref" / "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(str(tmp_path / "ora" / "Log.final.out")) == cf.log_counters(str(tmp_path / "ref" / "Log.final.out"))
