@@ -25,7 +25,7 @@ $(BUILD)/host_%.o: star_b200/csrc/host/%.cpp star_b200/csrc/host/host.h include/
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 $(LIB): $(ENG_OBJ) $(HOST_OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -lpthread -lz
 
 $(BIN): star_b200/csrc/cli_main.cpp $(LIB)
 	$(CXX) $(CXXFLAGS) -o $@ $< -Lstar_b200/lib -lstar_b200 -Wl,-rpath,'$$ORIGIN/../lib'

@@ -85,9 +85,13 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     OutputWriter W(P, idx);
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     std::ofstream samOut;
+    const bool bamYes = samYes && P.outBAMunsorted;
     if (samYes) {
-        samOut.open(P.outFileNamePrefix + "Aligned.out.sam", std::ios::binary);
-        if (P.gpuShardIndex == 0) samOut << W.samHeader();   // shards > 0 write records only; the merge concatenates in shard order
+        samOut.open(P.outFileNamePrefix + (bamYes ? "Aligned.out.bam" : "Aligned.out.sam"), std::ios::binary);
+        if (P.gpuShardIndex == 0) {   // shards > 0 write records only; the merge concatenates in shard order
+            if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samOut.write(z.data(), z.size()); }
+            else samOut << W.samHeader();
+        }
     }
     std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
     time(&stats.timeStartMap);
@@ -152,6 +156,12 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
                     uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
                     sam[t].reserve((size_t)(hi - lo) * 700);
                     W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t]);
+                    if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
+                        std::string z;
+                        z.reserve(sam[t].size() / 3);
+                        OutputWriter::bgzfCompress(sam[t].data(), sam[t].size(), P.outBAMcompression, z);
+                        sam[t].swap(z);
+                    }
                 };
                 if (nT == 1) {
                     work(0);
@@ -217,6 +227,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     if (runRc) { eng->destroy(ectx); return exitWithError(runErr, runRc, &logMain); }
     if (!outErr.empty()) { eng->destroy(ectx); return exitWithError(outErr, STAR_EXIT_BUG, &logMain); }
     eng->destroy(ectx);
+    if (bamYes && P.gpuShardCount == 1) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
     if (samYes) samOut.close();
     time_t tFinishMap; time(&tFinishMap);
     std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
@@ -268,8 +279,9 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
     std::vector<Junction> allSJ;
     int64_t tStart = 0, tStartMap = 0, tFinish = 0;
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    const std::string alnName = P.outBAMunsorted ? "Aligned.out.bam" : "Aligned.out.sam";
     std::ofstream samOut;
-    if (samYes) samOut.open(P.outFileNamePrefix + "Aligned.out.sam", std::ios::binary);
+    if (samYes) samOut.open(P.outFileNamePrefix + alnName, std::ios::binary);
     for (int r = 0; r < nShards; r++) {
         std::string sp = P.outFileNamePrefix + "shard" + std::to_string(r) + ".";
         std::ifstream sb(sp + "shard.bin", std::ios::binary);
@@ -284,11 +296,12 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
         allSJ.resize(old + nsj);
         if (nsj) sb.read((char*)(allSJ.data() + old), nsj * sizeof(Junction));
         if (samYes) {
-            std::ifstream in(sp + "Aligned.out.sam", std::ios::binary);
+            std::ifstream in(sp + alnName, std::ios::binary);
             samOut << in.rdbuf();
             samOut.clear();   // an empty shard sets failbit on operator<<
         }
     }
+    if (samYes && P.outBAMunsorted) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }
     if (counters) total.fromArray(counters);
     total.timeStart = (time_t)tStart; total.timeStartMap = (time_t)tStartMap; total.timeFinish = (time_t)tFinish;
     if (P.outSJyes) {

@@ -32,6 +32,8 @@ struct HostParams {
     std::string outFileNamePrefix = "./";
     std::string outStd = "Log";
     std::vector<std::string> outSAMtype = {"SAM"};
+    bool outBAMunsorted = false;            // --outSAMtype BAM Unsorted  -> Aligned.out.bam
+    int outBAMcompression = 1;              // --outBAMcompression (zlib level of the BGZF blocks; -1 = zlib default)
     std::string outSAMmode = "Full";
     std::string outSAMstrandField = "None";
     std::vector<std::string> outSAMattributes = {"Standard"};
@@ -155,6 +157,10 @@ class OutputWriter {
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
                      std::vector<Junction>& sj, Stats& st) const;
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
+    std::string bamHeader() const;                                   // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
+    // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`
+    static void bgzfCompress(const char* data, size_t n, int level, std::string& out);
+    static const char* bgzfEofBlock(size_t& n);
     // outputSJ.cpp:20-200: collapse + filters + SJ.out.tab text; returns error text (empty = ok)
     std::string writeSJ(std::vector<Junction>& all, const std::string& path) const;
     static void collapseSJ(std::vector<Junction>& v, std::string& err);
@@ -163,6 +169,10 @@ class OutputWriter {
    private:
     const HostParams& P;
     const LoadedIndex& idx;
+    void bamMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
+                   std::string& bam) const;                          // ReadAlign_alignBAM.cpp:47-614, mapped branch
+    void bamUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trBest, int unmapType,
+                     const bool* mateMap, std::string& bam) const;    // ReadAlign_alignBAM.cpp, alignType>=0 branch
     void samMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
                    std::string& sam) const;
     void samUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trBest, int unmapType,

@@ -14,6 +14,8 @@
 #include <iomanip>
 #include <sstream>
 
+#include <zlib.h>
+
 #include "host.h"
 
 namespace starhost {
@@ -304,6 +306,328 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// BAM records: restatement of ReadAlign::alignBAM (ReadAlign_alignBAM.cpp:47-614) for the path's
+// alignment types (-1 mapped, >=0 unmapped), the typed attribute writers of BAMfunctions.cpp / BAMfunctions.h:44-77 and
+// nuclPackBAM (SequenceFuns.cpp:99-129).  Records are appended uncompressed; the caller frames them into BGZF blocks.
+namespace {
+inline void put32(std::string& s, uint32_t v) { s.append((const char*)&v, 4); }
+inline void attrInt(std::string& s, const char* tag, long long x) {  // bamAttrArrayWriteInt: smallest fitting type
+    s.push_back(tag[0]); s.push_back(tag[1]);
+    if (x < 0) {
+        if (x >= -127) { s.push_back('c'); int8_t v = (int8_t)x; s.append((const char*)&v, 1); }
+        else if (x >= -32767) { s.push_back('s'); int16_t v = (int16_t)x; s.append((const char*)&v, 2); }
+        else { s.push_back('i'); int32_t v = (int32_t)x; s.append((const char*)&v, 4); }
+    } else {
+        if (x <= 255) { s.push_back('C'); uint8_t v = (uint8_t)x; s.append((const char*)&v, 1); }
+        else if (x <= 65535) { s.push_back('S'); uint16_t v = (uint16_t)x; s.append((const char*)&v, 2); }
+        else { s.push_back('I'); uint32_t v = (uint32_t)x; s.append((const char*)&v, 4); }
+    }
+}
+inline void attrChar(std::string& s, const char* tag, char c) { s.push_back(tag[0]); s.push_back(tag[1]); s.push_back('A'); s.push_back(c); }
+inline void attrStr(std::string& s, const char* tag, const std::string& v) { s.push_back(tag[0]); s.push_back(tag[1]); s.push_back('Z'); s.append(v.c_str(), v.size() + 1); }
+inline int reg2bin(int beg, int end) {  // BAMfunctions.cpp:95-104
+    --end;
+    if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+    if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+    if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+    if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+    if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+    return 0;
+}
+inline uint8_t nuclToNumBAM(char cc) {  // =ACMGRSVTWYHKDBN
+    switch (cc) {
+        case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': case 'm': return 3;
+        case 'G': case 'g': return 4; case 'R': case 'r': return 5; case 'S': case 's': return 6; case 'V': case 'v': return 7;
+        case 'T': case 't': return 8; case 'W': case 'w': return 9; case 'Y': case 'y': return 10; case 'H': case 'h': return 11;
+        case 'K': case 'k': return 12; case 'D': case 'd': return 13; case 'B': case 'b': return 14; default: return 15;
+    }
+}
+// name | cigar | packed seq | qual | attributes after the 9-word core; block_size is patched at the end
+void bamFinish(std::string& bam, size_t rec0) {
+    uint32_t sz = (uint32_t)(bam.size() - rec0 - 4);
+    memcpy(&bam[rec0], &sz, 4);
+}
+void bamSeqQual(std::string& bam, const char* seq, const char* qual, size_t L, bool fastqQual) {
+    for (size_t jj = 0; jj < L / 2; jj++) bam.push_back((char)(nuclToNumBAM(seq[2 * jj]) << 4 | nuclToNumBAM(seq[2 * jj + 1])));
+    if (L % 2 == 1) bam.push_back((char)(nuclToNumBAM(seq[L - 1]) << 4));
+    if (fastqQual) for (size_t ii = 0; ii < L; ii++) bam.push_back((char)(qual[ii] - 33));
+    else bam.append(L, (char)0xFF);
+}
+}  // namespace
+
+void OutputWriter::bamUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* tr, int unmapType,
+                               const bool* mateMap, std::string& bam) const {
+    const char* name = c.names.data() + c.nameOff[i];
+    const size_t nameLen = strlen(name);
+    for (unsigned imate = 0; imate < c.nMates; imate++) {
+        if (mateMap[imate]) continue;   // this mate was mapped, do not record it as unmapped (:121)
+        unsigned flag = 0x4;
+        uint32_t mateChr = 0xFFFFFFFFu, mateStart = 0xFFFFFFFFu;
+        if (c.nMates == 2) {
+            flag |= 0x1 + (imate == 0 ? 0x40 : 0x80);
+            if (mateMap[1 - imate]) {
+                if (tr->Str != (1 - imate)) flag |= 0x20;
+                mateChr = tr->Chr;
+                mateStart = (uint32_t)(tr->exG[0] - idx.chrStart[tr->Chr]);
+                if (!tr->primaryFlag && P.unmappedKeepPairs) flag |= 0x100;
+            } else {
+                flag |= 0x8;
+            }
+        }
+        if (c.readFilter[i] == 'Y') flag |= 0x200;
+        std::string at;
+        attrInt(at, "NH", 0); attrInt(at, "HI", 0);
+        attrInt(at, "AS", tr ? tr->maxScore : r.bestScore);
+        attrInt(at, "nM", tr ? (long long)tr->nMM : (long long)r.bestNMM);
+        attrChar(at, "uT", std::to_string((unsigned)unmapType).at(0));
+        if (!P.outSAMattrRG.empty()) attrStr(at, "RG", P.outSAMattrRG);
+        const uint64_t a = c.seqOff[(uint64_t)i * c.nMates + imate], b = c.seqOff[(uint64_t)i * c.nMates + imate + 1];
+        const size_t rec0 = bam.size();
+        put32(bam, 0);
+        put32(bam, 0xFFFFFFFFu);                                         // refID
+        put32(bam, 0xFFFFFFFFu);                                         // pos
+        put32(bam, (uint32_t)(reg2bin(-1, 0) << 16 | (uint32_t)(nameLen + 1)));
+        put32(bam, (((flag & P.outSAMflagAND) | P.outSAMflagOR) << 16) | 0u);
+        put32(bam, (uint32_t)(b - a));
+        put32(bam, mateChr < idx.chrName.size() ? mateChr : 0xFFFFFFFFu);
+        put32(bam, mateChr < idx.chrName.size() ? mateStart : 0xFFFFFFFFu);
+        put32(bam, 0);
+        bam.append(name, nameLen + 1);
+        bamSeqQual(bam, c.seq.data() + a, c.qual.data() + a, b - a, c.fastq && P.outSAMmode != "NoQS");
+        bam += at;
+        bamFinish(bam, rec0);
+    }
+}
+
+void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
+                             std::string& bam) const {
+    const char* name = c.names.data() + c.nameOff[i];
+    const size_t nameLen = strlen(name);
+    const bool flagPaired = c.nMates == 2;
+    const uint64_t Lread = r.Lread;
+    uint64_t readLength[2];
+    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
+    readLength[1] = flagPaired ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    uint32_t iExMate;
+    unsigned nMates = 1;
+    for (iExMate = 0; iExMate + 1 < tr.nExons; iExMate++) {
+        if (tr.canonSJ[iExMate] == -3) { nMates = 2; break; }
+    }
+    const unsigned Str = tr.Str;
+    const unsigned leftMate = flagPaired ? Str : 0;
+    const uint64_t chrStart = idx.chrStart[tr.Chr];
+    // CIGARs of both mates first (MC needs the other mate's), packed and as text (ReadAlign_calcCIGAR.cpp:3-60)
+    std::vector<uint32_t> packed[2];
+    std::string cigarText[2];
+    std::vector<char> sjMotif[2];
+    std::vector<int32_t> sjIntron[2];
+    uint32_t ex1[2] = {0, 0}, ex2[2] = {0, 0};
+    unsigned mateOf[2] = {0, 0};
+    for (unsigned imate = 0; imate < nMates; imate++) {
+        const uint32_t iEx1 = (imate == 0 ? 0 : iExMate + 1), iEx2 = (imate == 0 ? iExMate : tr.nExons - 1);
+        ex1[imate] = iEx1; ex2[imate] = iEx2;
+        const unsigned Mate = tr.exFrag[iEx1];
+        mateOf[imate] = Mate;
+        auto op = [&](uint64_t len, unsigned code, char ch) { packed[imate].push_back((uint32_t)(len << 4 | code)); putU(cigarText[imate], len); cigarText[imate].push_back(ch); };
+        const uint64_t trimL1 = (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
+        if (trimL1 > 0) op(trimL1, 4, 'S');
+        for (uint32_t ii = iEx1; ii <= iEx2; ii++) {
+            if (ii > iEx1) {
+                const uint64_t gapG = tr.exG[ii] - (tr.exG[ii - 1] + tr.exL[ii - 1]);
+                const uint64_t gapR = (uint64_t)tr.exR[ii] - tr.exR[ii - 1] - tr.exL[ii - 1];
+                if (gapR > 0) op(gapR, 1, 'I');
+                if (tr.canonSJ[ii - 1] >= 0 || tr.sjAnnot[ii - 1] == 1) {
+                    op(gapG, 3, 'N');
+                    sjMotif[imate].push_back((char)(tr.canonSJ[ii - 1] + (tr.sjAnnot[ii - 1] == 0 ? 0 : 20)));
+                    sjIntron[imate].push_back((int32_t)(tr.exG[ii - 1] + tr.exL[ii - 1] + 1 - chrStart));
+                    sjIntron[imate].push_back((int32_t)(tr.exG[ii] - chrStart));
+                } else if (gapG > 0) {
+                    op(gapG, 2, 'D');
+                }
+            }
+            if (tr.exL[ii] > 0) op(tr.exL[ii], 0, 'M');   // 0-length blocks are not recorded in BAM (:276)
+        }
+        if (sjMotif[imate].empty()) { sjMotif[imate].push_back(-1); sjIntron[imate].push_back(-1); }
+        const uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLength[leftMate] : readLength[leftMate] + 1 + readLength[Mate]) - tr.exR[iEx2] - tr.exL[iEx2];
+        if (trimR1 > 0) op(trimR1, 4, 'S');
+    }
+    std::string rc, rq;
+    for (unsigned imate = 0; imate < nMates; imate++) {
+        const uint32_t iEx1 = ex1[imate], iEx2 = ex2[imate];
+        const unsigned Mate = mateOf[imate];
+        unsigned samFLAG = 0;
+        if (flagPaired) {
+            samFLAG = 0x0001;
+            if (iExMate == tr.nExons - 1) samFLAG |= 0x0008;   // single mate: mateChr = (uint)-1 > nChrReal
+            else samFLAG |= 0x0002;                             // (alignBAM marks every two-mate transcript as proper pair, :187-189)
+        }
+        if (c.readFilter[i] == 'Y') samFLAG |= 0x200;
+        if (!tr.primaryFlag) samFLAG |= 0x100;
+        if (Mate == 0) {
+            samFLAG |= Str * 0x10;
+            if (nMates == 2) samFLAG |= (1 - Str) * 0x20;
+        } else {
+            samFLAG |= (1 - Str) * 0x10;
+            if (nMates == 2) samFLAG |= Str * 0x20;
+        }
+        if (flagPaired) samFLAG |= (Mate == 0 ? 0x0040 : 0x0080);
+        int MAPQ = P.outSAMmapqUnique;
+        if (nTrOut >= 5) MAPQ = 0; else if (nTrOut >= 3) MAPQ = 1; else if (nTrOut == 2) MAPQ = 3;
+        // attributes
+        uint64_t tagNM = 0;
+        std::string tagMD;
+        bool needNM = false;
+        for (int code : P.outSAMattrOrder) if (code == ATTR_NM || code == ATTR_MD) needNM = true;
+        if (needNM) {  // samAttrNM_MD, ReadAlign_alignBAM.cpp:9-45
+            std::string R(Lread, (char)4);
+            auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
+            const uint64_t a0 = c.seqOff[(uint64_t)i * c.nMates], a1 = c.seqOff[(uint64_t)i * c.nMates + 1];
+            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[a0 + k]);
+            if (flagPaired) {
+                R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
+                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[a1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+            }
+            if (tr.roStr != 0) {
+                std::string R2(Lread, (char)4);
+                for (uint64_t k = 0; k < Lread; k++) { char ch = R[k]; R2[Lread - 1 - k] = ch < 4 ? 3 - ch : ch; }
+                R.swap(R2);
+            }
+            static const char numToNT[6] = {'A', 'C', 'G', 'T', 'N', 'N'};
+            uint64_t matchN = 0, nMM = 0, nI = 0, nD = 0;
+            for (uint32_t iex = iEx1; iex <= iEx2; iex++) {
+                for (uint64_t ii = 0; ii < tr.exL[iex]; ii++) {
+                    const char r1 = R[ii + tr.exR[iex]];
+                    const char g1 = (char)idx.view.G[ii + tr.exG[iex]];
+                    if (r1 != g1 || r1 == 4 || g1 == 4) {
+                        ++nMM;
+                        tagMD += std::to_string(matchN);
+                        tagMD.push_back(numToNT[(uint8_t)g1 < 6 ? (uint8_t)g1 : 5]);
+                        matchN = 0;
+                    } else {
+                        matchN++;
+                    }
+                }
+                if (iex < iEx2) {
+                    if (tr.canonSJ[iex] < 0) nD += tr.exG[iex + 1] - (tr.exG[iex] + tr.exL[iex]);   // indels; junctions are not in the edit distance
+                    nI += (uint64_t)tr.exR[iex + 1] - tr.exR[iex] - tr.exL[iex];
+                    if (tr.canonSJ[iex] == -1) {
+                        tagMD += std::to_string(matchN) + "^";
+                        for (uint64_t ii = tr.exG[iex] + tr.exL[iex]; ii < tr.exG[iex + 1]; ii++) tagMD.push_back(numToNT[idx.view.G[ii] < 6 ? idx.view.G[ii] : 5]);
+                        matchN = 0;
+                    }
+                }
+            }
+            tagMD += std::to_string(matchN);
+            tagNM = nMM + nI + nD;
+        }
+        std::string at;
+        for (int code : P.outSAMattrOrder) {
+            switch (code) {
+                case ATTR_NH: attrInt(at, "NH", (long long)nTrOut); break;
+                case ATTR_HI: attrInt(at, "HI", (long long)(iTrOut + P.outSAMattrIHstart)); break;
+                case ATTR_AS: attrInt(at, "AS", tr.maxScore); break;
+                case ATTR_nM: attrInt(at, "nM", (long long)tr.nMM); break;
+                case ATTR_jM: {
+                    at += "jMBc"; put32(at, (uint32_t)sjMotif[imate].size()); at.append(sjMotif[imate].data(), sjMotif[imate].size());
+                    break;
+                }
+                case ATTR_jI: {
+                    at += "jIBi"; put32(at, (uint32_t)sjIntron[imate].size()); at.append((const char*)sjIntron[imate].data(), 4 * sjIntron[imate].size());
+                    break;
+                }
+                case ATTR_XS:
+                    if (tr.sjMotifStrand == 1) attrChar(at, "XS", '+');
+                    else if (tr.sjMotifStrand == 2) attrChar(at, "XS", '-');
+                    break;
+                case ATTR_NM: attrInt(at, "NM", (long long)tagNM); break;
+                case ATTR_MD: attrStr(at, "MD", tagMD); break;
+                case ATTR_RG: attrStr(at, "RG", P.outSAMattrRG); break;
+                case ATTR_MC: if (nMates > 1) attrStr(at, "MC", cigarText[1 - imate]); break;
+                default: break;   // ch: chimeric alignments only
+            }
+        }
+        // sequence / qualities in alignment orientation
+        const uint64_t a = c.seqOff[(uint64_t)i * c.nMates + Mate], b = c.seqOff[(uint64_t)i * c.nMates + Mate + 1];
+        const char* seqOut = c.seq.data() + a;
+        const char* qualOut = c.qual.data() + a;
+        if (Mate != Str) {
+            revComplement(c.seq.data() + a, b - a, rc);
+            rq.assign(b - a, 'A');
+            if (c.fastq) for (uint64_t k = 0; k < b - a; k++) rq[k] = c.qual[b - 1 - k];
+            seqOut = rc.data(); qualOut = rq.data();
+        }
+        const uint64_t gBeg = tr.exG[iEx1] - chrStart, gEnd = tr.exG[iEx2] + tr.exL[iEx2] - chrStart;
+        const size_t rec0 = bam.size();
+        put32(bam, 0);
+        put32(bam, tr.Chr);
+        put32(bam, (uint32_t)gBeg);
+        put32(bam, (uint32_t)(reg2bin((int)gBeg, (int)gEnd) << 16) | (uint32_t)(MAPQ << 8) | (uint32_t)(nameLen + 1));
+        put32(bam, (((samFLAG & P.outSAMflagAND) | P.outSAMflagOR) << 16) | (uint32_t)packed[imate].size());
+        put32(bam, (uint32_t)(b - a));
+        if (nMates > 1) {
+            put32(bam, tr.Chr);
+            put32(bam, (uint32_t)(tr.exG[(imate == 0 ? iExMate + 1 : 0)] - chrStart));
+            const int32_t tlen = (int32_t)(tr.exG[tr.nExons - 1] + tr.exL[tr.nExons - 1] - tr.exG[0]);
+            put32(bam, (uint32_t)(imate == 0 ? tlen : -tlen));
+        } else {
+            put32(bam, 0xFFFFFFFFu); put32(bam, 0xFFFFFFFFu); put32(bam, 0);
+        }
+        bam.append(name, nameLen + 1);
+        bam.append((const char*)packed[imate].data(), 4 * packed[imate].size());
+        bamSeqQual(bam, seqOut, qualOut, b - a, c.fastq && P.outSAMmode != "NoQS");
+        bam += at;
+        bamFinish(bam, rec0);
+    }
+}
+
+std::string OutputWriter::bamHeader() const {  // BAMfunctions.cpp:77-92
+    std::string h = "BAM\001";
+    const std::string text = samHeader();
+    put32(h, (uint32_t)text.size());
+    h += text;
+    put32(h, (uint32_t)idx.chrName.size());
+    for (size_t ii = 0; ii < idx.chrName.size(); ii++) {
+        put32(h, (uint32_t)(idx.chrName[ii].size() + 1));
+        h.append(idx.chrName[ii].c_str(), idx.chrName[ii].size() + 1);
+        put32(h, (uint32_t)idx.chrLength[ii]);
+    }
+    return h;
+}
+
+// BGZF: gzip members with the 'BC' extra field holding the block size; payload <= 0xff00 bytes so that a block always fits 64 KB
+void OutputWriter::bgzfCompress(const char* data, size_t n, int level, std::string& out) {
+    const size_t BLOCK = 0xff00;
+    std::vector<unsigned char> buf(0x10000 + 1024);
+    for (size_t off = 0; off < n || (n == 0 && off == 0); off += BLOCK) {
+        if (n == 0) break;
+        const size_t len = std::min(BLOCK, n - off);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = (Bytef*)(data + off); zs.avail_in = (uInt)len;
+        zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
+        deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)(data + off), (uInt)len);
+        const uint16_t bsize = (uint16_t)(clen + 25);   // total block size - 1 (18 header + clen + 8 trailer - 1)
+        static const unsigned char hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        out.append((const char*)hdr, 16);
+        out.append((const char*)&bsize, 2);
+        out.append((const char*)buf.data(), clen);
+        out.append((const char*)&crc, 4);
+        const uint32_t isize = (uint32_t)len;
+        out.append((const char*)&isize, 4);
+    }
+}
+
+const char* OutputWriter::bgzfEofBlock(size_t& n) {
+    static const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    n = 28;
+    return (const char*)eof;
+}
+
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
                                std::vector<Junction>& sj, Stats& st) const {
@@ -346,19 +670,24 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                 bool mm1[2] = {false, false};
                 mm1[trs[k].exFrag[0]] = true;
                 mm1[trs[k].exFrag[trs[k].nExons - 1]] = true;
-                if (samYes) {
+                if (samYes && !P.outBAMunsorted) {
                     samMapped(c, i, r, trs[k], nTr, k, sam);
                     if (P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) samUnmapped(c, i, r, &trs[k], 4, mm1, sam);
+                } else if (samYes) {   // ReadAlign_outputAlignments.cpp:183-197
+                    bamMapped(c, i, r, trs[k], nTr, k, sam);
+                    if (P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) bamUnmapped(c, i, r, &trs[k], 4, mm1, sam);
                 }
             }
             const star_align_t& best = trs[r.bestTr];
             mateMapped[best.exFrag[0]] = true;
             mateMapped[best.exFrag[best.nExons - 1]] = true;
             if (c.nMates > 1 && !(mateMapped[0] && mateMapped[1])) unmapType = 4;
-            if (unmapType == 4 && P.unmappedWithin && samYes && !P.unmappedKeepPairs) samUnmapped(c, i, r, &best, 4, mateMapped, sam);
+            if (unmapType == 4 && P.unmappedWithin && samYes && !P.unmappedKeepPairs) {
+                if (P.outBAMunsorted) bamUnmapped(c, i, r, &best, 4, mateMapped, sam); else samUnmapped(c, i, r, &best, 4, mateMapped, sam);
+            }
         } else if (P.unmappedWithin && samYes) {
             bool mateMapped[2] = {false, false};
-            samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
+            if (P.outBAMunsorted) bamUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam); else samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
         }
         if (unmapType >= 0) st.unmappedAll++;
     }

@@ -94,7 +94,7 @@ const char* kUnsupported[] = {
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitGenomeGenerateRAM", "limitIObufferSize",
     "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitSjdbInsertNsj", "limitNreadsSoft",
     "outTmpDir", "outTmpKeep", "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
-    "outSAMfilter", "outSAMtlen", "outBAMcompression", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
+    "outSAMfilter", "outSAMtlen", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
@@ -174,6 +174,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     tab["runThreadN"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.runThreadN) && P.runThreadN > 0; }};
     tab["readMapNumber"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.readMapNumber); }};
     tab["outSAMattrIHstart"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMattrIHstart); }};
+    tab["outBAMcompression"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outBAMcompression); }};
     tab["outSAMmapqUnique"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMmapqUnique); }};
     tab["outSAMflagOR"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagOR); }};
     tab["outSAMflagAND"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagAND); }};
@@ -304,8 +305,18 @@ int finalizeParams(HostParams& P, std::string& err) {
         return bad("EXITING because of FATAL INPUT error: unknown value for the option --outSAMprimaryFlag=" + P.outSAMprimaryFlag + "\nSOLUTION: re-run STAR with --outSAMprimaryFlag OneBestScore -OR- AllBestScore\n");
     // output type
     if (P.outSAMtype[0] == "None" || P.outSAMmode == "None") {}
-    else if (P.outSAMtype[0] != "SAM")
-        return bad("EXITING because of fatal input ERROR: --outSAMtype " + P.outSAMtype[0] + " is not supported yet by star-b200 (SAM or None; BAM is SURVEY.md §8f N1)\n");
+    else if (P.outSAMtype[0] == "BAM") {   // Parameters.cpp:613-660
+        if (P.outSAMtype.size() < 2)
+            return bad("EXITING because of fatal PARAMETER error: missing BAM option\nSOLUTION: re-run STAR with one of the allowed values of --outSAMtype BAM Unsorted OR SortedByCoordinate OR both\n");
+        for (size_t ii = 1; ii < P.outSAMtype.size(); ii++) {
+            if (P.outSAMtype[ii] == "Unsorted") P.outBAMunsorted = true;
+            else if (P.outSAMtype[ii] == "SortedByCoordinate")
+                return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported yet by star-b200 (Unsorted is; coordinate sorting is SURVEY.md §8f N4)\n");
+            else
+                return bad("EXITING because of fatal input ERROR: unknown value for the word " + std::to_string(ii + 1) + " of outSAMtype: " + P.outSAMtype[ii] + "\nSOLUTION: re-run STAR with one of the allowed values of --outSAMtype BAM Unsorted or SortedByCoordinate or both\n");
+        }
+    } else if (P.outSAMtype[0] != "SAM")
+        return bad("EXITING because of fatal input ERROR: unknown value for the first word of outSAMtype: " + P.outSAMtype[0] + "\nSOLUTION: re-run STAR with one of the allowed values of outSAMtype: BAM or SAM \n");
     if (P.outSAMmode != "Full" && P.outSAMmode != "NoQS" && P.outSAMmode != "None")
         return bad("EXITING because of FATAL input ERROR: unknown value for the option --outSAMmode=" + P.outSAMmode + "\nSOLUTION: use one of the allowed values: None or Full or NoQS\n");
     if (P.outSAMorder != "Paired")
