@@ -307,7 +307,9 @@ def main():
                     "stitch_kernel_ms": stitch_ms / a.steps}
         # ---- cpu baseline: the unmodified reference on all host cores, bounded sample
         cpu = None
-        if os.path.exists(REF_STAR):
+        if world > 1:
+            cpu = None   # the CPU baseline is timed at N=1 only (rank 0)
+        elif os.path.exists(REF_STAR):
             rp = min(a.ref_pairs, n)
             rep = max(1, a.ref_repeat)
             fq1, fq2 = os.path.join(workdir, "cpu_1.fq"), os.path.join(workdir, "cpu_2.fq")
