@@ -123,6 +123,15 @@ class ReadsReader {
     size_t bpos[2] = {0, 0}, blen[2] = {0, 0};
     bool getLine(int m, std::string& line);
     int peekChar(int m);
+    // fast path: plain (not piped) 4-line FASTQ files are memory-mapped; a chunk is line-indexed per mate and parsed by runThreadN threads
+    bool fast = false;
+    const char* map[2] = {nullptr, nullptr};
+    size_t mapSize[2] = {0, 0}, mapOff[2] = {0, 0};
+    long long nextFast(ReadChunk& c, uint32_t maxReads, std::string& err);
+    std::vector<ReadChunk> parts_;                       // per-thread pieces, kept between chunks (their buffers stay mapped)
+    std::vector<const char*> lineSt_[2], lineEn_[2];     // line index of the current chunk
+    // parses one FASTQ record given its four lines of each mate (pointers into the mapped files); appends to `c`; returns 0 or -STAR_EXIT_*
+    int parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls, const char* const* le, std::string& err) const;
 };
 
 // Stats.h:11-24

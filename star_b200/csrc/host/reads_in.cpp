@@ -5,20 +5,80 @@
 // the 2nd token, sequence / '+' / quality lines with one trailing control character removed) and of readLoad
 // (readLoad.cpp:4-100: name cut at --readNameSeparator, length checks).  Names and qualities stay on the host;
 // only the sequences go to the engine.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "host.h"
 
 namespace starhost {
 
 ReadsReader::~ReadsReader() {
-    for (int m = 0; m < 2; m++)
+    for (int m = 0; m < 2; m++) {
         if (f[m]) { if (piped[m]) pclose(f[m]); else fclose(f[m]); }
+        if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]);
+    }
+}
+
+// Maps a plain file read-only; returns false when the fast path does not apply (empty file, not a regular file, mmap failure).
+static bool mapFile(const std::string& path, const char*& ptr, size_t& size) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size == 0) { ::close(fd); return false; }
+    void* p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (p == MAP_FAILED) return false;
+    madvise(p, (size_t)st.st_size, MADV_SEQUENTIAL);
+    ptr = (const char*)p; size = (size_t)st.st_size;
+    return true;
+}
+
+// start of line number `line` (0-based) counted from `off`; = size when the file has fewer lines
+static size_t skipLines(const char* base, size_t size, size_t off, uint64_t line) {
+    while (line > 0 && off < size) {
+        const char* q = (const char*)memchr(base + off, '\n', size - off);
+        if (!q) return size;
+        off = (size_t)(q - base) + 1;
+        line--;
+    }
+    return off;
 }
 
 int ReadsReader::open(const HostParams& Pin, std::string& err) {
     P = &Pin;
     nMates = Pin.readNmates;
+    if (Pin.readFilesCommand[0] == "-" && !fast) {   // plain files: 4-line FASTQ goes through the memory-mapped parallel parser
+        bool ok = true;
+        for (unsigned m = 0; m < nMates && ok; m++) ok = mapFile(Pin.readFilesIn[m], map[m], mapSize[m]);
+        ok = ok && map[0][0] == '@';
+        if (ok) {
+            fast = true;
+            mapOff[0] = mapOff[1] = 0;
+            if (Pin.gpuShardCount > 1) {   // contiguous slice by record index: count the lines of mate 1 once
+                uint64_t lines = 0;
+                for (size_t off = 0; off < mapSize[0];) {
+                    const char* q = (const char*)memchr(map[0] + off, '\n', mapSize[0] - off);
+                    lines++;
+                    if (!q) break;
+                    off = (size_t)(q - map[0]) + 1;
+                }
+                const uint64_t nRec = lines / 4;
+                shardLo = nRec * Pin.gpuShardIndex / Pin.gpuShardCount;
+                shardHi = nRec * (Pin.gpuShardIndex + 1) / Pin.gpuShardCount;
+                for (unsigned m = 0; m < nMates; m++) mapOff[m] = skipLines(map[m], mapSize[m], 0, 4 * shardLo);
+                iReadAll = shardLo;
+            }
+            return 0;
+        }
+        for (unsigned m = 0; m < nMates; m++) { if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]); map[m] = nullptr; mapSize[m] = 0; }
+    }
     for (unsigned m = 0; m < nMates; m++) {
         if (Pin.readFilesCommand[0] != "-") {  // Parameters_openReadsFiles.cpp:83-101 pipes the command's stdout
             std::string cmd;
@@ -107,7 +167,170 @@ static inline void stripEndControl(std::string& s) {  // fastqReadOneLine :284-2
     if (!s.empty() && (int)(signed char)s.back() < 33) s.pop_back();
 }
 
+// One FASTQ record from its line pointers: ls/le[4*m + k] = start / end (newline excluded) of line k of mate m; a missing line has
+// ls == nullptr.  Same text rules and error messages as the stream parser below.
+int ReadsReader::parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls, const char* const* le, std::string& err) const {
+    auto strip = [](const char* s, const char*& e) { if (e > s && (int)(signed char)e[-1] < 33) e--; };   // removeStringEndControl
+    const char* s0 = ls[0];
+    const char* e0 = le[0];
+    const char* t = s0;
+    while (t < e0 && !isspace((unsigned char)*t)) t++;
+    const char* idEnd = t;
+    strip(s0, idEnd);
+    char passFilter = 'N';
+    {
+        const char* q0 = t;
+        while (q0 < e0 && isspace((unsigned char)*q0)) q0++;
+        const char* q1 = q0;
+        while (q1 < e0 && !isspace((unsigned char)*q1)) q1++;
+        if (t < e0 && q1 - q0 >= 3 && q0[1] == ':' && q0[2] == 'Y' && (q1 - q0 > 3 ? q0[3] : '\0') == ':') passFilter = 'Y';
+    }
+    std::string readID = P->outSAMreadID == "Number" ? std::string("@") + std::to_string(iRead) : std::string(s0, idEnd);
+    const char* sq[2] = {nullptr, nullptr};
+    const char* sqe[2] = {nullptr, nullptr};
+    const char* ql[2] = {nullptr, nullptr};
+    const char* qle[2] = {nullptr, nullptr};
+    for (unsigned m = 0; m < nMates; m++) {
+        if (!ls[4 * m + 1]) { err = "EXITING because of FATAL ERROR in reads input: unexpected end of file\n"; return -STAR_EXIT_INPUT_FILES; }
+        sq[m] = ls[4 * m + 1]; sqe[m] = le[4 * m + 1];
+        strip(sq[m], sqe[m]);
+        if (ls[4 * m + 3]) { ql[m] = ls[4 * m + 3]; qle[m] = le[4 * m + 3]; strip(ql[m], qle[m]); } else { ql[m] = qle[m] = sq[m]; }
+        const uint64_t Lr = (uint64_t)(sqe[m] - sq[m]);
+        if (Lr < 1) {
+            err = "EXITING because of FATAL ERROR in reads input: short read sequence line: " + std::to_string(Lr) + "\nRead Name=" + readID + "\nRead Sequence=\"" + std::string(sq[m], sqe[m]) + "\"\nDEF_readNameLengthMax=50000\nDEF_readSeqLengthMax=650\n";
+            return -STAR_EXIT_INPUT_FILES;
+        }
+        if (Lr > STAR_READ_SEQ_LENGTH_MAX) {
+            err = "EXITING because of FATAL ERROR in reads input: Lread>=" + std::to_string(Lr) + "   while DEF_readSeqLengthMax=650\nRead Name=" + readID + "\nSOLUTION: increase DEF_readSeqLengthMax in IncludeDefine.h and re-compile STAR\n";
+            return -STAR_EXIT_INPUT_FILES;
+        }
+        if ((uint64_t)(qle[m] - ql[m]) != Lr) {
+            err = "EXITING because of FATAL ERROR in reads input: quality string length is not equal to sequence length\n" + readID + "\n" + std::string(sq[m], sqe[m]) + "\n" + std::string(ql[m], qle[m]) + "\nSOLUTION: fix your fastq file\n";
+            return -STAR_EXIT_INPUT_FILES;
+        }
+    }
+    if (nMates == 2 && (uint64_t)(sqe[0] - sq[0]) + (uint64_t)(sqe[1] - sq[1]) + 1 > STAR_READ_SEQ_LENGTH_MAX) {
+        err = "EXITING because of FATAL ERROR in reads input: Lread of the pair = " + std::to_string((sqe[0] - sq[0]) + (sqe[1] - sq[1]) + 1) + "   while DEF_readSeqLengthMax=650\nRead Name=" + readID + "\nSOLUTION: increase DEF_readSeqLengthMax in IncludeDefine.h and re-compile STAR\n";
+        return -STAR_EXIT_INPUT_FILES;
+    }
+    for (unsigned m = 0; m < nMates; m++) {
+        c.seq.append(sq[m], sqe[m]);
+        c.qual.append(ql[m], qle[m]);
+        c.seqOff.push_back(c.seq.size());
+    }
+    {
+        std::string full = readID;
+        for (char sc : P->readNameSeparatorChar) {
+            size_t pos = full.find(sc);
+            if (pos != std::string::npos) full.resize(pos);
+        }
+        if (full.size() > 0) c.names.append(full, 1, std::string::npos);
+    }
+    c.names.push_back('\0');
+    c.nameOff.push_back((uint32_t)c.names.size());
+    c.readFilter.push_back(passFilter);
+    c.iReadAll.push_back(iRead);
+    c.nReads++;
+    return 0;
+}
+
+// Memory-mapped chunk: (A) one thread per mate indexes the lines of the next records, (B) runThreadN threads parse contiguous
+// record ranges into private pieces, (C) the pieces are concatenated in order.  Output identical to the stream parser.
+long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& err) {
+    c.clear();
+    c.nMates = nMates;
+    c.fastq = true;
+    c.seqOff.push_back(0);
+    c.nameOff.push_back(0);
+    uint64_t want = maxReads;
+    if (P->readMapNumber >= 0) want = std::min<uint64_t>(want, (uint64_t)P->readMapNumber > iReadAll ? (uint64_t)P->readMapNumber - iReadAll : 0);
+    if (shardHi != ~0ULL) want = std::min<uint64_t>(want, shardHi > iReadAll ? shardHi - iReadAll : 0);
+    if (want == 0) return 0;
+    auto T0 = std::chrono::steady_clock::now();
+    // (A) line index: starts[m][k], ends[m][k] for k < 4*want (shorter at the end of the file)
+    std::vector<const char*>* st = lineSt_;
+    std::vector<const char*>* en = lineEn_;
+    for (int m = 0; m < 2; m++) { st[m].clear(); en[m].clear(); }
+    size_t newOff[2] = {mapOff[0], mapOff[1]};
+    auto indexMate = [&](unsigned m) {
+        st[m].reserve(4 * want); en[m].reserve(4 * want);
+        const char* base = map[m];
+        const size_t size = mapSize[m];
+        size_t off = mapOff[m];
+        for (uint64_t k = 0; k < 4 * want && off < size; k++) {
+            if (m == 0 && (k & 3) == 0 && base[off] != '@') break;   // end of the records (e.g. trailing blank line)
+            const char* q = (const char*)memchr(base + off, '\n', size - off);
+            st[m].push_back(base + off);
+            if (q) { en[m].push_back(q); off = (size_t)(q - base) + 1; }
+            else { en[m].push_back(base + size); off = size; }
+        }
+        newOff[m] = off;
+    };
+    if (nMates == 2) { std::thread t1(indexMate, 1u); indexMate(0); t1.join(); } else indexMate(0);
+    const uint64_t nRec = (st[0].size() + 3) / 4;   // a last record with missing lines is still a record (its errors are reported)
+    if (nRec == 0) return 0;
+    if (nMates == 2 && st[1].size() > 4 * nRec) {   // mate 2 was indexed further than mate 1 has records: rewind it to the record boundary
+        st[1].resize(4 * nRec); en[1].resize(4 * nRec);
+        newOff[1] = (size_t)(en[1].back() - map[1]) + (en[1].back() < map[1] + mapSize[1] ? 1 : 0);
+    }
+    auto T1 = std::chrono::steady_clock::now();
+    // (B) parallel parse
+    const int nT = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, P->runThreadN), nRec / 256 + 1));
+    if ((int)parts_.size() < nT) parts_.resize(nT);
+    std::vector<ReadChunk>& part = parts_;
+    std::vector<std::string> perr(nT);
+    std::vector<int> prc(nT, 0);
+    auto work = [&](int t) {
+        ReadChunk& pc = part[t];
+        pc.clear(); pc.nMates = nMates; pc.seqOff.push_back(0); pc.nameOff.push_back(0);
+        const uint64_t lo = nRec * t / nT, hi = nRec * (t + 1) / nT;
+        pc.seq.reserve((hi - lo) * 220); pc.qual.reserve((hi - lo) * 220); pc.names.reserve((hi - lo) * 24);
+        const char* ls[8]; const char* le[8];
+        for (uint64_t r = lo; r < hi; r++) {
+            for (unsigned m = 0; m < nMates; m++)
+                for (unsigned k = 0; k < 4; k++) {
+                    const uint64_t li = 4 * r + k;
+                    const bool have = li < st[m].size();
+                    ls[4 * m + k] = have ? st[m][li] : nullptr;
+                    le[4 * m + k] = have ? en[m][li] : nullptr;
+                }
+            int rc = parseRecord(pc, iReadAll + r + 1, ls, le, perr[t]);
+            if (rc) { prc[t] = rc; return; }
+        }
+    };
+    if (nT == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nT; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (int t = 0; t < nT; t++) if (prc[t]) { err = perr[t]; return prc[t]; }   // first error in input order
+    auto T2 = std::chrono::steady_clock::now();
+    // (C) concatenate
+    size_t totSeq = 0, totNames = 0;
+    for (int t = 0; t < nT; t++) { totSeq += part[t].seq.size(); totNames += part[t].names.size(); }
+    c.seq.reserve(totSeq); c.qual.reserve(totSeq); c.names.reserve(totNames);
+    c.seqOff.reserve(nRec * nMates + 1); c.nameOff.reserve(nRec + 1); c.readFilter.reserve(nRec); c.iReadAll.reserve(nRec);
+    for (int t = 0; t < nT; t++) {
+        ReadChunk& pc = part[t];
+        const uint64_t sb = c.seq.size();
+        const uint32_t nb = (uint32_t)c.names.size();
+        c.seq += pc.seq; c.qual += pc.qual; c.names += pc.names;
+        for (size_t k = 1; k < pc.seqOff.size(); k++) c.seqOff.push_back(sb + pc.seqOff[k]);
+        for (size_t k = 1; k < pc.nameOff.size(); k++) c.nameOff.push_back(nb + pc.nameOff[k]);
+        c.readFilter.insert(c.readFilter.end(), pc.readFilter.begin(), pc.readFilter.end());
+        c.iReadAll.insert(c.iReadAll.end(), pc.iReadAll.begin(), pc.iReadAll.end());
+        c.nReads += pc.nReads;
+    }
+    auto T3 = std::chrono::steady_clock::now();
+    if (getenv("STAR_B200_READER_DEBUG")) fprintf(stderr, "reader: index %.1f ms, parse %.1f ms (%d threads), concat %.1f ms, %llu records\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count(), nT, std::chrono::duration<double, std::milli>(T3 - T2).count(), (unsigned long long)nRec);
+    iReadAll += nRec;
+    mapOff[0] = newOff[0]; mapOff[1] = newOff[1];
+    return c.nReads;
+}
+
 long long ReadsReader::next(ReadChunk& c, uint32_t maxReads, std::string& err) {
+    if (fast) return nextFast(c, maxReads, err);
     c.clear();
     c.nMates = nMates;
     c.seqOff.push_back(0);

@@ -83,3 +83,49 @@ def test_merge_without_allreduced_counters_sums_the_shard_files(oracle, lib, gol
     assert cf.sam_body(pre + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
     assert open(pre + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
     assert cf.log_counters(pre + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+
+
+def _variant(lines, kind):
+    out = list(lines)
+    n = len(out) // 4
+    if kind == "crlf":
+        return "\r\n".join(out[:4 * n]) + "\r\n"
+    if kind == "no_final_newline":
+        return "\n".join(out[:4 * n])
+    if kind == "trailing_blank_lines":
+        return "\n".join(out[:4 * n]) + "\n\n\n"
+    if kind == "comments_and_filter_flags":
+        for r in range(n):
+            out[4 * r] = out[4 * r].split()[0] + (" 1:Y:0:ACGT" if r % 3 == 0 else " 2:N:18:ACGT extra words")
+            if r % 5 == 0:
+                out[4 * r + 1] = out[4 * r + 1].lower()
+        return "\n".join(out[:4 * n]) + "\n"
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["crlf", "no_final_newline", "trailing_blank_lines", "comments_and_filter_flags"])
+def test_mapped_file_reader_equals_the_stream_reader(oracle, golden, tmp_path, kind):
+    """Plain FASTQ files go through the memory-mapped parallel parser, piped input (--readFilesCommand) through the line-by-line stream
+    parser (the restatement of processChunks/readLoad): same records, names, filter flags, order — on awkward but legal text."""
+    files = []
+    for m in (1, 2):
+        with open(os.path.join(golden, "std_%d.fq" % m)) as f:
+            lines = f.read().split("\n")
+        while lines and lines[-1] == "":
+            lines.pop()
+        p = str(tmp_path / ("v_%d.fq" % m))
+        with open(p, "w", newline="") as f:
+            f.write(_variant(lines[:4 * 600], kind))
+        files.append(p)
+    extra = ["--gpuChunkReads", "97", "--outSAMunmapped", "Within", "--readNameSeparator", "/", "_"]
+    a, b = str(tmp_path) + "/fast.", str(tmp_path) + "/stream."
+    _cli(os.path.join(golden, "idx"), files, a, extra, threads=4)
+    _cli(os.path.join(golden, "idx"), files, b, extra + ["--readFilesCommand", "cat"], threads=4)
+    assert "reads input" in open(a + "Log.out").read()
+    sa, sb_ = cf.sam_body(a + "Aligned.out.sam"), cf.sam_body(b + "Aligned.out.sam")
+    assert len(sa) > 1000 and sa == sb_
+    assert open(a + "SJ.out.tab", "rb").read() == open(b + "SJ.out.tab", "rb").read()
+    assert cf.log_counters(a + "Log.final.out") == cf.log_counters(b + "Log.final.out")
+    if kind == "comments_and_filter_flags":
+        flags = [int(l.split(b"\t")[1]) for l in sa]
+        assert any(f & 0x200 for f in flags) and not all(f & 0x200 for f in flags)
