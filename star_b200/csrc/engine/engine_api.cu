@@ -93,8 +93,8 @@ struct star_ctx {
     // flattened heavy path (stitch_flat.cuh): setup -> sub-tree tasks -> ordered recording, each over all heavy reads of the chunk
     bool flat = false;
     FlatArgs fa{};
-    Caps recCaps; u8* d_arenaRec = nullptr; int gridRec = 0;
-    int setupCtas = 2; u8* d_arenaSetup = nullptr; int recMode = 1; int recCtas = 4; int dfsMode = 1; int dfsCtas = 2; u8* d_laneScratch = nullptr; u32 fetchMin = 1;
+    Caps recCaps; u8* d_arenaRec = nullptr;
+    int setupCtas = 3; u8* d_arenaSetup = nullptr; int recCtas = 4; int dfsCtas = 4;
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -376,22 +376,10 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
                                  + (u64)c->recCaps.maxW * 4 + 255) & ~255ULL;
         c->setupCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_SETUP_CTAS_PER_SM", 3)));
         CK(cudaMalloc(&p, (size_t)c->nSM * c->setupCtas * 4 * c->heavyCaps.arenaBytes)); c->d_arenaSetup = (u8*)p; c->owned.push_back(p);
-        c->recMode = (int)envU32("STAR_B200_FLAT_REC_MODE", 1);   // 1: one read per warp (uniform execution); 0: one read per lane
-        c->recCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", c->recMode ? 4 : 2)));
-        if (c->recMode) {
-            CK(cudaMalloc(&p, (size_t)c->nSM * c->recCtas * 4 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
-        } else {
-            int recGrid = c->nSM * c->recCtas;
-            const int needGrid = (int)std::max<u64>(1, ((u64)N + 127) / 128);
-            c->gridRec = std::min(recGrid, needGrid);
-            CK(cudaMalloc(&p, (size_t)c->gridRec * 128 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);
-        }
-        c->dfsMode = (int)envU32("STAR_B200_FLAT_DFS_MODE", 1);   // 1: one task per warp (uniform execution); 0: one task per lane
+        // persistent grids of the three flat kernels (CTAs per SM; measured sweeps in profiles/r01_summary.md)
+        c->recCtas = (int)std::min<u32>(4, std::max<u32>(2, envU32("STAR_B200_FLAT_REC_CTAS_PER_SM", 4)));
+        CK(cudaMalloc(&p, (size_t)c->nSM * c->recCtas * 4 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);   // one arena per warp
         c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", 4)));
-        c->fetchMin = envU32("STAR_B200_FLAT_FETCH_MIN", 1);
-        if (envU32("STAR_B200_FLAT_LANE_SCRATCH", 0)) {
-            CK(cudaMalloc(&p, (size_t)c->nSM * c->dfsCtas * 128 * 4096)); c->d_laneScratch = (u8*)p; c->owned.push_back(p);
-        }
     }
     CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -532,11 +520,11 @@ static int runFlat(star_ctx* c, u32 nHeavyB) {
     const u32 nRecs = nHeavyB + nHeavyX;
     if (nRecs == 0) return 0;
     CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-    launch_flat_dfs(c->dfsMode, c->dfsCtas, c->nSM, c->stream, c->ix, c->P, c->fa, c->d_counter, caps, c->d_laneScratch, c->fetchMin);
+    launch_flat_dfs(c->dfsCtas, c->nSM, c->stream, c->ix, c->P, c->fa, c->d_counter, caps);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-    launch_flat_record(c->recMode, c->recCtas, c->nSM, c->gridRec, c->stream, c->ix, c->P, c->d_info, nRecs, c->d_counter, c->d_arenaRec, c->recCaps, c->d_results, c->d_staged, c->fa);
+    launch_flat_record(c->recCtas, c->nSM, c->stream, c->ix, c->P, c->d_info, nRecs, c->d_counter, c->d_arenaRec, c->recCaps, c->d_results, c->d_staged, c->fa);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->flatUse, c->fa.bumps, 32, cudaMemcpyDeviceToHost, c->stream));

@@ -10,10 +10,10 @@
 //                       the read is exported to the flat pool in HBM: R0 | R2 | FlatWin[nWin] | Seed[nSeeds], plus one FlatTask
 //                       per prefix sub-tree of every window (task ids of a read are contiguous and ascending = the reference's
 //                       DFS order, windows in window order);
-//   flat_dfs_kernel     one LANE per task, persistent lanes, warp-aggregated global ticket: the pure part of the recursion
+//   flat_dfs_warp_kernel   one WARP per task (all lanes execute the same scalar path), global ticket: the pure part of the recursion
 //                       (stitch chain, end extension, filters, score) for every leaf of the sub-tree; surviving leaves become
 //                       16-byte candidates in the task's FlatOut (first candidate inline, more in 128-byte blocks);
-//   flat_record_kernel  one LANE per read: the reference's order-dependent part (maxScoreMate, record test, blocksOverlap dedup,
+//   flat_record_warp_kernel  one WARP per read: the reference's order-dependent part (maxScoreMate, record test, blocksOverlap dedup,
 //                       ordered insert, multMapSelect) over the candidates in window / task / leaf order.
 //
 // Results are identical to the sequential recursion for the same reason as in the heavy kernel (evalLeaf is a pure function of
@@ -182,162 +182,9 @@ __global__ void __launch_bounds__(128, MINB) flat_setup_kernel(const __grid_cons
     PROF_ADD(16, tSetup);
 }
 
-// laneScratch != NULL: the DFS transcript, the leaf copy and the undo records of a lane live in a lane-contiguous 4 KB slice of HBM
-// (whole 128-byte lines belong to one lane) instead of lane-interleaved local memory; fetchMin: lanes fetch new tasks only when at
-// least that many lanes of the warp are waiting (or none is working), which keeps neighbouring lanes on neighbouring tasks.
-#define FLAT_LANE_SCRATCH 4096
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) flat_dfs_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, FlatArgs fa, u32* __restrict__ counter, Caps caps,
-                                                             u8* __restrict__ laneScratch, u32 fetchMin) {
-    const u32 lane = threadIdx.x & 31;
-    u64 nT = fa.bumps[1];
-    if (nT > fa.maxTasks) nT = fa.maxTasks;
-    Lane ln;
-    DevTr curL, leafL;
-    Frame stackL[STAR_UNDO_DEPTH];
-    u8 phL[STAR_DFS_MAX_DEPTH + 4];
-    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
-    if (laneScratch) {
-        u8* a = laneScratch + (u64)(blockIdx.x * blockDim.x + threadIdx.x) * FLAT_LANE_SCRATCH;
-        static_assert(2 * sizeof(DevTr) + STAR_UNDO_DEPTH * sizeof(Frame) <= FLAT_LANE_SCRATCH, "lane scratch too small");
-        ln.stack = (Frame*)a; a += STAR_UNDO_DEPTH * sizeof(Frame);
-        ln.cur = (DevTr*)a; a += sizeof(DevTr);
-        ln.leaf = (DevTr*)a;
-    }
-    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
-    ln.win = nullptr; ln.wa = nullptr; ln.pool = nullptr; ln.trPtr = nullptr; ln.winBase = nullptr; ln.winN = nullptr;
-    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
-    ln.overflow = 0; ln.saEnum = 0; ln.nodes = 0; ln.leaves = 0; ln.maxScoreMate[0] = ln.maxScoreMate[1] = 0;
-    ln.Lread = 0; ln.readLength[0] = ln.readLength[1] = 0; ln.outFilterMismatchNmaxTotal = 0;
-    ln.forceDepth = 0; ln.forceBits = 0;
-    u32 ph = 0;   // 0 fetch, 1 node, 2 leaf, 3 idle
-    u64 t = 0;
-    u32 k = FLAT_NONE, lastK = FLAT_NONE;
-    u32 Chr = 0, Str = 0, nA = 0;
-    const Seed* WA = nullptr;
-    const u8* rp = nullptr;
-    u32 rs = 0, nWinK = 0;
-    u32 curBlock = FLAT_NONE, firstBlock = FLAT_NONE, nCand = 0;
-    int taskBest = 0;
-    Cand c0; c0.mask = 0; c0.trOff = FLAT_NONE; c0.score = 0; c0.iFrag = 0; c0.pad = 0;
-    u64 trCur = 0, trEnd = 0;
-    long long hc = 0, eU[3] = {0, 0, 0};
-    long long tStart = clock64();
-    #pragma unroll 1
-    for (;;) {
-        {
-            u32 mF = __ballot_sync(0xffffffffu, ph == 0), mN = __ballot_sync(0xffffffffu, ph == 1), mL = __ballot_sync(0xffffffffu, ph == 2);
-            hc++; eU[0] += __popc(mF); eU[1] += __popc(mN); eU[2] += __popc(mL);
-            if (mF && ((u32)__popc(mF) >= fetchMin || (mN | mL) == 0)) {   // warp-aggregated ticket
-                const u32 leader = __ffs(mF) - 1;
-                u32 base = 0;
-                if (lane == leader) base = atomicAdd(counter, (u32)__popc(mF));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (ph == 0) { t = (u64)base + __popc(mF & ((1u << lane) - 1)); ph = 4; }
-            }
-        }
-        if (ph == 4) {
-            ph = 0;
-            if (t >= nT) { ph = 3; }
-            else {
-                const FlatTask tk = fa.tasks[t];
-                if (tk.k != FLAT_NONE) {
-                    k = tk.k;
-                    if (k != lastK) {
-                        const FlatRec rec = fa.recs[k];
-                        ln.Lread = rec.Lread; ln.readLength[0] = rec.readLength[0]; ln.readLength[1] = rec.readLength[1];
-                        ln.outFilterMismatchNmaxTotal = rec.mmMax;
-                        rp = fa.pool + rec.poolOff;
-                        rs = flatReadStride(rec.Lread);
-                        nWinK = rec.nWin;
-                        lastK = k;
-                    }
-                    const FlatWin W = ((const FlatWin*)(rp + 2 * (u64)rs))[tk.w];
-                    Chr = W.Chr; Str = W.Str; nA = W.nWA;
-                    WA = (const Seed*)(rp + 2 * (u64)rs + (u64)nWinK * sizeof(FlatWin)) + W.seedOff;
-                    ln.R0 = rp; ln.R2 = rp + rs;
-                    ln.R = Str == 0 ? ln.R0 : ln.R2;
-                    ln.nodes = 0; ln.leaves = 0;
-                    dfsInit(ln);
-                    ln.forceDepth = W.depth;
-                    ln.forceBits = tk.bits;
-                    curBlock = FLAT_NONE; firstBlock = FLAT_NONE; nCand = 0; taskBest = 0;
-                    ph = 1;
-                }
-                // a hole (task range of a read that did not fit): fetch again in the next iteration
-            }
-        }
-        if (ph == 1) {
-            int r = dfsStep(ln, WA, nA);
-            if (r == DFS_LEAF) ph = 2;
-            else if (r == DFS_DONE) {
-                FlatOut o;
-                o.c0 = c0; o.count = nCand; o.first = firstBlock; o.nodes = (u32)ln.nodes; o.leaves = (u32)ln.leaves;
-                fa.outs[t] = o;
-                ph = 0;
-            }
-        }
-        if (ph == 2) {
-            ln.leaves++;
-            if (evalLeaf(ln, ln.leafScore, ln.leafR2, ln.leafG2, Chr, Str, Str)) {
-                const int sc = ln.leaf->h.maxScore;
-                Cand c; c.mask = ln.inclMask; c.score = (short)sc; c.iFrag = ln.leaf->h.iFrag; c.pad = 0; c.trOff = FLAT_NONE;
-                if (sc + P.outFilterMultimapScoreRange >= taskBest) {   // likely to be recorded: keep the evaluated transcript
-                    if (sc > taskBest) taskBest = sc;
-                    const u32 nEx = ln.leaf->h.nExons;
-                    const u32 words = (u32)(sizeof(TrHead) / 8) + nEx * (u32)(sizeof(Exon) / 8);
-                    if (trCur + words > trEnd) {
-                        const u64 off = atomicAdd(&fa.bumps[3], (unsigned long long)FLAT_TR_CHUNK);
-                        if (off + FLAT_TR_CHUNK <= fa.trWords && off + FLAT_TR_CHUNK < 0xFFFFFFFFULL) { trCur = off; trEnd = off + FLAT_TR_CHUNK; }
-                        else { trCur = 0; trEnd = 0; }
-                    }
-                    if (trCur + words <= trEnd) {
-                        u64* dst = fa.trStore + trCur;
-                        const u64* sh8 = (const u64*)&ln.leaf->h;
-                        #pragma unroll 1
-                        for (u32 q = 0; q < sizeof(TrHead) / 8; q++) dst[q] = sh8[q];
-                        const u64* se = (const u64*)ln.leaf->ex;
-                        #pragma unroll 1
-                        for (u32 q = 0; q < nEx * (sizeof(Exon) / 8); q++) dst[sizeof(TrHead) / 8 + q] = se[q];
-                        c.trOff = (u32)trCur;
-                        trCur += words;
-                    }
-                }
-                if (nCand == 0) {
-                    c0 = c;
-                    nCand = 1;
-                } else {
-                    bool ok = true;
-                    if (curBlock == FLAT_NONE || fa.blocks[curBlock].count == FLAT_CAND_PER_BLOCK) {
-                        const u64 nb = atomicAdd(&fa.bumps[2], 1ULL);
-                        if (nb >= fa.maxBlocks) { fa.recs[k].over = 5; ok = false; }
-                        else {
-                            fa.blocks[nb].next = FLAT_NONE; fa.blocks[nb].count = 0;
-                            if (curBlock == FLAT_NONE) firstBlock = (u32)nb; else fa.blocks[curBlock].next = (u32)nb;
-                            curBlock = (u32)nb;
-                        }
-                    }
-                    if (ok) {
-                        FlatBlock& B = fa.blocks[curBlock];
-                        B.c[B.count] = c;
-                        B.count++;
-                        nCand++;
-                    }
-                }
-            }
-            ph = 1;
-        }
-        if (__all_sync(0xffffffffu, ph == 3)) break;
-    }
-    PROF_ADD(17, clock64() - tStart);
-    PROF_ADD(21, hc);
-    #pragma unroll 1
-    for (int q = 0; q < 3; q++) PROF_ADD(22 + q, eU[q]);
-}
-
-// ---- warp-uniform variant.  Measured on B200: in flat_dfs_kernel the lanes of a warp do not overlap at all (32-task batches with 1.7
-// lanes working on average take the same time as 12 lanes working): every lane walks its own branchy path, SIMT serialises them.
-// Here a WARP owns one task at a time and all 32 lanes execute the same scalar path (no divergence, every local-memory access is
+// ---- sub-tree task kernel, warp-uniform.  Measured on B200 with one task per LANE (removed; profiles/r01_summary.md): 1.97 lanes
+// execute per instruction and 32-task batches with 1.7 working lanes take the same time as 12 working lanes — every lane walks its
+// own branchy path and SIMT serialises them.  So a WARP owns one task at a time and all 32 lanes execute the same scalar path (no divergence, every local-memory access is
 // one full 128-byte line); the DFS transcript, leaf copy and undo records are ONE copy per warp in shared memory; the byte loops
 // (end extension, junction scan, gap mismatches) are done cooperatively, 32 bases per step (coop* functions in stitch.cu).
 // Tasks are fetched 32 at a time (lane j prefetches the descriptor, read header and window of task base+j).
@@ -574,130 +421,12 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
 }
 
 // host-side launcher (the kernels are templates over the occupancy target; engine_api.cu is another translation unit)
-void launch_flat_dfs(int mode, int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps,
-                     u8* laneScratch, u32 fetchMin) {
-    if (mode == 1) {
-        const u32 smem = 4 * FLAT_WARP_SMEM;
-        if (ctasPerSM <= 4) flat_dfs_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, fa, counter, caps);
-        else if (ctasPerSM == 5) flat_dfs_warp_kernel<5><<<nSM * 5, 128, smem, stream>>>(ix, P, fa, counter, caps);
-        else if (ctasPerSM <= 6) flat_dfs_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, fa, counter, caps);
-        else flat_dfs_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, fa, counter, caps);
-        return;
-    }
-    if (ctasPerSM <= 2) flat_dfs_kernel<2><<<nSM * 2, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
-    else if (ctasPerSM == 3) flat_dfs_kernel<3><<<nSM * 3, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
-    else flat_dfs_kernel<4><<<nSM * 4, 128, 0, stream>>>(ix, P, fa, counter, caps, laneScratch, fetchMin);
-}
-
-__global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) flat_record_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, ReadInfo* __restrict__ info, u32 nRecs, u32* __restrict__ counter,
-                                                    u8* __restrict__ arenas, Caps caps, star_read_result_t* __restrict__ results,
-                                                    star_align_t* __restrict__ staged, FlatArgs fa) {
-    const u32 gthread = blockIdx.x * blockDim.x + threadIdx.x;
-    Lane ln;
-    DevTr curL, leafL;
-    Frame stackL[2];
-    u8 phL[4];
-    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
-    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
-    {   // per-lane arena: compacted window Chr/Str | transcript pool | pointer arrays
-        u8* a = arenas + (u64)gthread * caps.arenaBytes;
-        ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
-        ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
-        ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
-        ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
-        ln.winN = (u16*)a;
-        ln.wa = nullptr;
-    }
-    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
-    long long tStart = clock64();
-    long long nReplay = 0;
-    // slot table of the transcript pool: recordLeaf only ever permutes it, and which physical slot holds a transcript is irrelevant,
-    // so it is initialised once per lane and not per read
-    #pragma unroll 1
-    for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
-    #pragma unroll 1
-    for (;;) {
-        const u32 k = atomicAdd(counter, 1u);
-        if (k >= nRecs) break;
-        const FlatRec rec = fa.recs[k];
-        if (rec.done) continue;
-        const u32 i = rec.read;
-        ReadInfo ri = info[i];
-        readBegin(ln, ri);
-        ln.saEnum = rec.saEnum;
-        if (rec.over) {
-            ln.overflow = rec.over;
-        } else {
-            const u8* rp = fa.pool + rec.poolOff;
-            const u32 rs = flatReadStride(rec.Lread);
-            ln.R0 = rp; ln.R2 = rp + rs;
-            const FlatWin* fw = (const FlatWin*)(rp + 2 * (u64)rs);
-            const Seed* fs = (const Seed*)(fw + rec.nWin);
-            u64 nd = 0, lv = 0;   // work counters of the sub-tree evaluation
-            u32 tSeen = 0;        // tasks [0,tSeen) are already counted
-            #pragma unroll 1
-            for (u32 w = 0; w < rec.nWin && !ln.overflow; w++) {
-                const FlatWin W = fw[w];
-                u16* wTr = nullptr; u16 nWinTr = 0;
-                int rc = windowBegin(ln, wTr, nWinTr);
-                if (rc == 2) { ln.overflow = 3; break; }
-                if (rc == 1) break;
-                const u32 Chr = W.Chr, Str = W.Str, nA = W.nWA;
-                const Seed* WA = fs + W.seedOff;
-                ln.R = Str == 0 ? ln.R0 : ln.R2;
-                const u64 tb = (u64)rec.taskBase + W.taskStart;
-                #pragma unroll 1
-                for (u32 tq = 0; tq < (1u << W.depth) && !ln.overflow; tq++) {
-                    const FlatOut o = fa.outs[tb + tq];
-                    nd += o.nodes; lv += o.leaves; tSeen = W.taskStart + tq + 1;
-                    u32 b = o.first, inBlock = 0;
-                    #pragma unroll 1
-                    for (u32 q = 0; q < o.count; q++) {
-                        Cand c;
-                        if (q == 0) c = o.c0;
-                        else {
-                            if (inBlock == FLAT_CAND_PER_BLOCK) { b = fa.blocks[b].next; inBlock = 0; }
-                            c = fa.blocks[b].c[inBlock++];
-                        }
-                        if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
-                        int wBest = ln.pool[wTr[0]].h.maxScore;
-                        if (c.score + P.outFilterMultimapScoreRange >= wBest ||
-                            (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
-                            if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; break; }
-                            if (c.trOff != FLAT_NONE) {   // transcript stored by the lane that evaluated the leaf
-                                const u64* src = fa.trStore + c.trOff;
-                                u64* dh = (u64*)&ln.leaf->h;
-                                #pragma unroll 1
-                                for (u32 z = 0; z < sizeof(TrHead) / 8; z++) dh[z] = src[z];
-                                const u32 nEx = ln.leaf->h.nExons;
-                                u64* de = (u64*)ln.leaf->ex;
-                                #pragma unroll 1
-                                for (u32 z = 0; z < nEx * (sizeof(Exon) / 8); z++) de[z] = src[sizeof(TrHead) / 8 + z];
-                                recordLeaf(ln, wTr, &nWinTr);
-                            } else {
-                                int Score; u32 tR2; u64 tG2;
-                                nReplay++;
-                                bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
-                                if (ok) recordLeaf(ln, wTr, &nWinTr);
-                            }
-                        }
-                    }
-                }
-                windowEnd(ln, Chr, Str, wTr, nWinTr);
-            }
-            #pragma unroll 1
-            for (u32 t = tSeen; t < rec.nTasks; t++) { const FlatOut& o = fa.outs[(u64)rec.taskBase + t]; nd += o.nodes; lv += o.leaves; }   // (windows skipped by an early exit)
-            ln.nodes = nd; ln.leaves = lv;
-        }
-        selectExport(ln, ri, i, 0, 0, results, staged, info);
-    }
-    PROF_ADD(18, clock64() - tStart);
-    {
-        long long r = nReplay;
-        #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-        PROF_ADD(20, r);
-    }
+void launch_flat_dfs(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps) {
+    const u32 smem = 4 * FLAT_WARP_SMEM;
+    if (ctasPerSM <= 4) flat_dfs_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, fa, counter, caps);
+    else if (ctasPerSM == 5) flat_dfs_warp_kernel<5><<<nSM * 5, 128, smem, stream>>>(ix, P, fa, counter, caps);
+    else if (ctasPerSM <= 6) flat_dfs_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, fa, counter, caps);
+    else flat_dfs_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, fa, counter, caps);
 }
 
 // ---- warp-uniform recording kernel: one WARP per read.  All 32 lanes execute the order-dependent recording with identical state
@@ -843,16 +572,12 @@ __global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __gri
     PROF_ADD(20, nReplay);
 }
 
-void launch_flat_record(int mode, int ctasPerSM, int nSM, int gridLane, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
+void launch_flat_record(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
                         u8* arenas, const Caps& caps, star_read_result_t* results, star_align_t* staged, const FlatArgs& fa) {
-    if (mode == 1) {
-        const u32 smem = 4 * FLAT_REC_SMEM;
-        if (ctasPerSM <= 2) flat_record_warp_kernel<2><<<nSM * 2, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
-        else if (ctasPerSM == 3) flat_record_warp_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
-        else flat_record_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
-        return;
-    }
-    flat_record_kernel<<<gridLane, 128, 0, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+    const u32 smem = 4 * FLAT_REC_SMEM;
+    if (ctasPerSM <= 2) flat_record_warp_kernel<2><<<nSM * 2, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+    else if (ctasPerSM == 3) flat_record_warp_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
+    else flat_record_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
 }
 
 void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,

@@ -64,9 +64,8 @@ struct FlatArgs {
 void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
                        const Piece* pieces, u32 nHeavy, const u32* heavyList, const u64* heavyOff, const u8* heavyPool, u32* counter, u8* arenas, const Caps& caps,
                        star_read_result_t* results, star_align_t* staged, u32 smemStride, const FlatArgs& fa, u32 kBase);
-void launch_flat_dfs(int mode, int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps,
-                     u8* laneScratch, u32 fetchMin);
-void launch_flat_record(int mode, int ctasPerSM, int nSM, int gridLane, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
+void launch_flat_dfs(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps);
+void launch_flat_record(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
                         u8* arenas, const Caps& caps, star_read_result_t* results, star_align_t* staged, const FlatArgs& fa);
 
 }  // namespace starb
