@@ -15,6 +15,7 @@
  * fixtures in tests/golden/ were produced by the reference binary (tests/golden/make_golden.py).
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -692,6 +693,81 @@ struct ReadAlign {
         return i2 - i1 + 1;
     }
 
+    // ------------------------------------------------------------------------------------------------------------------
+    // Design check for the round-2 GPU seed search (test infrastructure, env STAR_ORACLE_KARY_CHECK=1): the same answer as
+    // maxMappableLength — the maximal match length L over the SA rows of the start interval and the block of rows attaining it —
+    // computed by a 32-ary search, i.e. the shape a warp executes cooperatively (32 probes per step instead of one, ~5x fewer
+    // dependent steps).  Emulated here lane by lane on the CPU and compared with the reference binary search for every search.
+    uint karyLcp(uint S, uint N, uint L, uint iSA, bool dirR, bool& compRes) {   // compareSeqToGenome without the work counters
+        const auto saved = cnt;
+        uint r = compareSeqToGenome(S, N, L, iSA, dirR, compRes);
+        cnt = saved;
+        return r;
+    }
+    uint karyMaxMappableLength(uint S, uint N, uint lo, uint hi, bool dirR, uint& L, uint* indStartEnd) {
+        const uint K = 32;
+        bool cr = false;
+        uint i1 = lo, i2 = hi;
+        uint L1 = karyLcp(S, N, L, i1, dirR, cr);
+        uint L2 = karyLcp(S, N, L, i2, dirR, cr);
+        uint i3 = i1, L3 = L1;
+        bool full = false;
+        if (L1 == N) { i3 = i1; L3 = L1; full = true; }   // (the reference would find such a row later; the block is the same)
+        else if (L2 == N) { i3 = i2; L3 = L2; full = true; }
+        while (!full && i1 + 1 < i2) {
+            const uint Lc = std::min(L1, L2);
+            const uint span = i2 - i1 - 1;                 // interior rows
+            const uint np = std::min(K, span);
+            uint pr[32], pl[32]; bool pc[32];
+            for (uint j = 0; j < np; j++) {                // one probe per lane
+                pr[j] = np == span ? i1 + 1 + j : i1 + (uint)(((unsigned __int128)(i2 - i1) * (j + 1)) / (np + 1));
+                pl[j] = karyLcp(S, N, Lc, pr[j], dirR, pc[j]);
+            }
+            int jFull = -1, jLast1 = -1;
+            for (uint j = 0; j < np; j++) {
+                if (pl[j] == N && jFull < 0) jFull = (int)j;
+                if (pl[j] != N && pc[j]) jLast1 = (int)j;  // read > suffix: the insertion point is to the right
+            }
+            if (jFull >= 0) { i3 = pr[jFull]; L3 = N; full = true; break; }
+            if (jLast1 >= 0) { i1 = pr[jLast1]; L1 = pl[jLast1]; }
+            if (jLast1 + 1 < (int)np) { i2 = pr[jLast1 + 1]; L2 = pl[jLast1 + 1]; }
+        }
+        if (!full) {
+            if (L1 > L2) { i3 = i1; L3 = L1; } else { i3 = i2; L3 = L2; }
+        }
+        // block of rows with match length >= L3 around i3, clamped to [lo, hi]: k-ary boundary searches
+        auto boundary = [&](uint inRow, uint outRow, bool left) -> uint {   // inRow has LCP >= L3; outRow (towards the interval end) is tested first
+            bool c2;
+            uint Lout = karyLcp(S, L3, L, outRow, dirR, c2);
+            if (Lout >= L3) return outRow;
+            uint a = outRow, La = Lout, b = inRow;        // a: LCP < L3, b: LCP >= L3
+            while ((left ? a + 1 < b : b + 1 < a)) {
+                const uint span = (left ? b - a : a - b) - 1;
+                const uint np = std::min(K, span);
+                uint pr[32], pl[32];
+                for (uint j = 0; j < np; j++) {
+                    const uint step = np == span ? 1 + j : (uint)(((unsigned __int128)(span + 1) * (j + 1)) / (np + 1));
+                    pr[j] = left ? a + step : a - step;
+                    bool c3;
+                    pl[j] = karyLcp(S, L3, La, pr[j], dirR, c3);
+                }
+                // rows nearer to b have LCP >= L3: first probe (from a) that reaches L3 becomes b, the one before it a
+                int jIn = -1;
+                for (uint j = 0; j < np; j++) if (pl[j] >= L3) { jIn = (int)j; break; }
+                if (jIn < 0) { a = pr[np - 1]; La = pl[np - 1]; }
+                else { b = pr[jIn]; if (jIn > 0) { a = pr[jIn - 1]; La = pl[jIn - 1]; } }
+            }
+            return b;
+        };
+        const uint b1 = i3 == lo ? lo : boundary(i3, lo, true);
+        const uint b2 = i3 == hi ? hi : boundary(i3, hi, false);
+        L = L3;
+        indStartEnd[0] = b1; indStartEnd[1] = b2;
+        return b2 - b1 + 1;
+    }
+    unsigned long long karyChecked = 0, karyMismatch = 0;
+    bool karyCheck = getenv("STAR_ORACLE_KARY_CHECK") != nullptr;
+
     // ReadAlign_storeAligns.cpp:10-160 (OPTIM_STOREaligns_SIMPLE branch :27-51)
     void storeAligns(uint iDir, uint Shift, uint Nrep, uint L, uint indStartEnd[2], uint iFrag) {
         if (Nrep > P.seedMultimapNmax) {
@@ -781,7 +857,16 @@ struct ReadAlign {
                 maxL = compareSeqToGenome(pieceStart, pieceLength, Lind, iSA1, dirR, comparRes);
             } else {
                 if (iSA2good && iSA1noN) maxL = Lind; else maxL = 0;
+                uint kL = maxL, kInd[2] = {0, 0}, kN = 0;
+                if (karyCheck) kN = karyMaxMappableLength(pieceStart, pieceLength, iSA1 & mapGen.SAiMarkNmask, iSA2, dirR, kL, kInd);
                 Nrep = maxMappableLength(pieceStart, pieceLength, iSA1 & mapGen.SAiMarkNmask, iSA2, dirR, maxL, indStartEnd);
+                if (karyCheck) {
+                    karyChecked++;
+                    if (kN != Nrep || kL != maxL || kInd[0] != indStartEnd[0] || kInd[1] != indStartEnd[1]) {
+                        if (karyMismatch++ < 5)
+                            fprintf(stderr, "KARY MISMATCH: ref L=%llu [%llu,%llu] kary L=%llu [%llu,%llu] (S=%llu N=%llu dir=%d)\n", maxL, indStartEnd[0], indStartEnd[1], kL, kInd[0], kInd[1], pieceStart, pieceLength, (int)dirR);
+                    }
+                }
             }
             if (maxL > maxLbest) maxLbest = maxL;
         }
@@ -1387,6 +1472,7 @@ struct star_oracle_ctx {
 };
 
 static thread_local std::string g_oracle_error;
+static std::atomic<unsigned long long> g_karyChecked(0), g_karyMismatch(0);
 
 extern "C" {
 
@@ -1399,6 +1485,8 @@ int star_oracle_init(void** ctx, int /*device*/, const star_index_view_t* index,
 }
 
 void star_oracle_destroy(void* ctx) { delete (star_oracle_ctx*)ctx; }
+// k-ary seed search design check (STAR_ORACLE_KARY_CHECK=1): searches compared with the reference binary search / disagreements
+void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch) { *checked = g_karyChecked.load(); *mismatch = g_karyMismatch.load(); }
 const char* star_oracle_last_error(void) { return g_oracle_error.c_str(); }
 
 static int oracle_run(star_oracle_ctx* c, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats,
@@ -1449,6 +1537,7 @@ static int oracle_run(star_oracle_ctx* c, const star_read_batch_t* in, star_alig
             }
         }
         cnts[t] = RA.cnt;
+        g_karyChecked += RA.karyChecked; g_karyMismatch += RA.karyMismatch;
         fatals[t] = RA.fatal;
         fatalMsgs[t] = RA.fatalMsg;
     };

@@ -22,6 +22,8 @@ int star_oracle_map_chunk_dump(void* ctx, const star_read_batch_t* in, star_alig
 void star_oracle_dump_free(star_oracle_dump_t* d);
 void star_oracle_destroy(void* ctx);
 const char* star_oracle_last_error(void);
+/* test-only: statistics of the k-ary search design check (env STAR_ORACLE_KARY_CHECK=1) */
+void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch);
 const star_engine_vtbl_t* star_oracle_engine(void);
 
 #ifdef __cplusplus

@@ -86,3 +86,28 @@ def test_option_sets_vs_live_reference(oracle, golden, tmp_path, base, extra):
     assert cf.sam_body(str(tmp_path / "ora" / "Aligned.out.sam")) == cf.sam_body(str(tmp_path / "ref" / "Aligned.out.sam"))
     assert open(str(tmp_path / "ora" / "SJ.out.tab"), "rb").read() == open(str(tmp_path / "ref" / "SJ.out.tab"), "rb").read()
     assert cf.log_counters(str(tmp_path / "ora" / "Log.final.out")) == cf.log_counters(str(tmp_path / "ref" / "Log.final.out"))
+
+
+@pytest.mark.parametrize("name", ["std", "hard", "se"])
+def test_kary_seed_search_design_check(oracle, lib, golden, name, monkeypatch):
+    """Design check for the next GPU seed-search kernel: a 32-ary search (the shape a warp executes cooperatively) must return the
+    same maximal match length and the same block of SA rows as the reference's binary search (SuffixArrayFuns.cpp:133-207) for every
+    search of the read set — emulated lane by lane inside the oracle (oracle/star_oracle.cpp, karyMaxMappableLength)."""
+    import ctypes as C
+    import star_b200 as sb
+    monkeypatch.setenv("STAR_ORACLE_KARY_CHECK", "1")
+    files = [os.path.join(golden, name + "_1.fq")] + ([os.path.join(golden, name + "_2.fq")] if name != "se" else [])
+    mates = [cf.read_fastq_seqs(f) for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    oracle.star_oracle_kary_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    a0, b0 = C.c_uint64(), C.c_uint64()
+    oracle.star_oracle_kary_stats(C.byref(a0), C.byref(b0))
+    oe = oc.OracleEngine(oracle, idx)
+    oe.map_chunk(seq, off, n, nm)
+    oe.close()
+    idx.close()
+    a1, b1 = C.c_uint64(), C.c_uint64()
+    oracle.star_oracle_kary_stats(C.byref(a1), C.byref(b1))
+    assert a1.value - a0.value > 1000, "the check did not run"
+    assert b1.value - b0.value == 0
