@@ -12,6 +12,7 @@
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -85,8 +86,10 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     OutputWriter W(P, idx);
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     std::ofstream samOut;
+    const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);   // Aligned.out.sam / Aligned.out.bam
     const bool bamYes = samYes && P.outBAMunsorted;
-    if (samYes) {
+    const bool coordYes = samYes && P.outBAMcoord;                                        // Aligned.sortedByCoord.out.bam, sorted at the end
+    if (streamYes) {
         samOut.open(P.outFileNamePrefix + (bamYes ? "Aligned.out.bam" : "Aligned.out.sam"), std::ios::binary);
         if (P.gpuShardIndex == 0) {   // shards > 0 write records only; the merge concatenates in shard order
             if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samOut.write(z.data(), z.size()); }
@@ -121,6 +124,10 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     Queue freeQ, mapQ, outQ;
     for (auto& wk : bufs) freeQ.push(&wk);
     std::vector<Junction> allSJ;
+    // coordinate-sorted BAM: all records stay in host memory (uncompressed, ~0.55 kB per record) until the end of the run
+    struct CoordRec { uint64_t alignG, key; uint32_t blob, size; uint64_t off; };
+    std::vector<std::string> coordBlobs;
+    std::vector<CoordRec> coordIndex;
     const int nT = std::max(1, P.runThreadN);
     double msEngine = 0, msRead = 0, msFormat = 0, msWrite = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -152,10 +159,12 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
                 std::vector<std::string> sam(nT);
                 std::vector<std::vector<Junction>> sj(nT);
                 std::vector<Stats> st(nT);
+                std::vector<std::string> cblob(coordYes ? nT : 0);
+                std::vector<std::vector<uint64_t>> ckey(coordYes ? nT : 0);
                 auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
                     uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
                     sam[t].reserve((size_t)(hi - lo) * 700);
-                    W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t]);
+                    W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr);
                     if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
                         std::string z;
                         z.reserve(sam[t].size() / 3);
@@ -173,9 +182,22 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
                 msFormat += msSince(tf0);
                 auto tw0 = now();
                 for (int t = 0; t < nT; t++) {
-                    if (samYes) samOut.write(sam[t].data(), sam[t].size());
+                    if (streamYes) samOut.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
+                    if (coordYes && !cblob[t].empty()) {   // index the records of this piece (BAMoutput::coordOneAlign: key = refID<<32 | pos)
+                        const uint32_t ib = (uint32_t)coordBlobs.size();
+                        coordBlobs.emplace_back();
+                        coordBlobs.back().swap(cblob[t]);
+                        const std::string& b = coordBlobs.back();
+                        size_t o = 0, k = 0;
+                        while (o < b.size()) {
+                            uint32_t w[3]; memcpy(w, b.data() + o, 12);
+                            CoordRec cr; cr.alignG = ((uint64_t)w[1] << 32) | w[2]; cr.key = ckey[t][k++]; cr.blob = ib; cr.size = 4 + w[0]; cr.off = o;
+                            coordIndex.push_back(cr);
+                            o += cr.size;
+                        }
+                    }
                 }
                 msWrite += msSince(tw0);
                 if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
@@ -228,7 +250,33 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     if (!outErr.empty()) { eng->destroy(ectx); return exitWithError(outErr, STAR_EXIT_BUG, &logMain); }
     eng->destroy(ectx);
     if (bamYes && P.gpuShardCount == 1) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
-    if (samYes) samOut.close();
+    if (streamYes) samOut.close();
+    if (coordYes) {
+        // bamSortByCoordinate.cpp / BAMbinSortByCoordinate.cpp:49-55 / BAMbinSortUnmapped.cpp: mapped records by (refID<<32|pos, read-order key,
+        // emission order), then the unmapped ones (refID = -1 sorts last) in read order.  The reference bins by coordinate and sorts bin by
+        // bin on disk; one stable in-memory sort gives the same sequence.
+        time_t ts; time(&ts);
+        std::cout << timeMonthDayTime(ts) << " ..... started sorting BAM\n" << std::flush;
+        std::stable_sort(coordIndex.begin(), coordIndex.end(), [](const CoordRec& a, const CoordRec& b) { return a.alignG != b.alignG ? a.alignG < b.alignG : a.key < b.key; });
+        std::ofstream cb(P.outFileNamePrefix + "Aligned.sortedByCoord.out.bam", std::ios::binary);
+        { std::string z; const std::string h = W.bamHeader(true); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); cb.write(z.data(), z.size()); }
+        const size_t nRec = coordIndex.size();
+        const size_t batch = 1u << 16;   // records per compression task
+        for (size_t base = 0; base < nRec; base += batch * (size_t)nT) {
+            std::vector<std::string> z(nT);
+            auto cw = [&](int t) {
+                const size_t lo = std::min(nRec, base + batch * (size_t)t), hi = std::min(nRec, lo + batch);
+                std::string raw;
+                for (size_t q = lo; q < hi; q++) raw.append(coordBlobs[coordIndex[q].blob], coordIndex[q].off, coordIndex[q].size);
+                OutputWriter::bgzfCompress(raw.data(), raw.size(), P.outBAMcompression, z[t]);
+            };
+            std::vector<std::thread> th;
+            for (int t = 0; t < nT; t++) th.emplace_back(cw, t);
+            for (auto& t : th) t.join();
+            for (int t = 0; t < nT; t++) cb.write(z[t].data(), z[t].size());
+        }
+        size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); cb.write(e, ne);
+    }
     time_t tFinishMap; time(&tFinishMap);
     std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
     logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";

@@ -33,6 +33,7 @@ struct HostParams {
     std::string outStd = "Log";
     std::vector<std::string> outSAMtype = {"SAM"};
     bool outBAMunsorted = false;            // --outSAMtype BAM Unsorted  -> Aligned.out.bam
+    bool outBAMcoord = false;               // --outSAMtype BAM SortedByCoordinate -> Aligned.sortedByCoord.out.bam (sorted in host memory)
     int outBAMcompression = 1;              // --outBAMcompression (zlib level of the BGZF blocks; -1 = zlib default)
     std::string outSAMmode = "Full";
     std::string outSAMstrandField = "None";
@@ -163,10 +164,12 @@ class OutputWriter {
    public:
     OutputWriter(const HostParams& P, const LoadedIndex& idx) : P(P), idx(idx) {}
     // appends SAM text for reads [lo,hi) of the chunk to `sam`, junctions to `sj`, counters to `st`
+    // coord / coordKey (may be NULL): the records for the coordinate-sorted BAM (uncompressed) and, per record, the read-order key
+    // (iReadAll<<32 | iTr<<8 | mate) of BAMoutput::coordOneAlign
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                     std::vector<Junction>& sj, Stats& st) const;
+                     std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr) const;
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
-    std::string bamHeader() const;                                   // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
+    std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`
     static void bgzfCompress(const char* data, size_t n, int level, std::string& out);
     static const char* bgzfEofBlock(size_t& n);

@@ -581,9 +581,10 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
     }
 }
 
-std::string OutputWriter::bamHeader() const {  // BAMfunctions.cpp:77-92
+std::string OutputWriter::bamHeader(bool sortedCoord) const {  // BAMfunctions.cpp:77-92
     std::string h = "BAM\001";
-    const std::string text = samHeader();
+    std::string text = samHeader();
+    if (sortedCoord) text.replace(0, strlen("@HD\tVN:1.4"), "@HD\tVN:1.4\tSO:coordinate");   // samHeaderSortedCoord, samHeaders.cpp:99
     put32(h, (uint32_t)text.size());
     h += text;
     put32(h, (uint32_t)idx.chrName.size());
@@ -630,8 +631,20 @@ const char* OutputWriter::bgzfEofBlock(size_t& n) {
 
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                               std::vector<Junction>& sj, Stats& st) const {
+                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey) const {
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    const bool coordYes = samYes && P.outBAMcoord && coord && coordKey;
+    // records appended to `dst` since `from` also go to the coordinate-sorted set with read-order key `key` (one key per record)
+    auto toCoord = [&](const std::string& dst, size_t from, uint64_t key) {
+        size_t o = from;
+        while (o < dst.size()) {
+            uint32_t bs; memcpy(&bs, dst.data() + o, 4);
+            coord->append(dst, o, 4 + (size_t)bs);
+            coordKey->push_back(key);
+            o += 4 + (size_t)bs;
+        }
+    };
+    std::string scratch;
     for (uint32_t i = lo; i < hi; i++) {
         const star_read_result_t& r = out.reads[i];
         uint64_t L0 = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
@@ -670,24 +683,40 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                 bool mm1[2] = {false, false};
                 mm1[trs[k].exFrag[0]] = true;
                 mm1[trs[k].exFrag[trs[k].nExons - 1]] = true;
-                if (samYes && !P.outBAMunsorted) {
+                if (samYes && P.outSAMtype[0] == "SAM") {
                     samMapped(c, i, r, trs[k], nTr, k, sam);
                     if (P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) samUnmapped(c, i, r, &trs[k], 4, mm1, sam);
-                } else if (samYes) {   // ReadAlign_outputAlignments.cpp:183-197
-                    bamMapped(c, i, r, trs[k], nTr, k, sam);
-                    if (P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) bamUnmapped(c, i, r, &trs[k], 4, mm1, sam);
+                } else if (samYes) {   // ReadAlign_outputAlignments.cpp:183-203
+                    std::string& dst = P.outBAMunsorted ? sam : scratch;
+                    if (!P.outBAMunsorted) scratch.clear();
+                    const size_t from = dst.size();
+                    bamMapped(c, i, r, trs[k], nTr, k, dst);
+                    if (coordYes) toCoord(dst, from, (c.iReadAll[i] << 32) | (k << 8) | trs[k].exFrag[0]);
+                    if (P.outBAMunsorted && P.unmappedKeepPairs && c.nMates > 1 && (!mm1[0] || !mm1[1])) bamUnmapped(c, i, r, &trs[k], 4, mm1, sam);   // (unsorted stream only)
                 }
             }
             const star_align_t& best = trs[r.bestTr];
             mateMapped[best.exFrag[0]] = true;
             mateMapped[best.exFrag[best.nExons - 1]] = true;
             if (c.nMates > 1 && !(mateMapped[0] && mateMapped[1])) unmapType = 4;
-            if (unmapType == 4 && P.unmappedWithin && samYes && !P.unmappedKeepPairs) {
-                if (P.outBAMunsorted) bamUnmapped(c, i, r, &best, 4, mateMapped, sam); else samUnmapped(c, i, r, &best, 4, mateMapped, sam);
+            if (unmapType == 4 && P.unmappedWithin && samYes) {   // :214-232 (KeepPairs does not affect the sorted BAM)
+                if (P.outSAMtype[0] == "SAM") { if (!P.unmappedKeepPairs) samUnmapped(c, i, r, &best, 4, mateMapped, sam); }
+                else {
+                    scratch.clear();
+                    bamUnmapped(c, i, r, &best, 4, mateMapped, scratch);
+                    if (P.outBAMunsorted && !P.unmappedKeepPairs) sam += scratch;
+                    if (coordYes) toCoord(scratch, 0, c.iReadAll[i] << 32);
+                }
             }
         } else if (P.unmappedWithin && samYes) {
             bool mateMapped[2] = {false, false};
-            if (P.outBAMunsorted) bamUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam); else samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
+            if (P.outSAMtype[0] == "SAM") samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
+            else {
+                scratch.clear();
+                bamUnmapped(c, i, r, nullptr, unmapType, mateMapped, scratch);
+                if (P.outBAMunsorted) sam += scratch;
+                if (coordYes) toCoord(scratch, 0, c.iReadAll[i] << 32);
+            }
         }
         if (unmapType >= 0) st.unmappedAll++;
     }

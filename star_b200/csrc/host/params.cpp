@@ -310,8 +310,7 @@ int finalizeParams(HostParams& P, std::string& err) {
             return bad("EXITING because of fatal PARAMETER error: missing BAM option\nSOLUTION: re-run STAR with one of the allowed values of --outSAMtype BAM Unsorted OR SortedByCoordinate OR both\n");
         for (size_t ii = 1; ii < P.outSAMtype.size(); ii++) {
             if (P.outSAMtype[ii] == "Unsorted") P.outBAMunsorted = true;
-            else if (P.outSAMtype[ii] == "SortedByCoordinate")
-                return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported yet by star-b200 (Unsorted is; coordinate sorting is SURVEY.md §8f N4)\n");
+            else if (P.outSAMtype[ii] == "SortedByCoordinate") P.outBAMcoord = true;
             else
                 return bad("EXITING because of fatal input ERROR: unknown value for the word " + std::to_string(ii + 1) + " of outSAMtype: " + P.outSAMtype[ii] + "\nSOLUTION: re-run STAR with one of the allowed values of --outSAMtype BAM Unsorted or SortedByCoordinate or both\n");
         }
@@ -361,6 +360,8 @@ int finalizeParams(HostParams& P, std::string& err) {
         for (int c : P.outSAMattrOrder) if (c == 10) has = true;
         if (!has) P.outSAMattrOrder.push_back(10);
     }
+    if (P.outBAMcoord && P.gpuShardCount > 1)
+        return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported for sharded (multi-GPU) runs yet: use Unsorted and sort the merged file\n");
     if (P.gpuShardIndex >= P.gpuShardCount) return bad("EXITING because of fatal PARAMETERS error: --gpuShardIndex must be < --gpuShardCount\n");
     // geometry the sparse window map of the GPU engine relies on ("windows")
     if (2 * h.winFlankNbins > h.winAnchorDistNbins && P.userSet.count("winFlankNbins"))

@@ -116,3 +116,39 @@ def test_sharded_bam_merge(oracle, lib, golden, tmp_path):
     a, b = parse_bam(pre + "Aligned.out.bam"), parse_bam(whole + "Aligned.out.bam")
     check_bgzf(a[0])
     assert a[2] == b[2] and a[3] == b[3]
+
+
+SORT_CASES = [
+    ("std", []),
+    ("hard", ["--outSAMunmapped", "Within"]),
+    ("se", ["--outSAMunmapped", "Within", "--outSAMattributes", "NH", "HI", "AS", "nM", "NM", "MD"]),
+    ("hard", ["--outSAMunmapped", "Within", "KeepPairs", "--outFilterMultimapNmax", "20", "--winAnchorMultimapNmax", "100"]),
+]
+
+
+@pytest.mark.skipif(not os.path.exists(oc.REF_STAR), reason="oracle/_ref/STAR not built (needs /root/reference)")
+@pytest.mark.parametrize("base,extra", SORT_CASES)
+def test_sorted_bam_equals_the_reference(oracle, golden, tmp_path, base, extra):
+    """--outSAMtype BAM Unsorted SortedByCoordinate: both files; the sorted one must list the same records in the same order as the
+    reference's bin-sorted file (coordinate, then read order; unmapped reads last in read order), header with SO:coordinate."""
+    files = [os.path.join(golden, base + "_1.fq")] + ([os.path.join(golden, base + "_2.fq")] if base != "se" else [])
+    outs = {}
+    for tag, binary, thr in (("ref", oc.REF_STAR, 2), ("ora", oc.ORACLE_CLI, 3)):
+        out = str(tmp_path / tag) + "/"
+        os.makedirs(out)
+        cmd = [binary, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn"] + files + ["--outFileNamePrefix", out, "--runThreadN", str(thr),
+               "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate"] + extra + (["--gpuChunkReads", "500"] if tag == "ora" else [])
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, cwd=out)
+        outs[tag] = (parse_bam(out + "Aligned.sortedByCoord.out.bam"), parse_bam(out + "Aligned.out.bam"))
+    srt_o, uns_o = outs["ora"]
+    srt_r, uns_r = outs["ref"]
+    check_bgzf(srt_o[0])
+    assert srt_o[1].startswith(b"@HD\tVN:1.4\tSO:coordinate\n")
+    assert _header_lines(srt_o[1]) == _header_lines(srt_r[1]) and srt_o[2] == srt_r[2]
+    assert len(srt_o[3]) == len(srt_r[3])
+    for k, (x, y) in enumerate(zip(srt_o[3], srt_r[3])):
+        assert x == y, "sorted record %d differs" % k
+    # the unsorted file next to it is unchanged by the extra output (the reference runs 2 threads here: compare as a multiset)
+    assert sorted(uns_o[3]) == sorted(uns_r[3])
+    keys = [struct.unpack("<II", r[4:12]) for r in srt_o[3]]
+    assert keys == sorted(keys), "not coordinate-sorted"
