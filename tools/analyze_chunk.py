@@ -41,10 +41,12 @@ for k in range(3):
     tot = float(prof[:8].sum()) or 1.0
     print("light kernel warp-cycles by phase [fetch+copy, win, flank, assign, nextwin, node, leaf, select]: " + " ".join("%.1f%%" % (100.0 * float(x) / tot) for x in prof[:8]) + "  total %.3g" % tot)
     th = float(prof[16:19].sum()) or 1.0
+    # flat path (default): slots 16/17/18 = summed warp-cycles of flat_setup_kernel / flat_dfs_warp_kernel / flat_record_warp_kernel (the kernels run
+    # different numbers of warps: divide by the warp count of each grid for times); warp-per-read kernel (STAR_B200_HEAVY_FLAT=0): its setup / E / R phases
     print("heavy kernel warp-cycles [setup, E, R]: " + " ".join("%.1f%%" % (100.0 * float(x) / th) for x in prof[16:19]) + "  total %.3g; tasks %d replays %d" % (th, prof[19], prof[20]))
-    it = float(prof[21]) or 1.0
-    print("heavy E-phase: iterations/warp-sum %.3g, avg active lanes: fetch %.2f node %.2f leaf %.2f" % (it, prof[22] / it, prof[23] / it, prof[24] / it))
-    print("stitch memo: hits %d misses %d" % (prof[25], prof[26]))
+    if prof[21]:
+        it = float(prof[21])
+        print("warp-per-read kernel E-phase: iterations/warp-sum %.3g, avg active lanes: fetch %.2f node %.2f leaf %.2f" % (it, prof[22] / it, prof[23] / it, prof[24] / it))
     print("run", k, {k2: round(v, 2) if isinstance(v, float) else v for k2, v in st.as_dict().items()})
 info = np.zeros(n, dtype=INFO)
 rc = lib.star_gpu_debug_read_info(eng.ctx, info.ctypes.data, info.nbytes)
