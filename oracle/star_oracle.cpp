@@ -705,39 +705,52 @@ struct ReadAlign {
         return r;
     }
     uint karyMaxMappableLength(uint S, uint N, uint lo, uint hi, bool dirR, uint& L, uint* indStartEnd) {
-        const uint K = 32;
-        bool cr = false;
+        const uint K = karyK;
         uint i1 = lo, i2 = hi;
-        uint L1 = karyLcp(S, N, L, i1, dirR, cr);
-        uint L2 = karyLcp(S, N, L, i2, dirR, cr);
-        uint i3 = i1, L3 = L1;
-        bool full = false;
-        if (L1 == N) { i3 = i1; L3 = L1; full = true; }   // (the reference would find such a row later; the block is the same)
-        else if (L2 == N) { i3 = i2; L3 = L2; full = true; }
-        while (!full && i1 + 1 < i2) {
-            const uint Lc = std::min(L1, L2);
-            const uint span = i2 - i1 - 1;                 // interior rows
-            const uint np = std::min(K, span);
+        uint L3 = 0, i3 = lo;
+        uint Lc = L;                       // bases known to match for every row of [i1,i2]
+        bool have = false;
+        // (1) narrowing rounds: K probes spread over the window (both ends included) until the window has at most K rows
+        while (i2 - i1 + 1 > K) {
             uint pr[32], pl[32]; bool pc[32];
-            for (uint j = 0; j < np; j++) {                // one probe per lane
-                pr[j] = np == span ? i1 + 1 + j : i1 + (uint)(((unsigned __int128)(i2 - i1) * (j + 1)) / (np + 1));
+            karyRounds++; karyProbes += K;
+            for (uint j = 0; j < K; j++) {
+                pr[j] = i1 + (uint)(((unsigned __int128)(i2 - i1) * j) / (K - 1));
                 pl[j] = karyLcp(S, N, Lc, pr[j], dirR, pc[j]);
             }
             int jFull = -1, jLast1 = -1;
-            for (uint j = 0; j < np; j++) {
+            for (uint j = 0; j < K; j++) {
                 if (pl[j] == N && jFull < 0) jFull = (int)j;
-                if (pl[j] != N && pc[j]) jLast1 = (int)j;  // read > suffix: the insertion point is to the right
+                if (pl[j] != N && pc[j]) jLast1 = (int)j;   // read > suffix: the insertion point is to the right of this probe
             }
-            if (jFull >= 0) { i3 = pr[jFull]; L3 = N; full = true; break; }
-            if (jLast1 >= 0) { i1 = pr[jLast1]; L1 = pl[jLast1]; }
-            if (jLast1 + 1 < (int)np) { i2 = pr[jLast1 + 1]; L2 = pl[jLast1 + 1]; }
+            if (jFull >= 0) { i3 = pr[jFull]; L3 = N; have = true; break; }
+            if (jLast1 < 0) { i3 = pr[0]; L3 = pl[0]; have = true; break; }                    // read sorts before the first row: that row is the best
+            if (jLast1 == (int)K - 1) { i3 = pr[K - 1]; L3 = pl[K - 1]; have = true; break; }  // ... after the last row
+            i1 = pr[jLast1]; i2 = pr[jLast1 + 1];
+            Lc = std::min(pl[jLast1], pl[jLast1 + 1]);
         }
-        if (!full) {
-            if (L1 > L2) { i3 = i1; L3 = L1; } else { i3 = i2; L3 = L2; }
+        uint b1, b2;
+        if (!have) {
+            // (2) one round over every row of the window: match length per lane, maximum, block of lanes attaining it
+            const uint rows = i2 - i1 + 1;
+            uint pl[32] = {0}; bool pc[32];
+            karyRounds++; karyProbes += rows;
+            for (uint j = 0; j < rows; j++) pl[j] = karyLcp(S, N, Lc, i1 + j, dirR, pc[j]);
+            uint jm = 0;
+            for (uint j = 1; j < rows; j++) if (pl[j] > pl[jm]) jm = j;
+            L3 = pl[jm];
+            uint j1 = jm, j2 = jm;
+            while (j1 > 0 && pl[j1 - 1] >= L3) j1--;
+            while (j2 + 1 < rows && pl[j2 + 1] >= L3) j2++;
+            b1 = i1 + j1; b2 = i1 + j2;
+            i3 = i1 + jm;
+        } else {
+            b1 = b2 = i3;
         }
-        // block of rows with match length >= L3 around i3, clamped to [lo, hi]: k-ary boundary searches
-        auto boundary = [&](uint inRow, uint outRow, bool left) -> uint {   // inRow has LCP >= L3; outRow (towards the interval end) is tested first
+        // (3) the block may continue beyond the rows seen so far (repeats): k-ary boundary searches, clamped to [lo, hi]
+        auto boundary = [&](uint inRow, uint outRow, bool left) -> uint {   // inRow has LCP >= L3; outRow (the interval end) is tested first
             bool c2;
+            karyRounds++; karyProbes++;
             uint Lout = karyLcp(S, L3, L, outRow, dirR, c2);
             if (Lout >= L3) return outRow;
             uint a = outRow, La = Lout, b = inRow;        // a: LCP < L3, b: LCP >= L3
@@ -745,13 +758,13 @@ struct ReadAlign {
                 const uint span = (left ? b - a : a - b) - 1;
                 const uint np = std::min(K, span);
                 uint pr[32], pl[32];
+                karyRounds++; karyProbes += np;
                 for (uint j = 0; j < np; j++) {
                     const uint step = np == span ? 1 + j : (uint)(((unsigned __int128)(span + 1) * (j + 1)) / (np + 1));
                     pr[j] = left ? a + step : a - step;
                     bool c3;
                     pl[j] = karyLcp(S, L3, La, pr[j], dirR, c3);
                 }
-                // rows nearer to b have LCP >= L3: first probe (from a) that reaches L3 becomes b, the one before it a
                 int jIn = -1;
                 for (uint j = 0; j < np; j++) if (pl[j] >= L3) { jIn = (int)j; break; }
                 if (jIn < 0) { a = pr[np - 1]; La = pl[np - 1]; }
@@ -759,13 +772,15 @@ struct ReadAlign {
             }
             return b;
         };
-        const uint b1 = i3 == lo ? lo : boundary(i3, lo, true);
-        const uint b2 = i3 == hi ? hi : boundary(i3, hi, false);
+        const bool seenLeft = !have && b1 > i1, seenRight = !have && b2 < i2;   // a row with a shorter match was seen on that side
+        if (!seenLeft && b1 > lo) b1 = boundary(b1, lo, true);
+        if (!seenRight && b2 < hi) b2 = boundary(b2, hi, false);
         L = L3;
         indStartEnd[0] = b1; indStartEnd[1] = b2;
         return b2 - b1 + 1;
     }
-    unsigned long long karyChecked = 0, karyMismatch = 0;
+    unsigned long long karyChecked = 0, karyMismatch = 0, karyRounds = 0, karyProbes = 0;
+    uint karyK = getenv("STAR_ORACLE_KARY_K") ? std::min(32, std::max(2, atoi(getenv("STAR_ORACLE_KARY_K")))) : 32;
     bool karyCheck = getenv("STAR_ORACLE_KARY_CHECK") != nullptr;
 
     // ReadAlign_storeAligns.cpp:10-160 (OPTIM_STOREaligns_SIMPLE branch :27-51)
@@ -1472,7 +1487,7 @@ struct star_oracle_ctx {
 };
 
 static thread_local std::string g_oracle_error;
-static std::atomic<unsigned long long> g_karyChecked(0), g_karyMismatch(0);
+static std::atomic<unsigned long long> g_karyChecked(0), g_karyMismatch(0), g_karyRounds(0), g_karyProbes(0);
 
 extern "C" {
 
@@ -1487,6 +1502,8 @@ int star_oracle_init(void** ctx, int /*device*/, const star_index_view_t* index,
 void star_oracle_destroy(void* ctx) { delete (star_oracle_ctx*)ctx; }
 // k-ary seed search design check (STAR_ORACLE_KARY_CHECK=1): searches compared with the reference binary search / disagreements
 void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch) { *checked = g_karyChecked.load(); *mismatch = g_karyMismatch.load(); }
+// dependent rounds (one round = probes issued together) and SA probes of the emulated k-ary searches (STAR_ORACLE_KARY_K = 2..32)
+void star_oracle_kary_cost(uint64_t* rounds, uint64_t* probes) { *rounds = g_karyRounds.load(); *probes = g_karyProbes.load(); }
 const char* star_oracle_last_error(void) { return g_oracle_error.c_str(); }
 
 static int oracle_run(star_oracle_ctx* c, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats,
@@ -1537,7 +1554,7 @@ static int oracle_run(star_oracle_ctx* c, const star_read_batch_t* in, star_alig
             }
         }
         cnts[t] = RA.cnt;
-        g_karyChecked += RA.karyChecked; g_karyMismatch += RA.karyMismatch;
+        g_karyChecked += RA.karyChecked; g_karyMismatch += RA.karyMismatch; g_karyRounds += RA.karyRounds; g_karyProbes += RA.karyProbes;
         fatals[t] = RA.fatal;
         fatalMsgs[t] = RA.fatalMsg;
     };
