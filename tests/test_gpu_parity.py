@@ -136,3 +136,33 @@ def test_cli_option_sets_match_oracle_cli(lib, oracle, golden, tmp_path, base, e
     assert cf.sam_body(outs[0] + "Aligned.out.sam") == cf.sam_body(outs[1] + "Aligned.out.sam")
     assert open(outs[0] + "SJ.out.tab", "rb").read() == open(outs[1] + "SJ.out.tab", "rb").read()
     assert cf.log_counters(outs[0] + "Log.final.out") == cf.log_counters(outs[1] + "Log.final.out")
+
+
+def test_cli_bam_outputs_match_oracle_cli(lib, oracle, golden, tmp_path):
+    """--outSAMtype BAM Unsorted SortedByCoordinate on the GPU: decompressed records equal those of the same host code driven by the
+    oracle engine (which tests/test_bam_output.py pins to the unmodified reference record for record)."""
+    import gzip
+    import oracle_capi as oc
+    files = _sets(golden)["hard"]
+    recs = {}
+    for tag, binary in (("gpu", os.path.join(ROOT, "star_b200", "bin", "STAR")), ("ora", oc.ORACLE_CLI)):
+        out = str(tmp_path / tag) + "/"
+        os.makedirs(out)
+        cmd = [binary, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn"] + files + ["--outFileNamePrefix", out, "--runThreadN", "3",
+               "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate", "--outSAMunmapped", "Within", "--outSAMattributes", "All"]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        got = []
+        for name in ("Aligned.out.bam", "Aligned.sortedByCoord.out.bam"):
+            d = gzip.decompress(open(out + name, "rb").read())
+            lt = int.from_bytes(d[4:8], "little")
+            o = 8 + lt
+            nref = int.from_bytes(d[o:o + 4], "little")
+            o += 4
+            for _ in range(nref):
+                ln = int.from_bytes(d[o:o + 4], "little")
+                o += 8 + ln
+            got.append(d[o:])
+        recs[tag] = got
+    assert len(recs["gpu"][0]) > 100000
+    assert recs["gpu"][0] == recs["ora"][0]
+    assert recs["gpu"][1] == recs["ora"][1]
