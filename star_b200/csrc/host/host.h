@@ -25,6 +25,7 @@ struct HostParams {
     std::string genomeDir = "./GenomeDir/";
     std::string genomeLoad = "NoSharedMemory";
     std::vector<std::string> readFilesIn = {"Read1", "Read2"};
+    std::vector<std::vector<std::string>> readFilesNames;   // [mate][file]: --readFilesIn a1,a2 b1,b2 (Parameters_readFilesInit.cpp:43-62)
     std::vector<std::string> readFilesCommand = {"-"};
     long long readMapNumber = -1;
     std::vector<std::string> readNameSeparator = {"/"};
@@ -48,7 +49,9 @@ struct HostParams {
     int outSAMmapqUnique = 255;
     unsigned outSAMflagOR = 0, outSAMflagAND = 65535;
     std::vector<std::string> outSAMattrRGline = {"-"};
-    std::string outSAMattrRG;               // ID of the single read group (if any)
+    std::string outSAMattrRG;               // ID of the first read group (if any)
+    std::vector<std::string> outSAMattrRGs;        // read group ID per input file (Parameters_readFilesInit.cpp:65-95)
+    std::vector<std::string> outSAMattrRGlineSplit; // one @RG header line per read group (tab-joined fields)
     std::string outFilterType = "Normal";
     std::string outFilterIntronMotifs = "None";
     std::string outFilterIntronStrands = "RemoveInconsistentStrands";
@@ -101,6 +104,7 @@ struct ReadChunk {
     std::vector<char> readFilter;            // 'Y'/'N'
     std::vector<uint64_t> iReadAll;
     bool fastq = true;
+    uint32_t fileIndex = 0;                  // input file (of a comma-separated list) this chunk came from: a chunk never spans files
     void clear() {
         nReads = 0; seq.clear(); qual.clear(); seqOff.clear(); names.clear(); nameOff.clear(); readFilter.clear(); iReadAll.clear();
     }
@@ -114,6 +118,7 @@ class ReadsReader {
     long long next(ReadChunk& c, uint32_t maxReads, std::string& err);
     uint64_t iReadAll = 0;
     uint64_t shardLo = 0, shardHi = ~0ULL;   // reads (0-based) this process maps
+    uint32_t fileIdx = 0;                    // current file of the --readFilesIn lists
 
    private:
     FILE* f[2] = {nullptr, nullptr};
@@ -122,6 +127,8 @@ class ReadsReader {
     const HostParams* P = nullptr;
     std::vector<char> buf[2];
     size_t bpos[2] = {0, 0}, blen[2] = {0, 0};
+    int openFile(uint32_t idx, std::string& err);   // opens file `idx` of every mate (mapped or stream); closes the previous one
+    void closeFiles();
     bool getLine(int m, std::string& line);
     int peekChar(int m);
     // fast path: plain (not piped) 4-line FASTQ files are memory-mapped; a chunk is line-indexed per mate and parsed by runThreadN threads
@@ -129,6 +136,7 @@ class ReadsReader {
     const char* map[2] = {nullptr, nullptr};
     size_t mapSize[2] = {0, 0}, mapOff[2] = {0, 0};
     long long nextFast(ReadChunk& c, uint32_t maxReads, std::string& err);
+    long long nextStream(ReadChunk& c, uint32_t maxReads, std::string& err);   // line-by-line parser (piped input, FASTA)
     std::vector<ReadChunk> parts_;                       // per-thread pieces, kept between chunks (their buffers stay mapped)
     std::vector<const char*> lineSt_[2], lineEn_[2];     // line index of the current chunk
     // parses one FASTQ record given its four lines of each mate (pointers into the mapped files); appends to `c`; returns 0 or -STAR_EXIT_*

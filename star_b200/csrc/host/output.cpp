@@ -127,7 +127,7 @@ void OutputWriter::samUnmapped(const ReadChunk& c, uint32_t i, const star_read_r
         s += "\tNH:i:0\tHI:i:0\tAS:i:"; putI(s, tr ? tr->maxScore : r.bestScore);
         s += "\tnM:i:"; putU(s, tr ? tr->nMM : r.bestNMM);
         s += "\tuT:A:"; putI(s, unmapType);
-        if (!P.outSAMattrRG.empty()) { s += "\tRG:Z:"; s += P.outSAMattrRG; }
+        if (!P.outSAMattrRGs.empty()) { s += "\tRG:Z:"; s += P.outSAMattrRGs[c.fileIndex]; }
         s.push_back('\n');
     }
 }
@@ -297,7 +297,7 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
                     break;
                 case ATTR_NM: s += "\tNM:i:"; putU(s, tagNM); break;
                 case ATTR_MD: s += "\tMD:Z:"; s += tagMD; break;
-                case ATTR_RG: s += "\tRG:Z:"; s += P.outSAMattrRG; break;
+                case ATTR_RG: s += "\tRG:Z:"; s += P.outSAMattrRGs[c.fileIndex]; break;
                 case ATTR_MC: if (nMates > 1) { s += "\tMC:Z:"; s += cigars[1 - imate]; } break;
                 default: break;  // ch: BAM-only
             }
@@ -381,7 +381,7 @@ void OutputWriter::bamUnmapped(const ReadChunk& c, uint32_t i, const star_read_r
         attrInt(at, "AS", tr ? tr->maxScore : r.bestScore);
         attrInt(at, "nM", tr ? (long long)tr->nMM : (long long)r.bestNMM);
         attrChar(at, "uT", std::to_string((unsigned)unmapType).at(0));
-        if (!P.outSAMattrRG.empty()) attrStr(at, "RG", P.outSAMattrRG);
+        if (!P.outSAMattrRGs.empty()) attrStr(at, "RG", P.outSAMattrRGs[c.fileIndex]);
         const uint64_t a = c.seqOff[(uint64_t)i * c.nMates + imate], b = c.seqOff[(uint64_t)i * c.nMates + imate + 1];
         const size_t rec0 = bam.size();
         put32(bam, 0);
@@ -542,7 +542,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
                     break;
                 case ATTR_NM: attrInt(at, "NM", (long long)tagNM); break;
                 case ATTR_MD: attrStr(at, "MD", tagMD); break;
-                case ATTR_RG: attrStr(at, "RG", P.outSAMattrRG); break;
+                case ATTR_RG: attrStr(at, "RG", P.outSAMattrRGs[c.fileIndex]); break;
                 case ATTR_MC: if (nMates > 1) attrStr(at, "MC", cigarText[1 - imate]); break;
                 default: break;   // ch: chimeric alignments only
             }
@@ -727,11 +727,7 @@ std::string OutputWriter::samHeader() const {  // samHeaders.cpp:27-113
     h << "@HD\tVN:1.4\n";
     for (size_t ii = 0; ii < idx.chrName.size(); ii++) h << "@SQ\tSN:" << idx.chrName[ii] << "\tLN:" << idx.chrLength[ii] << "\n";
     h << "@PG\tID:STAR\tPN:STAR\tVN:2.7.11b\tCL:" << P.commandLineFull << "\n";
-    if (P.outSAMattrRGline[0] != "-") {
-        h << "@RG";
-        for (auto& w : P.outSAMattrRGline) h << "\t" << w;
-        h << "\n";
-    }
+    for (auto& l : P.outSAMattrRGlineSplit) h << "@RG\t" << l << "\n";   // samHeaders.cpp:83-85
     h << "@CO\tuser command line: " << P.commandLine << "\n";
     return h.str();
 }

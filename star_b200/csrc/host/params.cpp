@@ -245,8 +245,15 @@ int finalizeParams(HostParams& P, std::string& err) {
     if (P.outStd != "Log") return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not supported by star-b200 (only Log)\n");
     if (P.readFilesIn.size() > 2 || P.readFilesIn.empty() || P.readFilesIn[0] == "Read1")
         return bad("EXITING: because of fatal input ERROR: --readFilesIn must name 1 or 2 FASTQ/FASTA files\n");
-    for (auto& f : P.readFilesIn)
-        if (f.find(',') != std::string::npos) return bad("EXITING: because of fatal input ERROR: comma-separated lists in --readFilesIn are not supported by star-b200\n");
+    P.readFilesNames.assign(P.readFilesIn.size(), {});
+    for (size_t imate = 0; imate < P.readFilesIn.size(); imate++) {   // Parameters_readFilesInit.cpp:43-62
+        std::string cur;
+        for (char ch : P.readFilesIn[imate]) { if (ch == ',') { P.readFilesNames[imate].push_back(cur); cur.clear(); } else cur.push_back(ch); }
+        if (!cur.empty() || P.readFilesNames[imate].empty()) P.readFilesNames[imate].push_back(cur);   // (an extra comma at the end is ignored)
+        if (imate > 0 && P.readFilesNames[imate].size() != P.readFilesNames[imate - 1].size())
+            return bad("EXITING: because of fatal INPUT ERROR: number of input files for mate" + std::to_string(imate + 1) + "=" + std::to_string(P.readFilesNames[imate].size()) +
+                       " is not equal to that for mate" + std::to_string(imate - 1) + "=" + std::to_string(P.readFilesNames[imate - 1].size()) + "\nMake sure that the number of files in --readFilesIn is the same for both mates\n");
+    }
     P.readNmates = (unsigned)P.readFilesIn.size();
     if (h.seedSearchLmax != 0) return bad("EXITING because of fatal PARAMETERS error: --seedSearchLmax >0 is not supported by star-b200\n");
     if (P.outFilterType != "Normal") return bad("EXITING because of FATAL input ERROR: --outFilterType " + P.outFilterType + " is not supported by star-b200 (only Normal)\n");
@@ -352,10 +359,23 @@ int finalizeParams(HostParams& P, std::string& err) {
             if (!has) P.outSAMattrOrder.push_back(9);
         }
     }
-    if (P.outSAMattrRGline[0] != "-") {  // Parameters.cpp: outSAMattrRGline, single read group only
-        for (auto& s : P.outSAMattrRGline) if (s == ",") return bad("EXITING because of fatal input ERROR: multiple read groups are not supported by star-b200\n");
-        if (P.outSAMattrRGline[0].substr(0, 3) != "ID:") return bad("EXITING because of fatal input ERROR: the first word of a line from --outSAMattrRGline=" + P.outSAMattrRGline[0] + " does not start with ID:xxx read group identifier\nSOLUTION: re-run STAR with all lines in --outSAMattrRGline starting with ID:xxx\n");
-        P.outSAMattrRG = P.outSAMattrRGline[0].substr(3);
+    if (P.outSAMattrRGline[0] != "-") {  // Parameters_readFilesInit.cpp:65-95: entries separated by the word ","
+        for (size_t ii = 0; ii < P.outSAMattrRGline.size(); ii++) {
+            if (ii == 0 || P.outSAMattrRGline[ii] == ",") {
+                if (ii > 0) ++ii;   // skip the comma
+                if (ii >= P.outSAMattrRGline.size()) break;
+                P.outSAMattrRGlineSplit.push_back(P.outSAMattrRGline[ii]);
+                if (P.outSAMattrRGlineSplit.back().substr(0, 3) != "ID:") return bad("EXITING because of FATAL INPUT ERROR: the first word of a line from --outSAMattrRGline=" + P.outSAMattrRGlineSplit.back() + " does not start with ID:xxx read group identifier\nSOLUTION: re-run STAR with all lines in --outSAMattrRGline starting with ID:xxx\n");
+                P.outSAMattrRGs.push_back(P.outSAMattrRGlineSplit.back().substr(3));
+            } else {
+                P.outSAMattrRGlineSplit.back() += "\t" + P.outSAMattrRGline[ii];
+            }
+        }
+        const size_t nFiles = P.readFilesNames.empty() ? 1 : P.readFilesNames[0].size();
+        if (P.outSAMattrRGs.size() > 1 && P.outSAMattrRGs.size() != nFiles)
+            return bad("EXITING: because of fatal INPUT ERROR: number of input read files: " + std::to_string(nFiles) + " does not agree with number of read group RG entries: " + std::to_string(P.outSAMattrRGs.size()) + "\nMake sure that the number of RG lines in --outSAMattrRGline is equal to either 1, or the number of input read files in --readFilesIn\n");
+        while (P.outSAMattrRGs.size() < nFiles) P.outSAMattrRGs.push_back(P.outSAMattrRGs[0]);   // the same read group for all files
+        P.outSAMattrRG = P.outSAMattrRGs[0];
         bool has = false;
         for (int c : P.outSAMattrOrder) if (c == 10) has = true;
         if (!has) P.outSAMattrOrder.push_back(10);

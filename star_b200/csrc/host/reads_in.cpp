@@ -19,12 +19,7 @@
 
 namespace starhost {
 
-ReadsReader::~ReadsReader() {
-    for (int m = 0; m < 2; m++) {
-        if (f[m]) { if (piped[m]) pclose(f[m]); else fclose(f[m]); }
-        if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]);
-    }
-}
+ReadsReader::~ReadsReader() { closeFiles(); }
 
 // Maps a plain file read-only; returns false when the fast path does not apply (empty file, not a regular file, mmap failure).
 static bool mapFile(const std::string& path, const char*& ptr, size_t& size) {
@@ -51,17 +46,63 @@ static size_t skipLines(const char* base, size_t size, size_t off, uint64_t line
     return off;
 }
 
+void ReadsReader::closeFiles() {
+    for (int m = 0; m < 2; m++) {
+        if (f[m]) { if (piped[m]) pclose(f[m]); else fclose(f[m]); f[m] = nullptr; }
+        piped[m] = false;
+        if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]);
+        map[m] = nullptr; mapSize[m] = 0; mapOff[m] = 0;
+        bpos[m] = blen[m] = 0;
+    }
+    fast = false;
+}
+
+// Opens file `idx` of the --readFilesIn lists (Parameters_openReadsFiles.cpp:5-105; the reference concatenates the files of a list
+// through a FIFO with "FILE n" marker lines, here they are simply opened one after the other).
+int ReadsReader::openFile(uint32_t idx, std::string& err) {
+    closeFiles();
+    fileIdx = idx;
+    const HostParams& Pin = *P;
+    if (Pin.readFilesCommand[0] == "-") {   // plain files: 4-line FASTQ goes through the memory-mapped parallel parser
+        bool ok = true;
+        for (unsigned m = 0; m < nMates && ok; m++) ok = mapFile(Pin.readFilesNames[m][idx], map[m], mapSize[m]);
+        ok = ok && map[0][0] == '@';
+        if (ok) { fast = true; return 0; }
+        for (unsigned m = 0; m < nMates; m++) { if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]); map[m] = nullptr; mapSize[m] = 0; }
+    }
+    for (unsigned m = 0; m < nMates; m++) {
+        const std::string& name = Pin.readFilesNames[m][idx];
+        if (Pin.readFilesCommand[0] != "-") {  // Parameters_openReadsFiles.cpp:83-101 pipes the command's stdout
+            std::string cmd;
+            for (auto& w : Pin.readFilesCommand) cmd += w + " ";
+            cmd += "\"" + name + "\"";
+            f[m] = popen(cmd.c_str(), "r");
+            piped[m] = true;
+        } else {
+            f[m] = fopen(name.c_str(), "rb");
+        }
+        if (!f[m]) {
+            err = "EXITING because of fatal input ERROR: could not open readFilesIn=" + name + "\n";
+            return STAR_EXIT_INPUT_FILES;
+        }
+        buf[m].resize(1 << 22);
+        bpos[m] = blen[m] = 0;
+    }
+    return 0;
+}
+
 int ReadsReader::open(const HostParams& Pin, std::string& err) {
     P = &Pin;
     nMates = Pin.readNmates;
-    if (Pin.readFilesCommand[0] == "-" && !fast) {   // plain files: 4-line FASTQ goes through the memory-mapped parallel parser
-        bool ok = true;
-        for (unsigned m = 0; m < nMates && ok; m++) ok = mapFile(Pin.readFilesIn[m], map[m], mapSize[m]);
-        ok = ok && map[0][0] == '@';
-        if (ok) {
-            fast = true;
-            mapOff[0] = mapOff[1] = 0;
-            if (Pin.gpuShardCount > 1) {   // contiguous slice by record index: count the lines of mate 1 once
+    const uint32_t nFiles = (uint32_t)Pin.readFilesNames[0].size();
+    if (Pin.gpuShardCount > 1) {
+        // contiguous slice of the input by read index: count the records of mate 1 in every file first (one pass over the text)
+        std::vector<uint64_t> recs(nFiles, 0);
+        uint64_t nRec = 0;
+        for (uint32_t fi = 0; fi < nFiles; fi++) {
+            int rc = openFile(fi, err);
+            if (rc) return rc;
+            if (fast) {
                 uint64_t lines = 0;
                 for (size_t off = 0; off < mapSize[0];) {
                     const char* q = (const char*)memchr(map[0] + off, '\n', mapSize[0] - off);
@@ -69,67 +110,45 @@ int ReadsReader::open(const HostParams& Pin, std::string& err) {
                     if (!q) break;
                     off = (size_t)(q - map[0]) + 1;
                 }
-                const uint64_t nRec = lines / 4;
-                shardLo = nRec * Pin.gpuShardIndex / Pin.gpuShardCount;
-                shardHi = nRec * (Pin.gpuShardIndex + 1) / Pin.gpuShardCount;
-                for (unsigned m = 0; m < nMates; m++) mapOff[m] = skipLines(map[m], mapSize[m], 0, 4 * shardLo);
-                iReadAll = shardLo;
+                recs[fi] = lines / 4;
+            } else {
+                std::string line;
+                const bool fq = peekChar(0) == '@';
+                uint64_t lines = 0, nr = 0;
+                while (getLine(0, line)) { if (fq) lines++; else if (!line.empty() && line[0] == '>') nr++; }
+                recs[fi] = fq ? lines / 4 : nr;
             }
-            return 0;
+            nRec += recs[fi];
         }
-        for (unsigned m = 0; m < nMates; m++) { if (map[m] && mapSize[m]) munmap((void*)map[m], mapSize[m]); map[m] = nullptr; mapSize[m] = 0; }
-    }
-    for (unsigned m = 0; m < nMates; m++) {
-        if (Pin.readFilesCommand[0] != "-") {  // Parameters_openReadsFiles.cpp:83-101 pipes the command's stdout
-            std::string cmd;
-            for (auto& w : Pin.readFilesCommand) cmd += w + " ";
-            cmd += "\"" + Pin.readFilesIn[m] + "\"";
-            f[m] = popen(cmd.c_str(), "r");
-            piped[m] = true;
-        } else {
-            f[m] = fopen(Pin.readFilesIn[m].c_str(), "rb");
-        }
-        if (!f[m]) {
-            err = "EXITING because of fatal input ERROR: could not open readFilesIn=" + Pin.readFilesIn[m] + "\n";
-            return STAR_EXIT_INPUT_FILES;
-        }
-        buf[m].resize(1 << 22);
-        bpos[m] = blen[m] = 0;
-    }
-    if (Pin.gpuShardCount > 1) {
-        // contiguous slice of the input by read index: count the records of mate 1 first (one pass over the text), then reopen
-        uint64_t nRec = 0;
-        {
-            std::string line;
-            int ch = peekChar(0);
-            bool fq = ch == '@';
-            uint64_t lines = 0;
-            while (getLine(0, line)) { if (fq) lines++; else if (!line.empty() && line[0] == '>') nRec++; }
-            if (fq) nRec = lines / 4;
-        }
-        for (unsigned m = 0; m < nMates; m++) { if (piped[m]) pclose(f[m]); else fclose(f[m]); f[m] = nullptr; }
-        HostParams P1 = Pin;
-        P1.gpuShardCount = 1;
-        int rc = open(P1, err);
-        P = &Pin;
-        if (rc) return rc;
         shardLo = nRec * Pin.gpuShardIndex / Pin.gpuShardCount;
         shardHi = nRec * (Pin.gpuShardIndex + 1) / Pin.gpuShardCount;
-        // skip the records before the slice (both mates), keeping the global read numbering
-        std::string tmp;
-        while (iReadAll < shardLo) {
-            int ch = peekChar(0);
-            if (ch != '@' && ch != '>') break;
-            bool fq = ch == '@';
-            for (unsigned m = 0; m < nMates; m++) {
-                getLine(m, tmp);
-                if (fq) { getLine(m, tmp); getLine(m, tmp); getLine(m, tmp); }
-                else { for (;;) { int c2 = peekChar(m); if (c2 == '@' || c2 == '>' || c2 == ' ' || c2 == '\n' || c2 < 0) break; getLine(m, tmp); } }
+        // position at record shardLo: skip whole files, then records inside the file (both mates), keeping the global read numbering
+        uint64_t before = 0;
+        uint32_t fi = 0;
+        while (fi + 1 < nFiles && before + recs[fi] <= shardLo) { before += recs[fi]; fi++; }
+        int rc = openFile(fi, err);
+        if (rc) return rc;
+        iReadAll = before;
+        if (fast) {
+            for (unsigned m = 0; m < nMates; m++) mapOff[m] = skipLines(map[m], mapSize[m], 0, 4 * (shardLo - before));
+            iReadAll = shardLo;
+        } else {
+            std::string tmp;
+            while (iReadAll < shardLo) {
+                int ch = peekChar(0);
+                if (ch != '@' && ch != '>') break;
+                const bool fq = ch == '@';
+                for (unsigned m = 0; m < nMates; m++) {
+                    getLine(m, tmp);
+                    if (fq) { getLine(m, tmp); getLine(m, tmp); getLine(m, tmp); }
+                    else { for (;;) { int c2 = peekChar(m); if (c2 == '@' || c2 == '>' || c2 == ' ' || c2 == '\n' || c2 < 0) break; getLine(m, tmp); } }
+                }
+                iReadAll++;
             }
-            iReadAll++;
         }
+        return 0;
     }
-    return 0;
+    return openFile(0, err);
 }
 
 int ReadsReader::peekChar(int m) {
@@ -330,7 +349,19 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
 }
 
 long long ReadsReader::next(ReadChunk& c, uint32_t maxReads, std::string& err) {
-    if (fast) return nextFast(c, maxReads, err);
+    // a chunk never spans two files of a --readFilesIn list: when the current file is exhausted the next one is opened
+    for (;;) {
+        long long n = fast ? nextFast(c, maxReads, err) : nextStream(c, maxReads, err);
+        c.fileIndex = fileIdx;
+        if (n != 0) return n;
+        const bool limit = (P->readMapNumber >= 0 && (long long)iReadAll >= P->readMapNumber) || iReadAll >= shardHi;
+        if (limit || fileIdx + 1 >= P->readFilesNames[0].size()) return 0;
+        int rc = openFile(fileIdx + 1, err);
+        if (rc) return -rc;
+    }
+}
+
+long long ReadsReader::nextStream(ReadChunk& c, uint32_t maxReads, std::string& err) {
     c.clear();
     c.nMates = nMates;
     c.seqOff.push_back(0);

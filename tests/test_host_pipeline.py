@@ -129,3 +129,58 @@ def test_mapped_file_reader_equals_the_stream_reader(oracle, golden, tmp_path, k
     if kind == "comments_and_filter_flags":
         flags = [int(l.split(b"\t")[1]) for l in sa]
         assert any(f & 0x200 for f in flags) and not all(f & 0x200 for f in flags)
+
+
+def _split_fastq(src, n_first, dst_a, dst_b):
+    with open(src) as f:
+        lines = f.read().split("\n")
+    while lines and lines[-1] == "":
+        lines.pop()
+    open(dst_a, "w").write("\n".join(lines[:4 * n_first]) + "\n")
+    open(dst_b, "w").write("\n".join(lines[4 * n_first:]) + "\n")
+
+
+@pytest.mark.skipif(not os.path.exists(oc.REF_STAR), reason="oracle/_ref/STAR not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", ["plain", "command"])
+def test_comma_separated_file_lists_and_read_groups(oracle, golden, tmp_path, mode):
+    """--readFilesIn a1,a2 b1,b2 with one read group per file (--outSAMattrRGline ID:x , ID:y): records, RG tags, @RG header lines and
+    counters equal the unmodified reference's (which concatenates the lists through a FIFO with FILE markers)."""
+    parts = {}
+    for m in (1, 2):
+        a, b = str(tmp_path / ("a_%d.fq" % m)), str(tmp_path / ("b_%d.fq" % m))
+        _split_fastq(os.path.join(golden, "std_%d.fq" % m), 700, a, b)
+        parts[m] = a + "," + b
+    extra = ["--outSAMattrRGline", "ID:lane1", "SM:s1", ",", "ID:lane2", "SM:s1", "PL:x", "--outSAMunmapped", "Within", "--outSAMattributes", "NH", "HI", "AS", "nM", "RG"]
+    if mode == "command":
+        extra += ["--readFilesCommand", "cat"]
+    outs = {}
+    for tag, binary, thr, more in (("ref", oc.REF_STAR, 1, []), ("ora", oc.ORACLE_CLI, 3, ["--gpuChunkReads", "333"])):
+        out = str(tmp_path / tag) + "/"
+        os.makedirs(out)
+        subprocess.check_call([binary, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", parts[1], parts[2], "--outFileNamePrefix", out,
+                               "--runThreadN", str(thr)] + extra + more, stdout=subprocess.DEVNULL, cwd=out)
+        outs[tag] = out
+    sam_r, sam_o = cf.sam_body(outs["ref"] + "Aligned.out.sam"), cf.sam_body(outs["ora"] + "Aligned.out.sam")
+    assert sam_o == sam_r
+    assert any(b"RG:Z:lane1" in l for l in sam_o) and any(b"RG:Z:lane2" in l for l in sam_o)
+    rg = lambda p: [l for l in open(p, "rb").read().split(b"\n") if l.startswith(b"@RG")]
+    assert rg(outs["ora"] + "Aligned.out.sam") == rg(outs["ref"] + "Aligned.out.sam") and len(rg(outs["ora"] + "Aligned.out.sam")) == 2
+    assert open(outs["ora"] + "SJ.out.tab", "rb").read() == open(outs["ref"] + "SJ.out.tab", "rb").read()
+    assert cf.log_counters(outs["ora"] + "Log.final.out") == cf.log_counters(outs["ref"] + "Log.final.out")
+
+
+def test_shards_over_a_file_list(oracle, golden, tmp_path):
+    """sharding counts records across all files of a list: 3 shards over 2 files reproduce the unsharded output in order"""
+    parts = []
+    for m in (1, 2):
+        a, b = str(tmp_path / ("a_%d.fq" % m)), str(tmp_path / ("b_%d.fq" % m))
+        _split_fastq(os.path.join(golden, "std_%d.fq" % m), 450, a, b)
+        parts.append(a + "," + b)
+    bodies = []
+    for r in range(3):
+        out = str(tmp_path) + "/s%d." % r
+        _cli(os.path.join(golden, "idx"), parts, out, ["--gpuShardIndex", str(r), "--gpuShardCount", "3", "--outSAMreadID", "Number"])
+        bodies.append(cf.sam_body(out + "Aligned.out.sam"))
+    whole = str(tmp_path) + "/w."
+    _cli(os.path.join(golden, "idx"), parts, whole, ["--outSAMreadID", "Number"])
+    assert all(len(b) > 0 for b in bodies) and sum(bodies, []) == cf.sam_body(whole + "Aligned.out.sam")
