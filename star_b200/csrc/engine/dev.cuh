@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../../include/star_b200.h"
+#include "warp_prims.cuh"
 
 namespace starb {
 
@@ -55,10 +56,10 @@ __device__ __forceinline__ u64 packedGet(const u64* __restrict__ w, u32 bits, u6
     u64 b = ii * bits;
     u64 wi = b >> 6;
     u32 sh = (u32)(b & 63);
-    u64 lo = __ldg(w + wi);
+    u64 lo = SB_LDG(w + wi);
     u64 v = lo >> sh;
     if (sh + bits > 64) {
-        u64 hi = __ldg(w + wi + 1);
+        u64 hi = SB_LDG(w + wi + 1);
         v |= hi << (64 - sh);
     }
     return v & ((1ULL << bits) - 1ULL);

@@ -22,6 +22,7 @@ namespace starb {
 // kernels (seed.cu, stitch.cu)
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
 __global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
+void launch_seed_warp(int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, u32);
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
                               star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
 __global__ void stitch_heavy_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, const u64*, const u8*, u32*, u8*, Caps,
@@ -95,6 +96,7 @@ struct star_ctx {
     FlatArgs fa{};
     Caps recCaps; u8* d_arenaRec = nullptr;
     int setupCtas = 3; u8* d_arenaSetup = nullptr; int recCtas = 4; int dfsCtas = 4;
+    int seedWarpCtas = 0;   // > 0: seed_search_warp_kernel with this many CTAs per SM (STAR_B200_SEED_WARP)
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -334,6 +336,7 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     }
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
     c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 6);
+    c->seedWarpCtas = (int)envU32("STAR_B200_SEED_WARP", 0);
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
     {
         size_t bytes = (size_t)c->gridStitch * 128 * c->fast.arenaBytes;
@@ -559,8 +562,11 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     if (smemStitch > 200 * 1024) { g_err = "star_b200: read too long for the shared-memory staging"; return STAR_EXIT_RUNTIME; }
     // ---- fast path over all reads ----
     CK(cudaMemsetAsync(c->d_counter, 0, 16, c->stream));
-    seed_search_kernel<<<c->gridSeed, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr,
-                                                                   c->d_counter, c->d_wc, c->smemStride);
+    if (c->seedWarpCtas)   // opt-in: one read per warp, 32-ary search (seed_warp.cuh)
+        launch_seed_warp(c->seedWarpCtas, c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr, c->d_counter, c->smemStride);
+    else
+        seed_search_kernel<<<c->gridSeed, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr,
+                                                                       c->d_counter, c->d_wc, c->smemStride);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[4], c->stream));

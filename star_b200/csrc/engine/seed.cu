@@ -14,6 +14,7 @@
 // global slab.  The kernel is latency/HBM-sector bound (random 8-byte SA probes + short genome runs);
 // DESIGN.md states its algorithmic bytes and roofline.
 #include "dev.cuh"
+#include "seed_warp.cuh"
 
 namespace starb {
 
@@ -337,6 +338,55 @@ __global__ void __launch_bounds__(128) seed_search_kernel(const __grid_constant_
         ri.cSaEnum = 0; ri.cNodes = 0; ri.cLeaves = 0; ri.cSlow = readList ? 1 : 0;
         info[i] = ri;
     }
+}
+
+// Warp-uniform variant (seed_warp.cuh): one read per WARP, the search of a start interval narrows with 32 probes per step and
+// examines windows of <= 32 SA rows in one step.  Same stored pieces as seed_search_kernel (checked lane by lane on the CPU by
+// tests/test_warp_emulation.py).  Opt-in (STAR_B200_SEED_WARP=1) until it has been measured on the GPU.  Work counters of this
+// kernel: searches and SAindex words as the reference; cCompare = SA rows probed, cBases = genome bases examined by all lanes.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) seed_search_warp_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P,
+                                                                    const u8* __restrict__ reads, u32 stride, ReadInfo* __restrict__ info,
+                                                                    Piece* __restrict__ pieces, u32 maxP, u32 nReads, const u32* __restrict__ readList,
+                                                                    u32* __restrict__ counter, u32 smemStride) {
+    extern __shared__ u8 smem[];
+    u8* R = smem + (size_t)(threadIdx.x >> 5) * smemStride;
+    const DevWarp w;
+    #pragma unroll 1
+    for (;;) {
+        u32 k = 0;
+        if (w.lane == 0) k = atomicAdd(counter, 1u);
+        k = w.shfl(k, 0);
+        if (k >= nReads) break;
+        const u32 i = readList ? readList[k] : k;
+        ReadInfo ri = info[i];
+        const u32 Lread = ri.Lread;
+        const u8* src = reads + (u64)i * stride;
+        w.sync();
+        #pragma unroll 1
+        for (u32 b = w.lane; b < Lread; b += 32) R[b] = src[b];
+        w.sync();
+        SeedWarpOut st;
+        st.PC = pieces + (u64)k * maxP;   // slab index = position in this launch (k), not the read id
+        st.maxP = maxP;
+        warpSeedRead<DevWarp>(w, ix, P, R, Lread, st);
+        const u32 bases = w.reduceAdd(st.basesLane);
+        if (w.lane == 0) {
+            ri.Nsplit = (u16)st.Nsplit; ri.split1_0 = (u16)st.split1_0;
+            ri.nP = (u16)st.nP; ri.nA = st.nA; ri.multNminL = st.multNminL; ri.flags = st.flags;
+            ri.cSearches = st.searches; ri.cSaiWords = st.saiWords; ri.cCompare = st.probes; ri.cBases = bases;
+            ri.cSaEnum = 0; ri.cNodes = 0; ri.cLeaves = 0; ri.cSlow = readList ? 1 : 0;
+            info[i] = ri;
+        }
+    }
+}
+
+void launch_seed_warp(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
+                      Piece* pieces, u32 maxP, u32 nReads, const u32* readList, u32* counter, u32 smemStride) {
+    const u32 smem = 4 * smemStride;
+    if (ctasPerSM <= 6) seed_search_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
+    else if (ctasPerSM <= 8) seed_search_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
+    else seed_search_warp_kernel<12><<<nSM * 12, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
 }
 
 // sums the per-read work counters (one warp-reduced atomic per counter per warp)

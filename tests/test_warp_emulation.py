@@ -1,0 +1,55 @@
+"""The warp-uniform seed search of the next GPU kernel (star_b200/csrc/engine/seed_warp.cuh) compiled for the host: 32 threads play
+the 32 lanes and meet at a barrier in every collective (oracle/warp_emul.cpp).  Every stored piece of every read must equal the
+oracle's (= the reference's PC[] after seeding), i.e. the device logic is checked lane by lane without a GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import conftest as cf
+import oracle_capi as oc
+
+ROOT = cf.ROOT
+EMUL_LIB = os.path.join(ROOT, "oracle", "_build", "libwarp_emul.so")
+
+
+def _emul():
+    if not os.path.exists(EMUL_LIB):
+        oc.build_oracle()
+    from star_b200 import capi
+    lib = C.CDLL(EMUL_LIB)
+    lib.warp_emul_seed_chunk.argtypes = [C.POINTER(capi.IndexView), C.POINTER(capi.Params), C.POINTER(capi.ReadBatch), C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("name,n_take", [("std", 250), ("hard", 150), ("se", 250)])
+def test_emulated_warp_seed_search_equals_oracle_pieces(oracle, lib, golden, name, n_take):
+    import star_b200 as sb
+    files = [os.path.join(golden, name + "_1.fq")] + ([os.path.join(golden, name + "_2.fq")] if name != "se" else [])
+    mates = [cf.read_fastq_seqs(f)[:n_take] for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    oe = oc.OracleEngine(oracle, idx)
+    _, _, st_o, (pc_off_o, pc_o) = oe.map_chunk(seq, off, n, nm, dump=True)
+    batch = oe._batch(seq, off, n, nm)
+    oe.close()
+    em = _emul()
+    cap = int(pc_off_o[-1]) + 64 * n
+    pc_off = np.zeros(n + 1, dtype=np.uint64)
+    pc = np.zeros((cap, 8), dtype=np.uint64)
+    per_read = np.zeros(4 * n, dtype=np.uint32)
+    counters = np.zeros(4, dtype=np.uint64)
+    rc = em.warp_emul_seed_chunk(idx.view, C.byref(idx.params), C.byref(batch), pc_off.ctypes.data, pc.ctypes.data, cap, per_read.ctypes.data, counters.ctypes.data)
+    idx.close()
+    assert rc == 0, "lanes disagreed on a uniform value (2) or capacity (1): %d" % rc
+    assert np.array_equal(pc_off, pc_off_o)
+    got = pc[: int(pc_off[-1])]
+    # SAend of the oracle dump = SAstart + Nrep - 1; all eight fields must agree for every piece of every read
+    bad = np.nonzero((got != pc_o).any(axis=1))[0]
+    assert bad.size == 0, "first differing piece %d: emulated %s oracle %s" % (bad[0], got[bad[0]], pc_o[bad[0]])
+    # the SAindex part of the search is unchanged, so these two counters equal the reference's
+    assert int(counters[0]) == st_o.mmp_searches and int(counters[1]) == st_o.mmp_sai_words
+    # and the point of the design: far fewer dependent rounds than the binary search's compare calls
+    assert counters[3] * 2 < st_o.mmp_compare_calls
