@@ -4,7 +4,7 @@
 // SuffixArrayFuns.cpp:10-207, ReadAlign_storeAligns.cpp:10-160) with a different search strategy inside maxMappableLength:
 // the answer — the maximal match length L over the SA rows of the start interval and the block of rows attaining it — does not
 // depend on the probing order, so the warp narrows the interval with 32 probes per step until it has at most 32 rows and then
-// examines the whole window in ONE step (measured on the emulation in oracle/star_oracle.cpp: 1.30 dependent steps per search
+// examines the whole window in ONE step (measured on the CPU emulation of the test infrastructure: 1.30 dependent steps per search
 // instead of the binary search's 7.48; identical results on 4.5 M searches).  The SA words of a window are contiguous (coalesced);
 // every lane compares the read with its own suffix.
 //
