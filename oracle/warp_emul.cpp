@@ -59,7 +59,8 @@ int warp_emul_seed_chunk(const star_index_view_t* view, const star_params_t* par
     const star_params_t P = *params;
     const uint32_t n = in->nReads;
     HostWarpShared shared;
-    std::vector<u8> R(STAR_READ_SEQ_LENGTH_MAX + 16);
+    std::vector<u8> Rbuf(STAR_READ_SEQ_LENGTH_MAX + 64, 0);   // 16 bytes of slack on both sides (8-byte gathers of the compare)
+    u8* R = Rbuf.data() + 16;
     std::vector<Piece> slab(P.seedPerReadNmax + 2);
     SeedWarpOut outs[32];
     uint32_t Lread = 0;
@@ -85,7 +86,7 @@ int warp_emul_seed_chunk(const star_index_view_t* view, const star_params_t* par
             w.sync();
             SeedWarpOut& st = outs[lane];
             st.PC = slab.data(); st.maxP = (u32)slab.size();
-            warpSeedRead<HostWarp>(w, hix.ix, P, R.data(), Lread, st);
+            warpSeedRead<HostWarp>(w, hix.ix, P, R, Lread, st);
             w.sync();
             if (lane == 0) {
                 for (int l = 1; l < 32; l++)   // the lanes must agree on every uniform value

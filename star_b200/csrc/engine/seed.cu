@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128, MINB) seed_search_warp_kernel(const __gri
                                                                     Piece* __restrict__ pieces, u32 maxP, u32 nReads, const u32* __restrict__ readList,
                                                                     u32* __restrict__ counter, u32 smemStride) {
     extern __shared__ u8 smem[];
-    u8* R = smem + (size_t)(threadIdx.x >> 5) * smemStride;
+    u8* R = smem + 16 + (size_t)(threadIdx.x >> 5) * smemStride;   // 16 bytes of slack before the first and after the last row (8-byte gathers)
     const DevWarp w;
     #pragma unroll 1
     for (;;) {
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(128, MINB) seed_search_warp_kernel(const __gri
 
 void launch_seed_warp(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
                       Piece* pieces, u32 maxP, u32 nReads, const u32* readList, u32* counter, u32 smemStride) {
-    const u32 smem = 4 * smemStride;
+    const u32 smem = 4 * smemStride + 32;
     if (ctasPerSM <= 6) seed_search_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
     else if (ctasPerSM <= 8) seed_search_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
     else seed_search_warp_kernel<12><<<nSM * 12, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);

@@ -24,29 +24,60 @@ struct SeedWarpOut {
     u32 basesLane;             // genome bases examined by THIS lane (the only per-lane value; summed over the warp by the caller)
 };
 
+// 8 bytes starting at an arbitrary address as one little-endian word (byte k = p[k]): two aligned 64-bit loads and a funnel shift.
+// Up to 7 bytes before / 15 after p are touched: the genome carries 256 bytes of padding, the read rows 16 bytes of slack on both sides.
+SB_DEV u64 load8generic(const u8* p) {
+    const uintptr_t ad = (uintptr_t)p;
+    const u64* a = (const u64*)(ad & ~(uintptr_t)7);
+    const u32 sh = (u32)(ad & 7) * 8;
+    const u64 lo = a[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (a[1] << (64 - sh));
+}
+SB_DEV u64 load8global(const u8* p) {   // read-only data in global memory
+    const uintptr_t ad = (uintptr_t)p;
+    const u64* a = (const u64*)(ad & ~(uintptr_t)7);
+    const u32 sh = (u32)(ad & 7) * 8;
+    const u64 lo = SB_LDG(a);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (SB_LDG(a + 1) << (64 - sh));
+}
+SB_DEV u64 bswap64(u64 v) {
+#ifdef STAR_WARP_HOST_EMUL
+    return __builtin_bswap64(v);
+#else
+    const u32 lo = (u32)v, hi = (u32)(v >> 32);
+    return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | (u64)__byte_perm(hi, 0, 0x0123);
+#endif
+}
+
 // match length of the read piece against the suffix of SA row iSA, starting at offset L (all rows of the current window share the first L
-// bases); the four cases of compareSeqToGenome (SuffixArrayFuns.cpp:10-104) in one loop with per-lane direction flags.
-// Returns the length (N = full match) and compRes (read > suffix in SA order).
+// bases); the four cases of compareSeqToGenome (SuffixArrayFuns.cpp:10-104) in one loop with per-lane direction flags, 8 bases per step:
+// the 8 read bases and the 8 genome bases are gathered into two words (byte k = base ii+k in comparison order), XOR-ed, and the first
+// non-zero byte is the first mismatch.  Returns the length (N = full match) and compRes (read > suffix in SA order).
 template <class W>
 SB_DEV u32 lcpRow(const DevIndex& ix, const u8* R, u64 S, u32 N, u32 L, u64 iSA, bool dirR, bool& compRes, u32& bases) {
     u64 SAstr = packedGet(ix.SA, ix.saBits, iSA);
     const bool dirG = (SAstr >> ix.GstrandBit) == 0;
     SAstr &= ix.GstrandMask;
-    const u8* G = ix.G;
-    const bool compl_ = dirR != dirG;                 // the read is compared as its complement
-    const long long gBase = dirG ? (long long)(SAstr + L) : (long long)(ix.nGenome - 1 - SAstr - L);
-    const long long gStep = dirG ? 1 : -1;
-    const long long rBase = dirR ? (long long)(S + L) : (long long)S - (long long)L;
-    const long long rStep = dirR ? 1 : -1;
+    const bool compl_ = dirR != dirG;                 // the read is compared as its complement (piece bases are always 0..3: 3-x == x^3)
+    const u8* g0 = ix.G + (dirG ? (long long)(SAstr + L) : (long long)(ix.nGenome - 1 - SAstr - L));   // base ii is g0[+ii] / g0[-ii]
+    const u8* r0 = R + (dirR ? (long long)(S + L) : (long long)S - (long long)L);                      // base ii is r0[+ii] / r0[-ii]
     const u32 n = N - L;
-    for (u32 ii = 0; ii < n; ii++) {
-        u8 sv = R[rBase + rStep * (long long)ii];
-        if (compl_) sv = (u8)(3 - sv);                // piece bases are always 0..3
-        const u8 gv = SB_LDG(G + gBase + gStep * (long long)ii);
-        if (sv != gv) {
-            compRes = dirG ? (sv > gv) : !(sv > gv || gv > 3);
-            bases += ii + 1;
-            return ii + L;
+    for (u32 ii = 0; ii < n; ii += 8) {
+        u64 rs = dirR ? load8generic(r0 + ii) : bswap64(load8generic(r0 - (long long)ii - 7));
+        const u64 gs = dirG ? load8global(g0 + ii) : bswap64(load8global(g0 - (long long)ii - 7));
+        if (compl_) rs ^= 0x0303030303030303ULL;
+        const u64 x = rs ^ gs;
+        if (x) {
+            const u32 k = (u32)SB_CTZ64(x) >> 3;       // first differing base of this step
+            if (ii + k < n) {
+                const u8 sv = (u8)(rs >> (8 * k)), gv = (u8)(gs >> (8 * k));
+                compRes = dirG ? (sv > gv) : !(sv > gv || gv > 3);
+                bases += ii + k + 1;
+                return ii + k + L;
+            }
+            break;                                     // the difference lies beyond the piece
         }
     }
     compRes = false;

@@ -15,12 +15,14 @@
 #define SB_FFS(x) __builtin_ffs((int)(x))            /* 1-based index of the lowest set bit, 0 if none */
 #define SB_CLZ(x) __builtin_clz((unsigned)(x))        /* x != 0 */
 #define SB_CTZ(x) __builtin_ctz((unsigned)(x))        /* x != 0 */
+#define SB_CTZ64(x) __builtin_ctzll((unsigned long long)(x))
 #else
 #define SB_DEV __device__ __forceinline__
 #define SB_LDG(p) __ldg(p)
 #define SB_FFS(x) __ffs((int)(x))
 #define SB_CLZ(x) __clz((int)(x))
 #define SB_CTZ(x) (__ffs((int)(x)) - 1)
+#define SB_CTZ64(x) (__ffsll((long long)(x)) - 1)
 #endif
 
 namespace starb {
