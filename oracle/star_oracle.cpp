@@ -780,6 +780,7 @@ struct ReadAlign {
         return b2 - b1 + 1;
     }
     unsigned long long karyChecked = 0, karyMismatch = 0, karyRounds = 0, karyProbes = 0;
+    unsigned long long winHistN[16] = {0}, winHistNodes[16] = {0};   // analysis: windows / recursion nodes by seeds per window (15 = 15+)
     uint karyK = getenv("STAR_ORACLE_KARY_K") ? std::min(32, std::max(2, atoi(getenv("STAR_ORACLE_KARY_K")))) : 32;
     bool karyCheck = getenv("STAR_ORACLE_KARY_CHECK") != nullptr;
 
@@ -1332,7 +1333,9 @@ struct ReadAlign {
             if (trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) break;  // logs a warning in the reference
             *(trAll[iW1][0]) = trA;
             nWinTr[iW1] = 0;
+            const unsigned long long nodes0 = cnt.nodes;
             stitchWindowAligns(0, nWA[iW], 0, &WAincl[0], 0, 0, trA, iW, Read1[trA.roStr == 0 ? 0 : 2], trAll[iW1], &nWinTr[iW1]);
+            { const uint hb = nWA[iW] < 15 ? nWA[iW] : 15; winHistN[hb]++; winHistNodes[hb] += cnt.nodes - nodes0; }
             if (nWinTr[iW1] == 0) continue;
             if (trAll[iW1][0]->maxScore > trBest->maxScore || (trAll[iW1][0]->maxScore == trBest->maxScore && trAll[iW1][0]->gLength < trBest->gLength)) trBest = trAll[iW1][0];
             trNtotal += nWinTr[iW1];
@@ -1488,6 +1491,7 @@ struct star_oracle_ctx {
 
 static thread_local std::string g_oracle_error;
 static std::atomic<unsigned long long> g_karyChecked(0), g_karyMismatch(0), g_karyRounds(0), g_karyProbes(0);
+static std::atomic<unsigned long long> g_winHistN[16], g_winHistNodes[16];
 
 extern "C" {
 
@@ -1503,6 +1507,8 @@ void star_oracle_destroy(void* ctx) { delete (star_oracle_ctx*)ctx; }
 // k-ary seed search design check (STAR_ORACLE_KARY_CHECK=1): searches compared with the reference binary search / disagreements
 void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch) { *checked = g_karyChecked.load(); *mismatch = g_karyMismatch.load(); }
 // dependent rounds (one round = probes issued together) and SA probes of the emulated k-ary searches (STAR_ORACLE_KARY_K = 2..32)
+// analysis: windows and recursion nodes by number of seeds per window (bin 15 = 15 or more)
+void star_oracle_window_hist(uint64_t* windows16, uint64_t* nodes16) { for (int q = 0; q < 16; q++) { windows16[q] = g_winHistN[q].load(); nodes16[q] = g_winHistNodes[q].load(); } }
 void star_oracle_kary_cost(uint64_t* rounds, uint64_t* probes) { *rounds = g_karyRounds.load(); *probes = g_karyProbes.load(); }
 const char* star_oracle_last_error(void) { return g_oracle_error.c_str(); }
 
@@ -1554,6 +1560,7 @@ static int oracle_run(star_oracle_ctx* c, const star_read_batch_t* in, star_alig
             }
         }
         cnts[t] = RA.cnt;
+        for (int q = 0; q < 16; q++) { g_winHistN[q] += RA.winHistN[q]; g_winHistNodes[q] += RA.winHistNodes[q]; }
         g_karyChecked += RA.karyChecked; g_karyMismatch += RA.karyMismatch; g_karyRounds += RA.karyRounds; g_karyProbes += RA.karyProbes;
         fatals[t] = RA.fatal;
         fatalMsgs[t] = RA.fatalMsg;

@@ -25,6 +25,7 @@ const char* star_oracle_last_error(void);
 /* test-only: statistics of the k-ary search design check (env STAR_ORACLE_KARY_CHECK=1) */
 void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch);
 void star_oracle_kary_cost(uint64_t* rounds, uint64_t* probes);
+void star_oracle_window_hist(uint64_t* windows16, uint64_t* nodes16);
 const star_engine_vtbl_t* star_oracle_engine(void);
 
 #ifdef __cplusplus
