@@ -5,6 +5,12 @@
 // (source/ReadAlignChunk_mapChunk.cpp:7-128, ReadAlign_oneRead.cpp:8-121) and the shared-memory genome
 // residency (Genome_genomeLoad.cpp:177-243).  There is NO CPU fallback: every entry point fails with
 // STAR_EXIT_RUNTIME when no CUDA device is usable.
+//
+// Pipeline of one chunk (star_gpu_map_resident), all on one stream:
+//   prep_reads -> seed_search (MMP) -> radix sort by number of loci (heaviest first) -> stitch_kernel for reads with < 4 loci
+//   -> flat_setup (windows, export) -> flat_dfs_warp (sub-tree tasks) -> flat_record_warp (ordered recording, selection)
+//   -> overflow tiers for reads that exceeded a cap (bigger arenas; last tier = the reference's own limits) -> scan + pack
+//   -> work counters.  Environment knobs (STAR_B200_*) exist for measurements only; defaults are the measured best.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -10,7 +10,13 @@
 //   multMapSelect, mappedFilter              source/ReadAlign_multMapSelect.cpp:8-95, ReadAlign_mappedFilter.cpp:3-20
 //
 // How (B200-first, NOT the reference's structure):
-//  * persistent lanes (one read per lane at a time, next read from an atomic ticket) with a private arena in HBM;
+//  * three execution shapes share the device functions of this file:
+//      - the flattened path of stitch_flat.cuh (default for every read with >= 4 loci): setup (one warp per read) ->
+//        sub-tree tasks (one warp per task, all lanes on the same scalar path, byte loops 32 positions per step: the COOP
+//        template variants below) -> ordered recording (one warp per read);
+//      - stitch_kernel: one read per lane (persistent lanes, lockstep state machine) for reads with very few loci and as
+//        the engine of the overflow tiers, with stitch_heavy_kernel (one warp per read) for the DFS-heavy reads of a tier;
+//    every shape uses private arenas in HBM (windows, seeds, transcript pool) with caps and overflow flags;
 //  * the dense per-read winBin[2][nGenome>>16] array (190 KB memset per read in the reference, F8) is replaced by the
 //    window interval list itself: bins owned by a window are exactly [gStart,gEnd] of a live window on that strand,
 //    so "is the bin owned / nearest owned bin within winAnchorDistNbins" are interval queries (DESIGN.md proves the
