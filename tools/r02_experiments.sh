@@ -1,0 +1,28 @@
+# Round-2 first GPU call (prepared at the end of round 1, when the GPU budget was spent).  Run with:
+#   gpurun --timeout 1500 -- 'bash tools/r02_experiments.sh'
+# 1. warp-uniform seed kernel (seed_warp.cuh, validated on the CPU emulation only so far): outputs vs oracle, then timing
+# 2. prefix-split threshold of the task kernel: 82 % of the recursion nodes sit in windows with >= 15 seeds
+# 3. launch list of the default configuration
+mkdir -p gpurun_out
+python - <<'PY' > gpurun_out/r02_seedwarp_parity.log 2>&1
+import os, sys
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import tarfile, tempfile
+import conftest as cf, oracle_capi as oc, star_b200 as sb
+d = tempfile.mkdtemp(); tarfile.open("tests/golden/tiny.tar.gz").extractall(d); g = os.path.join(d, "tiny")
+lib = sb.load_library(); idx = sb.Index(lib, os.path.join(g, "idx")); ol = oc.load_oracle()
+for ctas in ("6", "8", "12"):
+    os.environ["STAR_B200_SEED_WARP"] = ctas
+    for name, files in (("std", ["std_1.fq", "std_2.fq"]), ("hard", ["hard_1.fq", "hard_2.fq"]), ("se", ["se_1.fq"])):
+        mates = [cf.read_fastq_seqs(os.path.join(g, f)) for f in files]
+        seq, off, n, nm = sb.pack_reads(mates)
+        oe = oc.OracleEngine(ol, idx); res_o, al_o, st_o = oe.map_chunk(seq, off, n, nm); oe.close()
+        eng = sb.Engine(lib, idx, max_reads=n); res_g, al_g, st_g = eng.map_chunk(seq, off, n, nm); eng.close()
+        diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
+        print("SEED_WARP", ctas, name, "diffs", len(diffs), "searches equal", st_g.mmp_searches == st_o.mmp_searches, "sai equal", st_g.mmp_sai_words == st_o.mmp_sai_words, diffs[:3], flush=True)
+PY
+cat gpurun_out/r02_seedwarp_parity.log | tail -12
+run() { tag=$1; shift; env "$@" timeout 600 python tools/analyze_chunk.py 1048576 > gpurun_out/r02_$tag.log 2>&1; echo "$tag $(grep -E '^run 2' gpurun_out/r02_$tag.log | sed -E 's/.*ms_seed.: ([0-9.]+).*ms_stitch.: ([0-9.]+).*ms_total.: ([0-9.]+).*ms_heavy.: ([0-9.]+).*/seed \1 stitch \2 total \3 ms_heavy \4/') | $(grep 'heavy kernel warp' gpurun_out/r02_$tag.log | tail -1 | cut -c1-110)"; }
+run base A=1
+for c in 6 8 12; do run seedwarp$c STAR_B200_SEED_WARP=$c; done
+for s in 16 20 30 52; do run split$s STAR_B200_HEAVY_SPLIT=$s; done
