@@ -1,0 +1,267 @@
+// engine_emul.cpp — TEST INFRASTRUCTURE ONLY: the kernel pipeline of the CUDA engine executed on the CPU.
+//
+// The kernel sources of star_b200/csrc/engine (seed.cu, stitch.cu, stitch_flat.cuh) are included UNMODIFIED and compiled as host
+// code through cuda_host_shim.h: every kernel runs as one emulated CTA of 128 (256 for the prep kernel) host threads, warp collectives
+// meet at per-warp barriers.  This file mirrors what engine_api.cu does around the kernels for the first tier of a chunk
+// (index layout, caps, arenas, pools, launch order: prep -> seed -> heaviest-first order -> stitch_kernel for reads with few loci ->
+// flat_setup -> flat_dfs_warp -> flat_record_warp -> scan/pack) on host memory.  tests/ compare the produced alignments with the
+// oracle's field by field, so the device logic of the whole stitching path is exercised lane by lane without a GPU.
+// Reads that exceed a first-tier cap are reported (nOverflow) instead of being redone by the tiers.
+#include "cuda_host_shim.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <thread>
+#include <vector>
+
+namespace cuda_shim {
+thread_local Dim tIdx, bIdx, bDim, gDim;
+thread_local CtaShared* cta;
+}
+
+#include "../star_b200/csrc/engine/seed.cu"
+#include "../star_b200/csrc/engine/stitch.cu"
+
+namespace starb { alignas(128) u8 smem[256 * 1024]; }   // dynamic shared memory of the (single) emulated CTA
+
+using namespace starb;
+
+namespace {
+
+// one CTA of nThreads host threads executing `body` (a kernel call with its arguments bound)
+void runCta(unsigned nThreads, const std::function<void()>& body) {
+    cuda_shim::CtaShared cta;
+    cta.nThreads = nThreads;
+    pthread_barrier_init(&cta.bar, nullptr, nThreads);
+    const unsigned nWarps = (nThreads + 31) / 32;
+    for (unsigned w = 0; w < nWarps; w++) { pthread_barrier_init(&cta.warp[w].bar, nullptr, 32); memset(cta.warp[w].slot, 0, sizeof(cta.warp[w].slot)); }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nThreads; t++)
+        th.emplace_back([&, t] {
+            cuda_shim::tIdx = {t, 0, 0}; cuda_shim::bIdx = {0, 0, 0}; cuda_shim::bDim = {nThreads, 1, 1}; cuda_shim::gDim = {1, 1, 1};
+            cuda_shim::cta = &cta;
+            body();
+        });
+    for (auto& t : th) t.join();
+    for (unsigned w = 0; w < nWarps; w++) pthread_barrier_destroy(&cta.warp[w].bar);
+    pthread_barrier_destroy(&cta.bar);
+}
+
+u64 arenaSize(const Caps& c) {   // engine_api.cu
+    u64 b = 0;
+    b += (u64)c.maxW * sizeof(Window);
+    b += (u64)c.maxW * c.spw * sizeof(Seed);
+    b += (u64)c.maxTr * sizeof(DevTr);
+    b += 2 * sizeof(DevTr);
+    b += (u64)(c.spw + 2) * 128;
+    b += (u64)c.maxTr * 2;
+    b += (u64)c.maxW * 2 * 2;
+    return (b + 255) & ~255ULL;
+}
+
+struct HostIndex {
+    DevIndex ix;
+    std::vector<u64> sa, sai, thr;
+    std::vector<int> val;
+    std::vector<u32> chrBin;
+    HostIndex(const star_index_view_t* v, const star_params_t* params) {
+        memset(&ix, 0, sizeof(ix));
+        ix.G = v->G; ix.nGenome = v->nGenome;
+        sa.assign((v->nSAbyte + 7) / 8 + 2, 0); memcpy(sa.data(), v->SA, v->nSAbyte);
+        sai.assign((v->nSAibyte + 7) / 8 + 2, 0); memcpy(sai.data(), v->SAi, v->nSAibyte);
+        ix.SA = sa.data(); ix.SAi = sai.data(); ix.nSA = v->nSA; ix.nSAi = v->nSAi;
+        ix.GstrandBit = v->GstrandBit; ix.saBits = v->GstrandBit + 1; ix.saiBits = v->GstrandBit + 3;
+        ix.gSAindexNbases = v->gSAindexNbases; ix.gChrBinNbits = v->gChrBinNbits; ix.nChrReal = v->nChrReal;
+        ix.GstrandMask = ~(1ULL << v->GstrandBit);
+        ix.SAiMarkNmaskC = 1ULL << (v->GstrandBit + 1); ix.SAiMarkNmask = ~ix.SAiMarkNmaskC; ix.SAiMarkAbsentMaskC = 1ULL << (v->GstrandBit + 2);
+        for (u32 i = 0; i <= v->gSAindexNbases; i++) ix.genomeSAindexStart[i] = v->genomeSAindexStart[i];
+        {   // Genome::chrBinFill Genome.cpp:209-216
+            const u64 nb = 1ULL << v->gChrBinNbits;
+            const u64 chrBinN = v->chrStart[v->nChrReal] / nb + 1;
+            chrBin.resize(chrBinN);
+            for (u64 ii = 0, ichr = 1; ii < chrBinN; ++ii) {
+                if (ii * nb >= v->chrStart[ichr]) ichr++;
+                chrBin[ii] = (u32)(ichr - 1);
+            }
+            ix.chrBin = chrBin.data(); ix.chrBinN = chrBinN;
+        }
+        ix.chrStart = (const u64*)v->chrStart; ix.chrLength = (const u64*)v->chrLength;
+        ix.sjdbN = v->sjdbN; ix.sjdbOverhang = v->sjdbOverhang; ix.sjdbLength = v->sjdbLength; ix.sjGstart = v->sjGstart;
+        ix.sjdbStart = (const u64*)v->sjdbStart; ix.sjdbEnd = (const u64*)v->sjdbEnd; ix.sjDstart = (const u64*)v->sjDstart; ix.sjAstart = (const u64*)v->sjAstart;
+        ix.sjdbMotif = v->sjdbMotif; ix.sjdbShiftLeft = v->sjdbShiftLeft; ix.sjdbShiftRight = v->sjdbShiftRight; ix.sjdbStrand = v->sjdbStrand;
+        {   // step table of the genomic-length score, host libm (engine_api.cu)
+            const double scale = params->scoreGenomicLengthLog2scale;
+            auto f = [&](u64 g) { return int(std::ceil(std::log2((double)g) * scale - 0.5)); };
+            const u64 gMax = 1ULL << 40;
+            u64 pos = 1;
+            thr.push_back(1); val.push_back(f(1));
+            while (pos < gMax && thr.size() < 4096) {
+                int cur = f(pos);
+                if (f(gMax) == cur) break;
+                u64 lo = pos, hi = pos + 1;
+                while (hi < gMax && f(hi) == cur) { lo = hi; hi = hi * 2 < gMax ? hi * 2 : gMax; }
+                if (f(hi) == cur) break;
+                while (lo + 1 < hi) { u64 mid = lo + (hi - lo) / 2; if (f(mid) == cur) lo = mid; else hi = mid; }
+                thr.push_back(hi); val.push_back(f(hi));
+                pos = hi;
+            }
+            ix.log2Thr = thr.data(); ix.log2Val = val.data(); ix.log2N = (int)thr.size();
+        }
+    }
+};
+
+u32 envU32(const char* name, u32 dflt) { const char* e = getenv(name); return e ? (u32)strtoul(e, nullptr, 10) : dflt; }
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+// Maps one chunk with the emulated kernels.  out: as star_gpu_map_chunk.  info4[4]: reads on the flat path, reads on the lane path,
+// reads that overflowed a first-tier cap (their results are not valid), tasks.  Returns 0 or a STAR_EXIT code.
+int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* params, const star_read_batch_t* in, star_align_batch_t* out, uint64_t* info4) {
+    HostIndex H(view, params);
+    const DevIndex& ix = H.ix;
+    const star_params_t P = *params;
+    const u32 n = in->nReads;
+    const u32 nMates = in->nMates;
+    const u32 nOut = (u32)(P.outFilterMultimapNmax > 0 ? P.outFilterMultimapNmax : 1);
+    // ---- upload_chunk
+    u32 maxL = 0;
+    for (u32 i = 0; i < n; i++) {
+        const uint64_t* o = in->seqOff + (u64)i * nMates;
+        u64 L = nMates == 2 ? (o[1] - o[0]) + (o[2] - o[1]) + 1 : o[1] - o[0];
+        if (L > maxL) maxL = (u32)L;
+    }
+    const u32 stride = (maxL + 16) & ~15u;
+    u32 smemStride = (maxL + 1 + 3) & ~3u;
+    if (((smemStride / 4) & 1) == 0) smemStride += 4;
+    std::vector<u8> reads((size_t)n * stride + 64, 0);
+    std::vector<ReadInfo> info(n);
+    // ---- caps (engine_api.cu defaults)
+    Caps fast;
+    fast.maxP = std::min<u32>(128, (u32)P.seedPerReadNmax);
+    fast.maxW = (std::min<u32>(128, (u32)P.alignWindowsPerReadNmax) + 1) & ~1u;
+    fast.maxTr = std::min<u32>(128, (u32)P.alignTranscriptsPerReadNmax);
+    fast.spw = (u32)P.seedPerWindowNmax; fast.nOut = nOut; fast.arenaBytes = arenaSize(fast);
+    Caps heavy = fast;
+    heavy.maxW = (std::min<u32>((u32)P.alignWindowsPerReadNmax, 256) + 1) & ~1u;
+    heavy.maxTr = std::min<u32>((u32)P.alignTranscriptsPerReadNmax, 1024);
+    heavy.arenaBytes = arenaSize(heavy);
+    Caps rec = heavy;
+    rec.arenaBytes = ((u64)rec.maxW * sizeof(Window) + (u64)rec.maxTr * sizeof(DevTr) + (u64)rec.maxTr * 2 + (u64)rec.maxW * 4 + 255) & ~255ULL;
+    const u32 heavyNA = envU32("STAR_B200_HEAVY_NA", 4), heavyEst = envU32("STAR_B200_HEAVY_EST", 1024);
+    std::vector<Piece> pieces((size_t)n * fast.maxP);
+    std::vector<star_read_result_t> results(n);
+    std::vector<star_align_t> staged((size_t)n * nOut);
+    memset(results.data(), 0, results.size() * sizeof(star_read_result_t));
+    std::vector<u32> counter(8, 0);
+    // ---- prep + seed
+    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, reads.data(), stride, info.data(), P); });
+    if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: seqOff %llu %llu %llu seq0=%c reads0=%d,%d winBinNbits=%u\n", (unsigned long long)in->seqOff[0], (unsigned long long)in->seqOff[1], (unsigned long long)in->seqOff[2], in->seq[0], reads[0], reads[1], (unsigned)P.winBinNbits);
+    if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after prep: Lread[0]=%u stride=%u smemStride=%u n=%u\n", info[0].Lread, stride, smemStride, n);
+    counter[0] = 0;
+    runCta(128, [&] { seed_search_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), fast.maxP, n, nullptr, counter.data(), nullptr, smemStride); });
+    if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after seed: nP[0]=%u nA[0]=%u flags=%u counter=%u\n", info[0].nP, info[0].nA, info[0].flags, counter[0]);
+    // ---- heaviest-first order (stable, like the radix sort on keys ~nA)
+    std::vector<u32> order(n);
+    for (u32 i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return info[a].nA > info[b].nA; });
+    u32 nHeavyA = 0;
+    if (heavyNA) for (u32 i = 0; i < n; i++) if (info[i].nA >= heavyNA) nHeavyA++;
+    // ---- heavy-read hand-over pool of stitch_kernel
+    std::vector<u8> heavyPool(64u << 20);
+    std::vector<unsigned long long> heavyBump(4, 0);
+    std::vector<u64> heavyOff(n, 0);
+    std::vector<u32> heavyList(n, 0);
+    HeavyArgs hv;
+    hv.pool = heavyPool.data(); hv.poolBytes = heavyPool.size(); hv.bump = heavyBump.data(); hv.readOff = heavyOff.data();
+    hv.list = heavyList.data(); hv.count = (u32*)(heavyBump.data() + 1); hv.estLimit = heavyEst;
+    const bool dbg = getenv("ENGINE_EMUL_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "emul: nHeavyA=%u of %u, arenaFast %.1f MB\n", nHeavyA, n, 128.0 * fast.arenaBytes / 1048576);
+    std::vector<u8> arenaFast((size_t)128 * fast.arenaBytes);
+    if (n > nHeavyA) {
+        counter[0] = 0;
+        runCta(128, [&] { stitch_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), n - nHeavyA, nullptr, counter.data(), arenaFast.data(), fast,
+                                        results.data(), staged.data(), order.data() + nHeavyA, smemStride, hv); });
+    }
+    const u32 nHeavyX = *hv.count;
+    if (dbg) fprintf(stderr, "emul: stitch_kernel done, exported %u\n", nHeavyX);
+    std::sort(heavyList.begin(), heavyList.begin() + nHeavyX);
+    // ---- flat path
+    FlatArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    std::vector<FlatRec> recs(n + 1);
+    std::vector<u8> pool(std::max<u64>(64ull << 20, (u64)n * 65536));
+    std::vector<unsigned long long> bumps(8, 0);
+    const u64 maxTasks = std::max<u64>(1u << 16, (u64)n * 1024);
+    std::vector<FlatTask> tasks(maxTasks);
+    std::vector<FlatOut> outs(maxTasks);
+    std::vector<FlatBlock> blocks(std::max<u64>(1u << 14, (u64)n * 64));
+    std::vector<u64> trStore(std::max<u64>(1u << 20, (u64)n * 8192));
+    fa.recs = recs.data(); fa.pool = pool.data(); fa.poolBytes = pool.size(); fa.bumps = bumps.data();
+    fa.tasks = tasks.data(); fa.outs = outs.data(); fa.maxTasks = maxTasks; fa.blocks = blocks.data(); fa.maxBlocks = (u32)blocks.size();
+    fa.trStore = trStore.data(); fa.trWords = trStore.size(); fa.maxTasksPerRead = 8192; fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
+    fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1);
+    std::vector<u8> arenaSetup((size_t)4 * heavy.arenaBytes), arenaRec((size_t)4 * rec.arenaBytes);
+    if (nHeavyA) {
+        counter[0] = 0;
+        runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
+                                               arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, 0); });
+    }
+    if (nHeavyX) {
+        counter[0] = 0;
+        runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(),
+                                               counter.data(), arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, nHeavyA); });
+    }
+    const u32 nRecs = nHeavyA + nHeavyX;
+    if (dbg) fprintf(stderr, "emul: setup done, tasks %llu pool %llu\n", bumps[1], bumps[0]);
+    if (nRecs) {
+        counter[0] = 0;
+        runCta(128, [&] { flat_dfs_warp_kernel<4>(ix, P, fa, counter.data(), heavy); });
+        if (dbg) fprintf(stderr, "emul: dfs done, blocks %llu words %llu\n", bumps[2], bumps[3]);
+        counter[0] = 0;
+        runCta(128, [&] { flat_record_warp_kernel<4>(ix, P, info.data(), nRecs, counter.data(), arenaRec.data(), rec, results.data(), staged.data(), fa); });
+    }
+    if (dbg) fprintf(stderr, "emul: record done\n");
+    // ---- overflow tier (engine_api.cu: reads that exceeded a first-tier cap are redone by stitch_kernel with bigger arenas)
+    {
+        std::vector<u32> list;
+        for (u32 i = 0; i < n; i++) if (info[i].flags & 1) list.push_back(i);
+        if (!list.empty()) {
+            Caps mid;
+            mid.maxP = std::min<u32>((u32)P.seedPerReadNmax, 512);
+            mid.maxW = (std::min<u32>((u32)P.alignWindowsPerReadNmax, 1024) + 1) & ~1u;
+            mid.maxTr = std::min<u32>((u32)P.alignTranscriptsPerReadNmax, 1024);
+            mid.spw = fast.spw; mid.nOut = nOut; mid.arenaBytes = arenaSize(mid);
+            std::vector<Piece> tp((size_t)list.size() * mid.maxP);
+            std::vector<u8> arenaMid((size_t)128 * mid.arenaBytes);
+            for (u32 i : list) info[i].flags &= ~1u;
+            counter[0] = 0;
+            runCta(128, [&] { seed_search_kernel(ix, P, reads.data(), stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), nullptr, smemStride); });
+            HeavyArgs hv0 = hv; hv0.estLimit = 0;   // (no hand-over inside the tier)
+            counter[0] = 0;
+            runCta(128, [&] { stitch_kernel(ix, P, reads.data(), stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
+                                            results.data(), staged.data(), nullptr, smemStride, hv0); });
+            if (dbg) fprintf(stderr, "emul: tier redid %zu reads\n", list.size());
+        }
+    }
+    // ---- scan + pack (host)
+    u64 nAl = 0, nOver = 0;
+    for (u32 i = 0; i < n; i++) {
+        if (info[i].flags & 1) { nOver++; results[i].nTrOut = 0; results[i].nTr = 0; }
+        results[i].trOffset = nAl;
+        if (nAl + results[i].nTrOut > out->alignsCapacity) return STAR_EXIT_RUNTIME;
+        for (u32 k = 0; k < results[i].nTrOut; k++) out->aligns[nAl++] = staged[(u64)i * nOut + k];
+        out->reads[i] = results[i];
+    }
+    out->nAligns = nAl;
+    if (info4) { info4[0] = nRecs; info4[1] = n - nHeavyA; info4[2] = nOver; info4[3] = bumps[1]; }
+    return 0;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

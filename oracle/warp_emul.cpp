@@ -49,6 +49,7 @@ inline u8 nt2num(char c) {
 }  // namespace
 
 extern "C" {
+#pragma GCC visibility push(default)
 
 // Seeds every read of the batch with the emulated warp.  pc receives 8 numbers per stored piece in the oracle's dump layout
 // (rStart, Length, Str=0, Dir, Nrep, SAstart, SAend, iFrag); pcOff[nReads+1]; perRead[4*i..] = nP, nA, flags, multNminL.
@@ -113,4 +114,5 @@ int warp_emul_seed_chunk(const star_index_view_t* view, const star_params_t* par
     return rcAll;
 }
 
+#pragma GCC visibility pop
 }  // extern "C"

@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(128, MINB) seed_search_warp_kernel(const __gri
     }
 }
 
+#ifndef STAR_CUDA_HOST_SHIM   // (kernel launches need nvcc; the host emulation of the tests calls the kernels directly)
 void launch_seed_warp(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
                       Piece* pieces, u32 maxP, u32 nReads, const u32* readList, u32* counter, u32 smemStride) {
     const u32 smem = 4 * smemStride + 32;
@@ -388,6 +389,7 @@ void launch_seed_warp(int ctasPerSM, int nSM, cudaStream_t stream, const DevInde
     else if (ctasPerSM <= 8) seed_search_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
     else seed_search_warp_kernel<12><<<nSM * 12, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, maxP, nReads, readList, counter, smemStride);
 }
+#endif
 
 // sums the per-read work counters (one warp-reduced atomic per counter per warp)
 __global__ void reduce_counters_kernel(const ReadInfo* __restrict__ info, u32 nReads, WorkCounters* __restrict__ wc) {

@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
 }
 
 // host-side launcher (the kernels are templates over the occupancy target; engine_api.cu is another translation unit)
+#ifndef STAR_CUDA_HOST_SHIM   // (kernel launches need nvcc; the host emulation of the tests calls the kernels directly)
 void launch_flat_dfs(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const FlatArgs& fa, u32* counter, const Caps& caps) {
     const u32 smem = 4 * FLAT_WARP_SMEM;
     if (ctasPerSM <= 4) flat_dfs_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, fa, counter, caps);
@@ -428,6 +429,7 @@ void launch_flat_dfs(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex
     else if (ctasPerSM <= 6) flat_dfs_warp_kernel<6><<<nSM * 6, 128, smem, stream>>>(ix, P, fa, counter, caps);
     else flat_dfs_warp_kernel<8><<<nSM * 8, 128, smem, stream>>>(ix, P, fa, counter, caps);
 }
+#endif
 
 // ---- warp-uniform recording kernel: one WARP per read.  All 32 lanes execute the order-dependent recording with identical state
 // (no divergence: one instruction stream per warp instead of 32); the scan over the read's tasks is cooperative: 32 FlatOut records
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __gri
     PROF_ADD(20, nReplay);
 }
 
+#ifndef STAR_CUDA_HOST_SHIM   // (kernel launches need nvcc; the host emulation of the tests calls the kernels directly)
 void launch_flat_record(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u32* counter,
                         u8* arenas, const Caps& caps, star_read_result_t* results, star_align_t* staged, const FlatArgs& fa) {
     const u32 smem = 4 * FLAT_REC_SMEM;
@@ -579,7 +582,9 @@ void launch_flat_record(int ctasPerSM, int nSM, cudaStream_t stream, const DevIn
     else if (ctasPerSM == 3) flat_record_warp_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
     else flat_record_warp_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, info, nRecs, counter, arenas, caps, results, staged, fa);
 }
+#endif
 
+#ifndef STAR_CUDA_HOST_SHIM   // (kernel launches need nvcc; the host emulation of the tests calls the kernels directly)
 void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
                        const Piece* pieces, u32 nHeavy, const u32* heavyList, const u64* heavyOff, const u8* heavyPool, u32* counter, u8* arenas, const Caps& caps,
                        star_read_result_t* results, star_align_t* staged, u32 smemStride, const FlatArgs& fa, u32 kBase) {
@@ -594,3 +599,4 @@ void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, co
     else if (ctasPerSM == 3) flat_setup_kernel<3><<<nSM * 3, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, nHeavy, heavyList, heavyOff, heavyPool, counter, arenas, caps, results, staged, smemStride, fa, kBase);
     else flat_setup_kernel<4><<<nSM * 4, 128, smem, stream>>>(ix, P, reads, stride, info, pieces, nHeavy, heavyList, heavyOff, heavyPool, counter, arenas, caps, results, staged, smemStride, fa, kBase);
 }
+#endif

@@ -53,3 +53,38 @@ def test_emulated_warp_seed_search_equals_oracle_pieces(oracle, lib, golden, nam
     assert int(counters[0]) == st_o.mmp_searches and int(counters[1]) == st_o.mmp_sai_words
     # and the point of the design: far fewer dependent rounds than the binary search's compare calls
     assert counters[3] * 2 < st_o.mmp_compare_calls
+
+
+ENGINE_EMUL_LIB = os.path.join(ROOT, "oracle", "_build", "libengine_emul.so")
+
+
+@pytest.mark.parametrize("name,n_take", [("std", 24), ("hard", 14), ("se", 24)])
+def test_emulated_kernels_lane_path_equals_oracle(oracle, lib, golden, name, n_take, monkeypatch):
+    """The UNMODIFIED kernel sources (seed.cu, stitch.cu) compiled as host code through oracle/cuda_host_shim.h: prep_reads_kernel,
+    seed_search_kernel and stitch_kernel (one read per lane: windows, recursion, extension, recording, selection; overflowing reads
+    redone by the tier with bigger arenas) run as emulated CTAs of host threads and must give the oracle's alignments field by field.
+    (The warp-uniform kernels of the flat path keep ONE transcript per warp in shared memory that all 32 lanes update in lockstep;
+    free-running host threads cannot reproduce that, so they are covered on the GPU only — see DESIGN.md.)"""
+    import star_b200 as sb
+    from star_b200 import capi
+    monkeypatch.setenv("STAR_B200_HEAVY_NA", "2000000000")   # every read on the lane path
+    monkeypatch.setenv("STAR_B200_HEAVY_EST", "0")
+    if not os.path.exists(ENGINE_EMUL_LIB):
+        oc.build_oracle()
+    files = [os.path.join(golden, name + "_1.fq")] + ([os.path.join(golden, name + "_2.fq")] if name != "se" else [])
+    mates = [cf.read_fastq_seqs(f)[:n_take] for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    oe = oc.OracleEngine(oracle, idx)
+    res_o, al_o, _ = oe.map_chunk(seq, off, n, nm)
+    batch = oe._batch(seq, off, n, nm)
+    res, al, ab = oe._out(n, oe.n_out)
+    oe.close()
+    em = C.CDLL(ENGINE_EMUL_LIB)
+    em.engine_emul_map_chunk.argtypes = [C.POINTER(capi.IndexView), C.POINTER(capi.Params), C.POINTER(capi.ReadBatch), C.POINTER(capi.AlignBatch), C.c_void_p]
+    info4 = np.zeros(4, dtype=np.uint64)
+    rc = em.engine_emul_map_chunk(idx.view, C.byref(idx.params), C.byref(batch), C.byref(ab), info4.ctypes.data)
+    idx.close()
+    assert rc == 0 and int(info4[0]) == 0 and int(info4[1]) == n and int(info4[2]) == 0
+    diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
+    assert not diffs, "\n".join(diffs[:10])
