@@ -207,17 +207,18 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     fa.trStore = trStore.data(); fa.trWords = trStore.size(); fa.maxTasksPerRead = 8192; fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
     fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1);
     std::vector<u8> arenaSetup((size_t)4 * heavy.arenaBytes), arenaRec((size_t)4 * rec.arenaBytes);
-    if (nHeavyA) {
+    if (nHeavyA && envU32("STAR_B200_HEAVY_FLAT", 1) != 0) {
         counter[0] = 0;
         runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
                                                arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, 0); });
     }
-    if (nHeavyX) {
+    if (nHeavyX && envU32("STAR_B200_HEAVY_FLAT", 1) != 0) {
         counter[0] = 0;
         runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(),
                                                counter.data(), arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, nHeavyA); });
     }
-    const u32 nRecs = nHeavyA + nHeavyX;
+    const bool oldHeavy = envU32("STAR_B200_HEAVY_FLAT", 1) == 0;   // warp-per-read kernel (the engine of the overflow tiers) instead of the flat path
+    const u32 nRecs = oldHeavy ? 0 : nHeavyA + nHeavyX;
     if (dbg) fprintf(stderr, "emul: setup done, tasks %llu pool %llu\n", bumps[1], bumps[0]);
     if (nRecs) {
         counter[0] = 0;
@@ -225,6 +226,26 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
         if (dbg) fprintf(stderr, "emul: dfs done, blocks %llu words %llu\n", bumps[2], bumps[3]);
         counter[0] = 0;
         runCta(128, [&] { flat_record_warp_kernel<4>(ix, P, info.data(), nRecs, counter.data(), arenaRec.data(), rec, results.data(), staged.data(), fa); });
+    }
+    if (oldHeavy && (nHeavyA || nHeavyX)) {   // launchHeavy of engine_api.cu
+        HeavyScratch hs;
+        hs.maxTasks = 8192; hs.maxBlocks = 4096; hs.maxWin = heavy.maxW;
+        const u32 W1 = (hs.maxWin + 2) & ~1u;
+        hs.trWords = 1u << 17; hs.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 6); hs.memoSlots = 0;
+        hs.bytesPerWarp = ((u64)W1 * 8 + ((W1 + 7) & ~7u) + (u64)hs.maxTasks * 8 + (u64)hs.maxBlocks * 504 + (u64)hs.trWords * 8 + 8 + (u64)hs.memoSlots * 72 + 255) & ~255ULL;
+        std::vector<u8> scratch((size_t)4 * hs.bytesPerWarp, 0);
+        std::vector<u8> arenaHeavy((size_t)4 * heavy.arenaBytes);
+        if (nHeavyA) {
+            counter[0] = 0;
+            runCta(128, [&] { stitch_heavy_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
+                                                  arenaHeavy.data(), heavy, results.data(), staged.data(), smemStride, scratch.data(), hs); });
+        }
+        if (nHeavyX) {
+            counter[0] = 0;
+            runCta(128, [&] { stitch_heavy_kernel(ix, P, reads.data(), stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(), counter.data(),
+                                                  arenaHeavy.data(), heavy, results.data(), staged.data(), smemStride, scratch.data(), hs); });
+        }
+        if (dbg) fprintf(stderr, "emul: warp-per-read kernel done (%u + %u reads)\n", nHeavyA, nHeavyX);
     }
     if (dbg) fprintf(stderr, "emul: record done\n");
     // ---- overflow tier (engine_api.cu: reads that exceeded a first-tier cap are redone by stitch_kernel with bigger arenas)
@@ -259,7 +280,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
         out->reads[i] = results[i];
     }
     out->nAligns = nAl;
-    if (info4) { info4[0] = nRecs; info4[1] = n - nHeavyA; info4[2] = nOver; info4[3] = bumps[1]; }
+    if (info4) { info4[0] = oldHeavy ? nHeavyA + nHeavyX : nRecs; info4[1] = n - nHeavyA; info4[2] = nOver; info4[3] = bumps[1]; }
     return 0;
 }
 
