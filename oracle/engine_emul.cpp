@@ -5,7 +5,7 @@
 // meet at per-warp barriers.  This file mirrors what engine_api.cu does around the kernels for the first tier of a chunk
 // (index layout, caps, arenas, pools, launch order: prep -> seed -> heaviest-first order -> stitch_kernel for reads with few loci ->
 // flat_setup -> flat_dfs_warp -> flat_record_warp -> scan/pack) on host memory.  tests/ compare the produced alignments with the
-// oracle's field by field, so the device logic of the whole stitching path is exercised lane by lane without a GPU.
+// oracle's field by field, so the device logic of the whole path (every kernel of the default pipeline) is exercised lane by lane without a GPU.
 // Reads that exceed a first-tier cap are reported (nOverflow) instead of being redone by the tiers.
 #include "cuda_host_shim.h"
 
@@ -112,6 +112,88 @@ struct HostIndex {
         }
     }
 };
+
+// flat_record_warp_kernel restated sequentially (ONE host thread, the non-cooperative device functions): an independent consumer of the
+// task outputs of the emulated flat_dfs_warp_kernel (ENGINE_EMUL_HOST_RECORD=1), used to cross-check the recording kernel.
+void hostRecord(const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 nRecs, u8* arena, const Caps& caps, star_read_result_t* results,
+                star_align_t* staged, const FlatArgs& fa) {
+    cuda_shim::tIdx = {0, 0, 0}; cuda_shim::bIdx = {0, 0, 0}; cuda_shim::bDim = {1, 1, 1}; cuda_shim::gDim = {1, 1, 1};
+    Lane ln;
+    static DevTr curL, leafL;
+    static Frame stackL[2];
+    static u8 phL[8];
+    ln.cur = &curL; ln.leaf = &leafL; ln.stack = stackL; ln.ph = phL;
+    ln.ix = &ix; ln.P = &P; ln.R0 = nullptr; ln.R2 = nullptr; ln.R = nullptr; ln.caps = caps;
+    u8* a = arena;
+    ln.win = (Window*)a; a += (u64)caps.maxW * sizeof(Window);
+    ln.pool = (DevTr*)a; a += (u64)caps.maxTr * sizeof(DevTr);
+    ln.trPtr = (u16*)a; a += (u64)caps.maxTr * sizeof(u16);
+    ln.winBase = (u16*)a; a += (u64)caps.maxW * sizeof(u16);
+    ln.winN = (u16*)a;
+    ln.wa = nullptr;
+    ln.memo = nullptr; ln.memoMask = 0; ln.memoBase = 0; ln.memoHit = 0; ln.memoMiss = 0; ln.lastSeed = -1; ln.coop = 0;
+    for (u32 q = 0; q < caps.maxTr; q++) ln.trPtr[q] = (u16)q;
+    for (u32 k = 0; k < nRecs; k++) {
+        const FlatRec rec = fa.recs[k];
+        if (rec.done) continue;
+        const u32 i = rec.read;
+        ReadInfo ri = info[i];
+        readBegin(ln, ri);
+        ln.saEnum = rec.saEnum;
+        if (rec.over) {
+            ln.overflow = rec.over;
+        } else {
+            const u8* rp = fa.pool + rec.poolOff;
+            const u32 rs = flatReadStride(rec.Lread);
+            ln.R0 = rp; ln.R2 = rp + rs;
+            const FlatWin* fw = (const FlatWin*)(rp + 2 * (u64)rs);
+            const Seed* fs = (const Seed*)(fw + rec.nWin);
+            u64 nd = 0, lv = 0;
+            for (u32 t = 0; t < rec.nTasks; t++) { nd += fa.outs[(u64)rec.taskBase + t].nodes; lv += fa.outs[(u64)rec.taskBase + t].leaves; }
+            ln.nodes = nd; ln.leaves = lv;
+            for (u32 w = 0; w < rec.nWin && !ln.overflow; w++) {
+                const FlatWin W = fw[w];
+                u16* wTr = nullptr; u16 nWinTr = 0;
+                int rc = windowBegin(ln, wTr, nWinTr);
+                if (rc == 2) { ln.overflow = 3; break; }
+                if (rc == 1) break;
+                const u32 Chr = W.Chr, Str = W.Str, nA = W.nWA;
+                const Seed* WA = fs + W.seedOff;
+                ln.R = Str == 0 ? ln.R0 : ln.R2;
+                const u64 tb = (u64)rec.taskBase + W.taskStart;
+                for (u32 tq = 0; tq < (1u << W.depth) && !ln.overflow; tq++) {
+                    const FlatOut o = fa.outs[tb + tq];
+                    u32 b = o.first, inBlock = 0;
+                    for (u32 q = 0; q < o.count; q++) {
+                        Cand c;
+                        if (q == 0) c = o.c0;
+                        else {
+                            if (inBlock == FLAT_CAND_PER_BLOCK) { b = fa.blocks[b].next; inBlock = 0; }
+                            c = fa.blocks[b].c[inBlock++];
+                        }
+                        if (c.iFrag >= 0 && ln.maxScoreMate[c.iFrag] < c.score) ln.maxScoreMate[c.iFrag] = c.score;
+                        const int wBest = ln.pool[wTr[0]].h.maxScore;
+                        if (c.score + P.outFilterMultimapScoreRange >= wBest || (c.iFrag >= 0 && c.score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[c.iFrag])) {
+                            if (nWinTr > caps.maxTr - ln.trNtotal - 1) { ln.overflow = 3; break; }
+                            if (c.trOff != FLAT_NONE) {
+                                const u64* src = fa.trStore + c.trOff;
+                                memcpy(&ln.leaf->h, src, sizeof(TrHead));
+                                memcpy(ln.leaf->ex, src + sizeof(TrHead) / 8, (size_t)ln.leaf->h.nExons * sizeof(Exon));
+                                recordLeaf(ln, wTr, &nWinTr);
+                            } else {
+                                int Score; u32 tR2; u64 tG2;
+                                bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                if (ok) recordLeaf(ln, wTr, &nWinTr);
+                            }
+                        }
+                    }
+                }
+                windowEnd(ln, Chr, Str, wTr, nWinTr);
+            }
+        }
+        selectExport(ln, ri, i, 0, 0, results, staged, info);
+    }
+}
 
 u32 envU32(const char* name, u32 dflt) { const char* e = getenv(name); return e ? (u32)strtoul(e, nullptr, 10) : dflt; }
 
@@ -224,8 +306,12 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
         counter[0] = 0;
         runCta(128, [&] { flat_dfs_warp_kernel<4>(ix, P, fa, counter.data(), heavy); });
         if (dbg) fprintf(stderr, "emul: dfs done, blocks %llu words %llu\n", bumps[2], bumps[3]);
-        counter[0] = 0;
-        runCta(128, [&] { flat_record_warp_kernel<4>(ix, P, info.data(), nRecs, counter.data(), arenaRec.data(), rec, results.data(), staged.data(), fa); });
+        if (envU32("ENGINE_EMUL_HOST_RECORD", 0)) {   // cross-check: the recording restated sequentially on one host thread
+            hostRecord(ix, P, info.data(), nRecs, arenaRec.data(), rec, results.data(), staged.data(), fa);
+        } else {
+            counter[0] = 0;
+            runCta(128, [&] { flat_record_warp_kernel<4>(ix, P, info.data(), nRecs, counter.data(), arenaRec.data(), rec, results.data(), staged.data(), fa); });
+        }
     }
     if (oldHeavy && (nHeavyA || nHeavyX)) {   // launchHeavy of engine_api.cu
         HeavyScratch hs;

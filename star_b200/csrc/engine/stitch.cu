@@ -292,12 +292,17 @@ template <bool COOP = false>
 __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBstart, u64 gBstart, u64 L, u32 iFragB, u32 sjAB, DevTr* t) {
     const star_params_t& P = *ln.P;
     const DevIndex& g = *ln.ix;
-    TrHead& h = t->h;
-    if (h.nExons >= STAR_MAX_N_EXONS) return -1000010;
+    if (t->h.nExons >= STAR_MAX_N_EXONS) return -1000010;
+    // COOP (the transcript is ONE copy per warp in shared memory): every lane works on private copies of the head, the last exon and the
+    // new exon and lane 0 alone writes them back on success — no lane ever reads shared state another lane is writing.
+    const u32 nEx0 = t->h.nExons;
+    TrHead hL; Exon eAL, eBL;
+    if constexpr (COOP) { hL = t->h; eAL = t->ex[nEx0 - 1]; eBL = t->ex[nEx0]; }
+    TrHead& h = COOP ? hL : t->h;
     const u8* R = ln.R;
     int Score = 0;
-    Exon& eA = t->ex[h.nExons - 1];
-    Exon& eB = t->ex[h.nExons];
+    Exon& eA = COOP ? eAL : t->ex[nEx0 - 1];
+    Exon& eB = COOP ? eBL : t->ex[nEx0];
     const u64 outFilterMismatchNmaxTotal = ln.outFilterMismatchNmaxTotal;
 
     if (__builtin_expect(sjAB != SJA_NONE && eA.sjA == sjAB && eA.iFrag == iFragB && rBstart == rAend + 1 && gAend + 1 < gBstart, 0)) {
@@ -672,8 +677,17 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
             return -1000008;
         }
     }
-    t->ex[h.nExons - 1].iFrag = (u8)iFragB;
-    t->ex[h.nExons - 1].sjA = sjAB;
+    if constexpr (COOP) {
+        Exon& last = h.nExons == nEx0 ? eAL : eBL;
+        last.iFrag = (u8)iFragB;
+        last.sjA = sjAB;
+        __syncwarp();                                  // every lane has finished reading the shared transcript
+        if ((threadIdx.x & 31) == 0) { t->h = hL; t->ex[nEx0 - 1] = eAL; if (hL.nExons != nEx0) t->ex[nEx0] = eBL; }
+        __syncwarp();
+    } else {
+        t->ex[h.nExons - 1].iFrag = (u8)iFragB;
+        t->ex[h.nExons - 1].sjA = sjAB;
+    }
     return Score;
 }
 
@@ -738,7 +752,11 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     DevTr& t = *ln.leaf;
     if constexpr (COOP) warpCopyWords(&t, ln.cur, 20 + 6 * (u32)ln.cur->h.nExons);   // head and exons are contiguous
     else copyTr(&t, ln.cur);
-    TrHead& h = t.h;
+    // COOP: the leaf copy is shared by the warp: the head is worked on privately and written back by lane 0 at the end, the two exon
+    // updates of the end extensions are done by lane 0 followed by a __syncwarp
+    TrHead hL;
+    if constexpr (COOP) hL = t.h;
+    TrHead& h = COOP ? hL : t.h;
     const u64 Lread = ln.Lread;
     int vOrder[2];
     if (roStr == 0) { vOrder[0] = 0; vOrder[1] = 1; } else { vOrder[0] = 1; vOrder[1] = 0; }
@@ -753,9 +771,14 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
                                 P.outFilterMismatchNoverLmax, P.alignEndsTypeExt[imate][(int)(Str != imate)], er)) {
                     h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                     Score += er.maxScore;
-                    h.rStart -= er.extendL; t.ex[0].R = (u16)h.rStart;
-                    h.gStart -= er.extendL; t.ex[0].G = h.gStart;
-                    t.ex[0].L = (u16)(t.ex[0].L + er.extendL);
+                    h.rStart -= er.extendL;
+                    h.gStart -= er.extendL;
+                    if (!COOP || (threadIdx.x & 31) == 0) {
+                        t.ex[0].R = (u16)h.rStart;
+                        t.ex[0].G = h.gStart;
+                        t.ex[0].L = (u16)(t.ex[0].L + er.extendL);
+                    }
+                    if constexpr (COOP) __syncwarp();
                 }
             }
         } else {
@@ -766,7 +789,8 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
                     h.maxScore += er.maxScore; h.nMatch += er.nMatch; h.nMM += er.nMM;
                     Score += er.maxScore;
                     tR2 += er.extendL; tG2 += er.extendL;
-                    t.ex[h.nExons - 1].L = (u16)(t.ex[h.nExons - 1].L + er.extendL);
+                    if (!COOP || (threadIdx.x & 31) == 0) t.ex[h.nExons - 1].L = (u16)(t.ex[h.nExons - 1].L + er.extendL);
+                    if constexpr (COOP) __syncwarp();
                 }
             }
         }
@@ -851,6 +875,11 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     }
     h.maxScore = Score;
     h.iFrag = (t.ex[0].iFrag == t.ex[nEx - 1].iFrag) ? (signed char)t.ex[0].iFrag : (signed char)-1;
+    if constexpr (COOP) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) t.h = hL;
+        __syncwarp();
+    }
     return true;
 }
 
@@ -869,24 +898,36 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
     int wBest = ln.pool[wTr[0]].h.maxScore;
     if (Score + P.outFilterMultimapScoreRange >= wBest || (h.iFrag >= 0 && Score + P.outFilterMultimapScoreRange >= ln.maxScoreMate[h.iFrag])) {
         u32 iTr = 0;
-        h.mappedLength = 0;
+        // COOP (warp-uniform caller): the leaf, the slot table and the pool are shared by the warp, so lane 0 is the only writer and
+        // every write is followed by a __syncwarp before any lane reads it
+        u32 mappedLength = 0;
         #pragma unroll 1
-        for (u32 iex = 0; iex < nEx; iex++) h.mappedLength += t.ex[iex].L;
+        for (u32 iex = 0; iex < nEx; iex++) mappedLength += t.ex[iex].L;
+        if constexpr (COOP) {
+            if ((threadIdx.x & 31) == 0) h.mappedLength = mappedLength;
+            __syncwarp();
+        } else {
+            h.mappedLength = mappedLength;
+        }
         u32 n = *nWinTr;
         #pragma unroll 1
         while (iTr < n) {
             const DevTr& o = ln.pool[wTr[iTr]];
             u64 nOverlap = blocksOverlap(t, o);
-            u64 uNew = h.mappedLength - nOverlap;
+            u64 uNew = mappedLength - nOverlap;
             u64 uOld = o.h.mappedLength - nOverlap;
             if (uNew == 0 && Score < o.h.maxScore) {
                 break;
             } else if (uOld == 0) {
-                u16 p = wTr[iTr];
-                #pragma unroll 1
-                for (u32 ii = iTr + 1; ii < n; ii++) wTr[ii - 1] = wTr[ii];
+                if constexpr (COOP) __syncwarp();
+                if (!COOP || (threadIdx.x & 31) == 0) {
+                    u16 p = wTr[iTr];
+                    #pragma unroll 1
+                    for (u32 ii = iTr + 1; ii < n; ii++) wTr[ii - 1] = wTr[ii];
+                    wTr[n - 1] = p;
+                }
+                if constexpr (COOP) __syncwarp();
                 n--;
-                wTr[n] = p;
             } else if (uOld > 0 && (uNew > 0 || Score >= o.h.maxScore)) {
                 iTr++;
             }
@@ -898,10 +939,13 @@ __device__ void recordLeaf(Lane& ln, u16* wTr, u16* nWinTr) {
                 if (Score > o.h.maxScore || (Score == o.h.maxScore && h.gLength < o.h.gLength)) break;
             }
             u16 p = wTr[n];
-            #pragma unroll 1
-            for (int ii = (int)n; ii > (int)iTr; ii--) wTr[ii] = wTr[ii - 1];
-            wTr[iTr] = p;
-            if constexpr (COOP) warpCopyWords(&ln.pool[p], &t, 20 + 6 * nEx);   // (warp-uniform caller)
+            if constexpr (COOP) __syncwarp();          // (every lane has read wTr[n] and finished the scans above)
+            if (!COOP || (threadIdx.x & 31) == 0) {
+                #pragma unroll 1
+                for (int ii = (int)n; ii > (int)iTr; ii--) wTr[ii] = wTr[ii - 1];
+                wTr[iTr] = p;
+            }
+            if constexpr (COOP) warpCopyWords(&ln.pool[p], &t, 20 + 6 * nEx);   // (one word per lane; syncs before and after)
             else copyTr(&ln.pool[p], &t);
             if (n < P.alignTranscriptsPerWindowNmax) n++;
         }
@@ -1358,29 +1402,33 @@ __device__ __forceinline__ void readBegin(Lane& ln, const ReadInfo& ri) {
 
 // start of a window's stitching (ReadAlign_stitchPieces.cpp:281-294).  Returns 0 ok, 1 reference's per-read transcript budget reached
 // (:288-292, remaining windows are skipped), 2 this lane's pool is full (overflow tier).
-__device__ __forceinline__ int windowBegin(Lane& ln, u16*& wTr, u16& nWinTr) {
+__device__ __forceinline__ int windowBegin(Lane& ln, u16*& wTr, u16& nWinTr, bool writer = true) {   // writer: false on the lanes of a warp-uniform caller that do not own the shared state
     const star_params_t& P = *ln.P;
     if (ln.trNtotal + P.alignTranscriptsPerWindowNmax >= P.alignTranscriptsPerReadNmax) return 1;
     if (ln.trNtotal + 1 > ln.caps.maxTr) return 2;
     wTr = ln.trPtr + ln.trNtotal;
     nWinTr = 0;
     // *(trAll[iW1][0]) = trA : the window-best comparison starts from maxScore 0 (:293)
-    ln.pool[wTr[0]].h.maxScore = 0;
-    ln.pool[wTr[0]].h.nExons = 0;
+    if (writer) {
+        ln.pool[wTr[0]].h.maxScore = 0;
+        ln.pool[wTr[0]].h.nExons = 0;
+    }
     return 0;
 }
 
 // end of a window (:324-331)
-__device__ __forceinline__ void windowEnd(Lane& ln, u32 Chr, u32 Str, const u16* wTr, u16 nWinTr) {
+__device__ __forceinline__ void windowEnd(Lane& ln, u32 Chr, u32 Str, const u16* wTr, u16 nWinTr, bool writer = true) {
     if (nWinTr == 0) return;
     const TrHead& b = ln.pool[wTr[0]].h;
     if (b.maxScore > ln.bestScore || (b.maxScore == ln.bestScore && b.gLength < ln.bestGLength)) {
         ln.bestPool = wTr[0]; ln.bestScore = b.maxScore; ln.bestGLength = b.gLength;
     }
-    ln.winBase[ln.nW1] = (u16)ln.trNtotal;
-    ln.winN[ln.nW1] = nWinTr;
-    ln.win[ln.nW1].Chr = Chr;      // compact (iW1 <= iW): Chr/Str of the windows that have transcripts
-    ln.win[ln.nW1].Str = (u8)Str;
+    if (writer) {
+        ln.winBase[ln.nW1] = (u16)ln.trNtotal;
+        ln.winN[ln.nW1] = nWinTr;
+        ln.win[ln.nW1].Chr = Chr;      // compact (iW1 <= iW): Chr/Str of the windows that have transcripts
+        ln.win[ln.nW1].Str = (u8)Str;
+    }
     ln.trNtotal += nWinTr;
     ln.nW1++;
 }

@@ -381,23 +381,27 @@ __global__ void __launch_bounds__(128, MINB) flat_dfs_warp_kernel(const __grid_c
                 Frame& u = stack[nInc];
                 warpCopyWords(&u.h, &tcur->h, 20);
                 if (nEx0 > 0) warpCopyWords(&u.last, &tcur->ex[nEx0 - 1], 6);
-                u.Score = Score; u.tR2 = tR2; u.tG2 = tG2;
+                if (lane == 0) { u.Score = Score; u.tR2 = tR2; u.tG2 = tG2; }   // (shared state has ONE writer: lane 0; readers come after a __syncwarp)
                 int dScore;
                 if (nEx0 > 0) {
                     dScore = stitchAlignToTranscript<true>(ln, tR2, tG2, s.rStart, s.gStart, s.Length, s.iFrag, s.sjA, tcur);
                 } else {
-                    tcur->ex[0].R = s.rStart; tcur->h.rStart = s.rStart;
-                    tcur->ex[0].G = s.gStart; tcur->h.gStart = s.gStart;
-                    tcur->ex[0].L = s.Length; tcur->ex[0].iFrag = s.iFrag; tcur->ex[0].sjA = s.sjA;
-                    tcur->ex[0].canon = 0; tcur->ex[0].annot = 0; tcur->ex[0].sjStr = 0; tcur->ex[0].shL = 0; tcur->ex[0].shR = 0;
-                    tcur->h.nExons = 1;
+                    if (lane == 0) {
+                        tcur->ex[0].R = s.rStart; tcur->h.rStart = s.rStart;
+                        tcur->ex[0].G = s.gStart; tcur->h.gStart = s.gStart;
+                        tcur->ex[0].L = s.Length; tcur->ex[0].iFrag = s.iFrag; tcur->ex[0].sjA = s.sjA;
+                        tcur->ex[0].canon = 0; tcur->ex[0].annot = 0; tcur->ex[0].sjStr = 0; tcur->ex[0].shL = 0; tcur->ex[0].shR = 0;
+                        tcur->h.nExons = 1;
+                        tcur->h.nMatch = s.Length;
+                    }
                     dScore = s.Length;
-                    tcur->h.nMatch = s.Length;
                 }
                 __syncwarp();
                 if (dScore > -1000000) {
-                    if (s.Nrep == 1) tcur->h.nUnique++;
-                    if (s.Anchor > 0) tcur->h.nAnchor++;
+                    if (lane == 0) {
+                        if (s.Nrep == 1) tcur->h.nUnique++;
+                        if (s.Anchor > 0) tcur->h.nAnchor++;
+                    }
                     __syncwarp();
                     incl |= 1ULL << L;
                     if (!forced) open |= 1ULL << L;   // a forced include never explores its exclude branch
@@ -518,8 +522,9 @@ __global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __gri
                         c0.score = (short)(pk & 0xffffu); c0.iFrag = (signed char)(pk >> 16); c0.pad = 0;
                     }
                     if (w != curW) {
-                        if (openWin) { windowEnd(ln, Chr, Str, wTr, nWinTr); openWin = false; }
-                        const int rc = windowBegin(ln, wTr, nWinTr);
+                        if (openWin) { windowEnd(ln, Chr, Str, wTr, nWinTr, lane == 0); openWin = false; }
+                        const int rc = windowBegin(ln, wTr, nWinTr, lane == 0);   // (shared state: lane 0 is the only writer)
+                        __syncwarp();
                         if (rc == 2) { ln.overflow = 3; stop = true; break; }
                         if (rc == 1) { stop = true; break; }
                         const FlatWin W = fw[w];
@@ -547,12 +552,14 @@ __global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __gri
                                 warpCopyWords(ln.leaf, fa.trStore + c.trOff, 20 + 6 * nEx);
                                 recordLeaf<true>(ln, wTr, &nWinTr);
                             } else {
-                                int Score; u32 tR2; u64 tG2;
                                 nReplay++;
                                 __syncwarp();
-                                bool ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2);
-                                __syncwarp();
-                                ok = ok && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                u32 ok = 0;
+                                if (lane == 0) {   // re-evaluation of the path (only when the transcript store was exhausted): sequential code, one lane
+                                    int Score; u32 tR2; u64 tG2;
+                                    ok = replayPath(ln, WA, nA, c.mask, Score, tR2, tG2) && evalLeaf(ln, Score, tR2, tG2, Chr, Str, Str);
+                                }
+                                ok = __shfl_sync(0xffffffffu, ok, 0);
                                 __syncwarp();
                                 if (ok) recordLeaf<true>(ln, wTr, &nWinTr);
                             }
@@ -561,13 +568,13 @@ __global__ void __launch_bounds__(128, MINB) flat_record_warp_kernel(const __gri
                     }
                 }
             }
-            if (openWin) windowEnd(ln, Chr, Str, wTr, nWinTr);
+            if (openWin) windowEnd(ln, Chr, Str, wTr, nWinTr, lane == 0);
             #pragma unroll 1
             for (int off = 16; off > 0; off >>= 1) { ndP += __shfl_xor_sync(0xffffffffu, ndP, off); lvP += __shfl_xor_sync(0xffffffffu, lvP, off); }
             ln.nodes = ndP; ln.leaves = lvP;
         }
         __syncwarp();
-        selectExport(ln, ri, i, 0, 0, results, staged, info);
+        if (lane == 0) selectExport(ln, ri, i, 0, 0, results, staged, info);   // sequential code on the read's final state: one lane
         __syncwarp();
     }
     PROF_ADD(18, clock64() - tStart);
