@@ -282,12 +282,42 @@ int star_cli_main(int argc, char** argv);
  * counters24 may be NULL (then the shard files are summed). */
 int star_host_merge_shards(int argc, char** argv, int nShards, const uint64_t* counters24);
 
+/* ---- on-the-fly junction insertion (--sjdbFileChrStartEnd at the mapping stage, --twopassMode Basic) -------
+ * The device part of sjdbBuildIndex (reference source/sjdbBuildIndex.cpp:16-333).  The host side (star_b200/csrc/host/sjdb_insert.cpp)
+ * prepares the junction inserts (sjdbPrepare.cpp:5-225), sorts the insertion points and patches SAindex; the two steps that touch
+ * every new suffix / every SA row run on the GPU:
+ *   star_gpu_sjdb_search   = the suffixArraySearch1 loop (sjdbBuildIndex.cpp:50-87, SuffixArrayFuns.cpp:233-351): for every suffix of
+ *                            every insert (both strands) the SA row it has to be inserted in front of;
+ *   star_gpu_sjdb_merge_sa = the SA rewrite (sjdbBuildIndex.cpp:141-214): old rows re-based to the new genome length / new junction
+ *                            order, new rows spliced in, packed at GstrandBit+1 bits.
+ * All pointers are HOST pointers. */
+typedef struct star_sjdb star_sjdb_t;
+/* uploads G and SA of the index the junctions are inserted into */
+int star_gpu_sjdb_open(star_sjdb_t** h, int device, const star_index_view_t* oldIndex);
+/* Gsj: 2*nGsj+1 bytes, nGsj = sjdbN*sjdbLength: the sjdbN inserts (donor flank, acceptor flank, one code 5), then their reverse
+ * complement, then one code 5 (sjdbBuildIndex.cpp:32-40).  skipSeq[q], q in [0, 2*sjdbN): sequence q belongs to a junction that is
+ * already in the index (no rows are added for it).  indArray: 2 * (2*sjdbN*sjdbLength) words; for k = q*sjdbLength + start:
+ * indArray[2k] = SA row in front of which the suffix goes ((uint64)-1: none, (uint64)-2: after the last row), indArray[2k+1] = k. */
+int star_gpu_sjdb_search(star_sjdb_t* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray);
+/* indSorted: nInd pairs (row, offset in Gsj) in insertion order (funCompareUintAndSuffixes.cpp:6-43).  nGsj = total insert bytes of
+ * the NEW junction set, nGsjNew = bytes of the junctions that were not in the old index, oldSJind[j] = new index of old junction j
+ * (oldIndex->sjdbN entries).  SAnew receives nSAnewByte bytes = PackedArray of oldIndex->nSA + nInd rows. */
+int star_gpu_sjdb_merge_sa(star_sjdb_t* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
+                           const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
+void star_gpu_sjdb_close(star_sjdb_t* h);
+
 /* Engine indirection used by star_cli_main; tests drive the same host code with the CPU oracle. */
 typedef struct star_engine_vtbl {
     int (*init)(void** ctx, int device, const star_index_view_t*, const star_params_t*, uint32_t maxReads);
     int (*map_chunk)(void* ctx, const star_read_batch_t*, star_align_batch_t*, star_chunk_stats_t*);
     void (*destroy)(void* ctx);
     const char* (*last_error)(void);
+    /* junction insertion (same meaning as star_gpu_sjdb_*; the handle is opaque to the host code) */
+    int (*sjdb_open)(void** h, int device, const star_index_view_t* oldIndex);
+    int (*sjdb_search)(void* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray);
+    int (*sjdb_merge_sa)(void* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
+                         const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
+    void (*sjdb_close)(void* h);
 } star_engine_vtbl_t;
 int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine);
 

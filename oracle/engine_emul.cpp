@@ -24,6 +24,7 @@ thread_local CtaShared* cta;
 
 #include "../star_b200/csrc/engine/seed.cu"
 #include "../star_b200/csrc/engine/stitch.cu"
+#include "../star_b200/csrc/engine/sjdb_kernels.cuh"
 
 namespace starb { alignas(128) u8 smem[256 * 1024]; }   // dynamic shared memory of the (single) emulated CTA
 
@@ -367,6 +368,47 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     }
     out->nAligns = nAl;
     if (info4) { info4[0] = oldHeavy ? nHeavyA + nHeavyX : nRecs; info4[1] = n - nHeavyA; info4[2] = nOver; info4[3] = bumps[1]; }
+    return 0;
+}
+
+// ---- junction insertion: the kernels of sjdb_kernels.cuh as one emulated CTA each, around them what sjdb.cu does on the host ----
+namespace {
+struct SjdbHost {
+    SjdbIndex ix;
+    std::vector<u64> sa;
+    u64 sjGstart, sjdbNold;
+    explicit SjdbHost(const star_index_view_t* v) {
+        sa.assign((v->nSAbyte + 7) / 8 + 2, 0);
+        memcpy(sa.data(), v->SA, v->nSAbyte);
+        ix.G = v->G; ix.SA = sa.data(); ix.nGenome = v->nGenome; ix.nSA = v->nSA; ix.GstrandBit = v->GstrandBit; ix.saBits = v->GstrandBit + 1;
+        sjGstart = v->chrStart[v->nChrReal]; sjdbNold = v->sjdbN;
+    }
+};
+}  // namespace
+
+int engine_emul_sjdb_search(const star_index_view_t* v, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray) {
+    SjdbHost H(v);
+    const u64 nSeq = 2 * sjdbN, nSuf = nSeq * sjdbLength;
+    std::vector<u8> g(nSuf + 1 + 256, 5);
+    memcpy(g.data(), Gsj, nSuf + 1);
+    runCta(256, [&] { sjdb_search_kernel(H.ix, g.data(), nSeq, sjdbLength, skipSeq, (u64*)indArray); });
+    return 0;
+}
+
+int engine_emul_sjdb_merge_sa(const star_index_view_t* v, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
+                              const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte) {
+    SjdbHost H(v);
+    const u64 nSAnew = H.ix.nSA + nInd;
+    std::vector<u64> row(nInd + 1), val(nInd + 1);
+    sjdbInsertedRows(indSorted, nInd, H.ix.nSA, nGsj, H.sjGstart, H.ix.GstrandBit, row.data(), val.data());
+    std::vector<u64> out((nSAnew + 63) / 64 * H.ix.saBits + 2, 0);
+    SjdbMerge m;
+    m.insRow = row.data(); m.insVal = val.data(); m.nInd = nInd; m.nSAnew = nSAnew;
+    m.nGenomeOld = H.ix.nGenome; m.nGenomeNew = H.sjGstart + nGsj; m.sjGstart = H.sjGstart; m.sjdbLength = sjdbLength; m.sjdbNold = H.sjdbNold;
+    m.nGsjNew = nGsjNew; m.oldSJind = (const u32*)oldSJind;
+    runCta(256, [&] { sjdb_merge_sa_kernel(H.ix, m, out.data()); });
+    if (nSAnewByte > out.size() * 8) return STAR_EXIT_BUG;
+    memcpy(SAnew, out.data(), nSAnewByte);
     return 0;
 }
 

@@ -1619,7 +1619,139 @@ void star_oracle_dump_free(star_oracle_dump_t* d) {
     d->pcOff = nullptr; d->pc = nullptr;
 }
 
-static const star_engine_vtbl_t g_oracle_vtbl = {star_oracle_init, star_oracle_map_chunk, star_oracle_destroy, star_oracle_last_error};
+// ---- junction insertion: CPU restatement of the two device steps (checker for star_gpu_sjdb_*) -------------------------------------
+// Sequential, in the reference's own shape: suffixArraySearch1 / compareSeqToGenome1 / compareRefEnds (SuffixArrayFuns.cpp:221-351)
+// per suffix, and the single two-pointer sweep with PackedArray::writePacked of sjdbBuildIndex.cpp:141-214.
+namespace {
+struct SjdbOracle {
+    const star_index_view_t* v;
+    uint64_t saGet(uint64_t i) const {   // PackedArray.h:24-32
+        const uint64_t b = i * (v->GstrandBit + 1);
+        uint64_t w;
+        memcpy(&w, v->SA + b / 8, 8);
+        return (w >> (b % 8)) & (~0ULL >> (64 - (v->GstrandBit + 1)));
+    }
+    // compareSeqToGenome1 with dirR = true, gInsert = -1: s0 = the insert text, s1 = its complement (as the reference passes both)
+    uint64_t compare1(const uint8_t* s0, const uint8_t* s1, uint64_t S, uint64_t N, uint64_t L, uint64_t iSA, int& compRes) const {
+        uint64_t SAstr = saGet(iSA);
+        const bool dirG = (SAstr >> v->GstrandBit) == 0;
+        SAstr &= ~(1ULL << v->GstrandBit);
+        if (dirG) {
+            const uint8_t* s = s0 + S + L;
+            const uint8_t* g = v->G + SAstr + L;
+            for (uint64_t ii = 0; ii < N - L; ii++) {
+                if (s[ii] != g[ii]) { compRes = s[ii] > g[ii] ? 1 : -1; return ii + L; }
+                else if (s[ii] == 5) { compRes = 1; /* compareRefEnds: strG, strR, SAstr < -1 */ return ii + L; }
+            }
+            return N;
+        } else {
+            const uint8_t* s = s1 + S + L;
+            const uint8_t* g = v->G + v->nGenome - 1 - SAstr - L;
+            for (uint64_t ii = 0; ii < N - L; ii++) {
+                if (s[ii] != *(g - ii)) {
+                    uint8_t a = s[ii], b = *(g - ii);
+                    if (a < 4) a = 3 - a;
+                    if (b < 4) b = 3 - b;
+                    compRes = a > b ? 1 : -1;
+                    return ii + L;
+                } else if (s[ii] == 5) { compRes = -1; /* compareRefEnds: !strG, strR */ return ii + L; }
+            }
+            return N;
+        }
+    }
+    uint64_t search1(const uint8_t* s0, const uint8_t* s1, uint64_t S) const {
+        const uint64_t N = 10000;
+        int compRes = 0;
+        uint64_t i1 = 0, i2 = v->nSA - 1;
+        uint64_t L1 = compare1(s0, s1, S, N, 0, i1, compRes);
+        if (compRes < 0) return 0;
+        uint64_t L2 = compare1(s0, s1, S, N, 0, i2, compRes);
+        if (compRes > 0) return (uint64_t)-2;
+        uint64_t L = std::min(L1, L2);
+        while (i1 + 1 < i2) {
+            const uint64_t i3 = i1 / 2 + i2 / 2 + (i1 % 2 + i2 % 2) / 2;
+            const uint64_t L3 = compare1(s0, s1, S, N, L, i3, compRes);
+            if (L3 == N) return i3;
+            if (compRes > 0) { i1 = i3; L1 = L3; } else if (compRes < 0) { i2 = i3; L2 = L3; }
+            L = std::min(L1, L2);
+        }
+        return i2;
+    }
+};
+}  // namespace
+
+int star_oracle_sjdb_open(void** h, int, const star_index_view_t* oldIndex) {
+    SjdbOracle* o = new SjdbOracle;
+    o->v = oldIndex;
+    *h = o;
+    return 0;
+}
+int star_oracle_sjdb_search(void* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray) {
+    const SjdbOracle* o = (const SjdbOracle*)h;
+    const uint64_t nText = 2 * sjdbN * sjdbLength + 1;
+    std::vector<uint8_t> G1c(nText + 16, 5);
+    for (uint64_t i = 0; i < nText; i++) G1c[i] = Gsj[i] < 4 ? 3 - Gsj[i] : Gsj[i];   // complementSeqNumbers
+    for (uint64_t isj = 0; isj < 2 * sjdbN; isj++)
+        for (uint64_t istart = 0; istart < sjdbLength; istart++) {
+            const uint64_t k = isj * sjdbLength + istart;
+            if (skipSeq[isj] || Gsj[k] > 3) indArray[2 * k] = (uint64_t)-1;
+            else indArray[2 * k] = o->search1(Gsj + isj * sjdbLength, G1c.data() + isj * sjdbLength, istart);
+            indArray[2 * k + 1] = k;
+        }
+    return 0;
+}
+int star_oracle_sjdb_merge_sa(void* h, const uint64_t* ind, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength, const uint32_t* oldSJind,
+                              uint8_t* SAnew, uint64_t nSAnewByte) {
+    const SjdbOracle* o = (const SjdbOracle*)h;
+    const star_index_view_t* v = o->v;
+    const uint32_t bits = v->GstrandBit + 1;
+    const uint64_t mask = ~0ULL >> (64 - bits);
+    std::vector<uint8_t> buf(nSAnewByte + 16, 0);
+    auto put = [&](uint64_t jj, uint64_t x) {   // PackedArray::writePacked
+        const uint64_t b = jj * bits, S = b % 8;
+        uint64_t w;
+        memcpy(&w, buf.data() + b / 8, 8);
+        w = (w & ~(mask << S)) | (x << S);
+        memcpy(buf.data() + b / 8, &w, 8);
+    };
+    const uint64_t N2bit = 1ULL << v->GstrandBit, strandMask = ~N2bit;
+    const uint64_t sjG = v->chrStart[v->nChrReal], nGenome1 = v->nGenome, nGenome = sjG + nGsj;
+    uint64_t isj = 0, isa2 = 0;
+    for (uint64_t isa = 0; isa < v->nSA; isa++) {
+        while (isj < nInd && isa == ind[isj * 2]) {
+            uint64_t ind1 = ind[isj * 2 + 1];
+            if (ind1 < nGsj) ind1 += sjG; else ind1 = (ind1 - nGsj) | N2bit;
+            put(isa2, ind1);
+            ++isa2; ++isj;
+        }
+        uint64_t ind1 = o->saGet(isa);
+        if ((ind1 & N2bit) > 0) {
+            uint64_t ind1s = nGenome1 - (ind1 & strandMask);
+            if (ind1s >= sjG) {
+                const uint64_t sj1 = (ind1s - sjG) / sjdbLength;
+                if (sj1 < v->sjdbN) ind1s += ((uint64_t)oldSJind[sj1] - sj1) * sjdbLength;
+                ind1 = (nGenome - ind1s) | N2bit;
+            } else ind1 += nGsjNew;
+        } else if (ind1 >= sjG) {
+            const uint64_t sj1 = (ind1 - sjG) / sjdbLength;
+            if (sj1 < v->sjdbN) ind1 += ((uint64_t)oldSJind[sj1] - sj1) * sjdbLength;
+        }
+        put(isa2, ind1);
+        ++isa2;
+    }
+    for (; isj < nInd; isj++) {
+        uint64_t ind1 = ind[isj * 2 + 1];
+        if (ind1 < nGsj) ind1 += sjG; else ind1 = (ind1 - nGsj) | N2bit;
+        put(isa2, ind1);
+        ++isa2;
+    }
+    memcpy(SAnew, buf.data(), nSAnewByte);
+    return 0;
+}
+void star_oracle_sjdb_close(void* h) { delete (SjdbOracle*)h; }
+
+static const star_engine_vtbl_t g_oracle_vtbl = {star_oracle_init, star_oracle_map_chunk, star_oracle_destroy, star_oracle_last_error,
+                                                 star_oracle_sjdb_open, star_oracle_sjdb_search, star_oracle_sjdb_merge_sa, star_oracle_sjdb_close};
 const star_engine_vtbl_t* star_oracle_engine(void) { return &g_oracle_vtbl; }
 
 }  // extern "C"

@@ -26,6 +26,12 @@ const char* star_oracle_last_error(void);
 void star_oracle_kary_stats(uint64_t* checked, uint64_t* mismatch);
 void star_oracle_kary_cost(uint64_t* rounds, uint64_t* probes);
 void star_oracle_window_hist(uint64_t* windows16, uint64_t* nodes16);
+/* junction insertion: CPU restatement of star_gpu_sjdb_* (same arguments; include/star_b200.h) */
+int star_oracle_sjdb_open(void** h, int device, const star_index_view_t* oldIndex);
+int star_oracle_sjdb_search(void* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray);
+int star_oracle_sjdb_merge_sa(void* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
+                              const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
+void star_oracle_sjdb_close(void* h);
 const star_engine_vtbl_t* star_oracle_engine(void);
 
 #ifdef __cplusplus

@@ -54,6 +54,10 @@ using namespace starb;
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;
+namespace starb {   // used by sjdb.cu
+void setLastError(const std::string& m) { g_err = m; }
+void countLaunches(unsigned n) { g_launches += n; }
+}
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -761,7 +765,16 @@ static int vt_map(void* ctx, const star_read_batch_t* in, star_align_batch_t* ou
     return star_gpu_map_chunk((star_ctx_t*)ctx, in, out, st);
 }
 static void vt_destroy(void* ctx) { star_gpu_destroy((star_ctx_t*)ctx); }
-static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error};
+static int vt_sjdb_open(void** h, int device, const star_index_view_t* v) { return star_gpu_sjdb_open((star_sjdb_t**)h, device, v); }
+static int vt_sjdb_search(void* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* ind) {
+    return star_gpu_sjdb_search((star_sjdb_t*)h, Gsj, sjdbN, sjdbLength, skipSeq, ind);
+}
+static int vt_sjdb_merge(void* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength, const uint32_t* oldSJind,
+                         uint8_t* SAnew, uint64_t nSAnewByte) {
+    return star_gpu_sjdb_merge_sa((star_sjdb_t*)h, indSorted, nInd, nGsj, nGsjNew, sjdbLength, oldSJind, SAnew, nSAnewByte);
+}
+static void vt_sjdb_close(void* h) { star_gpu_sjdb_close((star_sjdb_t*)h); }
+static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close};
 
 int star_cli_main(int argc, char** argv) { return star_cli_main_engine(argc, argv, &g_cuda_engine); }
 

@@ -17,6 +17,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <filesystem>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -44,44 +45,15 @@ static void makeDirs(const std::string& prefix) {  // createDirectory, Parameter
     }
 }
 
-static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
-    HostParams P;
-    std::string err;
-    Stats stats;
-    time(&stats.timeStart);
-    int rc = parseCommandLine(argc, argv, P, err);
-    if (rc == -1 && err == "version") { std::cout << "2.7.11b" << std::endl; return 0; }
-    auto exitWithError = [&](const std::string& msg, int code, std::ofstream* logMain) {  // ErrorWarning.cpp:8-23
-        time_t t; time(&t);
-        if (logMain && logMain->is_open()) *logMain << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
-        std::cerr << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
-        return code;
-    };
-    if (rc) return exitWithError(err, rc, nullptr);
-    makeDirs(P.outFileNamePrefix);
-    std::ofstream logMain(P.outFileNamePrefix + "Log.out");
-    if (logMain.fail())
-        return exitWithError("EXITING because of FATAL ERROR: could not create output file: " + P.outFileNamePrefix + "Log.out\nSOLUTION: check if the path " + P.outFileNamePrefix + " exists and you have permissions to write there\n", STAR_EXIT_PARAMETER, nullptr);
-    logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
-    std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
-
-    {
-        time_t t; time(&t);
-        std::cout << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;
-    }
-    LoadedIndex idx;
-    std::string glog;
-    rc = loadIndex(P.genomeDir, &P.hp, idx, err, &glog);
-    logMain << glog << std::flush;
-    if (rc) return exitWithError(err, rc, &logMain);
-
-    void* ectx = nullptr;
-    rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);
-    if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
-
+// One mapping pass over the read files (ReadAlignChunk::processChunks / mapThreadsSpawn for all chunks): reads -> engine -> records.
+// Used for the main pass and, with the outputs switched off in P, for the 1st pass of --twopassMode Basic.
+// Returns 0 or a STAR_EXIT_* code with the message in err.
+static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engine_vtbl_t* eng, void* ectx, Stats& stats, std::vector<Junction>& allSJ,
+                   std::ofstream& logMain, std::string& err) {
+    int rc = 0;
     ReadsReader reader;
     rc = reader.open(P, err);
-    if (rc) { eng->destroy(ectx); return exitWithError(err, rc, &logMain); }
+    if (rc) return rc;
 
     OutputWriter W(P, idx);
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
@@ -96,9 +68,6 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
             else samOut << W.samHeader();
         }
     }
-    std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
-    time(&stats.timeStartMap);
-    std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
 
     // ---- three overlapped stages, chunks flow in input order through bounded queues (3 chunk buffers in flight):
     //   reader thread   : FASTQ/FASTA text -> ReadChunk                      (ReadAlignChunk_processChunks.cpp:11-282)
@@ -123,7 +92,6 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     std::vector<Work> bufs(NBUF);
     Queue freeQ, mapQ, outQ;
     for (auto& wk : bufs) freeQ.push(&wk);
-    std::vector<Junction> allSJ;
     // coordinate-sorted BAM: all records stay in host memory (uncompressed, ~0.55 kB per record) until the end of the run
     struct CoordRec { uint64_t alignG, key; uint32_t blob, size; uint64_t off; };
     std::vector<std::string> coordBlobs;
@@ -246,9 +214,8 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         for (auto& wk : bufs) freeQ.push(&wk);
     }
     readerThread.join();
-    if (runRc) { eng->destroy(ectx); return exitWithError(runErr, runRc, &logMain); }
-    if (!outErr.empty()) { eng->destroy(ectx); return exitWithError(outErr, STAR_EXIT_BUG, &logMain); }
-    eng->destroy(ectx);
+    if (runRc) { err = runErr; return runRc; }
+    if (!outErr.empty()) { err = outErr; return STAR_EXIT_BUG; }
     if (bamYes && P.gpuShardCount == 1) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
     if (streamYes) samOut.close();
     if (coordYes) {
@@ -277,11 +244,108 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         }
         size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); cb.write(e, ne);
     }
-    time_t tFinishMap; time(&tFinishMap);
-    std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
-    logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
     logMain << "star-b200: host time: reads input " << msRead << " ms, SAM/SJ formatting " << msFormat << " ms, output writes " << msWrite << " ms\n";
+    return 0;
+}
+
+static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
+    HostParams P;
+    std::string err;
+    Stats stats;
+    time(&stats.timeStart);
+    int rc = parseCommandLine(argc, argv, P, err);
+    if (rc == -1 && err == "version") { std::cout << "2.7.11b" << std::endl; return 0; }
+    auto exitWithError = [&](const std::string& msg, int code, std::ofstream* logMain) {  // ErrorWarning.cpp:8-23
+        time_t t; time(&t);
+        if (logMain && logMain->is_open()) *logMain << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
+        std::cerr << "\n" << msg << "\n" << timeMonthDayTime(t) << " ...... FATAL ERROR, exiting\n" << std::flush;
+        return code;
+    };
+    if (rc) return exitWithError(err, rc, nullptr);
+    makeDirs(P.outFileNamePrefix);
+    std::ofstream logMain(P.outFileNamePrefix + "Log.out");
+    if (logMain.fail())
+        return exitWithError("EXITING because of FATAL ERROR: could not create output file: " + P.outFileNamePrefix + "Log.out\nSOLUTION: check if the path " + P.outFileNamePrefix + " exists and you have permissions to write there\n", STAR_EXIT_PARAMETER, nullptr);
+    logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
+    std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
+
+    {
+        time_t t; time(&t);
+        std::cout << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;
+    }
+    LoadedIndex idx;
+    std::string glog;
+    rc = loadIndex(P.genomeDir, &P.hp, idx, err, &glog);
+    logMain << glog << std::flush;
+    if (rc) return exitWithError(err, rc, &logMain);
+
+    // ---- on-the-fly junction insertion (STAR.cpp:145-150) and the 1st pass of --twopassMode Basic (twoPassRunPass1.cpp:9-96)
+    SjdbLoci sjdbLoci;
+    if (P.sjdbInsertYes) {
+        if (idx.sjdbInfoExists && idx.sjdbInsertSaveGenome.empty())   // Genome_genomeLoad.cpp:95-101
+            return exitWithError("EXITING because of FATAL ERROR: old Genome is INCOMPATIBLE with on the fly junction insertion\nSOLUTION: please re-generate genome from scratch with the latest version of STAR\n", STAR_EXIT_GENOME_FILES, &logMain);
+        uint64_t ov = P.sjdbOverhang;                                  // Genome_genomeLoad.cpp:113-125
+        if (!P.userSet.count("sjdbOverhang") && idx.sjdbOverhangGenome > 0) {
+            ov = idx.sjdbOverhangGenome;
+            logMain << "--sjdbOverhang = " << ov << " taken from the generated genome\n";
+        } else if (idx.sjdbInfoExists && P.userSet.count("sjdbOverhang") && ov != idx.sjdbOverhangGenome)
+            return exitWithError("EXITING because of fatal PARAMETERS error: present --sjdbOverhang=" + std::to_string(ov) + " is not equal to the value at the genome generation step =" + std::to_string(idx.sjdbOverhangGenome) + "\nSOLUTION: \n", STAR_EXIT_GENOME_FILES, &logMain);
+        idx.view.sjdbOverhang = ov;
+        idx.view.sjdbLength = 2 * ov + 1;
+        for (const std::string* d : {&P.sjdbInsertOutDir, &P.twoPassDir}) {   // Parameters.cpp:817-825, 1027-1035: fresh run-time directories
+            if (d->empty()) continue;
+            std::error_code ec;
+            std::filesystem::remove_all(*d, ec);
+            if (mkdir(d->c_str(), 0700) != 0)
+                return exitWithError("EXITING because of fatal ERROR: could not make run-time directory: " + *d + "\nSOLUTION: please check the path and writing permissions \n", STAR_EXIT_PARAMETER, &logMain);
+        }
+    }
+    if (P.sjdbInsertPass1) {
+        rc = sjdbInsertJunctions(P, &P.hp, idx, sjdbLoci, false, "", eng, logMain, err);
+        if (rc) return exitWithError(err, rc, &logMain);
+    }
+    void* ectx = nullptr;
+    rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);
+    if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
+    std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
+    if (P.twoPassYes) {
+        HostParams P1 = P;   // outputs off, files into _STARpass1/ (twoPassRunPass1.cpp:17-47)
+        P1.outSAMtype = {"None"}; P1.outBAMunsorted = false; P1.outBAMcoord = false; P1.unmappedWithin = false; P1.unmappedKeepPairs = false;
+        P1.outFileNamePrefix = P.twoPassDir;
+        const uint64_t nMax = std::min<uint64_t>(P.twopass1readsN, (uint64_t)P.readMapNumber);
+        P1.readMapNumber = nMax > (uint64_t)INT64_MAX ? -1 : (long long)nMax;
+        Stats st1;
+        st1.timeStart = stats.timeStart;
+        time(&st1.timeStartMap);
+        std::cout << timeMonthDayTime(st1.timeStartMap) << " ..... started 1st pass mapping\n" << std::flush;
+        std::vector<Junction> sj1;
+        rc = mapPass(P1, idx, eng, ectx, st1, sj1, logMain, err);
+        eng->destroy(ectx);
+        if (rc) return exitWithError(err, rc, &logMain);
+        OutputWriter W1(P1, idx);
+        std::string e2 = W1.writeSJ(sj1, P.twoPassDir + "SJ.out.tab");
+        if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
+        time(&st1.timeFinish);
+        std::cout << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass mapping\n" << std::flush;
+        W1.writeLogFinal(st1, P.twoPassDir + "Log.final.out");
+        rc = sjdbInsertJunctions(P, &P.hp, idx, sjdbLoci, true, P.twoPassDir + "SJ.out.tab", eng, logMain, err);
+        if (rc) return exitWithError(err, rc, &logMain);
+        rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);   // the index with the inserted junctions becomes resident
+        if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
+    }
+    time(&stats.timeStartMap);
+    std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
+    std::vector<Junction> allSJ;
+    rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err);
+    eng->destroy(ectx);
+    if (rc) return exitWithError(err, rc, &logMain);
+    OutputWriter W(P, idx);
+    {
+        time_t tFinishMap; time(&tFinishMap);
+        std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
+        logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
+    }
     time(&stats.timeFinish);
     if (P.gpuShardCount > 1) {
         // one shard of a multi-GPU run: leave the counters and the (collapsed) junction records for the merge

@@ -62,8 +62,12 @@ int loadIndex(const std::string& gDirIn, star_params_t* p, LoadedIndex& L, std::
             else if (w1 == "sjdbOverhang") ls >> sjdbOverhangGen;
             else if (w1 == "genomeType") ls >> genomeType;
             else if (w1 == "genomeTransformType") ls >> transformType;
+            else if (w1 == "sjdbInsertSave") ls >> L.sjdbInsertSaveGenome;
         }
     }
+    L.genomeDir = gDir;
+    L.sjdbOverhangGenome = sjdbOverhangGen;
+    { struct stat st1; L.sjdbInfoExists = stat((gDir + "/sjdbInfo.txt").c_str(), &st1) == 0; }
     if (L.versionGenome.empty())
         return fail(STAR_EXIT_GENOME_FILES, "EXITING because of FATAL ERROR: read no value for the versionGenome parameter from genomeParameters.txt file\nSOLUTION: please re-generate genome from scratch with the latest version of STAR\n");
     if (L.versionGenome != "2.7.4a")  // Parameters.versionGenome of 2.7.11b (parametersDefault)
@@ -188,16 +192,25 @@ int loadIndex(const std::string& gDirIn, star_params_t* p, LoadedIndex& L, std::
     p->winBinChrNbits = gChrBinNbits - p->winBinNbits;
     p->winBinN = nGenome / (1ULL << p->winBinNbits) + 1;
 
-    v.G = L.Gstore.data() + PAD; v.nGenome = nGenome;
-    v.SA = L.SAstore.data(); v.nSA = nSA; v.nSAbyte = nSAbyte;
-    v.SAi = L.SAistore.data(); v.nSAi = nSAi; v.nSAibyte = nSAibyte;
+    v.nGenome = nGenome;
+    v.nSA = nSA; v.nSAbyte = nSAbyte;
+    v.nSAi = nSAi; v.nSAibyte = nSAibyte;
     v.GstrandBit = GstrandBit; v.gSAindexNbases = gSAindexNbases; v.gSAsparseD = gSAsparseD; v.gChrBinNbits = gChrBinNbits;
-    v.genomeSAindexStart = L.genomeSAindexStart.data();
-    v.nChrReal = nChrReal; v.chrStart = L.chrStart.data(); v.chrLength = L.chrLength.data();
-    v.sjdbStart = L.sjdbStart.data(); v.sjdbEnd = L.sjdbEnd.data(); v.sjDstart = L.sjDstart.data(); v.sjAstart = L.sjAstart.data();
-    v.sjdbMotif = L.sjdbMotif.data(); v.sjdbShiftLeft = L.sjdbShiftLeft.data(); v.sjdbShiftRight = L.sjdbShiftRight.data(); v.sjdbStrand = L.sjdbStrand.data();
+    v.nChrReal = nChrReal;
+    L.pointView();
     if (log) *log = lg.str();
     return 0;
+}
+
+void LoadedIndex::pointView() {
+    star_index_view_t& v = view;
+    v.G = Gstore.data() + 256;   // PAD of loadIndex
+    v.SA = SAstore.data();
+    v.SAi = SAistore.data();
+    v.genomeSAindexStart = genomeSAindexStart.data();
+    v.chrStart = chrStart.data(); v.chrLength = chrLength.data();
+    v.sjdbStart = sjdbStart.data(); v.sjdbEnd = sjdbEnd.data(); v.sjDstart = sjDstart.data(); v.sjAstart = sjAstart.data();
+    v.sjdbMotif = sjdbMotif.data(); v.sjdbShiftLeft = sjdbShiftLeft.data(); v.sjdbShiftRight = sjdbShiftRight.data(); v.sjdbStrand = sjdbStrand.data();
 }
 
 }  // namespace starhost

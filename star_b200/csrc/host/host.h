@@ -69,6 +69,15 @@ struct HostParams {
     std::string alignInsertionFlush = "None";
     std::string outMultimapperOrder = "Old_2.4";
     unsigned readNmates = 1;
+    // on-the-fly junction insertion / 2-pass (Parameters.cpp:240-269, 779-825, 1000-1035)
+    std::vector<std::string> sjdbFileChrStartEnd = {"-"};
+    uint64_t sjdbOverhang = 100;
+    std::string sjdbInsertSave = "Basic";
+    uint64_t limitSjdbInsertNsj = 1000000;
+    std::string twopassMode = "None";
+    uint64_t twopass1readsN = ~0ULL;
+    bool twoPassYes = false, sjdbInsertPass1 = false, sjdbInsertPass2 = false, sjdbInsertYes = false;
+    std::string twoPassDir, sjdbInsertOutDir;
     // star-b200 extensions (not in the reference)
     int gpuDevice = 0;
     unsigned gpuChunkReads = 262144;        // reads (pairs) per engine call
@@ -91,7 +100,26 @@ struct LoadedIndex {
     std::vector<uint64_t> chrBin;
     star_index_view_t view;
     std::string versionGenome;
+    uint64_t sjdbOverhangGenome = 0;      // sjdbOverhang of genomeParameters.txt
+    bool sjdbInfoExists = false;
+    std::string sjdbInsertSaveGenome;     // sjdbInsertSave of genomeParameters.txt ("" = index older than on-the-fly insertion)
+    std::string genomeDir;
+    void pointView();                     // re-points view.* at the vectors (after they were replaced)
 };
+
+// ---- on-the-fly junction insertion (sjdb_insert.cpp) ---------------------------------------------------------------------------
+struct SjdbLoci {   // sjdbClass.h
+    std::vector<std::string> chr;
+    std::vector<uint64_t> start, end;
+    std::vector<char> str;
+    std::vector<uint8_t> priority;
+};
+void sjdbLoadFromStream(std::istream& in, SjdbLoci& loci);   // sjdbLoadFromStream.cpp:2-28
+// sjdbInsertJunctions.cpp:11-102: loads the junction lists, prepares the inserts, rebuilds G / SA / SAi of `idx` in place (the device part
+// through eng->sjdb_*), writes sjdbInfo.txt / sjdbList.out.tab (and the whole index with --sjdbInsertSave All) to P.sjdbInsertOutDir and
+// re-computes hp->winBinN.  pass2: the junctions of `pass1sjFile` are added.  Returns 0 or a STAR_EXIT_* code with the message in err.
+int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx, SjdbLoci& loci, bool pass2, const std::string& pass1sjFile,
+                        const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err);
 int loadIndex(const std::string& genomeDir, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log, bool chrInfoOnly = false);
 
 // one chunk of reads in host memory

@@ -87,24 +87,24 @@ bool parseU64(const std::string& s, uint64_t& out) {
 const char* kUnsupported[] = {
     "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeFastaFiles", "genomeChainFiles", "genomeFileSizes",
     "genomeTransformOutput", "genomeChrSetMitochondrial", "genomeChrBinNbits", "genomeSAindexNbases", "genomeSAsparseD",
-    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType", "sjdbFileChrStartEnd", "sjdbGTFfile",
+    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType", "sjdbGTFfile",
     "sjdbGTFchrPrefix", "sjdbGTFfeatureExon", "sjdbGTFtagExonParentTranscript", "sjdbGTFtagExonParentGene",
-    "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "sjdbInsertSave", "varVCFfile", "readFilesType",
+    "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "varVCFfile", "readFilesType",
     "readFilesSAMattrKeep", "readFilesManifest", "readFilesPrefix", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitGenomeGenerateRAM", "limitIObufferSize",
-    "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitSjdbInsertNsj", "limitNreadsSoft",
+    "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitNreadsSoft",
     "outTmpDir", "outTmpKeep", "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
     "outSAMfilter", "outSAMtlen", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
     "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", "quantMode",
-    "quantTranscriptomeBAMcompression", "quantTranscriptomeSAMoutput", "twopassMode", "twopass1readsN", "waspOutputMode", "soloType",
+    "quantTranscriptomeBAMcompression", "quantTranscriptomeSAMoutput", "waspOutputMode", "soloType",
     "soloCBtype", "soloCBwhitelist", "soloCBstart", "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate",
     "soloCBposition", "soloUMIposition", "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype",
     "soloInputSAMattrBarcodeSeq", "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup",
     "soloUMIfiltering", "soloOutFileNames", "soloCellFilter", "soloOutFormatFeaturesGeneField3", "soloCellReadStats", "soloClusterCBfile",
-    "sjdbOverhang", "sjdbScoreX"};
+    "sjdbScoreX"};
 
 }  // namespace
 
@@ -154,6 +154,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     DBL("scoreGenomicLengthLog2scale", &h.scoreGenomicLengthLog2scale);
     I32("scoreDelOpen", &h.scoreDelOpen); I32("scoreDelBase", &h.scoreDelBase); I32("scoreInsOpen", &h.scoreInsOpen); I32("scoreInsBase", &h.scoreInsBase);
     I32("scoreStitchSJshift", &h.scoreStitchSJshift); I32("sjdbScore", &h.sjdbScore);
+    VSTR("sjdbFileChrStartEnd", &P.sjdbFileChrStartEnd); U64("sjdbOverhang", &P.sjdbOverhang); STR("sjdbInsertSave", &P.sjdbInsertSave);
+    U64("limitSjdbInsertNsj", &P.limitSjdbInsertNsj); STR("twopassMode", &P.twopassMode); U64("twopass1readsN", &P.twopass1readsN);
     U64("outFilterMismatchNmax", &h.outFilterMismatchNmax); DBL("outFilterMismatchNoverLmax", &h.outFilterMismatchNoverLmax);
     DBL("outFilterMismatchNoverReadLmax", &h.outFilterMismatchNoverReadLmax); I32("outFilterMultimapScoreRange", &h.outFilterMultimapScoreRange);
     U64("outFilterMultimapNmax", &h.outFilterMultimapNmax); I32("outFilterScoreMin", &h.outFilterScoreMin);
@@ -379,6 +381,28 @@ int finalizeParams(HostParams& P, std::string& err) {
         bool has = false;
         for (int c : P.outSAMattrOrder) if (c == 10) has = true;
         if (!has) P.outSAMattrOrder.push_back(10);
+    }
+    // 2-pass and on-the-fly junction insertion: Parameters.cpp:779-825, 1000-1035 (the directories are made by the run driver)
+    if (P.userSet.count("twopass1readsN") && P.twopassMode == "None")
+        return bad("EXITING because of fatal PARAMETERS error: --twopass1readsN is defined, but --twoPassMode is not defined\nSOLUTION: to activate the 2-pass mode, use --twopassMode Basic");
+    if (P.twopassMode != "None") {
+        if (P.twopassMode != "Basic")
+            return bad("EXITING because of fatal PARAMETERS error: unrecognized value of --twopassMode=" + P.twopassMode + "\nSOLUTION: for the 2-pass mode, use allowed values --twopassMode: Basic");
+        if (P.twopass1readsN == 0)
+            return bad("EXITING because of fatal PARAMETERS error: --twopass1readsN = 0 in the 2-pass mode\nSOLUTION: for the 2-pass mode, specify --twopass1readsN > 0. Use a very large number or -1 to map all reads in the 1st pass.\n");
+        P.twoPassYes = true;
+        P.twoPassDir = P.outFileNamePrefix + "_STARpass1/";
+    }
+    if (P.sjdbFileChrStartEnd[0] != "-") { P.sjdbInsertPass1 = true; P.sjdbInsertYes = true; }
+    if (P.twoPassYes) { P.sjdbInsertPass2 = true; P.sjdbInsertYes = true; }
+    if (P.sjdbInsertYes) {
+        if (P.sjdbOverhang == 0 || (long long)P.sjdbOverhang < 0)
+            return bad("EXITING because of fatal PARAMETERS error: pGe.sjdbOverhang <=0 while junctions are inserted on the fly with --sjdbFileChrStartEnd or/and --sjdbGTFfile\nSOLUTION: specify pGe.sjdbOverhang>0, ideally readmateLength-1");
+        if (P.sjdbInsertSave != "Basic" && P.sjdbInsertSave != "All")
+            return bad("EXITING because of fatal PARAMETERS error: unrecognized value of --sjdbInsertSave=" + P.sjdbInsertSave + "\nSOLUTION: use allowed values: Basic or All\n");
+        P.sjdbInsertOutDir = P.outFileNamePrefix + "_STARgenome/";
+        if (P.gpuShardCount > 1)
+            return bad("EXITING because of fatal input ERROR: junction insertion / --twopassMode is not supported for sharded (multi-GPU) runs yet: the 1st-pass junctions of all shards would have to be gathered first\n");
     }
     if (P.outBAMcoord && P.gpuShardCount > 1)
         return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported for sharded (multi-GPU) runs yet: use Unsorted and sort the merged file\n");

@@ -64,3 +64,29 @@ def log_counters(path):
                 continue
             out.append((k, v.strip()))
     return out
+
+
+@pytest.fixture(scope="session")
+def twopass_golden(tmp_path_factory):
+    """Unpacked tests/golden/twopass.tar.gz (junction insertion / 2-pass outputs of the unmodified reference; make_golden_twopass.py)."""
+    d = tmp_path_factory.mktemp("golden_tp")
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", "twopass.tar.gz")) as t:
+        t.extractall(d)
+    return str(d / "twopass")
+
+
+def check_twopass_outputs(out, ref):
+    """Everything the reference writes in a junction-insertion / 2-pass run: records, junctions, counters of both passes, the junction
+    database and (by digest) the rebuilt Genome / SA / SAindex."""
+    import hashlib
+    assert sam_body(out + "Aligned.out.sam") == sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert log_counters(out + "Log.final.out") == log_counters(os.path.join(ref, "Log.final.out"))
+    for f in ("_STARgenome/sjdbInfo.txt", "_STARgenome/sjdbList.out.tab", "_STARpass1/SJ.out.tab"):
+        if os.path.exists(os.path.join(ref, f)):
+            assert open(out + f, "rb").read() == open(os.path.join(ref, f), "rb").read(), f
+    if os.path.exists(os.path.join(ref, "_STARpass1/Log.final.out")):
+        assert log_counters(out + "_STARpass1/Log.final.out") == log_counters(os.path.join(ref, "_STARpass1/Log.final.out"))
+    for line in open(os.path.join(ref, "_STARgenome/sha256.txt")):
+        name, digest = line.split()
+        assert hashlib.sha256(open(out + "_STARgenome/" + name, "rb").read()).hexdigest() == digest, name

@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/twopass.tar.gz — run in the BUILD container only (needs oracle/_ref/STAR, i.e. /root/reference).
+
+Golden outputs of the UNMODIFIED reference binary for on-the-fly junction insertion and --twopassMode Basic,
+on the inputs of tiny.tar.gz:
+
+  twopass/idx0/                     reference genomeGenerate WITHOUT annotation (--genomeSAindexNbases 7): every junction is novel
+  twopass/sj_{half,dot,opp,shift}.tab   junction lists derived from tiny/idx/sjdbList.out.tab: every 2nd line; every 3rd with strand '.';
+                                    every 4th on the opposite strand; every 5th moved by 3 bases (mostly non-canonical)
+  twopass/scenarios.json            name -> argument list (relative to the unpacked tiny/ directory; TP = the unpacked twopass/ directory)
+  twopass/<name>/                   Aligned.out.sam, SJ.out.tab, Log.final.out, _STARpass1/{SJ.out.tab,Log.final.out},
+                                    _STARgenome/{sjdbInfo.txt,sjdbList.out.tab,sha256.txt}; sha256.txt = digests of the Genome, SA and
+                                    SAindex files the reference wrote with --sjdbInsertSave All
+"""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import tarfile
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+STAR = os.path.join(ROOT, "oracle", "_ref", "STAR")
+
+SCENARIOS = {
+    "A_novel": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
+    "B_annot": ["--genomeDir", "idx", "--readFilesIn", "std_1.fq", "std_2.fq", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
+    "C_files_hard": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--twopassMode", "Basic", "--sjdbInsertSave", "All",
+                     "--sjdbFileChrStartEnd", "TP/sj_half.tab", "TP/sj_dot.tab", "TP/sj_opp.tab", "TP/sj_shift.tab", "--sjdbOverhang", "80"],
+    "D_annot_files_se": ["--genomeDir", "idx", "--readFilesIn", "se_1.fq", "--twopassMode", "Basic", "--sjdbInsertSave", "All",
+                         "--sjdbFileChrStartEnd", "TP/sj_dot.tab", "TP/sj_opp.tab", "TP/sj_shift.tab", "--twopass1readsN", "300"],
+    "E_insert_only": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbInsertSave", "All",
+                      "--sjdbFileChrStartEnd", "TP/sj_half.tab", "TP/sj_opp.tab"],
+}
+KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
+        "_STARgenome/sjdbList.out.tab"]
+
+
+def sha(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="golden_tp_")
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", "tiny.tar.gz")) as t:
+        t.extractall(tmp)
+    tiny = os.path.join(tmp, "tiny")
+    tp = os.path.join(tmp, "twopass")
+    os.makedirs(os.path.join(tp, "idx0"))
+    subprocess.check_call([STAR, "--runMode", "genomeGenerate", "--genomeDir", os.path.join(tp, "idx0"), "--genomeFastaFiles", "genome.fa",
+                           "--genomeSAindexNbases", "7", "--runThreadN", "4", "--outFileNamePrefix", os.path.join(tmp, "gen0_")], cwd=tiny, stdout=subprocess.DEVNULL)
+    os.remove(os.path.join(tp, "idx0", "Log.out"))
+    rows = [l.split("\t") for l in open(os.path.join(tiny, "idx", "sjdbList.out.tab")).read().splitlines()]
+    with open(os.path.join(tp, "sj_half.tab"), "w") as f:
+        f.writelines("\t".join(r) + "\n" for i, r in enumerate(rows, 1) if i % 2 == 0)
+    with open(os.path.join(tp, "sj_dot.tab"), "w") as f:
+        f.writelines("\t".join(r[:3] + ["."]) + "\n" for i, r in enumerate(rows, 1) if i % 3 == 0)
+    with open(os.path.join(tp, "sj_opp.tab"), "w") as f:
+        f.writelines("\t".join(r[:3] + ["-" if r[3] == "+" else "+"]) + "\n" for i, r in enumerate(rows, 1) if i % 4 == 0)
+    with open(os.path.join(tp, "sj_shift.tab"), "w") as f:
+        f.writelines("\t".join([r[0], str(int(r[1]) + 3), str(int(r[2]) + 3), r[3]]) + "\n" for i, r in enumerate(rows, 1) if i % 5 == 0)
+    for name, args in SCENARIOS.items():
+        out = os.path.join(tmp, "run_" + name) + "/"
+        os.makedirs(out)
+        a = [x.replace("TP/", tp + "/") for x in args]
+        subprocess.check_call([STAR] + a + ["--outFileNamePrefix", out, "--runThreadN", "1"], cwd=tiny, stdout=subprocess.DEVNULL)
+        dst = os.path.join(tp, name)
+        for k in KEEP:
+            if os.path.exists(out + k):
+                os.makedirs(os.path.dirname(os.path.join(dst, k)), exist_ok=True)
+                shutil.copy(out + k, os.path.join(dst, k))
+        with open(os.path.join(dst, "_STARgenome", "sha256.txt"), "w") as f:
+            for g in ("Genome", "SA", "SAindex"):
+                f.write("%s\t%s\n" % (g, sha(out + "_STARgenome/" + g)))
+    with open(os.path.join(tp, "scenarios.json"), "w") as f:
+        json.dump(SCENARIOS, f, indent=1)
+    dst = os.path.join(ROOT, "tests", "golden", "twopass.tar.gz")
+    with tarfile.open(dst, "w:gz", compresslevel=9) as t:
+        t.add(tp, arcname="twopass")
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+    shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""On-the-fly junction insertion and --twopassMode Basic against outputs of the UNMODIFIED reference
+(tests/golden/twopass.tar.gz, make_golden_twopass.py): Aligned.out.sam, SJ.out.tab, Log.final.out of both passes, sjdbInfo.txt /
+sjdbList.out.tab and the bytes of the rebuilt Genome / SA / SAindex (--sjdbInsertSave All, compared by digest).
+
+CPU: the repository's host code (star_b200/csrc/host/sjdb_insert.cpp + driver) with (a) the oracle's sequential restatement of the
+two device steps and (b) the EMULATED CUDA kernels of sjdb_kernels.cuh (oracle/engine_emul.cpp through the test-only CLI).
+GPU: the drop-in CLI, i.e. the real kernels behind star_gpu_sjdb_*.
+"""
+import json
+import os
+import subprocess
+
+import pytest
+
+import conftest as cf
+import oracle_capi as oc
+
+ROOT = cf.ROOT
+NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only"]
+
+
+def _args(tp, golden, name):
+    sc = json.load(open(os.path.join(tp, "scenarios.json")))[name]
+    out = []
+    for a in sc:
+        if a.startswith("TP/"):
+            out.append(os.path.join(tp, a[3:]))
+        elif a in ("idx",) or a.endswith(".fq"):
+            out.append(os.path.join(golden, a))
+        else:
+            out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_cli_twopass_matches_reference(oracle, golden, twopass_golden, tmp_path, name):
+    out = str(tmp_path) + "/"
+    subprocess.check_call([oc.ORACLE_CLI] + _args(twopass_golden, golden, name) + ["--outFileNamePrefix", out, "--runThreadN", "2"], stdout=subprocess.DEVNULL)
+    cf.check_twopass_outputs(out, os.path.join(twopass_golden, name))
+
+
+@pytest.mark.parametrize("name", ["B_annot", "C_files_hard"])
+def test_emulated_sjdb_kernels_match_reference(oracle, golden, twopass_golden, tmp_path, name):
+    """sjdb_search_kernel / sjdb_merge_sa_kernel compiled for the host: old junctions that move (B), two insertions in one run (C)."""
+    out = str(tmp_path) + "/"
+    env = dict(os.environ, STAR_CLI_SJDB_EMUL=os.path.join(ROOT, "oracle", "_build", "libengine_emul.so"))
+    subprocess.check_call([oc.ORACLE_CLI] + _args(twopass_golden, golden, name) + ["--outFileNamePrefix", out, "--runThreadN", "2"], stdout=subprocess.DEVNULL, env=env)
+    cf.check_twopass_outputs(out, os.path.join(twopass_golden, name))
+
+
+def test_twopass_parameter_errors(oracle, golden, twopass_golden, tmp_path):
+    """Parameters.cpp:779-825, 1019-1026 and sjdbPrepare.cpp:24-29: exit codes of the reference."""
+    base = [oc.ORACLE_CLI, "--genomeDir", os.path.join(twopass_golden, "idx0"), "--readFilesIn", os.path.join(golden, "se_1.fq"), "--outFileNamePrefix", str(tmp_path) + "/"]
+    def rc(extra):
+        return subprocess.run(base + extra, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode
+    assert rc(["--twopass1readsN", "100"]) == 102                 # without --twopassMode
+    assert rc(["--twopassMode", "Full"]) == 102
+    assert rc(["--twopassMode", "Basic", "--twopass1readsN", "0"]) == 102
+    assert rc(["--twopassMode", "Basic", "--sjdbOverhang", "0"]) == 102
+    assert rc(["--twopassMode", "Basic", "--gpuShardCount", "2", "--gpuShardIndex", "0"]) == 102
+    bad = os.path.join(str(tmp_path), "bad.tab")
+    open(bad, "w").write("chrNope\t100\t200\t+\n")
+    assert rc(["--sjdbFileChrStartEnd", bad]) == 104
+    assert rc(["--sjdbFileChrStartEnd", os.path.join(str(tmp_path), "missing.tab")]) == 104
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_cli_twopass_matches_reference(lib, golden, twopass_golden, tmp_path, name):
+    out = str(tmp_path) + "/"
+    subprocess.check_call([os.path.join(ROOT, "star_b200", "bin", "STAR")] + _args(twopass_golden, golden, name) + ["--outFileNamePrefix", out, "--runThreadN", "2"],
+                          stdout=subprocess.DEVNULL)
+    cf.check_twopass_outputs(out, os.path.join(twopass_golden, name))
