@@ -71,6 +71,8 @@ struct HostParams {
     unsigned readNmates = 1;
     // on-the-fly junction insertion / 2-pass (Parameters.cpp:240-269, 779-825, 1000-1035)
     std::vector<std::string> sjdbFileChrStartEnd = {"-"};
+    std::string sjdbGTFfile = "-", sjdbGTFchrPrefix = "-", sjdbGTFfeatureExon = "exon", sjdbGTFtagExonParentTranscript = "transcript_id",
+                sjdbGTFtagExonParentGene = "gene_id";
     uint64_t sjdbOverhang = 100;
     std::string sjdbInsertSave = "Basic";
     uint64_t limitSjdbInsertNsj = 1000000;

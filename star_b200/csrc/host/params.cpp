@@ -87,8 +87,7 @@ bool parseU64(const std::string& s, uint64_t& out) {
 const char* kUnsupported[] = {
     "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeFastaFiles", "genomeChainFiles", "genomeFileSizes",
     "genomeTransformOutput", "genomeChrSetMitochondrial", "genomeChrBinNbits", "genomeSAindexNbases", "genomeSAsparseD",
-    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType", "sjdbGTFfile",
-    "sjdbGTFchrPrefix", "sjdbGTFfeatureExon", "sjdbGTFtagExonParentTranscript", "sjdbGTFtagExonParentGene",
+    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "varVCFfile", "readFilesType",
     "readFilesSAMattrKeep", "readFilesManifest", "readFilesPrefix", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitGenomeGenerateRAM", "limitIObufferSize",
@@ -154,6 +153,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     DBL("scoreGenomicLengthLog2scale", &h.scoreGenomicLengthLog2scale);
     I32("scoreDelOpen", &h.scoreDelOpen); I32("scoreDelBase", &h.scoreDelBase); I32("scoreInsOpen", &h.scoreInsOpen); I32("scoreInsBase", &h.scoreInsBase);
     I32("scoreStitchSJshift", &h.scoreStitchSJshift); I32("sjdbScore", &h.sjdbScore);
+    STR("sjdbGTFfile", &P.sjdbGTFfile); STR("sjdbGTFchrPrefix", &P.sjdbGTFchrPrefix); STR("sjdbGTFfeatureExon", &P.sjdbGTFfeatureExon);
+    STR("sjdbGTFtagExonParentTranscript", &P.sjdbGTFtagExonParentTranscript); STR("sjdbGTFtagExonParentGene", &P.sjdbGTFtagExonParentGene);
     VSTR("sjdbFileChrStartEnd", &P.sjdbFileChrStartEnd); U64("sjdbOverhang", &P.sjdbOverhang); STR("sjdbInsertSave", &P.sjdbInsertSave);
     U64("limitSjdbInsertNsj", &P.limitSjdbInsertNsj); STR("twopassMode", &P.twopassMode); U64("twopass1readsN", &P.twopass1readsN);
     U64("outFilterMismatchNmax", &h.outFilterMismatchNmax); DBL("outFilterMismatchNoverLmax", &h.outFilterMismatchNoverLmax);
@@ -393,7 +394,7 @@ int finalizeParams(HostParams& P, std::string& err) {
         P.twoPassYes = true;
         P.twoPassDir = P.outFileNamePrefix + "_STARpass1/";
     }
-    if (P.sjdbFileChrStartEnd[0] != "-") { P.sjdbInsertPass1 = true; P.sjdbInsertYes = true; }
+    if (P.sjdbFileChrStartEnd[0] != "-" || P.sjdbGTFfile != "-") { P.sjdbInsertPass1 = true; P.sjdbInsertYes = true; }
     if (P.twoPassYes) { P.sjdbInsertPass2 = true; P.sjdbInsertYes = true; }
     if (P.sjdbInsertYes) {
         if (P.sjdbOverhang == 0 || (long long)P.sjdbOverhang < 0)

@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <set>
 #include <sstream>
 
 #include "host.h"
@@ -197,6 +199,108 @@ bool copyFile(const std::string& a, const std::string& b) {
 
 }  // namespace
 
+// The junction part of GTF::GTF + GTF::transcriptGeneSJ (GTF.cpp:7-200, GTF_transcriptGeneSJ.cpp:23-183): exon lines -> exons per
+// transcript -> introns between consecutive exons, collapsed by (start, end, strand); writes sjdbList.fromGTF.out.tab.  The transcript /
+// exon / gene tables of the reference (exonInfo.tab, transcriptInfo.tab, geneInfo.tab, exonGeTrInfo.tab) serve --quantMode and are not written.
+static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const std::string& outDir, SjdbLoci& loci, std::ostream& logMain, std::string& err) {
+    std::ifstream in(P.sjdbGTFfile);
+    if (in.fail()) { err = "FATAL error, could not open file pGe.sjdbGTFfile=" + P.sjdbGTFfile + "\n"; return STAR_EXIT_INPUT_FILES; }
+    std::map<std::string, uint32_t> chrIndex;
+    for (uint32_t i = 0; i < idx.view.nChrReal; i++) chrIndex[idx.chrName[i]] = i;
+    std::map<std::string, uint64_t> trNumber, geNumber;
+    std::vector<uint8_t> trStrand;
+    struct Ex { uint64_t t, s, e, g; };
+    std::vector<Ex> ex;
+    uint64_t nExonLines = 0;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string chr1, f2, feature;
+        ls >> chr1 >> f2 >> feature;
+        if (chr1.substr(0, 1) == "#" || feature != P.sjdbGTFfeatureExon) continue;
+        nExonLines++;
+        if (P.sjdbGTFchrPrefix != "-") chr1 = P.sjdbGTFchrPrefix + chr1;
+        auto ci = chrIndex.find(chr1);
+        if (ci == chrIndex.end()) {
+            logMain << "WARNING: while processing sjdbGTFfile=" << P.sjdbGTFfile << ": chromosome '" << chr1 << "' not found in Genome fasta files for line:\n" << line << "\n";
+            continue;
+        }
+        uint64_t ex1 = 0, ex2 = 0;
+        char str1 = '.';
+        ls >> ex1 >> ex2 >> f2 >> str1 >> f2;
+        if (ex2 > idx.chrLength[ci->second]) {
+            logMain << "WARNING: while processing sjdbGTFfile=" << P.sjdbGTFfile << ", line:\n" << line << "\n exon end = " << ex2 << " is larger than the chromosome " << chr1
+                    << " length = " << idx.chrLength[ci->second] << " , will skip this exon\n";
+            continue;
+        }
+        std::string attrs;
+        std::getline(ls, attrs);
+        for (char& c : attrs) if (c == ';' || c == '=' || c == '\t' || c == '"') c = ' ';
+        auto attr = [&](const std::string& name) {
+            std::string v;
+            size_t pos = attrs.find(" " + name + " ");
+            if (pos != std::string::npos) pos = attrs.find_first_not_of(" ", pos + name.size() + 1);
+            if (pos != std::string::npos) v = attrs.substr(pos, attrs.find_first_of(" ", pos) - pos);
+            return v;
+        };
+        std::string trID = attr(P.sjdbGTFtagExonParentTranscript), gID = attr(P.sjdbGTFtagExonParentGene);
+        if (trID.empty()) {
+            logMain << "WARNING: while processing pGe.sjdbGTFfile=" << P.sjdbGTFfile << ": no transcript_id for line:\n" << line << "\n";
+            trID = "tr_" + chr1 + "_" + std::to_string(ex1) + "_" + std::to_string(ex2) + "_" + std::to_string(ex.size());
+        }
+        if (gID.empty()) {
+            logMain << "WARNING: while processing pGe.sjdbGTFfile=" << P.sjdbGTFfile << ": no gene_id for line:\n" << line << "\n";
+            gID = "MissingGeneID";
+        }
+        auto ti = trNumber.insert({trID, trNumber.size()});
+        if (ti.second) trStrand.push_back(str1 == '+' ? 1 : (str1 == '-' ? 2 : 0));
+        auto gi = geNumber.insert({gID, geNumber.size()});
+        ex.push_back(Ex{ti.first->second, ex1 + idx.chrStart[ci->second] - 1, ex2 + idx.chrStart[ci->second] - 1, gi.first->second});
+    }
+    if (nExonLines == 0) {
+        err = "Fatal INPUT FILE error, no exon lines in the GTF file: " + P.sjdbGTFfile + "\nSolution: check the formatting of the GTF file, it must contain some lines with exon in the 3rd column.\n          Make sure the GTF file is unzipped.\n          If exons are marked with a different word, use --sjdbGTFfeatureExon .\n";
+        return STAR_EXIT_INPUT_FILES;
+    }
+    if (ex.empty()) {
+        err = "Fatal INPUT FILE error, no valid exon lines in the GTF file: " + P.sjdbGTFfile + "\nSolution: check the formatting of the GTF file. One likely cause is the difference in chromosome naming between GTF and FASTA file.\n";
+        return STAR_EXIT_INPUT_FILES;
+    }
+    std::stable_sort(ex.begin(), ex.end(), [](const Ex& a, const Ex& b) { return a.t != b.t ? a.t < b.t : a.s < b.s; });   // funCompareUint2 on (transcript, start)
+    struct Sj { uint64_t s, e, str, g; };
+    std::vector<Sj> sj;
+    uint64_t trCur = ex[0].t;
+    for (size_t i = 1; i < ex.size(); i++) {
+        if (trCur != ex[i].t) { trCur = ex[i].t; continue; }
+        if (ex[i].s <= ex[i - 1].e + 1) continue;   // touching or overlapping exons: no intron
+        sj.push_back(Sj{ex[i - 1].e + 1, ex[i].s - 1, trStrand[trCur], ex[i].g + 1});
+    }
+    std::stable_sort(sj.begin(), sj.end(), [](const Sj& a, const Sj& b) { return a.s != b.s ? a.s < b.s : a.e < b.e; });
+    const char strandChar[3] = {'.', '+', '-'};
+    const size_t n0 = loci.chr.size();
+    std::vector<std::set<uint64_t>> genes;
+    for (size_t i = 0; i < sj.size(); i++) {
+        if (i == 0 || sj[i].s != sj[i - 1].s || sj[i].e != sj[i - 1].e || sj[i].str != sj[i - 1].str) {
+            const uint64_t chr1 = idx.chrBin[sj[i].s >> idx.view.gChrBinNbits];
+            loci.chr.push_back(idx.chrName[chr1]);
+            loci.start.push_back(sj[i].s + 1 - idx.chrStart[chr1]);
+            loci.end.push_back(sj[i].e + 1 - idx.chrStart[chr1]);
+            loci.str.push_back(strandChar[sj[i].str]);
+            genes.push_back({sj[i].g});
+        } else genes.back().insert(sj[i].g);
+    }
+    std::ofstream list(outDir + "/sjdbList.fromGTF.out.tab");
+    for (size_t i = n0; i < loci.chr.size(); i++) {
+        list << loci.chr[i] << "\t" << loci.start[i] << "\t" << loci.end[i] << "\t" << loci.str[i];
+        bool first = true;
+        for (uint64_t g : genes[i - n0]) { list << (first ? "\t" : ",") << g; first = false; }
+        list << "\n";
+    }
+    loci.priority.resize(loci.chr.size(), 20);
+    logMain << "Processing pGe.sjdbGTFfile=" << P.sjdbGTFfile << ", found:\n\t\t" << trNumber.size() << " transcripts\n\t\t" << ex.size() << " exons (non-collapsed)\n\t\t"
+            << loci.chr.size() - n0 << " collapsed junctions\nTotal junctions: " << loci.chr.size() << "\n";
+    return 0;
+}
+
 int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx, SjdbLoci& loci, bool pass2, const std::string& pass1sjFile,
                         const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err) {
     star_index_view_t& v = idx.view;
@@ -214,13 +318,18 @@ int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx
         sjdbLoadFromStream(in, loci);
         loci.priority.resize(loci.chr.size(), 0);
         logMain << "   Loaded database junctions from the 1st pass file: " << pass1sjFile << ": " << loci.chr.size() << " total junctions\n\n";
-    } else if (P.sjdbFileChrStartEnd[0] != "-") {   // sjdbLoadFromFiles.cpp:6-26
-        for (const std::string& fn : P.sjdbFileChrStartEnd) {
-            std::ifstream in(fn);
-            if (in.fail()) { err = "FATAL INPUT error, could not open input file pGe.sjdbFileChrStartEnd=" + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
-            sjdbLoadFromStream(in, loci);
-            loci.priority.resize(loci.chr.size(), 10);
-            logMain << "   Loaded database junctions from the pGe.sjdbFileChrStartEnd file(s), total number of junctions:" << loci.chr.size() << "\n\n";
+    } else {
+        if (P.sjdbFileChrStartEnd[0] != "-")   // sjdbLoadFromFiles.cpp:6-26
+            for (const std::string& fn : P.sjdbFileChrStartEnd) {
+                std::ifstream in(fn);
+                if (in.fail()) { err = "FATAL INPUT error, could not open input file pGe.sjdbFileChrStartEnd=" + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
+                sjdbLoadFromStream(in, loci);
+                loci.priority.resize(loci.chr.size(), 10);
+                logMain << "   Loaded database junctions from the pGe.sjdbFileChrStartEnd file(s), total number of junctions:" << loci.chr.size() << "\n\n";
+            }
+        if (P.sjdbGTFfile != "-") {
+            int rcg = sjdbLoadFromGTF(P, idx, outDir, loci, logMain, err);
+            if (rcg) return rcg;
         }
     }
     const uint64_t sjdbOverhang = v.sjdbOverhang, sjdbLength = v.sjdbLength;

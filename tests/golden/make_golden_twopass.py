@@ -32,9 +32,12 @@ SCENARIOS = {
                          "--sjdbFileChrStartEnd", "TP/sj_dot.tab", "TP/sj_opp.tab", "TP/sj_shift.tab", "--twopass1readsN", "300"],
     "E_insert_only": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbInsertSave", "All",
                       "--sjdbFileChrStartEnd", "TP/sj_half.tab", "TP/sj_opp.tab"],
+    "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
+    "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
+                            "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
 }
 KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
-        "_STARgenome/sjdbList.out.tab"]
+        "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab"]
 
 
 def sha(path):

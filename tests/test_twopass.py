@@ -16,7 +16,7 @@ import conftest as cf
 import oracle_capi as oc
 
 ROOT = cf.ROOT
-NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only"]
+NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only", "F_gtf_insert", "G_gtf_files_twopass"]
 
 
 def _args(tp, golden, name):
@@ -25,7 +25,7 @@ def _args(tp, golden, name):
     for a in sc:
         if a.startswith("TP/"):
             out.append(os.path.join(tp, a[3:]))
-        elif a in ("idx",) or a.endswith(".fq"):
+        elif a in ("idx",) or a.endswith(".fq") or a.endswith(".gtf"):
             out.append(os.path.join(golden, a))
         else:
             out.append(a)
