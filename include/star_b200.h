@@ -306,6 +306,12 @@ int star_gpu_sjdb_merge_sa(star_sjdb_t* h, const uint64_t* indSorted, uint64_t n
                            const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
 void star_gpu_sjdb_close(star_sjdb_t* h);
 
+/* Sharded --twopassMode Basic: between the two phases (--gpuTwoPassPhase 1 / 2 of every rank) the collapsed 1st-pass junction records of
+ * all shards are all-gathered (star_b200.dist: sizes, then payload, over NCCL / gloo); every rank stores them as <dir>gather<r>.bin and
+ * calls this with the ORIGINAL command line to get the same global <dir>SJ.out.tab (collapse + filters of outputSJ.cpp:20-200 over all
+ * shards) and <dir>Log.final.out; dir = <shard prefix>_STARpass1/. */
+int star_host_merge_pass1(int argc, char** argv, int nShards, const char* dir);
+
 /* Engine indirection used by star_cli_main; tests drive the same host code with the CPU oracle. */
 typedef struct star_engine_vtbl {
     int (*init)(void** ctx, int device, const star_index_view_t*, const star_params_t*, uint32_t maxReads);

@@ -45,6 +45,19 @@ static void makeDirs(const std::string& prefix) {  // createDirectory, Parameter
     }
 }
 
+// what one shard of a multi-GPU run leaves for the merge: the 24 counters, 3 times, the collapsed junction records
+static void writeShardBin(const std::string& path, const Stats& stats, const std::vector<Junction>& sj) {
+    std::ofstream sb(path, std::ios::binary);
+    uint64_t cnt[Stats::N_COUNTERS];
+    stats.toArray(cnt);
+    int64_t tm[3] = {(int64_t)stats.timeStart, (int64_t)stats.timeStartMap, (int64_t)stats.timeFinish};
+    uint64_t nsj = sj.size();
+    sb.write((const char*)cnt, sizeof(cnt));
+    sb.write((const char*)tm, sizeof(tm));
+    sb.write((const char*)&nsj, 8);
+    if (nsj) sb.write((const char*)sj.data(), nsj * sizeof(Junction));
+}
+
 // One mapping pass over the read files (ReadAlignChunk::processChunks / mapThreadsSpawn for all chunks): reads -> engine -> records.
 // Used for the main pass and, with the outputs switched off in P, for the 1st pass of --twopassMode Basic.
 // Returns 0 or a STAR_EXIT_* code with the message in err.
@@ -295,6 +308,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         idx.view.sjdbLength = 2 * ov + 1;
         for (const std::string* d : {&P.sjdbInsertOutDir, &P.twoPassDir}) {   // Parameters.cpp:817-825, 1027-1035: fresh run-time directories
             if (d->empty()) continue;
+            if (d == &P.twoPassDir && P.gpuTwoPassPhase == 2) continue;        // holds the gathered 1st-pass junctions of all shards
             std::error_code ec;
             std::filesystem::remove_all(*d, ec);
             if (mkdir(d->c_str(), 0700) != 0)
@@ -306,10 +320,12 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         if (rc) return exitWithError(err, rc, &logMain);
     }
     void* ectx = nullptr;
-    rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);
-    if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
+    if (!(P.twoPassYes && P.gpuTwoPassPhase == 2)) {   // (phase 2 of a sharded 2-pass run goes straight to the insertion)
+        rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);
+        if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
+    }
     std::ofstream logProgress(P.outFileNamePrefix + "Log.progress.out");
-    if (P.twoPassYes) {
+    if (P.twoPassYes && P.gpuTwoPassPhase != 2) {
         HostParams P1 = P;   // outputs off, files into _STARpass1/ (twoPassRunPass1.cpp:17-47)
         P1.outSAMtype = {"None"}; P1.outBAMunsorted = false; P1.outBAMcoord = false; P1.unmappedWithin = false; P1.unmappedKeepPairs = false;
         P1.outFileNamePrefix = P.twoPassDir;
@@ -323,12 +339,22 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         rc = mapPass(P1, idx, eng, ectx, st1, sj1, logMain, err);
         eng->destroy(ectx);
         if (rc) return exitWithError(err, rc, &logMain);
+        time(&st1.timeFinish);
+        if (P.gpuTwoPassPhase == 1) {   // one shard of a multi-GPU run: the junction records go to the gather (star_b200.dist), nothing else to do here
+            std::string e2;
+            OutputWriter::collapseSJ(sj1, e2);
+            if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
+            writeShardBin(P.twoPassDir + "shard.bin", st1, sj1);
+            std::cout << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+            return 0;
+        }
         OutputWriter W1(P1, idx);
         std::string e2 = W1.writeSJ(sj1, P.twoPassDir + "SJ.out.tab");
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
-        time(&st1.timeFinish);
         std::cout << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass mapping\n" << std::flush;
         W1.writeLogFinal(st1, P.twoPassDir + "Log.final.out");
+    }   // (phase 2: the 1st pass was a separate run; star_b200.dist gathered the junctions of all shards into _STARpass1/SJ.out.tab)
+    if (P.twoPassYes) {
         rc = sjdbInsertJunctions(P, &P.hp, idx, sjdbLoci, true, P.twoPassDir + "SJ.out.tab", eng, logMain, err);
         if (rc) return exitWithError(err, rc, &logMain);
         rc = eng->init(&ectx, P.gpuDevice, &idx.view, &P.hp, P.gpuChunkReads);   // the index with the inserted junctions becomes resident
@@ -353,15 +379,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         std::string e2;
         OutputWriter::collapseSJ(allSJ, e2);
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
-        std::ofstream sb(P.outFileNamePrefix + "shard.bin", std::ios::binary);
-        uint64_t cnt[Stats::N_COUNTERS];
-        stats.toArray(cnt);
-        int64_t tm[3] = {(int64_t)stats.timeStart, (int64_t)stats.timeStartMap, (int64_t)stats.timeFinish};
-        uint64_t nsj = allSJ.size();
-        sb.write((const char*)cnt, sizeof(cnt));
-        sb.write((const char*)tm, sizeof(tm));
-        sb.write((const char*)&nsj, 8);
-        if (nsj) sb.write((const char*)allSJ.data(), nsj * sizeof(Junction));
+        writeShardBin(P.outFileNamePrefix + "shard.bin", stats, allSJ);
         std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
         logMain << "ALL DONE!\n" << std::flush;
         return 0;
@@ -424,7 +442,46 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
     return 0;
 }
 
+// 1st pass of a sharded 2-pass run: `dir`/gather<r>.bin (r < nShards) hold the shard.bin payloads of ALL shards, as gathered over
+// the collective by star_b200.dist.  Every rank calls this with its own directory and gets the same global junction list:
+// `dir`/SJ.out.tab (the collapse + filters of outputSJ.cpp:20-200 over all shards) and `dir`/Log.final.out (summed counters).
+static int mergePass1(int argc, char** argv, int nShards, const char* dir) {
+    HostParams P;
+    std::string err;
+    int rc = parseCommandLine(argc, argv, P, err);
+    if (rc) { std::cerr << err << std::endl; return rc; }
+    LoadedIndex idx;
+    rc = loadIndex(P.genomeDir, &P.hp, idx, err, nullptr, true);
+    if (rc) { std::cerr << err << std::endl; return rc; }
+    P.outSAMtype = {"None"};
+    OutputWriter W(P, idx);
+    Stats total;
+    std::vector<Junction> allSJ;
+    int64_t tStart = 0, tStartMap = 0, tFinish = 0;
+    for (int r = 0; r < nShards; r++) {
+        const std::string fn = std::string(dir) + "gather" + std::to_string(r) + ".bin";
+        std::ifstream sb(fn, std::ios::binary);
+        if (!sb.good()) { std::cerr << "EXITING because of FATAL ERROR: missing gathered 1st-pass junctions " << fn << "\n"; return STAR_EXIT_RUNTIME; }
+        uint64_t cnt[Stats::N_COUNTERS]; int64_t tm[3]; uint64_t nsj = 0;
+        sb.read((char*)cnt, sizeof(cnt)); sb.read((char*)tm, sizeof(tm)); sb.read((char*)&nsj, 8);
+        Stats s1; s1.fromArray(cnt); total.add(s1);
+        if (r == 0 || tm[0] < tStart) tStart = tm[0];
+        if (r == 0 || tm[1] < tStartMap) tStartMap = tm[1];
+        if (tm[2] > tFinish) tFinish = tm[2];
+        const size_t old = allSJ.size();
+        allSJ.resize(old + nsj);
+        if (nsj) sb.read((char*)(allSJ.data() + old), nsj * sizeof(Junction));
+    }
+    total.timeStart = (time_t)tStart; total.timeStartMap = (time_t)tStartMap; total.timeFinish = (time_t)tFinish;
+    std::string e2 = W.writeSJ(allSJ, std::string(dir) + "SJ.out.tab");
+    if (!e2.empty()) { std::cerr << e2 << std::endl; return STAR_EXIT_BUG; }
+    W.writeLogFinal(total, std::string(dir) + "Log.final.out");
+    return 0;
+}
+
 }  // namespace starhost
+
+extern "C" int star_host_merge_pass1(int argc, char** argv, int nShards, const char* dir) { return starhost::mergePass1(argc, argv, nShards, dir); }
 
 extern "C" int star_host_merge_shards(int argc, char** argv, int nShards, const uint64_t* counters24) {
     return starhost::mergeShards(argc, argv, nShards, counters24);

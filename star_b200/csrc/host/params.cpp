@@ -183,6 +183,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     tab["outSAMflagAND"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagAND); }};
     tab["gpuDevice"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuDevice); }};
     tab["gpuShardIndex"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardIndex); }};
+    tab["gpuTwoPassPhase"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuTwoPassPhase) && P.gpuTwoPassPhase <= 2; }};
     tab["gpuShardCount"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardCount) && P.gpuShardCount > 0; }};
     tab["gpuChunkReads"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuChunkReads) && P.gpuChunkReads > 0; }};
 
@@ -402,9 +403,11 @@ int finalizeParams(HostParams& P, std::string& err) {
         if (P.sjdbInsertSave != "Basic" && P.sjdbInsertSave != "All")
             return bad("EXITING because of fatal PARAMETERS error: unrecognized value of --sjdbInsertSave=" + P.sjdbInsertSave + "\nSOLUTION: use allowed values: Basic or All\n");
         P.sjdbInsertOutDir = P.outFileNamePrefix + "_STARgenome/";
-        if (P.gpuShardCount > 1)
-            return bad("EXITING because of fatal input ERROR: junction insertion / --twopassMode is not supported for sharded (multi-GPU) runs yet: the 1st-pass junctions of all shards would have to be gathered first\n");
+        if (P.twoPassYes && P.gpuShardCount > 1 && P.gpuTwoPassPhase == 0)
+            return bad("EXITING because of fatal input ERROR: --twopassMode Basic of a sharded (multi-GPU) run needs the junctions of all shards after the 1st pass: run it through `python -m star_b200.dist` (which gathers them between --gpuTwoPassPhase 1 and 2)\n");
     }
+    if (P.gpuTwoPassPhase != 0 && !(P.twoPassYes && P.gpuShardCount > 1))
+        return bad("EXITING because of fatal PARAMETERS error: --gpuTwoPassPhase is only meaningful for a sharded --twopassMode Basic run\n");
     if (P.outBAMcoord && P.gpuShardCount > 1)
         return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported for sharded (multi-GPU) runs yet: use Unsorted and sort the merged file\n");
     if (P.gpuShardIndex >= P.gpuShardCount) return bad("EXITING because of fatal PARAMETERS error: --gpuShardIndex must be < --gpuShardCount\n");

@@ -1,9 +1,13 @@
 """Multi-GPU driver: one process per GPU (torchrun), reads sharded by contiguous slices, index replicated per GPU.
 
-There is no collective on the data path.  Collectives, all after mapping:
-  * allreduce(sum) of the 24 Log.final.out counters (NCCL on GPUs; gloo in the CPU test-suite),
+There is no collective on the data path of a pass.  Collectives:
+  * allreduce(sum) of the 24 Log.final.out counters after mapping (NCCL on GPUs; gloo in the CPU test-suite),
   * a barrier; the junction records and SAM shards are files on the node's filesystem and are merged by rank 0 through the
-    C-ABI helper star_host_merge_shards (global collapse + the neighbour-distance filter need the complete sorted list).
+    C-ABI helper star_host_merge_shards (global collapse + the neighbour-distance filter need the complete sorted list),
+  * --twopassMode Basic: the one real exchange step of the program.  Every rank maps its slice in the 1st pass
+    (--gpuTwoPassPhase 1), the collapsed junction records of all shards are ALL-GATHERED (sizes, then padded payload), every rank
+    derives the same global junction list from them (star_host_merge_pass1) and inserts it into its replica of the index
+    (--gpuTwoPassPhase 2) before mapping its slice again.
 
   torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m star_b200.dist -- --genomeDir idx --readFilesIn r_1.fq r_2.fq --outFileNamePrefix out/
 """
@@ -44,6 +48,27 @@ def read_shard_counters(prefix, rank):
         return np.frombuffer(f.read(8 * N_COUNTERS), dtype=np.uint64).copy()
 
 
+def two_pass(argv):
+    return "--twopassMode" in argv and argv[argv.index("--twopassMode") + 1] != "None"
+
+
+def all_gather_bytes(blob, world, device):
+    """Variable-length all-gather: sizes first, then the payload padded to the longest.  Returns the list of every rank's bytes."""
+    import torch
+    import torch.distributed as dist
+    n = torch.tensor([len(blob)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    mine = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if blob:
+        mine[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    parts = [torch.zeros(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return [bytes(p[:sz].cpu().numpy().tobytes()) for p, sz in zip(parts, sizes)]
+
+
 def run_sharded(argv, cli=None, backend=None):
     """Runs under torchrun (RANK/WORLD_SIZE/LOCAL_RANK set).  cli: None = the CUDA engine in-process (star_cli_main);
     or the path of an executable with the same command line (the test-suite passes the oracle-driven CLI)."""
@@ -66,14 +91,46 @@ def run_sharded(argv, cli=None, backend=None):
     prog = "STAR"
     sargv = shard_args(argv, rank, world, device=local_rank if use_cuda else None)
     os.makedirs(os.path.dirname(_prefix(argv)) or ".", exist_ok=True)
-    if cli is None:
-        arr = (C.c_char_p * (len(sargv) + 1))(*([prog.encode()] + [a.encode() for a in sargv]))
-        rc = lib.star_cli_main(len(sargv) + 1, arr)
+    dev = "cuda" if use_cuda else "cpu"
+
+    def run_cli(extra):
+        a = sargv + extra
+        if cli is None:
+            arr = (C.c_char_p * (len(a) + 1))(*([prog.encode()] + [x.encode() for x in a]))
+            return lib.star_cli_main(len(a) + 1, arr)
+        return subprocess.call([cli] + a, stdout=subprocess.DEVNULL)
+
+    def all_ok(rc):
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return int(ok.item()) == 1
+
+    if two_pass(argv):
+        rc = run_cli(["--gpuTwoPassPhase", "1"])
+        if not all_ok(rc):
+            dist.destroy_process_group()
+            return rc or 1
+        p1dir = _prefix(sargv) + "_STARpass1/"
+        gathered = all_gather_bytes(open(p1dir + "shard.bin", "rb").read(), world, dev)
+        for r, blob in enumerate(gathered):
+            with open(p1dir + "gather%d.bin" % r, "wb") as f:
+                f.write(blob)
+        lib.star_host_merge_pass1.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
+        margv = [prog] + list(argv)
+        arr = (C.c_char_p * len(margv))(*[a.encode() for a in margv])
+        rc = lib.star_host_merge_pass1(len(margv), arr, world, p1dir.encode())
+        if rank == 0 and rc == 0:   # the run's own _STARpass1/ as the reference leaves it
+            os.makedirs(_prefix(argv) + "_STARpass1", exist_ok=True)
+            for f in ("SJ.out.tab", "Log.final.out"):
+                with open(p1dir + f, "rb") as src, open(_prefix(argv) + "_STARpass1/" + f, "wb") as dst:
+                    dst.write(src.read())
+        if not all_ok(rc):
+            dist.destroy_process_group()
+            return rc or 1
+        rc = run_cli(["--gpuTwoPassPhase", "2"])
     else:
-        rc = subprocess.call([cli] + sargv, stdout=subprocess.DEVNULL)
-    ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device="cuda" if use_cuda else "cpu")
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if int(ok.item()) == 0:
+        rc = run_cli([])
+    if not all_ok(rc):
         dist.destroy_process_group()
         return rc or 1
     # the one collective of the path: the Log.final.out counters

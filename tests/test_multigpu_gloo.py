@@ -36,3 +36,28 @@ def test_shard_arguments():
     a = dist.shard_args(["--genomeDir", "g", "--outFileNamePrefix", "o/x_"], 3, 8, device=3)
     assert a[a.index("--outFileNamePrefix") + 1] == "o/x_shard3."
     assert a[a.index("--gpuShardIndex") + 1] == "3" and a[a.index("--gpuShardCount") + 1] == "8" and a[a.index("--gpuDevice") + 1] == "3"
+
+
+def test_two_rank_twopass_equals_reference(oracle, lib, golden, twopass_golden, tmp_path):
+    """--twopassMode Basic over 2 ranks: the 1st-pass junction records of both shards are all-gathered (gloo), every rank inserts the same
+    global list into its replica of the index and maps its slice again; merged outputs = the single-process reference run."""
+    out = str(tmp_path) + "/"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613",
+           "-m", "star_b200.dist", "--cli", oc.ORACLE_CLI, "--",
+           "--genomeDir", os.path.join(twopass_golden, "idx0"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
+           "--outFileNamePrefix", out, "--runThreadN", "2", "--twopassMode", "Basic", "--sjdbInsertSave", "All"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = os.path.join(twopass_golden, "A_novel")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+    assert open(out + "_STARpass1/SJ.out.tab", "rb").read() == open(os.path.join(ref, "_STARpass1/SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "_STARpass1/Log.final.out") == cf.log_counters(os.path.join(ref, "_STARpass1/Log.final.out"))
+    import hashlib
+    for shard in ("shard0.", "shard1."):   # both replicas of the index were rebuilt to the reference's bytes
+        for line in open(os.path.join(ref, "_STARgenome/sha256.txt")):
+            name, digest = line.split()
+            assert hashlib.sha256(open(out + shard + "_STARgenome/" + name, "rb").read()).hexdigest() == digest, (shard, name)
