@@ -306,6 +306,14 @@ int star_gpu_sjdb_merge_sa(star_sjdb_t* h, const uint64_t* indSorted, uint64_t n
                            const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
 void star_gpu_sjdb_close(star_sjdb_t* h);
 
+/* ---- index generation (--runMode genomeGenerate) --------------------------------------------------------------
+ * star_gpu_sa_build replaces the suffix sort of Genome::genomeGenerate (reference source/Genome_genomeGenerate.cpp:178-330,
+ * funCompareSuffixes :29-89).  G: nGenome bytes, codes 0..5, at least 100 bytes of code 5 readable on both sides (HOST pointer).
+ * The text is G followed by its reverse complement; every position holding a code < 4 is a suffix; order = lexicographic by code,
+ * a code 5 met at the same offset in both suffixes ends the comparison and the smaller text position goes first.
+ * SA receives nSAbyte bytes: nSA entries of GstrandBit+1 bits, forward positions as they are, reverse ones as (pos - nGenome) | 1<<GstrandBit. */
+int star_gpu_sa_build(int device, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte);
+
 /* Sharded --twopassMode Basic: between the two phases (--gpuTwoPassPhase 1 / 2 of every rank) the collapsed 1st-pass junction records of
  * all shards are all-gathered (star_b200.dist: sizes, then payload, over NCCL / gloo); every rank stores them as <dir>gather<r>.bin and
  * calls this with the ORIGINAL command line to get the same global <dir>SJ.out.tab (collapse + filters of outputSJ.cpp:20-200 over all
@@ -324,6 +332,8 @@ typedef struct star_engine_vtbl {
     int (*sjdb_merge_sa)(void* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
                          const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
     void (*sjdb_close)(void* h);
+    /* index generation (same meaning as star_gpu_sa_build) */
+    int (*sa_build)(int device, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte);
 } star_engine_vtbl_t;
 int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine);
 

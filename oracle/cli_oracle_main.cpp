@@ -3,9 +3,9 @@
 // Used by tests/ to (a) pin the oracle + host code against the unmodified reference (oracle/_ref/STAR) and
 // (b) produce expected outputs on machines without a GPU.  Never shipped, never linked into libstar_b200.so.
 //
-// With STAR_CLI_SJDB_EMUL=<path of libengine_emul.so> the two device steps of the junction insertion are run by the EMULATED CUDA
-// kernels (sjdb_kernels.cuh through cuda_host_shim.h) instead of the oracle's sequential restatement, so that a whole 2-pass run
-// checks the kernel logic against the reference's outputs.
+// With STAR_CLI_SJDB_EMUL=<path of libengine_emul.so> the device steps of the junction insertion and of the index generation are run
+// by the EMULATED CUDA kernels (sjdb_kernels.cuh, sa_build_impl.cuh through cuda_host_shim.h) instead of the oracle's sequential
+// restatements, so that a whole 2-pass run / genomeGenerate checks the kernel logic against the reference's outputs.
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -35,6 +35,10 @@ int main(int argc, char** argv) {
         g_merge = (emul_merge_t)dlsym(so, "engine_emul_sjdb_merge_sa");
         if (!g_search || !g_merge) { fprintf(stderr, "%s lacks the sjdb entry points\n", lib); return 1; }
         vt.sjdb_open = emOpen; vt.sjdb_search = emSearch; vt.sjdb_merge_sa = emMerge; vt.sjdb_close = emClose;
+        typedef int (*emul_sa_t)(int, const uint8_t*, uint64_t, uint32_t, uint64_t, uint8_t*, uint64_t);
+        emul_sa_t sa = (emul_sa_t)dlsym(so, "engine_emul_sa_build");
+        if (!sa) { fprintf(stderr, "%s lacks engine_emul_sa_build\n", lib); return 1; }
+        vt.sa_build = sa;
     }
     return star_cli_main_engine(argc, argv, &vt);
 }

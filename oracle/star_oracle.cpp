@@ -1750,8 +1750,43 @@ int star_oracle_sjdb_merge_sa(void* h, const uint64_t* ind, uint64_t nInd, uint6
 }
 void star_oracle_sjdb_close(void* h) { delete (SjdbOracle*)h; }
 
+// ---- index generation: CPU restatement of the suffix sort (checker for star_gpu_sa_build) -------------------------------------------
+// std::sort with the comparison of funCompareSuffixes (Genome_genomeGenerate.cpp:29-89) written character by character on the
+// text G + reverse complement: first difference decides (codes compare by value, 5 largest); a 5 at the same offset in both ends the
+// comparison and the smaller text position sorts first.
+int star_oracle_sa_build(int, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte) {
+    const uint64_t n = 2 * nGenome;
+    std::vector<uint8_t> T(n + 256, 5);
+    for (uint64_t i = 0; i < nGenome; i++) { T[i] = G[i]; T[n - 1 - i] = G[i] < 4 ? 3 - G[i] : G[i]; }
+    std::vector<uint64_t> pos;
+    pos.reserve(nSA);
+    for (uint64_t i = 0; i < n; i++) if (T[i] < 4) pos.push_back(i);
+    if (pos.size() != nSA) return STAR_EXIT_BUG;
+    const uint8_t* t = T.data();
+    std::sort(pos.begin(), pos.end(), [t](uint64_t a, uint64_t b) {
+        for (uint64_t k = 0;; k++) {
+            const uint8_t ca = t[a + k], cb = t[b + k];
+            if (ca != cb) return ca < cb;
+            if (ca == 5) return a < b;
+        }
+    });
+    const uint32_t bits = GstrandBit + 1;
+    const uint64_t N2bit = 1ULL << GstrandBit;
+    std::vector<uint8_t> buf(nSAbyte + 16, 0);
+    for (uint64_t j = 0; j < nSA; j++) {
+        const uint64_t x = pos[j] < nGenome ? pos[j] : ((pos[j] - nGenome) | N2bit);
+        const uint64_t b = j * bits, S = b % 8;
+        uint64_t w;
+        memcpy(&w, buf.data() + b / 8, 8);
+        w |= x << S;
+        memcpy(buf.data() + b / 8, &w, 8);
+    }
+    memcpy(SA, buf.data(), nSAbyte);
+    return 0;
+}
+
 static const star_engine_vtbl_t g_oracle_vtbl = {star_oracle_init, star_oracle_map_chunk, star_oracle_destroy, star_oracle_last_error,
-                                                 star_oracle_sjdb_open, star_oracle_sjdb_search, star_oracle_sjdb_merge_sa, star_oracle_sjdb_close};
+                                                 star_oracle_sjdb_open, star_oracle_sjdb_search, star_oracle_sjdb_merge_sa, star_oracle_sjdb_close, star_oracle_sa_build};
 const star_engine_vtbl_t* star_oracle_engine(void) { return &g_oracle_vtbl; }
 
 }  // extern "C"

@@ -774,7 +774,7 @@ static int vt_sjdb_merge(void* h, const uint64_t* indSorted, uint64_t nInd, uint
     return star_gpu_sjdb_merge_sa((star_sjdb_t*)h, indSorted, nInd, nGsj, nGsjNew, sjdbLength, oldSJind, SAnew, nSAnewByte);
 }
 static void vt_sjdb_close(void* h) { star_gpu_sjdb_close((star_sjdb_t*)h); }
-static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close};
+static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close, star_gpu_sa_build};
 
 int star_cli_main(int argc, char** argv) { return star_cli_main_engine(argc, argv, &g_cuda_engine); }
 

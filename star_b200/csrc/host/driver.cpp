@@ -283,6 +283,12 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
     std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
 
+    if (P.runMode == "genomeGenerate") {   // STAR.cpp:120-125
+        rc = genomeGenerate(P, eng, logMain, err);
+        if (rc) return exitWithError(err, rc, &logMain);
+        logMain << "DONE: Genome generation, EXITING\n" << std::flush;
+        return 0;
+    }
     {
         time_t t; time(&t);
         std::cout << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;

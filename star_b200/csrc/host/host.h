@@ -69,6 +69,9 @@ struct HostParams {
     std::string alignInsertionFlush = "None";
     std::string outMultimapperOrder = "Old_2.4";
     unsigned readNmates = 1;
+    // --runMode genomeGenerate (Parameters.cpp:230-256)
+    std::vector<std::string> genomeFastaFiles = {"-"};
+    uint64_t genomeSAindexNbases = 14, genomeChrBinNbits = 18, genomeSAsparseD = 1, limitGenomeGenerateRAM = 31000000000ULL;
     // on-the-fly junction insertion / 2-pass (Parameters.cpp:240-269, 779-825, 1000-1035)
     std::vector<std::string> sjdbFileChrStartEnd = {"-"};
     std::string sjdbGTFfile = "-", sjdbGTFchrPrefix = "-", sjdbGTFfeatureExon = "exon", sjdbGTFtagExonParentTranscript = "transcript_id",
@@ -121,8 +124,10 @@ void sjdbLoadFromStream(std::istream& in, SjdbLoci& loci);   // sjdbLoadFromStre
 // sjdbInsertJunctions.cpp:11-102: loads the junction lists, prepares the inserts, rebuilds G / SA / SAi of `idx` in place (the device part
 // through eng->sjdb_*), writes sjdbInfo.txt / sjdbList.out.tab (and the whole index with --sjdbInsertSave All) to P.sjdbInsertOutDir and
 // re-computes hp->winBinN.  pass2: the junctions of `pass1sjFile` are added.  Returns 0 or a STAR_EXIT_* code with the message in err.
+// --runMode genomeGenerate (genome_generate.cpp): FASTA -> Genome, SA (eng->sa_build), SAindex, junction inserts, index files in P.genomeDir
+int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err);
 int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx, SjdbLoci& loci, bool pass2, const std::string& pass1sjFile,
-                        const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err);
+                        const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err, bool generateMode = false);
 int loadIndex(const std::string& genomeDir, star_params_t* p, LoadedIndex& L, std::string& err, std::string* log, bool chrInfoOnly = false);
 
 // one chunk of reads in host memory

@@ -85,12 +85,12 @@ bool parseU64(const std::string& s, uint64_t& out) {
 
 // STAR parameters that exist in the reference but belong to subsystems outside the hot path
 const char* kUnsupported[] = {
-    "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeFastaFiles", "genomeChainFiles", "genomeFileSizes",
-    "genomeTransformOutput", "genomeChrSetMitochondrial", "genomeChrBinNbits", "genomeSAindexNbases", "genomeSAsparseD",
+    "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeChainFiles", "genomeFileSizes",
+    "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "varVCFfile", "readFilesType",
     "readFilesSAMattrKeep", "readFilesManifest", "readFilesPrefix", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
-    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitGenomeGenerateRAM", "limitIObufferSize",
+    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitIObufferSize",
     "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitNreadsSoft",
     "outTmpDir", "outTmpKeep", "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
     "outSAMfilter", "outSAMtlen", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
@@ -155,6 +155,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     I32("scoreStitchSJshift", &h.scoreStitchSJshift); I32("sjdbScore", &h.sjdbScore);
     STR("sjdbGTFfile", &P.sjdbGTFfile); STR("sjdbGTFchrPrefix", &P.sjdbGTFchrPrefix); STR("sjdbGTFfeatureExon", &P.sjdbGTFfeatureExon);
     STR("sjdbGTFtagExonParentTranscript", &P.sjdbGTFtagExonParentTranscript); STR("sjdbGTFtagExonParentGene", &P.sjdbGTFtagExonParentGene);
+    VSTR("genomeFastaFiles", &P.genomeFastaFiles); U64("genomeSAindexNbases", &P.genomeSAindexNbases); U64("genomeChrBinNbits", &P.genomeChrBinNbits);
+    U64("genomeSAsparseD", &P.genomeSAsparseD); U64("limitGenomeGenerateRAM", &P.limitGenomeGenerateRAM);
     VSTR("sjdbFileChrStartEnd", &P.sjdbFileChrStartEnd); U64("sjdbOverhang", &P.sjdbOverhang); STR("sjdbInsertSave", &P.sjdbInsertSave);
     U64("limitSjdbInsertNsj", &P.limitSjdbInsertNsj); STR("twopassMode", &P.twopassMode); U64("twopass1readsN", &P.twopass1readsN);
     U64("outFilterMismatchNmax", &h.outFilterMismatchNmax); DBL("outFilterMismatchNoverLmax", &h.outFilterMismatchNoverLmax);
@@ -242,8 +244,18 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
 int finalizeParams(HostParams& P, std::string& err) {
     star_params_t& h = P.hp;
     auto bad = [&](const std::string& m) { err = m; return STAR_EXIT_PARAMETER; };
+    if (P.runMode == "genomeGenerate") {   // index generation (genome_generate.cpp): only the genome / junction parameters matter
+        if (P.genomeFastaFiles.empty() || P.genomeFastaFiles[0] == "-")
+            return bad("EXITING because of fatal PARAMETERS error: --runMode genomeGenerate needs --genomeFastaFiles\n");
+        if (P.genomeSAsparseD != 1) return bad("EXITING because of fatal PARAMETERS error: star-b200 builds --genomeSAsparseD 1 indices only\n");
+        if (P.genomeSAindexNbases < 1 || P.genomeSAindexNbases > 18) return bad("EXITING because of fatal PARAMETERS error: --genomeSAindexNbases must be in 1..18\n");
+        if (P.twopassMode != "None") return bad("EXITING because of fatal PARAMETERS error: 2-pass mapping option  can only be used with --runMode alignReads\nSOLUTION: remove --twopassMode option");
+        if (P.sjdbFileChrStartEnd[0] != "-" || P.sjdbGTFfile != "-") { P.sjdbInsertPass1 = true; P.sjdbInsertYes = true; }
+        if (P.genomeDir.empty() || P.genomeDir.back() != '/') P.genomeDir += "/";
+        return 0;
+    }
     if (P.runMode != "alignReads")
-        return bad("EXITING because of fatal input ERROR: star-b200 implements --runMode alignReads only (indices are built with the reference STAR --runMode genomeGenerate)\n");
+        return bad("EXITING because of fatal input ERROR: star-b200 implements --runMode alignReads and genomeGenerate only\n");
     if (P.genomeLoad != "NoSharedMemory")
         return bad("EXITING because of fatal input ERROR: --genomeLoad " + P.genomeLoad + " is not supported: the index is resident in GPU HBM instead of host shared memory\n");
     if (P.outStd != "Log") return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not supported by star-b200 (only Log)\n");

@@ -302,7 +302,7 @@ static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const st
 }
 
 int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx, SjdbLoci& loci, bool pass2, const std::string& pass1sjFile,
-                        const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err) {
+                        const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err, bool generateMode) {
     star_index_view_t& v = idx.view;
     const std::string& outDir = P.sjdbInsertOutDir;
     if (v.sjdbN > 0 && loci.chr.empty()) {   // junctions of the generated genome (only if they were not loaded before)
@@ -319,6 +319,10 @@ int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx
         loci.priority.resize(loci.chr.size(), 0);
         logMain << "   Loaded database junctions from the 1st pass file: " << pass1sjFile << ": " << loci.chr.size() << " total junctions\n\n";
     } else {
+        if (generateMode && P.sjdbGTFfile != "-") {   // at genome generation the GTF junctions come first (Genome_genomeGenerate.cpp:160-163)
+            int rcg = sjdbLoadFromGTF(P, idx, outDir, loci, logMain, err);
+            if (rcg) return rcg;
+        }
         if (P.sjdbFileChrStartEnd[0] != "-")   // sjdbLoadFromFiles.cpp:6-26
             for (const std::string& fn : P.sjdbFileChrStartEnd) {
                 std::ifstream in(fn);
@@ -327,7 +331,7 @@ int sjdbInsertJunctions(const HostParams& P, star_params_t* hp, LoadedIndex& idx
                 loci.priority.resize(loci.chr.size(), 10);
                 logMain << "   Loaded database junctions from the pGe.sjdbFileChrStartEnd file(s), total number of junctions:" << loci.chr.size() << "\n\n";
             }
-        if (P.sjdbGTFfile != "-") {
+        if (!generateMode && P.sjdbGTFfile != "-") {
             int rcg = sjdbLoadFromGTF(P, idx, outDir, loci, logMain, err);
             if (rcg) return rcg;
         }
