@@ -406,7 +406,7 @@ int engine_emul_sjdb_merge_sa(const star_index_view_t* v, const uint64_t* indSor
     m.insRow = row.data(); m.insVal = val.data(); m.nInd = nInd; m.nSAnew = nSAnew;
     m.nGenomeOld = H.ix.nGenome; m.nGenomeNew = H.sjGstart + nGsj; m.sjGstart = H.sjGstart; m.sjdbLength = sjdbLength; m.sjdbNold = H.sjdbNold;
     m.nGsjNew = nGsjNew; m.oldSJind = (const u32*)oldSJind;
-    runCta(256, [&] { sjdb_merge_sa_kernel(H.ix, m, out.data()); });
+    runCta(128, [&] { sjdb_merge_sa_kernel(H.ix, m, out.data()); });
     if (nSAnewByte > out.size() * 8) return STAR_EXIT_BUG;
     memcpy(SAnew, out.data(), nSAnewByte);
     return 0;
@@ -431,6 +431,7 @@ static void emSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
 #define SA_ALLOC(bytes) starb::emAlloc(bytes)
 #define SA_FREE(p) free(p)
 #define SA_LAUNCH(count, kernel, ...) runCta(256, [&] { kernel(__VA_ARGS__); })
+#define SA_LAUNCH_PACK(nRows, bits, kernel, ...) runCta(128, [&] { kernel(__VA_ARGS__); })
 #define SA_COPY_TO(dst, src, bytes) memcpy(dst, src, bytes)
 #define SA_COPY_FROM(dst, src, bytes) memcpy(dst, src, bytes)
 #define SA_SORT_PAIRS(kIn, kOut, vIn, vOut, n, endBit) starb::emSortPairs(kIn, kOut, vIn, vOut, n, endBit)

@@ -53,6 +53,15 @@ static void saSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
 #define SA_ALLOC(bytes) starb::saAlloc(bytes)
 #define SA_FREE(p) cudaFree(p)
 #define SA_LAUNCH(count, kernel, ...) do { kernel<<<starb::saGrid(count), 256>>>(__VA_ARGS__); starb::saNote(cudaGetLastError()); starb::countLaunches(1); } while (0)
+#define SA_LAUNCH_PACK(nRows, bits, kernel, ...)                                                                                   \
+    do {   /* 4 warps per CTA, one tile of 32 x 64 rows per warp and step, tile staged in dynamic shared memory */              \
+        const unsigned long long tiles_ = (((nRows) + 63) / 64 + 31) / 32, want_ = (tiles_ + 3) / 4, cap_ = (unsigned long long)starb::g_saSM * 8; \
+        const size_t smem_ = (size_t)4 * 32 * (bits) * 8;                                                                          \
+        starb::saNote(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                      \
+        kernel<<<(unsigned)(want_ < cap_ ? (want_ ? want_ : 1) : cap_), 128, smem_>>>(__VA_ARGS__);                                 \
+        starb::saNote(cudaGetLastError());                                                                                         \
+        starb::countLaunches(1);                                                                                                   \
+    } while (0)
 #define SA_COPY_TO(dst, src, bytes) starb::saNote(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice))
 #define SA_COPY_FROM(dst, src, bytes) starb::saNote(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost))
 #define SA_SORT_PAIRS(kIn, kOut, vIn, vOut, n, endBit) starb::saSortPairs(kIn, kOut, vIn, vOut, n, endBit)

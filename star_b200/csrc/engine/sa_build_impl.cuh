@@ -80,24 +80,38 @@ __global__ void __launch_bounds__(256) sa_base_flag_kernel(const u8* __restrict_
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (u64)gridDim.x * blockDim.x) flag[j] = SB_LDG(T + pos[j]) < 4;
 }
 
-// one thread per 64 rows = `bits` whole words of the packed array
-__global__ void __launch_bounds__(256) sa_pack_kernel(const u32* __restrict__ sa, u64 nSA, u64 nGenome, u32 GstrandBit, u64* __restrict__ out) {
+// one thread per 64 rows = `bits` whole words of the packed array; a warp's 32 groups are staged in shared memory and stored coalesced
+// (dynamic shared memory: (blockDim.x/32) * 32 * bits * 8 bytes; launched with 128 threads)
+__global__ void __launch_bounds__(128) sa_pack_kernel(const u32* __restrict__ sa, u64 nSA, u64 nGenome, u32 GstrandBit, u64* __restrict__ out) {
+    extern __shared__ u8 smem[];
     const u32 bits = GstrandBit + 1;
+    const u32 lane = threadIdx.x & 31;
+    u64* tile = (u64*)smem + (u64)(threadIdx.x >> 5) * 32 * bits;
     const u64 N2bit = 1ULL << GstrandBit;
     const u64 nGroups = (nSA + 63) / 64;
-    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (u64)gridDim.x * blockDim.x) {
-        u64* o = out + g * bits;
-        u64 acc = 0;
-        u32 sh = 0;
+    const u64 nWarps = ((u64)gridDim.x * blockDim.x) >> 5;
 #pragma unroll 1
-        for (u32 e = 0; e < 64; e++) {
-            const u64 r = g * 64 + e;
-            u64 val = 0;
-            if (r < nSA) { const u64 p = sa[r]; val = p < nGenome ? p : ((p - nGenome) | N2bit); }
-            acc |= val << sh;
-            if (sh + bits >= 64) { *o++ = acc; acc = sh + bits > 64 ? val >> (64 - sh) : 0; }
-            sh = (sh + bits) & 63;
+    for (u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t * 32 < nGroups; t += nWarps) {
+        const u64 g = t * 32 + lane;
+        if (g < nGroups) {
+            u64* o = tile + (u64)lane * bits;
+            u64 acc = 0;
+            u32 sh = 0;
+#pragma unroll 1
+            for (u32 e = 0; e < 64; e++) {
+                const u64 r = g * 64 + e;
+                u64 val = 0;
+                if (r < nSA) { const u64 p = sa[r]; val = p < nGenome ? p : ((p - nGenome) | N2bit); }
+                acc |= val << sh;
+                if (sh + bits >= 64) { *o++ = acc; acc = sh + bits > 64 ? val >> (64 - sh) : 0; }
+                sh = (sh + bits) & 63;
+            }
         }
+        __syncwarp();
+        const u64 rows = nGroups - t * 32 < 32 ? nGroups - t * 32 : 32;
+        u64* dst = out + t * 32 * bits;
+        for (u64 k = lane; k < rows * bits; k += 32) dst[k] = tile[k];
+        __syncwarp();
     }
 }
 
@@ -115,7 +129,10 @@ inline int saBuildRun(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u64* o
     u32* rank = (u32*)SA_ALLOC((n + 1) * 4);
     u32* hd = (u32*)SA_ALLOC(n * 4);
     unsigned long long* cnt = (unsigned long long*)SA_ALLOC(8);
-    if (!T || !keyA || !keyB || !posA || !posB || !rank || !hd || !cnt) return 3;
+    if (!T || !keyA || !keyB || !posA || !posB || !rank || !hd || !cnt) {
+        SA_FREE(T); SA_FREE(keyA); SA_FREE(keyB); SA_FREE(posA); SA_FREE(posB); SA_FREE(rank); SA_FREE(hd); SA_FREE(cnt);
+        return 3;
+    }
     SA_LAUNCH(n + padT, sa_text_kernel, dG, nGenome, T, padT);
     SA_LAUNCH(n, sa_key0_kernel, T, n, keyA, posA);
     const u32 nU32 = (u32)n;
@@ -142,7 +159,7 @@ inline int saBuildRun(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u64* o
         u64 nSel = 0;
         SA_SELECT(posA, flag, posB, n, &nSel);                                       // positions holding a base, in suffix order
         if (nSel != nSA) rc = 1;
-        else SA_LAUNCH((nSA + 63) / 64, sa_pack_kernel, posB, nSA, nGenome, GstrandBit, outWords);
+        else SA_LAUNCH_PACK(nSA, GstrandBit + 1, sa_pack_kernel, posB, nSA, nGenome, GstrandBit, outWords);
     }
     SA_SYNC();
     if (roundsOut) *roundsOut = rounds;

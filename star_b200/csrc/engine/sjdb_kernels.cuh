@@ -5,7 +5,7 @@
 //                        search over the whole SA in which a spacer (code 5) of the insert sorts behind the genome's (compareRefEnds,
 //                        :221-231, with gInsert = -1: new rows always go behind equal old ones).
 //   sjdb_merge_sa_kernel one thread per 64 rows of the NEW suffix array (= GstrandBit+1 whole 64-bit words, so no two threads share a
-//                        word): old rows are re-based (reverse-strand coordinates grow with the genome, rows of old inserts move with
+//                        word), a warp's 32 groups staged in shared memory and stored coalesced: old rows are re-based (reverse-strand coordinates grow with the genome, rows of old inserts move with
 //                        their junction's new index) and the sorted new rows are spliced in (sjdbBuildIndex.cpp:141-214).
 //                        HBM-bound: reads nSA x (GstrandBit+1)/8 bytes, writes as much plus the new rows.
 // Both are grid-stride loops, so that the host emulation (oracle/engine_emul.cpp) can run them as one CTA.
@@ -100,35 +100,50 @@ __device__ __forceinline__ u64 sjdbRebase(const SjdbMerge& m, u64 ind1, u64 N2bi
     return ind1;
 }
 
-__global__ void __launch_bounds__(256) sjdb_merge_sa_kernel(const SjdbIndex ix, const SjdbMerge m, u64* __restrict__ SAnew) {
+// Tile = 32 groups of 64 rows per warp: every lane packs its group into the warp's shared-memory tile (same layout as the global
+// array: group after group, `bits` words each), then the warp stores the tile with consecutive 8-byte words per lane (256 B per
+// store instruction instead of 32 stores 8*bits bytes apart).  Dynamic shared memory: (blockDim.x/32) * 32 * bits * 8 bytes.
+__global__ void __launch_bounds__(128) sjdb_merge_sa_kernel(const SjdbIndex ix, const SjdbMerge m, u64* __restrict__ SAnew) {
+    extern __shared__ u8 smem[];
     const u32 bits = ix.saBits;
+    const u32 lane = threadIdx.x & 31;
+    u64* tile = (u64*)smem + (u64)(threadIdx.x >> 5) * 32 * bits;
     const u64 N2bit = 1ULL << ix.GstrandBit;
     const u64 nGroups = (m.nSAnew + 63) / 64;
+    const u64 nWarps = ((u64)gridDim.x * blockDim.x) >> 5;
 #pragma unroll 1
-    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (u64)gridDim.x * blockDim.x) {
-        const u64 r0 = g * 64;
-        u64 lo = 0, hi = m.nInd;            // j = number of inserted rows in front of r0
-        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (SB_LDG(m.insRow + mid) < r0) lo = mid + 1; else hi = mid; }
-        u64 j = lo;
-        u64 nextIns = j < m.nInd ? SB_LDG(m.insRow + j) : ~0ULL;
-        u64* out = SAnew + g * bits;
-        u64 acc = 0;
-        u32 sh = 0;
+    for (u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t * 32 < nGroups; t += nWarps) {
+        const u64 g = t * 32 + lane;
+        if (g < nGroups) {
+            const u64 r0 = g * 64;
+            u64 lo = 0, hi = m.nInd;            // j = number of inserted rows in front of r0
+            while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (SB_LDG(m.insRow + mid) < r0) lo = mid + 1; else hi = mid; }
+            u64 j = lo;
+            u64 nextIns = j < m.nInd ? SB_LDG(m.insRow + j) : ~0ULL;
+            u64* out = tile + (u64)lane * bits;
+            u64 acc = 0;
+            u32 sh = 0;
 #pragma unroll 1
-        for (u32 e = 0; e < 64; e++) {
-            const u64 r = r0 + e;
-            u64 val = 0;
-            if (r < m.nSAnew) {
-                if (r == nextIns) { val = SB_LDG(m.insVal + j); j++; nextIns = j < m.nInd ? SB_LDG(m.insRow + j) : ~0ULL; }
-                else val = sjdbRebase(m, packedGet(ix.SA, bits, r - j), N2bit);
+            for (u32 e = 0; e < 64; e++) {
+                const u64 r = r0 + e;
+                u64 val = 0;
+                if (r < m.nSAnew) {
+                    if (r == nextIns) { val = SB_LDG(m.insVal + j); j++; nextIns = j < m.nInd ? SB_LDG(m.insRow + j) : ~0ULL; }
+                    else val = sjdbRebase(m, packedGet(ix.SA, bits, r - j), N2bit);
+                }
+                acc |= val << sh;
+                if (sh + bits >= 64) {
+                    *out++ = acc;
+                    acc = sh + bits > 64 ? val >> (64 - sh) : 0;
+                }
+                sh = (sh + bits) & 63;
             }
-            acc |= val << sh;
-            if (sh + bits >= 64) {
-                *out++ = acc;
-                acc = sh + bits > 64 ? val >> (64 - sh) : 0;
-            }
-            sh = (sh + bits) & 63;
         }
+        __syncwarp();
+        const u64 rows = nGroups - t * 32 < 32 ? nGroups - t * 32 : 32;
+        u64* dst = SAnew + t * 32 * bits;
+        for (u64 k = lane; k < rows * bits; k += 32) dst[k] = tile[k];
+        __syncwarp();
     }
 }
 

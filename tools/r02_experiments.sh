@@ -26,3 +26,29 @@ run() { tag=$1; shift; env "$@" timeout 600 python tools/analyze_chunk.py 104857
 run base A=1
 for c in 6 8 12; do run seedwarp$c STAR_B200_SEED_WARP=$c; done
 for s in 16 20 30 52; do run split$s STAR_B200_HEAVY_SPLIT=$s; done
+# 4. the round-1 kernels that were written after the GPU budget was spent and have only run under the host emulation:
+#    GPU test-suite of junction insertion / 2-pass / genomeGenerate, then a timing of the suffix-array build and of an insertion on a
+#    48 Mb random genome (chr21 size), with the launch list of the genomeGenerate run
+timeout 900 python -m pytest tests/test_twopass.py tests/test_genome_generate.py -m gpu -q > gpurun_out/r02_new_gpu_tests.log 2>&1; tail -3 gpurun_out/r02_new_gpu_tests.log
+python - <<'PY'
+import numpy as np
+rng = np.random.default_rng(5)
+with open("/tmp/g48.fa", "w") as f:
+    for c in range(3):
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 16_000_000)].tobytes().decode()
+        f.write(">chr%d\n" % (c + 1))
+        for i in range(0, len(s), 80):
+            f.write(s[i:i + 80] + "\n")
+with open("/tmp/sj48.tab", "w") as f:   # 20 k random junctions
+    for i in range(20000):
+        a = int(rng.integers(1000, 15_900_000)); L = int(rng.integers(50, 20000))
+        f.write("chr%d\t%d\t%d\t%s\n" % (1 + i % 3, a, a + L, "+-"[i % 2]))
+PY
+( time star_b200/bin/STAR --runMode genomeGenerate --genomeDir /tmp/idx48 --genomeFastaFiles /tmp/g48.fa --genomeSAindexNbases 12 --outFileNamePrefix /tmp/gen48_ ) > gpurun_out/r02_generate48.log 2>&1; tail -8 gpurun_out/r02_generate48.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_generate48_launches.csv star_b200/bin/STAR --runMode genomeGenerate --genomeDir /tmp/idx48b --genomeFastaFiles /tmp/g48.fa --genomeSAindexNbases 12 --outFileNamePrefix /tmp/gen48b_ > /dev/null 2>&1
+head -c 400 tests/golden/tiny.tar.gz > /dev/null
+python - <<'PY'
+# a 1-read FASTQ is enough to time the insertion itself
+open("/tmp/one.fq", "w").write("@r1\n" + "ACGT" * 25 + "\n+\n" + "I" * 100 + "\n")
+PY
+( time star_b200/bin/STAR --genomeDir /tmp/idx48 --readFilesIn /tmp/one.fq --sjdbFileChrStartEnd /tmp/sj48.tab --sjdbOverhang 99 --outFileNamePrefix /tmp/ins48_ ) > gpurun_out/r02_insert48.log 2>&1; tail -6 gpurun_out/r02_insert48.log; grep -i "SA search\|inserting\|Finished" /tmp/ins48_Log.out | tail -8 >> gpurun_out/r02_insert48.log
