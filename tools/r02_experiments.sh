@@ -29,7 +29,7 @@ for s in 16 20 30 52; do run split$s STAR_B200_HEAVY_SPLIT=$s; done
 # 4. the round-1 kernels that were written after the GPU budget was spent and have only run under the host emulation:
 #    GPU test-suite of junction insertion / 2-pass / genomeGenerate, then a timing of the suffix-array build and of an insertion on a
 #    48 Mb random genome (chr21 size), with the launch list of the genomeGenerate run
-timeout 900 python -m pytest tests/test_twopass.py tests/test_genome_generate.py -m gpu -q > gpurun_out/r02_new_gpu_tests.log 2>&1; tail -3 gpurun_out/r02_new_gpu_tests.log
+timeout 900 python -m pytest tests/test_zz_twopass.py tests/test_zz_genome_generate.py -m gpu -q > gpurun_out/r02_new_gpu_tests.log 2>&1; tail -3 gpurun_out/r02_new_gpu_tests.log
 python - <<'PY'
 import numpy as np
 rng = np.random.default_rng(5)
