@@ -106,7 +106,8 @@ typedef struct star_params {
     uint8_t  outSAMstrandFieldType;   /* 0 None, 1 intronMotif */
     uint8_t  outSAMprimaryFlagAllBestScore;
     uint64_t outSAMmultNmax;          /* (uint64)-1 = all */
-    /* outFilterType BySJout stage 2 and --outMultimapperOrder Random are not built (rejected by the host parser) */
+    /* --outFilterType BySJout: the 2nd stage's junction list is set with star_gpu_set_sj_novel; --outMultimapperOrder Random is not built
+       (rejected by the host parser) */
 } star_params_t;
 
 /*
@@ -240,6 +241,11 @@ int star_gpu_map_resident(star_ctx_t* ctx, star_chunk_stats_t* stats);
 /* Copies the results of the last star_gpu_map_resident to host buffers. */
 int star_gpu_download_results(star_ctx_t* ctx, star_align_batch_t* out);
 
+/* 2nd stage of --outFilterType BySJout (reference source/stitchWindowAligns.cpp:169-177, outputSJ.cpp:139-160): from now on an alignment
+ * with an unannotated junction is only kept when the junction (first / last intron base, 0-based genome coordinates) is in this list, which
+ * must be sorted by start, then end.  n = 0 drops every alignment with an unannotated junction. */
+int star_gpu_set_sj_novel(star_ctx_t* ctx, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n);
+
 /* analysis helper: per-read records of the resident chunk (44 bytes each: Lread u32, readLength u16[2], nP u16, pad u16, nA, mapMarker,
  * multNminL u32, Nsplit u16, split1_0 u16, mmTotal u32, flags u32, then 8 x u32 work counters: searches, saiWords, compareCalls,
  * basesExamined, saEnumerated, stitchNodes, stitchLeaves, slowPath) */
@@ -334,6 +340,8 @@ typedef struct star_engine_vtbl {
     void (*sjdb_close)(void* h);
     /* index generation (same meaning as star_gpu_sa_build) */
     int (*sa_build)(int device, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte);
+    /* 2nd stage of --outFilterType BySJout (same meaning as star_gpu_set_sj_novel) */
+    int (*set_sj_novel)(void* ctx, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n);
 } star_engine_vtbl_t;
 int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine);
 

@@ -63,6 +63,10 @@ u64 arenaSize(const Caps& c) {   // engine_api.cu
     return (b + 255) & ~255ULL;
 }
 
+// 2nd stage of --outFilterType BySJout for the next engine_emul_map_chunk calls (engine_emul_set_sj_novel)
+std::vector<u64> g_sjNovelStart, g_sjNovelEnd;
+bool g_sjNovelOn = false;
+
 struct HostIndex {
     DevIndex ix;
     std::vector<u64> sa, sai, thr;
@@ -93,6 +97,7 @@ struct HostIndex {
         ix.sjdbN = v->sjdbN; ix.sjdbOverhang = v->sjdbOverhang; ix.sjdbLength = v->sjdbLength; ix.sjGstart = v->sjGstart;
         ix.sjdbStart = (const u64*)v->sjdbStart; ix.sjdbEnd = (const u64*)v->sjdbEnd; ix.sjDstart = (const u64*)v->sjDstart; ix.sjAstart = (const u64*)v->sjAstart;
         ix.sjdbMotif = v->sjdbMotif; ix.sjdbShiftLeft = v->sjdbShiftLeft; ix.sjdbShiftRight = v->sjdbShiftRight; ix.sjdbStrand = v->sjdbStrand;
+        if (g_sjNovelOn) { ix.sjNovelStart = g_sjNovelStart.data(); ix.sjNovelEnd = g_sjNovelEnd.data(); ix.sjNovelN = g_sjNovelStart.size(); ix.sjNovelOn = 1; }
         {   // step table of the genomic-length score, host libm (engine_api.cu)
             const double scale = params->scoreGenomicLengthLog2scale;
             auto f = [&](u64 g) { return int(std::ceil(std::log2((double)g) * scale - 0.5)); };
@@ -385,6 +390,15 @@ struct SjdbHost {
     }
 };
 }  // namespace
+
+// n = (uint64)-1 switches the filter off again
+int engine_emul_set_sj_novel(const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n) {
+    if (n == ~0ULL) { g_sjNovelOn = false; return 0; }
+    g_sjNovelStart.assign(sjStart, sjStart + n);
+    g_sjNovelEnd.assign(sjEnd, sjEnd + n);
+    g_sjNovelOn = true;
+    return 0;
+}
 
 int engine_emul_sjdb_search(const star_index_view_t* v, const uint8_t* Gsj, uint64_t sjdbN, uint64_t sjdbLength, const uint8_t* skipSeq, uint64_t* indArray) {
     SjdbHost H(v);

@@ -87,6 +87,9 @@ struct Index {  // the slice of `class Genome` the path reads (Genome.h:26-56)
     unsigned saBits, saiBits;
     std::vector<uint> chrBin;
     const uint* genomeSAindexStart;
+    // 2nd stage of --outFilterType BySJout: the novel junctions that passed the filters (Parameters.h:354 sjNovelN/Start/End)
+    bool sjNovelOn = false;
+    std::vector<uint> sjNovelStart, sjNovelEnd;
 
     // PackedArray::operator[] PackedArray.h:24-32
     static inline uint packed(const uint8_t* a, unsigned bits, uint ii) {
@@ -1130,7 +1133,15 @@ struct ReadAlign {
                     }
                 }
             }
-            // :169-177 outFilterBySJoutStage==2 is not built (rejected by the host parser)
+            if (mapGen.sjNovelOn) {  // :169-177 outFilterBySJoutStage==2: unannotated junctions have to be in the filtered set
+                for (uint iex = 0; iex < trA.nExons - 1; iex++) {
+                    if (trA.canonSJ[iex] >= 0 && trA.sjAnnot[iex] == 0) {
+                        uint jS = trA.exons[iex][EX_G] + trA.exons[iex][EX_L];
+                        uint jE = trA.exons[iex + 1][EX_G] - 1;
+                        if (binarySearch2(jS, jE, mapGen.sjNovelStart.data(), mapGen.sjNovelEnd.data(), (int)mapGen.sjNovelStart.size()) < 0) return;
+                    }
+                }
+            }
             if (trA.exons[0][EX_iFrag] != trA.exons[trA.nExons - 1][EX_iFrag]) {  // :179-219
                 if (trA.exons[trA.nExons - 1][EX_G] + trA.exons[trA.nExons - 1][EX_L] <= trA.exons[0][EX_G]) return;
                 uint iexM2 = trA.nExons;
@@ -1619,6 +1630,14 @@ void star_oracle_dump_free(star_oracle_dump_t* d) {
     d->pcOff = nullptr; d->pc = nullptr;
 }
 
+int star_oracle_set_sj_novel(void* ctx, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n) {
+    star_oracle_ctx* c = (star_oracle_ctx*)ctx;
+    c->index.sjNovelOn = true;
+    c->index.sjNovelStart.assign(sjStart, sjStart + n);
+    c->index.sjNovelEnd.assign(sjEnd, sjEnd + n);
+    return 0;
+}
+
 // ---- junction insertion: CPU restatement of the two device steps (checker for star_gpu_sjdb_*) -------------------------------------
 // Sequential, in the reference's own shape: suffixArraySearch1 / compareSeqToGenome1 / compareRefEnds (SuffixArrayFuns.cpp:221-351)
 // per suffix, and the single two-pointer sweep with PackedArray::writePacked of sjdbBuildIndex.cpp:141-214.
@@ -1786,7 +1805,7 @@ int star_oracle_sa_build(int, const uint8_t* G, uint64_t nGenome, uint32_t Gstra
 }
 
 static const star_engine_vtbl_t g_oracle_vtbl = {star_oracle_init, star_oracle_map_chunk, star_oracle_destroy, star_oracle_last_error,
-                                                 star_oracle_sjdb_open, star_oracle_sjdb_search, star_oracle_sjdb_merge_sa, star_oracle_sjdb_close, star_oracle_sa_build};
+                                                 star_oracle_sjdb_open, star_oracle_sjdb_search, star_oracle_sjdb_merge_sa, star_oracle_sjdb_close, star_oracle_sa_build, star_oracle_set_sj_novel};
 const star_engine_vtbl_t* star_oracle_engine(void) { return &g_oracle_vtbl; }
 
 }  // extern "C"

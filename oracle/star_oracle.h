@@ -32,6 +32,8 @@ int star_oracle_sjdb_search(void* h, const uint8_t* Gsj, uint64_t sjdbN, uint64_
 int star_oracle_sjdb_merge_sa(void* h, const uint64_t* indSorted, uint64_t nInd, uint64_t nGsj, uint64_t nGsjNew, uint64_t sjdbLength,
                               const uint32_t* oldSJind, uint8_t* SAnew, uint64_t nSAnewByte);
 void star_oracle_sjdb_close(void* h);
+/* 2nd stage of --outFilterType BySJout (same meaning as star_gpu_set_sj_novel) */
+int star_oracle_set_sj_novel(void* ctx, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n);
 /* index generation: CPU restatement of star_gpu_sa_build */
 int star_oracle_sa_build(int device, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte);
 const star_engine_vtbl_t* star_oracle_engine(void);

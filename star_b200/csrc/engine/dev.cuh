@@ -44,6 +44,11 @@ struct DevIndex {
     const u8* sjdbShiftLeft;
     const u8* sjdbShiftRight;
     const u8* sjdbStrand;
+    // 2nd stage of --outFilterType BySJout: novel junctions that passed the filters, sorted by (start, end); sjNovelOn = 0: no filtering
+    const u64* sjNovelStart;
+    const u64* sjNovelEnd;
+    u64 sjNovelN;
+    u32 sjNovelOn;
     // integer thresholds of the genomic-length score: value v[k] applies for gLen >= thr[k] (host libm, see engine_api.cu)
     const u64* log2Thr;
     const int* log2Val;

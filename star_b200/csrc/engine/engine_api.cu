@@ -161,6 +161,16 @@ extern "C" {
 const char* star_gpu_last_error(void) { return g_err.c_str(); }
 uint64_t star_gpu_launch_count(void) { return g_launches; }
 
+int star_gpu_set_sj_novel(star_ctx_t* c, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    if (devUpload(c, &c->ix.sjNovelStart, (const u64*)sjStart, n)) return STAR_EXIT_RUNTIME;
+    if (devUpload(c, &c->ix.sjNovelEnd, (const u64*)sjEnd, n)) return STAR_EXIT_RUNTIME;
+    c->ix.sjNovelN = n;
+    c->ix.sjNovelOn = 1;
+    return 0;
+}
+
 void star_gpu_destroy(star_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -773,8 +783,9 @@ static int vt_sjdb_merge(void* h, const uint64_t* indSorted, uint64_t nInd, uint
                          uint8_t* SAnew, uint64_t nSAnewByte) {
     return star_gpu_sjdb_merge_sa((star_sjdb_t*)h, indSorted, nInd, nGsj, nGsjNew, sjdbLength, oldSJind, SAnew, nSAnewByte);
 }
+static int vt_set_sj_novel(void* c, const uint64_t* a, const uint64_t* b, uint64_t n) { return star_gpu_set_sj_novel((star_ctx_t*)c, a, b, n); }
 static void vt_sjdb_close(void* h) { star_gpu_sjdb_close((star_sjdb_t*)h); }
-static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close, star_gpu_sa_build};
+static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close, star_gpu_sa_build, vt_set_sj_novel};
 
 int star_cli_main(int argc, char** argv) { return star_cli_main_engine(argc, argv, &g_cuda_engine); }
 

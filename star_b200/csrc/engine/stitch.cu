@@ -742,6 +742,15 @@ __device__ int log2Score(const DevIndex& ix, u64 gLen) {
     return v;
 }
 
+// binarySearch2 over the novel junctions of the 2nd BySJout stage (sorted by start, then end): is (jS, jE) in the list?  Cold path.
+__device__ __noinline__ bool sjNovelHas(const DevIndex& g, u64 jS, u64 jE) {
+    u64 lo = 0, hi = g.sjNovelN;
+    while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (g.sjNovelStart[mid] < jS) lo = mid + 1; else hi = mid; }
+    #pragma unroll 1
+    for (; lo < g.sjNovelN && g.sjNovelStart[lo] == jS; lo++) if (g.sjNovelEnd[lo] == jE) return true;
+    return false;
+}
+
 // Leaf of stitchWindowAligns, part 1 (stitchWindowAligns.cpp:19-243): extend both ends, apply the filters, compute the final score.
 // Pure function of the DFS path (reads no per-read mutable state), so the heavy path can evaluate leaves of different sub-trees
 // in parallel.  Result in ln.leaf (h.maxScore, h.iFrag set).  Returns false when a filter drops the transcript.
@@ -844,6 +853,11 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
                 nsj++;
             }
         }
+    }
+    if (__builtin_expect(g.sjNovelOn != 0, 0)) {   // stitchWindowAligns.cpp:169-177 (2nd stage of --outFilterType BySJout)
+        #pragma unroll 1
+        for (u32 iex = 0; iex + 1 < nEx; iex++)
+            if (t.ex[iex].canon >= 0 && t.ex[iex].annot == 0 && !sjNovelHas(g, t.ex[iex].G + t.ex[iex].L, t.ex[iex + 1].G - 1)) return false;
     }
     if (t.ex[0].iFrag != t.ex[nEx - 1].iFrag) {
         if (t.ex[nEx - 1].G + t.ex[nEx - 1].L <= t.ex[0].G) return false;

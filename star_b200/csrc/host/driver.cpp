@@ -61,12 +61,48 @@ static void writeShardBin(const std::string& path, const Stats& stats, const std
 // One mapping pass over the read files (ReadAlignChunk::processChunks / mapThreadsSpawn for all chunks): reads -> engine -> records.
 // Used for the main pass and, with the outputs switched off in P, for the 1st pass of --twopassMode Basic.
 // Returns 0 or a STAR_EXIT_* code with the message in err.
+// State that outlives one call of mapPass when a run maps in two stages (--outFilterType BySJout, STAR.cpp:196-220): the reads held
+// back by the 1st stage, the junction records of all reads, and the records waiting for the coordinate sort.
+struct CoordRec { uint64_t alignG, key; uint32_t blob, size; uint64_t off; };
+struct StageState {
+    int bySJstage = 0;                       // 0: single stage; 1: hold reads with unannotated junctions; 2: map the held reads
+    std::vector<Junction> sjAll;             // stage 1: junction records of ALL mapped reads (chunkOutSJ1)
+    std::vector<ReadChunk> held;             // stage 1 -> 2: the reads to map again, in input order, chunked (never across input files)
+    std::vector<std::string> coordBlobs;     // coordinate-sorted BAM: uncompressed records of every stage
+    std::vector<CoordRec> coordIndex;
+};
+
+static void holdRead(std::vector<ReadChunk>& held, const ReadChunk& c, uint32_t i, uint32_t maxReads) {
+    if (held.empty() || held.back().nReads >= maxReads || held.back().fileIndex != c.fileIndex) {
+        held.emplace_back();
+        ReadChunk& h = held.back();
+        h.nMates = c.nMates; h.fastq = c.fastq; h.fileIndex = c.fileIndex;
+        h.seqOff.push_back(0); h.nameOff.push_back(0);
+    }
+    ReadChunk& h = held.back();
+    for (uint32_t m = 0; m < c.nMates; m++) {
+        const uint64_t a = c.seqOff[(uint64_t)i * c.nMates + m], b = c.seqOff[(uint64_t)i * c.nMates + m + 1];
+        h.seq.append(c.seq, a, b - a);
+        if (!c.qual.empty()) h.qual.append(c.qual, a, b - a);
+        h.seqOff.push_back(h.seq.size());
+    }
+    h.names.append(c.names, c.nameOff[i], c.nameOff[i + 1] - c.nameOff[i]);
+    h.nameOff.push_back((uint32_t)h.names.size());
+    h.readFilter.push_back(c.readFilter[i]);
+    h.iReadAll.push_back(c.iReadAll[i]);
+    h.nReads++;
+}
+
 static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engine_vtbl_t* eng, void* ectx, Stats& stats, std::vector<Junction>& allSJ,
-                   std::ofstream& logMain, std::string& err) {
+                   std::ofstream& logMain, std::string& err, StageState& stage) {
     int rc = 0;
+    const bool firstStage = stage.bySJstage != 2, lastStage = stage.bySJstage != 1;
     ReadsReader reader;
-    rc = reader.open(P, err);
-    if (rc) return rc;
+    if (firstStage) {
+        rc = reader.open(P, err);
+        if (rc) return rc;
+    }
+    size_t heldNext = 0;   // 2nd stage: the held chunks are the input
 
     OutputWriter W(P, idx);
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
@@ -75,8 +111,8 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     const bool bamYes = samYes && P.outBAMunsorted;
     const bool coordYes = samYes && P.outBAMcoord;                                        // Aligned.sortedByCoord.out.bam, sorted at the end
     if (streamYes) {
-        samOut.open(P.outFileNamePrefix + (bamYes ? "Aligned.out.bam" : "Aligned.out.sam"), std::ios::binary);
-        if (P.gpuShardIndex == 0) {   // shards > 0 write records only; the merge concatenates in shard order
+        samOut.open(P.outFileNamePrefix + (bamYes ? "Aligned.out.bam" : "Aligned.out.sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (P.gpuShardIndex == 0 && firstStage) {   // shards > 0 write records only; the merge concatenates in shard order
             if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samOut.write(z.data(), z.size()); }
             else samOut << W.samHeader();
         }
@@ -106,9 +142,8 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     Queue freeQ, mapQ, outQ;
     for (auto& wk : bufs) freeQ.push(&wk);
     // coordinate-sorted BAM: all records stay in host memory (uncompressed, ~0.55 kB per record) until the end of the run
-    struct CoordRec { uint64_t alignG, key; uint32_t blob, size; uint64_t off; };
-    std::vector<std::string> coordBlobs;
-    std::vector<CoordRec> coordIndex;
+    std::vector<std::string>& coordBlobs = stage.coordBlobs;
+    std::vector<CoordRec>& coordIndex = stage.coordIndex;
     const int nT = std::max(1, P.runThreadN);
     double msEngine = 0, msRead = 0, msFormat = 0, msWrite = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -123,7 +158,9 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             if (abortRun.load()) { wk->n = 0; mapQ.push(wk); return; }
             auto t0 = now();
             wk->err.clear();
-            wk->n = reader.next(wk->chunk, P.gpuChunkReads, wk->err);
+            if (firstStage) wk->n = reader.next(wk->chunk, P.gpuChunkReads, wk->err);
+            else if (heldNext < stage.held.size()) { wk->chunk = std::move(stage.held[heldNext++]); wk->n = wk->chunk.nReads; }
+            else wk->n = 0;
             msRead += msSince(t0);
             const long long n = wk->n;
             mapQ.push(wk);
@@ -142,10 +179,12 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 std::vector<Stats> st(nT);
                 std::vector<std::string> cblob(coordYes ? nT : 0);
                 std::vector<std::vector<uint64_t>> ckey(coordYes ? nT : 0);
+                std::vector<OutputWriter::BySJoutHold> hold(stage.bySJstage == 1 ? nT : 0);
                 auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
                     uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
                     sam[t].reserve((size_t)(hi - lo) * 700);
-                    W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr);
+                    W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr,
+                                  stage.bySJstage == 1 ? &hold[t] : nullptr);
                     if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
                         std::string z;
                         z.reserve(sam[t].size() / 3);
@@ -166,6 +205,10 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     if (streamYes) samOut.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
+                    if (stage.bySJstage == 1) {
+                        stage.sjAll.insert(stage.sjAll.end(), hold[t].sjAll.begin(), hold[t].sjAll.end());
+                        for (uint32_t i : hold[t].held) holdRead(stage.held, chunk, i, P.gpuChunkReads);
+                    }
                     if (coordYes && !cblob[t].empty()) {   // index the records of this piece (BAMoutput::coordOneAlign: key = refID<<32 | pos)
                         const uint32_t ib = (uint32_t)coordBlobs.size();
                         coordBlobs.emplace_back();
@@ -184,6 +227,11 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
                     std::string e2;
                     OutputWriter::collapseSJ(allSJ, e2);
+                    if (!e2.empty()) { outErr = e2; abortRun.store(true); }
+                }
+                if (stage.sjAll.size() > 4000000) {
+                    std::string e2;
+                    OutputWriter::collapseSJ(stage.sjAll, e2);
                     if (!e2.empty()) { outErr = e2; abortRun.store(true); }
                 }
             }
@@ -229,9 +277,9 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     readerThread.join();
     if (runRc) { err = runErr; return runRc; }
     if (!outErr.empty()) { err = outErr; return STAR_EXIT_BUG; }
-    if (bamYes && P.gpuShardCount == 1) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
+    if (bamYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
     if (streamYes) samOut.close();
-    if (coordYes) {
+    if (coordYes && lastStage) {
         // bamSortByCoordinate.cpp / BAMbinSortByCoordinate.cpp:49-55 / BAMbinSortUnmapped.cpp: mapped records by (refID<<32|pos, read-order key,
         // emission order), then the unmapped ones (refID = -1 sorts last) in read order.  The reference bins by coordinate and sorts bin by
         // bin on disk; one stable in-memory sort gives the same sequence.
@@ -342,7 +390,8 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         time(&st1.timeStartMap);
         std::cout << timeMonthDayTime(st1.timeStartMap) << " ..... started 1st pass mapping\n" << std::flush;
         std::vector<Junction> sj1;
-        rc = mapPass(P1, idx, eng, ectx, st1, sj1, logMain, err);
+        StageState stage1;
+        rc = mapPass(P1, idx, eng, ectx, st1, sj1, logMain, err, stage1);
         eng->destroy(ectx);
         if (rc) return exitWithError(err, rc, &logMain);
         time(&st1.timeFinish);
@@ -369,10 +418,24 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     time(&stats.timeStartMap);
     std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
     std::vector<Junction> allSJ;
-    rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err);
+    StageState stage;
+    OutputWriter W(P, idx);
+    const bool bySJout = P.outFilterType == "BySJout";
+    stage.bySJstage = bySJout ? 1 : 0;
+    rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err, stage);
+    if (!rc && bySJout) {   // STAR.cpp:203-220: the novel junctions that pass the filters over ALL reads, then the held reads once more
+        logMain << "Completed stage 1 mapping of outFilterBySJout mapping\n" << std::flush;
+        std::vector<uint64_t> njS, njE;
+        std::string e2 = W.novelJunctions(stage.sjAll, njS, njE);
+        if (!e2.empty()) { eng->destroy(ectx); return exitWithError(e2, STAR_EXIT_BUG, &logMain); }
+        logMain << "Detected " << njS.size() << " novel junctions that passed filtering, will proceed to filter reads that contained unannotated junctions" << std::endl;
+        rc = eng->set_sj_novel(ectx, njS.data(), njE.data(), njS.size());
+        if (rc) err = std::string("EXITING because of FATAL ERROR: ") + eng->last_error() + "\n";
+        stage.bySJstage = 2;
+        if (!rc) rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err, stage);
+    }
     eng->destroy(ectx);
     if (rc) return exitWithError(err, rc, &logMain);
-    OutputWriter W(P, idx);
     {
         time_t tFinishMap; time(&tFinishMap);
         std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
@@ -391,7 +454,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         return 0;
     }
     if (P.outSJyes) {
-        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab");
+        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab", /*distFilter*/ !bySJout);
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
     }
     W.writeLogFinal(stats, P.outFileNamePrefix + "Log.final.out");

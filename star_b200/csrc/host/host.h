@@ -210,15 +210,20 @@ class OutputWriter {
     // appends SAM text for reads [lo,hi) of the chunk to `sam`, junctions to `sj`, counters to `st`
     // coord / coordKey (may be NULL): the records for the coordinate-sorted BAM (uncompressed) and, per record, the read-order key
     // (iReadAll<<32 | iTr<<8 | mate) of BAMoutput::coordOneAlign
+    // by (1st stage of --outFilterType BySJout): reads with an unannotated junction are neither counted nor written but listed in
+    // by->held; the junction records of ALL mapped reads are appended to by->sjAll
+    struct BySJoutHold { std::vector<uint32_t> held; std::vector<Junction> sjAll; };
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                     std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr) const;
+                     std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr,
+                     BySJoutHold* by = nullptr) const;
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
     std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`
     static void bgzfCompress(const char* data, size_t n, int level, std::string& out);
     static const char* bgzfEofBlock(size_t& n);
     // outputSJ.cpp:20-200: collapse + filters + SJ.out.tab text; returns error text (empty = ok)
-    std::string writeSJ(std::vector<Junction>& all, const std::string& path) const;
+    std::string writeSJ(std::vector<Junction>& all, const std::string& path, bool distFilter = true) const;
+    std::string novelJunctions(std::vector<Junction>& all, std::vector<uint64_t>& sjStart, std::vector<uint64_t>& sjEnd) const;
     static void collapseSJ(std::vector<Junction>& v, std::string& err);
     void writeLogFinal(const Stats& st, const std::string& path) const;  // Stats.cpp:99-145
 

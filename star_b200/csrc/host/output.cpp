@@ -631,7 +631,7 @@ const char* OutputWriter::bgzfEofBlock(size_t& n) {
 
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey) const {
+                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by) const {
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     const bool coordYes = samYes && P.outBAMcoord && coord && coordKey;
     // records appended to `dst` since `from` also go to the coordinate-sorted set with read-order key `key` (one key per record)
@@ -649,6 +649,18 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
         const star_read_result_t& r = out.reads[i];
         uint64_t L0 = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
         uint64_t L1 = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+        if (by && r.unmapType < 0) {   // ReadAlign::outFilterBySJout (ReadAlign_outputAlignments.cpp:90-130), 1st stage of --outFilterType BySJout
+            const star_align_t* tr1 = out.aligns + r.trOffset;
+            bool pass = true;
+            for (uint64_t k = 0; k < r.nTrOut && pass; k++)
+                for (uint32_t iex = 0; iex + 1 < tr1[k].nExons; iex++)
+                    if (tr1[k].canonSJ[iex] >= 0 && tr1[k].sjAnnot[iex] == 0) { pass = false; break; }
+            if (P.outSJyes && (P.outSJfilterReads == "All" || r.nTrOut == 1)) {   // the junctions of ALL reads decide which novel ones survive
+                size_t s0 = by->sjAll.size();
+                for (uint64_t k = 0; k < r.nTrOut; k++) recordSJ(tr1[k], r.nTrOut, by->sjAll, s0);
+            }
+            if (!pass) { by->held.push_back(i); continue; }   // not counted, not written: mapped again in the 2nd stage
+        }
         st.readN++;
         st.readBases += L0 + L1;
         int unmapType = r.unmapType;
@@ -751,11 +763,13 @@ void OutputWriter::collapseSJ(std::vector<Junction>& v, std::string& err) {  // 
     v.resize(k + 1);
 }
 
-std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string& path) const {  // outputSJ.cpp:20-165
+// outputSJ.cpp:20-124: collapse, the count / overhang / intron-size filters (kept), then the distance-to-neighbour filters (sjFilter);
+// distFilter = false is the 2nd stage of --outFilterType BySJout, where every kept junction is written (outputSJ.cpp:86, 130)
+static std::string filterSJ(const HostParams& P, std::vector<Junction>& all, std::vector<Junction>& kept, std::vector<char>& sjFilter, bool distFilter) {
     std::string err;
-    collapseSJ(all, err);
+    OutputWriter::collapseSJ(all, err);
     if (!err.empty()) return err;
-    std::vector<Junction> kept;
+    kept.clear();
     for (auto& j : all) {
         int mi = (j.motif + 1) / 2;
         uint32_t tot = j.countMultiple + j.countUnique;
@@ -766,7 +780,8 @@ std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string&
         if (f) kept.push_back(j);
     }
     size_t N = kept.size();
-    std::vector<char> sjFilter(N, 0);
+    sjFilter.assign(N, distFilter ? 0 : 1);
+    if (!distFilter) return std::string();
     std::vector<uint64_t> sjA(N * 3);
     for (size_t ii = 0; ii < N; ii++) {
         uint64_t x1 = 0, x2 = (uint64_t)-1;
@@ -793,6 +808,15 @@ std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string&
             sjFilter[sjA[ii * 3 + 1]] = sjFilter[sjA[ii * 3 + 1]] && (minDist >= (uint64_t)P.outSJfilterDistToOtherSJmin[(sjA[ii * 3 + 2] + 1) / 2]);
         }
     }
+    return std::string();
+}
+
+std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string& path, bool distFilter) const {  // outputSJ.cpp:20-165
+    std::vector<Junction> kept;
+    std::vector<char> sjFilter;
+    std::string err = filterSJ(P, all, kept, sjFilter, distFilter);
+    if (!err.empty()) return err;
+    const size_t N = kept.size();
     std::string txt;
     for (size_t ii = 0; ii < N; ii++) {
         if (!sjFilter[ii]) continue;
@@ -805,6 +829,19 @@ std::string OutputWriter::writeSJ(std::vector<Junction>& all, const std::string&
     }
     std::ofstream o(path);
     o << txt;
+    return std::string();
+}
+
+// 1st stage of --outFilterType BySJout (outputSJ.cpp:139-160): the unannotated junctions of ALL reads that pass every filter, as
+// (first, last) intron base, in collapsed (start, gap) order
+std::string OutputWriter::novelJunctions(std::vector<Junction>& all, std::vector<uint64_t>& sjStart, std::vector<uint64_t>& sjEnd) const {
+    std::vector<Junction> kept;
+    std::vector<char> sjFilter;
+    std::string err = filterSJ(P, all, kept, sjFilter, true);
+    if (!err.empty()) return err;
+    sjStart.clear(); sjEnd.clear();
+    for (size_t ii = 0; ii < kept.size(); ii++)
+        if (sjFilter[ii] && kept[ii].annot == 0) { sjStart.push_back(kept[ii].start); sjEnd.push_back(kept[ii].start + (uint64_t)kept[ii].gap - 1); }
     return std::string();
 }
 

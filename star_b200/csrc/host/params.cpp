@@ -272,7 +272,10 @@ int finalizeParams(HostParams& P, std::string& err) {
     }
     P.readNmates = (unsigned)P.readFilesIn.size();
     if (h.seedSearchLmax != 0) return bad("EXITING because of fatal PARAMETERS error: --seedSearchLmax >0 is not supported by star-b200\n");
-    if (P.outFilterType != "Normal") return bad("EXITING because of FATAL input ERROR: --outFilterType " + P.outFilterType + " is not supported by star-b200 (only Normal)\n");
+    if (P.outFilterType != "Normal" && P.outFilterType != "BySJout")   // Parameters.cpp:1176-1190
+        return bad("EXITING because of FATAL input ERROR: unknown value of parameter outFilterType: " + P.outFilterType + "\nSOLUTION: re-run STAR with --outFilterType Normal OR BySJout\n");
+    if (P.outFilterType == "BySJout" && P.gpuShardCount > 1)
+        return bad("EXITING because of fatal input ERROR: --outFilterType BySJout is not supported for sharded (multi-GPU) runs yet: the junctions of all shards decide which reads are kept\n");
     if (P.outMultimapperOrder != "Old_2.4") return bad("EXITING because of fatal PARAMETERS error: --outMultimapperOrder " + P.outMultimapperOrder + " is not supported by star-b200 (only Old_2.4)\n");
     // Parameters.cpp:944-955
     if (P.outSAMstrandField == "None") h.outSAMstrandFieldType = 0;

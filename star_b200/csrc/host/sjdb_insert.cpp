@@ -21,10 +21,12 @@ namespace starhost {
 
 // sjdbLoadFromStream.cpp:2-28: chr, start, end, strand ('+', '-', '.', or the 1 / 2 / 0 of SJ.out.tab); further columns are ignored
 void sjdbLoadFromStream(std::istream& in, SjdbLoci& loci) {
+    // A line without a 4th column leaves the reference's (uninitialised) strand variable as it was: in practice the converted strand
+    // of the previous line.  Kept across the lines of one stream here, '.' for the first line.
+    char s1 = 0;
     while (in.good()) {
         std::string line, chr;
         uint64_t u1 = 0, u2 = 0;
-        char s1 = 0;
         std::getline(in, line);
         std::istringstream ls(line);
         ls >> chr >> u1 >> u2 >> s1;
@@ -32,7 +34,8 @@ void sjdbLoadFromStream(std::istream& in, SjdbLoci& loci) {
         loci.chr.push_back(chr);
         loci.start.push_back(u1);
         loci.end.push_back(u2);
-        loci.str.push_back(s1 == '1' || s1 == '+' ? '+' : (s1 == '2' || s1 == '-' ? '-' : '.'));
+        s1 = s1 == '1' || s1 == '+' ? '+' : (s1 == '2' || s1 == '-' ? '-' : '.');
+        loci.str.push_back(s1);
     }
 }
 

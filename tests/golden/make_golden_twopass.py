@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Regenerates tests/golden/twopass.tar.gz — run in the BUILD container only (needs oracle/_ref/STAR, i.e. /root/reference).
 
-Golden outputs of the UNMODIFIED reference binary for on-the-fly junction insertion and --twopassMode Basic,
+Golden outputs of the UNMODIFIED reference binary for on-the-fly junction insertion, --twopassMode Basic and
+--outFilterType BySJout (the S* scenarios),
 on the inputs of tiny.tar.gz:
 
   twopass/idx0/                     reference genomeGenerate WITHOUT annotation (--genomeSAindexNbases 7): every junction is novel
@@ -32,6 +33,12 @@ SCENARIOS = {
                          "--sjdbFileChrStartEnd", "TP/sj_dot.tab", "TP/sj_opp.tab", "TP/sj_shift.tab", "--twopass1readsN", "300"],
     "E_insert_only": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbInsertSave", "All",
                       "--sjdbFileChrStartEnd", "TP/sj_half.tab", "TP/sj_opp.tab"],
+    "S1_bysjout": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--outFilterType", "BySJout"],
+    "S2_bysjout_annot_within": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outFilterType", "BySJout", "--outSAMunmapped", "Within"],
+    "S3_bysjout_se_filters": ["--genomeDir", "TP/idx0", "--readFilesIn", "se_1.fq", "--outFilterType", "BySJout", "--outSJfilterCountUniqueMin", "1", "1", "1", "1",
+                              "--outSJfilterOverhangMin", "20", "10", "10", "10"],
+    "S4_bysjout_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outFilterType", "BySJout", "--twopassMode", "Basic",
+                           "--outSAMattributes", "NH", "HI", "AS", "nM", "XS", "--sjdbInsertSave", "All"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
@@ -76,9 +83,10 @@ def main():
             if os.path.exists(out + k):
                 os.makedirs(os.path.dirname(os.path.join(dst, k)), exist_ok=True)
                 shutil.copy(out + k, os.path.join(dst, k))
-        with open(os.path.join(dst, "_STARgenome", "sha256.txt"), "w") as f:
-            for g in ("Genome", "SA", "SAindex"):
-                f.write("%s\t%s\n" % (g, sha(out + "_STARgenome/" + g)))
+        if os.path.exists(out + "_STARgenome/SA"):
+            with open(os.path.join(dst, "_STARgenome", "sha256.txt"), "w") as f:
+                for g in ("Genome", "SA", "SAindex"):
+                    f.write("%s\t%s\n" % (g, sha(out + "_STARgenome/" + g)))
     with open(os.path.join(tp, "scenarios.json"), "w") as f:
         json.dump(SCENARIOS, f, indent=1)
     dst = os.path.join(ROOT, "tests", "golden", "twopass.tar.gz")

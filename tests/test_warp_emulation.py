@@ -103,3 +103,55 @@ def test_emulated_kernels_equal_oracle(oracle, lib, golden, name, n_take, env, m
         assert int(info4[0]) > 0, "no read reached the flat path / the warp-per-read kernel"
     diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
     assert not diffs, "\n".join(diffs[:10])
+
+
+@pytest.mark.parametrize("env", [{}, {"STAR_B200_HEAVY_NA": "2000000000", "STAR_B200_HEAVY_EST": "0"}])
+def test_emulated_kernels_sj_novel_filter(oracle, lib, golden, twopass_golden, env, monkeypatch):
+    """2nd stage of --outFilterType BySJout (stitchWindowAligns.cpp:169-177) in the device code: with the list of surviving novel
+    junctions set, evalLeaf drops transcripts whose unannotated junctions are not in it.  Emulated kernels (default pipeline and lane
+    path) against the oracle on the un-annotated index, with every second junction of the unfiltered alignments in the list."""
+    import star_b200 as sb
+    from star_b200 import capi
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    all_mates = [cf.read_fastq_seqs(os.path.join(golden, "std_%d.fq" % m))[:300] for m in (1, 2)]
+    idx = sb.Index(lib, os.path.join(twopass_golden, "idx0"))
+    oe = oc.OracleEngine(oracle, idx)
+    seq, off, n, nm = sb.pack_reads(all_mates)
+    resA, alA, _ = oe.map_chunk(seq, off, n, nm)   # pick 6 spliced reads and 4 others (the emulation is slow)
+    spliced = [i for i in range(n) if resA["nTrOut"][i] > 0 and any(
+        (alA[int(resA["trOffset"][i]) + k]["canonSJ"][:max(0, int(alA[int(resA["trOffset"][i]) + k]["nExons"]) - 1)] >= 0).any() for k in range(int(resA["nTrOut"][i])))]
+    pick = sorted(spliced[:6] + [i for i in range(n) if i not in spliced][:4])
+    mates = [[m[i] for i in pick] for m in all_mates]
+    seq, off, n, nm = sb.pack_reads(mates)
+    res0, al0, _ = oe.map_chunk(seq, off, n, nm)
+    sj = set()
+    for a in al0:
+        for iex in range(int(a["nExons"]) - 1):
+            if a["canonSJ"][iex] >= 0 and a["sjAnnot"][iex] == 0:
+                sj.add((int(a["exG"][iex]) + int(a["exL"][iex]), int(a["exG"][iex + 1]) - 1))
+    sj = sorted(sj)
+    assert len(sj) >= 3
+    keep = sj[::2]
+    s = np.array([x[0] for x in keep], dtype=np.uint64)
+    e = np.array([x[1] for x in keep], dtype=np.uint64)
+    oracle.star_oracle_set_sj_novel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    assert oracle.star_oracle_set_sj_novel(oe.ctx, s.ctypes.data, e.ctypes.data, len(keep)) == 0
+    res_o, al_o, _ = oe.map_chunk(seq, off, n, nm)
+    assert oc.compare_outputs(res0, al0, res_o, al_o), "the filter changed nothing: the test does not test"
+    batch = oe._batch(seq, off, n, nm)
+    res, al, ab = oe._out(n, oe.n_out)
+    oe.close()
+    em = C.CDLL(ENGINE_EMUL_LIB)
+    em.engine_emul_map_chunk.argtypes = [C.POINTER(capi.IndexView), C.POINTER(capi.Params), C.POINTER(capi.ReadBatch), C.POINTER(capi.AlignBatch), C.c_void_p]
+    em.engine_emul_set_sj_novel.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    em.engine_emul_set_sj_novel(s.ctypes.data, e.ctypes.data, len(keep))
+    try:
+        info4 = np.zeros(4, dtype=np.uint64)
+        rc = em.engine_emul_map_chunk(idx.view, C.byref(idx.params), C.byref(batch), C.byref(ab), info4.ctypes.data)
+    finally:
+        em.engine_emul_set_sj_novel(None, None, C.c_uint64(2**64 - 1))
+        idx.close()
+    assert rc == 0 and int(info4[2]) == 0
+    diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
+    assert not diffs, "\n".join(diffs[:10])

@@ -1,4 +1,4 @@
-"""On-the-fly junction insertion and --twopassMode Basic against outputs of the UNMODIFIED reference
+"""On-the-fly junction insertion, --twopassMode Basic and --outFilterType BySJout (the S* scenarios) against outputs of the UNMODIFIED reference
 (tests/golden/twopass.tar.gz, make_golden_twopass.py): Aligned.out.sam, SJ.out.tab, Log.final.out of both passes, sjdbInfo.txt /
 sjdbList.out.tab and the bytes of the rebuilt Genome / SA / SAindex (--sjdbInsertSave All, compared by digest).
 
@@ -16,7 +16,8 @@ import conftest as cf
 import oracle_capi as oc
 
 ROOT = cf.ROOT
-NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only", "F_gtf_insert", "G_gtf_files_twopass"]
+NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only", "F_gtf_insert", "G_gtf_files_twopass",
+         "S1_bysjout", "S2_bysjout_annot_within", "S3_bysjout_se_filters", "S4_bysjout_twopass"]
 
 
 def _args(tp, golden, name):
