@@ -39,6 +39,11 @@ SCENARIOS = {
                               "--outSJfilterOverhangMin", "20", "10", "10", "10"],
     "S4_bysjout_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outFilterType", "BySJout", "--twopassMode", "Basic",
                            "--outSAMattributes", "NH", "HI", "AS", "nM", "XS", "--sjdbInsertSave", "All"],
+    # the ENCODE long-RNA option set (STAR manual, "ENCODE options") with 2-pass on the hard reads
+    "T_encode_twopass": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outFilterType", "BySJout", "--outSAMattributes", "NH", "HI", "AS", "NM", "MD",
+                         "--outFilterMultimapNmax", "20", "--outFilterMismatchNmax", "999", "--outFilterMismatchNoverReadLmax", "0.04", "--alignIntronMin", "20",
+                         "--alignIntronMax", "1000000", "--alignMatesGapMax", "1000000", "--alignSJoverhangMin", "8", "--alignSJDBoverhangMin", "1", "--sjdbScore", "1",
+                         "--outSAMunmapped", "Within", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
