@@ -329,6 +329,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     if (logMain.fail())
         return exitWithError("EXITING because of FATAL ERROR: could not create output file: " + P.outFileNamePrefix + "Log.out\nSOLUTION: check if the path " + P.outFileNamePrefix + " exists and you have permissions to write there\n", STAR_EXIT_PARAMETER, nullptr);
     logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
+    for (const std::string& ip : P.ignoredParams) logMain << "star-b200: --" << ip << " is accepted and has no effect (no host-side buffer / temporary-file limits)\n";
     std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
 
     if (P.runMode == "genomeGenerate") {   // STAR.cpp:120-125

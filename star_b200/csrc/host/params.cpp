@@ -85,15 +85,15 @@ bool parseU64(const std::string& s, uint64_t& out) {
 
 // STAR parameters that exist in the reference but belong to subsystems outside the hot path
 const char* kUnsupported[] = {
-    "parametersFiles", "sysShell", "runDirPerm", "runRNGseed", "genomeChainFiles", "genomeFileSizes",
+    "parametersFiles", "genomeChainFiles", "genomeFileSizes",
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "varVCFfile", "readFilesType",
-    "readFilesSAMattrKeep", "readFilesManifest", "readFilesPrefix", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
-    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", "limitIObufferSize",
-    "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed", "limitBAMsortRAM", "limitNreadsSoft",
-    "outTmpDir", "outTmpKeep", "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
-    "outSAMfilter", "outSAMtlen", "outBAMsortingThreadN", "outBAMsortingBinsN", "outWigType", "outWigStrand",
+    "readFilesSAMattrKeep", "readFilesManifest", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
+    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
+    
+    "outReadsUnmapped", "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
+    "outSAMfilter", "outSAMtlen", "outWigType", "outWigStrand",
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
@@ -104,6 +104,11 @@ const char* kUnsupported[] = {
     "soloInputSAMattrBarcodeSeq", "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup",
     "soloUMIfiltering", "soloOutFileNames", "soloCellFilter", "soloOutFormatFeaturesGeneField3", "soloCellReadStats", "soloClusterCBfile",
     "sjdbScoreX"};
+
+// resource / housekeeping knobs of the reference that cannot change any output here (buffers are sized from the chunk, the BAM sort is in
+// memory, there are no temporary files): accepted and ignored, so that existing command lines keep working
+const char* kIgnored[] = {"sysShell", "runDirPerm", "runRNGseed", "limitIObufferSize", "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed",
+                          "limitBAMsortRAM", "limitNreadsSoft", "outTmpDir", "outTmpKeep", "outBAMsortingThreadN", "outBAMsortingBinsN"};
 
 }  // namespace
 
@@ -164,7 +169,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     U64("outFilterMultimapNmax", &h.outFilterMultimapNmax); I32("outFilterScoreMin", &h.outFilterScoreMin);
     DBL("outFilterScoreMinOverLread", &h.outFilterScoreMinOverLread); U64("outFilterMatchNmin", &h.outFilterMatchNmin);
     DBL("outFilterMatchNminOverLread", &h.outFilterMatchNminOverLread); U64("outSAMmultNmax", &h.outSAMmultNmax);
-    STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn);
+    STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
     VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outSAMorder", &P.outSAMorder);
@@ -211,6 +216,15 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     for (auto& g : given) {
         auto it = tab.find(g.first);
         if (it == tab.end()) {
+            bool ignored = false;
+            for (const char* u : kIgnored) if (g.first == u) ignored = true;
+            if (ignored && !g.second.empty() && !P.userSet.count(g.first)) {
+                P.userSet[g.first] = 2;
+                P.ignoredParams.push_back(g.first);
+                full << "   --" << g.first;
+                for (auto& v : g.second) full << " " << v;
+                continue;
+            }
             bool known = false;
             for (const char* u : kUnsupported) if (g.first == u) known = true;
             if (known)
@@ -256,6 +270,11 @@ int finalizeParams(HostParams& P, std::string& err) {
     }
     if (P.runMode != "alignReads")
         return bad("EXITING because of fatal input ERROR: star-b200 implements --runMode alignReads and genomeGenerate only\n");
+    if (P.genomeLoad == "LoadAndKeep" || P.genomeLoad == "LoadAndRemove") {   // the index lives in this process' HBM; nothing is shared or kept
+        if (P.twopassMode != "None" || P.sjdbFileChrStartEnd[0] != "-" || P.sjdbGTFfile != "-")   // Parameters.cpp:809-814, 1012-1017
+            return bad("EXITING because of fatal PARAMETERS error: on the fly junction insertion and 2-pass mappng cannot be used with shared memory genome \nSOLUTION: run STAR with --genomeLoad NoSharedMemory to avoid using shared memory\n");
+        P.genomeLoad = "NoSharedMemory";
+    }
     if (P.genomeLoad != "NoSharedMemory")
         return bad("EXITING because of fatal input ERROR: --genomeLoad " + P.genomeLoad + " is not supported: the index is resident in GPU HBM instead of host shared memory\n");
     if (P.outStd != "Log") return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not supported by star-b200 (only Log)\n");
@@ -266,6 +285,7 @@ int finalizeParams(HostParams& P, std::string& err) {
         std::string cur;
         for (char ch : P.readFilesIn[imate]) { if (ch == ',') { P.readFilesNames[imate].push_back(cur); cur.clear(); } else cur.push_back(ch); }
         if (!cur.empty() || P.readFilesNames[imate].empty()) P.readFilesNames[imate].push_back(cur);   // (an extra comma at the end is ignored)
+        if (P.readFilesPrefix != "-") for (auto& fn : P.readFilesNames[imate]) fn = P.readFilesPrefix + fn;   // Parameters_readFilesInit.cpp:40,59
         if (imate > 0 && P.readFilesNames[imate].size() != P.readFilesNames[imate - 1].size())
             return bad("EXITING: because of fatal INPUT ERROR: number of input files for mate" + std::to_string(imate + 1) + "=" + std::to_string(P.readFilesNames[imate].size()) +
                        " is not equal to that for mate" + std::to_string(imate - 1) + "=" + std::to_string(P.readFilesNames[imate - 1].size()) + "\nMake sure that the number of files in --readFilesIn is the same for both mates\n");
@@ -344,7 +364,7 @@ int finalizeParams(HostParams& P, std::string& err) {
         return bad("EXITING because of fatal input ERROR: unknown value for the first word of outSAMtype: " + P.outSAMtype[0] + "\nSOLUTION: re-run STAR with one of the allowed values of outSAMtype: BAM or SAM \n");
     if (P.outSAMmode != "Full" && P.outSAMmode != "NoQS" && P.outSAMmode != "None")
         return bad("EXITING because of FATAL input ERROR: unknown value for the option --outSAMmode=" + P.outSAMmode + "\nSOLUTION: use one of the allowed values: None or Full or NoQS\n");
-    if (P.outSAMorder != "Paired")
+    if (P.outSAMorder != "Paired" && P.outSAMorder != "PairedKeepInputOrder")   // (records are always written in input order, which both values allow)
         return bad("EXITING because of fatal input ERROR: --outSAMorder " + P.outSAMorder + ": star-b200 always writes records in input order (the reference's --runThreadN 1 order)\n");
     // SJ
     if (P.outSJtype[0] == "None") P.outSJyes = false;

@@ -72,3 +72,18 @@ def test_gpu_cli_twopass_matches_reference(lib, golden, twopass_golden, tmp_path
     subprocess.check_call([os.path.join(ROOT, "star_b200", "bin", "STAR")] + _args(twopass_golden, golden, name) + ["--outFileNamePrefix", out, "--runThreadN", "2"],
                           stdout=subprocess.DEVNULL)
     cf.check_twopass_outputs(out, os.path.join(twopass_golden, name))
+
+
+def test_housekeeping_parameters_are_accepted(oracle, golden, tmp_path):
+    """Resource limits / temporary-file knobs of the reference have no effect here and must not break existing command lines;
+    --readFilesPrefix, --outSAMorder PairedKeepInputOrder and --genomeLoad LoadAndKeep map onto what the GPU build does anyway."""
+    out = str(tmp_path) + "/"
+    cmd = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesPrefix", golden + "/", "--readFilesIn", "se_1.fq", "--outFileNamePrefix", out,
+           "--limitBAMsortRAM", "1000000000", "--outBAMsortingThreadN", "2", "--limitOutSJcollapsed", "2000000", "--outSAMorder", "PairedKeepInputOrder",
+           "--genomeLoad", "LoadAndKeep", "--runRNGseed", "5", "--outTmpKeep", "None", "--runThreadN", "2"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, cwd=str(tmp_path))
+    ref = os.path.join(golden, "ref_se")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert "--limitBAMsortRAM is accepted and has no effect" in open(out + "Log.out").read()
+    r = subprocess.run(cmd + ["--twopassMode", "Basic"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    assert r.returncode == 102 and "cannot be used with shared memory genome" in r.stderr
