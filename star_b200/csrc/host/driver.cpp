@@ -68,6 +68,7 @@ struct StageState {
     int bySJstage = 0;                       // 0: single stage; 1: hold reads with unannotated junctions; 2: map the held reads
     std::vector<Junction> sjAll;             // stage 1: junction records of ALL mapped reads (chunkOutSJ1)
     std::vector<ReadChunk> held;             // stage 1 -> 2: the reads to map again, in input order, chunked (never across input files)
+    std::string streamSuffix;                // sharded 2nd stage: records go to Aligned.out<suffix>.sam|bam (the merge orders the parts)
     std::vector<std::string> coordBlobs;     // coordinate-sorted BAM: uncompressed records of every stage
     std::vector<CoordRec> coordIndex;
 };
@@ -93,6 +94,59 @@ static void holdRead(std::vector<ReadChunk>& held, const ReadChunk& c, uint32_t 
     h.nReads++;
 }
 
+// Sharded --outFilterType BySJout: what the 1st stage of a shard leaves for its 2nd stage (a separate call of the command line, after the
+// junction records of all shards have been gathered): counters, the junction records of the reads written so far, the held reads.
+template <class T> static void putVec(std::ofstream& o, const std::vector<T>& v) { uint64_t n = v.size(); o.write((const char*)&n, 8); if (n) o.write((const char*)v.data(), n * sizeof(T)); }
+template <class T> static void getVec(std::ifstream& in, std::vector<T>& v) { uint64_t n = 0; in.read((char*)&n, 8); v.resize(n); if (n) in.read((char*)v.data(), n * sizeof(T)); }
+static void putStr(std::ofstream& o, const std::string& v) { uint64_t n = v.size(); o.write((const char*)&n, 8); o.write(v.data(), n); }
+static void getStr(std::ifstream& in, std::string& v) { uint64_t n = 0; in.read((char*)&n, 8); v.resize(n); if (n) in.read(&v[0], n); }
+static void saveStage1(const std::string& path, const Stats& stats, const std::vector<Junction>& allSJ, const std::vector<ReadChunk>& held) {
+    std::ofstream o(path, std::ios::binary);
+    uint64_t cnt[Stats::N_COUNTERS];
+    stats.toArray(cnt);
+    int64_t tm[3] = {(int64_t)stats.timeStart, (int64_t)stats.timeStartMap, (int64_t)stats.timeFinish};
+    o.write((const char*)cnt, sizeof(cnt)); o.write((const char*)tm, sizeof(tm));
+    putVec(o, allSJ);
+    uint64_t nh = held.size();
+    o.write((const char*)&nh, 8);
+    for (const ReadChunk& c : held) {
+        uint32_t hd[4] = {c.nReads, c.nMates, (uint32_t)c.fastq, c.fileIndex};
+        o.write((const char*)hd, sizeof(hd));
+        putStr(o, c.seq); putStr(o, c.qual); putVec(o, c.seqOff); putStr(o, c.names); putVec(o, c.nameOff); putVec(o, c.readFilter); putVec(o, c.iReadAll);
+    }
+}
+static bool loadStage1(const std::string& path, Stats& stats, std::vector<Junction>& allSJ, std::vector<ReadChunk>& held) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) return false;
+    uint64_t cnt[Stats::N_COUNTERS]; int64_t tm[3];
+    in.read((char*)cnt, sizeof(cnt)); in.read((char*)tm, sizeof(tm));
+    stats.fromArray(cnt);
+    stats.timeStart = (time_t)tm[0]; stats.timeStartMap = (time_t)tm[1]; stats.timeFinish = (time_t)tm[2];
+    getVec(in, allSJ);
+    uint64_t nh = 0;
+    in.read((char*)&nh, 8);
+    held.resize(nh);
+    for (ReadChunk& c : held) {
+        uint32_t hd[4];
+        in.read((char*)hd, sizeof(hd));
+        c.nReads = hd[0]; c.nMates = hd[1]; c.fastq = hd[2] != 0; c.fileIndex = hd[3];
+        getStr(in, c.seq); getStr(in, c.qual); getVec(in, c.seqOff); getStr(in, c.names); getVec(in, c.nameOff); getVec(in, c.readFilter); getVec(in, c.iReadAll);
+    }
+    return in.good();
+}
+// junction records of shard.bin-style files (24 counters, 3 times, count, records)
+static bool readShardJunctions(const std::string& path, std::vector<Junction>& sj) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) return false;
+    in.seekg(8 * Stats::N_COUNTERS + 24);
+    uint64_t n = 0;
+    in.read((char*)&n, 8);
+    const size_t old = sj.size();
+    sj.resize(old + n);
+    if (n) in.read((char*)(sj.data() + old), n * sizeof(Junction));
+    return in.good();
+}
+
 static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engine_vtbl_t* eng, void* ectx, Stats& stats, std::vector<Junction>& allSJ,
                    std::ofstream& logMain, std::string& err, StageState& stage) {
     int rc = 0;
@@ -111,7 +165,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     const bool bamYes = samYes && P.outBAMunsorted;
     const bool coordYes = samYes && P.outBAMcoord;                                        // Aligned.sortedByCoord.out.bam, sorted at the end
     if (streamYes) {
-        samOut.open(P.outFileNamePrefix + (bamYes ? "Aligned.out.bam" : "Aligned.out.sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
         if (P.gpuShardIndex == 0 && firstStage) {   // shards > 0 write records only; the merge concatenates in shard order
             if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samOut.write(z.data(), z.size()); }
             else samOut << W.samHeader();
@@ -423,7 +477,30 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     OutputWriter W(P, idx);
     const bool bySJout = P.outFilterType == "BySJout";
     stage.bySJstage = bySJout ? 1 : 0;
-    rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err, stage);
+    const std::string stateFile = P.outFileNamePrefix + "bysj_stage1.bin";
+    if (!(bySJout && P.gpuBySJoutPhase == 2)) rc = mapPass(P, idx, eng, ectx, stats, allSJ, logMain, err, stage);
+    if (!rc && bySJout && P.gpuBySJoutPhase == 1) {   // one shard of a multi-GPU run: the junction records of ALL its reads go to the gather
+        std::string e2;
+        OutputWriter::collapseSJ(stage.sjAll, e2);
+        if (e2.empty()) OutputWriter::collapseSJ(allSJ, e2);
+        eng->destroy(ectx);
+        if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
+        time(&stats.timeFinish);
+        saveStage1(stateFile, stats, allSJ, stage.held);
+        writeShardBin(P.outFileNamePrefix + "bysj_sjall.bin", stats, stage.sjAll);
+        std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished 1st BySJout stage of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+        return 0;
+    }
+    if (!rc && bySJout && P.gpuBySJoutPhase == 2) {   // ... and come back from every shard (star_b200.dist: bysj_gather<r>.bin)
+        const time_t t0 = stats.timeStart;
+        if (!loadStage1(stateFile, stats, allSJ, stage.held)) { rc = STAR_EXIT_RUNTIME; err = "EXITING because of FATAL ERROR: missing 1st-stage state " + stateFile + "\n"; }
+        stats.timeStart = t0;
+        for (unsigned r = 0; r < P.gpuShardCount && !rc; r++)
+            if (!readShardJunctions(P.outFileNamePrefix + "bysj_gather" + std::to_string(r) + ".bin", stage.sjAll)) {
+                rc = STAR_EXIT_RUNTIME; err = "EXITING because of FATAL ERROR: missing gathered junctions " + P.outFileNamePrefix + "bysj_gather" + std::to_string(r) + ".bin\n";
+            }
+        stage.streamSuffix = ".stage2";
+    }
     if (!rc && bySJout) {   // STAR.cpp:203-220: the novel junctions that pass the filters over ALL reads, then the held reads once more
         logMain << "Completed stage 1 mapping of outFilterBySJout mapping\n" << std::flush;
         std::vector<uint64_t> njS, njE;
@@ -501,11 +578,17 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
             samOut.clear();   // an empty shard sets failbit on operator<<
         }
     }
+    if (samYes && P.outFilterType == "BySJout")   // the reference writes the reads held by the 1st stage after all others
+        for (int r = 0; r < nShards; r++) {
+            std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Aligned.out.stage2" + (P.outBAMunsorted ? ".bam" : ".sam"), std::ios::binary);
+            samOut << in.rdbuf();
+            samOut.clear();
+        }
     if (samYes && P.outBAMunsorted) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }
     if (counters) total.fromArray(counters);
     total.timeStart = (time_t)tStart; total.timeStartMap = (time_t)tStartMap; total.timeFinish = (time_t)tFinish;
     if (P.outSJyes) {
-        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab");
+        std::string e2 = W.writeSJ(allSJ, P.outFileNamePrefix + "SJ.out.tab", P.outFilterType != "BySJout");
         if (!e2.empty()) { std::cerr << e2 << std::endl; return STAR_EXIT_BUG; }
     }
     W.writeLogFinal(total, P.outFileNamePrefix + "Log.final.out");

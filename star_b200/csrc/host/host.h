@@ -88,6 +88,7 @@ struct HostParams {
     // star-b200 extensions (not in the reference)
     int gpuDevice = 0;
     unsigned gpuChunkReads = 262144;        // reads (pairs) per engine call
+    unsigned gpuBySJoutPhase = 0;           // sharded --outFilterType BySJout (star_b200.dist): 1 = 1st stage of this shard, 2 = 2nd stage with the gathered junctions
     unsigned gpuTwoPassPhase = 0;           // sharded --twopassMode Basic (star_b200.dist): 1 = 1st pass of this shard only, 2 = insertion of the gathered junctions + 2nd pass
     unsigned gpuShardIndex = 0, gpuShardCount = 1;   // multi-GPU: this process maps reads [n*i/N, n*(i+1)/N) (contiguous slices keep input order)
     std::map<std::string, int> userSet;     // parameter name -> input level (for --sjdbOverhang style checks)

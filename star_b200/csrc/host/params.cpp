@@ -190,6 +190,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     tab["outSAMflagAND"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.outSAMflagAND); }};
     tab["gpuDevice"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuDevice); }};
     tab["gpuShardIndex"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardIndex); }};
+    tab["gpuBySJoutPhase"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuBySJoutPhase) && P.gpuBySJoutPhase <= 2; }};
     tab["gpuTwoPassPhase"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuTwoPassPhase) && P.gpuTwoPassPhase <= 2; }};
     tab["gpuShardCount"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuShardCount) && P.gpuShardCount > 0; }};
     tab["gpuChunkReads"] = Setter{[&P](const Vals& v) { return v.size() == 1 && parseNum(v[0], P.gpuChunkReads) && P.gpuChunkReads > 0; }};
@@ -294,8 +295,10 @@ int finalizeParams(HostParams& P, std::string& err) {
     if (h.seedSearchLmax != 0) return bad("EXITING because of fatal PARAMETERS error: --seedSearchLmax >0 is not supported by star-b200\n");
     if (P.outFilterType != "Normal" && P.outFilterType != "BySJout")   // Parameters.cpp:1176-1190
         return bad("EXITING because of FATAL input ERROR: unknown value of parameter outFilterType: " + P.outFilterType + "\nSOLUTION: re-run STAR with --outFilterType Normal OR BySJout\n");
-    if (P.outFilterType == "BySJout" && P.gpuShardCount > 1)
-        return bad("EXITING because of fatal input ERROR: --outFilterType BySJout is not supported for sharded (multi-GPU) runs yet: the junctions of all shards decide which reads are kept\n");
+    if (P.outFilterType == "BySJout" && P.gpuShardCount > 1 && P.gpuBySJoutPhase == 0 && P.gpuTwoPassPhase != 1)   // (the 1st pass of a 2-pass run does not filter)
+        return bad("EXITING because of fatal input ERROR: --outFilterType BySJout of a sharded (multi-GPU) run needs the junctions of all shards between its two stages: run it through `python -m star_b200.dist` (which gathers them between --gpuBySJoutPhase 1 and 2)\n");
+    if (P.gpuBySJoutPhase != 0 && !(P.outFilterType == "BySJout" && P.gpuShardCount > 1))
+        return bad("EXITING because of fatal PARAMETERS error: --gpuBySJoutPhase is only meaningful for a sharded --outFilterType BySJout run\n");
     if (P.outMultimapperOrder != "Old_2.4") return bad("EXITING because of fatal PARAMETERS error: --outMultimapperOrder " + P.outMultimapperOrder + " is not supported by star-b200 (only Old_2.4)\n");
     // Parameters.cpp:944-955
     if (P.outSAMstrandField == "None") h.outSAMstrandFieldType = 0;
@@ -370,6 +373,8 @@ int finalizeParams(HostParams& P, std::string& err) {
     if (P.outSJtype[0] == "None") P.outSJyes = false;
     else if (P.outSJtype[0] == "Standard") P.outSJyes = true;
     else return bad("EXITING because of FATAL input ERROR: unrecognized option in --outSJtype   " + P.outSJtype[0] + "\nSOLUTION: use one of the allowed options: --outSJtype   Standard   OR   None\n");
+    if (P.outFilterType == "BySJout" && !P.outSJyes)   // Parameters.cpp:1179-1183
+        return bad("EXITING because of FATAL input ERROR: --outFilterType BySJout requires --outSJtype Standard\nSOLUTION: --outFilterType Normal    OR   --outFilterType BySJout --outSJtype Standard\n");
     if (P.outSJfilterReads != "All" && P.outSJfilterReads != "Unique")
         return bad("EXITING because of FATAL INPUT error: unknown value for the option --outSJfilterReads=" + P.outSJfilterReads + "\nSOLUTION: re-run STAR with --outSJfilterReads All -OR- Unique\n");
     for (auto* v : {&P.outSJfilterOverhangMin, &P.outSJfilterCountUniqueMin, &P.outSJfilterCountTotalMin, &P.outSJfilterDistToOtherSJmin}) {

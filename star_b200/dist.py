@@ -8,6 +8,8 @@ There is no collective on the data path of a pass.  Collectives
     (--gpuTwoPassPhase 1), the collapsed junction records of all shards are ALL-GATHERED (sizes, then padded payload), every rank
     derives the same global junction list from them (star_host_merge_pass1) and inserts it into its replica of the index
     (--gpuTwoPassPhase 2) before mapping its slice again.
+  * --outFilterType BySJout: the same kind of exchange between its two stages (--gpuBySJoutPhase 1 / 2): the junction records of all
+    reads of all shards are all-gathered, every rank derives the same list of surviving novel junctions and maps its held reads again.
 
   torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m star_b200.dist -- --genomeDir idx --readFilesIn r_1.fq r_2.fq --outFileNamePrefix out/
 """
@@ -50,6 +52,10 @@ def read_shard_counters(prefix, rank):
 
 def two_pass(argv):
     return "--twopassMode" in argv and argv[argv.index("--twopassMode") + 1] != "None"
+
+
+def by_sjout(argv):
+    return "--outFilterType" in argv and argv[argv.index("--outFilterType") + 1] == "BySJout"
 
 
 def all_gather_bytes(blob, world, device):
@@ -127,9 +133,22 @@ def run_sharded(argv, cli=None, backend=None):
         if not all_ok(rc):
             dist.destroy_process_group()
             return rc or 1
-        rc = run_cli(["--gpuTwoPassPhase", "2"])
+        phase = ["--gpuTwoPassPhase", "2"]
     else:
-        rc = run_cli([])
+        phase = []
+    if by_sjout(argv):   # two stages: the junctions of ALL reads of ALL shards decide which reads with novel junctions survive
+        rc = run_cli(phase + ["--gpuBySJoutPhase", "1"])
+        if not all_ok(rc):
+            dist.destroy_process_group()
+            return rc or 1
+        sp = _prefix(sargv)
+        gathered = all_gather_bytes(open(sp + "bysj_sjall.bin", "rb").read(), world, dev)
+        for r, blob in enumerate(gathered):
+            with open(sp + "bysj_gather%d.bin" % r, "wb") as f:
+                f.write(blob)
+        rc = run_cli(phase + ["--gpuBySJoutPhase", "2"])
+    else:
+        rc = run_cli(phase)
     if not all_ok(rc):
         dist.destroy_process_group()
         return rc or 1

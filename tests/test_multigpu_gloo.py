@@ -61,3 +61,24 @@ def test_two_rank_twopass_equals_reference(oracle, lib, golden, twopass_golden, 
         for line in open(os.path.join(ref, "_STARgenome/sha256.txt")):
             name, digest = line.split()
             assert hashlib.sha256(open(out + shard + "_STARgenome/" + name, "rb").read()).hexdigest() == digest, (shard, name)
+
+
+def test_two_rank_bysjout_twopass_equals_reference(oracle, lib, golden, twopass_golden, tmp_path):
+    """--outFilterType BySJout with --twopassMode Basic over 2 ranks: two exchanges (1st-pass junctions, then the junction records of
+    all reads between the BySJout stages, both all-gathered over gloo); merged outputs = the single-process reference run
+    (held reads of every shard after the 1st-stage records of all shards)."""
+    out = str(tmp_path) + "/"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29615",
+           "-m", "star_b200.dist", "--cli", oc.ORACLE_CLI, "--",
+           "--genomeDir", os.path.join(twopass_golden, "idx0"), "--readFilesIn", os.path.join(golden, "hard_1.fq"), os.path.join(golden, "hard_2.fq"),
+           "--outFileNamePrefix", out, "--runThreadN", "2", "--outFilterType", "BySJout", "--twopassMode", "Basic",
+           "--outSAMattributes", "NH", "HI", "AS", "nM", "XS", "--sjdbInsertSave", "All"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = os.path.join(twopass_golden, "S4_bysjout_twopass")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+    assert len(cf.sam_body(out + "shard0.Aligned.out.stage2.sam")) + len(cf.sam_body(out + "shard1.Aligned.out.stage2.sam")) > 0
