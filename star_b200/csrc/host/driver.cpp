@@ -147,6 +147,58 @@ static bool readShardJunctions(const std::string& path, std::vector<Junction>& s
     return in.good();
 }
 
+// bamSortByCoordinate.cpp / BAMbinSortByCoordinate.cpp:49-55 / BAMbinSortUnmapped.cpp: mapped records by (refID<<32|pos, read-order key,
+// emission order), then the unmapped ones (refID = -1 sorts last) in read order.  The reference bins by coordinate and sorts bin by
+// bin on disk; one stable in-memory sort gives the same sequence.
+static void writeSortedBam(const HostParams& P, const OutputWriter& W, const std::vector<std::string>& coordBlobs, std::vector<CoordRec>& coordIndex, int nT) {
+    std::stable_sort(coordIndex.begin(), coordIndex.end(), [](const CoordRec& a, const CoordRec& b) { return a.alignG != b.alignG ? a.alignG < b.alignG : a.key < b.key; });
+    std::ofstream cb(P.outFileNamePrefix + "Aligned.sortedByCoord.out.bam", std::ios::binary);
+    { std::string z; const std::string h = W.bamHeader(true); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); cb.write(z.data(), z.size()); }
+    const size_t nRec = coordIndex.size();
+    const size_t batch = 1u << 16;   // records per compression task
+    for (size_t base = 0; base < nRec; base += batch * (size_t)nT) {
+        std::vector<std::string> z(nT);
+        auto cw = [&](int t) {
+            const size_t lo = std::min(nRec, base + batch * (size_t)t), hi = std::min(nRec, lo + batch);
+            std::string raw;
+            for (size_t q = lo; q < hi; q++) raw.append(coordBlobs[coordIndex[q].blob], coordIndex[q].off, coordIndex[q].size);
+            OutputWriter::bgzfCompress(raw.data(), raw.size(), P.outBAMcompression, z[t]);
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < nT; t++) th.emplace_back(cw, t);
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nT; t++) cb.write(z[t].data(), z[t].size());
+    }
+    size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); cb.write(e, ne);
+}
+// sharded runs: records + keys of one shard (and stage) for the merge
+static void writeCoordShard(const std::string& path, const std::vector<std::string>& coordBlobs, const std::vector<CoordRec>& coordIndex) {
+    std::ofstream o(path, std::ios::binary);
+    uint64_t n = coordIndex.size();
+    o.write((const char*)&n, 8);
+    for (const CoordRec& r : coordIndex) { o.write((const char*)&r.alignG, 8); o.write((const char*)&r.key, 8); o.write((const char*)&r.size, 4); }
+    for (const CoordRec& r : coordIndex) o.write(coordBlobs[r.blob].data() + r.off, r.size);
+}
+static bool readCoordShard(const std::string& path, std::vector<std::string>& coordBlobs, std::vector<CoordRec>& coordIndex) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) return false;
+    uint64_t n = 0;
+    in.read((char*)&n, 8);
+    const uint32_t ib = (uint32_t)coordBlobs.size();
+    const size_t base = coordIndex.size();
+    coordIndex.resize(base + n);
+    uint64_t off = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        CoordRec& r = coordIndex[base + i];
+        in.read((char*)&r.alignG, 8); in.read((char*)&r.key, 8); in.read((char*)&r.size, 4);
+        r.blob = ib; r.off = off; off += r.size;
+    }
+    coordBlobs.emplace_back();
+    coordBlobs.back().resize(off);
+    if (off) in.read(&coordBlobs.back()[0], off);
+    return in.good();
+}
+
 static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engine_vtbl_t* eng, void* ectx, Stats& stats, std::vector<Junction>& allSJ,
                    std::ofstream& logMain, std::string& err, StageState& stage) {
     int rc = 0;
@@ -333,31 +385,12 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     if (!outErr.empty()) { err = outErr; return STAR_EXIT_BUG; }
     if (bamYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
     if (streamYes) samOut.close();
-    if (coordYes && lastStage) {
-        // bamSortByCoordinate.cpp / BAMbinSortByCoordinate.cpp:49-55 / BAMbinSortUnmapped.cpp: mapped records by (refID<<32|pos, read-order key,
-        // emission order), then the unmapped ones (refID = -1 sorts last) in read order.  The reference bins by coordinate and sorts bin by
-        // bin on disk; one stable in-memory sort gives the same sequence.
+    if (coordYes && P.gpuShardCount > 1) {   // one shard: the (unsorted) records and their keys go to the merge, which sorts the whole run
+        writeCoordShard(P.outFileNamePrefix + "coord" + stage.streamSuffix + ".bin", coordBlobs, coordIndex);
+    } else if (coordYes && lastStage) {
         time_t ts; time(&ts);
         std::cout << timeMonthDayTime(ts) << " ..... started sorting BAM\n" << std::flush;
-        std::stable_sort(coordIndex.begin(), coordIndex.end(), [](const CoordRec& a, const CoordRec& b) { return a.alignG != b.alignG ? a.alignG < b.alignG : a.key < b.key; });
-        std::ofstream cb(P.outFileNamePrefix + "Aligned.sortedByCoord.out.bam", std::ios::binary);
-        { std::string z; const std::string h = W.bamHeader(true); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); cb.write(z.data(), z.size()); }
-        const size_t nRec = coordIndex.size();
-        const size_t batch = 1u << 16;   // records per compression task
-        for (size_t base = 0; base < nRec; base += batch * (size_t)nT) {
-            std::vector<std::string> z(nT);
-            auto cw = [&](int t) {
-                const size_t lo = std::min(nRec, base + batch * (size_t)t), hi = std::min(nRec, lo + batch);
-                std::string raw;
-                for (size_t q = lo; q < hi; q++) raw.append(coordBlobs[coordIndex[q].blob], coordIndex[q].off, coordIndex[q].size);
-                OutputWriter::bgzfCompress(raw.data(), raw.size(), P.outBAMcompression, z[t]);
-            };
-            std::vector<std::thread> th;
-            for (int t = 0; t < nT; t++) th.emplace_back(cw, t);
-            for (auto& t : th) t.join();
-            for (int t = 0; t < nT; t++) cb.write(z[t].data(), z[t].size());
-        }
-        size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); cb.write(e, ne);
+        writeSortedBam(P, W, coordBlobs, coordIndex, nT);
     }
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
     logMain << "star-b200: host time: reads input " << msRead << " ms, SAM/SJ formatting " << msFormat << " ms, output writes " << msWrite << " ms\n";
@@ -558,7 +591,8 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     const std::string alnName = P.outBAMunsorted ? "Aligned.out.bam" : "Aligned.out.sam";
     std::ofstream samOut;
-    if (samYes) samOut.open(P.outFileNamePrefix + alnName, std::ios::binary);
+    const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);
+    if (streamYes) samOut.open(P.outFileNamePrefix + alnName, std::ios::binary);
     for (int r = 0; r < nShards; r++) {
         std::string sp = P.outFileNamePrefix + "shard" + std::to_string(r) + ".";
         std::ifstream sb(sp + "shard.bin", std::ios::binary);
@@ -572,19 +606,32 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
         size_t old = allSJ.size();
         allSJ.resize(old + nsj);
         if (nsj) sb.read((char*)(allSJ.data() + old), nsj * sizeof(Junction));
-        if (samYes) {
+        if (streamYes) {
             std::ifstream in(sp + alnName, std::ios::binary);
             samOut << in.rdbuf();
             samOut.clear();   // an empty shard sets failbit on operator<<
         }
     }
-    if (samYes && P.outFilterType == "BySJout")   // the reference writes the reads held by the 1st stage after all others
+    if (streamYes && P.outFilterType == "BySJout")   // the reference writes the reads held by the 1st stage after all others
         for (int r = 0; r < nShards; r++) {
             std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Aligned.out.stage2" + (P.outBAMunsorted ? ".bam" : ".sam"), std::ios::binary);
             samOut << in.rdbuf();
             samOut.clear();
         }
     if (samYes && P.outBAMunsorted) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }
+    if (samYes && P.outBAMcoord) {   // Aligned.sortedByCoord.out.bam of the whole run: the shards' records (both BySJout stages), one stable sort
+        std::vector<std::string> blobs;
+        std::vector<CoordRec> index;
+        for (int r = 0; r < nShards; r++)
+            for (const char* part : {"coord.bin", "coord.stage2.bin"}) {
+                const std::string fn = P.outFileNamePrefix + "shard" + std::to_string(r) + "." + part;
+                if (!readCoordShard(fn, blobs, index) && std::string(part) == "coord.bin" && !(P.outFilterType == "BySJout")) {
+                    std::cerr << "EXITING because of FATAL ERROR: missing shard output " << fn << "\n";
+                    return STAR_EXIT_RUNTIME;
+                }
+            }
+        writeSortedBam(P, W, blobs, index, std::max(1, P.runThreadN));
+    }
     if (counters) total.fromArray(counters);
     total.timeStart = (time_t)tStart; total.timeStartMap = (time_t)tStartMap; total.timeFinish = (time_t)tFinish;
     if (P.outSJyes) {

@@ -448,8 +448,6 @@ int finalizeParams(HostParams& P, std::string& err) {
     }
     if (P.gpuTwoPassPhase != 0 && !(P.twoPassYes && P.gpuShardCount > 1))
         return bad("EXITING because of fatal PARAMETERS error: --gpuTwoPassPhase is only meaningful for a sharded --twopassMode Basic run\n");
-    if (P.outBAMcoord && P.gpuShardCount > 1)
-        return bad("EXITING because of fatal input ERROR: --outSAMtype BAM SortedByCoordinate is not supported for sharded (multi-GPU) runs yet: use Unsorted and sort the merged file\n");
     if (P.gpuShardIndex >= P.gpuShardCount) return bad("EXITING because of fatal PARAMETERS error: --gpuShardIndex must be < --gpuShardCount\n");
     // geometry the sparse window map of the GPU engine relies on ("windows")
     if (2 * h.winFlankNbins > h.winAnchorDistNbins && P.userSet.count("winFlankNbins"))

@@ -118,6 +118,27 @@ def test_sharded_bam_merge(oracle, lib, golden, tmp_path):
     assert a[2] == b[2] and a[3] == b[3]
 
 
+def test_sharded_sorted_bam_merge(oracle, lib, golden, tmp_path):
+    """Coordinate-sorted BAM of a sharded run: every shard leaves its records + sort keys, the merge sorts the whole run; equal to the
+    single-process file record for record (Within: the unmapped records come last, in read order, across shards)."""
+    world = 3
+    pre = str(tmp_path) + "/m_"
+    args = ["--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "hard_1.fq"), os.path.join(golden, "hard_2.fq"),
+            "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate", "--outSAMunmapped", "Within", "--runThreadN", "2"]
+    for r in range(world):
+        subprocess.check_call([oc.ORACLE_CLI] + args + ["--outFileNamePrefix", pre + "shard%d." % r, "--gpuShardIndex", str(r), "--gpuShardCount", str(world)], stdout=subprocess.DEVNULL)
+    argv = ["STAR"] + args + ["--outFileNamePrefix", pre]
+    arr = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+    lib.star_host_merge_shards.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_void_p]
+    assert lib.star_host_merge_shards(len(argv), arr, world, None) == 0
+    whole = str(tmp_path) + "/w_"
+    subprocess.check_call([oc.ORACLE_CLI] + args + ["--outFileNamePrefix", whole], stdout=subprocess.DEVNULL)
+    for f in ("Aligned.out.bam", "Aligned.sortedByCoord.out.bam"):
+        a, b = parse_bam(pre + f), parse_bam(whole + f)
+        check_bgzf(a[0])
+        assert a[2] == b[2] and len(a[3]) == len(b[3]) and a[3] == b[3], f
+
+
 SORT_CASES = [
     ("std", []),
     ("hard", ["--outSAMunmapped", "Within"]),
