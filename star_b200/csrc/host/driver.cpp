@@ -89,6 +89,7 @@ static void holdRead(std::vector<ReadChunk>& held, const ReadChunk& c, uint32_t 
     }
     h.names.append(c.names, c.nameOff[i], c.nameOff[i + 1] - c.nameOff[i]);
     h.nameOff.push_back((uint32_t)h.names.size());
+    if (!c.nameFullOff.empty()) { h.nameFullOff.push_back((uint32_t)h.namesFull.size()); h.namesFull += c.namesFull.c_str() + c.nameFullOff[i]; h.namesFull.push_back('\0'); }
     h.readFilter.push_back(c.readFilter[i]);
     h.iReadAll.push_back(c.iReadAll[i]);
     h.nReads++;
@@ -112,7 +113,7 @@ static void saveStage1(const std::string& path, const Stats& stats, const std::v
     for (const ReadChunk& c : held) {
         uint32_t hd[4] = {c.nReads, c.nMates, (uint32_t)c.fastq, c.fileIndex};
         o.write((const char*)hd, sizeof(hd));
-        putStr(o, c.seq); putStr(o, c.qual); putVec(o, c.seqOff); putStr(o, c.names); putVec(o, c.nameOff); putVec(o, c.readFilter); putVec(o, c.iReadAll);
+        putStr(o, c.seq); putStr(o, c.qual); putVec(o, c.seqOff); putStr(o, c.names); putVec(o, c.nameOff); putVec(o, c.readFilter); putVec(o, c.iReadAll); putStr(o, c.namesFull); putVec(o, c.nameFullOff);
     }
 }
 static bool loadStage1(const std::string& path, Stats& stats, std::vector<Junction>& allSJ, std::vector<ReadChunk>& held) {
@@ -130,7 +131,7 @@ static bool loadStage1(const std::string& path, Stats& stats, std::vector<Juncti
         uint32_t hd[4];
         in.read((char*)hd, sizeof(hd));
         c.nReads = hd[0]; c.nMates = hd[1]; c.fastq = hd[2] != 0; c.fileIndex = hd[3];
-        getStr(in, c.seq); getStr(in, c.qual); getVec(in, c.seqOff); getStr(in, c.names); getVec(in, c.nameOff); getVec(in, c.readFilter); getVec(in, c.iReadAll);
+        getStr(in, c.seq); getStr(in, c.qual); getVec(in, c.seqOff); getStr(in, c.names); getVec(in, c.nameOff); getVec(in, c.readFilter); getVec(in, c.iReadAll); getStr(in, c.namesFull); getVec(in, c.nameFullOff);
     }
     return in.good();
 }
@@ -216,6 +217,10 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);   // Aligned.out.sam / Aligned.out.bam
     const bool bamYes = samYes && P.outBAMunsorted;
     const bool coordYes = samYes && P.outBAMcoord;                                        // Aligned.sortedByCoord.out.bam, sorted at the end
+    const bool unmYes = P.outReadsUnmapped == "Fastx";   // Unmapped.out.mate1/2 (Parameters.cpp:838-844); both stages of BySJout append
+    std::ofstream unmOut[2];
+    if (unmYes) for (unsigned m = 0; m < P.readNmates; m++)
+        unmOut[m].open(P.outFileNamePrefix + "Unmapped.out" + stage.streamSuffix + ".mate" + std::to_string(m + 1), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
     if (streamYes) {
         samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
         if (P.gpuShardIndex == 0 && firstStage) {   // shards > 0 write records only; the merge concatenates in shard order
@@ -286,11 +291,12 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 std::vector<std::string> cblob(coordYes ? nT : 0);
                 std::vector<std::vector<uint64_t>> ckey(coordYes ? nT : 0);
                 std::vector<OutputWriter::BySJoutHold> hold(stage.bySJstage == 1 ? nT : 0);
+                std::vector<std::string> unm(unmYes ? 2 * nT : 0);   // [2*t + mate]
                 auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
                     uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
                     sam[t].reserve((size_t)(hi - lo) * 700);
                     W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr,
-                                  stage.bySJstage == 1 ? &hold[t] : nullptr);
+                                  stage.bySJstage == 1 ? &hold[t] : nullptr, unmYes ? &unm[2 * t] : nullptr);
                     if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
                         std::string z;
                         z.reserve(sam[t].size() / 3);
@@ -311,6 +317,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     if (streamYes) samOut.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
+                    if (unmYes) for (unsigned m = 0; m < P.readNmates; m++) unmOut[m].write(unm[2 * t + m].data(), unm[2 * t + m].size());
                     if (stage.bySJstage == 1) {
                         stage.sjAll.insert(stage.sjAll.end(), hold[t].sjAll.begin(), hold[t].sjAll.end());
                         for (uint32_t i : hold[t].held) holdRead(stage.held, chunk, i, P.gpuChunkReads);
@@ -619,6 +626,15 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
             samOut.clear();
         }
     if (samYes && P.outBAMunsorted) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }
+    if (P.outReadsUnmapped == "Fastx")
+        for (unsigned m = 0; m < P.readNmates; m++) {
+            std::ofstream uo(P.outFileNamePrefix + "Unmapped.out.mate" + std::to_string(m + 1), std::ios::binary);
+            for (const char* part : {"", ".stage2"})
+                for (int r = 0; r < nShards; r++) {
+                    std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Unmapped.out" + part + ".mate" + std::to_string(m + 1), std::ios::binary);
+                    if (in.good()) { uo << in.rdbuf(); uo.clear(); }
+                }
+        }
     if (samYes && P.outBAMcoord) {   // Aligned.sortedByCoord.out.bam of the whole run: the shards' records (both BySJout stages), one stable sort
         std::vector<std::string> blobs;
         std::vector<CoordRec> index;

@@ -43,6 +43,7 @@ struct HostParams {
     std::vector<std::string> outSAMattributes = {"Standard"};
     std::vector<int> outSAMattrOrder;       // ATTR_* codes
     unsigned outSAMattrIHstart = 1;
+    std::string outReadsUnmapped = "None";  // Fastx: Unmapped.out.mate1/2 (ReadAlign::outReadsUnmapped)
     std::vector<std::string> outSAMunmapped = {"None"};
     bool unmappedWithin = false, unmappedKeepPairs = false;
     std::string outSAMorder = "Paired";
@@ -140,12 +141,15 @@ struct ReadChunk {
     std::vector<uint64_t> seqOff;            // nReads*nMates+1 (same offsets index qual)
     std::string names;                       // read names (without '@', cut at the separator), '\0'-separated
     std::vector<uint32_t> nameOff;           // nReads+1
+    std::string namesFull;                   // only with --outReadsUnmapped Fastx: the read IDs as in the file ('@'/'>' included, not cut), '\0'-separated
+    std::vector<uint32_t> nameFullOff;       // nReads: start of read i's ID in namesFull
     std::vector<char> readFilter;            // 'Y'/'N'
     std::vector<uint64_t> iReadAll;
     bool fastq = true;
     uint32_t fileIndex = 0;                  // input file (of a comma-separated list) this chunk came from: a chunk never spans files
     void clear() {
         nReads = 0; seq.clear(); qual.clear(); seqOff.clear(); names.clear(); nameOff.clear(); readFilter.clear(); iReadAll.clear();
+        namesFull.clear(); nameFullOff.clear();
     }
 };
 
@@ -216,9 +220,10 @@ class OutputWriter {
     // by (1st stage of --outFilterType BySJout): reads with an unannotated junction are neither counted nor written but listed in
     // by->held; the junction records of ALL mapped reads are appended to by->sjAll
     struct BySJoutHold { std::vector<uint32_t> held; std::vector<Junction> sjAll; };
+    // unm (--outReadsUnmapped Fastx): text for Unmapped.out.mate1 / mate2
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
                      std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr,
-                     BySJoutHold* by = nullptr) const;
+                     BySJoutHold* by = nullptr, std::string* unm = nullptr) const;
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
     std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`

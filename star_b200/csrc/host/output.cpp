@@ -631,7 +631,7 @@ const char* OutputWriter::bgzfEofBlock(size_t& n) {
 
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by) const {
+                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by, std::string* unm) const {
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     const bool coordYes = samYes && P.outBAMcoord && coord && coordKey;
     // records appended to `dst` since `from` also go to the coordinate-sorted set with read-order key `key` (one key per record)
@@ -664,6 +664,7 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
         st.readN++;
         st.readBases += L0 + L1;
         int unmapType = r.unmapType;
+        bool mateMappedOut[2] = {false, false};
         switch (unmapType) { case 0: st.unmappedOther++; break; case 1: st.unmappedShort++; break; case 2: st.unmappedMismatch++; break; case 3: st.unmappedMulti++; break; default: break; }
         const star_align_t* trs = out.aligns + r.trOffset;
         if (unmapType < 0) {
@@ -711,6 +712,7 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
             mateMapped[best.exFrag[0]] = true;
             mateMapped[best.exFrag[best.nExons - 1]] = true;
             if (c.nMates > 1 && !(mateMapped[0] && mateMapped[1])) unmapType = 4;
+            mateMappedOut[0] = mateMapped[0]; mateMappedOut[1] = mateMapped[1];
             if (unmapType == 4 && P.unmappedWithin && samYes) {   // :214-232 (KeepPairs does not affect the sorted BAM)
                 if (P.outSAMtype[0] == "SAM") { if (!P.unmappedKeepPairs) samUnmapped(c, i, r, &best, 4, mateMapped, sam); }
                 else {
@@ -730,7 +732,21 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                 if (coordYes) toCoord(scratch, 0, c.iReadAll[i] << 32);
             }
         }
-        if (unmapType >= 0) st.unmappedAll++;
+        if (unmapType >= 0) {
+            st.unmappedAll++;
+            if (unm) {   // ReadAlign::outReadsUnmapped (ReadAlign_outputAlignments.cpp:259-274): unmapped reads and pairs with one mapped mate
+                for (uint32_t m = 0; m < c.nMates; m++) {
+                    std::string& u = unm[m];
+                    u += c.namesFull.c_str() + c.nameFullOff[i];
+                    u.push_back(' '); u.push_back((char)('0' + m)); u.push_back(':'); u.push_back(c.readFilter[i]); u += ": ";
+                    if (c.nMates > 1) { u.push_back(' '); u.push_back(mateMappedOut[0] ? '1' : '0'); u.push_back(mateMappedOut[1] ? '1' : '0'); }
+                    u.push_back('\n');
+                    const uint64_t a = c.seqOff[(uint64_t)i * c.nMates + m], b = c.seqOff[(uint64_t)i * c.nMates + m + 1];
+                    u.append(c.seq, a, b - a); u.push_back('\n');
+                    if (c.fastq) { u += "+\n"; u.append(c.qual, a, b - a); u.push_back('\n'); }
+                }
+            }
+        }
     }
 }
 

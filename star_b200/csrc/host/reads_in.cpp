@@ -247,6 +247,7 @@ int ReadsReader::parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls
     }
     c.names.push_back('\0');
     c.nameOff.push_back((uint32_t)c.names.size());
+    if (P->outReadsUnmapped == "Fastx") { c.nameFullOff.push_back((uint32_t)c.namesFull.size()); c.namesFull += readID; c.namesFull.push_back('\0'); }
     c.readFilter.push_back(passFilter);
     c.iReadAll.push_back(iRead);
     c.nReads++;
@@ -334,6 +335,9 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
         ReadChunk& pc = part[t];
         const uint64_t sb = c.seq.size();
         const uint32_t nb = (uint32_t)c.names.size();
+        const uint32_t nbFull = (uint32_t)c.namesFull.size();
+        c.namesFull += pc.namesFull;
+        for (uint32_t o : pc.nameFullOff) c.nameFullOff.push_back(nbFull + o);
         c.seq += pc.seq; c.qual += pc.qual; c.names += pc.names;
         for (size_t k = 1; k < pc.seqOff.size(); k++) c.seqOff.push_back(sb + pc.seqOff[k]);
         for (size_t k = 1; k < pc.nameOff.size(); k++) c.nameOff.push_back(nb + pc.nameOff[k]);
@@ -446,6 +450,7 @@ long long ReadsReader::nextStream(ReadChunk& c, uint32_t maxReads, std::string& 
         c.names += name;
         c.names.push_back('\0');
         c.nameOff.push_back((uint32_t)c.names.size());
+        if (P->outReadsUnmapped == "Fastx") { c.nameFullOff.push_back((uint32_t)c.namesFull.size()); c.namesFull += readID; c.namesFull.push_back('\0'); }
         c.readFilter.push_back(passFilter);
         c.iReadAll.push_back(iReadAll);
         c.nReads++;

@@ -44,12 +44,14 @@ SCENARIOS = {
                          "--outFilterMultimapNmax", "20", "--outFilterMismatchNmax", "999", "--outFilterMismatchNoverReadLmax", "0.04", "--alignIntronMin", "20",
                          "--alignIntronMax", "1000000", "--alignMatesGapMax", "1000000", "--alignSJoverhangMin", "8", "--alignSJDBoverhangMin", "1", "--sjdbScore", "1",
                          "--outSAMunmapped", "Within", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
+    "U_unmapped_fastx_bysjout": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outReadsUnmapped", "Fastx", "--outFilterType", "BySJout",
+                                 "--outSAMunmapped", "Within"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
 }
 KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
-        "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab"]
+        "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "Unmapped.out.mate1", "Unmapped.out.mate2"]
 
 
 def sha(path):
