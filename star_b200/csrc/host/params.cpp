@@ -399,6 +399,9 @@ int finalizeParams(HostParams& P, std::string& err) {
             P.outSAMattrOrder.push_back(it->second);
             if (s == "XS") h.outSAMstrandFieldType = 1;   // Parameters_samAttributes.cpp:172-179: XS implies --outSAMstrandField intronMotif
         }
+        for (int c : P.outSAMattrOrder)   // Parameters_samAttributes.cpp:226, 252-260
+            if (c == 14 && !P.outBAMunsorted && !P.outBAMcoord)
+                return bad("EXITING because of fatal PARAMETER error: --outSAMattributes contains ch tag, which requires BAM output.\nSOLUTION: re-run STAR with --outSAMtype BAM Unsorted (and/or) SortedByCoordinate option, or without ch tag in --outSAMattributes\n");
         if (h.outSAMstrandFieldType == 1) {  // Parameters_samAttributes.cpp: XS added for intronMotif
             bool has = false;
             for (int c : P.outSAMattrOrder) if (c == 9) has = true;
