@@ -24,6 +24,9 @@ PY
 cat gpurun_out/r02_seedwarp_parity.log | tail -12
 run() { tag=$1; shift; env "$@" timeout 600 python tools/analyze_chunk.py 1048576 > gpurun_out/r02_$tag.log 2>&1; echo "$tag $(grep -E '^run 2' gpurun_out/r02_$tag.log | sed -E 's/.*ms_seed.: ([0-9.]+).*ms_stitch.: ([0-9.]+).*ms_total.: ([0-9.]+).*ms_heavy.: ([0-9.]+).*/seed \1 stitch \2 total \3 ms_heavy \4/') | $(grep 'heavy kernel warp' gpurun_out/r02_$tag.log | tail -1 | cut -c1-110)"; }
 run base A=1
+# A/B of the last kernel change of round 1 (single-writer discipline of the flat kernels, never timed): star_b200/lib_ab/ holds the library
+# built from the commit before it (same ABI for this tool); built by `git worktree add build/wt 83ba07a^ && make` in the build container
+if [ -e star_b200/lib_ab/libstar_b200_pre_single_writer.so ]; then run pre_single_writer STAR_B200_LIB=$PWD/star_b200/lib_ab/libstar_b200_pre_single_writer.so; fi
 for c in 6 8 12; do run seedwarp$c STAR_B200_SEED_WARP=$c; done
 for s in 16 20 30 52; do run split$s STAR_B200_HEAVY_SPLIT=$s; done
 # 4. the round-1 kernels that were written after the GPU budget was spent and have only run under the host emulation:
