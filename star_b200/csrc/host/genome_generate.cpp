@@ -4,7 +4,6 @@
 // chr*.txt (writeChrInfo, :417-432), SAindex (genomeSAindex.cpp:6-220), genomeParameters.txt (genomeParametersWrite.cpp:4-46) and the
 // junction insertion shared with the mapping stage (sjdb_insert.cpp).  The suffix sort — hours of qsort over 16-mer buckets in the
 // reference (:213-330) — is the device step behind star_gpu_sa_build (star_b200/csrc/engine/sa_build.cu).
-// Not written: exonInfo.tab / transcriptInfo.tab / geneInfo.tab / exonGeTrInfo.tab (they serve --quantMode, which is out of scope).
 #include <sys/stat.h>
 
 #include <cmath>

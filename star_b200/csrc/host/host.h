@@ -79,6 +79,7 @@ struct HostParams {
     std::vector<std::string> sjdbFileChrStartEnd = {"-"};
     std::string sjdbGTFfile = "-", sjdbGTFchrPrefix = "-", sjdbGTFfeatureExon = "exon", sjdbGTFtagExonParentTranscript = "transcript_id",
                 sjdbGTFtagExonParentGene = "gene_id";
+    std::vector<std::string> sjdbGTFtagExonParentGeneName = {"gene_name"}, sjdbGTFtagExonParentGeneType = {"gene_type", "gene_biotype"};
     uint64_t sjdbOverhang = 100;
     std::string sjdbInsertSave = "Basic";
     uint64_t limitSjdbInsertNsj = 1000000;

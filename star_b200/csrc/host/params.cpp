@@ -88,7 +88,7 @@ const char* kUnsupported[] = {
     "parametersFiles", "genomeChainFiles", "genomeFileSizes",
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
-    "sjdbGTFtagExonParentGeneName", "sjdbGTFtagExonParentGeneType", "varVCFfile", "readFilesType",
+    "varVCFfile", "readFilesType",
     "readFilesSAMattrKeep", "readFilesManifest", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
     
@@ -160,6 +160,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     I32("scoreStitchSJshift", &h.scoreStitchSJshift); I32("sjdbScore", &h.sjdbScore);
     STR("sjdbGTFfile", &P.sjdbGTFfile); STR("sjdbGTFchrPrefix", &P.sjdbGTFchrPrefix); STR("sjdbGTFfeatureExon", &P.sjdbGTFfeatureExon);
     STR("sjdbGTFtagExonParentTranscript", &P.sjdbGTFtagExonParentTranscript); STR("sjdbGTFtagExonParentGene", &P.sjdbGTFtagExonParentGene);
+    VSTR("sjdbGTFtagExonParentGeneName", &P.sjdbGTFtagExonParentGeneName); VSTR("sjdbGTFtagExonParentGeneType", &P.sjdbGTFtagExonParentGeneType);
     VSTR("genomeFastaFiles", &P.genomeFastaFiles); U64("genomeSAindexNbases", &P.genomeSAindexNbases); U64("genomeChrBinNbits", &P.genomeChrBinNbits);
     U64("genomeSAsparseD", &P.genomeSAsparseD); U64("limitGenomeGenerateRAM", &P.limitGenomeGenerateRAM);
     VSTR("sjdbFileChrStartEnd", &P.sjdbFileChrStartEnd); U64("sjdbOverhang", &P.sjdbOverhang); STR("sjdbInsertSave", &P.sjdbInsertSave);

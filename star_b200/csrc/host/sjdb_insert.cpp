@@ -8,6 +8,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -203,8 +204,8 @@ bool copyFile(const std::string& a, const std::string& b) {
 }  // namespace
 
 // The junction part of GTF::GTF + GTF::transcriptGeneSJ (GTF.cpp:7-200, GTF_transcriptGeneSJ.cpp:23-183): exon lines -> exons per
-// transcript -> introns between consecutive exons, collapsed by (start, end, strand); writes sjdbList.fromGTF.out.tab.  The transcript /
-// exon / gene tables of the reference (exonInfo.tab, transcriptInfo.tab, geneInfo.tab, exonGeTrInfo.tab) serve --quantMode and are not written.
+// transcript -> introns between consecutive exons, collapsed by (start, end, strand); writes sjdbList.fromGTF.out.tab and the transcript /
+// exon / gene tables of the reference (exonInfo.tab, transcriptInfo.tab, geneInfo.tab, exonGeTrInfo.tab; they serve --quantMode).
 static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const std::string& outDir, SjdbLoci& loci, std::ostream& logMain, std::string& err) {
     std::ifstream in(P.sjdbGTFfile);
     if (in.fail()) { err = "FATAL error, could not open file pGe.sjdbGTFfile=" + P.sjdbGTFfile + "\n"; return STAR_EXIT_INPUT_FILES; }
@@ -212,6 +213,8 @@ static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const st
     for (uint32_t i = 0; i < idx.view.nChrReal; i++) chrIndex[idx.chrName[i]] = i;
     std::map<std::string, uint64_t> trNumber, geNumber;
     std::vector<uint8_t> trStrand;
+    std::vector<std::string> transcriptID, geneID;
+    std::vector<std::array<std::string, 2>> geneAttr;
     struct Ex { uint64_t t, s, e, g; };
     std::vector<Ex> ex;
     uint64_t nExonLines = 0;
@@ -246,7 +249,9 @@ static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const st
             if (pos != std::string::npos) v = attrs.substr(pos, attrs.find_first_of(" ", pos) - pos);
             return v;
         };
-        std::string trID = attr(P.sjdbGTFtagExonParentTranscript), gID = attr(P.sjdbGTFtagExonParentGene);
+        std::string trID = attr(P.sjdbGTFtagExonParentTranscript), gID = attr(P.sjdbGTFtagExonParentGene), gName, gType;
+        for (const std::string& nm : P.sjdbGTFtagExonParentGeneName) { std::string v = attr(nm); if (!v.empty()) gName = v; }
+        for (const std::string& nm : P.sjdbGTFtagExonParentGeneType) { std::string v = attr(nm); if (!v.empty()) gType = v; }
         if (trID.empty()) {
             logMain << "WARNING: while processing pGe.sjdbGTFfile=" << P.sjdbGTFfile << ": no transcript_id for line:\n" << line << "\n";
             trID = "tr_" + chr1 + "_" + std::to_string(ex1) + "_" + std::to_string(ex2) + "_" + std::to_string(ex.size());
@@ -255,9 +260,12 @@ static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const st
             logMain << "WARNING: while processing pGe.sjdbGTFfile=" << P.sjdbGTFfile << ": no gene_id for line:\n" << line << "\n";
             gID = "MissingGeneID";
         }
+        if (gName.empty()) gName = gID;
+        if (gType.empty()) gType = "MissingGeneType";
         auto ti = trNumber.insert({trID, trNumber.size()});
-        if (ti.second) trStrand.push_back(str1 == '+' ? 1 : (str1 == '-' ? 2 : 0));
+        if (ti.second) { trStrand.push_back(str1 == '+' ? 1 : (str1 == '-' ? 2 : 0)); transcriptID.push_back(trID); }
         auto gi = geNumber.insert({gID, geNumber.size()});
+        if (gi.second) { geneID.push_back(gID); geneAttr.push_back({gName, gType}); }
         ex.push_back(Ex{ti.first->second, ex1 + idx.chrStart[ci->second] - 1, ex2 + idx.chrStart[ci->second] - 1, gi.first->second});
     }
     if (nExonLines == 0) {
@@ -269,6 +277,49 @@ static int sjdbLoadFromGTF(const HostParams& P, const LoadedIndex& idx, const st
         return STAR_EXIT_INPUT_FILES;
     }
     std::stable_sort(ex.begin(), ex.end(), [](const Ex& a, const Ex& b) { return a.t != b.t ? a.t < b.t : a.s < b.s; });   // funCompareUint2 on (transcript, start)
+    {   // the annotation tables next to the index (GTF_transcriptGeneSJ.cpp:32-114): exons by locus, genes, transcripts with their exons
+        const uint64_t exonN = ex.size();
+        std::vector<std::array<uint64_t, 5>> exge(exonN);
+        for (uint64_t i = 0; i < exonN; i++) exge[i] = {ex[i].s, ex[i].e, (uint64_t)trStrand[ex[i].t], ex[i].g, ex[i].t};
+        std::sort(exge.begin(), exge.end());
+        std::ofstream exgeOut(outDir + "/exonGeTrInfo.tab");
+        exgeOut << exonN << "\n";
+        for (auto& r : exge) exgeOut << r[0] << "\t" << r[1] << "\t" << r[2] << "\t" << r[3] << "\t" << r[4] << "\n";
+        std::ofstream geOut(outDir + "/geneInfo.tab");
+        geOut << geneID.size() << "\n";
+        for (size_t ig = 0; ig < geneID.size(); ig++) geOut << geneID[ig] << "\t" << geneAttr[ig][0] << "\t" << geneAttr[ig][1] << "\n";
+        // rows (transcript start, transcript end, transcript, exon start, exon end, gene) sorted by the first five
+        std::vector<std::array<uint64_t, 6>> extr(exonN);
+        uint64_t trex1 = 0;
+        for (uint64_t iex = 0; iex <= exonN; iex++) {
+            if (iex == exonN || ex[iex].t != ex[trex1].t) {
+                for (uint64_t k = trex1; k < iex; k++) extr[k][1] = ex[iex - 1].e;   // (the end of the transcript's LAST exon by start)
+                if (iex == exonN) break;
+                trex1 = iex;
+            }
+            extr[iex][0] = ex[trex1].s; extr[iex][2] = ex[iex].t; extr[iex][3] = ex[iex].s; extr[iex][4] = ex[iex].e; extr[iex][5] = ex[iex].g;
+        }
+        std::stable_sort(extr.begin(), extr.end(), [](const std::array<uint64_t, 6>& a, const std::array<uint64_t, 6>& b) {
+            for (int k = 0; k < 5; k++) if (a[k] != b[k]) return a[k] < b[k];
+            return false;
+        });
+        std::ofstream trOut(outDir + "/transcriptInfo.tab"), exOut(outDir + "/exonInfo.tab");
+        trOut << transcriptID.size() << "\n";
+        exOut << exonN << "\n";
+        uint64_t trid = extr[0][2], trex = 0, trstart = extr[0][0], trend = extr[0][1], exlen = 0;
+        for (uint64_t iex = 0; iex <= exonN; iex++) {
+            if (iex == exonN || extr[iex][2] != trid) {
+                trOut << transcriptID.at(trid) << "\t" << extr[iex - 1][0] << "\t" << extr[iex - 1][1] << "\t" << trend << "\t" << (uint64_t)trStrand[trid] << "\t" << iex - trex << "\t"
+                      << trex << "\t" << extr[iex - 1][5] << "\n";
+                if (iex == exonN) break;
+                trid = extr[iex][2]; trstart = extr[iex][0]; trex = iex;
+                trend = std::max(trend, extr[iex - 1][1]);
+                exlen = 0;
+            }
+            exOut << extr[iex][3] - trstart << "\t" << extr[iex][4] - trstart << "\t" << exlen << "\n";
+            exlen += extr[iex][4] - extr[iex][3] + 1;
+        }
+    }
     struct Sj { uint64_t s, e, str, g; };
     std::vector<Sj> sj;
     uint64_t trCur = ex[0].t;

@@ -51,7 +51,8 @@ SCENARIOS = {
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
 }
 KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
-        "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "Unmapped.out.mate1", "Unmapped.out.mate2"]
+        "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "_STARgenome/exonInfo.tab", "_STARgenome/transcriptInfo.tab", "_STARgenome/geneInfo.tab",
+        "_STARgenome/exonGeTrInfo.tab", "Unmapped.out.mate1", "Unmapped.out.mate2"]
 
 
 def sha(path):

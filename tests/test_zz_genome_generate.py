@@ -43,7 +43,8 @@ def _check_torture(torture, out):
 
 
 def _check_tiny(golden, out):
-    for name in ("Genome", "SA", "SAindex", "chrName.txt", "chrStart.txt", "chrLength.txt", "chrNameLength.txt", "sjdbInfo.txt", "sjdbList.out.tab", "sjdbList.fromGTF.out.tab"):
+    for name in ("Genome", "SA", "SAindex", "chrName.txt", "chrStart.txt", "chrLength.txt", "chrNameLength.txt", "sjdbInfo.txt", "sjdbList.out.tab", "sjdbList.fromGTF.out.tab",
+                 "exonInfo.tab", "transcriptInfo.tab", "geneInfo.tab", "exonGeTrInfo.tab"):
         assert open(os.path.join(out, name), "rb").read() == open(os.path.join(golden, "idx", name), "rb").read(), name
     ours = open(os.path.join(out, "genomeParameters.txt")).read().split("\n", 1)[1]
     assert ours == open(os.path.join(golden, "idx", "genomeParameters.txt")).read().split("\n", 1)[1]
