@@ -68,6 +68,8 @@ struct StageState {
     int bySJstage = 0;                       // 0: single stage; 1: hold reads with unannotated junctions; 2: map the held reads
     std::vector<Junction> sjAll;             // stage 1: junction records of ALL mapped reads (chunkOutSJ1)
     std::vector<ReadChunk> held;             // stage 1 -> 2: the reads to map again, in input order, chunked (never across input files)
+    const GeneModel* geneModel = nullptr;    // --quantMode GeneCounts: exons / genes, and the counts of every stage
+    GeneCounts geneCounts;
     std::string streamSuffix;                // sharded 2nd stage: records go to Aligned.out<suffix>.sam|bam (the merge orders the parts)
     std::vector<std::string> coordBlobs;     // coordinate-sorted BAM: uncompressed records of every stage
     std::vector<CoordRec> coordIndex;
@@ -135,6 +137,23 @@ static bool loadStage1(const std::string& path, Stats& stats, std::vector<Juncti
     }
     return in.good();
 }
+// adds the counts of a ReadsPerGene table (4 summary rows, then one row per gene) to gc; N_unmapped is recomputed from the counters
+static bool readGeneCounts(const std::string& path, GeneCounts& gc) {
+    std::ifstream in(path);
+    if (!in.good()) return false;
+    std::string name;
+    uint64_t v[3];
+    size_t ig = 0;
+    for (int row = 0; in >> name >> v[0] >> v[1] >> v[2]; row++) {
+        if (row == 0) continue;
+        if (row == 1) gc.cMulti += v[0];
+        else if (row == 2) for (int t = 0; t < 3; t++) gc.cNone[t] += v[t];
+        else if (row == 3) for (int t = 0; t < 3; t++) gc.cAmbig[t] += v[t];
+        else { for (int t = 0; t < 3; t++) { if (gc.gCount[t].size() <= ig) gc.gCount[t].resize(ig + 1, 0); gc.gCount[t][ig] += v[t]; } ig++; }
+    }
+    return true;
+}
+
 // junction records of shard.bin-style files (24 counters, 3 times, count, records)
 static bool readShardJunctions(const std::string& path, std::vector<Junction>& sj) {
     std::ifstream in(path, std::ios::binary);
@@ -212,6 +231,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     size_t heldNext = 0;   // 2nd stage: the held chunks are the input
 
     OutputWriter W(P, idx);
+    W.geneModel = stage.geneModel;
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     std::ofstream samOut;
     const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);   // Aligned.out.sam / Aligned.out.bam
@@ -292,11 +312,14 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 std::vector<std::vector<uint64_t>> ckey(coordYes ? nT : 0);
                 std::vector<OutputWriter::BySJoutHold> hold(stage.bySJstage == 1 ? nT : 0);
                 std::vector<std::string> unm(unmYes ? 2 * nT : 0);   // [2*t + mate]
+                std::vector<GeneCounts> gcs(stage.geneModel ? nT : 0);
+                for (auto& gcT : gcs) gcT.init(stage.geneModel->geID.size());
                 auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
                     uint32_t lo = (uint64_t)chunk.nReads * t / nT, hi = (uint64_t)chunk.nReads * (t + 1) / nT;
                     sam[t].reserve((size_t)(hi - lo) * 700);
                     W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr,
-                                  stage.bySJstage == 1 ? &hold[t] : nullptr, unmYes ? &unm[2 * t] : nullptr);
+                                  stage.bySJstage == 1 ? &hold[t] : nullptr, unmYes ? &unm[2 * t] : nullptr,
+                                  stage.geneModel ? &gcs[t] : nullptr);
                     if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
                         std::string z;
                         z.reserve(sam[t].size() / 3);
@@ -317,6 +340,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     if (streamYes) samOut.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
+                    if (stage.geneModel) stage.geneCounts.add(gcs[t]);
                     if (unmYes) for (unsigned m = 0; m < P.readNmates; m++) unmOut[m].write(unm[2 * t + m].data(), unm[2 * t + m].size());
                     if (stage.bySJstage == 1) {
                         stage.sjAll.insert(stage.sjAll.end(), hold[t].sjAll.begin(), hold[t].sjAll.end());
@@ -515,6 +539,13 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     std::vector<Junction> allSJ;
     StageState stage;
     OutputWriter W(P, idx);
+    GeneModel geneModel;
+    if (P.quantGeneCounts) {   // the tables of the index, or of the GTF given at the mapping stage (Transcriptome.cpp:13)
+        rc = geneModel.load(P.sjdbGTFfile == "-" ? P.genomeDir : P.sjdbInsertOutDir, err);
+        if (rc) { eng->destroy(ectx); return exitWithError(err, rc, &logMain); }
+        stage.geneModel = &geneModel;
+        stage.geneCounts.init(geneModel.geID.size());
+    }
     const bool bySJout = P.outFilterType == "BySJout";
     stage.bySJstage = bySJout ? 1 : 0;
     const std::string stateFile = P.outFileNamePrefix + "bysj_stage1.bin";
@@ -527,6 +558,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
         time(&stats.timeFinish);
         saveStage1(stateFile, stats, allSJ, stage.held);
+        if (stage.geneModel) stage.geneCounts.write(geneModel, stats, P.outFileNamePrefix + "bysj_stage1.ReadsPerGene.tab");
         writeShardBin(P.outFileNamePrefix + "bysj_sjall.bin", stats, stage.sjAll);
         std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished 1st BySJout stage of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
         return 0;
@@ -540,6 +572,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
                 rc = STAR_EXIT_RUNTIME; err = "EXITING because of FATAL ERROR: missing gathered junctions " + P.outFileNamePrefix + "bysj_gather" + std::to_string(r) + ".bin\n";
             }
         stage.streamSuffix = ".stage2";
+        if (stage.geneModel && !rc) readGeneCounts(P.outFileNamePrefix + "bysj_stage1.ReadsPerGene.tab", stage.geneCounts);
     }
     if (!rc && bySJout) {   // STAR.cpp:203-220: the novel junctions that pass the filters over ALL reads, then the held reads once more
         logMain << "Completed stage 1 mapping of outFilterBySJout mapping\n" << std::flush;
@@ -560,6 +593,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
     }
     time(&stats.timeFinish);
+    if (stage.geneModel) stage.geneCounts.write(geneModel, stats, P.outFileNamePrefix + "ReadsPerGene.out.tab");   // STAR.cpp:258-265 (a shard: its part)
     if (P.gpuShardCount > 1) {
         // one shard of a multi-GPU run: leave the counters and the (collapsed) junction records for the merge
         // (the neighbour-distance filter of outputSJ needs the GLOBAL sorted junction list)
@@ -655,6 +689,16 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
         if (!e2.empty()) { std::cerr << e2 << std::endl; return STAR_EXIT_BUG; }
     }
     W.writeLogFinal(total, P.outFileNamePrefix + "Log.final.out");
+    if (P.quantGeneCounts) {   // ReadsPerGene.out.tab of the run = the sum of the shards' tables
+        GeneModel gm;
+        rc = gm.load(P.sjdbGTFfile == "-" ? P.genomeDir : P.outFileNamePrefix + "shard0._STARgenome/", err);
+        if (rc) { std::cerr << err << std::endl; return rc; }
+        GeneCounts gc;
+        gc.init(gm.geID.size());
+        for (int r = 0; r < nShards; r++)
+            if (!readGeneCounts(P.outFileNamePrefix + "shard" + std::to_string(r) + ".ReadsPerGene.out.tab", gc)) { std::cerr << "EXITING because of FATAL ERROR: missing gene counts of shard " << r << "\n"; return STAR_EXIT_RUNTIME; }
+        gc.write(gm, total, P.outFileNamePrefix + "ReadsPerGene.out.tab");
+    }
     return 0;
 }
 

@@ -43,6 +43,8 @@ struct HostParams {
     std::vector<std::string> outSAMattributes = {"Standard"};
     std::vector<int> outSAMattrOrder;       // ATTR_* codes
     unsigned outSAMattrIHstart = 1;
+    std::vector<std::string> quantMode = {"-"};   // GeneCounts only (ReadsPerGene.out.tab); TranscriptomeSAM is out of scope
+    bool quantGeneCounts = false;
     std::string outReadsUnmapped = "None";  // Fastx: Unmapped.out.mate1/2 (ReadAlign::outReadsUnmapped)
     std::vector<std::string> outSAMunmapped = {"None"};
     bool unmappedWithin = false, unmappedKeepPairs = false;
@@ -211,6 +213,24 @@ struct Junction {
     uint16_t overhangLeft, overhangRight;
 };
 
+// --quantMode GeneCounts: exons by locus with their genes (exonGeTrInfo.tab, geneInfo.tab; Transcriptome.cpp:18-98) and the counters of
+// Quantifications.h (3 strandedness types: unstranded, read strand = gene strand, reverse)
+struct GeneModel {
+    std::vector<uint64_t> s, e, eMax;
+    std::vector<uint8_t> str;
+    std::vector<uint32_t> g;
+    std::vector<std::string> geID;
+    int load(const std::string& dir, std::string& err);
+};
+struct GeneCounts {
+    uint64_t cMulti = 0, cNone[3] = {0, 0, 0}, cAmbig[3] = {0, 0, 0};
+    std::vector<uint64_t> gCount[3];
+    void init(size_t nGe) { for (auto& v : gCount) v.assign(nGe, 0); }
+    void add(const GeneCounts& o);
+    void addAlign(const GeneModel& gm, uint64_t nTr, const star_align_t* trs);   // Transcriptome::geneCountsAddAlign
+    void write(const GeneModel& gm, const Stats& st, const std::string& path) const;   // Transcriptome::quantsOutput
+};
+
 // Formats everything the reference writes per read: SAM records, junction records, counters.
 class OutputWriter {
    public:
@@ -224,7 +244,8 @@ class OutputWriter {
     // unm (--outReadsUnmapped Fastx): text for Unmapped.out.mate1 / mate2
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
                      std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr,
-                     BySJoutHold* by = nullptr, std::string* unm = nullptr) const;
+                     BySJoutHold* by = nullptr, std::string* unm = nullptr, GeneCounts* gc = nullptr) const;
+    const GeneModel* geneModel = nullptr;   // set for --quantMode GeneCounts
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
     std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`

@@ -631,7 +631,7 @@ const char* OutputWriter::bgzfEofBlock(size_t& n) {
 
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by, std::string* unm) const {
+                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by, std::string* unm, GeneCounts* gc) const {
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     const bool coordYes = samYes && P.outBAMcoord && coord && coordKey;
     // records appended to `dst` since `from` also go to the coordinate-sorted set with read-order key `key` (one key per record)
@@ -685,6 +685,7 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                     st.mappedBases += mappedL;
                 }
             }
+            if (gc && geneModel) gc->addAlign(*geneModel, nTr, trs);   // ReadAlign::alignedAnnotation :296-308
             if (P.outSJyes && (P.outSJfilterReads == "All" || nTr == 1)) {  // recordSJ :76-87
                 size_t sjReadStartN = sj.size();
                 for (uint64_t k = 0; k < nTr; k++) recordSJ(trs[k], nTr, sj, sjReadStartN);
@@ -859,6 +860,87 @@ std::string OutputWriter::novelJunctions(std::vector<Junction>& all, std::vector
     for (size_t ii = 0; ii < kept.size(); ii++)
         if (sjFilter[ii] && kept[ii].annot == 0) { sjStart.push_back(kept[ii].start); sjEnd.push_back(kept[ii].start + (uint64_t)kept[ii].gap - 1); }
     return std::string();
+}
+
+// ---- --quantMode GeneCounts --------------------------------------------------------------------------------------------------------
+int GeneModel::load(const std::string& dir, std::string& err) {   // Transcriptome.cpp:18-31, 78-98
+    const char* sol = "SOLUTION: utilize --sjdbGTFfile /path/to/annotations.gtf option at the genome generation step or mapping step\n";
+    std::ifstream ge(dir + "/geneInfo.tab");
+    if (ge.fail()) { err = "EXITING because of fatal INPUT error: could not open input file " + dir + "/geneInfo.tab\n" + sol; return STAR_EXIT_INPUT_FILES; }
+    uint64_t nGe = 0;
+    ge >> nGe;
+    geID.resize(nGe);
+    std::string line;
+    std::getline(ge, line);
+    for (uint64_t i = 0; i < nGe; i++) { std::getline(ge, line); std::istringstream ls(line); ls >> geID[i]; }
+    std::ifstream ex(dir + "/exonGeTrInfo.tab");
+    if (ex.fail()) { err = "EXITING because of fatal INPUT error: could not open input file " + dir + "/exonGeTrInfo.tab\n" + sol; return STAR_EXIT_INPUT_FILES; }
+    uint64_t nEx = 0;
+    ex >> nEx;
+    s.resize(nEx); e.resize(nEx); eMax.resize(nEx); str.resize(nEx); g.resize(nEx);
+    for (uint64_t i = 0; i < nEx; i++) { int st1; uint32_t t1; ex >> s[i] >> e[i] >> st1 >> g[i] >> t1; str[i] = (uint8_t)st1; }
+    for (uint64_t i = 0; i < nEx; i++) eMax[i] = i == 0 ? e[0] : std::max(eMax[i - 1], e[i]);
+    return 0;
+}
+
+void GeneCounts::add(const GeneCounts& o) {
+    cMulti += o.cMulti;
+    for (int t = 0; t < 3; t++) {
+        cNone[t] += o.cNone[t]; cAmbig[t] += o.cAmbig[t];
+        for (size_t i = 0; i < gCount[t].size() && i < o.gCount[t].size(); i++) gCount[t][i] += o.gCount[t][i];
+    }
+}
+
+// Transcriptome_geneCountsAddAlign.cpp:4-63: a uniquely mapped read counts for the one gene whose exons its blocks overlap
+void GeneCounts::addAlign(const GeneModel& gm, uint64_t nTr, const star_align_t* trs) {
+    if (nTr > 1) { cMulti++; return; }
+    const star_align_t& a = trs[0];
+    int64_t gene1[3] = {-1, -1, -1};
+    const int64_t nEx = (int64_t)gm.s.size();
+    for (int ib = (int)a.nExons - 1; ib >= 0 && nEx > 0; ib--) {
+        const uint64_t g1 = a.exG[ib] + a.exL[ib] - 1;   // end of the block
+        int64_t e1;                                        // binarySearch1a: last exon start <= g1
+        if (g1 > gm.s[nEx - 1]) e1 = nEx - 1;
+        else if (g1 < gm.s[0]) e1 = -1;
+        else {
+            int64_t i1 = 0, i2 = nEx - 1;
+            while (i2 > i1 + 1) { const int64_t i3 = (i1 + i2) / 2; if (gm.s[i3] > g1) i2 = i3; else i1 = i3; }
+            while (i1 < nEx - 1 && g1 == gm.s[i1 + 1]) ++i1;
+            e1 = i1;
+        }
+        while (e1 >= 0 && gm.eMax[e1] >= a.exG[ib]) {
+            if (gm.e[e1] >= a.exG[ib]) {
+                const unsigned str1 = (unsigned)gm.str[e1] - 1;
+                for (int itype = 0; itype < 3; itype++) {
+                    if (itype == 1 && a.Str != str1 && str1 < 2) continue;
+                    if (itype == 2 && a.Str == str1 && str1 < 2) continue;
+                    if (gene1[itype] == -1) gene1[itype] = gm.g[e1];
+                    else if (gene1[itype] == -2) continue;
+                    else if (gene1[itype] != (int64_t)gm.g[e1]) gene1[itype] = -2;
+                }
+            }
+            --e1;
+        }
+    }
+    for (int itype = 0; itype < 3; itype++) {
+        if (gene1[itype] == -1) cNone[itype]++;
+        else if (gene1[itype] == -2) cAmbig[itype]++;
+        else gCount[itype][gene1[itype]]++;
+    }
+}
+
+void GeneCounts::write(const GeneModel& gm, const Stats& st, const std::string& path) const {   // Transcriptome.cpp:156-190
+    std::ofstream q(path);
+    const uint64_t unm = st.unmappedMismatch + st.unmappedShort + st.unmappedOther + st.unmappedMulti;
+    q << "N_unmapped"; for (int t = 0; t < 3; t++) q << "\t" << unm; q << "\n";
+    q << "N_multimapping"; for (int t = 0; t < 3; t++) q << "\t" << cMulti; q << "\n";
+    q << "N_noFeature"; for (int t = 0; t < 3; t++) q << "\t" << cNone[t]; q << "\n";
+    q << "N_ambiguous"; for (int t = 0; t < 3; t++) q << "\t" << cAmbig[t]; q << "\n";
+    for (size_t ig = 0; ig < gm.geID.size(); ig++) {
+        q << gm.geID[ig];
+        for (int t = 0; t < 3; t++) q << "\t" << gCount[t][ig];
+        q << "\n";
+    }
 }
 
 static std::string timeMonthDayTime(time_t t) {  // TimeFunctions.cpp:14-20

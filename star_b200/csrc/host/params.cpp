@@ -97,7 +97,7 @@ const char* kUnsupported[] = {
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
-    "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", "quantMode",
+    "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", 
     "quantTranscriptomeBAMcompression", "quantTranscriptomeSAMoutput", "waspOutputMode", "soloType",
     "soloCBtype", "soloCBwhitelist", "soloCBstart", "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate",
     "soloCBposition", "soloUMIposition", "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype",
@@ -173,7 +173,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
-    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); STR("outSAMorder", &P.outSAMorder);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); STR("outSAMorder", &P.outSAMorder);
     STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
     STR("outFilterType", &P.outFilterType); STR("outFilterIntronMotifs", &P.outFilterIntronMotifs); STR("outFilterIntronStrands", &P.outFilterIntronStrands);
     VSTR("outSJtype", &P.outSJtype); STR("outSJfilterReads", &P.outSJfilterReads); VI32("outSJfilterOverhangMin", &P.outSJfilterOverhangMin);
@@ -370,6 +370,12 @@ int finalizeParams(HostParams& P, std::string& err) {
         return bad("EXITING because of FATAL input ERROR: unknown value for the option --outSAMmode=" + P.outSAMmode + "\nSOLUTION: use one of the allowed values: None or Full or NoQS\n");
     if (P.outSAMorder != "Paired" && P.outSAMorder != "PairedKeepInputOrder")   // (records are always written in input order, which both values allow)
         return bad("EXITING because of fatal input ERROR: --outSAMorder " + P.outSAMorder + ": star-b200 always writes records in input order (the reference's --runThreadN 1 order)\n");
+    if (P.quantMode[0] != "-")   // Parameters.cpp:898-935
+        for (const std::string& m : P.quantMode) {
+            if (m == "GeneCounts") P.quantGeneCounts = true;
+            else if (m == "TranscriptomeSAM") return bad("EXITING because of fatal INPUT error: --quantMode TranscriptomeSAM is outside the scope of star-b200 (GeneCounts is supported)\n");
+            else return bad("EXITING because of fatal INPUT error: unrecognized option in --quantMode=" + m + "\nSOLUTION: use one of the allowed values of --quantMode : TranscriptomeSAM or GeneCounts or - .\n");
+        }
     if (P.outReadsUnmapped != "None" && P.outReadsUnmapped != "Fastx")   // Parameters.cpp (outReadsUnmapped)
         return bad("EXITING because of FATAL INPUT ERROR: unknown value of --outReadsUnmapped: " + P.outReadsUnmapped + "\nSOLUTION: use allowed values: None OR Fastx\n");
     // SJ

@@ -84,7 +84,7 @@ def check_twopass_outputs(out, ref):
     assert log_counters(out + "Log.final.out") == log_counters(os.path.join(ref, "Log.final.out"))
     for f in ("_STARgenome/sjdbInfo.txt", "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "_STARgenome/exonInfo.tab",
               "_STARgenome/transcriptInfo.tab", "_STARgenome/geneInfo.tab", "_STARgenome/exonGeTrInfo.tab", "_STARpass1/SJ.out.tab",
-              "Unmapped.out.mate1", "Unmapped.out.mate2"):
+              "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab"):
         if os.path.exists(os.path.join(ref, f)):
             assert open(out + f, "rb").read() == open(os.path.join(ref, f), "rb").read(), f
     if os.path.exists(os.path.join(ref, "_STARpass1/Log.final.out")):

@@ -18,9 +18,14 @@ def test_two_rank_sharded_run_equals_reference(oracle, lib, golden, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
            "-m", "star_b200.dist", "--cli", oc.ORACLE_CLI, "--",
            "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
-           "--outFileNamePrefix", out, "--runThreadN", "2"]
+           "--outFileNamePrefix", out, "--runThreadN", "2", "--quantMode", "GeneCounts", "--outReadsUnmapped", "Fastx"]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
+    whole = str(tmp_path) + "/whole_"   # gene counts and unmapped reads of the merged run = those of a single-process run
+    subprocess.check_call([oc.ORACLE_CLI] + cmd[cmd.index("--genomeDir"):cmd.index("--outFileNamePrefix")] + ["--outFileNamePrefix", whole, "--quantMode", "GeneCounts",
+                          "--outReadsUnmapped", "Fastx"], stdout=subprocess.DEVNULL)
+    for f in ("ReadsPerGene.out.tab", "Unmapped.out.mate1", "Unmapped.out.mate2"):
+        assert open(out + f, "rb").read() == open(whole + f, "rb").read(), f
     ref = os.path.join(golden, "ref_std")
     assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
     assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
