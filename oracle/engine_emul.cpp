@@ -440,6 +440,15 @@ static void emSortPairs(const u64* kIn, u64* kOut, const u32* vIn, u32* vOut, u6
     for (u64 i = 0; i < n; i++) { kOut[i] = kIn[order[i]]; vOut[i] = vIn[order[i]]; }
 }
 static void emMaxScan(u32* a, u64 n) { for (u64 i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
+static void emSortPairs64(const u64* kIn, u64* kOut, const u64* vIn, u64* vOut, u64 n, int endBit) {
+    std::vector<u64> order(n);
+    for (u64 i = 0; i < n; i++) order[i] = i;
+    const u64 mask = endBit >= 64 ? ~0ULL : ((1ULL << endBit) - 1);
+    std::stable_sort(order.begin(), order.end(), [&](u64 a, u64 b) { return (kIn[a] & mask) < (kIn[b] & mask); });
+    for (u64 i = 0; i < n; i++) { kOut[i] = kIn[order[i]]; vOut[i] = vIn[order[i]]; }
+}
+static void emMaxScan64(u64* a, u64 n) { for (u64 i = 1; i < n; i++) if (a[i] < a[i - 1]) a[i] = a[i - 1]; }
+template <class F> static void emSelectIf(F f, u64 lo, u64 hi, u64* out, u64* nSel) { u64 k = 0; for (u64 v = lo; v < hi; v++) if (f(v)) out[k++] = v; *nSel = k; }
 static void emSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) { u64 k = 0; for (u64 i = 0; i < n; i++) if (flag[i]) out[k++] = in[i]; *nSel = k; }
 }  // namespace starb
 #define SA_ALLOC(bytes) starb::emAlloc(bytes)
@@ -452,17 +461,23 @@ static void emSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
 #define SA_MAX_SCAN(a, n) starb::emMaxScan(a, n)
 #define SA_SELECT(in, flag, out, n, nSel) starb::emSelect(in, flag, out, n, nSel)
 #define SA_SYNC() ((void)0)
-#include "../star_b200/csrc/engine/sa_build_impl.cuh"
+#define SA_SORT_PAIRS64(kIn, kOut, vIn, vOut, n, endBit) starb::emSortPairs64(kIn, kOut, vIn, vOut, n, endBit)
+#define SA_MAX_SCAN64(a, n) starb::emMaxScan64(a, n)
+#define SA_SELECT_IF(f, lo, hi, out, nSel) starb::emSelectIf(f, lo, hi, out, nSel)
+#include "../star_b200/csrc/engine/sa_build_large.cuh"
 
 extern "C" {
 #pragma GCC visibility push(default)
 int engine_emul_sa_build(int, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte) {
-    if (2 * nGenome >= (1ULL << 32) - 64) return STAR_EXIT_PARAMETER;
+    if (2 * nGenome >= (1ULL << 32) - 64 && !getenv("STAR_B200_SA_LARGE_CAP")) return STAR_EXIT_PARAMETER;
     const u64 outWords = (nSA + 63) / 64 * (GstrandBit + 1) + 2;
     std::vector<u64> out(outWords, 0);
     u64 rounds = 0;
-    const int rc = saBuildRun(G, nGenome, GstrandBit, nSA, out.data(), &rounds);
+    u64 largeCap = 0;   // STAR_B200_SA_LARGE_CAP=<elements per sort>: the batched 64-bit path of sa_build_large.cuh
+    if (const char* e = getenv("STAR_B200_SA_LARGE_CAP")) largeCap = strtoull(e, nullptr, 10);
+    const int rc = largeCap ? saBuildRunLarge(G, nGenome, GstrandBit, nSA, out.data(), largeCap, &rounds) : saBuildRun(G, nGenome, GstrandBit, nSA, out.data(), &rounds);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: sa_build rc %d after %llu rounds\n", rc, (unsigned long long)rounds);
+    if (rc == 4) return STAR_EXIT_PARAMETER;   // a bin or a tied group exceeds the forced capacity
     if (rc) return STAR_EXIT_BUG;
     if (nSAbyte > outWords * 8) return STAR_EXIT_BUG;
     memcpy(SA, out.data(), nSAbyte);

@@ -2,7 +2,9 @@
 // the sorting / scanning / compaction primitives are cub's (library code, like the radix sort of the mapping path).
 // No CPU fallback: without a CUDA device the call fails.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "dev.cuh"
@@ -48,8 +50,44 @@ static void saSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
     countLaunches(2);
     cudaFree(tmp); cudaFree(dN);
 }
+struct SaMax64 { __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } };
+static void saSortPairs64(const u64* kIn, u64* kOut, const u64* vIn, u64* vOut, u64 n, int endBit) {
+    size_t tb = 0;
+    saNote(cub::DeviceRadixSort::SortPairs(nullptr, tb, kIn, kOut, vIn, vOut, (long long)n, 0, endBit));
+    void* tmp = saAlloc(tb);
+    if (tmp) saNote(cub::DeviceRadixSort::SortPairs(tmp, tb, kIn, kOut, vIn, vOut, (long long)n, 0, endBit));
+    countLaunches(4);
+    cudaFree(tmp);
+}
+static void saMaxScan64(u64* a, u64 n) {
+    size_t tb = 0;
+    saNote(cub::DeviceScan::InclusiveScan(nullptr, tb, a, a, SaMax64(), (long long)n));
+    void* tmp = saAlloc(tb);
+    if (tmp) saNote(cub::DeviceScan::InclusiveScan(tmp, tb, a, a, SaMax64(), (long long)n));
+    countLaunches(2);
+    cudaFree(tmp);
+}
+template <class F> static void saSelectIf(F f, u64 lo, u64 hi, u64* out, u64* nSel) {   // values v in [lo, hi) with f(v), in order
+    size_t tb = 0;
+    *nSel = 0;
+    if (hi <= lo) return;
+    unsigned long long* dN = (unsigned long long*)saAlloc(8);
+    if (!dN) return;
+    thrust::counting_iterator<unsigned long long> it(lo);
+    saNote(cub::DeviceSelect::If(nullptr, tb, it, out, dN, (long long)(hi - lo), f));
+    void* tmp = saAlloc(tb);
+    if (tmp) saNote(cub::DeviceSelect::If(tmp, tb, it, out, dN, (long long)(hi - lo), f));
+    unsigned long long h = 0;
+    saNote(cudaMemcpy(&h, dN, 8, cudaMemcpyDeviceToHost));
+    *nSel = h;
+    countLaunches(2);
+    cudaFree(tmp); cudaFree(dN);
+}
 }  // namespace starb
 
+#define SA_SORT_PAIRS64(kIn, kOut, vIn, vOut, n, endBit) starb::saSortPairs64(kIn, kOut, vIn, vOut, n, endBit)
+#define SA_MAX_SCAN64(a, n) starb::saMaxScan64(a, n)
+#define SA_SELECT_IF(f, lo, hi, out, nSel) starb::saSelectIf(f, lo, hi, out, nSel)
 #define SA_ALLOC(bytes) starb::saAlloc(bytes)
 #define SA_FREE(p) cudaFree(p)
 #define SA_LAUNCH(count, kernel, ...) do { kernel<<<starb::saGrid(count), 256>>>(__VA_ARGS__); starb::saNote(cudaGetLastError()); starb::countLaunches(1); } while (0)
@@ -68,7 +106,7 @@ static void saSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
 #define SA_MAX_SCAN(a, n) starb::saMaxScan(a, n)
 #define SA_SELECT(in, flag, out, n, nSel) starb::saSelect(in, flag, out, n, nSel)
 #define SA_SYNC() starb::saNote(cudaDeviceSynchronize())
-#include "sa_build_impl.cuh"
+#include "sa_build_large.cuh"
 
 using namespace starb;
 
@@ -80,8 +118,12 @@ extern "C" int star_gpu_sa_build(int device, const uint8_t* G, uint64_t nGenome,
         return STAR_EXIT_RUNTIME;
     }
     if (device < 0 || device >= nDev) { setLastError("star_b200: bad device ordinal"); return STAR_EXIT_RUNTIME; }
-    if (2 * nGenome >= (1ULL << 32) - 64) {
-        setLastError("star_b200: this version of the suffix-array build uses 32-bit ranks: genomes up to 2^31 bases incl. padding");
+    // texts beyond 32-bit ranks take the batched 64-bit path (sa_build_large.cuh); STAR_B200_SA_LARGE_CAP=<elements per sort> forces it (tests)
+    u64 largeCap = 0;
+    if (const char* e = getenv("STAR_B200_SA_LARGE_CAP")) largeCap = strtoull(e, nullptr, 10);
+    if (2 * nGenome >= (1ULL << 32) - 64 && largeCap == 0) largeCap = 700000000ULL;
+    if (2 * nGenome >= (1ULL << 33)) {
+        setLastError("star_b200: the suffix-array build handles genomes up to 2^32 bases incl. padding");
         return STAR_EXIT_PARAMETER;
     }
     cudaSetDevice(device);
@@ -96,12 +138,13 @@ extern "C" int star_gpu_sa_build(int device, const uint8_t* G, uint64_t nGenome,
         saNote(cudaMemcpy(dG, G, nGenome, cudaMemcpyHostToDevice));
         saNote(cudaMemset(dOut, 0, outWords * 8));
         u64 rounds = 0;
-        rc = saBuildRun(dG, nGenome, GstrandBit, nSA, dOut, &rounds);
+        rc = largeCap ? saBuildRunLarge(dG, nGenome, GstrandBit, nSA, dOut, largeCap, &rounds) : saBuildRun(dG, nGenome, GstrandBit, nSA, dOut, &rounds);
         if (rc == 0 && nSAbyte <= outWords * 8) saNote(cudaMemcpy(SA, dOut, nSAbyte, cudaMemcpyDeviceToHost));
     }
     cudaFree(dG); cudaFree(dOut);
     if (g_saErr != cudaSuccess) { setLastError(std::string("CUDA error in the suffix-array build: ") + cudaGetErrorString(g_saErr)); return g_saErr == cudaErrorMemoryAllocation ? STAR_EXIT_MEMORY_ALLOCATION : STAR_EXIT_RUNTIME; }
     if (rc == 3) { setLastError("star_b200: out of device memory for the suffix-array build"); return STAR_EXIT_MEMORY_ALLOCATION; }
+    if (rc == 4) { setLastError("star_b200: suffix-array build: a 4-mer bin or a group of tied suffixes exceeds the sort capacity (STAR_B200_SA_LARGE_CAP)"); return STAR_EXIT_PARAMETER; }
     if (rc) { setLastError(rc == 1 ? "star_b200: suffix-array build: number of bases differs from nSA" : "star_b200: suffix-array build did not converge"); return STAR_EXIT_BUG; }
     return 0;
 }

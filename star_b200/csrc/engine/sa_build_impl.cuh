@@ -11,7 +11,7 @@
 // Every kernel is a grid-stride loop; the round loop below is written against a handful of macros (SA_LAUNCH, SA_ALLOC, ...) so that
 // the same source runs on the device (sa_build.cu: CUDA + cub radix sort / scan / select) and, for tests, as emulated CTAs of host
 // threads (oracle/engine_emul.cpp: the library primitives replaced by std:: equivalents).
-// Limits of this version: 2*nGenome < 2^32 - 64 (32-bit ranks: genomes up to 2.1 Gb); ~37 bytes of HBM per text position.
+// This path: 2*nGenome < 2^32 - 64 (32-bit ranks), ~37 bytes of HBM per text position; larger texts: sa_build_large.cuh.
 #pragma once
 #include "dev.cuh"
 

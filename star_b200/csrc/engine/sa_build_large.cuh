@@ -1,0 +1,238 @@
+// sa_build_large.cuh — suffix-array build for texts beyond 32-bit ranks / beyond one sort of the whole text (GRCh38: n = 2 x 3.1 G).
+//
+// Same ordering as sa_build_impl.cuh (prefix doubling, every code 5 its own symbol ordered by position), arranged so that no sort is
+// larger than `cap` elements and only 64-bit rank / order arrays of the whole text stay resident:
+//   round 0   the text is split by the first 4 codes (4096 bins = the top 12 bits of the 60-bit key) into runs of bins of <= cap
+//             positions; every run is selected (in position order), keyed, sorted and ranked on its own — bins are in key order, so
+//             the runs concatenate to the global order.
+//   round h   only members of groups that are still tied are touched ("active"): batches of consecutive groups (<= cap order slots,
+//             cut at a group start) are selected, keyed with (group start - batch start, rank[p+h]) in ONE 64-bit word (31 + 33 bits),
+//             sorted, and written back into the group's own slots with refined ranks.  Ranks are refined in place: a later batch may
+//             read ranks already refined in this round, which only sharpens its keys (rank[a] < rank[b] always implies suffix a <
+//             suffix b).  Stops when a round finds nothing active.
+//   output    positions holding a base, in order, compacted batch by batch into one array and packed.
+// HBM at n positions: text n + rank 8n + order 8n + max(4 x 8 x cap work buffers, 8 x nSA) bytes (GRCh38: ~155 GB with cap = 7e8).
+// Limits: n < 2^33, cap <= 2^31, no single 4-mer bin and no single tied group larger than cap.
+// Written against the SA_* macros of sa_build_impl.cuh plus SA_SELECT_IF / SA_MAX_SCAN64 / SA_SORT_PAIRS64.
+#pragma once
+#include <vector>
+
+#include "sa_build_impl.cuh"
+
+namespace starb {
+
+struct SaBinInRange {   // position p starts with a 4-code prefix whose bin is in [b0, b1)
+    const u8* T; u32 b0, b1;
+    __host__ __device__ bool operator()(u64 p) const {
+        u32 b = 0; bool live = true;
+        for (int j = 0; j < 4; j++) { u32 c = 0; if (live) { c = T[p + j]; if (c == 5) live = false; } b = (b << 3) | c; }
+        return b >= b0 && b < b1;
+    }
+};
+struct SaActive {       // order slot j belongs to a group of more than one member (rank = first slot of the group)
+    const u64* rank; const u64* order; u64 n;
+    __host__ __device__ bool operator()(u64 j) const {
+        const bool head = rank[order[j]] == j;
+        const bool nextHead = j + 1 >= n || rank[order[j + 1]] == j + 1;
+        return !(head && nextHead);
+    }
+};
+struct SaIsBase {       // order slot j holds a position with a base
+    const u8* T; const u64* order;
+    __host__ __device__ bool operator()(u64 j) const { return T[order[j]] < 4; }
+};
+
+__global__ void __launch_bounds__(256) sal_hist_kernel(const u8* __restrict__ T, u64 n, unsigned long long* __restrict__ hist) {
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) {
+        u32 b = 0; bool live = true;
+        for (int j = 0; j < 4; j++) { u32 c = 0; if (live) { c = SB_LDG(T + p + j); if (c == 5) live = false; } b = (b << 3) | c; }
+        atomicAdd(hist + b, 1ULL);
+    }
+}
+__global__ void __launch_bounds__(256) sal_key0_kernel(const u8* __restrict__ T, const u64* __restrict__ pos, u64 m, u64* __restrict__ key) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 p = pos[i];
+        u64 k = 0; bool live = true;
+#pragma unroll 1
+        for (int j = 0; j < SA_K0; j++) { u64 c = 0; if (live) { c = SB_LDG(T + p + j); if (c == 5) live = false; } k = (k << 3) | c; }
+        key[i] = k;
+    }
+}
+// run heads of sorted round-0 keys, as (local index + 1) for heads and 0 otherwise (index 0 is always a head, so max-scan works with +1)
+__global__ void __launch_bounds__(256) sal_heads0_kernel(const u64* __restrict__ key, u64 m, u64* __restrict__ hd) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = key[i];
+        hd[i] = (i == 0 || k != key[i - 1] || saHas5(k)) ? i + 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) sal_write0_kernel(const u64* __restrict__ pos, const u64* __restrict__ hd, u64 m, u64 base, u64* __restrict__ order, u64* __restrict__ rank) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        order[base + i] = pos[i];
+        rank[pos[i]] = base + hd[i] - 1;
+    }
+}
+__global__ void __launch_bounds__(256) sal_key_kernel(const u64* __restrict__ rank, const u64* __restrict__ order, const u64* __restrict__ slot, u64 m, u64 a, u64 h, u64 n,
+                                                      u64* __restrict__ key, u64* __restrict__ val) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 p = order[slot[i]];
+        const u64 q = p + h < n ? p + h : n;
+        key[i] = ((rank[p] - a) << 33) | rank[q];
+        val[i] = p;
+    }
+}
+// gh: (index + 1) of the first list member of the element's group; nh: (index + 1) of the latest member that starts a new sub-group
+__global__ void __launch_bounds__(256) sal_heads_kernel(const u64* __restrict__ key, u64 m, u64* __restrict__ gh, u64* __restrict__ nh) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = key[i];
+        const bool g = i == 0 || (k >> 33) != (key[i - 1] >> 33);
+        gh[i] = g ? i + 1 : 0;
+        nh[i] = (g || k != key[i - 1]) ? i + 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) sal_write_kernel(const u64* __restrict__ key, const u64* __restrict__ val, const u64* __restrict__ gh, const u64* __restrict__ nh, u64 m, u64 a,
+                                                        u64* __restrict__ order, u64* __restrict__ rank) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+        const u64 r1 = a + (key[i] >> 33);
+        order[r1 + (i + 1 - gh[i])] = val[i];
+        rank[val[i]] = r1 + (nh[i] - gh[i]);
+    }
+}
+__global__ void __launch_bounds__(256) sal_gather_kernel(const u64* __restrict__ order, const u64* __restrict__ slot, u64 m, u64* __restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) out[i] = order[slot[i]];
+}
+// as sa_pack_kernel, 64-bit positions
+__global__ void __launch_bounds__(128) sal_pack_kernel(const u64* __restrict__ sa, u64 nSA, u64 nGenome, u32 GstrandBit, u64* __restrict__ out) {
+    extern __shared__ u8 smem[];
+    const u32 bits = GstrandBit + 1;
+    const u32 lane = threadIdx.x & 31;
+    u64* tile = (u64*)smem + (u64)(threadIdx.x >> 5) * 32 * bits;
+    const u64 N2bit = 1ULL << GstrandBit;
+    const u64 nGroups = (nSA + 63) / 64;
+    const u64 nWarps = ((u64)gridDim.x * blockDim.x) >> 5;
+#pragma unroll 1
+    for (u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t * 32 < nGroups; t += nWarps) {
+        const u64 g = t * 32 + lane;
+        if (g < nGroups) {
+            u64* o = tile + (u64)lane * bits;
+            u64 acc = 0;
+            u32 sh = 0;
+#pragma unroll 1
+            for (u32 e = 0; e < 64; e++) {
+                const u64 r = g * 64 + e;
+                u64 val = 0;
+                if (r < nSA) { const u64 p = sa[r]; val = p < nGenome ? p : ((p - nGenome) | N2bit); }
+                acc |= val << sh;
+                if (sh + bits >= 64) { *o++ = acc; acc = sh + bits > 64 ? val >> (64 - sh) : 0; }
+                sh = (sh + bits) & 63;
+            }
+        }
+        __syncwarp();
+        const u64 rows = nGroups - t * 32 < 32 ? nGroups - t * 32 : 32;
+        u64* dst = out + t * 32 * bits;
+        for (u64 k = lane; k < rows * bits; k += 32) dst[k] = tile[k];
+        __syncwarp();
+    }
+}
+
+#ifdef SA_LAUNCH
+// Returns 0, or: 1 = number of bases differs from nSA, 2 = no convergence, 3 = out of memory, 4 = a 4-mer bin or a tied group exceeds cap.
+inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u64* outWords, u64 cap, u64* roundsOut) {
+    const u64 n = 2 * nGenome, padT = 64;
+    if (n >= (1ULL << 33) || cap > (1ULL << 31) || cap < 64) return 4;
+    u8* T = (u8*)SA_ALLOC(n + padT);
+    u64* rank = (u64*)SA_ALLOC((n + 1) * 8);
+    u64* order = (u64*)SA_ALLOC(n * 8);
+    u64 *keyA = (u64*)SA_ALLOC(cap * 8), *keyB = (u64*)SA_ALLOC(cap * 8), *valA = (u64*)SA_ALLOC(cap * 8), *valB = (u64*)SA_ALLOC(cap * 8);
+    unsigned long long* hist = (unsigned long long*)SA_ALLOC(4096 * 8);
+    u64* sa64 = nullptr;
+    int rc = 0;
+    u64 rounds = 0;
+    if (!T || !rank || !order || !keyA || !keyB || !valA || !valB || !hist) rc = 3;
+    if (!rc) {
+        SA_LAUNCH(n + padT, sa_text_kernel, dG, nGenome, T, padT);
+        SA_COPY_TO(rank + n, &n, 8);
+        std::vector<unsigned long long> h4(4096, 0);
+        SA_COPY_TO(hist, h4.data(), 4096 * 8);
+        SA_LAUNCH(n, sal_hist_kernel, T, n, hist);
+        SA_COPY_FROM(h4.data(), hist, 4096 * 8);
+        // ---- round 0: runs of bins
+        u64 base = 0;
+        for (u32 b0 = 0; b0 < 4096 && !rc;) {
+            u64 cnt = h4[b0];
+            u32 b1 = b0 + 1;
+            if (cnt > cap) { rc = 4; break; }
+            while (b1 < 4096 && cnt + h4[b1] <= cap) cnt += h4[b1++];
+            if (cnt) {
+                u64 m = 0;
+                SA_SELECT_IF((SaBinInRange{T, b0, b1}), 0, n, valA, &m);
+                if (m != cnt) { rc = 2; break; }
+                SA_LAUNCH(m, sal_key0_kernel, T, valA, m, keyA);
+                SA_SORT_PAIRS64(keyA, keyB, valA, valB, m, 3 * SA_K0);
+                SA_LAUNCH(m, sal_heads0_kernel, keyB, m, keyA);
+                SA_MAX_SCAN64(keyA, m);
+                SA_LAUNCH(m, sal_write0_kernel, valB, keyA, m, base, order, rank);
+                base += m;
+            }
+            b0 = b1;
+        }
+        if (!rc && base != n) rc = 2;
+        rounds = 1;
+        // ---- doubling rounds over the active groups
+        for (u64 h = SA_K0; !rc; h *= 2) {
+            u64 active = 0;
+            for (u64 a = 0; a < n && !rc;) {
+                u64 b = a + cap < n ? a + cap : n;
+                if (b < n) {   // cut at the start of the group that slot b belongs to
+                    u64 pb = 0, gs = 0;
+                    SA_COPY_FROM(&pb, order + b, 8);
+                    SA_COPY_FROM(&gs, rank + pb, 8);
+                    if (gs <= a) { rc = 4; break; }
+                    b = gs;
+                }
+                u64 m = 0;
+                SA_SELECT_IF((SaActive{rank, order, n}), a, b, valA, &m);   // active slots of the batch
+                if (m) {
+                    SA_LAUNCH(m, sal_key_kernel, rank, order, valA, m, a, h, n, keyA, valB);
+                    SA_SORT_PAIRS64(keyA, keyB, valB, valA, m, 64);           // sorted keys in keyB, positions in valA
+                    SA_LAUNCH(m, sal_heads_kernel, keyB, m, keyA, valB);
+                    SA_MAX_SCAN64(keyA, m);
+                    SA_MAX_SCAN64(valB, m);
+                    SA_LAUNCH(m, sal_write_kernel, keyB, valA, keyA, valB, m, a, order, rank);
+                    active += m;
+                }
+                a = b;
+            }
+            if (rc) break;
+            if (active == 0) break;
+            rounds++;
+            if (h > 2 * n) { rc = 2; break; }
+        }
+    }
+    SA_SYNC();
+    SA_FREE(keyA); SA_FREE(keyB); SA_FREE(valB); SA_FREE(hist);
+    keyA = keyB = valB = nullptr;
+    if (!rc) {
+        sa64 = (u64*)SA_ALLOC((nSA + 64) * 8);
+        if (!sa64) rc = 3;
+    }
+    if (!rc) {
+        u64 got = 0;
+        for (u64 a = 0; a < n && !rc; a += cap) {
+            const u64 b = a + cap < n ? a + cap : n;
+            u64 m = 0;
+            SA_SELECT_IF((SaIsBase{T, order}), a, b, valA, &m);
+            if (got + m > nSA) { rc = 1; break; }
+            if (m) SA_LAUNCH(m, sal_gather_kernel, order, valA, m, sa64 + got);
+            got += m;
+        }
+        if (!rc && got != nSA) rc = 1;
+        if (!rc) SA_LAUNCH_PACK(nSA, GstrandBit + 1, sal_pack_kernel, sa64, nSA, nGenome, GstrandBit, outWords);
+    }
+    SA_SYNC();
+    if (roundsOut) *roundsOut = rounds;
+    SA_FREE(T); SA_FREE(rank); SA_FREE(order); SA_FREE(valA); SA_FREE(sa64);
+    return rc;
+}
+#endif
+
+}  // namespace starb

@@ -53,9 +53,13 @@ def _check_tiny(golden, out):
 TINY_ARGS = ["--genomeFastaFiles", "genome.fa", "--sjdbGTFfile", "annot.gtf", "--sjdbOverhang", "99", "--genomeSAindexNbases", "7"]
 
 
-@pytest.mark.parametrize("emulated", [False, True])
+@pytest.mark.parametrize("emulated", [False, True, "large"])
 def test_generate_torture_genome_matches_reference(oracle, torture, tmp_path, emulated):
+    """emulated = "large": the batched 64-bit path for texts beyond one sort (sa_build_large.cuh), forced with a small capacity so that
+    round 0 runs in several bin runs and the doubling rounds in several batches of tied groups."""
     env = dict(os.environ, STAR_CLI_SJDB_EMUL=EMUL) if emulated else None
+    if emulated == "large":
+        env["STAR_B200_SA_LARGE_CAP"] = "20000"
     out = str(tmp_path / "idx") + "/"
     _generate(oc.ORACLE_CLI, torture, out, ["--genomeFastaFiles", "g1.fa", "g2.fa"] + json.load(open(os.path.join(torture, "args.json"))), env)
     _check_torture(torture, out)
@@ -86,6 +90,9 @@ def test_gpu_generate_matches_reference(lib, golden, torture, tmp_path):
     star = os.path.join(ROOT, "star_b200", "bin", "STAR")
     out = str(tmp_path / "idx_t") + "/"
     _generate(star, torture, out, ["--genomeFastaFiles", "g1.fa", "g2.fa"] + json.load(open(os.path.join(torture, "args.json"))))
+    _check_torture(torture, out)
+    out = str(tmp_path / "idx_tl") + "/"   # the batched 64-bit path, forced
+    _generate(star, torture, out, ["--genomeFastaFiles", "g1.fa", "g2.fa"] + json.load(open(os.path.join(torture, "args.json"))), dict(os.environ, STAR_B200_SA_LARGE_CAP="20000"))
     _check_torture(torture, out)
     out = str(tmp_path / "idx_tiny") + "/"
     _generate(star, golden, out, TINY_ARGS)
