@@ -20,6 +20,7 @@
 #include <filesystem>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <thread>
 
 #include "host.h"
@@ -68,6 +69,8 @@ struct StageState {
     int bySJstage = 0;                       // 0: single stage; 1: hold reads with unannotated junctions; 2: map the held reads
     std::vector<Junction> sjAll;             // stage 1: junction records of ALL mapped reads (chunkOutSJ1)
     std::vector<ReadChunk> held;             // stage 1 -> 2: the reads to map again, in input order, chunked (never across input files)
+    const TranscriptModel* trModel = nullptr;   // --quantMode TranscriptomeSAM
+    std::mt19937 rngMultOrder;               // one draw per mapped, written read, in read order (ReadAlign_quantTranscriptome.cpp:69)
     const GeneModel* geneModel = nullptr;    // --quantMode GeneCounts: exons / genes, and the counts of every stage
     GeneCounts geneCounts;
     std::string streamSuffix;                // sharded 2nd stage: records go to Aligned.out<suffix>.sam|bam (the merge orders the parts)
@@ -232,6 +235,13 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
 
     OutputWriter W(P, idx);
     W.geneModel = stage.geneModel;
+    W.trModel = stage.trModel;
+    const bool trYes = stage.trModel != nullptr;
+    std::ofstream trOut;
+    if (trYes) {   // Aligned.toTranscriptome.out.bam (Parameters.cpp:911-914)
+        trOut.open(P.outFileNamePrefix + "Aligned.toTranscriptome.out" + stage.streamSuffix + ".bam", firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (P.gpuShardIndex == 0 && firstStage) { std::string z; const std::string h = W.bamHeaderTranscriptome(); OutputWriter::bgzfCompress(h.data(), h.size(), P.quantTranscriptomeBAMcompression, z); trOut.write(z.data(), z.size()); }
+    }
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     std::ofstream samOut;
     const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);   // Aligned.out.sam / Aligned.out.bam
@@ -312,6 +322,14 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 std::vector<std::vector<uint64_t>> ckey(coordYes ? nT : 0);
                 std::vector<OutputWriter::BySJoutHold> hold(stage.bySJstage == 1 ? nT : 0);
                 std::vector<std::string> unm(unmYes ? 2 * nT : 0);   // [2*t + mate]
+                std::vector<std::string> trb(trYes ? nT : 0);
+                std::vector<double> trDraw;
+                if (trYes) {   // the run's random stream is consumed read by read: draw before the ranges are formatted in parallel
+                    trDraw.assign(chunk.nReads, 0.0);
+                    std::uniform_real_distribution<double> u01(0.0, 1.0);
+                    for (uint32_t i = 0; i < chunk.nReads; i++)
+                        if (wk->out.reads[i].unmapType < 0 && !(stage.bySJstage == 1 && OutputWriter::heldBySJout(wk->out, i))) trDraw[i] = u01(stage.rngMultOrder);
+                }
                 std::vector<GeneCounts> gcs(stage.geneModel ? nT : 0);
                 for (auto& gcT : gcs) gcT.init(stage.geneModel->geID.size());
                 auto work = [&](int t) {   // contiguous read ranges; concatenated in input order below
@@ -319,7 +337,8 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     sam[t].reserve((size_t)(hi - lo) * 700);
                     W.formatReads(chunk, wk->out, lo, hi, sam[t], sj[t], st[t], coordYes ? &cblob[t] : nullptr, coordYes ? &ckey[t] : nullptr,
                                   stage.bySJstage == 1 ? &hold[t] : nullptr, unmYes ? &unm[2 * t] : nullptr,
-                                  stage.geneModel ? &gcs[t] : nullptr);
+                                  stage.geneModel ? &gcs[t] : nullptr, trYes ? &trb[t] : nullptr, trYes ? trDraw.data() : nullptr);
+                    if (trYes) { std::string z; OutputWriter::bgzfCompress(trb[t].data(), trb[t].size(), P.quantTranscriptomeBAMcompression, z); trb[t].swap(z); }
                     if (bamYes) {   // BGZF framing in the formatting thread: complete blocks, so the per-thread pieces simply concatenate
                         std::string z;
                         z.reserve(sam[t].size() / 3);
@@ -341,6 +360,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
                     if (stage.geneModel) stage.geneCounts.add(gcs[t]);
+                    if (trYes) trOut.write(trb[t].data(), trb[t].size());
                     if (unmYes) for (unsigned m = 0; m < P.readNmates; m++) unmOut[m].write(unm[2 * t + m].data(), unm[2 * t + m].size());
                     if (stage.bySJstage == 1) {
                         stage.sjAll.insert(stage.sjAll.end(), hold[t].sjAll.begin(), hold[t].sjAll.end());
@@ -414,6 +434,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     readerThread.join();
     if (runRc) { err = runErr; return runRc; }
     if (!outErr.empty()) { err = outErr; return STAR_EXIT_BUG; }
+    if (trYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); trOut.write(e, ne); }
     if (bamYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
     if (streamYes) samOut.close();
     if (coordYes && P.gpuShardCount > 1) {   // one shard: the (unsorted) records and their keys go to the merge, which sorts the whole run
@@ -546,6 +567,13 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         stage.geneModel = &geneModel;
         stage.geneCounts.init(geneModel.geID.size());
     }
+    TranscriptModel trModel;
+    if (P.quantTrSAM) {
+        rc = trModel.load(P.sjdbGTFfile == "-" ? P.genomeDir : P.sjdbInsertOutDir, err);
+        if (rc) { eng->destroy(ectx); return exitWithError(err, rc, &logMain); }
+        stage.trModel = &trModel;
+        stage.rngMultOrder.seed((uint32_t)(P.runRNGseed * (P.gpuShardIndex + 1)));   // thread iChunk of the reference: runRNGseed*(iChunk+1)
+    }
     const bool bySJout = P.outFilterType == "BySJout";
     stage.bySJstage = bySJout ? 1 : 0;
     const std::string stateFile = P.outFileNamePrefix + "bysj_stage1.bin";
@@ -660,6 +688,15 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
             samOut.clear();
         }
     if (samYes && P.outBAMunsorted) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }
+    if (P.quantTrSAM) {   // Aligned.toTranscriptome.out.bam: header of shard 0, then the parts in the reference's order
+        std::ofstream to(P.outFileNamePrefix + "Aligned.toTranscriptome.out.bam", std::ios::binary);
+        for (const char* part : {"", ".stage2"})
+            for (int r = 0; r < nShards; r++) {
+                std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Aligned.toTranscriptome.out" + part + ".bam", std::ios::binary);
+                if (in.good()) { to << in.rdbuf(); to.clear(); }
+            }
+        size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); to.write(e, ne);
+    }
     if (P.outReadsUnmapped == "Fastx")
         for (unsigned m = 0; m < P.readNmates; m++) {
             std::ofstream uo(P.outFileNamePrefix + "Unmapped.out.mate" + std::to_string(m + 1), std::ios::binary);

@@ -44,7 +44,11 @@ struct HostParams {
     std::vector<int> outSAMattrOrder;       // ATTR_* codes
     unsigned outSAMattrIHstart = 1;
     std::vector<std::string> quantMode = {"-"};   // GeneCounts only (ReadsPerGene.out.tab); TranscriptomeSAM is out of scope
-    bool quantGeneCounts = false;
+    bool quantGeneCounts = false, quantTrSAM = false;
+    int32_t quantTranscriptomeBAMcompression = 1;
+    uint64_t runRNGseed = 777;               // seeds the primary-flag draw of Aligned.toTranscriptome.out.bam (ReadAlign.cpp:11)
+    std::string quantTranscriptomeSAMoutput = "BanSingleEnd_BanIndels_ExtendSoftclip";
+    bool quantTrIndel = false, quantTrSoftClip = false, quantTrSingleEnd = false;   // what Aligned.toTranscriptome.out.bam may contain
     std::string outReadsUnmapped = "None";  // Fastx: Unmapped.out.mate1/2 (ReadAlign::outReadsUnmapped)
     std::vector<std::string> outSAMunmapped = {"None"};
     bool unmappedWithin = false, unmappedKeepPairs = false;
@@ -231,6 +235,19 @@ struct GeneCounts {
     void write(const GeneModel& gm, const Stats& st, const std::string& path) const;   // Transcriptome::quantsOutput
 };
 
+// --quantMode TranscriptomeSAM: transcripts and their exons (transcriptInfo.tab, exonInfo.tab; Transcriptome.cpp:32-75)
+struct TranscriptModel {
+    std::vector<uint64_t> trS, trE, trEmax;
+    std::vector<uint32_t> trExI, trLen;
+    std::vector<uint16_t> trExN;
+    std::vector<uint8_t> trStr;
+    std::vector<std::string> trID;
+    std::vector<uint32_t> exSE, exLenCum;
+    int load(const std::string& dir, std::string& err);
+    // Transcriptome::quantAlign (Transcriptome_quantAlign.cpp:94-114): the projections of a genomic alignment onto every transcript it fits
+    uint32_t quantAlign(const star_align_t& aG, uint64_t Lread, std::vector<star_align_t>& out) const;
+};
+
 // Formats everything the reference writes per read: SAM records, junction records, counters.
 class OutputWriter {
    public:
@@ -244,8 +261,13 @@ class OutputWriter {
     // unm (--outReadsUnmapped Fastx): text for Unmapped.out.mate1 / mate2
     void formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
                      std::vector<Junction>& sj, Stats& st, std::string* coord = nullptr, std::vector<uint64_t>* coordKey = nullptr,
-                     BySJoutHold* by = nullptr, std::string* unm = nullptr, GeneCounts* gc = nullptr) const;
+                     BySJoutHold* by = nullptr, std::string* unm = nullptr, GeneCounts* gc = nullptr, std::string* trBam = nullptr,
+                     const double* trDraw = nullptr) const;
     const GeneModel* geneModel = nullptr;   // set for --quantMode GeneCounts
+    const TranscriptModel* trModel = nullptr;   // set for --quantMode TranscriptomeSAM
+    std::string bamHeaderTranscriptome() const;   // samHeaders.cpp:8-20
+    // true when read i of stage 1 of BySJout is held back (ReadAlign::outFilterBySJout)
+    static bool heldBySJout(const star_align_batch_t& out, uint32_t i);
     std::string samHeader() const;                                   // samHeaders.cpp:5-113
     std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`
@@ -261,7 +283,8 @@ class OutputWriter {
     const HostParams& P;
     const LoadedIndex& idx;
     void bamMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
-                   std::string& bam) const;                          // ReadAlign_alignBAM.cpp:47-614, mapped branch
+                   std::string& bam, bool transcriptomic = false) const;                          // ReadAlign_alignBAM.cpp:47-614, mapped branch
+    void quantTranscriptome(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trs, uint64_t nTr, double draw, std::string& bam) const;
     void bamUnmapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trBest, int unmapType,
                      const bool* mateMap, std::string& bam) const;    // ReadAlign_alignBAM.cpp, alignType>=0 branch
     void samMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,

@@ -401,7 +401,15 @@ void OutputWriter::bamUnmapped(const ReadChunk& c, uint32_t i, const star_read_r
 }
 
 void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t& tr, uint64_t nTrOut, uint64_t iTrOut,
-                             std::string& bam) const {
+                             std::string& bam, bool transcriptomic) const {
+    // transcriptomic (ReadAlign_quantTranscriptome.cpp:72: alignBAM(..., trChrStart = 0, ..., outSAMattrOrderQuant)): tr.Chr is a transcript,
+    // coordinates are transcript coordinates, attributes NH HI (+ RG, MC when requested)
+    std::vector<int> quantAttr;
+    if (transcriptomic) {
+        quantAttr = {ATTR_NH, ATTR_HI};
+        for (int code : P.outSAMattrOrder) if (code == ATTR_RG || code == ATTR_MC) quantAttr.push_back(code);
+    }
+    const std::vector<int>& attrOrder = transcriptomic ? quantAttr : P.outSAMattrOrder;
     const char* name = c.names.data() + c.nameOff[i];
     const size_t nameLen = strlen(name);
     const bool flagPaired = c.nMates == 2;
@@ -416,7 +424,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
     }
     const unsigned Str = tr.Str;
     const unsigned leftMate = flagPaired ? Str : 0;
-    const uint64_t chrStart = idx.chrStart[tr.Chr];
+    const uint64_t chrStart = transcriptomic ? 0 : idx.chrStart[tr.Chr];
     // CIGARs of both mates first (MC needs the other mate's), packed and as text (ReadAlign_calcCIGAR.cpp:3-60)
     std::vector<uint32_t> packed[2];
     std::string cigarText[2];
@@ -478,7 +486,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
         uint64_t tagNM = 0;
         std::string tagMD;
         bool needNM = false;
-        for (int code : P.outSAMattrOrder) if (code == ATTR_NM || code == ATTR_MD) needNM = true;
+        for (int code : attrOrder) if (code == ATTR_NM || code == ATTR_MD) needNM = true;
         if (needNM) {  // samAttrNM_MD, ReadAlign_alignBAM.cpp:9-45
             std::string R(Lread, (char)4);
             auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
@@ -522,7 +530,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
             tagNM = nMM + nI + nD;
         }
         std::string at;
-        for (int code : P.outSAMattrOrder) {
+        for (int code : attrOrder) {
             switch (code) {
                 case ATTR_NH: attrInt(at, "NH", (long long)nTrOut); break;
                 case ATTR_HI: attrInt(at, "HI", (long long)(iTrOut + P.outSAMattrIHstart)); break;
@@ -631,7 +639,7 @@ const char* OutputWriter::bgzfEofBlock(size_t& n) {
 
 // ReadAlign_oneRead.cpp:74-75, ReadAlign_mappedFilter.cpp, ReadAlign_outputAlignments.cpp:18-90,133-260
 void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out, uint32_t lo, uint32_t hi, std::string& sam,
-                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by, std::string* unm, GeneCounts* gc) const {
+                               std::vector<Junction>& sj, Stats& st, std::string* coord, std::vector<uint64_t>* coordKey, BySJoutHold* by, std::string* unm, GeneCounts* gc, std::string* trBam, const double* trDraw) const {
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     const bool coordYes = samYes && P.outBAMcoord && coord && coordKey;
     // records appended to `dst` since `from` also go to the coordinate-sorted set with read-order key `key` (one key per record)
@@ -651,10 +659,7 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
         uint64_t L1 = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
         if (by && r.unmapType < 0) {   // ReadAlign::outFilterBySJout (ReadAlign_outputAlignments.cpp:90-130), 1st stage of --outFilterType BySJout
             const star_align_t* tr1 = out.aligns + r.trOffset;
-            bool pass = true;
-            for (uint64_t k = 0; k < r.nTrOut && pass; k++)
-                for (uint32_t iex = 0; iex + 1 < tr1[k].nExons; iex++)
-                    if (tr1[k].canonSJ[iex] >= 0 && tr1[k].sjAnnot[iex] == 0) { pass = false; break; }
+            const bool pass = !heldBySJout(out, i);
             if (P.outSJyes && (P.outSJfilterReads == "All" || r.nTrOut == 1)) {   // the junctions of ALL reads decide which novel ones survive
                 size_t s0 = by->sjAll.size();
                 for (uint64_t k = 0; k < r.nTrOut; k++) recordSJ(tr1[k], r.nTrOut, by->sjAll, s0);
@@ -686,6 +691,7 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                 }
             }
             if (gc && geneModel) gc->addAlign(*geneModel, nTr, trs);   // ReadAlign::alignedAnnotation :296-308
+            if (trBam && trModel) quantTranscriptome(c, i, r, trs, nTr, trDraw ? trDraw[i] : 0.0, *trBam);   // ReadAlign_outputAlignments.cpp:50-57
             if (P.outSJyes && (P.outSJfilterReads == "All" || nTr == 1)) {  // recordSJ :76-87
                 size_t sjReadStartN = sj.size();
                 for (uint64_t k = 0; k < nTr; k++) recordSJ(trs[k], nTr, sj, sjReadStartN);
@@ -860,6 +866,210 @@ std::string OutputWriter::novelJunctions(std::vector<Junction>& all, std::vector
     for (size_t ii = 0; ii < kept.size(); ii++)
         if (sjFilter[ii] && kept[ii].annot == 0) { sjStart.push_back(kept[ii].start); sjEnd.push_back(kept[ii].start + (uint64_t)kept[ii].gap - 1); }
     return std::string();
+}
+
+bool OutputWriter::heldBySJout(const star_align_batch_t& out, uint32_t i) {
+    const star_read_result_t& r = out.reads[i];
+    if (r.unmapType >= 0) return false;
+    const star_align_t* tr1 = out.aligns + r.trOffset;
+    for (uint64_t k = 0; k < r.nTrOut; k++)
+        for (uint32_t iex = 0; iex + 1 < tr1[k].nExons; iex++)
+            if (tr1[k].canonSJ[iex] >= 0 && tr1[k].sjAnnot[iex] == 0) return true;
+    return false;
+}
+
+// ---- --quantMode TranscriptomeSAM ----------------------------------------------------------------------------------------------------
+int TranscriptModel::load(const std::string& dir, std::string& err) {   // Transcriptome.cpp:32-75
+    const char* sol = "SOLUTION: utilize --sjdbGTFfile /path/to/annotantions.gtf option at the genome generation step or mapping step\n";
+    std::ifstream tr(dir + "/transcriptInfo.tab");
+    if (tr.fail()) { err = "EXITING because of fatal INPUT error: could not open input file " + dir + "/transcriptInfo.tab\n" + sol; return STAR_EXIT_INPUT_FILES; }
+    uint64_t nTr = 0;
+    tr >> nTr;
+    trS.resize(nTr); trE.resize(nTr); trEmax.resize(nTr); trExI.resize(nTr); trExN.resize(nTr); trStr.resize(nTr); trID.resize(nTr); trLen.resize(nTr);
+    for (uint64_t i = 0; i < nTr; i++) {
+        uint32_t str1, gene;
+        tr >> trID[i] >> trS[i] >> trE[i] >> trEmax[i] >> str1 >> trExN[i] >> trExI[i] >> gene;
+        trStr[i] = (uint8_t)str1;
+        if (!tr.good()) { err = "EXITING because of FATAL GENOME INDEX FILE error: transcriptInfo.tab is corrupt, or is incompatible with the current STAR version\nSOLUTION: re-generate genome index"; return STAR_EXIT_GENOME_FILES; }
+    }
+    std::ifstream ex(dir + "/exonInfo.tab");
+    if (ex.fail()) { err = "EXITING because of fatal INPUT error: could not open input file " + dir + "/exonInfo.tab\n" + sol; return STAR_EXIT_INPUT_FILES; }
+    uint64_t nEx = 0;
+    ex >> nEx;
+    exSE.resize(2 * nEx); exLenCum.resize(nEx);
+    for (uint64_t i = 0; i < nEx; i++) ex >> exSE[2 * i] >> exSE[2 * i + 1] >> exLenCum[i];
+    for (uint64_t i = 0; i < nTr; i++) { const uint32_t l = trExI[i] + trExN[i] - 1; trLen[i] = exLenCum[l] + exSE[2 * l + 1] - exSE[2 * l] + 1; }
+    return 0;
+}
+
+namespace {
+uint32_t bsearch1(uint32_t x, const uint32_t* X, uint32_t N) {   // binarySearch1, serviceFuns.cpp:192-209: last element <= x, (uint32)-1 outside the range
+    if (x > X[N - 1] || x < X[0]) return (uint32_t)-1;
+    uint32_t i1 = 0, i2 = N - 1;
+    while (i2 > i1 + 1) { const uint32_t i3 = (i1 + i2) / 2; if (X[i3] > x) i2 = i3; else i1 = i3; }
+    while (i1 < N - 1 && x == X[i1 + 1]) ++i1;
+    return i1;
+}
+// alignToTranscript, Transcriptome_quantAlign.cpp:5-92
+int alignToTranscript(star_align_t aG, uint64_t Lread, uint64_t trS1, uint8_t trStr1, const uint32_t* exSE1, const uint32_t* exLenCum1, uint16_t exN1, star_align_t& aT) {
+    const uint32_t g1 = (uint32_t)(aG.exG[0] - trS1);
+    uint32_t ex1 = bsearch1(g1, exSE1, 2 * (uint32_t)exN1);
+    if (ex1 >= 2 * (uint32_t)exN1) return 0;
+    if (ex1 % 2 == 1) { if (exSE1[ex1] == g1) --ex1; else return 0; }
+    ex1 /= 2;
+    aT.nExons = 0;
+    aT.primaryFlag = 0;
+    const int LAST = -99;
+    aG.canonSJ[aG.nExons - 1] = LAST;
+    for (uint32_t iab = 0; iab < aG.nExons; iab++) {
+        if (aG.exG[iab] + aG.exL[iab] > (uint64_t)exSE1[2 * ex1 + 1] + trS1 + 1) return 0;   // block runs past the exon
+        if (iab == 0 || aG.canonSJ[iab - 1] < 0) {
+            aT.exR[aT.nExons] = aG.exR[iab];
+            aT.exG[aT.nExons] = aG.exG[iab] - trS1 - exSE1[2 * ex1] + exLenCum1[ex1];
+            aT.exL[aT.nExons] = aG.exL[iab];
+            aT.exFrag[aT.nExons] = aG.exFrag[iab];
+            if (aT.nExons > 0) aT.canonSJ[aT.nExons - 1] = aG.canonSJ[iab - 1];
+            ++aT.nExons;
+        } else aT.exL[aT.nExons - 1] = (uint16_t)(aT.exL[aT.nExons - 1] + aG.exL[iab]);
+        switch (aG.canonSJ[iab]) {
+            case LAST:
+                if (trStr1 == 2) {   // transcript on the - strand: mirror the coordinates
+                    const uint32_t trlength = exLenCum1[exN1 - 1] + exSE1[2 * exN1 - 1] - exSE1[2 * exN1 - 2] + 1;
+                    for (uint32_t iex = 0; iex < aT.nExons; iex++) {
+                        aT.exR[iex] = (uint16_t)(Lread - (aT.exR[iex] + aT.exL[iex]));
+                        aT.exG[iex] = trlength - (aT.exG[iex] + aT.exL[iex]);
+                    }
+                    for (uint32_t iex = 0; iex < aT.nExons / 2; iex++) {
+                        std::swap(aT.exR[iex], aT.exR[aT.nExons - 1 - iex]); std::swap(aT.exG[iex], aT.exG[aT.nExons - 1 - iex]);
+                        std::swap(aT.exL[iex], aT.exL[aT.nExons - 1 - iex]); std::swap(aT.exFrag[iex], aT.exFrag[aT.nExons - 1 - iex]);
+                    }
+                    for (uint32_t iex = 0; iex < (aT.nExons - 1) / 2; iex++) std::swap(aT.canonSJ[iex], aT.canonSJ[aT.nExons - 2 - iex]);
+                }
+                for (uint32_t iex = 0; iex < aT.nExons; iex++) { aT.sjAnnot[iex] = 0; aT.shiftSJ[iex][0] = 0; aT.shiftSJ[iex][1] = 0; aT.sjStr[iex] = 0; }
+                return 1;
+            case -3:   // mate connection
+                ex1 = bsearch1((uint32_t)(aG.exG[iab + 1] - trS1), exSE1, 2 * (uint32_t)exN1);
+                if (ex1 % 2 == 1) return 0;
+                ex1 /= 2;
+                break;
+            case -2: case -1: break;   // insertion, deletion
+            default:   // junction: has to be the transcript's
+                if (aG.exG[iab] + aG.exL[iab] == (uint64_t)exSE1[2 * ex1 + 1] + trS1 + 1 && aG.exG[iab + 1] == (uint64_t)exSE1[2 * (ex1 + 1)] + trS1) ++ex1;
+                else return 0;
+        }
+    }
+    return 0;
+}
+}  // namespace
+
+uint32_t TranscriptModel::quantAlign(const star_align_t& aG, uint64_t Lread, std::vector<star_align_t>& out) const {
+    const int64_t nTr = (int64_t)trS.size();
+    if (nTr == 0) return 0;
+    const uint64_t g0 = aG.exG[0];
+    int64_t tr1;   // binarySearch1a: last transcript start <= align start
+    if (g0 > trS[nTr - 1]) tr1 = nTr - 1;
+    else if (g0 < trS[0]) return 0;
+    else {
+        int64_t i1 = 0, i2 = nTr - 1;
+        while (i2 > i1 + 1) { const int64_t i3 = (i1 + i2) / 2; if (trS[i3] > g0) i2 = i3; else i1 = i3; }
+        while (i1 < nTr - 1 && g0 == trS[i1 + 1]) ++i1;
+        tr1 = i1;
+    }
+    const uint64_t aGend = aG.exG[aG.nExons - 1];
+    uint32_t n = 0;
+    ++tr1;
+    do {
+        --tr1;
+        if (aGend <= trE[tr1]) {
+            star_align_t aT = aG;   // the scalars (maxScore, nMM, ...) of the genomic alignment stay
+            if (alignToTranscript(aG, Lread, trS[tr1], trStr[tr1], exSE.data() + 2 * trExI[tr1], exLenCum.data() + trExI[tr1], trExN[tr1], aT) == 1) {
+                aT.Chr = (uint32_t)tr1;
+                aT.Str = trStr[tr1] == 1 ? aG.Str : 1 - aG.Str;
+                out.push_back(aT);
+                ++n;
+            }
+        }
+    } while (trEmax[tr1] >= aGend && tr1 > 0);
+    return n;
+}
+
+// ReadAlign::quantTranscriptome, ReadAlign_quantTranscriptome.cpp:7-91.  draw = this read's number of the run's random stream (uniform in [0,1))
+void OutputWriter::quantTranscriptome(const ReadChunk& c, uint32_t i, const star_read_result_t& r, const star_align_t* trs, uint64_t nTr, double draw, std::string& bam) const {
+    std::vector<star_align_t> alignT;
+    const uint64_t Lread = r.Lread;
+    uint64_t readLength[2];
+    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
+    readLength[1] = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    std::string R;   // Read1[0]: mate 1, spacer, reverse complement of mate 2 (numeric); reversed-complemented for roStr = 1
+    for (uint64_t iag = 0; iag < nTr; iag++) {
+        const star_align_t* a1 = &trs[iag];
+        if (!P.quantTrIndel && (a1->nDel > 0 || a1->nIns > 0)) continue;
+        if (!P.quantTrSingleEnd && c.nMates == 2 && a1->exFrag[0] == a1->exFrag[a1->nExons - 1]) continue;
+        star_align_t a2;
+        if (!P.quantTrSoftClip) {   // soft clips are extended to the read ends if the mismatches allow it
+            if (R.empty()) {
+                auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
+                R.assign(Lread, (char)4);
+                const uint64_t o0 = c.seqOff[(uint64_t)i * c.nMates], o1 = c.seqOff[(uint64_t)i * c.nMates + 1];
+                for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[o0 + k]);
+                if (c.nMates == 2) {
+                    R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
+                    for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[o1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+                }
+            }
+            std::string Rr;
+            const std::string* Rp = &R;
+            if (a1->roStr != 0) {
+                Rr.assign(Lread, (char)4);
+                for (uint64_t k = 0; k < Lread; k++) { char ch = R[k]; Rr[Lread - 1 - k] = ch < 4 ? 3 - ch : ch; }
+                Rp = &Rr;
+            }
+            a2 = *a1;
+            uint64_t nMM1 = 0;
+            for (uint32_t iab = 0; iab < a2.nExons; iab++) {
+                uint64_t left1 = 0, right1 = 0;
+                if (iab == 0) left1 = a2.exR[iab];
+                else if (a2.canonSJ[iab - 1] == -3) left1 = a2.exR[iab] - readLength[a2.exFrag[iab - 1]] - 1;
+                if (iab == a2.nExons - 1) right1 = Lread - a2.exR[iab] - a2.exL[iab];
+                else if (a2.canonSJ[iab] == -3) right1 = readLength[a2.exFrag[iab]] - a2.exR[iab] - a2.exL[iab];
+                for (uint64_t b = 1; b <= left1; b++) {
+                    const char r1 = (*Rp)[a2.exR[iab] - b], g1 = (char)idx.view.G[a2.exG[iab] - b];
+                    if (r1 != g1 && r1 < 4 && g1 < 4) ++nMM1;
+                }
+                for (uint64_t b = 0; b < right1; b++) {
+                    const char r1 = (*Rp)[a2.exR[iab] + a2.exL[iab] + b], g1 = (char)idx.view.G[a2.exG[iab] + a2.exL[iab] + b];
+                    if (r1 != g1 && r1 < 4 && g1 < 4) ++nMM1;
+                }
+                a2.exR[iab] = (uint16_t)(a2.exR[iab] - left1);
+                a2.exG[iab] -= left1;
+                a2.exL[iab] = (uint16_t)(a2.exL[iab] + left1 + right1);
+            }
+            const uint64_t mmTotal = std::min<uint64_t>(P.hp.outFilterMismatchNmax, (uint64_t)(P.hp.outFilterMismatchNoverReadLmax * (double)(readLength[0] + readLength[1])));
+            if (a2.nMM + nMM1 > std::min<uint64_t>(mmTotal, (uint64_t)(P.hp.outFilterMismatchNoverLmax * (double)(Lread - 1)))) continue;
+            a1 = &a2;
+        }
+        trModel->quantAlign(*a1, Lread, alignT);
+    }
+    const uint64_t nAlignT = alignT.size();
+    if (nAlignT == 0) return;
+    alignT[(size_t)(draw * (double)nAlignT)].primaryFlag = 1;
+    for (uint64_t k = 0; k < nAlignT; k++) bamMapped(c, i, r, alignT[k], nAlignT, k, bam, true);
+}
+
+std::string OutputWriter::bamHeaderTranscriptome() const {   // samHeaders.cpp:8-20, outBAMwriteHeader
+    std::string text;
+    for (size_t ii = 0; ii < trModel->trID.size(); ii++) text += "@SQ\tSN:" + trModel->trID[ii] + "\tLN:" + std::to_string(trModel->trLen[ii]) + "\n";
+    for (const std::string& rg : P.outSAMattrRGlineSplit) text += "@RG\t" + rg + "\n";
+    std::string h = "BAM\001";
+    put32(h, (uint32_t)text.size());
+    h += text;
+    put32(h, (uint32_t)trModel->trID.size());
+    for (size_t ii = 0; ii < trModel->trID.size(); ii++) {
+        put32(h, (uint32_t)(trModel->trID[ii].size() + 1));
+        h.append(trModel->trID[ii].c_str(), trModel->trID[ii].size() + 1);
+        put32(h, trModel->trLen[ii]);
+    }
+    return h;
 }
 
 // ---- --quantMode GeneCounts --------------------------------------------------------------------------------------------------------

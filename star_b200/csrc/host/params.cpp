@@ -98,7 +98,7 @@ const char* kUnsupported[] = {
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
     "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", 
-    "quantTranscriptomeBAMcompression", "quantTranscriptomeSAMoutput", "waspOutputMode", "soloType",
+    "waspOutputMode", "soloType",
     "soloCBtype", "soloCBwhitelist", "soloCBstart", "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate",
     "soloCBposition", "soloUMIposition", "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype",
     "soloInputSAMattrBarcodeSeq", "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup",
@@ -107,7 +107,7 @@ const char* kUnsupported[] = {
 
 // resource / housekeeping knobs of the reference that cannot change any output here (buffers are sized from the chunk, the BAM sort is in
 // memory, there are no temporary files): accepted and ignored, so that existing command lines keep working
-const char* kIgnored[] = {"sysShell", "runDirPerm", "runRNGseed", "limitIObufferSize", "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed",
+const char* kIgnored[] = {"sysShell", "runDirPerm", "limitIObufferSize", "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed",
                           "limitBAMsortRAM", "limitNreadsSoft", "outTmpDir", "outTmpKeep", "outBAMsortingThreadN", "outBAMsortingBinsN"};
 
 }  // namespace
@@ -173,7 +173,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
-    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); STR("outSAMorder", &P.outSAMorder);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); STR("quantTranscriptomeSAMoutput", &P.quantTranscriptomeSAMoutput);
+    I32("quantTranscriptomeBAMcompression", &P.quantTranscriptomeBAMcompression); U64("runRNGseed", &P.runRNGseed); STR("outSAMorder", &P.outSAMorder);
     STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
     STR("outFilterType", &P.outFilterType); STR("outFilterIntronMotifs", &P.outFilterIntronMotifs); STR("outFilterIntronStrands", &P.outFilterIntronStrands);
     VSTR("outSJtype", &P.outSJtype); STR("outSJfilterReads", &P.outSJfilterReads); VI32("outSJfilterOverhangMin", &P.outSJfilterOverhangMin);
@@ -373,9 +374,16 @@ int finalizeParams(HostParams& P, std::string& err) {
     if (P.quantMode[0] != "-")   // Parameters.cpp:898-935
         for (const std::string& m : P.quantMode) {
             if (m == "GeneCounts") P.quantGeneCounts = true;
-            else if (m == "TranscriptomeSAM") return bad("EXITING because of fatal INPUT error: --quantMode TranscriptomeSAM is outside the scope of star-b200 (GeneCounts is supported)\n");
+            else if (m == "TranscriptomeSAM") P.quantTrSAM = true;
             else return bad("EXITING because of fatal INPUT error: unrecognized option in --quantMode=" + m + "\nSOLUTION: use one of the allowed values of --quantMode : TranscriptomeSAM or GeneCounts or - .\n");
         }
+    if (P.quantTrSAM) {   // Parameters.cpp:905-927
+        if (P.quantTranscriptomeSAMoutput == "BanSingleEnd_BanIndels_ExtendSoftclip") { P.quantTrIndel = false; P.quantTrSoftClip = false; P.quantTrSingleEnd = false; }
+        else if (P.quantTranscriptomeSAMoutput == "BanSingleEnd") { P.quantTrIndel = true; P.quantTrSoftClip = true; P.quantTrSingleEnd = false; }
+        else if (P.quantTranscriptomeSAMoutput == "BanSingleEnd_ExtendSoftclip") { P.quantTrIndel = true; P.quantTrSoftClip = false; P.quantTrSingleEnd = false; }
+        else return bad("EXITING because of fatal INPUT error: unrecognized option in --quantTranscriptomeSAMoutput=" + P.quantTranscriptomeSAMoutput + "\nSOLUTION: use one of the allowed values: BanSingleEnd_BanIndels_ExtendSoftclip OR BanSingleEnd OR BanSingleEnd_ExtendSoftclip\n");
+        if (P.quantTranscriptomeBAMcompression < -1) P.quantTrSAM = false;   // -2: no BAM output (Parameters.cpp:906-908)
+    }
     if (P.outReadsUnmapped != "None" && P.outReadsUnmapped != "Fastx")   // Parameters.cpp (outReadsUnmapped)
         return bad("EXITING because of FATAL INPUT ERROR: unknown value of --outReadsUnmapped: " + P.outReadsUnmapped + "\nSOLUTION: use allowed values: None OR Fastx\n");
     // SJ

@@ -87,6 +87,9 @@ def check_twopass_outputs(out, ref):
               "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab"):
         if os.path.exists(os.path.join(ref, f)):
             assert open(out + f, "rb").read() == open(os.path.join(ref, f), "rb").read(), f
+    if os.path.exists(os.path.join(ref, "Aligned.toTranscriptome.out.bam")):   # header (@SQ per transcript, @RG), references and every record incl. the drawn primary flags
+        import gzip
+        assert gzip.decompress(open(out + "Aligned.toTranscriptome.out.bam", "rb").read()) == gzip.decompress(open(os.path.join(ref, "Aligned.toTranscriptome.out.bam"), "rb").read())
     if os.path.exists(os.path.join(ref, "_STARpass1/Log.final.out")):
         assert log_counters(out + "_STARpass1/Log.final.out") == log_counters(os.path.join(ref, "_STARpass1/Log.final.out"))
     if os.path.exists(os.path.join(ref, "_STARgenome/sha256.txt")):

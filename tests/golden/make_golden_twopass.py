@@ -47,13 +47,16 @@ SCENARIOS = {
     "U_unmapped_fastx_bysjout": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--outReadsUnmapped", "Fastx", "--outFilterType", "BySJout",
                                  "--outSAMunmapped", "Within"],
     "Q_genecounts_bysjout": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--quantMode", "GeneCounts", "--outFilterType", "BySJout"],
+    "R_transcriptome_sam": ["--genomeDir", "idx", "--readFilesIn", "std_1.fq", "std_2.fq", "--quantMode", "TranscriptomeSAM", "GeneCounts"],
+    "R2_transcriptome_sam_bysjout_rg": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--quantMode", "TranscriptomeSAM", "--outFilterType", "BySJout",
+                                        "--quantTranscriptomeSAMoutput", "BanSingleEnd", "--outSAMattrRGline", "ID:x", "SM:y", "--outSAMattributes", "NH", "HI", "AS", "nM", "RG", "MC"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
 }
 KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
         "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "_STARgenome/exonInfo.tab", "_STARgenome/transcriptInfo.tab", "_STARgenome/geneInfo.tab",
-        "_STARgenome/exonGeTrInfo.tab", "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab"]
+        "_STARgenome/exonGeTrInfo.tab", "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab", "Aligned.toTranscriptome.out.bam"]
 
 
 def sha(path):
