@@ -49,6 +49,8 @@ struct HostParams {
     uint64_t runRNGseed = 777;               // seeds the primary-flag draw of Aligned.toTranscriptome.out.bam (ReadAlign.cpp:11)
     std::string quantTranscriptomeSAMoutput = "BanSingleEnd_BanIndels_ExtendSoftclip";
     bool quantTrIndel = false, quantTrSoftClip = false, quantTrSingleEnd = false;   // what Aligned.toTranscriptome.out.bam may contain
+    std::vector<std::string> outSAMheaderHD = {"-"}, outSAMheaderPG = {"-"};
+    std::string outSAMheaderCommentFile = "-";
     std::string outReadsUnmapped = "None";  // Fastx: Unmapped.out.mate1/2 (ReadAlign::outReadsUnmapped)
     std::vector<std::string> outSAMunmapped = {"None"};
     bool unmappedWithin = false, unmappedKeepPairs = false;
@@ -268,7 +270,7 @@ class OutputWriter {
     std::string bamHeaderTranscriptome() const;   // samHeaders.cpp:8-20
     // true when read i of stage 1 of BySJout is held back (ReadAlign::outFilterBySJout)
     static bool heldBySJout(const star_align_batch_t& out, uint32_t i);
-    std::string samHeader() const;                                   // samHeaders.cpp:5-113
+    std::string samHeader(bool sortedCoord = false) const;            // samHeaders.cpp:5-113
     std::string bamHeader(bool sortedCoord = false) const;           // outBAMwriteHeader, BAMfunctions.cpp:77-92 (uncompressed bytes)
     // BGZF framing (htslib bgzf.c: 0xff00-byte payload blocks, raw deflate, crc32 + isize trailer); appends to `out`
     static void bgzfCompress(const char* data, size_t n, int level, std::string& out);

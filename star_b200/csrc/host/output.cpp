@@ -591,8 +591,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
 
 std::string OutputWriter::bamHeader(bool sortedCoord) const {  // BAMfunctions.cpp:77-92
     std::string h = "BAM\001";
-    std::string text = samHeader();
-    if (sortedCoord) text.replace(0, strlen("@HD\tVN:1.4"), "@HD\tVN:1.4\tSO:coordinate");   // samHeaderSortedCoord, samHeaders.cpp:99
+    std::string text = samHeader(sortedCoord);   // samHeaderSortedCoord, samHeaders.cpp:99
     put32(h, (uint32_t)text.size());
     h += text;
     put32(h, (uint32_t)idx.chrName.size());
@@ -729,13 +728,14 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
                     if (coordYes) toCoord(scratch, 0, c.iReadAll[i] << 32);
                 }
             }
-        } else if (P.unmappedWithin && samYes) {
+        } else if (P.unmappedWithin && (samYes || trBam)) {
             bool mateMapped[2] = {false, false};
-            if (P.outSAMtype[0] == "SAM") samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
-            else {
+            if (samYes && P.outSAMtype[0] == "SAM") samUnmapped(c, i, r, nullptr, unmapType, mateMapped, sam);
+            if ((samYes && P.outSAMtype[0] != "SAM") || trBam) {   // :236-248: the unmapped record also goes to Aligned.toTranscriptome.out.bam
                 scratch.clear();
                 bamUnmapped(c, i, r, nullptr, unmapType, mateMapped, scratch);
-                if (P.outBAMunsorted) sam += scratch;
+                if (samYes && P.outBAMunsorted) sam += scratch;
+                if (trBam) *trBam += scratch;
                 if (coordYes) toCoord(scratch, 0, c.iReadAll[i] << 32);
             }
         }
@@ -757,11 +757,20 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
     }
 }
 
-std::string OutputWriter::samHeader() const {  // samHeaders.cpp:27-113
+std::string OutputWriter::samHeader(bool sortedCoord) const {  // samHeaders.cpp:27-113
     std::ostringstream h;
-    h << "@HD\tVN:1.4\n";
+    if (P.outSAMheaderHD[0] != "-") { for (size_t ii = 0; ii < P.outSAMheaderHD.size(); ii++) h << (ii ? "\t" : "") << P.outSAMheaderHD[ii]; }
+    else h << "@HD\tVN:1.4";
+    if (sortedCoord) h << "\tSO:coordinate";   // (appended to a user-given @HD line too, as the reference does)
+    h << "\n";
     for (size_t ii = 0; ii < idx.chrName.size(); ii++) h << "@SQ\tSN:" << idx.chrName[ii] << "\tLN:" << idx.chrLength[ii] << "\n";
+    if (P.outSAMheaderPG[0] != "-") { for (size_t ii = 0; ii < P.outSAMheaderPG.size(); ii++) h << (ii ? "\t" : "") << P.outSAMheaderPG[ii]; h << "\n"; }
     h << "@PG\tID:STAR\tPN:STAR\tVN:2.7.11b\tCL:" << P.commandLineFull << "\n";
+    if (P.outSAMheaderCommentFile != "-") {
+        std::ifstream com(P.outSAMheaderCommentFile);
+        std::string line1;
+        while (std::getline(com, line1)) if (line1.find_first_not_of(" \t\n\v\f\r") != std::string::npos) h << line1 << "\n";
+    }
     for (auto& l : P.outSAMattrRGlineSplit) h << "@RG\t" << l << "\n";   // samHeaders.cpp:83-85
     h << "@CO\tuser command line: " << P.commandLine << "\n";
     return h.str();

@@ -92,7 +92,7 @@ const char* kUnsupported[] = {
     "readFilesSAMattrKeep", "readFilesManifest", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
     
-    "outQSconversionAdd", "outSAMheaderHD", "outSAMheaderPG", "outSAMheaderCommentFile",
+    "outQSconversionAdd", 
     "outSAMfilter", "outSAMtlen", "outWigType", "outWigStrand",
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
@@ -173,7 +173,8 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
-    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); STR("quantTranscriptomeSAMoutput", &P.quantTranscriptomeSAMoutput);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
+    STR("outSAMheaderCommentFile", &P.outSAMheaderCommentFile); STR("quantTranscriptomeSAMoutput", &P.quantTranscriptomeSAMoutput);
     I32("quantTranscriptomeBAMcompression", &P.quantTranscriptomeBAMcompression); U64("runRNGseed", &P.runRNGseed); STR("outSAMorder", &P.outSAMorder);
     STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
     STR("outFilterType", &P.outFilterType); STR("outFilterIntronMotifs", &P.outFilterIntronMotifs); STR("outFilterIntronStrands", &P.outFilterIntronStrands);

@@ -50,13 +50,21 @@ SCENARIOS = {
     "R_transcriptome_sam": ["--genomeDir", "idx", "--readFilesIn", "std_1.fq", "std_2.fq", "--quantMode", "TranscriptomeSAM", "GeneCounts"],
     "R2_transcriptome_sam_bysjout_rg": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--quantMode", "TranscriptomeSAM", "--outFilterType", "BySJout",
                                         "--quantTranscriptomeSAMoutput", "BanSingleEnd", "--outSAMattrRGline", "ID:x", "SM:y", "--outSAMattributes", "NH", "HI", "AS", "nM", "RG", "MC"],
+    # the complete ENCODE long-RNA command line (STAR manual / ENCODE pipeline): BySJout, both quant modes, header options, both BAM files
+    "T2_encode_full": ["--genomeDir", "idx", "--readFilesIn", "std_1.fq", "std_2.fq", "--outFilterType", "BySJout", "--outSAMattributes", "NH", "HI", "AS", "NM", "MD",
+                       "--outFilterMultimapNmax", "20", "--outFilterMismatchNmax", "999", "--outFilterMismatchNoverReadLmax", "0.04", "--alignIntronMin", "20",
+                       "--alignIntronMax", "1000000", "--alignMatesGapMax", "1000000", "--alignSJoverhangMin", "8", "--alignSJDBoverhangMin", "1", "--sjdbScore", "1",
+                       "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate", "--quantMode", "TranscriptomeSAM", "GeneCounts", "--outSAMunmapped", "Within",
+                       "--outSAMstrandField", "intronMotif", "--outSAMheaderHD", "@HD", "VN:1.4", "SO:unsorted", "--outSAMheaderCommentFile", "TP/COfile.txt",
+                       "--outSAMheaderPG", "@PG", "ID:x", "PN:y", "--limitBAMsortRAM", "10000000000"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],
 }
 KEEP = ["Aligned.out.sam", "SJ.out.tab", "Log.final.out", "_STARpass1/SJ.out.tab", "_STARpass1/Log.final.out", "_STARgenome/sjdbInfo.txt",
         "_STARgenome/sjdbList.out.tab", "_STARgenome/sjdbList.fromGTF.out.tab", "_STARgenome/exonInfo.tab", "_STARgenome/transcriptInfo.tab", "_STARgenome/geneInfo.tab",
-        "_STARgenome/exonGeTrInfo.tab", "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab", "Aligned.toTranscriptome.out.bam"]
+        "_STARgenome/exonGeTrInfo.tab", "Unmapped.out.mate1", "Unmapped.out.mate2", "ReadsPerGene.out.tab", "Aligned.toTranscriptome.out.bam", "Aligned.out.bam",
+        "Aligned.sortedByCoord.out.bam"]
 
 
 def sha(path):
@@ -85,6 +93,8 @@ def main():
         f.writelines("\t".join(r[:3] + ["-" if r[3] == "+" else "+"]) + "\n" for i, r in enumerate(rows, 1) if i % 4 == 0)
     with open(os.path.join(tp, "sj_shift.tab"), "w") as f:
         f.writelines("\t".join([r[0], str(int(r[1]) + 3), str(int(r[2]) + 3), r[3]]) + "\n" for i, r in enumerate(rows, 1) if i % 5 == 0)
+    with open(os.path.join(tp, "COfile.txt"), "w") as f:
+        f.write("@CO\tLIBID:ENCLB175ZZZ\n\n@CO\tREFID:ENCFF001RGS\n")
     for name, args in SCENARIOS.items():
         out = os.path.join(tmp, "run_" + name) + "/"
         os.makedirs(out)
