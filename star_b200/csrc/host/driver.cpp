@@ -27,6 +27,10 @@
 
 namespace starhost {
 
+// what the reference sends to stdout goes to <prefix>Log.std.out when stdout carries alignments (--outStd SAM | BAM_*; Parameters.cpp:385-391)
+static std::ostream* g_logStd = &std::cout;
+static std::ofstream g_logStdFile;
+
 static std::string timeMonthDayTime(time_t t) {
     char b[100];
     strftime(b, 80, "%b %d %H:%M:%S", localtime(&t));
@@ -175,7 +179,9 @@ static bool readShardJunctions(const std::string& path, std::vector<Junction>& s
 // bin on disk; one stable in-memory sort gives the same sequence.
 static void writeSortedBam(const HostParams& P, const OutputWriter& W, const std::vector<std::string>& coordBlobs, std::vector<CoordRec>& coordIndex, int nT) {
     std::stable_sort(coordIndex.begin(), coordIndex.end(), [](const CoordRec& a, const CoordRec& b) { return a.alignG != b.alignG ? a.alignG < b.alignG : a.key < b.key; });
-    std::ofstream cb(P.outFileNamePrefix + "Aligned.sortedByCoord.out.bam", std::ios::binary);
+    std::ofstream cbFile;
+    if (P.outStd != "BAM_SortedByCoordinate") cbFile.open(P.outFileNamePrefix + "Aligned.sortedByCoord.out.bam", std::ios::binary);   // Parameters.cpp:642-644
+    std::ostream& cb = P.outStd == "BAM_SortedByCoordinate" ? static_cast<std::ostream&>(std::cout) : cbFile;
     { std::string z; const std::string h = W.bamHeader(true); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); cb.write(z.data(), z.size()); }
     const size_t nRec = coordIndex.size();
     const size_t batch = 1u << 16;   // records per compression task
@@ -193,6 +199,7 @@ static void writeSortedBam(const HostParams& P, const OutputWriter& W, const std
         for (int t = 0; t < nT; t++) cb.write(z[t].data(), z[t].size());
     }
     size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); cb.write(e, ne);
+    cb.flush();
 }
 // sharded runs: records + keys of one shard (and stage) for the merge
 static void writeCoordShard(const std::string& path, const std::vector<std::string>& coordBlobs, const std::vector<CoordRec>& coordIndex) {
@@ -238,9 +245,10 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     W.trModel = stage.trModel;
     const bool trYes = stage.trModel != nullptr;
     std::ofstream trOut;
+    std::ostream& trO = P.outStd == "BAM_Quant" ? static_cast<std::ostream&>(std::cout) : trOut;   // Parameters.cpp:908-909
     if (trYes) {   // Aligned.toTranscriptome.out.bam (Parameters.cpp:911-914)
-        trOut.open(P.outFileNamePrefix + "Aligned.toTranscriptome.out" + stage.streamSuffix + ".bam", firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
-        if (P.gpuShardIndex == 0 && firstStage) { std::string z; const std::string h = W.bamHeaderTranscriptome(); OutputWriter::bgzfCompress(h.data(), h.size(), P.quantTranscriptomeBAMcompression, z); trOut.write(z.data(), z.size()); }
+        if (P.outStd != "BAM_Quant") trOut.open(P.outFileNamePrefix + "Aligned.toTranscriptome.out" + stage.streamSuffix + ".bam", firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (P.gpuShardIndex == 0 && firstStage) { std::string z; const std::string h = W.bamHeaderTranscriptome(); OutputWriter::bgzfCompress(h.data(), h.size(), P.quantTranscriptomeBAMcompression, z); trO.write(z.data(), z.size()); }
     }
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
     std::ofstream samOut;
@@ -251,11 +259,13 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     std::ofstream unmOut[2];
     if (unmYes) for (unsigned m = 0; m < P.readNmates; m++)
         unmOut[m].open(P.outFileNamePrefix + "Unmapped.out" + stage.streamSuffix + ".mate" + std::to_string(m + 1), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+    const bool samToStdout = (P.outStd == "SAM" && streamYes && !bamYes) || (P.outStd == "BAM_Unsorted" && bamYes);   // Parameters.cpp:634-636, 669-670
+    std::ostream& samO = samToStdout ? static_cast<std::ostream&>(std::cout) : samOut;
     if (streamYes) {
-        samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (!samToStdout) samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
         if (P.gpuShardIndex == 0 && firstStage) {   // shards > 0 write records only; the merge concatenates in shard order
-            if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samOut.write(z.data(), z.size()); }
-            else samOut << W.samHeader();
+            if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samO.write(z.data(), z.size()); }
+            else samO << W.samHeader();
         }
     }
 
@@ -356,11 +366,11 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 msFormat += msSince(tf0);
                 auto tw0 = now();
                 for (int t = 0; t < nT; t++) {
-                    if (streamYes) samOut.write(sam[t].data(), sam[t].size());
+                    if (streamYes) samO.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
                     if (stage.geneModel) stage.geneCounts.add(gcs[t]);
-                    if (trYes) trOut.write(trb[t].data(), trb[t].size());
+                    if (trYes) trO.write(trb[t].data(), trb[t].size());
                     if (unmYes) for (unsigned m = 0; m < P.readNmates; m++) unmOut[m].write(unm[2 * t + m].data(), unm[2 * t + m].size());
                     if (stage.bySJstage == 1) {
                         stage.sjAll.insert(stage.sjAll.end(), hold[t].sjAll.begin(), hold[t].sjAll.end());
@@ -434,14 +444,14 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     readerThread.join();
     if (runRc) { err = runErr; return runRc; }
     if (!outErr.empty()) { err = outErr; return STAR_EXIT_BUG; }
-    if (trYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); trOut.write(e, ne); }
-    if (bamYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samOut.write(e, ne); }   // (sharded runs: the merge appends it)
-    if (streamYes) samOut.close();
+    if (trYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); trO.write(e, ne); trO.flush(); }
+    if (bamYes && P.gpuShardCount == 1 && lastStage) { size_t ne; const char* e = OutputWriter::bgzfEofBlock(ne); samO.write(e, ne); }   // (sharded runs: the merge appends it)
+    if (streamYes) { samO.flush(); if (!samToStdout) samOut.close(); }
     if (coordYes && P.gpuShardCount > 1) {   // one shard: the (unsorted) records and their keys go to the merge, which sorts the whole run
         writeCoordShard(P.outFileNamePrefix + "coord" + stage.streamSuffix + ".bin", coordBlobs, coordIndex);
     } else if (coordYes && lastStage) {
         time_t ts; time(&ts);
-        std::cout << timeMonthDayTime(ts) << " ..... started sorting BAM\n" << std::flush;
+        *g_logStd << timeMonthDayTime(ts) << " ..... started sorting BAM\n" << std::flush;
         writeSortedBam(P, W, coordBlobs, coordIndex, nT);
     }
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
@@ -467,9 +477,15 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     std::ofstream logMain(P.outFileNamePrefix + "Log.out");
     if (logMain.fail())
         return exitWithError("EXITING because of FATAL ERROR: could not create output file: " + P.outFileNamePrefix + "Log.out\nSOLUTION: check if the path " + P.outFileNamePrefix + " exists and you have permissions to write there\n", STAR_EXIT_PARAMETER, nullptr);
+    g_logStd = &std::cout;
+    if (P.outStd != "Log") {
+        if (g_logStdFile.is_open()) g_logStdFile.close();
+        g_logStdFile.open(P.outFileNamePrefix + "Log.std.out");
+        g_logStd = &g_logStdFile;
+    }
     logMain << "STAR version=2.7.11b (star-b200 GPU alignment hot path)\n##### Command Line:\n" << P.commandLine << "\n##### Final effective command line:\n" << P.commandLineFull << "\n" << std::flush;
     for (const std::string& ip : P.ignoredParams) logMain << "star-b200: --" << ip << " is accepted and has no effect (no host-side buffer / temporary-file limits)\n";
-    std::cout << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
+    *g_logStd << "\t" << P.commandLine << "\n\tSTAR version: 2.7.11b (star-b200)\n" << timeMonthDayTime(stats.timeStart) << " ..... started STAR run\n" << std::flush;
 
     if (P.runMode == "genomeGenerate") {   // STAR.cpp:120-125
         rc = genomeGenerate(P, eng, logMain, err);
@@ -479,7 +495,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     }
     {
         time_t t; time(&t);
-        std::cout << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;
+        *g_logStd << timeMonthDayTime(t) << " ..... loading genome\n" << std::flush;
     }
     LoadedIndex idx;
     std::string glog;
@@ -528,7 +544,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         Stats st1;
         st1.timeStart = stats.timeStart;
         time(&st1.timeStartMap);
-        std::cout << timeMonthDayTime(st1.timeStartMap) << " ..... started 1st pass mapping\n" << std::flush;
+        *g_logStd << timeMonthDayTime(st1.timeStartMap) << " ..... started 1st pass mapping\n" << std::flush;
         std::vector<Junction> sj1;
         StageState stage1;
         rc = mapPass(P1, idx, eng, ectx, st1, sj1, logMain, err, stage1);
@@ -540,13 +556,13 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
             OutputWriter::collapseSJ(sj1, e2);
             if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
             writeShardBin(P.twoPassDir + "shard.bin", st1, sj1);
-            std::cout << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+            *g_logStd << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
             return 0;
         }
         OutputWriter W1(P1, idx);
         std::string e2 = W1.writeSJ(sj1, P.twoPassDir + "SJ.out.tab");
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
-        std::cout << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass mapping\n" << std::flush;
+        *g_logStd << timeMonthDayTime(st1.timeFinish) << " ..... finished 1st pass mapping\n" << std::flush;
         W1.writeLogFinal(st1, P.twoPassDir + "Log.final.out");
     }   // (phase 2: the 1st pass was a separate run; star_b200.dist gathered the junctions of all shards into _STARpass1/SJ.out.tab)
     if (P.twoPassYes) {
@@ -556,7 +572,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         if (rc) return exitWithError(std::string("EXITING because of FATAL ERROR: engine initialisation failed: ") + eng->last_error() + "\n", rc, &logMain);
     }
     time(&stats.timeStartMap);
-    std::cout << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
+    *g_logStd << timeMonthDayTime(stats.timeStartMap) << " ..... started mapping\n" << std::flush;
     std::vector<Junction> allSJ;
     StageState stage;
     OutputWriter W(P, idx);
@@ -588,7 +604,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         saveStage1(stateFile, stats, allSJ, stage.held);
         if (stage.geneModel) stage.geneCounts.write(geneModel, stats, P.outFileNamePrefix + "bysj_stage1.ReadsPerGene.tab");
         writeShardBin(P.outFileNamePrefix + "bysj_sjall.bin", stats, stage.sjAll);
-        std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished 1st BySJout stage of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+        *g_logStd << timeMonthDayTime(stats.timeFinish) << " ..... finished 1st BySJout stage of shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
         return 0;
     }
     if (!rc && bySJout && P.gpuBySJoutPhase == 2) {   // ... and come back from every shard (star_b200.dist: bysj_gather<r>.bin)
@@ -617,7 +633,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
     if (rc) return exitWithError(err, rc, &logMain);
     {
         time_t tFinishMap; time(&tFinishMap);
-        std::cout << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
+        *g_logStd << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n" << std::flush;
         logMain << timeMonthDayTime(tFinishMap) << " ..... finished mapping\n";
     }
     time(&stats.timeFinish);
@@ -629,7 +645,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         OutputWriter::collapseSJ(allSJ, e2);
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
         writeShardBin(P.outFileNamePrefix + "shard.bin", stats, allSJ);
-        std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
+        *g_logStd << timeMonthDayTime(stats.timeFinish) << " ..... finished shard " << P.gpuShardIndex << " of " << P.gpuShardCount << "\n" << std::flush;
         logMain << "ALL DONE!\n" << std::flush;
         return 0;
     }
@@ -638,7 +654,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         if (!e2.empty()) return exitWithError(e2, STAR_EXIT_BUG, &logMain);
     }
     W.writeLogFinal(stats, P.outFileNamePrefix + "Log.final.out");
-    std::cout << timeMonthDayTime(stats.timeFinish) << " ..... finished successfully\n" << std::flush;
+    *g_logStd << timeMonthDayTime(stats.timeFinish) << " ..... finished successfully\n" << std::flush;
     logMain << "ALL DONE!\n" << std::flush;
     return 0;
 }

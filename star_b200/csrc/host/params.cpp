@@ -281,7 +281,10 @@ int finalizeParams(HostParams& P, std::string& err) {
     }
     if (P.genomeLoad != "NoSharedMemory")
         return bad("EXITING because of fatal input ERROR: --genomeLoad " + P.genomeLoad + " is not supported: the index is resident in GPU HBM instead of host shared memory\n");
-    if (P.outStd != "Log") return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not supported by star-b200 (only Log)\n");
+    if (P.outStd != "Log" && P.outStd != "SAM" && P.outStd != "BAM_Unsorted" && P.outStd != "BAM_SortedByCoordinate" && P.outStd != "BAM_Quant")   // Parameters.cpp:385-396
+        return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not a valid value of the parameter\nSOLUTION: provide a valid value fot outStd: Log / SAM / BAM_Unsorted / BAM_SortedByCoordinate");
+    if (P.outStd != "Log" && P.gpuShardCount > 1)
+        return bad("EXITING because of fatal input ERROR: --outStd " + P.outStd + " is not supported for sharded (multi-GPU) runs: the shards' outputs are merged from files\n");
     if (P.readFilesIn.size() > 2 || P.readFilesIn.empty() || P.readFilesIn[0] == "Read1")
         return bad("EXITING: because of fatal input ERROR: --readFilesIn must name 1 or 2 FASTQ/FASTA files\n");
     P.readFilesNames.assign(P.readFilesIn.size(), {});

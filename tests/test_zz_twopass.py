@@ -87,3 +87,24 @@ def test_housekeeping_parameters_are_accepted(oracle, golden, tmp_path):
     assert "--limitBAMsortRAM is accepted and has no effect" in open(out + "Log.out").read()
     r = subprocess.run(cmd + ["--twopassMode", "Basic"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
     assert r.returncode == 102 and "cannot be used with shared memory genome" in r.stderr
+
+
+def test_outstd_streams_alignments_to_stdout(oracle, golden, tmp_path):
+    """--outStd SAM | BAM_Unsorted | BAM_SortedByCoordinate (Parameters.cpp:385-391, 634-670): the alignments go to stdout, the messages the
+    reference prints to stdout go to Log.std.out, the file is not created.  (Checked against the reference's own stdout when this was written.)"""
+    import gzip
+    base = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "se_1.fq"), "--runThreadN", "2"]
+    ref = [l for l in open(os.path.join(golden, "ref_se", "Aligned.out.sam"), "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+    out = str(tmp_path / "a") + "/"
+    r = subprocess.run(base + ["--outFileNamePrefix", out, "--outStd", "SAM"], stdout=subprocess.PIPE, check=True)
+    assert [l for l in r.stdout.split(b"\n") if l and not l.startswith(b"@")] == ref
+    assert r.stdout.startswith(b"@HD\tVN:1.4\n") and os.path.exists(out + "Log.std.out") and not os.path.exists(out + "Aligned.out.sam")
+    assert b"started mapping" in open(out + "Log.std.out", "rb").read()
+    out = str(tmp_path / "b") + "/"
+    r = subprocess.run(base + ["--outFileNamePrefix", out, "--outStd", "BAM_Unsorted", "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate"], stdout=subprocess.PIPE, check=True)
+    d = gzip.decompress(r.stdout)
+    assert d[:4] == b"BAM\x01" and not os.path.exists(out + "Aligned.out.bam") and os.path.exists(out + "Aligned.sortedByCoord.out.bam")
+    names = set(l.split(b"\t")[0] for l in ref)
+    assert all(n in d for n in list(names)[:20])
+    r = subprocess.run(base + ["--outFileNamePrefix", out, "--outStd", "Nonsense"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 102
