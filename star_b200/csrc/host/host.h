@@ -26,7 +26,8 @@ struct HostParams {
     std::string genomeLoad = "NoSharedMemory";
     std::vector<std::string> readFilesIn = {"Read1", "Read2"};
     std::vector<std::vector<std::string>> readFilesNames;   // [mate][file]: --readFilesIn a1,a2 b1,b2 (Parameters_readFilesInit.cpp:43-62)
-    std::string readFilesPrefix = "-";
+    std::string readFilesPrefix = "-", readFilesManifest = "-";
+    bool rgFromManifest = false;             // read groups came from --readFilesManifest: @RG header lines, RG tag only on request
     std::vector<std::string> ignoredParams;  // accepted reference parameters without effect here (resource limits, temporary directories)
     std::vector<std::string> readFilesCommand = {"-"};
     long long readMapNumber = -1;

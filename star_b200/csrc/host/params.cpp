@@ -6,6 +6,7 @@
 // rejected with a clear message when given: config breadth is outside the hot-path scope.
 #include <cmath>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <limits>
 #include <sstream>
@@ -89,7 +90,7 @@ const char* kUnsupported[] = {
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "varVCFfile", "readFilesType",
-    "readFilesSAMattrKeep", "readFilesManifest", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
+    "readFilesSAMattrKeep", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
     
     "outQSconversionAdd", 
@@ -170,7 +171,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     U64("outFilterMultimapNmax", &h.outFilterMultimapNmax); I32("outFilterScoreMin", &h.outFilterScoreMin);
     DBL("outFilterScoreMinOverLread", &h.outFilterScoreMinOverLread); U64("outFilterMatchNmin", &h.outFilterMatchNmin);
     DBL("outFilterMatchNminOverLread", &h.outFilterMatchNminOverLread); U64("outSAMmultNmax", &h.outSAMmultNmax);
-    STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix);
+    STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix); STR("readFilesManifest", &P.readFilesManifest);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
     VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
@@ -285,6 +286,34 @@ int finalizeParams(HostParams& P, std::string& err) {
         return bad("EXITING because of FATAL PARAMETER error: outStd=" + P.outStd + " is not a valid value of the parameter\nSOLUTION: provide a valid value fot outStd: Log / SAM / BAM_Unsorted / BAM_SortedByCoordinate");
     if (P.outStd != "Log" && P.gpuShardCount > 1)
         return bad("EXITING because of fatal input ERROR: --outStd " + P.outStd + " is not supported for sharded (multi-GPU) runs: the shards' outputs are merged from files\n");
+    if (P.readFilesManifest != "-") {   // Parameters_readFilesInit.cpp:96-137: Read1 <tab> Read2 (or -) <tab> read group line, one input file (pair) per line
+        std::ifstream rfM(P.readFilesManifest);
+        if (rfM.fail()) return bad("EXITING because of fatal INPUT error: could not open input file " + P.readFilesManifest + "\nSOLUTION: check the path and permissions for readFilesManifest = " + P.readFilesManifest + "\n");
+        std::string m1, m2, line;
+        std::vector<std::string> rg;
+        bool first = true;
+        while (std::getline(rfM, line)) {
+            if (line.find_first_not_of(" \t") == std::string::npos) continue;
+            const size_t t1 = line.find('\t'), t2 = t1 == std::string::npos ? t1 : line.find('\t', t1 + 1);
+            if (t1 == std::string::npos || t2 == std::string::npos) {
+                err = "EXITING because of FATAL INPUT FILE error: readFileManifest file " + P.readFilesManifest + " has to contain at least 3 tab separated columns\nSOLUTION: fix the formatting of the readFileManifest file: Read1 <tab> Read2 <tab> ReadGroup. For single-end reads, use - in the 2nd column.\n";
+                return STAR_EXIT_INPUT_FILES;
+            }
+            m1 += (first ? "" : ",") + line.substr(0, t1);
+            m2 += (first ? "" : ",") + line.substr(t1 + 1, t2 - t1 - 1);
+            std::string g = line.substr(t2 + 1);
+            if (g.substr(0, 3) != "ID:") g.insert(0, "ID:");
+            if (!first) rg.push_back(",");
+            size_t a = 0;
+            for (;;) { const size_t b = g.find('\t', a); rg.push_back(g.substr(a, b == std::string::npos ? b : b - a)); if (b == std::string::npos) break; a = b + 1; }
+            first = false;
+        }
+        if (first) return bad("EXITING because of FATAL INPUT FILE error: readFileManifest file " + P.readFilesManifest + " is empty\n");
+        P.readFilesIn = {m1};
+        if (m2.empty() || m2.back() != '-') P.readFilesIn.push_back(m2);   // (the reference looks at the last character of the first Read2 entry)
+        P.outSAMattrRGline = rg;
+        P.rgFromManifest = true;
+    }
     if (P.readFilesIn.size() > 2 || P.readFilesIn.empty() || P.readFilesIn[0] == "Read1")
         return bad("EXITING: because of fatal input ERROR: --readFilesIn must name 1 or 2 FASTQ/FASTA files\n");
     P.readFilesNames.assign(P.readFilesIn.size(), {});
@@ -446,7 +475,7 @@ int finalizeParams(HostParams& P, std::string& err) {
         P.outSAMattrRG = P.outSAMattrRGs[0];
         bool has = false;
         for (int c : P.outSAMattrOrder) if (c == 10) has = true;
-        if (!has) P.outSAMattrOrder.push_back(10);
+        if (!has && !P.rgFromManifest) P.outSAMattrOrder.push_back(10);   // (Parameters_samAttributes.cpp:201-205: only --outSAMattrRGline adds the tag by itself)
     }
     // 2-pass and on-the-fly junction insertion: Parameters.cpp:779-825, 1000-1035 (the directories are made by the run driver)
     if (P.userSet.count("twopass1readsN") && P.twopassMode == "None")

@@ -108,3 +108,26 @@ def test_outstd_streams_alignments_to_stdout(oracle, golden, tmp_path):
     assert all(n in d for n in list(names)[:20])
     r = subprocess.run(base + ["--outFileNamePrefix", out, "--outStd", "Nonsense"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 102
+
+
+def test_read_files_manifest(oracle, golden, tmp_path):
+    """--readFilesManifest (Parameters_readFilesInit.cpp:96-137): files and read groups from a table; @RG header lines, RG tags only when asked for.
+    (Equal to the reference's output when this was written; here: records equal the plain run's, header and tags as specified.)"""
+    lines = open(os.path.join(golden, "se_1.fq")).read().split("\n")
+    a, b = str(tmp_path / "sA.fq"), str(tmp_path / "sB.fq")
+    open(a, "w").write("\n".join(lines[:200]) + "\n")
+    open(b, "w").write("\n".join(lines[200:]))
+    man = str(tmp_path / "man.tsv")
+    open(man, "w").write("%s\t-\tID:grpA\tSM:x\n\n%s\t-\tgrpB\tSM:y\tPL:ill\n" % (a, b))
+    out = str(tmp_path / "o") + "/"
+    subprocess.check_call([oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesManifest", man, "--outFileNamePrefix", out, "--runThreadN", "2"], stdout=subprocess.DEVNULL)
+    sam = open(out + "Aligned.out.sam").read()
+    assert "@RG\tID:grpA\tSM:x\n@RG\tID:grpB\tSM:y\tPL:ill\n" in sam and "RG:Z:" not in sam
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(golden, "ref_se", "Aligned.out.sam"))
+    out = str(tmp_path / "p") + "/"
+    subprocess.check_call([oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesManifest", man, "--outFileNamePrefix", out, "--outSAMattributes", "NH", "HI", "RG"], stdout=subprocess.DEVNULL)
+    body = [l for l in open(out + "Aligned.out.sam").read().split("\n") if l and not l.startswith("@")]
+    assert body[0].endswith("RG:Z:grpA") and body[-1].endswith("RG:Z:grpB")
+    bad = str(tmp_path / "bad.tsv")
+    open(bad, "w").write("x.fq\t-\n")
+    assert subprocess.run([oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesManifest", bad, "--outFileNamePrefix", out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 104

@@ -64,8 +64,13 @@ maybe(.3,"--outSAMunmapped",["Within"],["Within","KeepPairs"],["None"])
 maybe(.3,"--outSAMattributes",["NH","HI","AS","nM","NM","MD","jM","jI","MC"],["All"],["Standard"],["NH","HI","XS"])
 maybe(.15,"--twopassMode","Basic")
 maybe(.2,"--outSJfilterReads","All","Unique")
+maybe(.25,"--outReadsUnmapped","Fastx")
+qm=random.random()<0.35
 ds=ch(("std",["std_1.fq","std_2.fq"]),("hard",["hard_1.fq","hard_2.fq"]),("se",["se_1.fq"]),("hard1",["hard_1.fq"]))
 idx=ch("idx","idx0")
+if qm:
+    idx="idx"; opts.extend(["--quantMode"]+ch(["GeneCounts"],["TranscriptomeSAM"],["TranscriptomeSAM","GeneCounts"]))
+    if random.random()<0.4: opts.extend(["--quantTranscriptomeSAMoutput",ch("BanSingleEnd","BanSingleEnd_ExtendSoftclip","BanSingleEnd_BanIndels_ExtendSoftclip")])
 args=["--genomeDir",idx,"--readFilesIn"]+ds[1]+opts
 res=[]
 for tag,b,nt in (("fm_ref","/root/repo/oracle/_ref/STAR","1"),("fm_our","/root/repo/oracle/_build/star_cli_oracle","3")):
@@ -79,6 +84,15 @@ def logc(fn):
     try: return [l for l in open(fn) if "|" in l and not any(k in l for k in ("Started","Finished","speed"))]
     except Exception: return None
 r="fm_ref%d/"%seed; o="fm_our%d/"%seed
-ok = res[0][0]==res[1][0] and (res[0][0]!=0 or (body(r+"Aligned.out.sam")==body(o+"Aligned.out.sam") and open(r+"SJ.out.tab").read()==open(o+"SJ.out.tab").read() and logc(r+"Log.final.out")==logc(o+"Log.final.out")))
+import gzip
+def extra():
+    for f in ("ReadsPerGene.out.tab","Unmapped.out.mate1","Unmapped.out.mate2"):
+        if os.path.exists(r+f) != os.path.exists(o+f): return False
+        if os.path.exists(r+f) and open(r+f,"rb").read()!=open(o+f,"rb").read(): return False
+    f="Aligned.toTranscriptome.out.bam"
+    if os.path.exists(r+f) != os.path.exists(o+f): return False
+    if os.path.exists(r+f) and gzip.decompress(open(r+f,"rb").read())!=gzip.decompress(open(o+f,"rb").read()): return False
+    return True
+ok = res[0][0]==res[1][0] and (res[0][0]!=0 or (extra() and body(r+"Aligned.out.sam")==body(o+"Aligned.out.sam") and open(r+"SJ.out.tab").read()==open(o+"SJ.out.tab").read() and logc(r+"Log.final.out")==logc(o+"Log.final.out")))
 print("seed",seed,"OK" if ok else "MISMATCH",res[0][0],res[1][0],ds[0],idx," ".join(opts), "" if ok else res[1][1], flush=True)
 if ok: shutil.rmtree(r,ignore_errors=True); shutil.rmtree(o,ignore_errors=True)
