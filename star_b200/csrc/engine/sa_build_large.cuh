@@ -11,7 +11,8 @@
 //             read ranks already refined in this round, which only sharpens its keys (rank[a] < rank[b] always implies suffix a <
 //             suffix b).  Stops when a round finds nothing active.
 //   output    positions holding a base, in order, compacted batch by batch into one array and packed.
-// HBM at n positions: text n + rank 8n + order 8n + max(4 x 8 x cap work buffers, 8 x nSA) bytes (GRCh38: ~155 GB with cap = 7e8).
+// HBM at n positions: text n + order 8n + max(rank 8n + 4 x 8 x cap work buffers + sort scratch, 8 x nSA) bytes, plus the caller's genome and
+// packed output (GRCh38 with cap = 7e8: ~170 GB at the peak of the sort rounds, ~130 GB while packing).
 // Limits: n < 2^33, cap <= 2^31, no single 4-mer bin and no single tied group larger than cap.
 // Written against the SA_* macros of sa_build_impl.cuh plus SA_SELECT_IF / SA_MAX_SCAN64 / SA_SORT_PAIRS64.
 #pragma once
@@ -209,8 +210,8 @@ inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u
         }
     }
     SA_SYNC();
-    SA_FREE(keyA); SA_FREE(keyB); SA_FREE(valB); SA_FREE(hist);
-    keyA = keyB = valB = nullptr;
+    SA_FREE(keyA); SA_FREE(keyB); SA_FREE(valB); SA_FREE(hist); SA_FREE(rank);   // (the order is final: the ranks are not needed any more)
+    keyA = keyB = valB = nullptr; rank = nullptr;
     if (!rc) {
         sa64 = (u64*)SA_ALLOC((nSA + 64) * 8);
         if (!sa64) rc = 3;
