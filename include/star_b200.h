@@ -56,7 +56,7 @@ typedef struct star_params {
     /* seeding: ReadAlign_mapOneRead.cpp, ReadAlign_storeAligns.cpp */
     uint64_t seedSearchStartLmax;
     double   seedSearchStartLmaxOverLread;
-    uint64_t seedSearchLmax;          /* must be 0 (default); the fixed-length search is not built */
+    uint64_t seedSearchLmax;          /* 0 (default): off; > 0: one more search of at most this length from every start */
     uint64_t seedMapMin;
     uint64_t seedSplitMin;
     uint64_t seedMultimapNmax;

@@ -1389,6 +1389,12 @@ struct ReadAlign {
                             if (fatal) return;
                         }
                     }
+                    if (P.seedSearchLmax > 0) {   // :81-87 one more search of fixed maximum length from every start
+                        uint Shift = iDir == 0 ? (splitR[0][ip] + istart * Lstart) : (splitR[0][ip] + splitR[1][ip] - istart * Lstart - 1);
+                        uint seedLength = std::min((uint)P.seedSearchLmax, iDir == 0 ? (splitR[0][ip] + splitR[1][ip] - Shift) : (Shift + 1));
+                        maxMappableLength2strands(Shift, seedLength, iDir, 0, mapGen.nSA - 1, L, splitR[2][ip]);
+                        if (fatal) return;
+                    }
                 }
             }
         }

@@ -325,6 +325,12 @@ __global__ void __launch_bounds__(128) seed_search_kernel(const __grid_constant_
                             if (st.flags) break;
                         }
                     }
+                    if (__builtin_expect(P.seedSearchLmax > 0, 0) && !st.flags) {   // ReadAlign_mapOneRead.cpp:81-87: fixed-length search from every start (off by default)
+                        const u64 Shift = iDir == 0 ? (ps + istart * Lstart) : (ps + pl - istart * Lstart - 1);
+                        const u64 room = iDir == 0 ? (ps + pl - Shift) : (Shift + 1);
+                        u64 L;
+                        maxMappableLength2strands(c, st, P, Shift, P.seedSearchLmax < room ? P.seedSearchLmax : room, iDir, L, splitFrag[ip]);
+                    }
                     if (st.flags) break;
                 }
                 if (st.flags) break;

@@ -304,6 +304,12 @@ SB_DEV void warpSeedRead(const W& w, const DevIndex& ix, const star_params_t& P,
                         if (st.flags) break;
                     }
                 }
+                if (P.seedSearchLmax > 0 && !st.flags) {   // ReadAlign_mapOneRead.cpp:81-87: fixed-length search from every start (off by default)
+                    const u64 Shift = iDir == 0 ? (ps + istart * Lstart) : (ps + pl - istart * Lstart - 1);
+                    const u64 room = iDir == 0 ? (ps + pl - Shift) : (Shift + 1);
+                    u64 L;
+                    warpMaxMappableLength2strands<W>(w, ix, P, R, st, Shift, P.seedSearchLmax < room ? P.seedSearchLmax : room, iDir, L, splitFrag[ip]);
+                }
                 if (st.flags) break;
             }
             if (st.flags) break;

@@ -327,7 +327,6 @@ int finalizeParams(HostParams& P, std::string& err) {
                        " is not equal to that for mate" + std::to_string(imate - 1) + "=" + std::to_string(P.readFilesNames[imate - 1].size()) + "\nMake sure that the number of files in --readFilesIn is the same for both mates\n");
     }
     P.readNmates = (unsigned)P.readFilesIn.size();
-    if (h.seedSearchLmax != 0) return bad("EXITING because of fatal PARAMETERS error: --seedSearchLmax >0 is not supported by star-b200\n");
     if (P.outFilterType != "Normal" && P.outFilterType != "BySJout")   // Parameters.cpp:1176-1190
         return bad("EXITING because of FATAL input ERROR: unknown value of parameter outFilterType: " + P.outFilterType + "\nSOLUTION: re-run STAR with --outFilterType Normal OR BySJout\n");
     if (P.outFilterType == "BySJout" && P.gpuShardCount > 1 && P.gpuBySJoutPhase == 0 && P.gpuTwoPassPhase != 1)   // (the 1st pass of a 2-pass run does not filter)

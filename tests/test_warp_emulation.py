@@ -24,13 +24,17 @@ def _emul():
     return lib
 
 
-@pytest.mark.parametrize("name,n_take", [("std", 250), ("hard", 70), ("se", 250)])
-def test_emulated_warp_seed_search_equals_oracle_pieces(oracle, lib, golden, name, n_take):
+@pytest.mark.parametrize("name,n_take,lmax", [("std", 250, 0), ("hard", 70, 0), ("se", 250, 0), ("hard", 40, 25)])
+def test_emulated_warp_seed_search_equals_oracle_pieces(oracle, lib, golden, name, n_take, lmax):
+    """lmax > 0: --seedSearchLmax, the extra fixed-length search from every start (ReadAlign_mapOneRead.cpp:81-87)."""
     import star_b200 as sb
+    from star_b200 import capi
     files = [os.path.join(golden, name + "_1.fq")] + ([os.path.join(golden, name + "_2.fq")] if name != "se" else [])
     mates = [cf.read_fastq_seqs(f)[:n_take] for f in files]
     seq, off, n, nm = sb.pack_reads(mates)
-    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    params = capi.default_params(lib)
+    params.seedSearchLmax = lmax
+    idx = sb.Index(lib, os.path.join(golden, "idx"), params=params)
     oe = oc.OracleEngine(oracle, idx)
     _, _, st_o, (pc_off_o, pc_o) = oe.map_chunk(seq, off, n, nm, dump=True)
     batch = oe._batch(seq, off, n, nm)
