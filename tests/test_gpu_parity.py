@@ -120,7 +120,6 @@ def test_cli_matches_reference_golden(lib, golden, tmp_path, name, extra):
     ("std", ["--alignEndsType", "Extend5pOfRead1", "--outSAMprimaryFlag", "AllBestScore"]),
     ("std", ["--outFilterMultimapNmax", "3", "--winAnchorMultimapNmax", "100", "--outSAMmultNmax", "2"]),
     ("hard", ["--outFilterMismatchNoverLmax", "0.1", "--scoreGenomicLengthLog2scale", "0", "--alignSJoverhangMin", "8"]),
-    ("hard", ["--seedSearchLmax", "25", "--seedSearchStartLmax", "30"]),   # the fixed-length search from every start (off by default)
 ])
 def test_cli_option_sets_match_oracle_cli(lib, oracle, golden, tmp_path, base, extra):
     """Option sets without committed goldens: the drop-in CLI on the GPU vs the same host code driven by the oracle engine

@@ -131,3 +131,19 @@ def test_read_files_manifest(oracle, golden, tmp_path):
     bad = str(tmp_path / "bad.tsv")
     open(bad, "w").write("x.fq\t-\n")
     assert subprocess.run([oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesManifest", bad, "--outFileNamePrefix", out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 104
+
+
+@pytest.mark.gpu
+def test_gpu_seed_search_lmax_matches_oracle_cli(lib, oracle, golden, tmp_path):
+    """--seedSearchLmax on the GPU (the extra fixed-length search of seed_search_kernel) vs the same host code driven by the oracle
+    (the oracle equals the reference for this option: tools/fuzz_mapping_params.py runs)."""
+    outs = []
+    for tag, binary in (("gpu", os.path.join(ROOT, "star_b200", "bin", "STAR")), ("ora", oc.ORACLE_CLI)):
+        out = str(tmp_path / tag) + "/"
+        os.makedirs(out)
+        subprocess.check_call([binary, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "hard_1.fq"), os.path.join(golden, "hard_2.fq"),
+                               "--outFileNamePrefix", out, "--runThreadN", "2", "--seedSearchLmax", "25", "--seedSearchStartLmax", "30"], stdout=subprocess.DEVNULL)
+        outs.append(out)
+    assert cf.sam_body(outs[0] + "Aligned.out.sam") == cf.sam_body(outs[1] + "Aligned.out.sam")
+    assert open(outs[0] + "SJ.out.tab", "rb").read() == open(outs[1] + "SJ.out.tab", "rb").read()
+    assert cf.log_counters(outs[0] + "Log.final.out") == cf.log_counters(outs[1] + "Log.final.out")
