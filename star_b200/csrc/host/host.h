@@ -52,6 +52,8 @@ struct HostParams {
     bool quantTrIndel = false, quantTrSoftClip = false, quantTrSingleEnd = false;   // what Aligned.toTranscriptome.out.bam may contain
     std::vector<std::string> outSAMheaderHD = {"-"}, outSAMheaderPG = {"-"};
     std::string outSAMheaderCommentFile = "-";
+    int32_t outSAMtlen = 1;                 // 2: leftmost base of any mate to rightmost base of any mate, + for the leftmost mate (BAM records; ReadAlign_alignBAM.cpp:84-88)
+    int32_t outQSconversionAdd = 0;         // added to every quality value, clamped to 33..126 (readLoad.cpp:71-81)
     std::string outReadsUnmapped = "None";  // Fastx: Unmapped.out.mate1/2 (ReadAlign::outReadsUnmapped)
     std::vector<std::string> outSAMunmapped = {"None"};
     bool unmappedWithin = false, unmappedKeepPairs = false;

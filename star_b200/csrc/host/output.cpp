@@ -576,8 +576,15 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
         if (nMates > 1) {
             put32(bam, tr.Chr);
             put32(bam, (uint32_t)(tr.exG[(imate == 0 ? iExMate + 1 : 0)] - chrStart));
-            const int32_t tlen = (int32_t)(tr.exG[tr.nExons - 1] + tr.exL[tr.nExons - 1] - tr.exG[0]);
-            put32(bam, (uint32_t)(imate == 0 ? tlen : -tlen));
+            if (P.outSAMtlen == 2) {   // ReadAlign_alignBAM.cpp:84-88, 571-573
+                const uint64_t hi = std::max(tr.exG[tr.nExons - 1] + tr.exL[tr.nExons - 1], tr.exG[iExMate] + tr.exL[iExMate]), lo = std::min(tr.exG[0], tr.exG[iExMate + 1]);
+                const int32_t tlen = (int32_t)(hi - lo);
+                const unsigned leftMostMate = tr.exG[0] <= tr.exG[iExMate + 1] ? 0 : 1;
+                put32(bam, (uint32_t)(imate == leftMostMate ? tlen : -tlen));
+            } else {
+                const int32_t tlen = (int32_t)(tr.exG[tr.nExons - 1] + tr.exL[tr.nExons - 1] - tr.exG[0]);
+                put32(bam, (uint32_t)(imate == 0 ? tlen : -tlen));
+            }
         } else {
             put32(bam, 0xFFFFFFFFu); put32(bam, 0xFFFFFFFFu); put32(bam, 0);
         }

@@ -93,8 +93,8 @@ const char* kUnsupported[] = {
     "readFilesSAMattrKeep", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
     "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
     
-    "outQSconversionAdd", 
-    "outSAMfilter", "outSAMtlen", "outWigType", "outWigStrand",
+    
+    "outSAMfilter", "outWigType", "outWigStrand",
     "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
     "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
@@ -174,7 +174,7 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix); STR("readFilesManifest", &P.readFilesManifest);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
-    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); I32("outSAMtlen", &P.outSAMtlen); I32("outQSconversionAdd", &P.outQSconversionAdd); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
     STR("outSAMheaderCommentFile", &P.outSAMheaderCommentFile); STR("quantTranscriptomeSAMoutput", &P.quantTranscriptomeSAMoutput);
     I32("quantTranscriptomeBAMcompression", &P.quantTranscriptomeBAMcompression); U64("runRNGseed", &P.runRNGseed); STR("outSAMorder", &P.outSAMorder);
     STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
@@ -416,6 +416,8 @@ int finalizeParams(HostParams& P, std::string& err) {
         else return bad("EXITING because of fatal INPUT error: unrecognized option in --quantTranscriptomeSAMoutput=" + P.quantTranscriptomeSAMoutput + "\nSOLUTION: use one of the allowed values: BanSingleEnd_BanIndels_ExtendSoftclip OR BanSingleEnd OR BanSingleEnd_ExtendSoftclip\n");
         if (P.quantTranscriptomeBAMcompression < -1) P.quantTrSAM = false;   // -2: no BAM output (Parameters.cpp:906-908)
     }
+    if (P.outSAMtlen != 1 && P.outSAMtlen != 2)   // Parameters.cpp (outSAMtlen)
+        return bad("EXITING because of FATAL INPUT ERROR: --outSAMtlen can only be 1 or 2\nSOLUTION: re-run STAR with --outSAMtlen 1 OR 2\n");
     if (P.outReadsUnmapped != "None" && P.outReadsUnmapped != "Fastx")   // Parameters.cpp (outReadsUnmapped)
         return bad("EXITING because of FATAL INPUT ERROR: unknown value of --outReadsUnmapped: " + P.outReadsUnmapped + "\nSOLUTION: use allowed values: None OR Fastx\n");
     // SJ

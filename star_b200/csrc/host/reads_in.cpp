@@ -235,6 +235,8 @@ int ReadsReader::parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls
     for (unsigned m = 0; m < nMates; m++) {
         c.seq.append(sq[m], sqe[m]);
         c.qual.append(ql[m], qle[m]);
+        if (P->outQSconversionAdd != 0 && ls[4 * m + 3])   // readLoad.cpp:71-81
+            for (size_t k = c.qual.size() - (size_t)(qle[m] - ql[m]); k < c.qual.size(); k++) { int qs = (int)(unsigned char)c.qual[k] + P->outQSconversionAdd; c.qual[k] = (char)(qs < 33 ? 33 : (qs > 126 ? 126 : qs)); }
         c.seqOff.push_back(c.seq.size());
     }
     {
@@ -435,6 +437,8 @@ long long ReadsReader::nextStream(ReadChunk& c, uint32_t maxReads, std::string& 
         for (unsigned m = 0; m < nMates; m++) {
             c.seq += seq[m];
             c.qual += qual[m];
+            if (P->outQSconversionAdd != 0 && c.fastq)
+                for (size_t k = c.qual.size() - qual[m].size(); k < c.qual.size(); k++) { int qs = (int)(unsigned char)c.qual[k] + P->outQSconversionAdd; c.qual[k] = (char)(qs < 33 ? 33 : (qs > 126 ? 126 : qs)); }
             c.seqOff.push_back(c.seq.size());
         }
         // readLoad.cpp:95-98: name without the leading '@'/'>' cut at every separator character

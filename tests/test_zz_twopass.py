@@ -147,3 +147,14 @@ def test_gpu_seed_search_lmax_matches_oracle_cli(lib, oracle, golden, tmp_path):
     assert cf.sam_body(outs[0] + "Aligned.out.sam") == cf.sam_body(outs[1] + "Aligned.out.sam")
     assert open(outs[0] + "SJ.out.tab", "rb").read() == open(outs[1] + "SJ.out.tab", "rb").read()
     assert cf.log_counters(outs[0] + "Log.final.out") == cf.log_counters(outs[1] + "Log.final.out")
+
+
+def test_quality_conversion_and_tlen_options(oracle, golden, tmp_path):
+    """--outQSconversionAdd (readLoad.cpp:71-81) and --outSAMtlen (ReadAlign_alignBAM.cpp:84-88; both equal to the reference when written)."""
+    out = str(tmp_path) + "/"
+    base = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "se_1.fq"), "--outFileNamePrefix", out]
+    subprocess.check_call(base + ["--outQSconversionAdd", "1"], stdout=subprocess.DEVNULL)
+    a = cf.sam_body(out + "Aligned.out.sam")
+    b = cf.sam_body(os.path.join(golden, "ref_se", "Aligned.out.sam"))
+    assert len(a) == len(b) and all(x.split(b"\t")[:10] == y.split(b"\t")[:10] and x.split(b"\t")[10] == bytes(c + 1 for c in y.split(b"\t")[10]) for x, y in zip(a, b))
+    assert subprocess.run(base + ["--outSAMtlen", "3"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 102
