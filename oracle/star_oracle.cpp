@@ -543,7 +543,8 @@ struct ReadAlign {
     bool loadRead(const char* seq0, uint l0, const char* seq1, uint l1, uint nMates) {
         readNmates = nMates;
         readLength[0] = l0; readLength[1] = nMates == 2 ? l1 : 0;
-        if (l0 < 1 || (nMates == 2 && l1 < 1)) { raise(STAR_EXIT_INPUT_FILES, "EXITING because of FATAL ERROR in reads input: short read sequence line: 0\n"); return false; }
+        if (nMates == 1 && l0 < 1) {   // (a mate of a pair may be empty: clipped to nothing, ClipMate_clip.cpp)
+            raise(STAR_EXIT_INPUT_FILES, "EXITING because of FATAL ERROR in reads input: short read sequence line: 0\n"); return false; }
         Lread = nMates == 2 ? l0 + l1 + 1 : l0;
         if (Lread > DEF_readSeqLengthMax) { raise(STAR_EXIT_INPUT_FILES, "EXITING because of FATAL ERROR in reads input: Lread of the pair exceeds DEF_readSeqLengthMax\n"); return false; }
         auto conv = [](char c) -> char {

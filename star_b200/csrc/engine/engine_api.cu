@@ -439,7 +439,8 @@ int star_gpu_upload_chunk(star_ctx_t* c, const star_read_batch_t* in) {
     for (u64 i = 0; i < in->nReads; i++) {
         const uint64_t* o = in->seqOff + i * in->nMates;
         u64 l0 = o[1] - o[0], l1 = in->nMates == 2 ? o[2] - o[1] : 0;
-        if (l0 < 1 || (in->nMates == 2 && l1 < 1)) { g_err = "EXITING because of FATAL ERROR in reads input: short read sequence line: 0\n"; return STAR_EXIT_INPUT_FILES; }
+        if (in->nMates == 1 && l0 < 1) {   // (a mate of a pair may be empty: clipped to nothing before mapping)
+            g_err = "EXITING because of FATAL ERROR in reads input: short read sequence line: 0\n"; return STAR_EXIT_INPUT_FILES; }
         u64 L = in->nMates == 2 ? l0 + l1 + 1 : l0;
         if (L > STAR_READ_SEQ_LENGTH_MAX) { g_err = "EXITING because of FATAL ERROR in reads input: Lread of the pair exceeds DEF_readSeqLengthMax\n"; return STAR_EXIT_INPUT_FILES; }
         if (L > maxL) maxL = (u32)L;

@@ -98,6 +98,15 @@ static void holdRead(std::vector<ReadChunk>& held, const ReadChunk& c, uint32_t 
     }
     h.names.append(c.names, c.nameOff[i], c.nameOff[i + 1] - c.nameOff[i]);
     h.nameOff.push_back((uint32_t)h.names.size());
+    if (c.clipped()) {
+        if (h.seqOffC.empty()) h.seqOffC.push_back(0);
+        for (uint32_t m = 0; m < c.nMates; m++) {
+            const uint64_t a = c.seqOffC[(uint64_t)i * c.nMates + m], b = c.seqOffC[(uint64_t)i * c.nMates + m + 1];
+            h.seqC.append(c.seqC, a, b - a);
+            h.seqOffC.push_back(h.seqC.size());
+            h.clip5.push_back(c.clip5[(uint64_t)i * c.nMates + m]); h.clip3.push_back(c.clip3[(uint64_t)i * c.nMates + m]);
+        }
+    }
     if (!c.nameFullOff.empty()) { h.nameFullOff.push_back((uint32_t)h.namesFull.size()); h.namesFull += c.namesFull.c_str() + c.nameFullOff[i]; h.namesFull.push_back('\0'); }
     h.readFilter.push_back(c.readFilter[i]);
     h.iReadAll.push_back(c.iReadAll[i]);
@@ -122,7 +131,7 @@ static void saveStage1(const std::string& path, const Stats& stats, const std::v
     for (const ReadChunk& c : held) {
         uint32_t hd[4] = {c.nReads, c.nMates, (uint32_t)c.fastq, c.fileIndex};
         o.write((const char*)hd, sizeof(hd));
-        putStr(o, c.seq); putStr(o, c.qual); putVec(o, c.seqOff); putStr(o, c.names); putVec(o, c.nameOff); putVec(o, c.readFilter); putVec(o, c.iReadAll); putStr(o, c.namesFull); putVec(o, c.nameFullOff);
+        putStr(o, c.seq); putStr(o, c.qual); putVec(o, c.seqOff); putStr(o, c.names); putVec(o, c.nameOff); putVec(o, c.readFilter); putVec(o, c.iReadAll); putStr(o, c.namesFull); putVec(o, c.nameFullOff); putVec(o, c.clip5); putVec(o, c.clip3); putStr(o, c.seqC); putVec(o, c.seqOffC);
     }
 }
 static bool loadStage1(const std::string& path, Stats& stats, std::vector<Junction>& allSJ, std::vector<ReadChunk>& held) {
@@ -140,7 +149,7 @@ static bool loadStage1(const std::string& path, Stats& stats, std::vector<Juncti
         uint32_t hd[4];
         in.read((char*)hd, sizeof(hd));
         c.nReads = hd[0]; c.nMates = hd[1]; c.fastq = hd[2] != 0; c.fileIndex = hd[3];
-        getStr(in, c.seq); getStr(in, c.qual); getVec(in, c.seqOff); getStr(in, c.names); getVec(in, c.nameOff); getVec(in, c.readFilter); getVec(in, c.iReadAll); getStr(in, c.namesFull); getVec(in, c.nameFullOff);
+        getStr(in, c.seq); getStr(in, c.qual); getVec(in, c.seqOff); getStr(in, c.names); getVec(in, c.nameOff); getVec(in, c.readFilter); getVec(in, c.iReadAll); getStr(in, c.namesFull); getVec(in, c.nameFullOff); getVec(in, c.clip5); getVec(in, c.clip3); getStr(in, c.seqC); getVec(in, c.seqOffC);
     }
     return in.good();
 }
@@ -419,6 +428,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         const ReadChunk& chunk = wk->chunk;
         star_read_batch_t in;
         in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
+        if (chunk.clipped()) { in.seq = chunk.seqC.data(); in.seqOff = chunk.seqOffC.data(); }   // the engine maps the clipped reads
         uint64_t cap = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
         if (wk->alignsCap < cap) { wk->aligns.reset(new star_align_t[cap]); wk->alignsCap = cap; }
         if (wk->results.size() < chunk.nReads) wk->results.resize(chunk.nReads);

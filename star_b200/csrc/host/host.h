@@ -26,6 +26,14 @@ struct HostParams {
     std::string genomeLoad = "NoSharedMemory";
     std::vector<std::string> readFilesIn = {"Read1", "Read2"};
     std::vector<std::vector<std::string>> readFilesNames;   // [mate][file]: --readFilesIn a1,a2 b1,b2 (Parameters_readFilesInit.cpp:43-62)
+    // read clipping before mapping (ParametersClip_initialize.cpp, ClipMate_clip.cpp): fixed numbers of bases at either end, a 3' adapter
+    // found by ungapped search with a mismatch ratio, bases after the adapter; per mate
+    std::vector<std::string> clip5pNbases = {"0"}, clip3pNbases = {"0"}, clip3pAdapterSeq = {"-"}, clip3pAdapterMMp = {"0.1"}, clip3pAfterAdapterNbases = {"0"},
+                             clip5pAdapterSeq = {"-"}, clipAdapterType = {"Hamming"};
+    bool clipYes = false;
+    uint32_t clip5N[2] = {0, 0}, clip3N[2] = {0, 0}, clip3After[2] = {0, 0};
+    std::string clip3Ad[2];                  // adapter as codes 0..4
+    double clip3MMp[2] = {0.1, 0.1};
     std::string readFilesPrefix = "-", readFilesManifest = "-";
     bool rgFromManifest = false;             // read groups came from --readFilesManifest: @RG header lines, RG tag only on request
     std::vector<std::string> ignoredParams;  // accepted reference parameters without effect here (resource limits, temporary directories)
@@ -157,11 +165,24 @@ struct ReadChunk {
     std::vector<uint32_t> nameFullOff;       // nReads: start of read i's ID in namesFull
     std::vector<char> readFilter;            // 'Y'/'N'
     std::vector<uint64_t> iReadAll;
+    // clipping: seq / qual / seqOff hold the reads as they are in the file (what the output prints); clip5 / clip3 = bases cut at the ends of
+    // every mate (empty vectors: no clipping in this run); seqC / seqOffC = the clipped sequences handed to the engine (a mate clipped
+    // to nothing stays empty in a pair and is passed as one N for single-end reads)
+    std::vector<uint16_t> clip5, clip3;
+    std::string seqC;
+    std::vector<uint64_t> seqOffC;
+    bool clipped() const { return !clip5.empty(); }
+    uint64_t lenOrig(uint64_t i, uint32_t m) const { return seqOff[i * nMates + m + 1] - seqOff[i * nMates + m]; }
+    uint64_t lenTrue(uint64_t i, uint32_t m) const { return clipped() ? lenOrig(i, m) - clip5[i * nMates + m] - clip3[i * nMates + m] : lenOrig(i, m); }   // readLength of the reference
+    uint64_t len(uint64_t i, uint32_t m) const { const uint64_t l = lenTrue(i, m); return l || nMates == 2 ? l : 1; }                              // what the engine mapped
+    uint64_t c5(uint64_t i, uint32_t m) const { return clipped() ? clip5[i * nMates + m] : 0; }
+    uint64_t c3(uint64_t i, uint32_t m) const { return clipped() ? lenOrig(i, m) - c5(i, m) - len(i, m) : 0; }
+    char base(uint64_t i, uint32_t m, uint64_t k) const { return clipped() && lenTrue(i, m) == 0 ? 'N' : seq[seqOff[i * nMates + m] + c5(i, m) + k]; }   // base k of the clipped mate
     bool fastq = true;
     uint32_t fileIndex = 0;                  // input file (of a comma-separated list) this chunk came from: a chunk never spans files
     void clear() {
         nReads = 0; seq.clear(); qual.clear(); seqOff.clear(); names.clear(); nameOff.clear(); readFilter.clear(); iReadAll.clear();
-        namesFull.clear(); nameFullOff.clear();
+        namesFull.clear(); nameFullOff.clear(); clip5.clear(); clip3.clear(); seqC.clear(); seqOffC.clear();
     }
 };
 

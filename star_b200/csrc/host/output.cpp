@@ -139,8 +139,9 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
     const bool flagPaired = c.nMates == 2;
     const uint64_t Lread = r.Lread;
     uint64_t readLength[2];
-    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
-    readLength[1] = flagPaired ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    readLength[0] = c.len(i, 0);   // the lengths that were mapped (after clipping)
+    readLength[1] = flagPaired ? c.len(i, 1) : 0;
+    const uint64_t readLengthOriginal[2] = {c.lenOrig(i, 0), flagPaired ? c.lenOrig(i, 1) : 0};
     uint32_t iExMate;
     unsigned nMates = 1;
     for (iExMate = 0; iExMate + 1 < tr.nExons; iExMate++) {
@@ -173,7 +174,9 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
         unsigned Mate = tr.exFrag[iEx1];
         mateOf[imate] = Mate;
         std::string& cg = cigars[imate];
-        uint64_t trimL1 = (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
+        // bases clipped before mapping come back as soft clips (ReadAlign_outputTranscriptSAM.cpp:134-146, 184-186)
+        const uint64_t trimL = (Str == 0) == (Mate == 0) ? c.c5(i, Mate) : c.c3(i, Mate);
+        uint64_t trimL1 = trimL + (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
         if (trimL1 > 0) { putU(cg, trimL1); cg.push_back('S'); }
         for (uint32_t ii = iEx1; ii <= iEx2; ii++) {
             if (ii > iEx1) {
@@ -192,7 +195,7 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
             putU(cg, tr.exL[ii]); cg.push_back('M');
         }
         if (sjMotif[imate].empty()) { sjMotif[imate] = ",-1"; sjIntron[imate] = ",-1"; }
-        uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLength[leftMate] : readLength[leftMate] + 1 + readLength[Mate]) - tr.exR[iEx2] - tr.exL[iEx2];
+        uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLengthOriginal[leftMate] : readLength[leftMate] + 1 + readLengthOriginal[Mate]) - tr.exR[iEx2] - tr.exL[iEx2] - trimL;
         if (trimR1 > 0) { putU(cg, trimR1); cg.push_back('S'); }
     }
 
@@ -244,11 +247,10 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
         if (needNM) {  // :252-288; R = Read1[roStr==0?0:2], built here from the original mates
             std::string R(Lread, (char)4);
             auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
-            uint64_t a0 = c.seqOff[(uint64_t)i * c.nMates], a1 = c.seqOff[(uint64_t)i * c.nMates + 1];
-            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[a0 + k]);
+            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.base(i, 0, k));
             if (flagPaired) {
                 R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
-                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[a1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.base(i, 1, readLength[1] - 1 - k)); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
             }
             if (tr.roStr != 0) {
                 std::string R2(Lread, (char)4);
@@ -415,8 +417,9 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
     const bool flagPaired = c.nMates == 2;
     const uint64_t Lread = r.Lread;
     uint64_t readLength[2];
-    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
-    readLength[1] = flagPaired ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    readLength[0] = c.len(i, 0);   // the lengths that were mapped (after clipping)
+    readLength[1] = flagPaired ? c.len(i, 1) : 0;
+    const uint64_t readLengthOriginal[2] = {c.lenOrig(i, 0), flagPaired ? c.lenOrig(i, 1) : 0};
     uint32_t iExMate;
     unsigned nMates = 1;
     for (iExMate = 0; iExMate + 1 < tr.nExons; iExMate++) {
@@ -438,7 +441,8 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
         const unsigned Mate = tr.exFrag[iEx1];
         mateOf[imate] = Mate;
         auto op = [&](uint64_t len, unsigned code, char ch) { packed[imate].push_back((uint32_t)(len << 4 | code)); putU(cigarText[imate], len); cigarText[imate].push_back(ch); };
-        const uint64_t trimL1 = (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
+        const uint64_t trimL = (Str == 0) == (Mate == 0) ? c.c5(i, Mate) : c.c3(i, Mate);   // ReadAlign_alignBAM.cpp:222-233, 268-271
+        const uint64_t trimL1 = trimL + (uint64_t)tr.exR[iEx1] - (tr.exR[iEx1] < readLength[leftMate] ? 0 : readLength[leftMate] + 1);
         if (trimL1 > 0) op(trimL1, 4, 'S');
         for (uint32_t ii = iEx1; ii <= iEx2; ii++) {
             if (ii > iEx1) {
@@ -457,7 +461,7 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
             if (tr.exL[ii] > 0) op(tr.exL[ii], 0, 'M');   // 0-length blocks are not recorded in BAM (:276)
         }
         if (sjMotif[imate].empty()) { sjMotif[imate].push_back(-1); sjIntron[imate].push_back(-1); }
-        const uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLength[leftMate] : readLength[leftMate] + 1 + readLength[Mate]) - tr.exR[iEx2] - tr.exL[iEx2];
+        const uint64_t trimR1 = (tr.exR[iEx1] < readLength[leftMate] ? readLengthOriginal[leftMate] : readLength[leftMate] + 1 + readLengthOriginal[Mate]) - tr.exR[iEx2] - tr.exL[iEx2] - trimL;
         if (trimR1 > 0) op(trimR1, 4, 'S');
     }
     std::string rc, rq;
@@ -490,11 +494,10 @@ void OutputWriter::bamMapped(const ReadChunk& c, uint32_t i, const star_read_res
         if (needNM) {  // samAttrNM_MD, ReadAlign_alignBAM.cpp:9-45
             std::string R(Lread, (char)4);
             auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
-            const uint64_t a0 = c.seqOff[(uint64_t)i * c.nMates], a1 = c.seqOff[(uint64_t)i * c.nMates + 1];
-            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[a0 + k]);
+            for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.base(i, 0, k));
             if (flagPaired) {
                 R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
-                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[a1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+                for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.base(i, 1, readLength[1] - 1 - k)); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
             }
             if (tr.roStr != 0) {
                 std::string R2(Lread, (char)4);
@@ -661,8 +664,8 @@ void OutputWriter::formatReads(const ReadChunk& c, const star_align_batch_t& out
     std::string scratch;
     for (uint32_t i = lo; i < hi; i++) {
         const star_read_result_t& r = out.reads[i];
-        uint64_t L0 = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
-        uint64_t L1 = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+        uint64_t L0 = c.lenTrue(i, 0);   // readLength after clipping (ReadAlign_oneRead.cpp: statsRA.readBases)
+        uint64_t L1 = c.nMates == 2 ? c.lenTrue(i, 1) : 0;
         if (by && r.unmapType < 0) {   // ReadAlign::outFilterBySJout (ReadAlign_outputAlignments.cpp:90-130), 1st stage of --outFilterType BySJout
             const star_align_t* tr1 = out.aligns + r.trOffset;
             const bool pass = !heldBySJout(out, i);
@@ -1014,8 +1017,8 @@ void OutputWriter::quantTranscriptome(const ReadChunk& c, uint32_t i, const star
     std::vector<star_align_t> alignT;
     const uint64_t Lread = r.Lread;
     uint64_t readLength[2];
-    readLength[0] = c.seqOff[(uint64_t)i * c.nMates + 1] - c.seqOff[(uint64_t)i * c.nMates];
-    readLength[1] = c.nMates == 2 ? c.seqOff[(uint64_t)i * c.nMates + 2] - c.seqOff[(uint64_t)i * c.nMates + 1] : 0;
+    readLength[0] = c.len(i, 0);
+    readLength[1] = c.nMates == 2 ? c.len(i, 1) : 0;
     std::string R;   // Read1[0]: mate 1, spacer, reverse complement of mate 2 (numeric); reversed-complemented for roStr = 1
     for (uint64_t iag = 0; iag < nTr; iag++) {
         const star_align_t* a1 = &trs[iag];
@@ -1026,11 +1029,10 @@ void OutputWriter::quantTranscriptome(const ReadChunk& c, uint32_t i, const star
             if (R.empty()) {
                 auto conv = [](char ch) -> char { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
                 R.assign(Lread, (char)4);
-                const uint64_t o0 = c.seqOff[(uint64_t)i * c.nMates], o1 = c.seqOff[(uint64_t)i * c.nMates + 1];
-                for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.seq[o0 + k]);
+                for (uint64_t k = 0; k < readLength[0]; k++) R[k] = conv(c.base(i, 0, k));
                 if (c.nMates == 2) {
                     R[readLength[0]] = STAR_MARK_FRAG_SPACER_BASE;
-                    for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.seq[o1 + readLength[1] - 1 - k]); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
+                    for (uint64_t k = 0; k < readLength[1]; k++) { char ch = conv(c.base(i, 1, readLength[1] - 1 - k)); R[readLength[0] + 1 + k] = ch < 4 ? 3 - ch : ch; }
                 }
             }
             std::string Rr;

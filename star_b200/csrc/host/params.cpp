@@ -90,8 +90,8 @@ const char* kUnsupported[] = {
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "varVCFfile", "readFilesType",
-    "readFilesSAMattrKeep", "readQualityScoreBase", "clipAdapterType", "clip3pNbases",
-    "clip3pAdapterSeq", "clip3pAdapterMMp", "clip3pAfterAdapterNbases", "clip5pNbases", 
+    "readFilesSAMattrKeep", "readQualityScoreBase", 
+    
     
     
     "outSAMfilter", "outWigType", "outWigStrand",
@@ -174,7 +174,9 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
     STR("runMode", &P.runMode); STR("genomeDir", &P.genomeDir); STR("genomeLoad", &P.genomeLoad); VSTR("readFilesIn", &P.readFilesIn); STR("readFilesPrefix", &P.readFilesPrefix); STR("readFilesManifest", &P.readFilesManifest);
     VSTR("readFilesCommand", &P.readFilesCommand); VSTR("readNameSeparator", &P.readNameSeparator); STR("outFileNamePrefix", &P.outFileNamePrefix);
     STR("outStd", &P.outStd); VSTR("outSAMtype", &P.outSAMtype); STR("outSAMmode", &P.outSAMmode); STR("outSAMstrandField", &P.outSAMstrandField);
-    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("quantMode", &P.quantMode); I32("outSAMtlen", &P.outSAMtlen); I32("outQSconversionAdd", &P.outQSconversionAdd); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
+    VSTR("outSAMattributes", &P.outSAMattributes); VSTR("outSAMunmapped", &P.outSAMunmapped); STR("outReadsUnmapped", &P.outReadsUnmapped); VSTR("clip5pNbases", &P.clip5pNbases); VSTR("clip3pNbases", &P.clip3pNbases); VSTR("clip3pAdapterSeq", &P.clip3pAdapterSeq);
+    VSTR("clip3pAdapterMMp", &P.clip3pAdapterMMp); VSTR("clip3pAfterAdapterNbases", &P.clip3pAfterAdapterNbases); VSTR("clipAdapterType", &P.clipAdapterType);
+    VSTR("quantMode", &P.quantMode); I32("outSAMtlen", &P.outSAMtlen); I32("outQSconversionAdd", &P.outQSconversionAdd); VSTR("outSAMheaderHD", &P.outSAMheaderHD); VSTR("outSAMheaderPG", &P.outSAMheaderPG);
     STR("outSAMheaderCommentFile", &P.outSAMheaderCommentFile); STR("quantTranscriptomeSAMoutput", &P.quantTranscriptomeSAMoutput);
     I32("quantTranscriptomeBAMcompression", &P.quantTranscriptomeBAMcompression); U64("runRNGseed", &P.runRNGseed); STR("outSAMorder", &P.outSAMorder);
     STR("outSAMprimaryFlag", &P.outSAMprimaryFlag); STR("outSAMreadID", &P.outSAMreadID); VSTR("outSAMattrRGline", &P.outSAMattrRGline);
@@ -334,6 +336,31 @@ int finalizeParams(HostParams& P, std::string& err) {
     if (P.gpuBySJoutPhase != 0 && !(P.outFilterType == "BySJout" && P.gpuShardCount > 1))
         return bad("EXITING because of fatal PARAMETERS error: --gpuBySJoutPhase is only meaningful for a sharded --outFilterType BySJout run\n");
     if (P.outMultimapperOrder != "Old_2.4") return bad("EXITING because of fatal PARAMETERS error: --outMultimapperOrder " + P.outMultimapperOrder + " is not supported by star-b200 (only Old_2.4)\n");
+    {   // ParametersClip_initialize.cpp:6-99: one value per mate; a single default value is repeated
+        if (P.clipAdapterType[0] != "Hamming")
+            return bad(P.clipAdapterType[0] == "CellRanger4" ? "EXITING because of fatal PARAMETER error: --clipAdapterType CellRanger4 is outside the scope of star-b200\n"
+                       : "EXITING because of fatal PARAMETER error: --clipAdapterType = " + P.clipAdapterType[0] + " is not a valid option\nSOLUTION: use valid --clipAdapterType options: Hamming OR CellRanger4\n");
+        auto spread = [&](std::vector<std::string>& v, const char* dflt) { if (v[0] == dflt && v.size() == 1) v.assign(P.readNmates, dflt); };
+        spread(P.clip5pNbases, "0"); spread(P.clip3pNbases, "0"); spread(P.clip3pAfterAdapterNbases, "0");
+        if (P.clip3pAdapterSeq[0] == "-" && P.clip3pAdapterSeq.size() == 1) { P.clip3pAdapterSeq.assign(P.readNmates, "-"); P.clip3pAdapterMMp.assign(P.readNmates, "0"); }
+        const std::pair<const std::vector<std::string>*, const char*> chk[] = {{&P.clip5pNbases, "--clip5pNbases"}, {&P.clip3pNbases, "--clip3pNbases"}, {&P.clip3pAdapterSeq, "--clip3pAdapterSeq"},
+                                                                               {&P.clip3pAdapterMMp, "--clip3pAdapterMMp"}, {&P.clip3pAfterAdapterNbases, "--clip3pAfterAdapterNbases"}};
+        for (auto& c : chk)
+            if (c.first->size() != P.readNmates)
+                return bad(std::string("EXITING because of fatal PARAMETER error: ") + c.second + " has to contain " + std::to_string(P.readNmates) + " values to match the number of mates.\n");
+        for (unsigned m = 0; m < P.readNmates; m++) {
+            unsigned long long v5 = 0, v3 = 0, va = 0;
+            double mm = 0;
+            if (!parseNum(P.clip5pNbases[m], v5) || !parseNum(P.clip3pNbases[m], v3) || !parseNum(P.clip3pAfterAdapterNbases[m], va) || !parseNum(P.clip3pAdapterMMp[m], mm))
+                return bad("EXITING: FATAL INPUT ERROR: could not parse the value of a --clip* parameter\n");
+            P.clip5N[m] = (uint32_t)v5; P.clip3N[m] = (uint32_t)v3; P.clip3After[m] = (uint32_t)va; P.clip3MMp[m] = mm;
+            P.clip3Ad[m].clear();
+            if (P.clip3pAdapterSeq[m] == "polyA") P.clip3Ad[m].assign(STAR_READ_SEQ_LENGTH_MAX, (char)0);   // ClipMate_initialize.cpp:13-15
+            else if (P.clip3pAdapterSeq[m] != "-")
+                for (char ch : P.clip3pAdapterSeq[m]) { char v; switch (ch) { case 'A': case 'a': v = 0; break; case 'C': case 'c': v = 1; break; case 'G': case 'g': v = 2; break; case 'T': case 't': v = 3; break; default: v = 4; } P.clip3Ad[m].push_back(v); }
+            if (v5 || v3 || va || !P.clip3Ad[m].empty()) P.clipYes = true;
+        }
+    }
     // Parameters.cpp:944-955
     if (P.outSAMstrandField == "None") h.outSAMstrandFieldType = 0;
     else if (P.outSAMstrandField == "intronMotif") h.outSAMstrandFieldType = 1;

@@ -188,6 +188,37 @@ static inline void stripEndControl(std::string& s) {  // fastqReadOneLine :284-2
 
 // One FASTQ record from its line pointers: ls/le[4*m + k] = start / end (newline excluded) of line k of mate m; a missing line has
 // ls == nullptr.  Same text rules and error messages as the stream parser below.
+// ClipMate::clip for the 5' end (fixed number of bases) and then the 3' end (fixed number, adapter by localSearch, bases after the
+// adapter) of one mate (ClipMate_clip.cpp:5-78, SequenceFuns.cpp:293-315); appends the clip amounts and the clipped sequence for the engine
+static void clipMateAppend(const HostParams& P, unsigned m, const char* s, uint64_t L0, ReadChunk& c) {
+    uint64_t L = L0, c5 = 0, c3 = 0;
+    if (P.clip5N[m] > 0) { if (L > P.clip5N[m]) { L -= P.clip5N[m]; c5 = P.clip5N[m]; } else { c5 = L; L = 0; } }
+    const uint64_t Lold = L;
+    if (P.clip3N[m] > 0) { if (L > P.clip3N[m]) { L -= P.clip3N[m]; c3 += P.clip3N[m]; } else { L = 0; c3 = Lold; } }
+    if (!P.clip3Ad[m].empty()) {
+        const std::string& ad = P.clip3Ad[m];
+        auto num = [](char ch) -> int { switch (ch) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } };
+        uint64_t nMatchBest = 0, nMMbest = 0, ixBest = L;
+        for (uint64_t ix = 0; ix < L; ix++) {
+            uint64_t nMatch = 0, nMM = 0;
+            const uint64_t ny = std::min<uint64_t>(ad.size(), L - ix);
+            for (uint64_t iy = 0; iy < ny; iy++) {
+                const int x = num(s[c5 + ix + iy]);
+                if (x > 3) continue;
+                if (x == ad[iy]) nMatch++; else nMM++;
+            }
+            if ((nMatch > nMatchBest || (nMatch == nMatchBest && nMM < nMMbest)) && double(nMM) / double(nMatch) <= P.clip3MMp[m]) { ixBest = ix; nMatchBest = nMatch; nMMbest = nMM; }
+        }
+        const uint64_t clippedAdN = L - ixBest;
+        L -= clippedAdN; c3 += clippedAdN;
+    }
+    if (P.clip3After[m] > 0) { if (L > P.clip3After[m]) { L -= P.clip3After[m]; c3 += P.clip3After[m]; } else { L = 0; c3 = Lold; } }
+    c.clip5.push_back((uint16_t)c5);
+    c.clip3.push_back((uint16_t)(L0 - c5 - L));
+    if (L == 0 && c.nMates == 1) c.seqC.push_back('N'); else c.seqC.append(s + c5, L);   // (an empty single-end read is passed as one N: it maps nowhere either)
+    c.seqOffC.push_back(c.seqC.size());
+}
+
 int ReadsReader::parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls, const char* const* le, std::string& err) const {
     auto strip = [](const char* s, const char*& e) { if (e > s && (int)(signed char)e[-1] < 33) e--; };   // removeStringEndControl
     const char* s0 = ls[0];
@@ -233,6 +264,7 @@ int ReadsReader::parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls
         return -STAR_EXIT_INPUT_FILES;
     }
     for (unsigned m = 0; m < nMates; m++) {
+        if (P->clipYes) { if (c.seqOffC.empty()) c.seqOffC.push_back(0); clipMateAppend(*P, m, sq[m], (uint64_t)(sqe[m] - sq[m]), c); }
         c.seq.append(sq[m], sqe[m]);
         c.qual.append(ql[m], qle[m]);
         if (P->outQSconversionAdd != 0 && ls[4 * m + 3])   // readLoad.cpp:71-81
@@ -337,6 +369,14 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
         ReadChunk& pc = part[t];
         const uint64_t sb = c.seq.size();
         const uint32_t nb = (uint32_t)c.names.size();
+        if (P->clipYes) {
+            if (c.seqOffC.empty()) c.seqOffC.push_back(0);
+            const uint64_t sbC = c.seqC.size();
+            c.seqC += pc.seqC;
+            for (size_t k = 1; k < pc.seqOffC.size(); k++) c.seqOffC.push_back(sbC + pc.seqOffC[k]);
+            c.clip5.insert(c.clip5.end(), pc.clip5.begin(), pc.clip5.end());
+            c.clip3.insert(c.clip3.end(), pc.clip3.begin(), pc.clip3.end());
+        }
         const uint32_t nbFull = (uint32_t)c.namesFull.size();
         c.namesFull += pc.namesFull;
         for (uint32_t o : pc.nameFullOff) c.nameFullOff.push_back(nbFull + o);
@@ -435,6 +475,7 @@ long long ReadsReader::nextStream(ReadChunk& c, uint32_t maxReads, std::string& 
             return -STAR_EXIT_INPUT_FILES;
         }
         for (unsigned m = 0; m < nMates; m++) {
+            if (P->clipYes) { if (c.seqOffC.empty()) c.seqOffC.push_back(0); clipMateAppend(*P, m, seq[m].data(), seq[m].size(), c); }
             c.seq += seq[m];
             c.qual += qual[m];
             if (P->outQSconversionAdd != 0 && c.fastq)

@@ -57,6 +57,14 @@ SCENARIOS = {
                        "--outSAMtype", "BAM", "Unsorted", "SortedByCoordinate", "--quantMode", "TranscriptomeSAM", "GeneCounts", "--outSAMunmapped", "Within",
                        "--outSAMstrandField", "intronMotif", "--outSAMheaderHD", "@HD", "VN:1.4", "SO:unsorted", "--outSAMheaderCommentFile", "TP/COfile.txt",
                        "--outSAMheaderPG", "@PG", "ID:x", "PN:y", "--limitBAMsortRAM", "10000000000"],
+    # read clipping before mapping (--clip5pNbases / --clip3pNbases / 3' adapter): soft clips in the CIGARs, NM / MD / MC, both BAM files, quantification
+    "V_clip_pe_all_outputs": ["--genomeDir", "idx", "--readFilesIn", "std_1.fq", "std_2.fq", "--clip5pNbases", "4", "9", "--clip3pNbases", "12", "6", "--outSAMtype", "BAM", "Unsorted",
+                              "SortedByCoordinate", "--outSAMunmapped", "Within", "--quantMode", "TranscriptomeSAM", "GeneCounts", "--outReadsUnmapped", "Fastx",
+                              "--outSAMattributes", "NH", "HI", "AS", "nM", "NM", "MD", "MC"],
+    "V2_clip_adapter_se": ["--genomeDir", "idx", "--readFilesIn", "se_1.fq", "--clip3pAdapterSeq", "AGGTC", "--clip3pAdapterMMp", "0.2", "--clip3pAfterAdapterNbases", "2",
+                           "--outSAMunmapped", "Within"],
+    "V3_clip_mate_to_nothing": ["--genomeDir", "idx", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--clip3pNbases", "0", "200", "--clip3pAdapterSeq", "GATC", "polyA",
+                                "--clip3pAdapterMMp", "0.1", "0.3", "--outSAMunmapped", "Within", "--outSAMattributes", "NH", "HI", "AS", "nM", "NM", "MD"],
     "F_gtf_insert": ["--genomeDir", "TP/idx0", "--readFilesIn", "std_1.fq", "std_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbInsertSave", "All", "--sjdbOverhang", "99"],
     "G_gtf_files_twopass": ["--genomeDir", "TP/idx0", "--readFilesIn", "hard_1.fq", "hard_2.fq", "--sjdbGTFfile", "annot.gtf", "--sjdbFileChrStartEnd", "TP/sj_opp.tab",
                             "TP/sj_shift.tab", "--twopassMode", "Basic", "--sjdbInsertSave", "All"],

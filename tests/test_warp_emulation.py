@@ -159,3 +159,47 @@ def test_emulated_kernels_sj_novel_filter(oracle, lib, golden, twopass_golden, e
     assert rc == 0 and int(info4[2]) == 0
     diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
     assert not diffs, "\n".join(diffs[:10])
+
+
+@pytest.mark.parametrize("env", [{}, {"STAR_B200_HEAVY_NA": "2000000000", "STAR_B200_HEAVY_EST": "0"}])
+def test_emulated_kernels_take_empty_mates(oracle, lib, golden, env, monkeypatch):
+    """A mate that was clipped to nothing before mapping (--clip3pNbases, adapters) reaches the engine as an empty mate of a pair: mate 1
+    empty, mate 2 empty, both empty, a 19-base mate with an empty partner — emulated kernels equal the oracle on the flat and the lane path."""
+    import star_b200 as sb
+    from star_b200 import capi
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m1 = cf.read_fastq_seqs(os.path.join(golden, "std_1.fq"))[:8]
+    m2 = cf.read_fastq_seqs(os.path.join(golden, "std_2.fq"))[:8]
+    parts, off = [], [0]
+    for i, (a, b) in enumerate(zip(m1, m2)):
+        a, b = bytes(a), bytes(b)
+        if i % 3 == 0:
+            b = b""
+        if i % 4 == 1:
+            a = b""
+        if i == 5:
+            a, b = a[:19], b""
+        if i == 7:
+            a, b = b"", b""
+        for s in (a, b):
+            parts.append(s)
+            off.append(off[-1] + len(s))
+    seq = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    off = np.array(off, dtype=np.uint64)
+    n, nm = 8, 2
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    oe = oc.OracleEngine(oracle, idx)
+    res_o, al_o, _ = oe.map_chunk(seq, off, n, nm)
+    batch = oe._batch(seq, off, n, nm)
+    res, al, ab = oe._out(n, oe.n_out)
+    oe.close()
+    em = C.CDLL(ENGINE_EMUL_LIB)
+    em.engine_emul_map_chunk.argtypes = [C.POINTER(capi.IndexView), C.POINTER(capi.Params), C.POINTER(capi.ReadBatch), C.POINTER(capi.AlignBatch), C.c_void_p]
+    info4 = np.zeros(4, dtype=np.uint64)
+    rc = em.engine_emul_map_chunk(idx.view, C.byref(idx.params), C.byref(batch), C.byref(ab), info4.ctypes.data)
+    idx.close()
+    assert rc == 0 and int(info4[2]) == 0
+    assert (res_o["unmapType"] < 0).sum() >= 4
+    diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
+    assert not diffs, "\n".join(diffs[:10])

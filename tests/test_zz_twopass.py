@@ -17,7 +17,8 @@ import oracle_capi as oc
 
 ROOT = cf.ROOT
 NAMES = ["A_novel", "B_annot", "C_files_hard", "D_annot_files_se", "E_insert_only", "F_gtf_insert", "G_gtf_files_twopass",
-         "S1_bysjout", "S2_bysjout_annot_within", "S3_bysjout_se_filters", "S4_bysjout_twopass", "T_encode_twopass", "U_unmapped_fastx_bysjout", "Q_genecounts_bysjout", "R_transcriptome_sam", "R2_transcriptome_sam_bysjout_rg", "T2_encode_full"]
+         "S1_bysjout", "S2_bysjout_annot_within", "S3_bysjout_se_filters", "S4_bysjout_twopass", "T_encode_twopass", "U_unmapped_fastx_bysjout", "Q_genecounts_bysjout", "R_transcriptome_sam", "R2_transcriptome_sam_bysjout_rg", "T2_encode_full",
+         "V_clip_pe_all_outputs", "V2_clip_adapter_se", "V3_clip_mate_to_nothing"]
 
 
 def _args(tp, golden, name):
