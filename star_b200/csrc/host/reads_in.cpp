@@ -212,7 +212,8 @@ static void clipMateAppend(const HostParams& P, unsigned m, const char* s, uint6
         const uint64_t clippedAdN = L - ixBest;
         L -= clippedAdN; c3 += clippedAdN;
     }
-    if (P.clip3After[m] > 0) { if (L > P.clip3After[m]) { L -= P.clip3After[m]; c3 += P.clip3After[m]; } else { L = 0; c3 = Lold; } }
+    if (P.clip3After[m] > 0 && (P.clip3N[m] > 0 || !P.clip3Ad[m].empty())) {   // (ClipMate_initialize.cpp:22-23: an end with neither N nor adapter is not clipped at all)
+        if (L > P.clip3After[m]) { L -= P.clip3After[m]; c3 += P.clip3After[m]; } else { L = 0; c3 = Lold; } }
     c.clip5.push_back((uint16_t)c5);
     c.clip3.push_back((uint16_t)(L0 - c5 - L));
     if (L == 0 && c.nMates == 1) c.seqC.push_back('N'); else c.seqC.append(s + c5, L);   // (an empty single-end read is passed as one N: it maps nowhere either)

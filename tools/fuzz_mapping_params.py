@@ -71,6 +71,14 @@ idx=ch("idx","idx0")
 if qm:
     idx="idx"; opts.extend(["--quantMode"]+ch(["GeneCounts"],["TranscriptomeSAM"],["TranscriptomeSAM","GeneCounts"]))
     if random.random()<0.4: opts.extend(["--quantTranscriptomeSAMoutput",ch("BanSingleEnd","BanSingleEnd_ExtendSoftclip","BanSingleEnd_BanIndels_ExtendSoftclip")])
+if random.random()<0.5:
+    nm=len(ds[1])
+    if random.random()<0.6: opts.extend(["--clip5pNbases"]+[str(ch(0,3,10,40)) for _ in range(nm)])
+    if random.random()<0.6: opts.extend(["--clip3pNbases"]+[str(ch(0,5,20,90,200)) for _ in range(nm)])
+    if random.random()<0.5:
+        opts.extend(["--clip3pAdapterSeq"]+[ch("AGGTC","GATC","polyA","TTTTTTTT","-") for _ in range(nm)])
+        opts.extend(["--clip3pAdapterMMp"]+[str(ch(0,0.1,0.3)) for _ in range(nm)])
+        if random.random()<0.4: opts.extend(["--clip3pAfterAdapterNbases"]+[str(ch(0,1,4)) for _ in range(nm)])
 args=["--genomeDir",idx,"--readFilesIn"]+ds[1]+opts
 res=[]
 for tag,b,nt in (("fm_ref","/root/repo/oracle/_ref/STAR","1"),("fm_our","/root/repo/oracle/_build/star_cli_oracle","3")):
