@@ -86,7 +86,7 @@ bool parseU64(const std::string& s, uint64_t& out) {
 
 // STAR parameters that exist in the reference but belong to subsystems outside the hot path
 const char* kUnsupported[] = {
-    "parametersFiles", "genomeChainFiles", "genomeFileSizes",
+    "genomeChainFiles", "genomeFileSizes",
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "varVCFfile", "readFilesType",
@@ -218,15 +218,42 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
             given.back().second.push_back(a);
         }
     }
+    // --parametersFiles (Parameters.cpp:331-365, 400-440): "name value(s)" lines, '#' comments; the command line overrides them
+    std::vector<std::pair<std::string, Vals>> fromFile;
+    for (auto& g : given)
+        if (g.first == "parametersFiles") {
+            for (const std::string& fn : g.second) {
+                if (fn == "-") continue;
+                std::ifstream pf(fn);
+                if (pf.fail()) { err = "EXITING because of fatal input ERROR: could not open user-defined parameters file " + fn + "\n"; return STAR_EXIT_PARAMETER; }
+                std::string line;
+                while (std::getline(pf, line)) {
+                    std::istringstream ls(line);
+                    std::string name, v;
+                    if (!(ls >> name) || name[0] == '#') continue;
+                    Vals vals;
+                    while (ls >> v) vals.push_back(v);   // (no inline comments: the reference takes everything after the name as values)
+                    fromFile.push_back({name, vals});
+                }
+            }
+        }
+    std::map<std::string, int> levelOf;   // 1 = parameters file, 2 = command line
+    std::vector<std::pair<std::string, Vals>> ordered;
+    std::vector<int> levels;
+    for (auto& g : fromFile) { ordered.push_back(g); levels.push_back(1); }
+    for (auto& g : given) if (g.first != "parametersFiles") { ordered.push_back(g); levels.push_back(2); }
     std::ostringstream full;
     full << (argc > 0 ? argv[0] : "STAR");
-    for (auto& g : given) {
+    for (size_t ig = 0; ig < ordered.size(); ig++) {
+        auto& g = ordered[ig];
+        const int level = levels[ig];
+        const char* source = level == 1 ? "parametersFiles" : "Command-Line";
         auto it = tab.find(g.first);
         if (it == tab.end()) {
             bool ignored = false;
             for (const char* u : kIgnored) if (g.first == u) ignored = true;
-            if (ignored && !g.second.empty() && !P.userSet.count(g.first)) {
-                P.userSet[g.first] = 2;
+            if (ignored && !g.second.empty() && !(levelOf.count(g.first) && levelOf[g.first] == level)) {
+                P.userSet[g.first] = 2; levelOf[g.first] = level;
                 P.ignoredParams.push_back(g.first);
                 full << "   --" << g.first;
                 for (auto& v : g.second) full << " " << v;
@@ -238,25 +265,24 @@ int parseCommandLine(int argc, char** argv, HostParams& P, std::string& err) {
                 err = "EXITING: FATAL INPUT ERROR: parameter --" + g.first +
                       " belongs to a STAR subsystem that is outside the scope of star-b200 (the GPU alignment hot path); remove it\n";
             else
-                err = "EXITING: FATAL INPUT ERROR: unrecognized parameter name \"" + g.first + "\" in input \"Command-Line\"\n" +
+                err = "EXITING: FATAL INPUT ERROR: unrecognized parameter name \"" + g.first + "\" in input \"" + source + "\"\n" +
                       "SOLUTION: use correct parameter name (check the manual)\n";  // Parameters.cpp:1245-1250
             return STAR_EXIT_PARAMETER;
         }
-        if (P.userSet.count(g.first)) {
-            err = "EXITING: FATAL INPUT ERROR: duplicate parameter \"" + g.first + "\" in input \"Command-Line\"\nSOLUTION: keep only one definition of input parameters in each input source\n";
+        if (levelOf.count(g.first) && levelOf[g.first] == level) {
+            err = "EXITING: FATAL INPUT ERROR: duplicate parameter \"" + g.first + "\" in input \"" + source + "\"\nSOLUTION: keep only one definition of input parameters in each input source\n";
             return STAR_EXIT_PARAMETER;
         }
         if (g.second.empty()) {
-            err = "EXITING: FATAL INPUT ERROR: empty value for parameter \"" + g.first + "\" in input \"Command-Line\"\nSOLUTION: use non-empty value for this parameter\n";
+            err = "EXITING: FATAL INPUT ERROR: empty value for parameter \"" + g.first + "\" in input \"" + source + "\"\nSOLUTION: use non-empty value for this parameter\n";
             return STAR_EXIT_PARAMETER;
         }
         if (!it->second.fn(g.second)) {
             err = "EXITING: FATAL INPUT ERROR: could not parse the value of parameter \"" + g.first + "\"\n";
             return STAR_EXIT_PARAMETER;
         }
-        P.userSet[g.first] = 2;
-        full << "   --" << g.first;
-        for (auto& v : g.second) full << " " << v;
+        P.userSet[g.first] = 2; levelOf[g.first] = level;
+        if (level == 2) { full << "   --" << g.first; for (auto& v : g.second) full << " " << v; }
     }
     P.commandLineFull = full.str();
     return finalizeParams(P, err);

@@ -159,3 +159,19 @@ def test_quality_conversion_and_tlen_options(oracle, golden, tmp_path):
     b = cf.sam_body(os.path.join(golden, "ref_se", "Aligned.out.sam"))
     assert len(a) == len(b) and all(x.split(b"\t")[:10] == y.split(b"\t")[:10] and x.split(b"\t")[10] == bytes(c + 1 for c in y.split(b"\t")[10]) for x, y in zip(a, b))
     assert subprocess.run(base + ["--outSAMtlen", "3"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 102
+
+
+def test_parameters_file(oracle, golden, tmp_path):
+    """--parametersFiles (Parameters.cpp:331-440): values from the file, overridden by the command line; equal to the reference when written."""
+    pf = str(tmp_path / "pf.txt")
+    open(pf, "w").write("# comment\noutSAMattributes NH HI AS nM XS\n\noutFilterMultimapNmax 5\nalignEndsType EndToEnd\n")
+    out = str(tmp_path / "o") + "/"
+    base = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "se_1.fq"), "--outFileNamePrefix", out]
+    subprocess.check_call(base + ["--parametersFiles", pf], stdout=subprocess.DEVNULL)
+    sam = open(out + "Aligned.out.sam").read()
+    assert "XS:A:" in sam and not any("S\t" in l.split("\t")[5] + "\t" for l in sam.split("\n") if l and not l.startswith("@") and l.split("\t")[5] != "*")   # EndToEnd from the file
+    subprocess.check_call(base + ["--parametersFiles", pf, "--alignEndsType", "Local"], stdout=subprocess.DEVNULL)   # the command line wins
+    assert any("S" in l.split("\t")[5] for l in open(out + "Aligned.out.sam").read().split("\n") if l and not l.startswith("@"))
+    open(pf, "a").write("alignEndsType Local\n")
+    r = subprocess.run(base + ["--parametersFiles", pf], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 102 and "duplicate parameter" in r.stderr and "parametersFiles" in r.stderr
