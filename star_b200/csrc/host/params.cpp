@@ -90,13 +90,13 @@ const char* kUnsupported[] = {
     "genomeTransformOutput", "genomeChrSetMitochondrial", 
     "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
     "varVCFfile", "readFilesType",
-    "readFilesSAMattrKeep", "readQualityScoreBase", 
+    "readFilesSAMattrKeep", 
     
     
     
     "outSAMfilter", "outWigType", "outWigStrand",
-    "outWigReferencesPrefix", "outWigNorm", "seedNoneLociPerWindow", "peOverlapNbasesMin", "peOverlapMMp", "winReadCoverageRelativeMin",
-    "winReadCoverageBasesMin", "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
+    "outWigReferencesPrefix", "outWigNorm", "peOverlapNbasesMin", "peOverlapMMp", 
+    "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
     "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
     "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", 
     "waspOutputMode", "soloType",
@@ -109,7 +109,9 @@ const char* kUnsupported[] = {
 // resource / housekeeping knobs of the reference that cannot change any output here (buffers are sized from the chunk, the BAM sort is in
 // memory, there are no temporary files): accepted and ignored, so that existing command lines keep working
 const char* kIgnored[] = {"sysShell", "runDirPerm", "limitIObufferSize", "limitOutSAMoneReadBytes", "limitOutSJoneRead", "limitOutSJcollapsed",
-                          "limitBAMsortRAM", "limitNreadsSoft", "outTmpDir", "outTmpKeep", "outBAMsortingThreadN", "outBAMsortingBinsN"};
+                          "limitBAMsortRAM", "limitNreadsSoft", "outTmpDir", "outTmpKeep", "outBAMsortingThreadN", "outBAMsortingBinsN",
+                          // read by the long-read stitcher / solo statistics only: no effect in the short-read build of the reference either
+                          "seedNoneLociPerWindow", "winReadCoverageRelativeMin", "winReadCoverageBasesMin", "readQualityScoreBase"};
 
 }  // namespace
 
