@@ -86,25 +86,17 @@ bool parseU64(const std::string& s, uint64_t& out) {
 
 // STAR parameters that exist in the reference but belong to subsystems outside the hot path
 const char* kUnsupported[] = {
-    "genomeChainFiles", "genomeFileSizes",
-    "genomeTransformOutput", "genomeChrSetMitochondrial", 
-    "genomeSuffixLengthMax", "genomeTransformType", "genomeTransformVCF", "genomeType",
-    "varVCFfile", "readFilesType",
-    "readFilesSAMattrKeep", 
-    
-    
-    
-    "outSAMfilter", "outWigType", "outWigStrand",
-    "outWigReferencesPrefix", "outWigNorm", "peOverlapNbasesMin", "peOverlapMMp", 
-    "chimOutType", "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation",
-    "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin", "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax",
-    "chimMultimapNmax", "chimMultimapScoreRange", "chimNonchimScoreDropMin", "chimOutJunctionFormat", 
-    "waspOutputMode", "soloType",
-    "soloCBtype", "soloCBwhitelist", "soloCBstart", "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate",
-    "soloCBposition", "soloUMIposition", "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype",
-    "soloInputSAMattrBarcodeSeq", "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup",
-    "soloUMIfiltering", "soloOutFileNames", "soloCellFilter", "soloOutFormatFeaturesGeneField3", "soloCellReadStats", "soloClusterCBfile",
-    "sjdbScoreX"};
+    "genomeChainFiles", "genomeFileSizes", "genomeTransformOutput", "genomeChrSetMitochondrial", "genomeSuffixLengthMax",
+    "genomeTransformType", "genomeTransformVCF", "genomeType", "varVCFfile", "readFilesType", "readFilesSAMattrKeep", "outSAMfilter",
+    "outWigType", "outWigStrand", "outWigReferencesPrefix", "outWigNorm", "peOverlapNbasesMin", "peOverlapMMp", "chimOutType",
+    "chimSegmentMin", "chimScoreMin", "chimScoreDropMax", "chimScoreSeparation", "chimScoreJunctionNonGTAG", "chimJunctionOverhangMin",
+    "chimSegmentReadGapMax", "chimFilter", "chimMainSegmentMultNmax", "chimMultimapNmax", "chimMultimapScoreRange",
+    "chimNonchimScoreDropMin", "chimOutJunctionFormat", "waspOutputMode", "soloType", "soloCBtype", "soloCBwhitelist", "soloCBstart",
+    "soloCBlen", "soloUMIstart", "soloUMIlen", "soloBarcodeReadLength", "soloBarcodeMate", "soloCBposition", "soloUMIposition",
+    "soloAdapterSequence", "soloAdapterMismatchesNmax", "soloCBmatchWLtype", "soloInputSAMattrBarcodeSeq",
+    "soloInputSAMattrBarcodeQual", "soloStrand", "soloFeatures", "soloMultiMappers", "soloUMIdedup", "soloUMIfiltering",
+    "soloOutFileNames", "soloCellFilter", "soloOutFormatFeaturesGeneField3", "soloCellReadStats", "soloClusterCBfile", "sjdbScoreX",
+    "clip5pAdapterSeq", "clip5pAdapterMMp", "clip5pAfterAdapterNbases"};
 
 // resource / housekeeping knobs of the reference that cannot change any output here (buffers are sized from the chunk, the BAM sort is in
 // memory, there are no temporary files): accepted and ignored, so that existing command lines keep working
