@@ -175,3 +175,38 @@ def test_parameters_file(oracle, golden, tmp_path):
     open(pf, "a").write("alignEndsType Local\n")
     r = subprocess.run(base + ["--parametersFiles", pf], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 102 and "duplicate parameter" in r.stderr and "parametersFiles" in r.stderr
+
+
+@pytest.mark.gpu
+def test_gpu_engine_takes_empty_mates(lib, oracle, golden):
+    """Empty mates of a pair (clipped to nothing before mapping) through the C-ABI on the GPU: equal to the oracle field by field."""
+    import numpy as np
+    import star_b200 as sb
+    m1 = cf.read_fastq_seqs(os.path.join(golden, "std_1.fq"))[:64]
+    m2 = cf.read_fastq_seqs(os.path.join(golden, "std_2.fq"))[:64]
+    parts, off = [], [0]
+    for i, (a, b) in enumerate(zip(m1, m2)):
+        a, b = bytes(a), bytes(b)
+        if i % 3 == 0:
+            b = b""
+        if i % 4 == 1:
+            a = b""
+        if i % 16 == 5:
+            a, b = a[:19], b""
+        if i % 16 == 7:
+            a, b = b"", b""
+        for s in (a, b):
+            parts.append(s)
+            off.append(off[-1] + len(s))
+    seq = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    off = np.array(off, dtype=np.uint64)
+    idx = sb.Index(lib, os.path.join(golden, "idx"))
+    oe = oc.OracleEngine(oracle, idx)
+    res_o, al_o, _ = oe.map_chunk(seq, off, 64, 2)
+    oe.close()
+    eng = sb.Engine(lib, idx, max_reads=64)
+    res_g, al_g, _ = eng.map_chunk(seq, off, 64, 2)
+    eng.close()
+    idx.close()
+    diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
+    assert not diffs, "\n".join(diffs[:10])
