@@ -148,7 +148,8 @@ typedef struct star_index_view {
  * One chunk of reads (what processChunks() hands to mapChunk(), ReadAlignChunk_processChunks.cpp:130-157,
  * minus names and qualities which never go to the device).
  * Mate m of read i occupies seq[seqOff[i*nMates+m] .. seqOff[i*nMates+m+1]) as ASCII (ACGTacgt, anything
- * else is N: SequenceFuns.cpp:131-146).
+ * else is N: SequenceFuns.cpp:131-146).  A mate of a PAIR may be empty (a read clipped to nothing before mapping, ClipMate_clip.cpp);
+ * a single-end read has at least one base.
  */
 typedef struct star_read_batch {
     uint32_t nReads;
