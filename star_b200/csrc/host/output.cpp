@@ -33,15 +33,17 @@ static inline void putI(std::string& s, long long v) {
 }
 
 static void revComplement(const char* in, size_t L, std::string& out) {  // SequenceFuns.cpp:16-54
-    static char tab[256];
-    static bool init = false;
-    if (!init) {
-        for (int i = 0; i < 256; i++) tab[i] = (char)i;
-        const char* a = "ACGTNRYKMSWBDVHacgtnrykmswbdvh";
-        const char* b = "TGCANYRMKSWVHBDtgcanyrmkswvhbd";
-        for (int i = 0; a[i]; i++) tab[(unsigned char)a[i]] = b[i];
-        init = true;
-    }
+    struct Tab {   // built once, thread-safely (function-local static): the formatting threads call this concurrently
+        char t[256];
+        Tab() {
+            for (int i = 0; i < 256; i++) t[i] = (char)i;
+            const char* a = "ACGTNRYKMSWBDVHacgtnrykmswbdvh";
+            const char* b = "TGCANYRMKSWVHBDtgcanyrmkswvhbd";
+            for (int i = 0; a[i]; i++) t[(unsigned char)a[i]] = b[i];
+        }
+    };
+    static const Tab T;
+    const char* tab = T.t;
     out.resize(L);
     for (size_t j = 0; j < L; j++) out[j] = tab[(unsigned char)in[L - 1 - j]];
 }

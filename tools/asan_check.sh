@@ -19,3 +19,9 @@ for cap in 0 1500000; do   # 0: 32-bit path; > 0: the batched 64-bit path (the p
     timeout 900 "$B" --runMode genomeGenerate --genomeDir AS_gen$cap --genomeFastaFiles genome.fa --sjdbGTFfile annot.gtf --sjdbOverhang 99 --genomeSAindexNbases 7 --outFileNamePrefix AS_gen${cap}_ > /dev/null 2> AS_gen$cap.err
     echo "generate cap=$cap rc=$? findings=$(grep -c 'ERROR: AddressSanitizer\|runtime error' AS_gen$cap.err) SA=$(cmp AS_gen$cap/SA idx/SA > /dev/null && echo reference-bytes || echo DIFFERS)"
 done
+# ThreadSanitizer over the three-stage host pipeline (reader thread, engine thread, formatting threads; many small chunks)
+unset STAR_CLI_SJDB_EMUL STAR_B200_SA_LARGE_CAP
+rm -rf TS_run; mkdir TS_run
+TSAN_OPTIONS=halt_on_error=0 timeout 900 "$ROOT/oracle/_build/asan/star_cli_tsan" --genomeDir idx --readFilesIn std_1.fq std_2.fq --gpuChunkReads 300 --runThreadN 4 --outFilterType BySJout \
+    --quantMode TranscriptomeSAM GeneCounts --outSAMtype BAM Unsorted SortedByCoordinate --outSAMunmapped Within --outReadsUnmapped Fastx --outFileNamePrefix TS_run/ > /dev/null 2> TS_run.err
+echo "tsan pipeline rc=$? races=$(grep -c 'WARNING: ThreadSanitizer' TS_run.err)"
