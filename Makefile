@@ -18,7 +18,8 @@ all: $(LIB) $(BIN)
 $(BUILD):
 	mkdir -p $(BUILD) star_b200/lib star_b200/bin
 
-$(BUILD)/eng_%.o: star_b200/csrc/engine/%.cu star_b200/csrc/engine/dev.cuh star_b200/csrc/engine/sjdb_kernels.cuh star_b200/csrc/engine/stitch_flat.cuh star_b200/csrc/engine/stitch_types.cuh include/star_b200.h | $(BUILD)
+ENG_HDR  := $(wildcard star_b200/csrc/engine/*.cuh)
+$(BUILD)/eng_%.o: star_b200/csrc/engine/%.cu $(ENG_HDR) include/star_b200.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(BUILD)/host_%.o: star_b200/csrc/host/%.cpp star_b200/csrc/host/host.h include/star_b200.h | $(BUILD)

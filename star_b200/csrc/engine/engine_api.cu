@@ -176,10 +176,15 @@ void star_gpu_destroy(star_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->owned) cudaFree(p);
+    if (c->d_seq) cudaFree(c->d_seq);                 // grown on demand (ensureSeq / ensureReads / launchHeavy), not in `owned`
+    if (c->d_reads) cudaFree(c->d_reads);
+    if (c->d_heavyScratch) cudaFree(c->d_heavyScratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
 }
+
+static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const star_params_t* params, uint32_t maxReadsPerChunk);
 
 int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, const star_params_t* params, uint32_t maxReadsPerChunk) {
     *out = nullptr;
@@ -200,6 +205,13 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     star_ctx* c = new star_ctx;
     memset(c->ev, 0, sizeof(c->ev));
     c->device = device;
+    const int rc = initCtx(c, device, v, params, maxReadsPerChunk);
+    if (rc) { const std::string keep = g_err; star_gpu_destroy(c); g_err = keep; return rc; }   // nothing allocated so far outlives a failed init
+    *out = c;
+    return 0;
+}
+
+static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const star_params_t* params, uint32_t maxReadsPerChunk) {
     c->P = *params;
     c->maxReads = maxReadsPerChunk;
     cudaDeviceProp prop;
@@ -407,7 +419,6 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    *out = c;
     return 0;
 }
 

@@ -242,6 +242,9 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                    std::ofstream& logMain, std::string& err, StageState& stage) {
     int rc = 0;
     const bool firstStage = stage.bySJstage != 2, lastStage = stage.bySJstage != 1;
+    // the 2nd BySJout stage appends only when both stages run in this process and share the files; a sharded phase-2 process owns its
+    // own ".stage2" files and must not inherit what an earlier run left under the same prefix
+    const std::ios::openmode outMode = (!firstStage && stage.streamSuffix.empty()) ? (std::ios::binary | std::ios::app) : (std::ios::binary | std::ios::trunc);
     ReadsReader reader;
     if (firstStage) {
         rc = reader.open(P, err);
@@ -256,7 +259,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     std::ofstream trOut;
     std::ostream& trO = P.outStd == "BAM_Quant" ? static_cast<std::ostream&>(std::cout) : trOut;   // Parameters.cpp:908-909
     if (trYes) {   // Aligned.toTranscriptome.out.bam (Parameters.cpp:911-914)
-        if (P.outStd != "BAM_Quant") trOut.open(P.outFileNamePrefix + "Aligned.toTranscriptome.out" + stage.streamSuffix + ".bam", firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (P.outStd != "BAM_Quant") trOut.open(P.outFileNamePrefix + "Aligned.toTranscriptome.out" + stage.streamSuffix + ".bam", outMode);
         if (P.gpuShardIndex == 0 && firstStage) { std::string z; const std::string h = W.bamHeaderTranscriptome(); OutputWriter::bgzfCompress(h.data(), h.size(), P.quantTranscriptomeBAMcompression, z); trO.write(z.data(), z.size()); }
     }
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
@@ -267,11 +270,11 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     const bool unmYes = P.outReadsUnmapped == "Fastx";   // Unmapped.out.mate1/2 (Parameters.cpp:838-844); both stages of BySJout append
     std::ofstream unmOut[2];
     if (unmYes) for (unsigned m = 0; m < P.readNmates; m++)
-        unmOut[m].open(P.outFileNamePrefix + "Unmapped.out" + stage.streamSuffix + ".mate" + std::to_string(m + 1), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        unmOut[m].open(P.outFileNamePrefix + "Unmapped.out" + stage.streamSuffix + ".mate" + std::to_string(m + 1), outMode);
     const bool samToStdout = (P.outStd == "SAM" && streamYes && !bamYes) || (P.outStd == "BAM_Unsorted" && bamYes);   // Parameters.cpp:634-636, 669-670
     std::ostream& samO = samToStdout ? static_cast<std::ostream&>(std::cout) : samOut;
     if (streamYes) {
-        if (!samToStdout) samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), firstStage ? std::ios::binary : (std::ios::binary | std::ios::app));
+        if (!samToStdout) samOut.open(P.outFileNamePrefix + "Aligned.out" + stage.streamSuffix + (bamYes ? ".bam" : ".sam"), outMode);
         if (P.gpuShardIndex == 0 && firstStage) {   // shards > 0 write records only; the merge concatenates in shard order
             if (bamYes) { std::string z; const std::string h = W.bamHeader(); OutputWriter::bgzfCompress(h.data(), h.size(), P.outBAMcompression, z); samO.write(z.data(), z.size()); }
             else samO << W.samHeader();
@@ -549,6 +552,7 @@ static int runAlign(int argc, char** argv, const star_engine_vtbl_t* eng) {
         HostParams P1 = P;   // outputs off, files into _STARpass1/ (twoPassRunPass1.cpp:17-47)
         P1.outSAMtype = {"None"}; P1.outBAMunsorted = false; P1.outBAMcoord = false; P1.unmappedWithin = false; P1.unmappedKeepPairs = false;
         P1.outFileNamePrefix = P.twoPassDir;
+        P1.outReadsUnmapped = "None";   // twoPassRunPass1.cpp:24-33: no unmapped-read files, no quantification in the 1st pass
         const uint64_t nMax = std::min<uint64_t>(P.twopass1readsN, (uint64_t)P.readMapNumber);
         P1.readMapNumber = nMax > (uint64_t)INT64_MAX ? -1 : (long long)nMax;
         Stats st1;
@@ -684,6 +688,7 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
     std::vector<Junction> allSJ;
     int64_t tStart = 0, tStartMap = 0, tFinish = 0;
     const bool samYes = !(P.outSAMtype[0] == "None" || P.outSAMmode == "None");
+    const bool bySJ = P.outFilterType == "BySJout";   // only then do the shards hold ".stage2" parts
     const std::string alnName = P.outBAMunsorted ? "Aligned.out.bam" : "Aligned.out.sam";
     std::ofstream samOut;
     const bool streamYes = samYes && (P.outSAMtype[0] == "SAM" || P.outBAMunsorted);
@@ -717,7 +722,7 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
     if (P.quantTrSAM) {   // Aligned.toTranscriptome.out.bam: header of shard 0, then the parts in the reference's order
         std::ofstream to(P.outFileNamePrefix + "Aligned.toTranscriptome.out.bam", std::ios::binary);
         for (const char* part : {"", ".stage2"})
-            for (int r = 0; r < nShards; r++) {
+            for (int r = 0; r < nShards && (part[0] == 0 || bySJ); r++) {
                 std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Aligned.toTranscriptome.out" + part + ".bam", std::ios::binary);
                 if (in.good()) { to << in.rdbuf(); to.clear(); }
             }
@@ -727,7 +732,7 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
         for (unsigned m = 0; m < P.readNmates; m++) {
             std::ofstream uo(P.outFileNamePrefix + "Unmapped.out.mate" + std::to_string(m + 1), std::ios::binary);
             for (const char* part : {"", ".stage2"})
-                for (int r = 0; r < nShards; r++) {
+                for (int r = 0; r < nShards && (part[0] == 0 || bySJ); r++) {
                     std::ifstream in(P.outFileNamePrefix + "shard" + std::to_string(r) + ".Unmapped.out" + part + ".mate" + std::to_string(m + 1), std::ios::binary);
                     if (in.good()) { uo << in.rdbuf(); uo.clear(); }
                 }
@@ -737,6 +742,7 @@ static int mergeShards(int argc, char** argv, int nShards, const uint64_t* count
         std::vector<CoordRec> index;
         for (int r = 0; r < nShards; r++)
             for (const char* part : {"coord.bin", "coord.stage2.bin"}) {
+                if (!bySJ && std::string(part) != "coord.bin") continue;   // stage-2 parts exist only in a BySJout run; never pick up leftovers
                 const std::string fn = P.outFileNamePrefix + "shard" + std::to_string(r) + "." + part;
                 if (!readCoordShard(fn, blobs, index) && std::string(part) == "coord.bin" && !(P.outFilterType == "BySJout")) {
                     std::cerr << "EXITING because of FATAL ERROR: missing shard output " << fn << "\n";

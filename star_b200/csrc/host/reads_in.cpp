@@ -103,14 +103,16 @@ int ReadsReader::open(const HostParams& Pin, std::string& err) {
             int rc = openFile(fi, err);
             if (rc) return rc;
             if (fast) {
-                uint64_t lines = 0;
+                uint64_t lines = 0, lastText = 0;   // lastText: number of lines up to the last non-empty one (trailing blank lines end the input)
                 for (size_t off = 0; off < mapSize[0];) {
                     const char* q = (const char*)memchr(map[0] + off, '\n', mapSize[0] - off);
                     lines++;
+                    const size_t len = q ? (size_t)(q - map[0]) - off : mapSize[0] - off;
+                    if (len > 0 && !(len == 1 && map[0][off] == '\r')) lastText = lines;
                     if (!q) break;
                     off = (size_t)(q - map[0]) + 1;
                 }
-                recs[fi] = lines / 4;
+                recs[fi] = (lastText + 3) / 4;   // the same rule as nextFast: a last record with missing lines is still a record
             } else {
                 std::string line;
                 const bool fq = peekChar(0) == '@';
@@ -307,13 +309,17 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     std::vector<const char*>* en = lineEn_;
     for (int m = 0; m < 2; m++) { st[m].clear(); en[m].clear(); }
     size_t newOff[2] = {mapOff[0], mapOff[1]};
+    long long badOff = -1;   // offset of a record start (mate 1) that is neither '@' nor end of input
     auto indexMate = [&](unsigned m) {
         st[m].reserve(4 * want); en[m].reserve(4 * want);
         const char* base = map[m];
         const size_t size = mapSize[m];
         size_t off = mapOff[m];
         for (uint64_t k = 0; k < 4 * want && off < size; k++) {
-            if (m == 0 && (k & 3) == 0 && base[off] != '@') break;   // end of the records (e.g. trailing blank line)
+            if (m == 0 && (k & 3) == 0 && base[off] != '@') {        // end of the records (e.g. trailing blank line) ...
+                if (base[off] != ' ' && base[off] != '\n') badOff = (long long)off;   // ... or text that is not a record: fatal in the reference
+                break;
+            }
             const char* q = (const char*)memchr(base + off, '\n', size - off);
             st[m].push_back(base + off);
             if (q) { en[m].push_back(q); off = (size_t)(q - base) + 1; }
@@ -323,6 +329,13 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     };
     if (nMates == 2) { std::thread t1(indexMate, 1u); indexMate(0); t1.join(); } else indexMate(0);
     const uint64_t nRec = (st[0].size() + 3) / 4;   // a last record with missing lines is still a record (its errors are reported)
+    if (nRec == 0 && badOff >= 0) {                 // the records before the offending line are mapped first, as the reference's chunker does
+        const char* b = map[0] + badOff;
+        const char* q = (const char*)memchr(b, '\n', mapSize[0] - (size_t)badOff);
+        err = "EXITING because of FATAL ERROR in input reads: wrong read ID line format: the read ID lines should start with @ or > \nOffending line for read # " +
+              std::to_string(iReadAll + 1) + "\n" + std::string(b, q ? (size_t)(q - b) : mapSize[0] - (size_t)badOff) + "\nSOLUTION: verify and correct the input read files\n";
+        return -STAR_EXIT_INPUT_FILES;
+    }
     if (nRec == 0) return 0;
     if (nMates == 2 && st[1].size() > 4 * nRec) {   // mate 2 was indexed further than mate 1 has records: rewind it to the record boundary
         st[1].resize(4 * nRec); en[1].resize(4 * nRec);
@@ -418,7 +431,14 @@ long long ReadsReader::nextStream(ReadChunk& c, uint32_t maxReads, std::string& 
         if (P->readMapNumber >= 0 && (long long)iReadAll >= P->readMapNumber) break;  // processChunks.cpp:25
         if (iReadAll >= shardHi) break;                                               // end of this process' slice (multi-GPU)
         int ch = peekChar(0);
-        if (ch != '@' && ch != '>') break;  // end of stream (:198-200)
+        if (ch != '@' && ch != '>') {
+            if (ch == ' ' || ch == '\n' || ch < 0) break;   // end of stream (ReadAlignChunk_processChunks.cpp:192-194)
+            std::string rest;                              // anything else at a record boundary is fatal there (:199-207)
+            getLine(0, rest);
+            err = "EXITING because of FATAL ERROR in input reads: wrong read ID line format: the read ID lines should start with @ or > \nOffending line for read # " +
+                  std::to_string(iReadAll + 1) + "\n" + rest + "\nSOLUTION: verify and correct the input read files\n";
+            return -STAR_EXIT_INPUT_FILES;
+        }
         bool fastq = ch == '@';
         c.fastq = fastq;
         iReadAll++;

@@ -51,6 +51,22 @@ def test_input_error_in_a_late_chunk_stops_the_run(oracle, golden, tmp_path):
     assert "FATAL ERROR, exiting" in r.stderr
 
 
+@pytest.mark.parametrize("piped", [False, True])
+def test_text_that_is_not_a_record_is_fatal(oracle, golden, tmp_path, piped):
+    """ReadAlignChunk_processChunks.cpp:192-207: at a record boundary only '@' / '>' start a record and only a blank / end of file ends the
+    input; anything else is the reference's 'wrong read ID line format' error (exit 104), not a silent end of the input.  Both parsers
+    (memory-mapped files; the stream parser behind --readFilesCommand)."""
+    with open(os.path.join(golden, "se_1.fq")) as f:
+        lines = f.read().split("\n")
+    bad = lines[:4 * 100] + ["garbage that is not a record"] + lines[4 * 100:]
+    fq = str(tmp_path / "bad.fq")
+    open(fq, "w").write("\n".join(bad))
+    extra = ["--gpuChunkReads", "64"] + (["--readFilesCommand", "cat"] if piped else [])
+    r = _cli(os.path.join(golden, "idx"), [fq], str(tmp_path) + "/o/", extra, check=False)
+    assert r.returncode == 104
+    assert "wrong read ID line format" in r.stderr and "garbage that is not a record" in r.stderr
+
+
 @pytest.mark.parametrize("world", [3])
 def test_shards_partition_the_reads_in_order(oracle, golden, tmp_path, world):
     """--gpuShardIndex/--gpuShardCount: contiguous slices by record index, every read in exactly one shard, global read numbering kept."""
