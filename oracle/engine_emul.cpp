@@ -461,6 +461,7 @@ static void emSelect(const u32* in, const u8* flag, u32* out, u64 n, u64* nSel) 
 #define SA_MAX_SCAN(a, n) starb::emMaxScan(a, n)
 #define SA_SELECT(in, flag, out, n, nSel) starb::emSelect(in, flag, out, n, nSel)
 #define SA_SYNC() ((void)0)
+#define SA_ZERO(p, bytes) memset(p, 0, bytes)
 #define SA_SORT_PAIRS64(kIn, kOut, vIn, vOut, n, endBit) starb::emSortPairs64(kIn, kOut, vIn, vOut, n, endBit)
 #define SA_MAX_SCAN64(a, n) starb::emMaxScan64(a, n)
 #define SA_SELECT_IF(f, lo, hi, out, nSel) starb::emSelectIf(f, lo, hi, out, nSel)
@@ -475,7 +476,15 @@ int engine_emul_sa_build(int, const uint8_t* G, uint64_t nGenome, uint32_t Gstra
     u64 rounds = 0;
     u64 largeCap = 0;   // STAR_B200_SA_LARGE_CAP=<elements per sort>: the batched 64-bit path of sa_build_large.cuh
     if (const char* e = getenv("STAR_B200_SA_LARGE_CAP")) largeCap = strtoull(e, nullptr, 10);
-    const int rc = largeCap ? saBuildRunLarge(G, nGenome, GstrandBit, nSA, out.data(), largeCap, &rounds) : saBuildRun(G, nGenome, GstrandBit, nSA, out.data(), &rounds);
+    int rc;
+    if (largeCap) {   // (the large path releases its genome copy early and allocates the packed output late)
+        u8* Gc = (u8*)emAlloc(nGenome);
+        memcpy(Gc, G, nGenome);
+        u64* ow = nullptr;
+        rc = saBuildRunLarge(Gc, nGenome, GstrandBit, nSA, &ow, outWords, largeCap, &rounds);
+        if (!rc) memcpy(out.data(), ow, outWords * 8);
+        free(ow);
+    } else rc = saBuildRun(G, nGenome, GstrandBit, nSA, out.data(), &rounds);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: sa_build rc %d after %llu rounds\n", rc, (unsigned long long)rounds);
     if (rc == 4) return STAR_EXIT_PARAMETER;   // a bin or a tied group exceeds the forced capacity
     if (rc) return STAR_EXIT_BUG;

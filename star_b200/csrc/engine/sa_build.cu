@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -106,6 +107,7 @@ template <class F> static void saSelectIf(F f, u64 lo, u64 hi, u64* out, u64* nS
 #define SA_MAX_SCAN(a, n) starb::saMaxScan(a, n)
 #define SA_SELECT(in, flag, out, n, nSel) starb::saSelect(in, flag, out, n, nSel)
 #define SA_SYNC() starb::saNote(cudaDeviceSynchronize())
+#define SA_ZERO(p, bytes) starb::saNote(cudaMemset(p, 0, bytes))
 #include "sa_build_large.cuh"
 
 using namespace starb;
@@ -132,15 +134,30 @@ extern "C" int star_gpu_sa_build(int device, const uint8_t* G, uint64_t nGenome,
     g_saErr = cudaSuccess;
     u8* dG = (u8*)saAlloc(nGenome);
     const u64 outWords = (nSA + 63) / 64 * (GstrandBit + 1) + 2;
-    u64* dOut = (u64*)saAlloc(outWords * 8);
+    u64* dOut = nullptr;
     int rc = 3;
-    if (dG && dOut) {
+    u64 rounds = 0;
+    const bool timing = getenv("STAR_B200_SA_DEBUG") != nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (dG) {
         saNote(cudaMemcpy(dG, G, nGenome, cudaMemcpyHostToDevice));
-        saNote(cudaMemset(dOut, 0, outWords * 8));
-        u64 rounds = 0;
-        rc = largeCap ? saBuildRunLarge(dG, nGenome, GstrandBit, nSA, dOut, largeCap, &rounds) : saBuildRun(dG, nGenome, GstrandBit, nSA, dOut, &rounds);
+        cudaEventRecord(e0);
+        if (largeCap) {   // releases dG once the text exists, allocates the packed output after the ranks are gone (peak memory)
+            rc = saBuildRunLarge(dG, nGenome, GstrandBit, nSA, &dOut, outWords, largeCap, &rounds);
+            dG = nullptr;
+        } else {
+            dOut = (u64*)saAlloc(outWords * 8);
+            if (dOut) {
+                saNote(cudaMemset(dOut, 0, outWords * 8));
+                rc = saBuildRun(dG, nGenome, GstrandBit, nSA, dOut, &rounds);
+            }
+        }
+        cudaEventRecord(e1);
         if (rc == 0 && nSAbyte <= outWords * 8) saNote(cudaMemcpy(SA, dOut, nSAbyte, cudaMemcpyDeviceToHost));
+        if (timing) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); fprintf(stderr, "star_b200 sa_build: n=%llu %s path, %llu rounds, %.1f ms on the device, rc %d\n", (unsigned long long)(2 * nGenome), largeCap ? "batched 64-bit" : "32-bit", (unsigned long long)rounds, ms, rc); }
     }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(dG); cudaFree(dOut);
     if (g_saErr != cudaSuccess) { setLastError(std::string("CUDA error in the suffix-array build: ") + cudaGetErrorString(g_saErr)); return g_saErr == cudaErrorMemoryAllocation ? STAR_EXIT_MEMORY_ALLOCATION : STAR_EXIT_RUNTIME; }
     if (rc == 3) { setLastError("star_b200: out of device memory for the suffix-array build"); return STAR_EXIT_MEMORY_ALLOCATION; }

@@ -10,9 +10,12 @@
 //             sorted, and written back into the group's own slots with refined ranks.  Ranks are refined in place: a later batch may
 //             read ranks already refined in this round, which only sharpens its keys (rank[a] < rank[b] always implies suffix a <
 //             suffix b).  Stops when a round finds nothing active.
-//   output    positions holding a base, in order, compacted batch by batch into one array and packed.
-// HBM at n positions: text n + order 8n + max(rank 8n + 4 x 8 x cap work buffers + sort scratch, 8 x nSA) bytes, plus the caller's genome and
-// packed output (GRCh38 with cap = 7e8: ~170 GB at the peak of the sort rounds, ~130 GB while packing).
+//   heads     one byte per order slot says "a group starts here"; it is written by the same kernels that write the order, so a round finds
+//             its active slots (members of groups with more than one member) by streaming that array — no gather through rank[order[j]].
+//   output    the first code is the most significant digit of every key, so the positions holding a base (codes 0..3) are exactly the first
+//             nSA order slots: they are packed straight from `order`, nothing is compacted.
+// HBM at n positions: text n + heads n + order 8n + rank 8n + 4 x 8 x cap work buffers + sort scratch (~2 x 8 x cap); the genome copy is
+// released once the text exists and the packed output is allocated after the ranks are released (GRCh38 with cap = 7e8: ~146 GB at the peak).
 // Limits: n < 2^33, cap <= 2^31, no single 4-mer bin and no single tied group larger than cap.
 // Written against the SA_* macros of sa_build_impl.cuh plus SA_SELECT_IF / SA_MAX_SCAN64 / SA_SORT_PAIRS64.
 #pragma once
@@ -30,17 +33,9 @@ struct SaBinInRange {   // position p starts with a 4-code prefix whose bin is i
         return b >= b0 && b < b1;
     }
 };
-struct SaActive {       // order slot j belongs to a group of more than one member (rank = first slot of the group)
-    const u64* rank; const u64* order; u64 n;
-    __host__ __device__ bool operator()(u64 j) const {
-        const bool head = rank[order[j]] == j;
-        const bool nextHead = j + 1 >= n || rank[order[j + 1]] == j + 1;
-        return !(head && nextHead);
-    }
-};
-struct SaIsBase {       // order slot j holds a position with a base
-    const u8* T; const u64* order;
-    __host__ __device__ bool operator()(u64 j) const { return T[order[j]] < 4; }
+struct SaActive {       // order slot j belongs to a group of more than one member (head[j]: a group starts at slot j; head[n] = 1)
+    const u8* head;
+    __host__ __device__ bool operator()(u64 j) const { return !(head[j] && head[j + 1]); }
 };
 
 __global__ void __launch_bounds__(256) sal_hist_kernel(const u8* __restrict__ T, u64 n, unsigned long long* __restrict__ hist) {
@@ -66,10 +61,13 @@ __global__ void __launch_bounds__(256) sal_heads0_kernel(const u64* __restrict__
         hd[i] = (i == 0 || k != key[i - 1] || saHas5(k)) ? i + 1 : 0;
     }
 }
-__global__ void __launch_bounds__(256) sal_write0_kernel(const u64* __restrict__ pos, const u64* __restrict__ hd, u64 m, u64 base, u64* __restrict__ order, u64* __restrict__ rank) {
+// (hd after the max-scan: index + 1 of the latest head at or before i; i is a head itself iff hd[i] == i + 1)
+__global__ void __launch_bounds__(256) sal_write0_kernel(const u64* __restrict__ pos, const u64* __restrict__ hd, u64 m, u64 base, u64* __restrict__ order, u64* __restrict__ rank,
+                                                         u8* __restrict__ head) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
         order[base + i] = pos[i];
         rank[pos[i]] = base + hd[i] - 1;
+        head[base + i] = hd[i] == i + 1;
     }
 }
 __global__ void __launch_bounds__(256) sal_key_kernel(const u64* __restrict__ rank, const u64* __restrict__ order, const u64* __restrict__ slot, u64 m, u64 a, u64 h, u64 n,
@@ -91,15 +89,14 @@ __global__ void __launch_bounds__(256) sal_heads_kernel(const u64* __restrict__ 
     }
 }
 __global__ void __launch_bounds__(256) sal_write_kernel(const u64* __restrict__ key, const u64* __restrict__ val, const u64* __restrict__ gh, const u64* __restrict__ nh, u64 m, u64 a,
-                                                        u64* __restrict__ order, u64* __restrict__ rank) {
+                                                        u64* __restrict__ order, u64* __restrict__ rank, u8* __restrict__ head) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
         const u64 r1 = a + (key[i] >> 33);
-        order[r1 + (i + 1 - gh[i])] = val[i];
+        const u64 slot = r1 + (i + 1 - gh[i]);
+        order[slot] = val[i];
         rank[val[i]] = r1 + (nh[i] - gh[i]);
+        head[slot] = nh[i] == i + 1;     // this member opens a (sub-)group: the old group's first slot stays a head, new ones appear inside it
     }
-}
-__global__ void __launch_bounds__(256) sal_gather_kernel(const u64* __restrict__ order, const u64* __restrict__ slot, u64 m, u64* __restrict__ out) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) out[i] = order[slot[i]];
 }
 // as sa_pack_kernel, 64-bit positions
 __global__ void __launch_bounds__(128) sal_pack_kernel(const u64* __restrict__ sa, u64 nSA, u64 nGenome, u32 GstrandBit, u64* __restrict__ out) {
@@ -136,26 +133,38 @@ __global__ void __launch_bounds__(128) sal_pack_kernel(const u64* __restrict__ s
 }
 
 #ifdef SA_LAUNCH
-// Returns 0, or: 1 = number of bases differs from nSA, 2 = no convergence, 3 = out of memory, 4 = a 4-mer bin or a tied group exceeds cap.
-inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u64* outWords, u64 cap, u64* roundsOut) {
+// dG: device copy of G, RELEASED here as soon as the text exists.  *outWordsPtr: allocated here (nOutWords zeroed words) once the ranks
+// are released; the caller frees it.  Returns 0, or: 1 = number of bases differs from nSA, 2 = no convergence, 3 = out of memory,
+// 4 = a 4-mer bin or a tied group exceeds cap.
+inline int saBuildRunLarge(u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u64** outWordsPtr, u64 nOutWords, u64 cap, u64* roundsOut) {
     const u64 n = 2 * nGenome, padT = 64;
-    if (n >= (1ULL << 33) || cap > (1ULL << 31) || cap < 64) return 4;
+    *outWordsPtr = nullptr;
+    if (n >= (1ULL << 33) || cap > (1ULL << 31) || cap < 64) { SA_FREE(dG); return 4; }
     u8* T = (u8*)SA_ALLOC(n + padT);
+    if (T) SA_LAUNCH(n + padT, sa_text_kernel, dG, nGenome, T, padT);
+    SA_SYNC();
+    SA_FREE(dG);
+    u8* head = (u8*)SA_ALLOC(n + 1);
     u64* rank = (u64*)SA_ALLOC((n + 1) * 8);
     u64* order = (u64*)SA_ALLOC(n * 8);
     u64 *keyA = (u64*)SA_ALLOC(cap * 8), *keyB = (u64*)SA_ALLOC(cap * 8), *valA = (u64*)SA_ALLOC(cap * 8), *valB = (u64*)SA_ALLOC(cap * 8);
     unsigned long long* hist = (unsigned long long*)SA_ALLOC(4096 * 8);
-    u64* sa64 = nullptr;
     int rc = 0;
     u64 rounds = 0;
-    if (!T || !rank || !order || !keyA || !keyB || !valA || !valB || !hist) rc = 3;
+    if (!T || !head || !rank || !order || !keyA || !keyB || !valA || !valB || !hist) rc = 3;
     if (!rc) {
-        SA_LAUNCH(n + padT, sa_text_kernel, dG, nGenome, T, padT);
         SA_COPY_TO(rank + n, &n, 8);
+        const u8 one = 1;
+        SA_COPY_TO(head + n, &one, 1);
         std::vector<unsigned long long> h4(4096, 0);
         SA_COPY_TO(hist, h4.data(), 4096 * 8);
         SA_LAUNCH(n, sal_hist_kernel, T, n, hist);
         SA_COPY_FROM(h4.data(), hist, 4096 * 8);
+        {   // positions that start with a base = bins whose first digit is 0..3 = the first nSA slots of the final order
+            u64 nBase = 0;
+            for (u32 b = 0; b < 4096; b++) if ((b >> 9) < 4) nBase += h4[b];
+            if (nBase != nSA) rc = 1;
+        }
         // ---- round 0: runs of bins
         u64 base = 0;
         for (u32 b0 = 0; b0 < 4096 && !rc;) {
@@ -171,7 +180,7 @@ inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u
                 SA_SORT_PAIRS64(keyA, keyB, valA, valB, m, 3 * SA_K0);
                 SA_LAUNCH(m, sal_heads0_kernel, keyB, m, keyA);
                 SA_MAX_SCAN64(keyA, m);
-                SA_LAUNCH(m, sal_write0_kernel, valB, keyA, m, base, order, rank);
+                SA_LAUNCH(m, sal_write0_kernel, valB, keyA, m, base, order, rank, head);
                 base += m;
             }
             b0 = b1;
@@ -191,14 +200,14 @@ inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u
                     b = gs;
                 }
                 u64 m = 0;
-                SA_SELECT_IF((SaActive{rank, order, n}), a, b, valA, &m);   // active slots of the batch
+                SA_SELECT_IF((SaActive{head}), a, b, valA, &m);   // active slots of the batch
                 if (m) {
                     SA_LAUNCH(m, sal_key_kernel, rank, order, valA, m, a, h, n, keyA, valB);
                     SA_SORT_PAIRS64(keyA, keyB, valB, valA, m, 64);           // sorted keys in keyB, positions in valA
                     SA_LAUNCH(m, sal_heads_kernel, keyB, m, keyA, valB);
                     SA_MAX_SCAN64(keyA, m);
                     SA_MAX_SCAN64(valB, m);
-                    SA_LAUNCH(m, sal_write_kernel, keyB, valA, keyA, valB, m, a, order, rank);
+                    SA_LAUNCH(m, sal_write_kernel, keyB, valA, keyA, valB, m, a, order, rank, head);
                     active += m;
                 }
                 a = b;
@@ -210,28 +219,19 @@ inline int saBuildRunLarge(const u8* dG, u64 nGenome, u32 GstrandBit, u64 nSA, u
         }
     }
     SA_SYNC();
-    SA_FREE(keyA); SA_FREE(keyB); SA_FREE(valB); SA_FREE(hist); SA_FREE(rank);   // (the order is final: the ranks are not needed any more)
-    keyA = keyB = valB = nullptr; rank = nullptr;
+    SA_FREE(keyA); SA_FREE(keyB); SA_FREE(valA); SA_FREE(valB); SA_FREE(hist); SA_FREE(rank); SA_FREE(head); SA_FREE(T);   // (the order is final)
     if (!rc) {
-        sa64 = (u64*)SA_ALLOC((nSA + 64) * 8);
-        if (!sa64) rc = 3;
-    }
-    if (!rc) {
-        u64 got = 0;
-        for (u64 a = 0; a < n && !rc; a += cap) {
-            const u64 b = a + cap < n ? a + cap : n;
-            u64 m = 0;
-            SA_SELECT_IF((SaIsBase{T, order}), a, b, valA, &m);
-            if (got + m > nSA) { rc = 1; break; }
-            if (m) SA_LAUNCH(m, sal_gather_kernel, order, valA, m, sa64 + got);
-            got += m;
+        u64* outWords = (u64*)SA_ALLOC(nOutWords * 8);
+        if (!outWords) rc = 3;
+        else {
+            SA_ZERO(outWords, nOutWords * 8);
+            SA_LAUNCH_PACK(nSA, GstrandBit + 1, sal_pack_kernel, order, nSA, nGenome, GstrandBit, outWords);
+            *outWordsPtr = outWords;
         }
-        if (!rc && got != nSA) rc = 1;
-        if (!rc) SA_LAUNCH_PACK(nSA, GstrandBit + 1, sal_pack_kernel, sa64, nSA, nGenome, GstrandBit, outWords);
     }
     SA_SYNC();
     if (roundsOut) *roundsOut = rounds;
-    SA_FREE(T); SA_FREE(rank); SA_FREE(order); SA_FREE(valA); SA_FREE(sa64);
+    SA_FREE(order);
     return rc;
 }
 #endif

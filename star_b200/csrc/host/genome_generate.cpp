@@ -4,13 +4,19 @@
 // chr*.txt (writeChrInfo, :417-432), SAindex (genomeSAindex.cpp:6-220), genomeParameters.txt (genomeParametersWrite.cpp:4-46) and the
 // junction insertion shared with the mapping stage (sjdb_insert.cpp).  The suffix sort — hours of qsort over 16-mer buckets in the
 // reference (:213-330) — is the device step behind star_gpu_sa_build (star_b200/csrc/engine/sa_build.cu).
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "host.h"
 
@@ -52,6 +58,12 @@ uint64_t calcSAiFromSA(const uint8_t* G, const PackedRW& SA, uint64_t nGenome, u
 
 int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& logMain, std::string& err) {
     const std::string& gDir = P.genomeDir;
+    auto tPhase = std::chrono::steady_clock::now();
+    auto phaseDone = [&](const char* what) {   // wall time of every phase in Log.out (the build is minutes for a mammalian genome: say where they go)
+        const auto now = std::chrono::steady_clock::now();
+        logMain << "   [" << what << ": " << std::chrono::duration<double>(now - tPhase).count() << " s]" << std::endl;
+        tPhase = now;
+    };
     // Genome_genomeGenerate.cpp:113-133
     const bool annot = P.sjdbFileChrStartEnd[0] != "-" || P.sjdbGTFfile != "-";
     uint64_t sjdbOverhang = P.sjdbOverhang;
@@ -77,21 +89,39 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
     Gs.assign(PAD, 5);
     uint64_t N = 0;
     auto padTo = [&](uint64_t n) { if (Gs.size() < PAD + n) Gs.resize(PAD + n, 5); };
+    uint8_t lut[256];   // convertNucleotidesToNumbersRemoveControls (SequenceFuns.cpp:170-192): 0..3, 4 = any other printable, 255 = control character
+    for (int c = 0; c < 256; c++) lut[c] = c < 32 ? 255 : 4;
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+    {
+        uint64_t total = 0;
+        for (const std::string& fn : P.genomeFastaFiles) { struct stat sb; if (stat(fn.c_str(), &sb) == 0) total += (uint64_t)sb.st_size; }
+        Gs.reserve(PAD + total + total / 8 + 2 * binN * 64 + 2 * PAD);
+    }
     for (const std::string& fn : P.genomeFastaFiles) {
-        std::ifstream in(fn);
-        if (!in.good()) { err = "EXITING because of INPUT ERROR: could not open genomeFastaFile: " + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
-        const int cc = in.peek();
-        if (!in.good()) { err = "EXITING because of INPUT ERROR: could not read from genomeFastaFile: " + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
+        // the file is mapped and walked line by line (the reference reads it with getline, genomeScanFastaFiles.cpp:24-78)
+        const int fd = open(fn.c_str(), O_RDONLY);
+        if (fd < 0) { err = "EXITING because of INPUT ERROR: could not open genomeFastaFile: " + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || sb.st_size == 0) { close(fd); err = "EXITING because of INPUT ERROR: could not read from genomeFastaFile: " + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
+        const size_t fsize = (size_t)sb.st_size;
+        const char* text = (const char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (text == MAP_FAILED) { err = "EXITING because of INPUT ERROR: could not read from genomeFastaFile: " + fn + "\n"; return STAR_EXIT_INPUT_FILES; }
+        madvise((void*)text, fsize, MADV_SEQUENTIAL);
+        const int cc = (unsigned char)text[0];
         if (cc != '>') {
+            munmap((void*)text, fsize);
             err = "EXITING because of INPUT ERROR: the file format of the genomeFastaFile: " + fn + " is not fasta: the first character is '" + std::string(1, (char)cc) + "' (" + std::to_string(cc) +
                   "), not '>'.\n Solution: check formatting of the fasta file. Make sure the file is uncompressed (unzipped).\n";
             return STAR_EXIT_INPUT_FILES;
         }
-        std::string line;
-        while (!in.eof()) {
-            std::getline(in, line);
-            if (!line.empty() && line[0] == '>') {
-                std::istringstream ls(line);
+        for (size_t off = 0; off < fsize;) {
+            const char* nl = (const char*)memchr(text + off, '\n', fsize - off);
+            const size_t len = nl ? (size_t)(nl - (text + off)) : fsize - off;
+            const char* line = text + off;
+            off += len + 1;
+            if (len > 0 && line[0] == '>') {
+                std::istringstream ls(std::string(line, len));
                 ls.ignore(1, ' ');
                 std::string name;
                 ls >> name;
@@ -101,26 +131,22 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
                 idx.chrStart.push_back(N);
                 padTo(N);
                 logMain << fn << " : chr # " << idx.chrStart.size() - 1 << "  \"" << name << "\" chrStart: " << N << "\n";
-            } else {   // convertNucleotidesToNumbersRemoveControls (SequenceFuns.cpp:170-192): control characters are dropped from the COUNT only
-                padTo(N + line.size());
+            } else {   // control characters are dropped from the COUNT only (the reference's quirk): a code lands at the character's column
+                padTo(N + len);
+                uint8_t* dst = Gs.data() + PAD + N;
                 uint64_t kept = 0;
-                for (size_t jj = 0; jj < line.size(); jj++) {
-                    const int c = (unsigned char)line[jj];
-                    uint8_t v;
-                    switch (c) {
-                        case 'A': case 'a': v = 0; break;
-                        case 'C': case 'c': v = 1; break;
-                        case 'G': case 'g': v = 2; break;
-                        case 'T': case 't': v = 3; break;
-                        default: if (c < 32) continue; v = 4;
-                    }
-                    Gs[PAD + N + jj] = v;
+                for (size_t jj = 0; jj < len; jj++) {
+                    const uint8_t v = lut[(unsigned char)line[jj]];
+                    if (v == 255) continue;
+                    dst[jj] = v;
                     kept++;
                 }
                 N += kept;
             }
         }
+        munmap((void*)text, fsize);
     }
+    phaseDone("FASTA scan");
     if (idx.chrStart.empty()) { err = "EXITING because of INPUT ERROR: no sequences in --genomeFastaFiles\n"; return STAR_EXIT_INPUT_FILES; }
     idx.chrLength.push_back(N - idx.chrStart.back());
     N = ((N + 1) / binN + 1) * binN;
@@ -159,6 +185,7 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
     { time_t t; time(&t); char b[100]; strftime(b, 80, "%b %d %H:%M:%S", localtime(&t)); std::cout << b << " ... starting to sort Suffix Array. This may take a long time...\n" << std::flush; }
     int rc = eng->sa_build(P.gpuDevice, Gs.data() + PAD, nGenome, GstrandBit, nSA, idx.SAstore.data(), nSAbyte);
     if (rc) { err = std::string("EXITING because of FATAL ERROR: suffix array generation failed: ") + eng->last_error() + "\n"; return rc; }
+    phaseDone("suffix array (device sort + copies)");
 
     // ---- SAindex, genomeSAindex.cpp:6-220 (the jump + bisect walk over runs of equal prefixes)
     { time_t t; time(&t); char b[100]; strftime(b, 80, "%b %d %H:%M:%S", localtime(&t)); std::cout << b << " ... generating Suffix Array index\n" << std::flush; }
@@ -169,48 +196,120 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
     const uint64_t nSAibyte = (nSAi - 1) * (GstrandBit + 3) / 8 + 8;
     idx.SAistore.assign(nSAibyte + 16, 0);
     {
+        // The reference walks the rows once, from run to run of equal (prefix, offset of the first base > 3), jump + bisect
+        // (funSAiFindNextIndex), keeping per prefix length the last prefix seen.  The same walk is cut into row ranges that start at run
+        // heads, one per host thread: what a range needs from the rows before it — the last prefix present at every length — is read off
+        // the rows in front of its first row, the entries are collected unpacked (threads own disjoint entries but share packed words),
+        // the "contains N" marks are applied after the join, and the table is packed by 64-entry groups (whole words) in parallel.
         const uint8_t* G = Gs.data() + PAD;
-        PackedRW SA(idx.SAstore.data(), GstrandBit + 1), SAi(idx.SAistore.data(), GstrandBit + 3);
+        const PackedRW SA(idx.SAstore.data(), GstrandBit + 1);
         const uint64_t nC = 1ULL << (GstrandBit + 1), absentC = 1ULL << (GstrandBit + 2);
         const uint64_t* start = idx.genomeSAindexStart.data();
-        std::vector<uint64_t> ind0(Lmax, ~0ULL);   // last prefix seen per length (-1: none yet)
-        const uint64_t isaStep = nSA / (1ULL << (2 * Lmax)) + 1;
-        uint64_t isa = 0;
-        int iL4;
-        uint64_t indFull = calcSAiFromSA(G, SA, nGenome, GstrandBit, isa, Lmax, iL4);
-        while (isa <= nSA - 1) {
-            for (uint32_t iL = 0; iL < Lmax; iL++) {
-                const uint64_t indPref = indFull >> (2 * (Lmax - 1 - iL));
-                if ((int)iL == iL4) {   // a base > 3 inside the prefix: flag the last present prefix of every longer length
-                    for (uint32_t iL1 = iL; iL1 < Lmax; iL1++) SAi.set(start[iL1] + ind0[iL1], SAi.get(start[iL1] + ind0[iL1]) | nC);
-                    break;
-                }
-                if (indPref > ind0[iL] || isa == 0) {
-                    SAi.set(start[iL] + indPref, isa);
-                    for (uint64_t ii = ind0[iL] + 1; ii < indPref; ii++) SAi.set(start[iL] + ii, isa | absentC);
-                    ind0[iL] = indPref;
-                } else if (indPref < ind0[iL]) { err = "BUG: next index is smaller than previous, EXITING\n"; return STAR_EXIT_INPUT_FILES; }
-            }
-            // funSAiFindNextIndex: first row whose (prefix, N offset) differs — steps of isaStep, then bisection
-            const uint64_t indPrev = indFull;
-            const int iL4prev = iL4;
-            isa += isaStep;
-            while (isa < nSA && (indFull = calcSAiFromSA(G, SA, nGenome, GstrandBit, isa, Lmax, iL4)) == indPrev && iL4 == iL4prev) isa += isaStep;
-            if (isa >= nSA) {
-                indFull = calcSAiFromSA(G, SA, nGenome, GstrandBit, nSA - 1, Lmax, iL4);
-                if (indFull == indPrev && iL4 == iL4prev) { isa = nSA; continue; }
-            }
-            uint64_t i1 = isa - isaStep, i2 = std::min(isa, nSA - 1);
-            while (i1 + 1 < i2) {
-                isa = i1 / 2 + i2 / 2 + (i1 % 2 + i2 % 2) / 2;
-                if ((indFull = calcSAiFromSA(G, SA, nGenome, GstrandBit, isa, Lmax, iL4)) == indPrev && iL4 == iL4prev) i1 = isa; else i2 = isa;
-            }
-            if (isa == i1) { isa = i2; indFull = calcSAiFromSA(G, SA, nGenome, GstrandBit, isa, Lmax, iL4); }
+        std::vector<uint64_t> tab(nSAi, 0);
+        const uint64_t NONE = ~0ULL;
+        auto keyOf = [&](uint64_t isa, int& iL4) { return calcSAiFromSA(G, SA, nGenome, GstrandBit, isa, (int)Lmax, iL4); };
+        int nT = std::max(1, std::min(P.runThreadN, 256));
+        if (nSA < 4096 * (uint64_t)nT) nT = 1;
+        std::vector<uint64_t> lo(nT + 1, nSA);
+        lo[0] = 0;
+        for (int t = 1; t < nT; t++) {   // first run head at or after the even split
+            uint64_t r = std::max<uint64_t>(lo[t - 1], nSA / nT * t);
+            if (r == 0) r = 1;
+            int a4, b4;
+            while (r < nSA) { const uint64_t ka = keyOf(r - 1, a4), kb = keyOf(r, b4); if (ka != kb || a4 != b4) break; r++; }
+            lo[t] = r;
         }
-        for (uint32_t iL = 0; iL < Lmax; iL++)
-            for (uint64_t ii = start[iL] + ind0[iL] + 1; ii < start[iL + 1]; ii++) SAi.set(ii, nSA | absentC);
+        struct Mark { uint32_t iL; uint64_t ind; };
+        std::vector<std::vector<Mark>> marks(nT);
+        std::vector<int> bug(nT, 0);
+        std::vector<std::vector<uint64_t>> lastInd(nT);
+        auto work = [&](int t) {
+            const uint64_t r0 = lo[t], r1 = lo[t + 1];
+            std::vector<uint64_t> ind0(Lmax, NONE);
+            if (r0 > 0) {   // last prefix present at every length among the rows before r0
+                uint32_t need = Lmax;
+                for (uint64_t r = r0; r-- > 0 && need > 0;) {
+                    int iL4;
+                    const uint64_t ind = keyOf(r, iL4);
+                    const uint32_t valid = iL4 < 0 ? Lmax : (uint32_t)iL4;   // lengths 1..valid hold bases only
+                    for (uint32_t iL = 0; iL < valid; iL++) if (ind0[iL] == NONE) { ind0[iL] = ind >> (2 * (Lmax - 1 - iL)); need--; }
+                }
+            }
+            const uint64_t isaStep = nSA / (1ULL << (2 * Lmax)) + 1;
+            for (uint64_t isa = r0; isa < r1;) {
+                int iL4;
+                const uint64_t indFull = keyOf(isa, iL4);
+                for (uint32_t iL = 0; iL < Lmax; iL++) {
+                    const uint64_t indPref = indFull >> (2 * (Lmax - 1 - iL));
+                    if ((int)iL == iL4) {   // a base > 3 inside the prefix: mark the last present prefix of every longer length
+                        for (uint32_t iL1 = iL; iL1 < Lmax; iL1++) marks[t].push_back({iL1, ind0[iL1]});   // (ind0 = -1 wraps to the entry in front, as in the reference)
+                        break;
+                    }
+                    if (indPref > ind0[iL] || isa == 0) {   // (unsigned compare: a length without any prefix so far, ind0 = -1, fails both tests unless isa == 0 ...
+                        tab[start[iL] + indPref] = isa;
+                        for (uint64_t ii = ind0[iL] + 1; ii < indPref; ii++) tab[start[iL] + ii] = isa | absentC;
+                        ind0[iL] = indPref;
+                    } else if (indPref < ind0[iL]) { bug[t] = 1; return; }   // ... and ends here like the reference)
+                }
+                // first row of the next run: gallop in steps of isaStep, then bisect (rows of a run are contiguous)
+                uint64_t a = isa, b = isa + isaStep;
+                int b4;
+                while (b < r1 && keyOf(b, b4) == indFull && b4 == iL4) { a = b; b += isaStep; }
+                if (b > r1) b = r1;   // (r1 is a run head or nSA: the run ends at or before it)
+                while (a + 1 < b) {
+                    const uint64_t m = a + (b - a) / 2;
+                    if (keyOf(m, b4) == indFull && b4 == iL4) a = m; else b = m;
+                }
+                isa = b;
+            }
+            lastInd[t] = ind0;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nT; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        for (int t = 0; t < nT; t++) if (bug[t]) { err = "BUG: next index is smaller than previous, EXITING\n"; return STAR_EXIT_INPUT_FILES; }
+        for (int t = 0; t < nT; t++) for (const Mark& m : marks[t]) { const uint64_t e = start[m.iL] + m.ind; if (e < nSAi) tab[e] |= nC; }
+        {   // prefixes behind the last present one
+            const std::vector<uint64_t>& ind0 = lastInd[nT - 1];
+            for (uint32_t iL = 0; iL < Lmax; iL++)
+                for (uint64_t ii = start[iL] + ind0[iL] + 1; ii < start[iL + 1]; ii++) tab[ii] = nSA | absentC;
+        }
+        {   // pack: 64 entries = (GstrandBit+3) whole words
+            const uint32_t bits = GstrandBit + 3;
+            uint64_t* out = reinterpret_cast<uint64_t*>(idx.SAistore.data());   // (vector storage is suitably aligned; nSAibyte + 16 bytes)
+            const uint64_t nGroups = (nSAi + 63) / 64;
+            auto packRange = [&](uint64_t g0, uint64_t g1) {
+                for (uint64_t g = g0; g < g1; g++) {
+                    const uint64_t e0 = g * 64, e1 = std::min<uint64_t>(nSAi, e0 + 64);
+                    uint8_t* base = idx.SAistore.data() + g * bits * 8;
+                    if (e1 - e0 == 64) {
+                        uint64_t* o = reinterpret_cast<uint64_t*>(base);
+                        uint64_t acc = 0; uint32_t sh = 0;
+                        for (uint64_t e = e0; e < e1; e++) {
+                            const uint64_t val = tab[e];
+                            acc |= val << sh;
+                            if (sh + bits >= 64) { *o++ = acc; acc = sh + bits > 64 ? val >> (64 - sh) : 0; }
+                            sh = (sh + bits) & 63;
+                        }
+                    } else {   // last, partial group: entry by entry (the buffer is zero-filled)
+                        PackedRW w(idx.SAistore.data(), bits);
+                        for (uint64_t e = e0; e < e1; e++) w.set(e, tab[e]);
+                    }
+                }
+            };
+            (void)out;
+            std::vector<std::thread> th;
+            const uint64_t per = (nGroups + nT - 1) / nT;
+            for (int t = 1; t < nT; t++) if (per * t < nGroups) th.emplace_back(packRange, per * t, std::min(nGroups, per * (t + 1)));
+            packRange(0, std::min(nGroups, per));
+            for (auto& x : th) x.join();
+        }
     }
 
+    phaseDone("SAindex");
     // ---- the loaded-index view, then the junction inserts (Genome_genomeGenerate.cpp:337-345)
     star_index_view_t& v = idx.view;
     memset(&v, 0, sizeof(v));
@@ -232,6 +331,7 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
         rc = sjdbInsertJunctions(Pi, &P.hp, idx, loci, false, "", eng, logMain, err, /*generateMode*/ true);
         if (rc) return rc;
     }
+    if (annot) phaseDone("junction insertion");
     // ---- genomeParameters.txt (genomeParametersWrite.cpp:4-46), Genome, SA, SAindex
     {
         std::ofstream gp(gDir + "genomeParameters.txt");
@@ -253,6 +353,7 @@ int genomeGenerate(HostParams& P, const star_engine_vtbl_t* eng, std::ostream& l
         sai.write((const char*)idx.genomeSAindexStart.data(), 8 * (nb + 1));
         sai.write((const char*)v.SAi, v.nSAibyte);
     }
+    phaseDone("index files written");
     { time_t t; time(&t); char b[100]; strftime(b, 80, "%b %d %H:%M:%S", localtime(&t)); std::cout << b << " ..... finished successfully\n" << std::flush; }
     return 0;
 }
