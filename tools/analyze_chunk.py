@@ -23,9 +23,10 @@ INFO = np.dtype({"names": ["Lread", "rl0", "rl1", "nP", "nA", "mapMarker", "mult
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 mm = float(sys.argv[2]) if len(sys.argv) > 2 else 0.005
 rl = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-workdir = "/tmp/star_b200_bench/chr21"
+preset = os.environ.get("STAR_B200_BENCH_PRESET", "chr21")
+workdir = os.path.join(os.environ.get("STAR_B200_BENCH_DIR", "/tmp/star_b200_bench"), preset)
 os.makedirs(workdir, exist_ok=True)
-chrs, trs, idx = bench.prepare_genome(workdir, "chr21")
+chrs, trs, idx, _ = bench.prepare_genome(workdir, preset)
 lib = sb.load_library()
 lib.star_gpu_debug_read_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
 index = sb.Index(lib, idx)

@@ -12,6 +12,9 @@ Presets
     small  : 3 chromosomes (2.0/1.2/0.8 Mb), 300 genes        -> fast GPU parity runs
     chr21  : 3 chromosomes (28/12/6.7 Mb = 46.7 Mb), 2000 genes, repeat families, N block
              (the survey's chr21-sized stand-in; BASELINE.json configs[0] analogue)
+    grch38 : 24 chromosomes with the GRCh38 primary-assembly lengths (3.09 Gb), ~27 k multi-exon genes -> ~350 k annotated
+             junctions, the chr21 repeat families scaled x66, one 100 kb N block per chromosome
+             (SURVEY.md §8(d) tier 2: the GRCh38 + GENCODE sized stand-in for BASELINE.json configs[1..4]; index ~29 GB)
 
 Reads: fragment length 300 (fixed), 50 % from spliced transcripts / 50 % from the genome,
 random strand, mate1 = first L bases, mate2 = reverse complement of the last L bases,
@@ -38,12 +41,113 @@ PRESETS = {
                   reps=[(300, 200, 0.05), (6000, 12, 0.02), (1000, 60, 0.10)], nblock=(1_000_000, 5_000)),
     "chr21": dict(chrs=[28_000_000, 12_000_000, 6_700_000], genes=2000,
                   reps=[(300, 3000, 0.05), (6000, 200, 0.02), (1000, 1000, 0.10)], nblock=(10_000_000, 50_000)),
+    # GRCh38 primary assembly chromosome lengths (chr1..22, X, Y)
+    "grch38": dict(chrs=[248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+                         133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                         58617616, 64444167, 46709983, 50818468, 156040895, 57227415], genes=27000,
+                   reps=[(300, 200_000, 0.05), (6000, 13_000, 0.02), (1000, 66_000, 0.10)], nblock=None, big=True),
+    # a 1/8 scale model of the same construction (386 Mb): used to exercise the large-genome code paths quickly
+    "grch38_8th": dict(chrs=[x // 8 for x in [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+                                              138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+                                              83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]],
+                       genes=3400, reps=[(300, 25_000, 0.05), (6000, 1_600, 0.02), (1000, 8_000, 0.10)], nblock=None, big=True),
 }
+
+
+def _make_genome_big(p, seed):
+    """Large presets: same construction as make_genome, generated in blocks / whole families at a time (seconds per Gb)."""
+    rng = np.random.default_rng(seed)
+    total = sum(p["chrs"])
+    g = np.empty(total, dtype=np.uint8)
+    lut = np.tile(ACGT, 64)   # byte -> base
+    step = 1 << 28
+    for lo in range(0, total, step):
+        hi = min(total, lo + step)
+        g[lo:hi] = lut[rng.integers(0, 256, size=hi - lo, dtype=np.uint8)]
+    for (rlen, copies, div) in p["reps"]:
+        cons = ACGT[rng.integers(0, 4, size=rlen, dtype=np.uint8)]
+        batch = max(1, (64 << 20) // rlen)
+        for c0 in range(0, copies, batch):
+            nb = min(batch, copies - c0)
+            starts = rng.integers(0, total - rlen, size=nb)
+            m = np.broadcast_to(cons, (nb, rlen)).copy()
+            mut = rng.random((nb, rlen)) < div
+            m[mut] = ACGT[rng.integers(0, 4, size=int(mut.sum()), dtype=np.uint8)]
+            flip = rng.random(nb) < 0.5
+            m[flip] = COMP[m[flip][:, ::-1]]
+            for k in range(nb):
+                s = int(starts[k])
+                g[s:s + rlen] = m[k]
+    chrs = []
+    off = 0
+    for i, L in enumerate(p["chrs"]):
+        name = "chr%d" % (i + 1) if i < 22 else ("chrX" if i == 22 else "chrY")
+        seq = g[off:off + L]
+        nb_start = int(L * 0.4)
+        seq[nb_start:nb_start + min(100_000, L // 50)] = ord("N")   # one N block per chromosome (centromere stand-in)
+        chrs.append((name, seq))
+        off += L
+    return chrs
+
+
+def _make_annotation_big(chrs, p, seed):
+    """Large presets: genes laid out left to right on every chromosome (random gaps), 4-24 exons of 80-400 bp, introns 200-8000 bp."""
+    rnd = random.Random(seed)
+    total = sum(len(c[1]) for c in chrs)
+    avg_span = 13 * 4100 + 14 * 240
+    gap_avg = max(2000, total // p["genes"] - avg_span)
+    dcode = {"GTAG": (b"GT", b"AG"), "GCAG": (b"GC", b"AG"), "ATAC": (b"AT", b"AC")}
+    trs = []
+    for ci, (_, seq) in enumerate(chrs):
+        L = len(seq)
+        pos = 1000 + rnd.randint(0, gap_avg)
+        while True:
+            n_ex = rnd.randint(4, 24)
+            ex_len = [rnd.randint(80, 400) for _ in range(n_ex)]
+            in_len = [rnd.randint(200, 8000) for _ in range(n_ex - 1)]
+            span = sum(ex_len) + sum(in_len)
+            s = pos
+            e = s + span
+            if e + 1000 >= L:
+                break
+            pos = e + 500 + rnd.randint(0, 2 * gap_avg)
+            if (seq[s:e:97] == ord("N")).any() or (seq[s:e] == ord("N")).any():
+                continue
+            exons = []
+            q = s
+            for k in range(n_ex):
+                exons.append((q, q + ex_len[k]))
+                q += ex_len[k]
+                if k < n_ex - 1:
+                    q += in_len[k]
+            strand = "+" if rnd.random() < 0.5 else "-"
+            for k in range(n_ex - 1):
+                i0 = exons[k][1]
+                i1 = exons[k + 1][0]
+                r = rnd.random()
+                if r < 0.80:
+                    d, a = dcode["GTAG"]
+                elif r < 0.88:
+                    d, a = dcode["GCAG"]
+                elif r < 0.92:
+                    d, a = dcode["ATAC"]
+                else:
+                    continue
+                if strand == "+":
+                    seq[i0:i0 + 2] = np.frombuffer(d, dtype=np.uint8)
+                    seq[i1 - 2:i1] = np.frombuffer(a, dtype=np.uint8)
+                else:
+                    seq[i0:i0 + 2] = COMP[np.frombuffer(a, dtype=np.uint8)[::-1]]
+                    seq[i1 - 2:i1] = COMP[np.frombuffer(d, dtype=np.uint8)[::-1]]
+            trs.append(dict(chr=ci, strand=strand, exons=exons, gid="G%06d" % len(trs)))
+    return trs
 
 
 def make_genome(preset, seed=7):
     """Returns list of (name, uint8 ASCII array)."""
     p = PRESETS[preset]
+    if p.get("big"):
+        return _make_genome_big(p, seed)
     rng = np.random.default_rng(seed)
     total = sum(p["chrs"])
     g = ACGT[rng.integers(0, 4, size=total, dtype=np.uint8)]
@@ -71,6 +175,8 @@ def make_genome(preset, seed=7):
 def make_annotation(chrs, preset, seed=3):
     """Returns list of transcripts: dict(chr index, strand, exons=[(start0, end0_exclusive)...] ascending)."""
     p = PRESETS[preset]
+    if p.get("big"):
+        return _make_annotation_big(chrs, p, seed)
     rnd = random.Random(seed)
     intron_max = 20_000 if preset != "tiny" else 3_000
     trs = []
