@@ -20,21 +20,30 @@
 
 namespace cuda_shim {
 struct Dim { unsigned x, y, z; };
-struct WarpShared { pthread_barrier_t bar; unsigned long long slot[32]; };
+struct WarpShared {
+    pthread_barrier_t bar; unsigned long long slot[32];
+    pthread_barrier_t gbar[4][16];   // sub-warp groups of 2 / 4 / 8 / 16 lanes (collectives whose mask names one aligned group)
+};
 struct CtaShared { pthread_barrier_t bar; WarpShared warp[32]; unsigned nThreads; };
 extern thread_local Dim tIdx, bIdx, bDim, gDim;
 extern thread_local CtaShared* cta;
 inline WarpShared& myWarp() { return cta->warp[tIdx.x >> 5]; }
 inline unsigned laneId() { return tIdx.x & 31; }
 inline void warpWait() { pthread_barrier_wait(&myWarp().bar); }
+// barrier of the lanes named by `mask`: the whole warp, or one aligned group of 2 / 4 / 8 / 16 lanes (the group the caller is in)
+inline void maskWait(unsigned mask) {
+    if (mask == 0xffffffffu) { warpWait(); return; }
+    const int G = __builtin_popcount(mask), lg = __builtin_ctz((unsigned)G) - 1;
+    pthread_barrier_wait(&myWarp().gbar[lg][__builtin_ctz(mask) / G]);
+}
 template <class T> inline unsigned long long toSlot(T v) { unsigned long long s = 0; static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes"); memcpy(&s, &v, sizeof(T)); return s; }
 template <class T> inline T fromSlot(unsigned long long s) { T v; memcpy(&v, &s, sizeof(T)); return v; }
-template <class T> inline T exchange(T v, unsigned src) {   // every lane publishes v, reads lane src
+template <class T> inline T exchange(T v, unsigned src, unsigned mask = 0xffffffffu) {   // every lane (of the mask) publishes v, reads lane src
     WarpShared& w = myWarp();
     w.slot[laneId()] = toSlot(v);
-    warpWait();
+    maskWait(mask);
     T r = fromSlot<T>(w.slot[src & 31]);
-    warpWait();
+    maskWait(mask);
     return r;
 }
 }  // namespace cuda_shim
@@ -45,7 +54,7 @@ template <class T> inline T exchange(T v, unsigned src) {   // every lane publis
 #define gridDim (cuda_shim::gDim)
 
 template <class T> inline T __ldg(const T* p) { return *p; }
-inline void __syncwarp(unsigned = 0xffffffffu) { cuda_shim::warpWait(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { cuda_shim::maskWait(mask); }
 inline void __syncthreads() { pthread_barrier_wait(&cuda_shim::cta->bar); }
 inline void __threadfence_block() { __sync_synchronize(); }
 inline long long clock64() { return 0; }
@@ -60,20 +69,24 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     for (int i = 0; i < 4; i++) r |= (unsigned)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return r;
 }
-inline unsigned __ballot_sync(unsigned, bool p) {
+inline unsigned __ballot_sync(unsigned mask, bool p) {
     cuda_shim::WarpShared& w = cuda_shim::myWarp();
     w.slot[cuda_shim::laneId()] = p ? 1 : 0;
-    cuda_shim::warpWait();
+    cuda_shim::maskWait(mask);
     unsigned m = 0;
-    for (int i = 0; i < 32; i++) m |= (unsigned)(w.slot[i] & 1) << i;
-    cuda_shim::warpWait();
+    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) m |= (unsigned)(w.slot[i] & 1) << i;
+    cuda_shim::maskWait(mask);
     return m;
 }
 inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cuda_shim::exchange(v, (unsigned)src); }
-template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { unsigned l = cuda_shim::laneId(); return cuda_shim::exchange(v, l + d < 32 ? l + d : l); }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return cuda_shim::exchange(v, cuda_shim::laneId() ^ (unsigned)m); }
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    const unsigned l = cuda_shim::laneId();
+    return cuda_shim::exchange(v, (l & ~(unsigned)(width - 1)) + ((unsigned)src & (unsigned)(width - 1)), mask);
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned d) { unsigned l = cuda_shim::laneId(); return cuda_shim::exchange(v, l + d < 32 ? l + d : l, mask); }
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned d) { unsigned l = cuda_shim::laneId(); return cuda_shim::exchange(v, l >= d ? l - d : l, mask); }
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int m, int width = 32) { (void)width; return cuda_shim::exchange(v, cuda_shim::laneId() ^ (unsigned)m, mask); }
 inline int __reduce_max_sync(unsigned, int v) {
     cuda_shim::WarpShared& w = cuda_shim::myWarp();
     w.slot[cuda_shim::laneId()] = (unsigned long long)(long long)v;

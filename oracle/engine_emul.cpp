@@ -38,7 +38,10 @@ void runCta(unsigned nThreads, const std::function<void()>& body) {
     cta.nThreads = nThreads;
     pthread_barrier_init(&cta.bar, nullptr, nThreads);
     const unsigned nWarps = (nThreads + 31) / 32;
-    for (unsigned w = 0; w < nWarps; w++) { pthread_barrier_init(&cta.warp[w].bar, nullptr, 32); memset(cta.warp[w].slot, 0, sizeof(cta.warp[w].slot)); }
+    for (unsigned w = 0; w < nWarps; w++) {
+        pthread_barrier_init(&cta.warp[w].bar, nullptr, 32); memset(cta.warp[w].slot, 0, sizeof(cta.warp[w].slot));
+        for (int lg = 0; lg < 4; lg++) for (int gi = 0; gi < 16; gi++) pthread_barrier_init(&cta.warp[w].gbar[lg][gi], nullptr, 2u << lg);
+    }
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nThreads; t++)
         th.emplace_back([&, t] {
@@ -47,7 +50,10 @@ void runCta(unsigned nThreads, const std::function<void()>& body) {
             body();
         });
     for (auto& t : th) t.join();
-    for (unsigned w = 0; w < nWarps; w++) pthread_barrier_destroy(&cta.warp[w].bar);
+    for (unsigned w = 0; w < nWarps; w++) {
+        pthread_barrier_destroy(&cta.warp[w].bar);
+        for (int lg = 0; lg < 4; lg++) for (int gi = 0; gi < 16; gi++) pthread_barrier_destroy(&cta.warp[w].gbar[lg][gi]);
+    }
     pthread_barrier_destroy(&cta.bar);
 }
 
@@ -66,6 +72,39 @@ u64 arenaSize(const Caps& c) {   // engine_api.cu
 // 2nd stage of --outFilterType BySJout for the next engine_emul_map_chunk calls (engine_emul_set_sj_novel)
 std::vector<u64> g_sjNovelStart, g_sjNovelEnd;
 bool g_sjNovelOn = false;
+
+
+u32 envU32(const char* name, u32 dflt) { const char* e = getenv(name); return e ? (u32)strtoul(e, nullptr, 10) : dflt; }
+
+// prep done: the seed stage as engine_api.cu runs it (default: keyed stage of seed_keyed.cuh; STAR_B200_SEED_WARP: the tier seeder over the whole chunk)
+static void emulSeedStage(const DevIndex& ix, const star_params_t& P, std::vector<u8>& reads, u32 stride, u32 smemStride, std::vector<ReadInfo>& info, std::vector<Piece>& pieces,
+                          u32 maxP, u32 n, std::vector<u32>& counter) {
+    if (envU32("STAR_B200_SEED_WARP", 0)) {
+        runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, reads.data(), stride, info.data(), pieces.data(), maxP, n, nullptr, counter.data(), smemStride); });
+        return;
+    }
+    std::vector<u32> saKeys((size_t)ix.nSA + 8, 0);
+    runCta(256, [&] { build_sa_keys_kernel(ix, saKeys.data()); });
+    KeyedArgs ka;
+    ka.saKeys = saKeys.data();
+    ka.maxItems = std::max<u32>(4096, n * envU32("STAR_B200_SEED_ITEMS_PER_READ", 20));
+    ka.maxRec = std::max<u32>(8, envU32("STAR_B200_SEED_RECS_PER_READ", 192));
+    ka.scanMax = envU32("STAR_B200_SEED_SCAN_MAX", 2048);
+    std::vector<ChainItem> items(ka.maxItems);
+    std::vector<u32> itemKey(ka.maxItems), itemIdx(ka.maxItems), itemCount(4, 0), recCount(n, 0);
+    std::vector<SeedRec> recs((size_t)n * ka.maxRec);
+    ka.items = items.data(); ka.itemKey = itemKey.data(); ka.itemIdx = itemIdx.data(); ka.itemCount = itemCount.data(); ka.recs = recs.data(); ka.recCount = recCount.data();
+    runCta(128, [&] { seed_chains_kernel(ix, P, reads.data(), stride, info.data(), n, ka); });
+    const u32 nItems = std::min(itemCount[0], ka.maxItems);
+    std::vector<u32> itemOrder(itemIdx.begin(), itemIdx.begin() + nItems);
+    const int sortBits = (int)std::min<u32>(2 * ix.gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16)), hiBit = 2 * (int)ix.gSAindexNbases;
+    if (sortBits > 0)
+        std::stable_sort(itemOrder.begin(), itemOrder.end(), [&](u32 a, u32 b) {
+            const u32 ka_ = (itemKey[a] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits), kb_ = (itemKey[b] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits);
+            return ka_ < kb_; });
+    runCta(128, [&] { seed_keyed_search_kernel(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    runCta(128, [&] { seed_replay_kernel(P, info.data(), pieces.data(), maxP, n, ka); });
+}
 
 struct HostIndex {
     DevIndex ix;
@@ -201,7 +240,6 @@ void hostRecord(const DevIndex& ix, const star_params_t& P, ReadInfo* info, u32 
     }
 }
 
-u32 envU32(const char* name, u32 dflt) { const char* e = getenv(name); return e ? (u32)strtoul(e, nullptr, 10) : dflt; }
 
 }  // namespace
 
@@ -252,7 +290,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: seqOff %llu %llu %llu seq0=%c reads0=%d,%d winBinNbits=%u\n", (unsigned long long)in->seqOff[0], (unsigned long long)in->seqOff[1], (unsigned long long)in->seqOff[2], in->seq[0], reads[0], reads[1], (unsigned)P.winBinNbits);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after prep: Lread[0]=%u stride=%u smemStride=%u n=%u\n", info[0].Lread, stride, smemStride, n);
     counter[0] = 0;
-    runCta(128, [&] { seed_search_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), fast.maxP, n, nullptr, counter.data(), nullptr, smemStride); });
+    emulSeedStage(ix, P, reads, stride, smemStride, info, pieces, fast.maxP, n, counter);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after seed: nP[0]=%u nA[0]=%u flags=%u counter=%u\n", info[0].nP, info[0].nA, info[0].flags, counter[0]);
     // ---- heaviest-first order (stable, like the radix sort on keys ~nA)
     std::vector<u32> order(n);
@@ -354,7 +392,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
             std::vector<u8> arenaMid((size_t)128 * mid.arenaBytes);
             for (u32 i : list) info[i].flags &= ~1u;
             counter[0] = 0;
-            runCta(128, [&] { seed_search_kernel(ix, P, reads.data(), stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), nullptr, smemStride); });
+            runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, reads.data(), stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), smemStride); });
             HeavyArgs hv0 = hv; hv0.estLimit = 0;   // (no hand-over inside the tier)
             counter[0] = 0;
             runCta(128, [&] { stitch_kernel(ix, P, reads.data(), stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
@@ -392,6 +430,51 @@ struct SjdbHost {
 }  // namespace
 
 // n = (uint64)-1 switches the filter off again
+// Seeding only (prep + the seed stage of the default pipeline): pc receives 8 numbers per stored piece in the oracle's dump layout
+// (rStart, Length, Str=0, Dir, Nrep, SAstart, SAend, iFrag); pcOff[nReads+1]; counters[4] = searches, SAindex words, probes, flagged reads.
+int engine_emul_seed_chunk(const star_index_view_t* view, const star_params_t* params, const star_read_batch_t* in, uint64_t* pcOff, uint64_t* pc, uint64_t pcCap,
+                           uint64_t* counters) {
+    HostIndex hix(view, params);
+    const DevIndex& ix = hix.ix;
+    const star_params_t P = *params;
+    const u32 n = in->nReads, nMates = in->nMates;
+    u32 maxL = 0;
+    for (u32 i = 0; i < n; i++) {
+        const uint64_t* o = in->seqOff + (u64)i * nMates;
+        u64 L = nMates == 2 ? (o[1] - o[0]) + (o[2] - o[1]) + 1 : o[1] - o[0];
+        if (L > maxL) maxL = (u32)L;
+    }
+    const u32 stride = (maxL + 16) & ~15u;
+    u32 smemStride = (maxL + 1 + 3) & ~3u;
+    if (((smemStride / 4) & 1) == 0) smemStride += 4;
+    std::vector<u8> reads((size_t)n * stride + 64, 0);
+    std::vector<ReadInfo> info(n);
+    const u32 maxP = std::min<u32>(128, (u32)P.seedPerReadNmax);
+    std::vector<Piece> pieces((size_t)n * maxP);
+    std::vector<u32> counter(8, 0);
+    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, reads.data(), stride, info.data(), P); });
+    emulSeedStage(ix, P, reads, stride, smemStride, info, pieces, maxP, n, counter);
+    u64 nPieces = 0;
+    pcOff[0] = 0;
+    counters[0] = counters[1] = counters[2] = counters[3] = 0;
+    for (u32 i = 0; i < n; i++) {
+        const ReadInfo& ri = info[i];
+        if (ri.flags & 1) counters[3]++;
+        else {
+            if (nPieces + ri.nP > pcCap) return 1;
+            for (u32 k = 0; k < ri.nP; k++) {
+                const Piece& p = pieces[(size_t)i * maxP + k];
+                uint64_t* o = pc + (nPieces + k) * 8;
+                o[0] = p.rStart; o[1] = p.Length; o[2] = 0; o[3] = p.Dir; o[4] = p.Nrep; o[5] = p.SAstart; o[6] = p.SAstart + p.Nrep - 1; o[7] = p.iFrag;
+            }
+            nPieces += ri.nP;
+        }
+        pcOff[i + 1] = nPieces;
+        counters[0] += ri.cSearches; counters[1] += ri.cSaiWords; counters[2] += ri.cCompare;
+    }
+    return 0;
+}
+
 int engine_emul_set_sj_novel(const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n) {
     if (n == ~0ULL) { g_sjNovelOn = false; return 0; }
     g_sjNovelStart.assign(sjStart, sjStart + n);

@@ -22,12 +22,16 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "dev.cuh"
+#include "seed_types.cuh"
 #include "stitch_types.cuh"
 
 namespace starb {
 // kernels (seed.cu, stitch.cu)
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
-__global__ void seed_search_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, WorkCounters*, u32);
+void launch_build_sa_keys(int, cudaStream_t, const DevIndex&, u32*);
+void launch_seed_chains(int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, u32, const KeyedArgs&);
+void launch_seed_keyed_search(int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, const u32*, const KeyedArgs&);
+void launch_seed_replay(int, cudaStream_t, const star_params_t&, ReadInfo*, Piece*, u32, u32, const KeyedArgs&);
 void launch_seed_warp(int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, u32);
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
                               star_read_result_t*, star_align_t*, const u32*, u32, HeavyArgs);
@@ -106,7 +110,13 @@ struct star_ctx {
     FlatArgs fa{};
     Caps recCaps; u8* d_arenaRec = nullptr;
     int setupCtas = 3; u8* d_arenaSetup = nullptr; int recCtas = 4; int dfsCtas = 4;
-    int seedWarpCtas = 0;   // > 0: seed_search_warp_kernel with this many CTAs per SM (STAR_B200_SEED_WARP)
+    int seedWarpCtas = 0;   // > 0: seed_search_warp_kernel with this many CTAs per SM for the whole chunk (STAR_B200_SEED_WARP; measurements)
+    // keyed seed stage (seed_keyed.cuh): SA keys of the index, chain items, their sort, records
+    KeyedArgs ka{};
+    u32* d_saKeys = nullptr;
+    u32 *d_itemKey2 = nullptr, *d_itemOrder = nullptr;
+    void* d_itemSortTmp = nullptr; size_t itemSortTmpBytes = 0;
+    int keyedCtas = 8; int seedSortBits = 16; float msKeys = 0;
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -367,8 +377,38 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         c->heavyCaps.arenaBytes = arenaSize(c->heavyCaps);
     }
     // persistent grids: as many 128-lane CTAs as fit per SM (registers / shared memory decide; queried per launch config)
-    c->gridSeed = c->nSM * (int)envU32("STAR_B200_SEED_CTAS_PER_SM", 6);
     c->seedWarpCtas = (int)envU32("STAR_B200_SEED_WARP", 0);
+    {   // SA keys: 4 bytes per SA row (23.6 GB for GRCh38), built once per context from the resident SA and genome
+        const size_t nk = (size_t)v->nSA + 8;
+        CK(cudaMalloc((void**)&c->d_saKeys, nk * 4));
+        c->owned.push_back(c->d_saKeys);
+        CK(cudaMemsetAsync(c->d_saKeys, 0, nk * 4, c->stream));
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        launch_build_sa_keys(c->nSM, c->stream, c->ix, c->d_saKeys);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventElapsedTime(&c->msKeys, c->ev[0], c->ev[1]));
+        if (getenv("STAR_B200_DEBUG")) fprintf(stderr, "star_b200: SA keys of %llu rows built in %.1f ms\n", (unsigned long long)v->nSA, c->msKeys);
+        KeyedArgs& ka = c->ka;
+        ka.saKeys = c->d_saKeys;
+        ka.maxItems = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(4096, (u64)N * envU32("STAR_B200_SEED_ITEMS_PER_READ", 20)));
+        ka.maxRec = std::max<u32>(8, envU32("STAR_B200_SEED_RECS_PER_READ", 192));
+        ka.scanMax = envU32("STAR_B200_SEED_SCAN_MAX", 2048);
+        if (devAlloc(c, &ka.items, ka.maxItems)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &ka.itemKey, ka.maxItems)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &ka.itemIdx, ka.maxItems)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &c->d_itemKey2, ka.maxItems)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &c->d_itemOrder, ka.maxItems)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &ka.itemCount, 4)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &ka.recs, (size_t)N * ka.maxRec)) return STAR_EXIT_RUNTIME;
+        if (devAlloc(c, &ka.recCount, N)) return STAR_EXIT_RUNTIME;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, c->itemSortTmpBytes, ka.itemKey, c->d_itemKey2, ka.itemIdx, c->d_itemOrder, (int)ka.maxItems));
+        CK(cudaMalloc(&c->d_itemSortTmp, c->itemSortTmpBytes + 64));
+        c->owned.push_back(c->d_itemSortTmp);
+        c->keyedCtas = (int)std::min<u32>(16, std::max<u32>(1, envU32("STAR_B200_SEED_KEYED_CTAS_PER_SM", 8)));
+        c->seedSortBits = (int)std::min<u32>(2 * v->gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16));   // 0: chains stay in read order
+    }
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
     {
         size_t bytes = (size_t)c->gridStitch * 128 * c->fast.arenaBytes;
@@ -416,7 +456,6 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         CK(cudaMalloc(&p, (size_t)c->nSM * c->recCtas * 4 * c->recCaps.arenaBytes)); c->d_arenaRec = (u8*)p; c->owned.push_back(p);   // one arena per warp
         c->dfsCtas = (int)std::min<u32>(8, std::max<u32>(2, envU32("STAR_B200_FLAT_DFS_CTAS_PER_SM", 4)));
     }
-    CK(cudaFuncSetAttribute(seed_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(stitch_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
@@ -589,16 +628,34 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(c->ev[3], c->stream));
-    const u32 smemSeed = 128 * c->smemStride;
     const u32 smemStitch = 128 * 2 * c->smemStride;
     if (smemStitch > 200 * 1024) { g_err = "star_b200: read too long for the shared-memory staging"; return STAR_EXIT_RUNTIME; }
     // ---- fast path over all reads ----
     CK(cudaMemsetAsync(c->d_counter, 0, 16, c->stream));
-    if (c->seedWarpCtas)   // opt-in: one read per warp, 32-ary search (seed_warp.cuh)
+    if (c->seedWarpCtas) {   // measurements: one read per warp, 32-ary search with genome comparisons (the tier seeder) over the whole chunk
         launch_seed_warp(c->seedWarpCtas, c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr, c->d_counter, c->smemStride);
-    else
-        seed_search_kernel<<<c->gridSeed, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, c->d_pieces, c->fast.maxP, n, nullptr,
-                                                                       c->d_counter, c->d_wc, c->smemStride);
+    } else {                 // default: chains binned by SAindex L-mer, keyed SA windows, ordered replay (seed_keyed.cuh)
+        const KeyedArgs& ka = c->ka;
+        CK(cudaMemsetAsync(ka.itemCount, 0, 4, c->stream));
+        launch_seed_chains(c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, n, ka);
+        const u32* order = nullptr;
+        if (c->seedSortBits > 0) {
+            u32 nItems = 0;
+            CK(cudaMemcpyAsync(&nItems, ka.itemCount, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (nItems > ka.maxItems) nItems = ka.maxItems;
+            if (nItems > 1) {
+                const int hiBit = 2 * (int)c->ix.gSAindexNbases;
+                CK(cub::DeviceRadixSort::SortPairs(c->d_itemSortTmp, c->itemSortTmpBytes, ka.itemKey, c->d_itemKey2, ka.itemIdx, c->d_itemOrder, (int)nItems,
+                                                   hiBit - c->seedSortBits, hiBit, c->stream));
+                g_launches += 3;
+                order = c->d_itemOrder;
+            }
+        }
+        launch_seed_keyed_search(c->keyedCtas, c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, order, ka);
+        launch_seed_replay(c->nSM, c->stream, c->P, c->d_info, c->d_pieces, c->fast.maxP, n, ka);
+        g_launches += 2;
+    }
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[4], c->stream));
@@ -659,8 +716,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         for (u32 lo = 0; lo < nSlow; lo += T.batch) {
             u32 m = nSlow - lo < T.batch ? nSlow - lo : T.batch;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
-            seed_search_kernel<<<grid, 128, smemSeed, c->stream>>>(c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, T.caps.maxP, m,
-                                                                    c->d_list + lo, c->d_counter, c->d_wc, c->smemStride);
+            launch_seed_warp(8, std::max(1, grid / 8), c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, T.caps.maxP, m, c->d_list + lo, c->d_counter, c->smemStride);
             g_launches++;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));

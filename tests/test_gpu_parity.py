@@ -46,8 +46,10 @@ def test_engine_matches_oracle_tiny(lib, oracle, golden, tiny_index, name):
     eng.close()
     diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
     assert not diffs, "\n".join(diffs[:20])
-    # the algorithmic work counters of the MMP search must agree with the instrumented oracle
-    for k in ("mmp_searches", "mmp_sai_words", "mmp_compare_calls", "mmp_bases_examined", "sa_enumerated"):
+    # the algorithm-determined work counters of the MMP search must agree with the instrumented oracle: searches and
+    # SAindex words.  (Compare calls / bases examined belong to the reference's binary search; the keyed kernel probes differently and
+    # reports its own probes there — the roofline numerator always takes the ORACLE's counts.)
+    for k in ("mmp_searches", "mmp_sai_words", "sa_enumerated"):
         assert getattr(st_g, k) == getattr(st_o, k), k
 
 
@@ -89,7 +91,7 @@ def test_engine_paths_are_all_exact(lib, oracle, golden, tiny_index, name, env):
                 os.environ[k] = v
     diffs = oc.compare_outputs(res_o, al_o, res_g, al_g)
     assert not diffs, "\n".join(diffs[:20])
-    for k in ("mmp_searches", "mmp_sai_words", "mmp_compare_calls", "mmp_bases_examined", "sa_enumerated"):
+    for k in ("mmp_searches", "mmp_sai_words", "sa_enumerated"):
         assert getattr(st_g, k) == getattr(st_o, k), k
 
 
