@@ -62,6 +62,56 @@ def test_emulated_warp_seed_search_equals_oracle_pieces(oracle, lib, golden, nam
 ENGINE_EMUL_LIB = os.path.join(ROOT, "oracle", "_build", "libengine_emul.so")
 
 
+@pytest.mark.parametrize("name,n_take,lmax,env", [
+    ("std", 400, 0, {}), ("hard", 120, 0, {}), ("se", 400, 0, {}), ("hard", 60, 25, {}), ("se", 300, 25, {}),
+    ("std", 300, 0, {"STAR_B200_SEED_SCAN_MAX": "3"}),                                  # every window larger than 3 rows is bisected on the keys
+    ("hard", 80, 25, {"STAR_B200_SEED_SCAN_MAX": "3", "STAR_B200_SEED_SORT_BITS": "0"}),  # ... chains in read order
+    ("std", 200, 0, {"STAR_B200_SEED_RECS_PER_READ": "16"}),                            # record slabs overflow: those reads are flagged for the tier path
+])
+def test_emulated_keyed_seed_stage_equals_oracle_pieces(oracle, lib, golden, name, n_take, lmax, env, monkeypatch):
+    """The DEFAULT seed stage (seed_keyed.cuh: SA keys, chain items sorted by SAindex L-mer, groups of 8 lanes, ordered replay) as emulated
+    CTAs: every stored piece of every read equals the oracle's PC[] (= the reference's after seeding), and the algorithm-determined
+    counters (searches, SAindex words) equal the instrumented oracle's."""
+    import star_b200 as sb
+    from star_b200 import capi
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    files = [os.path.join(golden, name + "_1.fq")] + ([os.path.join(golden, name + "_2.fq")] if name != "se" else [])
+    mates = [cf.read_fastq_seqs(f)[:n_take] for f in files]
+    seq, off, n, nm = sb.pack_reads(mates)
+    params = capi.default_params(lib)
+    params.seedSearchLmax = lmax
+    idx = sb.Index(lib, os.path.join(golden, "idx"), params=params)
+    oe = oc.OracleEngine(oracle, idx)
+    _, _, st_o, (pc_off_o, pc_o) = oe.map_chunk(seq, off, n, nm, dump=True)
+    batch = oe._batch(seq, off, n, nm)
+    oe.close()
+    if not os.path.exists(ENGINE_EMUL_LIB):
+        oc.build_oracle()
+    em = C.CDLL(ENGINE_EMUL_LIB)
+    em.engine_emul_seed_chunk.argtypes = [C.POINTER(capi.IndexView), C.POINTER(capi.Params), C.POINTER(capi.ReadBatch), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    cap = int(pc_off_o[-1]) + 64 * n
+    pc_off = np.zeros(n + 1, dtype=np.uint64)
+    pc = np.zeros((cap, 8), dtype=np.uint64)
+    counters = np.zeros(4, dtype=np.uint64)
+    rc = em.engine_emul_seed_chunk(idx.view, C.byref(idx.params), C.byref(batch), pc_off.ctypes.data, pc.ctypes.data, cap, counters.ctypes.data)
+    idx.close()
+    assert rc == 0
+    if "STAR_B200_SEED_RECS_PER_READ" in env:   # flagged reads keep no pieces here (the tier path redoes them); the others must be exact
+        assert 0 < int(counters[3]) < n
+        cnt_e, cnt_o = np.diff(pc_off), np.diff(pc_off_o)
+        flagged = cnt_e != cnt_o
+        assert int(flagged.sum()) <= int(counters[3]) and (cnt_e[flagged] == 0).all()
+        keep = np.repeat(~flagged, cnt_o.astype(np.int64))
+        assert not (pc[: int(pc_off[-1])] != pc_o[keep]).any()
+        return
+    assert int(counters[3]) == 0
+    assert np.array_equal(pc_off, pc_off_o)
+    bad = np.nonzero((pc[: int(pc_off[-1])] != pc_o).any(axis=1))[0]
+    assert bad.size == 0, "first differing piece %d: emulated %s oracle %s" % (bad[0], pc[bad[0]], pc_o[bad[0]])
+    assert int(counters[0]) == st_o.mmp_searches and int(counters[1]) == st_o.mmp_sai_words
+
+
 @pytest.mark.parametrize("name,n_take,env", [
     ("std", 24, {"STAR_B200_HEAVY_NA": "2000000000", "STAR_B200_HEAVY_EST": "0"}),     # every read on the lane path (stitch_kernel)
     ("hard", 8, {"STAR_B200_HEAVY_NA": "2000000000", "STAR_B200_HEAVY_EST": "0"}),
