@@ -102,7 +102,10 @@ static void emulSeedStage(const DevIndex& ix, const star_params_t& P, std::vecto
         std::stable_sort(itemOrder.begin(), itemOrder.end(), [&](u32 a, u32 b) {
             const u32 ka_ = (itemKey[a] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits), kb_ = (itemKey[b] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits);
             return ka_ < kb_; });
-    runCta(128, [&] { seed_keyed_search_kernel(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    const u32 gl = envU32("STAR_B200_SEED_GROUP_LANES", 8);
+    if (gl == 4) runCta(128, [&] { seed_keyed_search_kernel<4>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    else if (gl == 16) runCta(128, [&] { seed_keyed_search_kernel<16>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    else runCta(128, [&] { seed_keyed_search_kernel<8>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
     runCta(128, [&] { seed_replay_kernel(P, info.data(), pieces.data(), maxP, n, ka); });
 }
 

@@ -30,7 +30,7 @@ namespace starb {
 __global__ void prep_reads_kernel(const char*, const u64*, u32, u32, u8*, u32, ReadInfo*, star_params_t);
 void launch_build_sa_keys(int, cudaStream_t, const DevIndex&, u32*);
 void launch_seed_chains(int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, u32, const KeyedArgs&);
-void launch_seed_keyed_search(int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, const u32*, const KeyedArgs&);
+void launch_seed_keyed_search(int, int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, const u32*, const KeyedArgs&);
 void launch_seed_replay(int, cudaStream_t, const star_params_t&, ReadInfo*, Piece*, u32, u32, const KeyedArgs&);
 void launch_seed_warp(int, int, cudaStream_t, const DevIndex&, const star_params_t&, const u8*, u32, ReadInfo*, Piece*, u32, u32, const u32*, u32*, u32);
 __global__ void stitch_kernel(DevIndex, star_params_t, const u8*, u32, ReadInfo*, const Piece*, u32, const u32*, u32*, u8*, Caps,
@@ -116,7 +116,7 @@ struct star_ctx {
     u32* d_saKeys = nullptr;
     u32 *d_itemKey2 = nullptr, *d_itemOrder = nullptr;
     void* d_itemSortTmp = nullptr; size_t itemSortTmpBytes = 0;
-    int keyedCtas = 8; int seedSortBits = 16; float msKeys = 0;
+    int keyedCtas = 8, keyedLanes = 8; int seedSortBits = 16; float msKeys = 0;
     unsigned long long flatUse[4] = {0, 0, 0, 0};   // pool bytes / tasks / blocks / stored words used by the last chunk
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
@@ -407,6 +407,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         CK(cudaMalloc(&c->d_itemSortTmp, c->itemSortTmpBytes + 64));
         c->owned.push_back(c->d_itemSortTmp);
         c->keyedCtas = (int)std::min<u32>(16, std::max<u32>(1, envU32("STAR_B200_SEED_KEYED_CTAS_PER_SM", 8)));
+        c->keyedLanes = (int)envU32("STAR_B200_SEED_GROUP_LANES", 8);   // 4, 8 or 16 lanes per search
         c->seedSortBits = (int)std::min<u32>(2 * v->gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16));   // 0: chains stay in read order
     }
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
@@ -652,7 +653,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
                 order = c->d_itemOrder;
             }
         }
-        launch_seed_keyed_search(c->keyedCtas, c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, order, ka);
+        launch_seed_keyed_search(c->keyedLanes, c->keyedCtas, c->nSM, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, order, ka);
         launch_seed_replay(c->nSM, c->stream, c->P, c->d_info, c->d_pieces, c->fast.maxP, n, ka);
         g_launches += 2;
     }

@@ -28,21 +28,22 @@
 namespace starb {
 
 #define SK_KEY_BASES 14u
-#define SK_G 8u                 /* lanes per search group */
-#define SK_TILE (4u * SK_G)     /* SA rows per key tile: one 16-byte load per lane */
 
-// ---- groups of SK_G lanes inside a warp: every collective names the group's own lanes, so groups advance independently
-struct Grp {
+// ---- groups of Grp::G lanes inside a warp: every collective names the group's own lanes, so groups advance independently
+template <u32 GN>
+struct GrpT {
+    static constexpr u32 G = GN;            // lanes per group
+    static constexpr u32 TILE = 4u * GN;    // SA rows per key tile: one 16-byte load per lane
     u32 lane, shift, mask;
-    SB_DEV Grp() {
+    SB_DEV GrpT() {
         const u32 l = threadIdx.x & 31;
-        lane = l & (SK_G - 1); shift = l & ~(SK_G - 1); mask = ((1u << SK_G) - 1u) << shift;
+        lane = l & (G - 1); shift = l & ~(G - 1); mask = ((1u << G) - 1u) << shift;
     }
-    SB_DEV u32 ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & ((1u << SK_G) - 1u); }
-    SB_DEV u32 shfl(u32 v, int src) const { return __shfl_sync(mask, v, src, SK_G); }
-    SB_DEV u64 shfl64(u64 v, int src) const { return __shfl_sync(mask, v, src, SK_G); }
-    SB_DEV u32 maxU(u32 v) const { for (u32 o = SK_G / 2; o; o >>= 1) { const u32 x = __shfl_xor_sync(mask, v, o, SK_G); v = x > v ? x : v; } return v; }
-    SB_DEV u32 minU(u32 v) const { for (u32 o = SK_G / 2; o; o >>= 1) { const u32 x = __shfl_xor_sync(mask, v, o, SK_G); v = x < v ? x : v; } return v; }
+    SB_DEV u32 ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & ((1u << G) - 1u); }
+    SB_DEV u32 shfl(u32 v, int src) const { return __shfl_sync(mask, v, src, G); }
+    SB_DEV u64 shfl64(u64 v, int src) const { return __shfl_sync(mask, v, src, G); }
+    SB_DEV u32 maxU(u32 v) const { for (u32 o = G / 2; o; o >>= 1) { const u32 x = __shfl_xor_sync(mask, v, o, G); v = x > v ? x : v; } return v; }
+    SB_DEV u32 minU(u32 v) const { for (u32 o = G / 2; o; o >>= 1) { const u32 x = __shfl_xor_sync(mask, v, o, G); v = x < v ? x : v; } return v; }
     SB_DEV void sync() const { __syncwarp(mask); }
 };
 
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) build_sa_keys_kernel(const __grid_constan
 SB_DEV u32 pieceBase(const u8* R, u64 S, bool dirR, u32 ii) { return dirR ? (u32)R[S + ii] : 3u - (u32)R[S - ii]; }
 
 // match length (from offset L on) of the piece with ONE row, the group's lanes comparing 8 bases each per step.  Returns the length, N = all.
+template <class Grp>
 SB_DEV u32 grpLcpRow(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u32 L, u64 iSA, bool dirR, u32& bases) {
     u64 SAstr = packedGet(ix.SA, ix.saBits, iSA);
     const bool dirG = (SAstr >> ix.GstrandBit) == 0;
@@ -91,7 +93,7 @@ SB_DEV u32 grpLcpRow(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N
     const u32 n = N - L;
     u32 res = n;
 #pragma unroll 1
-    for (u32 base = 0; base < n; base += 8 * SK_G) {
+    for (u32 base = 0; base < n; base += 8 * Grp::G) {
         const u32 ii = base + 8 * g.lane;
         u32 mine = 0xffffffffu;                          // first mismatch seen by this lane (offset from L), none: big
         if (ii < n) {
@@ -109,7 +111,8 @@ SB_DEV u32 grpLcpRow(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N
 }
 
 // The block [b1,b2] of SA rows of [lo,hi] whose match length with the piece is maximal, and that length; rows of [lo,hi] share the first
-// Lc bases with the piece, L is the length the caller's interval guarantees (as in warpMaxMappableLength, with SK_G probes per step).
+// Lc bases with the piece, L is the length the caller's interval guarantees (as in warpMaxMappableLength, with Grp::G probes per step).
+template <class Grp>
 SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u64 lo, u64 hi, bool dirR, u32 Lin, u32& Lout, u64* indStartEnd,
                             u32& probes, u32& bases) {
     const u32 lane = g.lane;
@@ -117,17 +120,17 @@ SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S
     u32 L3 = 0, Lc = Lin;
     bool have = false;
 #pragma unroll 1
-    while (i2 - i1 + 1 > SK_G) {
-        const u64 row = i1 + (u64)(((unsigned __int128)(i2 - i1) * lane) / (SK_G - 1));
+    while (i2 - i1 + 1 > Grp::G) {
+        const u64 row = i1 + (u64)(((unsigned __int128)(i2 - i1) * lane) / (Grp::G - 1));
         bool c;
         const u32 Lj = lcpRow<Grp>(ix, R, S, N, Lc, row, dirR, c, bases);
-        probes += SK_G;
+        probes += Grp::G;
         const u32 fullMask = g.ballot(Lj == N);
         const u32 gtMask = g.ballot(Lj != N && c);
         if (fullMask) { const int src = SB_FFS(fullMask) - 1; i3 = g.shfl64(row, src); L3 = N; have = true; break; }
         if (!gtMask) { i3 = g.shfl64(row, 0); L3 = g.shfl(Lj, 0); have = true; break; }
         const int jLast = 31 - SB_CLZ(gtMask);
-        if (jLast == (int)SK_G - 1) { i3 = g.shfl64(row, SK_G - 1); L3 = g.shfl(Lj, SK_G - 1); have = true; break; }
+        if (jLast == (int)Grp::G - 1) { i3 = g.shfl64(row, Grp::G - 1); L3 = g.shfl(Lj, Grp::G - 1); have = true; break; }
         const u64 n1 = g.shfl64(row, jLast), n2 = g.shfl64(row, jLast + 1);
         const u32 l1 = g.shfl(Lj, jLast), l2 = g.shfl(Lj, jLast + 1);
         i1 = n1; i2 = n2;
@@ -145,7 +148,7 @@ SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S
         const u32 eq = g.ballot(valid && Lj == L3);
         const int jm = SB_FFS(eq) - 1;
         const u32 run = eq >> jm;
-        const int len = SB_CTZ(~run);                    // (eq has at most SK_G < 32 bits: ~run is never 0)
+        const int len = SB_CTZ(~run);                    // (eq has at most Grp::G < 32 bits: ~run is never 0)
         const int j1 = jm, j2 = jm + len - 1;
         b1 = i1 + (u64)j1; b2 = i1 + (u64)j2;
         i3 = b1;
@@ -169,7 +172,7 @@ SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S
 #pragma unroll 1
             while (left ? a + 1 < b : b + 1 < a) {
                 const u64 span = (left ? b - a : a - b) - 1;
-                const u32 np = span < SK_G ? (u32)span : SK_G;
+                const u32 np = span < Grp::G ? (u32)span : Grp::G;
                 const bool valid = lane < np;
                 const u64 step = np == span ? 1 + lane : (u64)(((unsigned __int128)(span + 1) * (lane + 1)) / (np + 1));
                 const u64 row = left ? a + step : a - step;
@@ -210,6 +213,7 @@ SB_DEV int keyCmp(u32 key, u32 rk, u32 p) {
 
 // Keyed window: rows [i1,i2] share the SAindex prefix (Lk bases) with the piece.  Finds the maximal match length over the next m = min(14, N-Lk)
 // bases and the block of rows attaining it from the keys alone.  Returns that length (0..m).
+template <class Grp>
 SB_DEV u32 keyedWindow(const Grp& g, const u32* __restrict__ keys, u32 scanMax, u64 i1, u64 i2, u32 rk, u32 m, u64& b1, u64& b2, u32& probes) {
     const u64 rows = i2 - i1 + 1;
     if (rows <= scanMax) {
@@ -217,7 +221,7 @@ SB_DEV u32 keyedWindow(const Grp& g, const u32* __restrict__ keys, u32 scanMax, 
         u64 first = i1, last = i1;
         bool any = false;
 #pragma unroll 1
-        for (u64 t = i1 & ~3ULL; t <= i2; t += SK_TILE) {
+        for (u64 t = i1 & ~3ULL; t <= i2; t += Grp::TILE) {
             const u64 r0 = t + 4 * g.lane;
             uint4 kv = make_uint4(0, 0, 0, 0);
             if (r0 <= i2) kv = SB_LDG((const uint4*)(keys + r0));
@@ -268,6 +272,7 @@ SB_DEV u32 keyedWindow(const Grp& g, const u32* __restrict__ keys, u32 scanMax, 
 // ReadAlign_maxMappableLength2strands.cpp:5-115 (gSAsparseD == 1) for one piece by one group.  Returns the record fields.
 // plain: the searched bases are codes 0..3 (always, except the reverse --seedSearchLmax search, which may reach in front of its piece:
 // such a search keeps the reference's arithmetic on the codes > 3 and never uses the keys).
+template <class Grp>
 SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict__ keys, u32 scanMax, const u8* R, u64 pieceStart, u32 pieceLength, bool dirR, bool plain,
                         u32& maxLout, u64& Nrep, u64& SAstart, u32& nSai, u32& probes, u32& bases) {
     u64 indStartEnd[2] = {0, 0};
@@ -411,13 +416,15 @@ __global__ void __launch_bounds__(128) seed_chains_kernel(const __grid_constant_
 
 // One group per chain item: the while loop of mapOneRead for (piece, direction, start), the reverse chain of start 0 when flagDirMap stays
 // set, and the fixed-length search of --seedSearchLmax.  order: item permutation (sorted by L-mer) or nullptr.
+template <u32 GN>
 __global__ void __launch_bounds__(128) seed_keyed_search_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                                 ReadInfo* __restrict__ info, const u32* __restrict__ order, const __grid_constant__ KeyedArgs ka) {
+    typedef GrpT<GN> Grp;
     const Grp g;
     const u32 nItems = *ka.itemCount < ka.maxItems ? *ka.itemCount : ka.maxItems;
-    const u32 nGroups = gridDim.x * blockDim.x / SK_G;
+    const u32 nGroups = gridDim.x * blockDim.x / Grp::G;
 #pragma unroll 1
-    for (u32 t = (blockIdx.x * blockDim.x + threadIdx.x) / SK_G; t < nItems; t += nGroups) {
+    for (u32 t = (blockIdx.x * blockDim.x + threadIdx.x) / Grp::G; t < nItems; t += nGroups) {
         const ChainItem it = ka.items[order ? order[t] : t];
         if (it.read == 0xffffffffu) continue;
         const u8* R = reads + (u64)it.read * stride;
