@@ -31,6 +31,19 @@
 #include "dev.cuh"
 #include "stitch_types.cuh"
 
+// Warp-shared transcript of the cooperative kernels (ONE transcript per warp in shared memory, every lane executes the same scalar path).
+// SB_PRIVATE_COPIES = 1: stitchAlignToTranscript / evalLeaf work on private copies of the head and the touched exons and lane 0 writes them
+// back (strict single writer; what the host emulation runs, where the 32 lanes are free-running threads).  0 (the GPU build): the lanes of
+// the converged warp update the shared transcript in place — every lane executes the same store instruction with the same value, which the
+// hardware issues as one shared-memory transaction; no lane branches on lane-dependent data between a store and the next load, and every
+// cooperative section ends in a __syncwarp.  Measured on B200: the private copies cost +29 % on the task kernel (80 + 2 x 24 bytes per lane
+// per stitch, 128 registers + 128 B of spills); -DSTAR_B200_PRIVATE_COPIES=1 builds the strict variant for the GPU (profiles/r02_summary.md).
+#if defined(STAR_CUDA_HOST_SHIM) || defined(STAR_B200_PRIVATE_COPIES)
+#define SB_PRIVATE_COPIES 1
+#else
+#define SB_PRIVATE_COPIES 0
+#endif
+
 namespace starb {
 
 #define SJA_NONE 0xFFFFFFFFu
@@ -296,13 +309,14 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
     // COOP (the transcript is ONE copy per warp in shared memory): every lane works on private copies of the head, the last exon and the
     // new exon and lane 0 alone writes them back on success — no lane ever reads shared state another lane is writing.
     const u32 nEx0 = t->h.nExons;
+    constexpr bool PRIV = COOP && SB_PRIVATE_COPIES;
     TrHead hL; Exon eAL, eBL;
-    if constexpr (COOP) { hL = t->h; eAL = t->ex[nEx0 - 1]; eBL = t->ex[nEx0]; }
-    TrHead& h = COOP ? hL : t->h;
+    if constexpr (PRIV) { hL = t->h; eAL = t->ex[nEx0 - 1]; eBL = t->ex[nEx0]; }
+    TrHead& h = PRIV ? hL : t->h;
     const u8* R = ln.R;
     int Score = 0;
-    Exon& eA = COOP ? eAL : t->ex[nEx0 - 1];
-    Exon& eB = COOP ? eBL : t->ex[nEx0];
+    Exon& eA = PRIV ? eAL : t->ex[nEx0 - 1];
+    Exon& eB = PRIV ? eBL : t->ex[nEx0];
     const u64 outFilterMismatchNmaxTotal = ln.outFilterMismatchNmaxTotal;
 
     if (__builtin_expect(sjAB != SJA_NONE && eA.sjA == sjAB && eA.iFrag == iFragB && rBstart == rAend + 1 && gAend + 1 < gBstart, 0)) {
@@ -677,7 +691,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
             return -1000008;
         }
     }
-    if constexpr (COOP) {
+    if constexpr (PRIV) {
         Exon& last = h.nExons == nEx0 ? eAL : eBL;
         last.iFrag = (u8)iFragB;
         last.sjA = sjAB;
@@ -687,6 +701,7 @@ __device__ int stitchAlignToTranscript(Lane& ln, u64 rAend, u64 gAend, u64 rBsta
     } else {
         t->ex[h.nExons - 1].iFrag = (u8)iFragB;
         t->ex[h.nExons - 1].sjA = sjAB;
+        if constexpr (COOP) __syncwarp();
     }
     return Score;
 }
@@ -763,9 +778,10 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     else copyTr(&t, ln.cur);
     // COOP: the leaf copy is shared by the warp: the head is worked on privately and written back by lane 0 at the end, the two exon
     // updates of the end extensions are done by lane 0 followed by a __syncwarp
+    constexpr bool PRIV = COOP && SB_PRIVATE_COPIES;
     TrHead hL;
-    if constexpr (COOP) hL = t.h;
-    TrHead& h = COOP ? hL : t.h;
+    if constexpr (PRIV) hL = t.h;
+    TrHead& h = PRIV ? hL : t.h;
     const u64 Lread = ln.Lread;
     int vOrder[2];
     if (roStr == 0) { vOrder[0] = 0; vOrder[1] = 1; } else { vOrder[0] = 1; vOrder[1] = 0; }
@@ -889,9 +905,11 @@ __device__ bool evalLeaf(Lane& ln, int Score, u64 tR2, u64 tG2, u32 Chr, u32 Str
     }
     h.maxScore = Score;
     h.iFrag = (t.ex[0].iFrag == t.ex[nEx - 1].iFrag) ? (signed char)t.ex[0].iFrag : (signed char)-1;
-    if constexpr (COOP) {
+    if constexpr (PRIV) {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) t.h = hL;
+        __syncwarp();
+    } else if constexpr (COOP) {
         __syncwarp();
     }
     return true;
