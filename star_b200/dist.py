@@ -14,9 +14,11 @@ There is no collective on the data path of a pass.  Collectives
   torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m star_b200.dist -- --genomeDir idx --readFilesIn r_1.fq r_2.fq --outFileNamePrefix out/
 """
 import ctypes as C
+import json
 import os
 import subprocess
 import sys
+import time
 
 import numpy as np
 
@@ -58,10 +60,18 @@ def by_sjout(argv):
     return "--outFilterType" in argv and argv[argv.index("--outFilterType") + 1] == "BySJout"
 
 
+TIMING = {}   # phase -> seconds on this rank (rank 0 writes <prefix>dist_timing.json: the product path's own measurement)
+
+
+def _timed(name, t0):
+    TIMING[name] = TIMING.get(name, 0.0) + time.time() - t0
+
+
 def all_gather_bytes(blob, world, device):
     """Variable-length all-gather: sizes first, then the payload padded to the longest.  Returns the list of every rank's bytes."""
     import torch
     import torch.distributed as dist
+    TIMING["gather_bytes_this_rank"] = TIMING.get("gather_bytes_this_rank", 0) + len(blob)
     n = torch.tensor([len(blob)], dtype=torch.int64, device=device)
     sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(sizes, n)
@@ -111,13 +121,19 @@ def run_sharded(argv, cli=None, backend=None):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         return int(ok.item()) == 1
 
+    t_all = time.time()
     if two_pass(argv):
+        t0 = time.time()
         rc = run_cli(["--gpuTwoPassPhase", "1"])
+        _timed("pass1_map_s", t0)
         if not all_ok(rc):
             dist.destroy_process_group()
             return rc or 1
         p1dir = _prefix(sargv) + "_STARpass1/"
+        t0 = time.time()
         gathered = all_gather_bytes(open(p1dir + "shard.bin", "rb").read(), world, dev)
+        _timed("junction_allgather_s", t0)
+        t0 = time.time()
         for r, blob in enumerate(gathered):
             with open(p1dir + "gather%d.bin" % r, "wb") as f:
                 f.write(blob)
@@ -125,6 +141,7 @@ def run_sharded(argv, cli=None, backend=None):
         margv = [prog] + list(argv)
         arr = (C.c_char_p * len(margv))(*[a.encode() for a in margv])
         rc = lib.star_host_merge_pass1(len(margv), arr, world, p1dir.encode())
+        _timed("pass1_junction_merge_s", t0)
         if rank == 0 and rc == 0:   # the run's own _STARpass1/ as the reference leaves it
             os.makedirs(_prefix(argv) + "_STARpass1", exist_ok=True)
             for f in ("SJ.out.tab", "Log.final.out"):
@@ -137,18 +154,26 @@ def run_sharded(argv, cli=None, backend=None):
     else:
         phase = []
     if by_sjout(argv):   # two stages: the junctions of ALL reads of ALL shards decide which reads with novel junctions survive
+        t0 = time.time()
         rc = run_cli(phase + ["--gpuBySJoutPhase", "1"])
+        _timed("map_s", t0)
         if not all_ok(rc):
             dist.destroy_process_group()
             return rc or 1
         sp = _prefix(sargv)
+        t0 = time.time()
         gathered = all_gather_bytes(open(sp + "bysj_sjall.bin", "rb").read(), world, dev)
+        _timed("junction_allgather_s", t0)
         for r, blob in enumerate(gathered):
             with open(sp + "bysj_gather%d.bin" % r, "wb") as f:
                 f.write(blob)
+        t0 = time.time()
         rc = run_cli(phase + ["--gpuBySJoutPhase", "2"])
+        _timed("map_s", t0)
     else:
+        t0 = time.time()
         rc = run_cli(phase)
+        _timed("map_s", t0)   # (2-pass: junction insertion into this rank's index replica + the 2nd mapping pass)
     if not all_ok(rc):
         dist.destroy_process_group()
         return rc or 1
@@ -157,14 +182,24 @@ def run_sharded(argv, cli=None, backend=None):
     t = torch.from_numpy(cnt)
     if use_cuda:
         t = t.cuda()
+    t0 = time.time()
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     dist.barrier()
+    _timed("counter_allreduce_and_barrier_s", t0)   # (includes waiting for the slowest rank's mapping)
     rc = 0
     if rank == 0:
+        t0 = time.time()
         total = t.cpu().numpy().astype(np.uint64)
         margv = [prog] + list(argv)
         arr = (C.c_char_p * len(margv))(*[a.encode() for a in margv])
         rc = lib.star_host_merge_shards(len(margv), arr, world, total.ctypes.data)
+        _timed("merge_shards_s", t0)
+        TIMING["total_s"] = time.time() - t_all
+        TIMING["world"] = world
+        try:
+            json.dump(TIMING, open(_prefix(argv) + "dist_timing.json", "w"))
+        except OSError:
+            pass
     dist.barrier()
     dist.destroy_process_group()
     return rc
