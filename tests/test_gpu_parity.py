@@ -168,3 +168,30 @@ def test_cli_bam_outputs_match_oracle_cli(lib, oracle, golden, tmp_path):
     assert len(recs["gpu"][0]) > 100000
     assert recs["gpu"][0] == recs["ora"][0]
     assert recs["gpu"][1] == recs["ora"][1]
+
+
+def test_init_failure_is_a_clean_error_and_leaves_nothing_behind(lib, oracle, golden, tiny_index):
+    """A context whose pools cannot fit in HBM: star_gpu_init returns STAR_EXIT_RUNTIME with a CUDA message, frees what it had allocated
+    (free memory before == after), and the next context on the same device works and is still exact."""
+    import torch
+    import oracle_capi as oc
+    import star_b200 as sb
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    with pytest.raises(sb.StarError) as e:
+        sb.Engine(lib, tiny_index, max_reads=400_000_000)      # hundreds of GB of per-read slabs
+    assert e.value.code == 103 and "CUDA error" in str(e.value)
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free1 >= free0 - (64 << 20), "device memory of the failed init was not released: %d MB" % ((free0 - free1) >> 20)
+    mates = [cf.read_fastq_seqs(f)[:200] for f in _sets(golden)["std"]]
+    seq, off, n, nm = sb.pack_reads(mates)
+    for _ in range(2):                                             # two init / destroy cycles: nothing accumulates
+        eng = sb.Engine(lib, tiny_index, max_reads=n)
+        res_g, al_g, _ = eng.map_chunk(seq, off, n, nm)
+        eng.close()
+    free2, _ = torch.cuda.mem_get_info(0)
+    assert free2 >= free0 - (64 << 20)
+    oe = oc.OracleEngine(oracle, tiny_index)
+    res_o, al_o, _ = oe.map_chunk(seq, off, n, nm)
+    oe.close()
+    assert not oc.compare_outputs(res_o, al_o, res_g, al_g)
