@@ -216,7 +216,13 @@ int star_gpu_init(star_ctx_t** out, int device, const star_index_view_t* v, cons
     memset(c->ev, 0, sizeof(c->ev));
     c->device = device;
     const int rc = initCtx(c, device, v, params, maxReadsPerChunk);
-    if (rc) { const std::string keep = g_err; star_gpu_destroy(c); g_err = keep; return rc; }   // nothing allocated so far outlives a failed init
+    if (rc) {   // nothing allocated so far outlives a failed init; the failed call's error state is consumed here
+        const std::string keep = g_err;
+        star_gpu_destroy(c);
+        cudaGetLastError();
+        g_err = keep;
+        return rc;
+    }
     *out = c;
     return 0;
 }
