@@ -330,10 +330,42 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             if (n <= 0) return;
         }
     });
+    // the alignment stream (the bulk of the output bytes) is written by its own thread, in chunk order, while the next chunk is being
+    // formatted: at most two formatted chunks wait in memory
+    struct WriteJob { std::vector<std::string> pieces; bool last = false; };
+    std::mutex wrM; std::condition_variable wrCv; std::deque<WriteJob> wrQ;
+    std::thread writerThread([&] {
+        for (;;) {
+            WriteJob job;
+            {
+                std::unique_lock<std::mutex> l(wrM);
+                wrCv.wait(l, [&] { return !wrQ.empty(); });
+                job = std::move(wrQ.front());
+            }
+            if (!job.last) {
+                auto tw0 = now();
+                for (const std::string& p : job.pieces) samO.write(p.data(), p.size());
+                msWrite += msSince(tw0);
+            }
+            {
+                std::lock_guard<std::mutex> l(wrM);
+                wrQ.pop_front();
+            }
+            wrCv.notify_all();
+            if (job.last) return;
+        }
+    });
+    auto pushWrite = [&](WriteJob&& job) {
+        std::unique_lock<std::mutex> l(wrM);
+        wrCv.wait(l, [&] { return wrQ.size() < 2; });
+        wrQ.push_back(std::move(job));
+        l.unlock();
+        wrCv.notify_all();
+    };
     std::thread outputThread([&] {
         for (;;) {
             Work* wk = outQ.pop();
-            if (wk->n <= 0) return;
+            if (wk->n <= 0) { WriteJob end; end.last = true; pushWrite(std::move(end)); return; }
             if (!abortRun.load()) {
                 const ReadChunk& chunk = wk->chunk;
                 auto tf0 = now();
@@ -376,9 +408,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                     for (auto& t : th) t.join();
                 }
                 msFormat += msSince(tf0);
-                auto tw0 = now();
                 for (int t = 0; t < nT; t++) {
-                    if (streamYes) samO.write(sam[t].data(), sam[t].size());
                     allSJ.insert(allSJ.end(), sj[t].begin(), sj[t].end());
                     stats.add(st[t]);
                     if (stage.geneModel) stage.geneCounts.add(gcs[t]);
@@ -402,7 +432,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                         }
                     }
                 }
-                msWrite += msSince(tw0);
+                if (streamYes) { WriteJob job; job.pieces.swap(sam); pushWrite(std::move(job)); }
                 if (allSJ.size() > 4000000) {  // ReadAlignChunk_mapChunk.cpp:66-86 collapses when the buffer fills
                     std::string e2;
                     OutputWriter::collapseSJ(allSJ, e2);
@@ -451,6 +481,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         outQ.push(wk);
     }
     outputThread.join();
+    writerThread.join();
     if (abortRun.load()) {   // release a reader that may be waiting for a free buffer
         for (auto& wk : bufs) freeQ.push(&wk);
     }
