@@ -77,10 +77,10 @@ bool g_sjNovelOn = false;
 u32 envU32(const char* name, u32 dflt) { const char* e = getenv(name); return e ? (u32)strtoul(e, nullptr, 10) : dflt; }
 
 // prep done: the seed stage as engine_api.cu runs it (default: keyed stage of seed_keyed.cuh; STAR_B200_SEED_WARP: the tier seeder over the whole chunk)
-static void emulSeedStage(const DevIndex& ix, const star_params_t& P, std::vector<u8>& reads, u32 stride, u32 smemStride, std::vector<ReadInfo>& info, std::vector<Piece>& pieces,
+static void emulSeedStage(const DevIndex& ix, const star_params_t& P, u8* readsPtr, u32 stride, u32 smemStride, std::vector<ReadInfo>& info, std::vector<Piece>& pieces,
                           u32 maxP, u32 n, std::vector<u32>& counter) {
     if (envU32("STAR_B200_SEED_WARP", 0)) {
-        runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, reads.data(), stride, info.data(), pieces.data(), maxP, n, nullptr, counter.data(), smemStride); });
+        runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, readsPtr, stride, info.data(), pieces.data(), maxP, n, nullptr, counter.data(), smemStride); });
         return;
     }
     std::vector<u32> saKeys((size_t)ix.nSA + 8, 0);
@@ -94,7 +94,7 @@ static void emulSeedStage(const DevIndex& ix, const star_params_t& P, std::vecto
     std::vector<u32> itemKey(ka.maxItems), itemIdx(ka.maxItems), itemCount(4, 0), recCount(n, 0);
     std::vector<SeedRec> recs((size_t)n * ka.maxRec);
     ka.items = items.data(); ka.itemKey = itemKey.data(); ka.itemIdx = itemIdx.data(); ka.itemCount = itemCount.data(); ka.recs = recs.data(); ka.recCount = recCount.data();
-    runCta(128, [&] { seed_chains_kernel(ix, P, reads.data(), stride, info.data(), n, ka); });
+    runCta(128, [&] { seed_chains_kernel(ix, P, readsPtr, stride, info.data(), n, ka); });
     const u32 nItems = std::min(itemCount[0], ka.maxItems);
     std::vector<u32> itemOrder(itemIdx.begin(), itemIdx.begin() + nItems);
     const int sortBits = (int)std::min<u32>(2 * ix.gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16)), hiBit = 2 * (int)ix.gSAindexNbases;
@@ -103,9 +103,9 @@ static void emulSeedStage(const DevIndex& ix, const star_params_t& P, std::vecto
             const u32 ka_ = (itemKey[a] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits), kb_ = (itemKey[b] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits);
             return ka_ < kb_; });
     const u32 gl = envU32("STAR_B200_SEED_GROUP_LANES", 8);
-    if (gl == 4) runCta(128, [&] { seed_keyed_search_kernel<4>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
-    else if (gl == 16) runCta(128, [&] { seed_keyed_search_kernel<16>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
-    else runCta(128, [&] { seed_keyed_search_kernel<8>(ix, P, reads.data(), stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    if (gl == 4) runCta(128, [&] { seed_keyed_search_kernel<4, 8>(ix, P, readsPtr, stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    else if (gl == 16) runCta(128, [&] { seed_keyed_search_kernel<16, 8>(ix, P, readsPtr, stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
+    else runCta(128, [&] { seed_keyed_search_kernel<8, 8>(ix, P, readsPtr, stride, info.data(), sortBits > 0 ? itemOrder.data() : nullptr, ka); });
     runCta(128, [&] { seed_replay_kernel(P, info.data(), pieces.data(), maxP, n, ka); });
 }
 
@@ -268,7 +268,8 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     const u32 stride = (maxL + 16) & ~15u;
     u32 smemStride = (maxL + 1 + 3) & ~3u;
     if (((smemStride / 4) & 1) == 0) smemStride += 4;
-    std::vector<u8> reads((size_t)n * stride + 64, 0);
+    std::vector<u8> readsStore((size_t)n * stride + 64 + 256, 0);   // 256 bytes in front: the 8-byte gathers of the seed stage reach before a row
+    u8* const readsPtr = readsStore.data() + 256;
     std::vector<ReadInfo> info(n);
     // ---- caps (engine_api.cu defaults)
     Caps fast;
@@ -289,11 +290,11 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     memset(results.data(), 0, results.size() * sizeof(star_read_result_t));
     std::vector<u32> counter(8, 0);
     // ---- prep + seed
-    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, reads.data(), stride, info.data(), P); });
-    if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: seqOff %llu %llu %llu seq0=%c reads0=%d,%d winBinNbits=%u\n", (unsigned long long)in->seqOff[0], (unsigned long long)in->seqOff[1], (unsigned long long)in->seqOff[2], in->seq[0], reads[0], reads[1], (unsigned)P.winBinNbits);
+    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, readsPtr, stride, info.data(), P); });
+    if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: seqOff %llu %llu %llu seq0=%c reads0=%d,%d winBinNbits=%u\n", (unsigned long long)in->seqOff[0], (unsigned long long)in->seqOff[1], (unsigned long long)in->seqOff[2], in->seq[0], readsPtr[0], readsPtr[1], (unsigned)P.winBinNbits);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after prep: Lread[0]=%u stride=%u smemStride=%u n=%u\n", info[0].Lread, stride, smemStride, n);
     counter[0] = 0;
-    emulSeedStage(ix, P, reads, stride, smemStride, info, pieces, fast.maxP, n, counter);
+    emulSeedStage(ix, P, readsPtr, stride, smemStride, info, pieces, fast.maxP, n, counter);
     if (getenv("ENGINE_EMUL_DEBUG")) fprintf(stderr, "emul: after seed: nP[0]=%u nA[0]=%u flags=%u counter=%u\n", info[0].nP, info[0].nA, info[0].flags, counter[0]);
     // ---- heaviest-first order (stable, like the radix sort on keys ~nA)
     std::vector<u32> order(n);
@@ -314,7 +315,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     std::vector<u8> arenaFast((size_t)128 * fast.arenaBytes);
     if (n > nHeavyA) {
         counter[0] = 0;
-        runCta(128, [&] { stitch_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), n - nHeavyA, nullptr, counter.data(), arenaFast.data(), fast,
+        runCta(128, [&] { stitch_kernel(ix, P, readsPtr, stride, info.data(), pieces.data(), n - nHeavyA, nullptr, counter.data(), arenaFast.data(), fast,
                                         results.data(), staged.data(), order.data() + nHeavyA, smemStride, hv); });
     }
     const u32 nHeavyX = *hv.count;
@@ -338,12 +339,12 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     std::vector<u8> arenaSetup((size_t)4 * heavy.arenaBytes), arenaRec((size_t)4 * rec.arenaBytes);
     if (nHeavyA && envU32("STAR_B200_HEAVY_FLAT", 1) != 0) {
         counter[0] = 0;
-        runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
+        runCta(128, [&] { flat_setup_kernel<3>(ix, P, readsPtr, stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
                                                arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, 0); });
     }
     if (nHeavyX && envU32("STAR_B200_HEAVY_FLAT", 1) != 0) {
         counter[0] = 0;
-        runCta(128, [&] { flat_setup_kernel<3>(ix, P, reads.data(), stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(),
+        runCta(128, [&] { flat_setup_kernel<3>(ix, P, readsPtr, stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(),
                                                counter.data(), arenaSetup.data(), heavy, results.data(), staged.data(), smemStride, fa, nHeavyA); });
     }
     const bool oldHeavy = envU32("STAR_B200_HEAVY_FLAT", 1) == 0;   // warp-per-read kernel (the engine of the overflow tiers) instead of the flat path
@@ -370,12 +371,12 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
         std::vector<u8> arenaHeavy((size_t)4 * heavy.arenaBytes);
         if (nHeavyA) {
             counter[0] = 0;
-            runCta(128, [&] { stitch_heavy_kernel(ix, P, reads.data(), stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
+            runCta(128, [&] { stitch_heavy_kernel(ix, P, readsPtr, stride, info.data(), pieces.data(), nHeavyA, order.data(), heavyOff.data(), nullptr, counter.data(),
                                                   arenaHeavy.data(), heavy, results.data(), staged.data(), smemStride, scratch.data(), hs); });
         }
         if (nHeavyX) {
             counter[0] = 0;
-            runCta(128, [&] { stitch_heavy_kernel(ix, P, reads.data(), stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(), counter.data(),
+            runCta(128, [&] { stitch_heavy_kernel(ix, P, readsPtr, stride, info.data(), nullptr, nHeavyX, heavyList.data(), heavyOff.data(), heavyPool.data(), counter.data(),
                                                   arenaHeavy.data(), heavy, results.data(), staged.data(), smemStride, scratch.data(), hs); });
         }
         if (dbg) fprintf(stderr, "emul: warp-per-read kernel done (%u + %u reads)\n", nHeavyA, nHeavyX);
@@ -395,10 +396,10 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
             std::vector<u8> arenaMid((size_t)128 * mid.arenaBytes);
             for (u32 i : list) info[i].flags &= ~1u;
             counter[0] = 0;
-            runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, reads.data(), stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), smemStride); });
+            runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, readsPtr, stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), smemStride); });
             HeavyArgs hv0 = hv; hv0.estLimit = 0;   // (no hand-over inside the tier)
             counter[0] = 0;
-            runCta(128, [&] { stitch_kernel(ix, P, reads.data(), stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
+            runCta(128, [&] { stitch_kernel(ix, P, readsPtr, stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
                                             results.data(), staged.data(), nullptr, smemStride, hv0); });
             if (dbg) fprintf(stderr, "emul: tier redid %zu reads\n", list.size());
         }
@@ -450,13 +451,14 @@ int engine_emul_seed_chunk(const star_index_view_t* view, const star_params_t* p
     const u32 stride = (maxL + 16) & ~15u;
     u32 smemStride = (maxL + 1 + 3) & ~3u;
     if (((smemStride / 4) & 1) == 0) smemStride += 4;
-    std::vector<u8> reads((size_t)n * stride + 64, 0);
+    std::vector<u8> readsStore((size_t)n * stride + 64 + 256, 0);   // 256 bytes in front: the 8-byte gathers of the seed stage reach before a row
+    u8* const readsPtr = readsStore.data() + 256;
     std::vector<ReadInfo> info(n);
     const u32 maxP = std::min<u32>(128, (u32)P.seedPerReadNmax);
     std::vector<Piece> pieces((size_t)n * maxP);
     std::vector<u32> counter(8, 0);
-    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, reads.data(), stride, info.data(), P); });
-    emulSeedStage(ix, P, reads, stride, smemStride, info, pieces, maxP, n, counter);
+    runCta(256, [&] { prep_reads_kernel(in->seq, (const u64*)in->seqOff, n, nMates, readsPtr, stride, info.data(), P); });
+    emulSeedStage(ix, P, readsPtr, stride, smemStride, info, pieces, maxP, n, counter);
     u64 nPieces = 0;
     pcOff[0] = 0;
     counters[0] = counters[1] = counters[2] = counters[3] = 0;

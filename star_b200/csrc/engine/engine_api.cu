@@ -83,7 +83,7 @@ struct star_ctx {
     // per-chunk buffers
     char* d_seq = nullptr; size_t seqCap = 0;
     u64* d_seqOff = nullptr;
-    u8* d_reads = nullptr; size_t readsCap = 0;
+    u8* d_reads = nullptr; u8* d_readsBase = nullptr; size_t readsCap = 0;   // d_reads = d_readsBase + 256: the 8-byte gathers of the seed stage touch up to 14 bytes in front of a row
     ReadInfo* d_info = nullptr;
     Piece* d_pieces = nullptr;
     star_read_result_t* d_results = nullptr;
@@ -187,7 +187,7 @@ void star_gpu_destroy(star_ctx_t* c) {
     cudaDeviceSynchronize();
     for (void* p : c->owned) cudaFree(p);
     if (c->d_seq) cudaFree(c->d_seq);                 // grown on demand (ensureSeq / ensureReads / launchHeavy), not in `owned`
-    if (c->d_reads) cudaFree(c->d_reads);
+    if (c->d_readsBase) cudaFree(c->d_readsBase);
     if (c->d_heavyScratch) cudaFree(c->d_heavyScratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -477,9 +477,13 @@ static int ensureSeq(star_ctx* c, size_t bytes) {
 }
 static int ensureReads(star_ctx* c, size_t bytes) {
     if (bytes <= c->readsCap) return 0;
-    if (c->d_reads) cudaFree(c->d_reads);
-    c->readsCap = bytes + bytes / 4 + 4096;
-    CK(cudaMalloc((void**)&c->d_reads, c->readsCap));
+    if (c->d_readsBase) cudaFree(c->d_readsBase);
+    c->d_readsBase = nullptr; c->d_reads = nullptr; c->readsCap = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    CK(cudaMalloc((void**)&c->d_readsBase, cap + 512));
+    CK(cudaMemset(c->d_readsBase, 0, 256));
+    c->d_reads = c->d_readsBase + 256;
+    c->readsCap = cap;
     return 0;
 }
 

@@ -192,11 +192,18 @@ void launch_build_sa_keys(int nSM, cudaStream_t stream, const DevIndex& ix, u32*
 void launch_seed_chains(int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info, u32 nReads, const KeyedArgs& ka) {
     seed_chains_kernel<<<nSM * 8, 128, 0, stream>>>(ix, P, reads, stride, info, nReads, ka);
 }
+template <u32 GN>
+static void launchKeyedSearchG(int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info, const u32* order,
+                               const KeyedArgs& ka) {   // the occupancy target is part of the kernel (register budget): 8, 12 or 16 CTAs of 128 threads per SM
+    if (ctasPerSM <= 8) seed_keyed_search_kernel<GN, 8><<<nSM * 8, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
+    else if (ctasPerSM <= 12) seed_keyed_search_kernel<GN, 12><<<nSM * 12, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
+    else seed_keyed_search_kernel<GN, 16><<<nSM * 16, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
+}
 void launch_seed_keyed_search(int groupLanes, int ctasPerSM, int nSM, cudaStream_t stream, const DevIndex& ix, const star_params_t& P, const u8* reads, u32 stride, ReadInfo* info,
                               const u32* order, const KeyedArgs& ka) {
-    if (groupLanes == 4) seed_keyed_search_kernel<4><<<nSM * ctasPerSM, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
-    else if (groupLanes == 16) seed_keyed_search_kernel<16><<<nSM * ctasPerSM, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
-    else seed_keyed_search_kernel<8><<<nSM * ctasPerSM, 128, 0, stream>>>(ix, P, reads, stride, info, order, ka);
+    if (groupLanes == 4) launchKeyedSearchG<4>(ctasPerSM, nSM, stream, ix, P, reads, stride, info, order, ka);
+    else if (groupLanes == 16) launchKeyedSearchG<16>(ctasPerSM, nSM, stream, ix, P, reads, stride, info, order, ka);
+    else launchKeyedSearchG<8>(ctasPerSM, nSM, stream, ix, P, reads, stride, info, order, ka);
 }
 void launch_seed_replay(int nSM, cudaStream_t stream, const star_params_t& P, ReadInfo* info, Piece* pieces, u32 maxP, u32 nReads, const KeyedArgs& ka) {
     seed_replay_kernel<<<nSM * 8, 128, 0, stream>>>(P, info, pieces, maxP, nReads, ka);

@@ -416,8 +416,8 @@ __global__ void __launch_bounds__(128) seed_chains_kernel(const __grid_constant_
 
 // One group per chain item: the while loop of mapOneRead for (piece, direction, start), the reverse chain of start 0 when flagDirMap stays
 // set, and the fixed-length search of --seedSearchLmax.  order: item permutation (sorted by L-mer) or nullptr.
-template <u32 GN>
-__global__ void __launch_bounds__(128) seed_keyed_search_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
+template <u32 GN, int MINB>
+__global__ void __launch_bounds__(128, MINB) seed_keyed_search_kernel(const __grid_constant__ DevIndex ix, const __grid_constant__ star_params_t P, const u8* __restrict__ reads, u32 stride,
                                                                 ReadInfo* __restrict__ info, const u32* __restrict__ order, const __grid_constant__ KeyedArgs ka) {
     typedef GrpT<GN> Grp;
     const Grp g;
