@@ -2223,11 +2223,14 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                         }
                     }
                 }
+                // loci that fall into no window (the majority for multi-mapping pieces) are no-ops of assignAlignToWindow: only the others are visited, in order
+                saEnum += nl;
+                u32 todo = __ballot_sync(0xffffffffu, kind == 1 ? wD >= 0 : (kind == 2 && (wD >= 0 || wA >= 0)));
                 #pragma unroll 1
-                for (u32 q = 0; q < nl; q++) {
-                    saEnum++;
+                while (todo) {
+                    const u32 q = (u32)__ffs((int)todo) - 1;
+                    todo &= todo - 1;
                     const u32 kq = __shfl_sync(0xffffffffu, kind, q);
-                    if (kq == 0) continue;
                     const u64 a1q = __shfl_sync(0xffffffffu, a1, q);
                     const u64 rq = __shfl_sync(0xffffffffu, aRstart, q);
                     const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
