@@ -397,10 +397,27 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
             for (u32 i : list) info[i].flags &= ~1u;
             counter[0] = 0;
             runCta(128, [&] { seed_search_warp_kernel<6>(ix, P, readsPtr, stride, info.data(), tp.data(), mid.maxP, (u32)list.size(), list.data(), counter.data(), smemStride); });
-            HeavyArgs hv0 = hv; hv0.estLimit = 0;   // (no hand-over inside the tier)
-            counter[0] = 0;
-            runCta(128, [&] { stitch_kernel(ix, P, readsPtr, stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
-                                            results.data(), staged.data(), nullptr, smemStride, hv0); });
+            if (envU32("STAR_B200_HEAVY_FLAT", 1) != 0 && envU32("STAR_B200_FLAT_TIER", 1) != 0) {
+                // runFlatTier of engine_api.cu: the flat kernels again with the tier's caps, piece slabs by list position
+                Caps midRec = mid;
+                midRec.arenaBytes = ((u64)mid.maxW * sizeof(Window) + (u64)mid.maxTr * sizeof(DevTr) + (u64)mid.maxTr * 2 + (u64)mid.maxW * 4 + 255) & ~255ULL;
+                std::vector<u8> arenaSetupT((size_t)4 * mid.arenaBytes), arenaRecT((size_t)4 * midRec.arenaBytes);
+                FlatArgs faT = fa;
+                faT.slabByPos = 1;
+                std::fill(bumps.begin(), bumps.end(), 0ULL);
+                counter[0] = 0;
+                runCta(128, [&] { flat_setup_kernel<2>(ix, P, readsPtr, stride, info.data(), tp.data(), (u32)list.size(), list.data(), heavyOff.data(), nullptr, counter.data(),
+                                                       arenaSetupT.data(), mid, results.data(), staged.data(), smemStride, faT, 0); });
+                counter[0] = 0;
+                runCta(128, [&] { flat_dfs_warp_kernel<4>(ix, P, faT, counter.data(), mid); });
+                counter[0] = 0;
+                runCta(128, [&] { flat_record_warp_kernel<2>(ix, P, info.data(), (u32)list.size(), counter.data(), arenaRecT.data(), midRec, results.data(), staged.data(), faT); });
+            } else {
+                HeavyArgs hv0 = hv; hv0.estLimit = 0;   // (no hand-over inside the tier)
+                counter[0] = 0;
+                runCta(128, [&] { stitch_kernel(ix, P, readsPtr, stride, info.data(), tp.data(), (u32)list.size(), list.data(), counter.data(), arenaMid.data(), mid,
+                                                results.data(), staged.data(), nullptr, smemStride, hv0); });
+            }
             if (dbg) fprintf(stderr, "emul: tier redid %zu reads\n", list.size());
         }
     }

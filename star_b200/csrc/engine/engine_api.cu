@@ -121,7 +121,7 @@ struct star_ctx {
     // fast path
     Caps fast; u8* d_arenaFast = nullptr; int gridSeed = 0, gridStitch = 0;
     // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
-    struct Tier { Caps caps; u8* arena = nullptr; Piece* pieces = nullptr; u32 lanes = 0, batch = 0; };
+    struct Tier { Caps caps; u8* arena = nullptr; Piece* pieces = nullptr; u32 lanes = 0, batch = 0; Caps recCaps; u8* arenaSetup = nullptr; u8* arenaRec = nullptr; };
     Tier tiers[2];
     // state of the resident chunk
     u32 nReads = 0, nMates = 1, stride = 0, smemStride = 0;
@@ -441,7 +441,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         if (getenv("STAR_B200_FLAT_MAXTASKS")) fa.maxTasks = strtoull(getenv("STAR_B200_FLAT_MAXTASKS"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_MAXBLOCKS")) fa.maxBlocks = (u32)strtoull(getenv("STAR_B200_FLAT_MAXBLOCKS"), nullptr, 10);
         if (getenv("STAR_B200_FLAT_TRWORDS")) fa.trWords = strtoull(getenv("STAR_B200_FLAT_TRWORDS"), nullptr, 10);
-        fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1); fa.pad_ = 0;
+        fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1); fa.slabByPos = 0;
         fa.maxTasksPerRead = c->heavyMaxTasks;
         fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
         void* p = nullptr;
@@ -616,6 +616,38 @@ static int runFlat(star_ctx* c, u32 nHeavyB) {
     return 0;
 }
 
+// Overflow tier on the flat path: the reads of `list` (read ids on the device; pieces re-seeded into `pieces`, one slab per list position)
+// with the tier's bigger caps — cooperative window creation / assignment, sub-tree tasks, ordered recording, as the first pass.
+// Measured on the GRCh38-sized index (profiles/r02_summary.md): 35 reads per million overflow the first-pass window cap (reads from
+// repeat families with hundreds of windows); redone by ONE LANE each they took 7.4 s per chunk, i.e. 96 % of the step.
+static int runFlatTier(star_ctx* c, star_ctx::Tier& T, const u32* list, u32 nList) {
+    const Caps& caps = T.caps;
+    const u32 perWarp = (2 * c->smemStride + 32 + caps.maxW * (u32)sizeof(Window) + (caps.maxW + 4) * 4 + ((caps.maxW + 3) & ~3u) + 15) & ~15u;
+    const u32 smem = 4 * perWarp;
+    const int ctas = 2;
+    if (!T.arenaSetup) {
+        CK(cudaMalloc((void**)&T.arenaSetup, (size_t)c->nSM * ctas * 4 * caps.arenaBytes));
+        c->owned.push_back(T.arenaSetup);
+        T.recCaps = caps;
+        T.recCaps.arenaBytes = ((u64)caps.maxW * sizeof(Window) + (u64)caps.maxTr * sizeof(DevTr) + (u64)caps.maxTr * 2 + (u64)caps.maxW * 4 + 255) & ~255ULL;
+        CK(cudaMalloc((void**)&T.arenaRec, (size_t)c->nSM * ctas * 4 * T.recCaps.arenaBytes));
+        c->owned.push_back(T.arenaRec);
+    }
+    FlatArgs fa = c->fa;
+    fa.slabByPos = 1;
+    CK(cudaMemsetAsync(fa.bumps, 0, 64, c->stream));
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    launch_flat_setup(ctas, c->nSM, smem, c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, nList, list, c->d_heavyOff, nullptr, c->d_counter,
+                      T.arenaSetup, caps, c->d_results, c->d_staged, c->smemStride, fa, 0);
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    launch_flat_dfs(c->dfsCtas, c->nSM, c->stream, c->ix, c->P, fa, c->d_counter, caps);
+    CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
+    launch_flat_record(ctas, c->nSM, c->stream, c->ix, c->P, c->d_info, nList, c->d_counter, T.arenaRec, T.recCaps, c->d_results, c->d_staged, fa);
+    g_launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static HeavyArgs heavyArgs(star_ctx* c) {
     HeavyArgs hv;
     hv.pool = c->d_heavyPool; hv.poolBytes = c->heavyPoolBytes; hv.bump = c->d_heavyBump; hv.readOff = c->d_heavyOff;
@@ -724,11 +756,17 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         CK(cudaMemcpy(c->d_list, list.data(), (size_t)nSlow * 4, cudaMemcpyHostToDevice));
         int grid = (int)(T.lanes / 128);
         if (grid < 1) grid = 1;
+        const u32 perWarpT = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + (T.caps.maxW + 4) * 4 + ((T.caps.maxW + 3) & ~3u) + 15) & ~15u;
+        const bool flatTier = tier == 0 && c->flat && 4 * perWarpT <= 200 * 1024 && envU32("STAR_B200_FLAT_TIER", 1) != 0;
         for (u32 lo = 0; lo < nSlow; lo += T.batch) {
             u32 m = nSlow - lo < T.batch ? nSlow - lo : T.batch;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             launch_seed_warp(8, std::max(1, grid / 8), c->stream, c->ix, c->P, c->d_reads, c->stride, c->d_info, T.pieces, T.caps.maxP, m, c->d_list + lo, c->d_counter, c->smemStride);
             g_launches++;
+            if (flatTier) {   // medium caps: the flat kernels again (warp-cooperative), not one lane per read
+                if (runFlatTier(c, T, c->d_list + lo, m)) return STAR_EXIT_RUNTIME;
+                continue;
+            }
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));
             if (c->heavyEst) CK(cudaMemsetAsync(c->d_heavyBump, 0, 16, c->stream));
             HeavyArgs hv = heavyArgs(c);

@@ -278,8 +278,34 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
     u64 indStartEnd[2] = {0, 0};
     const u32 Lmax = ix.gSAindexNbases < pieceLength ? ix.gSAindexNbases : pieceLength;
     u64 ind1 = 0;
+    u32 rk28 = 0;   // bases 14..27 of the piece (2 bits each, left-aligned in 28 bits): the key the SA keys are compared with (plain pieces, 14-base prefix)
+    if (plain && ix.gSAindexNbases == SK_KEY_BASES) {
+        // 32 bases of the piece in comparison orientation from four 8-byte gathers (the bytes behind the piece are never used)
+        u64 w0, w1, w2, w3;
+        if (dirR) {
+            const u8* p = R + pieceStart;
+            w0 = load8generic(p); w1 = load8generic(p + 8); w2 = load8generic(p + 16); w3 = load8generic(p + 24);
+        } else {
+            const u8* p = R + pieceStart;
+            const u64 c3 = 0x0303030303030303ULL;
+            w0 = bswap64(load8generic(p - 7)) ^ c3; w1 = bswap64(load8generic(p - 15)) ^ c3; w2 = bswap64(load8generic(p - 23)) ^ c3; w3 = bswap64(load8generic(p - 31)) ^ c3;
+        }
+        u32 full = 0;
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) full = (full << 2) | ((u32)(w0 >> (8 * k)) & 3u);
+#pragma unroll
+        for (u32 k = 0; k < 6; k++) full = (full << 2) | ((u32)(w1 >> (8 * k)) & 3u);
+        ind1 = (u64)(full >> (2 * (SK_KEY_BASES - Lmax)));
+#pragma unroll
+        for (u32 k = 6; k < 8; k++) rk28 = (rk28 << 2) | ((u32)(w1 >> (8 * k)) & 3u);
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) rk28 = (rk28 << 2) | ((u32)(w2 >> (8 * k)) & 3u);
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) rk28 = (rk28 << 2) | ((u32)(w3 >> (8 * k)) & 3u);
+    } else {
 #pragma unroll 1
-    for (u32 ii = 0; ii < Lmax; ii++) ind1 = (ind1 << 2) + (dirR ? (u64)R[pieceStart + ii] : 3 - (u64)R[pieceStart - ii]);   // (64-bit, as the reference: ReadAlign_maxMappableLength2strands.cpp:33-36)
+        for (u32 ii = 0; ii < Lmax; ii++) ind1 = (ind1 << 2) + (dirR ? (u64)R[pieceStart + ii] : 3 - (u64)R[pieceStart - ii]);   // (64-bit, as the reference: ReadAlign_maxMappableLength2strands.cpp:33-36)
+    }
     u32 Lind = Lmax;
     u64 iSA1 = 0, iSA2 = 0;
     nSai = 0;
@@ -312,8 +338,11 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
         const u32 Lk = Lind;
         const u32 m = pieceLength - Lk < SK_KEY_BASES ? pieceLength - Lk : SK_KEY_BASES;
         u32 rk = 0;
+        if (ix.gSAindexNbases == SK_KEY_BASES) rk = m ? (rk28 >> (2 * (SK_KEY_BASES - m))) << (2 * (SK_KEY_BASES - m)) : 0;   // the first m bases
+        else {
 #pragma unroll 1
-        for (u32 k = 0; k < m; k++) rk |= pieceBase(R, pieceStart, dirR, Lk + k) << (26 - 2 * k);
+            for (u32 k = 0; k < m; k++) rk |= pieceBase(R, pieceStart, dirR, Lk + k) << (26 - 2 * k);
+        }
         u64 b1, b2;
         const u32 kl = m ? keyedWindow(g, keys, scanMax, iSA1, iSA2, rk, m, b1, b2, probes) : 0;
         if (m == 0) { b1 = iSA1; b2 = iSA2; }

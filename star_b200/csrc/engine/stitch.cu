@@ -2101,7 +2101,7 @@ __device__ bool coopAssign(const Lane& ln, WarpWin& ww, int iW, u64 a1, u64 aLen
 // Window phases of a heavy read, executed by the whole warp (all lanes call with identical arguments): mode A imports the windows +
 // seeds a lane of stitch_kernel exported, mode B builds them cooperatively from the stored pieces.  Result: window table in shared
 // memory (swin[0..nWin)), seeds of window w at ln.wa[w*caps.spw ..].
-__device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const DevIndex& ix, const star_params_t& P, const ReadInfo& ri, u32 i,
+__device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const DevIndex& ix, const star_params_t& P, const ReadInfo& ri, u32 i, u32 slab,
                                                  const Piece* __restrict__ pieces, const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool,
                                                  const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason) {
     const u32 Lread = ri.Lread;
@@ -2129,7 +2129,7 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
         ww.nW = nWin;
     } else {
         // ---- mode B: cooperative window creation and seed assignment (ReadAlign_stitchPieces.cpp:41-185)
-        const Piece* PC = pieces + (u64)i * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier
+        const Piece* PC = pieces + (u64)slab * caps.maxP;   // caps.maxP = slab stride of the seed kernel of this tier; slab = read id, or list position in a tier
         const u32 nP = ri.nP;
         ww.nW = 0;
         #pragma unroll 1
@@ -2350,7 +2350,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
-        warpBuildWindows(ln, ww, ix, P, ri, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason);
+        warpBuildWindows(ln, ww, ix, P, ri, i, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason);
         __syncwarp();
         // ---- task table (lane 0): split depth per window, prefix sums (windows without seeds get an empty task range)
         u32 nTasks = 0;

@@ -57,7 +57,8 @@ struct FlatArgs {
     FlatBlock* blocks; u32 maxBlocks;
     u64* trStore; u64 trWords;
     u32 maxTasksPerRead, splitMin;
-    u32 storeAll, pad_;            // storeAll: keep the evaluated transcript of EVERY surviving leaf (no replays in the recording kernel)
+    u32 storeAll, slabByPos;       // storeAll: keep the evaluated transcript of EVERY surviving leaf (no replays in the recording kernel);
+                                   // slabByPos: the piece slab of list entry k is slab k (overflow tier), not the slab of its read id
 };
 
 // launchers defined next to the (templated) kernels in stitch_flat.cuh

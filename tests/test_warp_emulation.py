@@ -121,6 +121,8 @@ def test_emulated_keyed_seed_stage_equals_oracle_pieces(oracle, lib, golden, nam
     ("se", 12, {}),
     ("std", 8, {"STAR_B200_HEAVY_SPLIT": "2", "STAR_B200_FLAT_STORE_ALL": "0"}),           # many prefix sub-trees; leaves replayed by the recording kernel
     ("std", 8, {"ENGINE_EMUL_HOST_RECORD": "1"}),                                          # task kernel + sequential host restatement of the recording
+    ("std", 12, {"STAR_B200_SEED_RECS_PER_READ": "16"}),                                  # reads flagged by the seed stage: re-seeded by the warp kernel, flat kernels again (overflow tier)
+    ("hard", 3, {"STAR_B200_SEED_RECS_PER_READ": "16", "STAR_B200_FLAT_TIER": "0"}),       # ... the lane-per-read tier
     ("std", 16, {"STAR_B200_HEAVY_FLAT": "0"}),                                          # warp-per-read kernel, cooperative windows (mode B)
     ("hard", 10, {"STAR_B200_HEAVY_FLAT": "0", "STAR_B200_HEAVY_NA": "2000000000", "STAR_B200_HEAVY_EST": "1"}),   # ... reads exported by their lane (mode A)
 ])
@@ -153,7 +155,7 @@ def test_emulated_kernels_equal_oracle(oracle, lib, golden, name, n_take, env, m
     assert rc == 0 and int(info4[2]) == 0
     if "STAR_B200_HEAVY_NA" in env and "STAR_B200_HEAVY_FLAT" not in env:
         assert int(info4[0]) == 0 and int(info4[1]) == n
-    else:
+    elif "STAR_B200_FLAT_TIER" not in env:   # (with every read flagged by the seed stage, the tier is the only path taken)
         assert int(info4[0]) > 0, "no read reached the flat path / the warp-per-read kernel"
     diffs = oc.compare_outputs(res_o, al_o, res, al[:ab.nAligns])
     assert not diffs, "\n".join(diffs[:10])
