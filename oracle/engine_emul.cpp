@@ -97,7 +97,7 @@ static void emulSeedStage(const DevIndex& ix, const star_params_t& P, u8* readsP
     runCta(128, [&] { seed_chains_kernel(ix, P, readsPtr, stride, info.data(), n, ka); });
     const u32 nItems = std::min(itemCount[0], ka.maxItems);
     std::vector<u32> itemOrder(itemIdx.begin(), itemIdx.begin() + nItems);
-    const int sortBits = (int)std::min<u32>(2 * ix.gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16)), hiBit = 2 * (int)ix.gSAindexNbases;
+    const int sortBits = (int)std::min<u32>(2 * ix.gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 0)), hiBit = 2 * (int)ix.gSAindexNbases;
     if (sortBits > 0)
         std::stable_sort(itemOrder.begin(), itemOrder.end(), [&](u32 a, u32 b) {
             const u32 ka_ = (itemKey[a] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits), kb_ = (itemKey[b] & (u32)((1ULL << hiBit) - 1)) >> (hiBit - sortBits);

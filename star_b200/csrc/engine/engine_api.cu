@@ -41,7 +41,9 @@ __global__ void count_heavy_kernel(const ReadInfo*, u32, u32, u32*);
 __global__ void order_keys_kernel(const ReadInfo*, u32, u32*, u32*);
 __global__ void prof_read_kernel(unsigned long long*, int);
 __global__ void pack_kernel(const star_read_result_t*, const u64*, const star_align_t*, u32, u32, star_align_t*);
-__global__ void scan_kernel(star_read_result_t*, u64*, u32, u64*);
+__global__ void scan_partial_kernel(const star_read_result_t*, u32, u32, u64*);
+__global__ void scan_top_kernel(u64*, u32, u64*);
+__global__ void scan_write_kernel(star_read_result_t*, u64*, u32, u32, const u64*);
 __global__ void reduce_counters_kernel(const ReadInfo*, u32, WorkCounters*);
 
 // collects the indices of reads whose ReadInfo.flags has `mask` set
@@ -91,6 +93,7 @@ struct star_ctx {
     star_align_t* d_aligns = nullptr;
     u64* d_offsets = nullptr;
     u64* d_total = nullptr;
+    u64* d_scanPartial = nullptr;
     u32* d_counter = nullptr;    // [0] ticket, [1] flagged count
     u32* d_list = nullptr;
     u32 *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_order = nullptr;
@@ -352,6 +355,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     if (devAlloc(c, &c->d_aligns, (size_t)N * nOut)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_offsets, N)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_total, 2)) return STAR_EXIT_RUNTIME;
+    if (devAlloc(c, &c->d_scanPartial, (size_t)c->nSM * 8 + 8)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_counter, 4)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_list, N)) return STAR_EXIT_RUNTIME;
     if (devAlloc(c, &c->d_wc, 1)) return STAR_EXIT_RUNTIME;
@@ -414,7 +418,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         c->owned.push_back(c->d_itemSortTmp);
         c->keyedCtas = (int)std::min<u32>(16, std::max<u32>(1, envU32("STAR_B200_SEED_KEYED_CTAS_PER_SM", 8)));
         c->keyedLanes = (int)envU32("STAR_B200_SEED_GROUP_LANES", 8);   // 4, 8 or 16 lanes per search
-        c->seedSortBits = (int)std::min<u32>(2 * v->gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 16));   // 0: chains stay in read order
+        c->seedSortBits = (int)std::min<u32>(2 * v->gSAindexNbases, envU32("STAR_B200_SEED_SORT_BITS", 0));   // 0: chains stay in read order
     }
     c->gridStitch = c->nSM * (int)envU32("STAR_B200_STITCH_CTAS_PER_SM", 2);
     {
@@ -781,9 +785,14 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         }
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
-    scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_results, c->d_offsets, n, c->d_total);
+    {
+        const u32 nb = (u32)c->nSM * 8, per = (n + nb - 1) / nb;
+        scan_partial_kernel<<<nb, 256, 0, c->stream>>>(c->d_results, n, per, c->d_scanPartial);
+        scan_top_kernel<<<1, 32, 0, c->stream>>>(c->d_scanPartial, nb, c->d_total);
+        scan_write_kernel<<<nb, 256, 0, c->stream>>>(c->d_results, c->d_offsets, n, per, c->d_scanPartial);
+    }
     pack_kernel<<<c->nSM * 8, 256, 0, c->stream>>>(c->d_results, c->d_offsets, c->d_staged, c->fast.nOut, n, c->d_aligns);
-    g_launches += 2;
+    g_launches += 4;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev[6], c->stream));
     CK(cudaMemsetAsync(c->d_wc, 0, sizeof(WorkCounters), c->stream));

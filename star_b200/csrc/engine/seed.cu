@@ -118,20 +118,38 @@ __global__ void __launch_bounds__(128) seed_replay_kernel(const __grid_constant_
         u32 searches = 0, sai = 0;
         if (!st.flags) {
             const SeedRec* rec = ka.recs + (u64)i * ka.maxRec;
-            long long last = -1;
-#pragma unroll 1
-            for (u32 done = 0; done < n && !st.flags; done++) {
-                long long best = 1LL << 40;
-                u32 bi = 0;
+            if (n <= 64) {   // the usual case: sort (chainId, k, slot) words in a small local array, then replay in that order
+                u64 ord[64];
 #pragma unroll 1
                 for (u32 r = 0; r < n; r++) {
-                    const long long key = ((long long)rec[r].chainId << 8) | rec[r].k;
-                    if (key > last && key < best) { best = key; bi = r; }
+                    const u64 key = ((u64)rec[r].chainId << 16) | ((u64)rec[r].k << 8);
+                    u32 j = r;
+#pragma unroll 1
+                    while (j > 0 && (ord[j - 1] >> 8) > (key >> 8)) { ord[j] = ord[j - 1]; j--; }   // (keys are unique: one record per (chain, k))
+                    ord[j] = key | r;
                 }
-                last = best;
-                const SeedRec r = rec[bi];
-                searches++; sai += r.nSai;
-                storeAligns(st, P, (r.chainId >> 7) & 1u, r.Shift, r.Nrep, r.L, r.SAstart, r.iFrag);
+#pragma unroll 1
+                for (u32 q = 0; q < n && !st.flags; q++) {
+                    const SeedRec r = rec[ord[q] & 0xff];
+                    searches++; sai += r.nSai;
+                    storeAligns(st, P, (r.chainId >> 7) & 1u, r.Shift, r.Nrep, r.L, r.SAstart, r.iFrag);
+                }
+            } else {
+                long long last = -1;
+#pragma unroll 1
+                for (u32 done = 0; done < n && !st.flags; done++) {
+                    long long best = 1LL << 40;
+                    u32 bi = 0;
+#pragma unroll 1
+                    for (u32 r = 0; r < n; r++) {
+                        const long long key = ((long long)rec[r].chainId << 8) | rec[r].k;
+                        if (key > last && key < best) { best = key; bi = r; }
+                    }
+                    last = best;
+                    const SeedRec r = rec[bi];
+                    searches++; sai += r.nSai;
+                    storeAligns(st, P, (r.chainId >> 7) & 1u, r.Shift, r.Nrep, r.L, r.SAstart, r.iFrag);
+                }
             }
         }
         ri.nP = (u16)st.nP;

@@ -78,6 +78,15 @@ __global__ void __launch_bounds__(256) build_sa_keys_kernel(const __grid_constan
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ix.nSA; i += (u64)gridDim.x * blockDim.x) keys[i] = saKeyOfRow(ix, i);
 }
 
+// 8 codes 0..3, one per byte, byte 7 first -> 16 bits, 2 per code (the first code in bits 15:14)
+SB_DEV u64 pack8(u64 w) {
+    u64 x = w & 0x0303030303030303ULL;
+    x = (x | (x >> 6)) & 0x000F000F000F000FULL;
+    x = (x | (x >> 12)) & 0x000000FF000000FFULL;
+    x = (x | (x >> 24)) & 0xFFFFULL;
+    return x;
+}
+
 // base ii of the piece in comparison orientation (the piece holds codes 0..3 only)
 SB_DEV u32 pieceBase(const u8* R, u64 S, bool dirR, u32 ii) { return dirR ? (u32)R[S + ii] : 3u - (u32)R[S - ii]; }
 
@@ -113,7 +122,7 @@ SB_DEV u32 grpLcpRow(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N
 // The block [b1,b2] of SA rows of [lo,hi] whose match length with the piece is maximal, and that length; rows of [lo,hi] share the first
 // Lc bases with the piece, L is the length the caller's interval guarantees (as in warpMaxMappableLength, with Grp::G probes per step).
 template <class Grp>
-SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u64 lo, u64 hi, bool dirR, u32 Lin, u32& Lout, u64* indStartEnd,
+__device__ __noinline__ u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u64 lo, u64 hi, bool dirR, u32 Lin, u32& Lout, u64* indStartEnd,
                             u32& probes, u32& bases) {
     const u32 lane = g.lane;
     u64 i1 = lo, i2 = hi, i3 = lo;
@@ -121,7 +130,7 @@ SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S
     bool have = false;
 #pragma unroll 1
     while (i2 - i1 + 1 > Grp::G) {
-        const u64 row = i1 + (u64)(((unsigned __int128)(i2 - i1) * lane) / (Grp::G - 1));
+        const u64 row = i1 + ((i2 - i1) * lane) / (Grp::G - 1);   // (rows < 2^34: the product fits 64 bits)
         bool c;
         const u32 Lj = lcpRow<Grp>(ix, R, S, N, Lc, row, dirR, c, bases);
         probes += Grp::G;
@@ -174,7 +183,7 @@ SB_DEV u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S
                 const u64 span = (left ? b - a : a - b) - 1;
                 const u32 np = span < Grp::G ? (u32)span : Grp::G;
                 const bool valid = lane < np;
-                const u64 step = np == span ? 1 + lane : (u64)(((unsigned __int128)(span + 1) * (lane + 1)) / (np + 1));
+                const u64 step = np == span ? 1 + lane : ((span + 1) * (lane + 1)) / (np + 1);
                 const u64 row = left ? a + step : a - step;
                 const u32 Lj = valid ? lcpRow<Grp>(ix, R, S, L3, La, row, dirR, c, bases) : 0;
                 probes += np;
@@ -209,6 +218,32 @@ SB_DEV int keyCmp(u32 key, u32 rk, u32 p) {
     const u32 a = key >> sh, b = (rk << 4) >> sh;
     if (a != b) return a < b ? -1 : 1;
     return (SK_KEY_BASES - (key & 15u)) < p ? 1 : 0;
+}
+
+// first row of [i1, i2] whose key over p bases is >= (upper: >) the piece's; i2 + 1 if none
+__device__ __noinline__ u64 keyBound(const u32* __restrict__ keys, u64 i1, u64 i2, u32 rk, u32 p, bool upper, u32& probes) {
+    u64 a = i1, b = i2 + 1;
+    while (a < b) {
+        const u64 mid = a + (b - a) / 2;
+        const int c = keyCmp(SB_LDG(keys + mid), rk, p);
+        probes++;
+        if (upper ? c <= 0 : c < 0) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+// keyedWindow for a window too large to scan: the rows equal to the piece over m bases, else the block around the insertion point that
+// shares the most bases with it (the maximal match is attained next to the insertion point; its block = the rows equal over that many bases).
+// Every lane of the group runs the same bisection (broadcast loads).
+__device__ __noinline__ u32 keyedWindowBisect(const u32* __restrict__ keys, u64 i1, u64 i2, u32 rk, u32 m, u64& b1, u64& b2, u32& probes) {
+    const u64 lb = keyBound(keys, i1, i2, rk, m, false, probes), ub = keyBound(keys, i1, i2, rk, m, true, probes);
+    if (ub > lb) { b1 = lb; b2 = ub - 1; return m; }
+    u32 la = 0, lbv = 0;                                   // neighbours of the insertion point
+    if (lb > i1) la = keyLcp(SB_LDG(keys + lb - 1), rk, m);
+    if (lb <= i2) lbv = keyLcp(SB_LDG(keys + lb), rk, m);
+    const u32 best = la > lbv ? la : lbv;
+    b1 = best ? keyBound(keys, i1, i2, rk, best, false, probes) : i1;
+    b2 = best ? keyBound(keys, i1, i2, rk, best, true, probes) - 1 : i2;
+    return best;
 }
 
 // Keyed window: rows [i1,i2] share the SAindex prefix (Lk bases) with the piece.  Finds the maximal match length over the next m = min(14, N-Lk)
@@ -246,27 +281,7 @@ SB_DEV u32 keyedWindow(const Grp& g, const u32* __restrict__ keys, u32 scanMax, 
         b1 = first; b2 = last;
         return best;
     }
-    // large window (repeats, low-complexity prefixes): bisect on the keys.  All lanes of the group run the same search (broadcast loads).
-    auto lowerBound = [&](u32 p, bool upper) {   // first row whose key over p bases is >= (upper: >) the piece's
-        u64 a = i1, b = i2 + 1;
-        while (a < b) {
-            const u64 mid = a + (b - a) / 2;
-            const int c = keyCmp(SB_LDG(keys + mid), rk, p);
-            probes++;
-            if (upper ? c <= 0 : c < 0) a = mid + 1; else b = mid;
-        }
-        return a;
-    };
-    const u64 lb = lowerBound(m, false), ub = lowerBound(m, true);
-    if (ub > lb) { b1 = lb; b2 = ub - 1; return m; }
-    u32 la = 0, lbv = 0;                                   // neighbours of the insertion point
-    if (lb > i1) la = keyLcp(SB_LDG(keys + lb - 1), rk, m);
-    if (lb <= i2) lbv = keyLcp(SB_LDG(keys + lb), rk, m);
-    const u32 best = la > lbv ? la : lbv;
-    if (lb > i1 && la == best && !(lb <= i2 && lbv == best)) { b2 = lb - 1; b1 = best ? lowerBound(best, false) : i1; }
-    else if (lb <= i2 && lbv == best && !(lb > i1 && la == best)) { b1 = lb; b2 = best ? lowerBound(best, true) - 1 : i2; }
-    else { b1 = best ? lowerBound(best, false) : i1; b2 = best ? lowerBound(best, true) - 1 : i2; }
-    return best;
+    return keyedWindowBisect(keys, i1, i2, rk, m, b1, b2, probes);   // large window (repeats, low-complexity prefixes): cold, out of line
 }
 
 // ReadAlign_maxMappableLength2strands.cpp:5-115 (gSAsparseD == 1) for one piece by one group.  Returns the record fields.
@@ -278,30 +293,20 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
     u64 indStartEnd[2] = {0, 0};
     const u32 Lmax = ix.gSAindexNbases < pieceLength ? ix.gSAindexNbases : pieceLength;
     u64 ind1 = 0;
-    u32 rk28 = 0;   // bases 14..27 of the piece (2 bits each, left-aligned in 28 bits): the key the SA keys are compared with (plain pieces, 14-base prefix)
-    if (plain && ix.gSAindexNbases == SK_KEY_BASES) {
-        // 32 bases of the piece in comparison orientation from four 8-byte gathers (the bytes behind the piece are never used)
+    u32 rk28 = 0;   // the 14 bases behind the SAindex prefix (2 bits each, left-aligned in 28 bits): what the SA keys are compared with
+    if (plain) {
+        // 32 bases of the piece in comparison orientation from four 8-byte gathers, packed 2 bits per base (base 0 in the top bits);
+        // the bases behind the piece are never used
         u64 w0, w1, w2, w3;
-        if (dirR) {
-            const u8* p = R + pieceStart;
-            w0 = load8generic(p); w1 = load8generic(p + 8); w2 = load8generic(p + 16); w3 = load8generic(p + 24);
-        } else {
-            const u8* p = R + pieceStart;
+        const u8* p = R + pieceStart;
+        if (dirR) { w0 = bswap64(load8generic(p)); w1 = bswap64(load8generic(p + 8)); w2 = bswap64(load8generic(p + 16)); w3 = bswap64(load8generic(p + 24)); }
+        else {   // (base k = 3 - R[S - k]: byte 7 of the word at S-7 is base 0 already)
             const u64 c3 = 0x0303030303030303ULL;
-            w0 = bswap64(load8generic(p - 7)) ^ c3; w1 = bswap64(load8generic(p - 15)) ^ c3; w2 = bswap64(load8generic(p - 23)) ^ c3; w3 = bswap64(load8generic(p - 31)) ^ c3;
+            w0 = load8generic(p - 7) ^ c3; w1 = load8generic(p - 15) ^ c3; w2 = load8generic(p - 23) ^ c3; w3 = load8generic(p - 31) ^ c3;
         }
-        u32 full = 0;
-#pragma unroll
-        for (u32 k = 0; k < 8; k++) full = (full << 2) | ((u32)(w0 >> (8 * k)) & 3u);
-#pragma unroll
-        for (u32 k = 0; k < 6; k++) full = (full << 2) | ((u32)(w1 >> (8 * k)) & 3u);
-        ind1 = (u64)(full >> (2 * (SK_KEY_BASES - Lmax)));
-#pragma unroll
-        for (u32 k = 6; k < 8; k++) rk28 = (rk28 << 2) | ((u32)(w1 >> (8 * k)) & 3u);
-#pragma unroll
-        for (u32 k = 0; k < 8; k++) rk28 = (rk28 << 2) | ((u32)(w2 >> (8 * k)) & 3u);
-#pragma unroll
-        for (u32 k = 0; k < 4; k++) rk28 = (rk28 << 2) | ((u32)(w3 >> (8 * k)) & 3u);
+        const u64 pb = (pack8(w0) << 48) | (pack8(w1) << 32) | (pack8(w2) << 16) | pack8(w3);
+        ind1 = Lmax ? pb >> (64 - 2 * Lmax) : 0;
+        rk28 = (u32)((pb << (2 * ix.gSAindexNbases)) >> 36);
     } else {
 #pragma unroll 1
         for (u32 ii = 0; ii < Lmax; ii++) ind1 = (ind1 << 2) + (dirR ? (u64)R[pieceStart + ii] : 3 - (u64)R[pieceStart - ii]);   // (64-bit, as the reference: ReadAlign_maxMappableLength2strands.cpp:33-36)
@@ -337,12 +342,7 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
         // a plain SAindex interval: every row starts with the piece's first Lind bases -> keys
         const u32 Lk = Lind;
         const u32 m = pieceLength - Lk < SK_KEY_BASES ? pieceLength - Lk : SK_KEY_BASES;
-        u32 rk = 0;
-        if (ix.gSAindexNbases == SK_KEY_BASES) rk = m ? (rk28 >> (2 * (SK_KEY_BASES - m))) << (2 * (SK_KEY_BASES - m)) : 0;   // the first m bases
-        else {
-#pragma unroll 1
-            for (u32 k = 0; k < m; k++) rk |= pieceBase(R, pieceStart, dirR, Lk + k) << (26 - 2 * k);
-        }
+        const u32 rk = m ? (rk28 >> (2 * (SK_KEY_BASES - m))) << (2 * (SK_KEY_BASES - m)) : 0;   // its first m bases
         u64 b1, b2;
         const u32 kl = m ? keyedWindow(g, keys, scanMax, iSA1, iSA2, rk, m, b1, b2, probes) : 0;
         if (m == 0) { b1 = iSA1; b2 = iSA2; }
@@ -486,6 +486,10 @@ __global__ void __launch_bounds__(128, MINB) seed_keyed_search_kernel(const __gr
                         }
                     }
                     k++;
+                    if (__builtin_expect(k >= 254, 0)) {   // more searches in one chain than a record can number: the read takes the tier path
+                        if (g.lane == 0) atomicAdd(ka.recCount + it.read, ka.maxRec + 1u);
+                        break;
+                    }
                     Lmapped += L;
                 }
             }

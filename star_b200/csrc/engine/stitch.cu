@@ -2588,30 +2588,47 @@ __global__ void pack_kernel(const star_read_result_t* __restrict__ results, cons
     }
 }
 
-// single-block exclusive scan of nTrOut (nReads <= a few million: one pass of 1024 threads with a serial carry)
-__global__ void scan_kernel(star_read_result_t* __restrict__ results, u64* __restrict__ offsets, u32 nReads, u64* __restrict__ total) {
-    __shared__ u64 part[1024];
-    u32 t = threadIdx.x;
-    u32 per = (nReads + blockDim.x - 1) / blockDim.x;
-    u32 lo = t * per, hi = lo + per < nReads ? lo + per : nReads;
+// exclusive scan of nTrOut over the chunk (trOffset of every read, total number of records): per-block sums, a scan of the block sums,
+// then every block writes the offsets of its contiguous range of reads (tiles of blockDim reads, scanned with warp shuffles)
+__global__ void __launch_bounds__(256) scan_partial_kernel(const star_read_result_t* __restrict__ results, u32 nReads, u32 per, u64* __restrict__ partial) {
+    __shared__ u64 ws[8];
+    const u32 lo = blockIdx.x * per, hi = lo + per < nReads ? lo + per : nReads;
     u64 s = 0;
-    #pragma unroll 1
-    for (u32 i = lo; i < hi; i++) s += results[i].nTrOut;
-    part[t] = s;
+    for (u32 i = lo + threadIdx.x; i < hi; i += blockDim.x) s += results[i].nTrOut;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (t == 0) {
+    if (threadIdx.x == 0) { u64 t = 0; for (u32 w = 0; w < (blockDim.x >> 5); w++) t += ws[w]; partial[blockIdx.x] = t; }
+}
+__global__ void scan_top_kernel(u64* __restrict__ partial, u32 nBlocks, u64* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         u64 run = 0;
         #pragma unroll 1
-        for (u32 k = 0; k < blockDim.x; k++) { u64 v = part[k]; part[k] = run; run += v; }
+        for (u32 k = 0; k < nBlocks; k++) { const u64 v = partial[k]; partial[k] = run; run += v; }
         *total = run;
     }
+}
+__global__ void __launch_bounds__(256) scan_write_kernel(star_read_result_t* __restrict__ results, u64* __restrict__ offsets, u32 nReads, u32 per, const u64* __restrict__ partial) {
+    __shared__ u64 ws[8];
+    __shared__ u64 carry;
+    const u32 lo = blockIdx.x * per, hi = lo + per < nReads ? lo + per : nReads;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = partial[blockIdx.x];
     __syncthreads();
-    u64 run = part[t];
     #pragma unroll 1
-    for (u32 i = lo; i < hi; i++) {
-        offsets[i] = run;
-        results[i].trOffset = run;
-        run += results[i].nTrOut;
+    for (u32 base = lo; base < hi; base += blockDim.x) {
+        const u32 i = base + threadIdx.x;
+        const u64 v = i < hi ? results[i].nTrOut : 0;
+        u64 incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const u64 x = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += x; }
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        u64 before = carry;
+        for (u32 w = 0; w < warp; w++) before += ws[w];
+        if (i < hi) { const u64 off = before + incl - v; offsets[i] = off; results[i].trOffset = off; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + incl;
+        __syncthreads();
     }
 }
 
