@@ -465,7 +465,12 @@ def main():
                 threads = min(host_cores, 64)
                 t_base = cli_run(idx, f1, f2, os.path.join(workdir, "cli_base"), threads, ["--readMapNumber", "1"], local_rank)
                 t_full = cli_run(idx, f1, f2, os.path.join(workdir, "cli_run"), threads, [], local_rank)
-                cli = {"value": rp * rep / max(1e-3, t_full - t_base), "unit": UNIT, "pairs": rp * rep, "wall_s": t_full, "startup_and_index_load_s": t_base, "host_threads": threads,
+                host_lines = []
+                try:
+                    host_lines = [l.strip() for l in open(os.path.join(workdir, "cli_run", "Log.out")) if l.startswith("star-b200:")]
+                except OSError:
+                    pass
+                cli = {"value": rp * rep / max(1e-3, t_full - t_base), "stage_times_from_Log_out": host_lines, "unit": UNIT, "pairs": rp * rep, "wall_s": t_full, "startup_and_index_load_s": t_base, "host_threads": threads,
                        "scope": "star_b200/bin/STAR: FASTQ files -> Aligned.out.sam + SJ.out.tab + Log.final.out, wall clock minus a --readMapNumber 1 run (same files and scope as the reference arm)"}
                 # the command line's records for the sample equal the engine's input order: check them against the reference's on a small prefix
                 try:

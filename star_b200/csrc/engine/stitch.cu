@@ -2194,13 +2194,16 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
             const u64 aNrep = p.Nrep, aLength = p.Length;
             const u32 aFrag = p.iFrag;
             const bool aAnchor = aNrep <= P.winAnchorMultimapNmax;
+            u64 saNext = lane < p.Nrep ? packedGet(ix.SA, ix.saBits, p.SAstart + lane) : 0;
             #pragma unroll 1
             for (u64 base = 0; base < p.Nrep && !tooManyAnchors; base += 32) {
                 const u32 nl = (u32)(p.Nrep - base < 32 ? p.Nrep - base : 32);
                 u64 a1 = 0, a1A = 0, aRstart = 0, aLengthD = 0, aLengthA = 0; u32 aStr = 0, kind = 0, isj = SJA_NONE;
                 int wD = -1, wA = -1;
+                const u64 saCur = saNext;   // the SA rows of the next 32 loci are in flight while these are looked up (multi-mapping pieces: hundreds of batches)
+                saNext = base + 32 + lane < p.Nrep ? packedGet(ix.SA, ix.saBits, p.SAstart + base + 32 + lane) : 0;
                 if (lane < nl) {
-                    a1 = packedGet(ix.SA, ix.saBits, p.SAstart + base + lane);
+                    a1 = saCur;
                     aStr = (u32)(a1 >> ix.GstrandBit);
                     a1 &= ix.GstrandMask;
                     aRstart = p.rStart;
