@@ -379,7 +379,29 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     for (int t = 0; t < nT; t++) { totSeq += part[t].seq.size(); totNames += part[t].names.size(); }
     c.seq.reserve(totSeq); c.qual.reserve(totSeq); c.names.reserve(totNames);
     c.seqOff.reserve(nRec * nMates + 1); c.nameOff.reserve(nRec + 1); c.readFilter.reserve(nRec); c.iReadAll.reserve(nRec);
-    for (int t = 0; t < nT; t++) {
+    const bool plainMerge = !P->clipYes && P->outReadsUnmapped != "Fastx" && nT > 1;
+    if (plainMerge) {   // the common case: every parse thread copies its own piece to its final place (the copies are the reader's largest cost)
+        std::vector<uint64_t> seqBase(nT + 1, 0), nameBase(nT + 1, 0), recBase(nT + 1, 0);
+        for (int t = 0; t < nT; t++) { seqBase[t + 1] = seqBase[t] + part[t].seq.size(); nameBase[t + 1] = nameBase[t] + part[t].names.size(); recBase[t + 1] = recBase[t] + part[t].nReads; }
+        c.seq.resize(totSeq); c.qual.resize(totSeq); c.names.resize(totNames);
+        c.seqOff.resize(recBase[nT] * nMates + 1); c.nameOff.resize(recBase[nT] + 1); c.readFilter.resize(recBase[nT]); c.iReadAll.resize(recBase[nT]);
+        c.seqOff[0] = 0; c.nameOff[0] = 0;
+        auto merge = [&](int t) {
+            const ReadChunk& pc = part[t];
+            if (!pc.seq.empty()) { memcpy(&c.seq[seqBase[t]], pc.seq.data(), pc.seq.size()); memcpy(&c.qual[seqBase[t]], pc.qual.data(), pc.qual.size()); }
+            if (!pc.names.empty()) memcpy(&c.names[nameBase[t]], pc.names.data(), pc.names.size());
+            for (size_t k = 1; k < pc.seqOff.size(); k++) c.seqOff[recBase[t] * nMates + k] = seqBase[t] + pc.seqOff[k];
+            for (size_t k = 1; k < pc.nameOff.size(); k++) c.nameOff[recBase[t] + k] = (uint32_t)(nameBase[t] + pc.nameOff[k]);
+            for (size_t k = 0; k < pc.readFilter.size(); k++) c.readFilter[recBase[t] + k] = pc.readFilter[k];
+            for (size_t k = 0; k < pc.iReadAll.size(); k++) c.iReadAll[recBase[t] + k] = pc.iReadAll[k];
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nT; t++) th.emplace_back(merge, t);
+        merge(0);
+        for (auto& t : th) t.join();
+        c.nReads = (uint32_t)recBase[nT];
+    }
+    for (int t = 0; t < nT && !plainMerge; t++) {
         ReadChunk& pc = part[t];
         const uint64_t sb = c.seq.size();
         const uint32_t nb = (uint32_t)c.names.size();
