@@ -126,6 +126,7 @@ struct star_ctx {
     // overflow tiers (allocated on first use): [0] medium caps on many lanes, [1] the reference's own limits on few lanes
     struct Tier { Caps caps; u8* arena = nullptr; Piece* pieces = nullptr; u32 lanes = 0, batch = 0; Caps recCaps; u8* arenaSetup = nullptr; u8* arenaRec = nullptr; };
     Tier tiers[2];
+    u32 tierReads[2] = {0, 0};   // reads redone by each overflow tier in the last chunk
     // state of the resident chunk
     u32 nReads = 0, nMates = 1, stride = 0, smemStride = 0;
     u64 nAligns = 0;
@@ -334,8 +335,8 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     {
         star_ctx::Tier& M = c->tiers[0];
         M.caps.maxP = std::min<u32>((u32)params->seedPerReadNmax, envU32("STAR_B200_MID_MAXP", 512));
-        M.caps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_MID_MAXW", 1024)) + 1) & ~1u;
-        M.caps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_MID_MAXTR", 1024));
+        M.caps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_MID_MAXW", 2048)) + 1) & ~1u;
+        M.caps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_MID_MAXTR", 4096));
         M.caps.spw = c->fast.spw; M.caps.nOut = nOut;
         M.caps.arenaBytes = arenaSize(M.caps);
         M.lanes = envU32("STAR_B200_MID_LANES", 8192); M.batch = envU32("STAR_B200_MID_BATCH", 65536);
@@ -382,7 +383,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     }
     if (c->heavyEst) {
         c->heavyCaps = c->fast;
-        c->heavyCaps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_HEAVY_MAXW", 256)) + 1) & ~1u;
+        c->heavyCaps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_HEAVY_MAXW", 512)) + 1) & ~1u;
         c->heavyCaps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_HEAVY_MAXTR", 1024));
         c->heavyCaps.arenaBytes = arenaSize(c->heavyCaps);
     }
@@ -447,7 +448,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         if (getenv("STAR_B200_FLAT_TRWORDS")) fa.trWords = strtoull(getenv("STAR_B200_FLAT_TRWORDS"), nullptr, 10);
         fa.storeAll = envU32("STAR_B200_FLAT_STORE_ALL", 1); fa.slabByPos = 0;
         fa.maxTasksPerRead = c->heavyMaxTasks;
-        fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 12);
+        fa.splitMin = envU32("STAR_B200_HEAVY_SPLIT", 48);   // measured (profiles/r02_summary.md): 12 -> 351 ms, 40 -> 280, 48 -> 253, 52 -> 261 ms of stitching per million pairs
         void* p = nullptr;
         CK(cudaMalloc(&p, (size_t)N * sizeof(FlatRec))); fa.recs = (FlatRec*)p; c->owned.push_back(p);
         CK(cudaMalloc(&p, fa.poolBytes)); fa.pool = (u8*)p; c->owned.push_back(p);
@@ -738,6 +739,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
     }
     CK(cudaEventRecord(c->ev[8], c->stream));
     // ---- overflow tiers: reads that exceeded the caps of a tier are redone in the next one; the last tier has the reference's own limits ----
+    c->tierReads[0] = c->tierReads[1] = 0;
     for (int tier = 0; tier < 2; tier++) {
         CK(cudaMemsetAsync(c->d_counter + 1, 0, 4, c->stream));
         collect_flagged_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_info, n, 1u, c->d_list, c->d_counter + 1);
@@ -747,21 +749,32 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         CK(cudaStreamSynchronize(c->stream));
         if (nSlow == 0) break;
         star_ctx::Tier& T = c->tiers[tier];
-        if (!T.arena) {
-            CK(cudaMalloc((void**)&T.arena, (size_t)T.lanes * T.caps.arenaBytes));
-            c->owned.push_back(T.arena);
+        const u32 perWarpT = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + (T.caps.maxW + 4) * 4 + ((T.caps.maxW + 3) & ~3u) + 15) & ~15u;
+        const bool flatTier = tier == 0 && c->flat && 4 * perWarpT <= 200 * 1024 && envU32("STAR_B200_FLAT_TIER", 1) != 0;
+        if (!T.pieces) {
             CK(cudaMalloc((void**)&T.pieces, (size_t)T.batch * T.caps.maxP * sizeof(Piece)));
             c->owned.push_back(T.pieces);
+        }
+        if (!flatTier && !T.arena) {   // one arena per lane of the lane-per-read path (the flat tier has its own per-warp arenas)
+            CK(cudaMalloc((void**)&T.arena, (size_t)T.lanes * T.caps.arenaBytes));
+            c->owned.push_back(T.arena);
         }
         // heaviest first inside the tier too, deterministic order: sort (nA desc, index) on the host (the list is small)
         std::vector<u32> list(nSlow);
         CK(cudaMemcpy(list.data(), c->d_list, (size_t)nSlow * 4, cudaMemcpyDeviceToHost));
         std::sort(list.begin(), list.end());
+        c->tierReads[tier] = nSlow;
+        if (getenv("STAR_B200_DEBUG")) {   // why the reads of this tier left the previous one (reason in bits 8.. of ReadInfo.flags; 0 = seed stage)
+            std::vector<ReadInfo> inf(n);
+            CK(cudaMemcpy(inf.data(), c->d_info, (size_t)n * sizeof(ReadInfo), cudaMemcpyDeviceToHost));
+            unsigned long long hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (u32 r : list) hist[(inf[r].flags >> 8) & 7]++;
+            fprintf(stderr, "star_b200: overflow tier %d: %u reads (seed stage %llu, windows %llu, transcripts %llu, export pool %llu, flat pools / tasks %llu)\n", tier, nSlow,
+                    hist[0], hist[1], hist[3], hist[4], hist[5]);
+        }
         CK(cudaMemcpy(c->d_list, list.data(), (size_t)nSlow * 4, cudaMemcpyHostToDevice));
         int grid = (int)(T.lanes / 128);
         if (grid < 1) grid = 1;
-        const u32 perWarpT = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + (T.caps.maxW + 4) * 4 + ((T.caps.maxW + 3) & ~3u) + 15) & ~15u;
-        const bool flatTier = tier == 0 && c->flat && 4 * perWarpT <= 200 * 1024 && envU32("STAR_B200_FLAT_TIER", 1) != 0;
         for (u32 lo = 0; lo < nSlow; lo += T.batch) {
             u32 m = nSlow - lo < T.batch ? nSlow - lo : T.batch;
             CK(cudaMemsetAsync(c->d_counter, 0, 4, c->stream));

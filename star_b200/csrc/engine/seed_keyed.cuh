@@ -452,8 +452,14 @@ __global__ void __launch_bounds__(128, MINB) seed_keyed_search_kernel(const __gr
     const Grp g;
     const u32 nItems = *ka.itemCount < ka.maxItems ? *ka.itemCount : ka.maxItems;
     const u32 nGroups = gridDim.x * blockDim.x / Grp::G;
+    // The groups of a warp take neighbouring items and meet again before every item: between two meetings each group follows its own
+    // chain (different numbers of searches, different paths), and without the meeting they would stay apart for the rest of the kernel —
+    // measured: 8.0 instead of 12.6 lanes per issued instruction and 1.6 x the time.
 #pragma unroll 1
-    for (u32 t = (blockIdx.x * blockDim.x + threadIdx.x) / Grp::G; t < nItems; t += nGroups) {
+    for (u32 tb = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) / Grp::G; tb < nItems; tb += nGroups) {
+        __syncwarp();
+        const u32 t = tb + (threadIdx.x & 31u) / Grp::G;
+        if (t >= nItems) continue;
         const ChainItem it = ka.items[order ? order[t] : t];
         if (it.read == 0xffffffffu) continue;
         const u8* R = reads + (u64)it.read * stride;

@@ -2239,14 +2239,14 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                     const u32 sq = __shfl_sync(0xffffffffu, aStr, q);
                     const int wDq = __shfl_sync(0xffffffffu, wD, q);
                     if (kq == 1) {
-                        if (!coopAssign(ln, ww, wDq, a1q, aLength, aNrep, aFrag, rq, aAnchor, SJA_NONE)) { tooManyAnchors = true; break; }
+                        if (!coopAssign(ln, ww, wDq, a1q, aLength, aNrep, aFrag, rq, aAnchor, SJA_NONE)) { tooManyAnchors = true; saEnum -= nl - 1 - q; break; }   // (the loci behind q are not visited)
                     } else {
                         const u64 a1Aq = __shfl_sync(0xffffffffu, a1A, q);
                         const u64 lDq = __shfl_sync(0xffffffffu, aLengthD, q), lAq = __shfl_sync(0xffffffffu, aLengthA, q);
                         const u32 isjq = __shfl_sync(0xffffffffu, isj, q);
                         const int wAq = __shfl_sync(0xffffffffu, wA, q);
-                        if (!coopAssign(ln, ww, wDq, a1q, lDq, aNrep, aFrag, rq, aAnchor, isjq)) { tooManyAnchors = true; break; }
-                        if (!coopAssign(ln, ww, wAq, a1Aq, lAq, aNrep, aFrag, rq + lDq, aAnchor, isjq)) { tooManyAnchors = true; break; }
+                        if (!coopAssign(ln, ww, wDq, a1q, lDq, aNrep, aFrag, rq, aAnchor, isjq)) { tooManyAnchors = true; saEnum -= nl - 1 - q; break; }
+                        if (!coopAssign(ln, ww, wAq, a1Aq, lAq, aNrep, aFrag, rq + lDq, aAnchor, isjq)) { tooManyAnchors = true; saEnum -= nl - 1 - q; break; }
                     }
                 }
             }
