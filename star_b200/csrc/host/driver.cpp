@@ -310,6 +310,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     const int nT = std::max(1, P.runThreadN);
     double msEngine = 0, msRead = 0, msFormat = 0, msWrite = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto tPass0 = now();
     auto msSince = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
     uint64_t nChunks = 0;
     std::atomic<bool> abortRun(false);
@@ -498,7 +499,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         *g_logStd << timeMonthDayTime(ts) << " ..... started sorting BAM\n" << std::flush;
         writeSortedBam(P, W, coordBlobs, coordIndex, nT);
     }
-    logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks\n";
+    logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks; mapping pass wall " << msSince(tPass0) << " ms\n";
     logMain << "star-b200: host time: reads input " << msRead << " ms, SAM/SJ formatting " << msFormat << " ms, output writes " << msWrite << " ms\n";
     return 0;
 }
