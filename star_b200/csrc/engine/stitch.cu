@@ -2103,7 +2103,7 @@ __device__ bool coopAssign(const Lane& ln, WarpWin& ww, int iW, u64 a1, u64 aLen
 // memory (swin[0..nWin)), seeds of window w at ln.wa[w*caps.spw ..].
 __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const DevIndex& ix, const star_params_t& P, const ReadInfo& ri, u32 i, u32 slab,
                                                  const Piece* __restrict__ pieces, const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool,
-                                                 const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason) {
+                                                 const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason, u32* sortScratch = nullptr) {
     const u32 Lread = ri.Lread;
     bool tooManyAnchors = false;
     u64 saEnum = 0;
@@ -2187,6 +2187,51 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
             swin[w] = W;
         }
         __syncwarp();
+        // Reads with many windows (hundreds for long reads with many short multi-mapping seeds): the window of a locus is found by bisection
+        // over the live windows sorted by (strand, first bin) instead of a scan of the whole table per locus.  Live windows of one strand
+        // do not overlap (they were created more than winAnchorDistNbins apart and the flanks add 2 x winFlankNbins <= that), so the
+        // bisection finds the window the scan finds; should two neighbours in that order both hold the bin, the lane falls back to the scan.
+        const bool sortedLookup = sortScratch != nullptr && ww.nW > caps.sortMinW && ww.nW <= 4096 && P.winBinN < (1ULL << 19);
+        u32 nLive = 0;
+        if (sortedLookup) {
+            u32* tmpKeys = (u32*)ln.win;   // (the arena's window array is not used by the cooperative path: scratch for the unsorted keys)
+            #pragma unroll 1
+            for (u32 w = lane; w < ww.nW; w += 32) {
+                const Window W = swin[w];
+                tmpKeys[w] = W.gStart <= W.gEnd ? ((((u32)W.Str << 19) | W.gStart) << 12) | w : 0xFFFFFFFFu;
+            }
+            __syncwarp();
+            #pragma unroll 1
+            for (u32 w = lane; w < ww.nW; w += 32) {
+                const u32 mine = tmpKeys[w];
+                u32 rank = 0;
+                #pragma unroll 1
+                for (u32 v = 0; v < ww.nW; v++) { const u32 o = tmpKeys[v]; rank += (o < mine) || (o == mine && v < w); }
+                sortScratch[rank] = mine;
+            }
+            __syncwarp();
+            u32 live = 0;
+            #pragma unroll 1
+            for (u32 w = lane; w < ww.nW; w += 32) live += tmpKeys[w] != 0xFFFFFFFFu;
+            for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+            nLive = live;
+        }
+        auto findWindow = [&](u32 aStr, u64 bin) -> int {   // index of the live window of strand aStr that holds `bin`, -1 if none
+            if (nLive == 0 || bin >= (1ULL << 19)) return -1;
+            const u32 target = ((((u32)aStr << 19) | (u32)bin) << 12) | 0xFFFu;
+            u32 lo = 0, hi = nLive;                           // first sorted entry > target
+            #pragma unroll 1
+            while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (sortScratch[mid] <= target) lo = mid + 1; else hi = mid; }
+            if (lo == 0) return -1;
+            const u32 w = sortScratch[lo - 1] & 0xFFFu;
+            const Window W = swin[w];
+            if (W.Str != aStr || bin > W.gEnd) return -1;     // (gStart <= bin by the order)
+            if (lo >= 2) {                                    // the window in front must not hold the bin as well
+                const Window V = swin[sortScratch[lo - 2] & 0xFFFu];
+                if (V.Str == aStr && V.gEnd >= bin) return -2;
+            }
+            return (int)w;
+        };
         // assignment :129-185
         #pragma unroll 1
         for (u32 iP = 0; iP < nP && !overReason && !tooManyAnchors; iP++) {
@@ -2217,8 +2262,14 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                     }
                     if (kind) {   // window lookup: windows do not change during the assignment phase
                         const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
+                        bool scan = !sortedLookup;
+                        if (sortedLookup) {
+                            wD = findWindow(aStr, binD);
+                            if (kind == 2) wA = findWindow(aStr, binA);
+                            if (wD == -2 || wA == -2) { wD = -1; wA = -1; scan = true; }
+                        }
                         #pragma unroll 1
-                        for (u32 w = 0; w < ww.nW; w++) {
+                        for (u32 w = 0; scan && w < ww.nW; w++) {
                             const Window W = swin[w];
                             if (W.Str != aStr) continue;
                             if (wD < 0 && W.gStart <= binD && binD <= W.gEnd) wD = (int)w;
@@ -2353,7 +2404,7 @@ __global__ void __launch_bounds__(128, STITCH_MIN_BLOCKS) stitch_heavy_kernel(co
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
-        warpBuildWindows(ln, ww, ix, P, ri, i, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason);
+        warpBuildWindows(ln, ww, ix, P, ri, i, i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason, taskStart);
         __syncwarp();
         // ---- task table (lane 0): split depth per window, prefix sums (windows without seeds get an empty task range)
         u32 nTasks = 0;
