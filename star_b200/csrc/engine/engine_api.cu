@@ -436,11 +436,11 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     c->flat = c->heavyEst && envU32("STAR_B200_HEAVY_FLAT", 1) != 0;
     if (c->flat) {
         FlatArgs& fa = c->fa;
-        const u64 perRead = envU32("STAR_B200_FLAT_POOL_KB", 16) * 1024ULL;
+        const u64 perRead = envU32("STAR_B200_FLAT_POOL_KB", 24) * 1024ULL;
         fa.poolBytes = std::min<u64>(48ULL << 30, std::max<u64>(256ULL << 20, (u64)N * perRead));
-        fa.maxTasks = std::max<u64>(4ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TASKS_PER_READ", 192));
+        fa.maxTasks = std::max<u64>(4ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TASKS_PER_READ", 256));
         if (fa.maxTasks > 0xFFFF0000ULL) fa.maxTasks = 0xFFFF0000ULL;
-        fa.maxBlocks = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(1ULL << 20, (u64)N * envU32("STAR_B200_FLAT_BLOCKS_PER_READ", 16)));
+        fa.maxBlocks = (u32)std::min<u64>(0xFFFF0000ULL, std::max<u64>(1ULL << 20, (u64)N * envU32("STAR_B200_FLAT_BLOCKS_PER_READ", 32)));
         fa.trWords = std::min<u64>(0xFFFF0000ULL, std::max<u64>(16ULL << 20, (u64)N * envU32("STAR_B200_FLAT_TRWORDS_PER_READ", 2048)));
         // absolute overrides (tests exercise the exhaustion paths with tiny pools)
         if (getenv("STAR_B200_FLAT_POOL_BYTES")) fa.poolBytes = strtoull(getenv("STAR_B200_FLAT_POOL_BYTES"), nullptr, 10);

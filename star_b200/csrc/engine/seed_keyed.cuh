@@ -121,9 +121,11 @@ SB_DEV u32 grpLcpRow(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N
 
 // The block [b1,b2] of SA rows of [lo,hi] whose match length with the piece is maximal, and that length; rows of [lo,hi] share the first
 // Lc bases with the piece, L is the length the caller's interval guarantees (as in warpMaxMappableLength, with Grp::G probes per step).
+struct BlockRes { u64 b1, b2; u32 L, probes, bases; };   // returned BY VALUE by the out-of-line searches: taking the address of a hot
+                                                          // variable (probes, bases, maxL) would move it to local memory for the whole kernel
 template <class Grp>
-__device__ __noinline__ u64 groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u64 lo, u64 hi, bool dirR, u32 Lin, u32& Lout, u64* indStartEnd,
-                            u32& probes, u32& bases) {
+__device__ __noinline__ BlockRes groupMaxMappable(const Grp& g, const DevIndex& ix, const u8* R, u64 S, u32 N, u64 lo, u64 hi, bool dirR, u32 Lin) {
+    u32 probes = 0, bases = 0;
     const u32 lane = g.lane;
     u64 i1 = lo, i2 = hi, i3 = lo;
     u32 L3 = 0, Lc = Lin;
@@ -199,9 +201,9 @@ __device__ __noinline__ u64 groupMaxMappable(const Grp& g, const DevIndex& ix, c
         }
         if (left) b1 = res; else b2 = res;
     }
-    Lout = L3;
-    indStartEnd[0] = b1; indStartEnd[1] = b2;
-    return b2 - b1 + 1;
+    BlockRes r;
+    r.b1 = b1; r.b2 = b2; r.L = L3; r.probes = probes; r.bases = bases;
+    return r;
 }
 
 // match length of a row's key with the piece's key over m bases (both left-aligned in 28 bits)
@@ -234,16 +236,20 @@ __device__ __noinline__ u64 keyBound(const u32* __restrict__ keys, u64 i1, u64 i
 // keyedWindow for a window too large to scan: the rows equal to the piece over m bases, else the block around the insertion point that
 // shares the most bases with it (the maximal match is attained next to the insertion point; its block = the rows equal over that many bases).
 // Every lane of the group runs the same bisection (broadcast loads).
-__device__ __noinline__ u32 keyedWindowBisect(const u32* __restrict__ keys, u64 i1, u64 i2, u32 rk, u32 m, u64& b1, u64& b2, u32& probes) {
+__device__ __noinline__ BlockRes keyedWindowBisect(const u32* __restrict__ keys, u64 i1, u64 i2, u32 rk, u32 m) {
+    u32 probes = 0;
+    BlockRes r;
+    r.bases = 0;
     const u64 lb = keyBound(keys, i1, i2, rk, m, false, probes), ub = keyBound(keys, i1, i2, rk, m, true, probes);
-    if (ub > lb) { b1 = lb; b2 = ub - 1; return m; }
+    if (ub > lb) { r.b1 = lb; r.b2 = ub - 1; r.L = m; r.probes = probes; return r; }
     u32 la = 0, lbv = 0;                                   // neighbours of the insertion point
     if (lb > i1) la = keyLcp(SB_LDG(keys + lb - 1), rk, m);
     if (lb <= i2) lbv = keyLcp(SB_LDG(keys + lb), rk, m);
     const u32 best = la > lbv ? la : lbv;
-    b1 = best ? keyBound(keys, i1, i2, rk, best, false, probes) : i1;
-    b2 = best ? keyBound(keys, i1, i2, rk, best, true, probes) - 1 : i2;
-    return best;
+    r.b1 = best ? keyBound(keys, i1, i2, rk, best, false, probes) : i1;
+    r.b2 = best ? keyBound(keys, i1, i2, rk, best, true, probes) - 1 : i2;
+    r.L = best; r.probes = probes;
+    return r;
 }
 
 // Keyed window: rows [i1,i2] share the SAindex prefix (Lk bases) with the piece.  Finds the maximal match length over the next m = min(14, N-Lk)
@@ -281,7 +287,9 @@ SB_DEV u32 keyedWindow(const Grp& g, const u32* __restrict__ keys, u32 scanMax, 
         b1 = first; b2 = last;
         return best;
     }
-    return keyedWindowBisect(keys, i1, i2, rk, m, b1, b2, probes);   // large window (repeats, low-complexity prefixes): cold, out of line
+    const BlockRes r = keyedWindowBisect(keys, i1, i2, rk, m);   // large window (repeats, low-complexity prefixes): cold, out of line
+    b1 = r.b1; b2 = r.b2; probes += r.probes;
+    return r.L;
 }
 
 // ReadAlign_maxMappableLength2strands.cpp:5-115 (gSAsparseD == 1) for one piece by one group.  Returns the record fields.
@@ -348,7 +356,10 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
         if (m == 0) { b1 = iSA1; b2 = iSA2; }
         if (kl == m && Lk + m < pieceLength) {                         // rows b1..b2 match all 28 bases and the piece goes on: genome
             if (b1 == b2) { maxL = grpLcpRow(g, ix, R, pieceStart, pieceLength, Lk + m, b1, dirR, bases); probes++; indStartEnd[0] = indStartEnd[1] = b1; }
-            else groupMaxMappable(g, ix, R, pieceStart, pieceLength, b1, b2, dirR, Lk + m, maxL, indStartEnd, probes, bases);
+            else {
+                const BlockRes r = groupMaxMappable(g, ix, R, pieceStart, pieceLength, b1, b2, dirR, Lk + m);
+                maxL = r.L; indStartEnd[0] = r.b1; indStartEnd[1] = r.b2; probes += r.probes; bases += r.bases;
+            }
         } else {
             maxL = Lk + kl;
             indStartEnd[0] = b1; indStartEnd[1] = b2;
@@ -356,7 +367,9 @@ SB_DEV void groupSearch(const Grp& g, const DevIndex& ix, const u32* __restrict_
         Nrep = indStartEnd[1] - indStartEnd[0] + 1;
     } else {                                                           // interval with N inside the prefix / without an upper bound: search all of it
         const u32 L0 = (iSA2good && iSA1noN) ? Lind : 0;
-        Nrep = groupMaxMappable(g, ix, R, pieceStart, pieceLength, iSA1 & ix.SAiMarkNmask, iSA2, dirR, L0, maxL, indStartEnd, probes, bases);
+        const BlockRes r = groupMaxMappable(g, ix, R, pieceStart, pieceLength, iSA1 & ix.SAiMarkNmask, iSA2, dirR, L0);
+        maxL = r.L; indStartEnd[0] = r.b1; indStartEnd[1] = r.b2; probes += r.probes; bases += r.bases;
+        Nrep = r.b2 - r.b1 + 1;
     }
     maxLout = maxL;
     SAstart = indStartEnd[0];

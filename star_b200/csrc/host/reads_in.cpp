@@ -379,7 +379,7 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     for (int t = 0; t < nT; t++) { totSeq += part[t].seq.size(); totNames += part[t].names.size(); }
     c.seq.reserve(totSeq); c.qual.reserve(totSeq); c.names.reserve(totNames);
     c.seqOff.reserve(nRec * nMates + 1); c.nameOff.reserve(nRec + 1); c.readFilter.reserve(nRec); c.iReadAll.reserve(nRec);
-    const bool plainMerge = !P->clipYes && P->outReadsUnmapped != "Fastx" && nT > 1;
+    const bool plainMerge = !P->clipYes && P->outReadsUnmapped != "Fastx" && nT > 1 && getenv("STAR_B200_READER_PARALLEL_MERGE") != nullptr;   // (measured on the 128-core box: slower than the sequential appends; kept for experiments)
     if (plainMerge) {   // the common case: every parse thread copies its own piece to its final place (the copies are the reader's largest cost)
         std::vector<uint64_t> seqBase(nT + 1, 0), nameBase(nT + 1, 0), recBase(nT + 1, 0);
         for (int t = 0; t < nT; t++) { seqBase[t + 1] = seqBase[t] + part[t].seq.size(); nameBase[t + 1] = nameBase[t] + part[t].names.size(); recBase[t + 1] = recBase[t] + part[t].nReads; }
