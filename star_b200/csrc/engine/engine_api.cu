@@ -751,7 +751,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
         if (nSlow == 0) break;
         star_ctx::Tier& T = c->tiers[tier];
         const u32 perWarpT = (2 * c->smemStride + 32 + T.caps.maxW * (u32)sizeof(Window) + (T.caps.maxW + 4) * 4 + ((T.caps.maxW + 3) & ~3u) + 15) & ~15u;
-        const bool flatTier = tier == 0 && c->flat && 4 * perWarpT <= 200 * 1024 && envU32("STAR_B200_FLAT_TIER", 1) != 0;
+        const bool flatTier = tier == 0 && c->flat && 4 * perWarpT <= 226 * 1024 && envU32("STAR_B200_FLAT_TIER", 1) != 0;   // (one CTA of flat_setup_kernel<2> per SM)
         if (!T.pieces) {
             CK(cudaMalloc((void**)&T.pieces, (size_t)T.batch * T.caps.maxP * sizeof(Piece)));
             c->owned.push_back(T.pieces);

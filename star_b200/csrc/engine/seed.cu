@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(128) seed_replay_kernel(const __grid_constant_
         u32 searches = 0, sai = 0;
         if (!st.flags) {
             const SeedRec* rec = ka.recs + (u64)i * ka.maxRec;
-            if (n <= 64) {   // the usual case: sort (chainId, k, slot) words in a small local array, then replay in that order
-                u64 ord[64];
+            if (n <= 256) {   // the usual case: sort (chainId, k, slot) words in a small local array, then replay in that order
+                u32 ord[256];
 #pragma unroll 1
                 for (u32 r = 0; r < n; r++) {
-                    const u64 key = ((u64)rec[r].chainId << 16) | ((u64)rec[r].k << 8);
+                    const u32 key = ((u32)rec[r].chainId << 16) | ((u32)rec[r].k << 8);   // (chain ids use 12 bits; one record per (chain, k))
                     u32 j = r;
 #pragma unroll 1
-                    while (j > 0 && (ord[j - 1] >> 8) > (key >> 8)) { ord[j] = ord[j - 1]; j--; }   // (keys are unique: one record per (chain, k))
+                    while (j > 0 && (ord[j - 1] >> 8) > (key >> 8)) { ord[j] = ord[j - 1]; j--; }
                     ord[j] = key | r;
                 }
 #pragma unroll 1

@@ -597,7 +597,7 @@ void launch_flat_setup(int ctasPerSM, int nSM, u32 smem, cudaStream_t stream, co
                        star_read_result_t* results, star_align_t* staged, u32 smemStride, const FlatArgs& fa, u32 kBase) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(flat_setup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(flat_setup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);   // (sm_100: 227 KB per CTA; the overflow tier's window table of 2048 x 20 B per warp needs 203 KB)
         cudaFuncSetAttribute(flat_setup_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(flat_setup_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
