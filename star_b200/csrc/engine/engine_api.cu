@@ -237,6 +237,12 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->nSM = prop.multiProcessorCount;
+    {   // The path is random 32-byte sector access over an index of tens of GB; with the default 64-byte fill granularity of L2 every miss fetches
+        // a neighbour sector nobody reads (measured: DRAM bytes ~2 x the sectors the kernels request).  A hint: ignored where unsupported.
+        const u32 gran = envU32("STAR_B200_L2_FETCH_BYTES", 32);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
 
