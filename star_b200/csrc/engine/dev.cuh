@@ -152,7 +152,7 @@ struct Caps {
     u32 maxTr;       // transcript pool per read
     u32 spw;         // seedPerWindowNmax
     u32 nOut;        // staged alignments per read (outFilterMultimapNmax)
-    u32 sortMinW = 48;   // reads with more windows than this look a locus' window up by bisection (sorted index) instead of a scan
+    u32 sortMinW = 12;   // reads with more windows than this look a locus' window up by bisection (sorted index) instead of a scan
     u64 arenaBytes;
 };
 

@@ -333,7 +333,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     c->fast.maxTr = envU32("STAR_B200_FAST_MAXTR", 128);
     c->fast.spw = (u32)params->seedPerWindowNmax;
     c->fast.nOut = nOut;
-    c->fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 48);
+    c->fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12);
     if (c->fast.maxP > params->seedPerReadNmax) c->fast.maxP = (u32)params->seedPerReadNmax;
     if (c->fast.maxW > params->alignWindowsPerReadNmax) c->fast.maxW = (u32)params->alignWindowsPerReadNmax;
     c->fast.maxW = (c->fast.maxW + 1) & ~1u;
