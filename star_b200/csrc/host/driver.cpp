@@ -335,6 +335,9 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     // formatted: at most two formatted chunks wait in memory
     struct WriteJob { std::vector<std::string> pieces; bool last = false; };
     std::mutex wrM; std::condition_variable wrCv; std::deque<WriteJob> wrQ;
+    // the per-thread text pieces (hundreds of MB per chunk) circulate between the output thread and the writer instead of being allocated
+    // and released per chunk: fresh allocations of that size are mapped, faulted in page by page and unmapped again by every chunk
+    std::mutex poolM; std::vector<std::vector<std::string>> piecePool;
     std::thread writerThread([&] {
         for (;;) {
             WriteJob job;
@@ -347,6 +350,8 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
                 auto tw0 = now();
                 for (const std::string& p : job.pieces) samO.write(p.data(), p.size());
                 msWrite += msSince(tw0);
+                std::lock_guard<std::mutex> lp(poolM);
+                piecePool.emplace_back(std::move(job.pieces));
             }
             {
                 std::lock_guard<std::mutex> l(wrM);
@@ -370,7 +375,13 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             if (!abortRun.load()) {
                 const ReadChunk& chunk = wk->chunk;
                 auto tf0 = now();
-                std::vector<std::string> sam(nT);
+                std::vector<std::string> sam;
+                {
+                    std::lock_guard<std::mutex> lp(poolM);
+                    if (!piecePool.empty()) { sam.swap(piecePool.back()); piecePool.pop_back(); }
+                }
+                sam.resize(nT);
+                for (auto& piece : sam) piece.clear();   // (the capacity stays)
                 std::vector<std::vector<Junction>> sj(nT);
                 std::vector<Stats> st(nT);
                 std::vector<std::string> cblob(coordYes ? nT : 0);

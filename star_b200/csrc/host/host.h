@@ -215,6 +215,8 @@ class ReadsReader {
     long long nextStream(ReadChunk& c, uint32_t maxReads, std::string& err);   // line-by-line parser (piped input, FASTA)
     std::vector<ReadChunk> parts_;                       // per-thread pieces, kept between chunks (their buffers stay mapped)
     std::vector<const char*> lineSt_[2], lineEn_[2];     // line index of the current chunk
+    std::vector<std::vector<const char*>> idxFound_[2];  // newlines found by each indexing thread
+    double lineBytes_[2] = {64.0, 64.0};                  // mean line length seen so far (sizes the range the next index scans)
     // parses one FASTQ record given its four lines of each mate (pointers into the mapped files); appends to `c`; returns 0 or -STAR_EXIT_*
     int parseRecord(ReadChunk& c, uint64_t iRead, const char* const* ls, const char* const* le, std::string& err) const;
 };

@@ -310,22 +310,62 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     for (int m = 0; m < 2; m++) { st[m].clear(); en[m].clear(); }
     size_t newOff[2] = {mapOff[0], mapOff[1]};
     long long badOff = -1;   // offset of a record start (mate 1) that is neither '@' nor end of input
+    // every mate's lines are found by several threads: the range expected to hold 4*want lines (from the line length seen so far) is cut
+    // into slices, each thread collects the newlines of its slice (this is also where the pages of the mapped file are faulted in), the
+    // slices are concatenated in order; short of lines, the next range is scanned the same way
+    const int nIdx = (int)std::max(1, std::min(16, std::max(1, P->runThreadN) / (int)nMates));
     auto indexMate = [&](unsigned m) {
-        st[m].reserve(4 * want); en[m].reserve(4 * want);
         const char* base = map[m];
-        const size_t size = mapSize[m];
-        size_t off = mapOff[m];
-        for (uint64_t k = 0; k < 4 * want && off < size; k++) {
-            if (m == 0 && (k & 3) == 0 && base[off] != '@') {        // end of the records (e.g. trailing blank line) ...
-                if (base[off] != ' ' && base[off] != '\n') badOff = (long long)off;   // ... or text that is not a record: fatal in the reference
-                break;
+        const size_t size = mapSize[m], off0 = mapOff[m];
+        const uint64_t wantLines = 4 * want;
+        std::vector<const char*>& E = en[m];
+        E.reserve(wantLines);
+        std::vector<std::vector<const char*>>& found = idxFound_[m];
+        if ((int)found.size() < nIdx) found.resize(nIdx);
+        size_t scanned = off0;
+        while (E.size() < wantLines && scanned < size) {
+            const uint64_t need = wantLines - E.size();
+            const size_t est = (size_t)((double)need * lineBytes_[m] * 1.02) + 65536;
+            const size_t hi = est < size - scanned ? scanned + est : size;
+            const int nT = (int)std::max<size_t>(1, std::min<size_t>((size_t)nIdx, (hi - scanned) >> 20));
+            auto scan = [&](int t) {
+                std::vector<const char*>& F = found[t];
+                F.clear();
+                const char* p = base + scanned + (hi - scanned) * (size_t)t / nT;
+                const char* e = base + scanned + (hi - scanned) * (size_t)(t + 1) / nT;
+                while (p < e) {
+                    const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+                    if (!q) break;
+                    F.push_back(q);
+                    p = q + 1;
+                }
+            };
+            if (nT == 1) scan(0);
+            else {
+                std::vector<std::thread> th;
+                for (int t = 1; t < nT; t++) th.emplace_back(scan, t);
+                scan(0);
+                for (auto& t : th) t.join();
             }
-            const char* q = (const char*)memchr(base + off, '\n', size - off);
-            st[m].push_back(base + off);
-            if (q) { en[m].push_back(q); off = (size_t)(q - base) + 1; }
-            else { en[m].push_back(base + size); off = size; }
+            for (int t = 0; t < nT && E.size() < wantLines; t++) {
+                const size_t take = std::min<size_t>(found[t].size(), wantLines - E.size());
+                E.insert(E.end(), found[t].begin(), found[t].begin() + take);
+            }
+            scanned = hi;
         }
-        newOff[m] = off;
+        if (E.size() < wantLines && (E.empty() ? off0 : (size_t)(E.back() - base) + 1) < size) E.push_back(base + size);   // last line without a newline
+        std::vector<const char*>& S = st[m];
+        S.resize(E.size());
+        for (size_t k = 0; k < E.size(); k++) S[k] = k ? E[k - 1] + 1 : base + off0;
+        if (m == 0)
+            for (size_t k = 0; k < S.size(); k += 4)
+                if (*S[k] != '@') {                                   // end of the records (e.g. trailing blank line) ...
+                    if (*S[k] != ' ' && *S[k] != '\n') badOff = (long long)(S[k] - base);   // ... or text that is not a record: fatal in the reference
+                    S.resize(k); E.resize(k);
+                    break;
+                }
+        newOff[m] = E.empty() ? off0 : (E.back() < base + size ? (size_t)(E.back() - base) + 1 : size);
+        if (!E.empty()) lineBytes_[m] = (double)(newOff[m] - off0) / (double)E.size();
     };
     if (nMates == 2) { std::thread t1(indexMate, 1u); indexMate(0); t1.join(); } else indexMate(0);
     const uint64_t nRec = (st[0].size() + 3) / 4;   // a last record with missing lines is still a record (its errors are reported)

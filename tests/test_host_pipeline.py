@@ -200,3 +200,32 @@ def test_shards_over_a_file_list(oracle, golden, tmp_path):
     whole = str(tmp_path) + "/w."
     _cli(os.path.join(golden, "idx"), parts, whole, ["--outSAMreadID", "Number"])
     assert all(len(b) > 0 for b in bodies) and sum(bodies, []) == cf.sam_body(whole + "Aligned.out.sam")
+
+
+def test_parallel_line_index_of_a_large_file(oracle, golden, tmp_path):
+    """The memory-mapped reader finds the lines of a chunk with several threads per mate (slices of >= 1 MB, ranges sized from the line
+    length seen so far, a second range when the estimate was short).  A file of several MB with growing record lengths must give the
+    same records as the stream parser (behind --readFilesCommand cat), across chunk boundaries."""
+    with open(os.path.join(golden, "std_1.fq")) as f:
+        l1 = f.read().split("\n")
+    with open(os.path.join(golden, "std_2.fq")) as f:
+        l2 = f.read().split("\n")
+    nrec = min(len(l1), len(l2)) // 4
+    big1, big2 = [], []
+    k = 0
+    while sum(len(x) for x in big1) < 5_000_000:       # the records repeated under new names; later copies get longer ID lines
+        for r in range(nrec):
+            pad = " pad" * (k // 2000)
+            big1 += ["@n%d%s" % (k, pad), l1[4 * r + 1], "+", l1[4 * r + 3]]
+            big2 += ["@n%d%s" % (k, pad), l2[4 * r + 1], "+", l2[4 * r + 3]]
+            k += 1
+    f1, f2 = str(tmp_path / "big_1.fq"), str(tmp_path / "big_2.fq")
+    open(f1, "w").write("\n".join(big1))               # (no newline at the end of mate 1)
+    open(f2, "w").write("\n".join(big2) + "\n")
+    outs = []
+    for tag, extra, thr in (("map", [], 8), ("stream", ["--readFilesCommand", "cat"], 2)):
+        out = str(tmp_path) + "/" + tag + "/"
+        os.makedirs(out)
+        _cli(os.path.join(golden, "idx"), [f1, f2], out, ["--gpuChunkReads", "9000", "--readMapNumber", "30000"] + extra, threads=thr)
+        outs.append(cf.sam_body(out + "Aligned.out.sam"))
+    assert len(outs[0]) > 30000 and outs[0] == outs[1]
