@@ -239,8 +239,15 @@ int star_gpu_map_chunk(star_ctx_t* ctx, const star_read_batch_t* in, star_align_
 int star_gpu_upload_chunk(star_ctx_t* ctx, const star_read_batch_t* in);
 /* Runs all kernels on the uploaded chunk; results stay on the device.  stats->ms_* are filled. */
 int star_gpu_map_resident(star_ctx_t* ctx, star_chunk_stats_t* stats);
-/* Copies the results of the last star_gpu_map_resident to host buffers. */
+/* Copies the results of the last star_gpu_map_resident / star_gpu_map_chunk to host buffers.  When out->alignsCapacity is smaller than
+ * the number of records, nothing is copied: STAR_EXIT_RUNTIME is returned with out->nAligns = the capacity needed (the results stay
+ * resident; the call can be repeated with a larger buffer).  star_gpu_map_chunk behaves the same way. */
 int star_gpu_download_results(star_ctx_t* ctx, star_align_batch_t* out);
+
+/* Page-locked host memory for the chunk buffers (`in->seq`, `out->reads`, `out->aligns`): copies from / to pageable memory reach a
+ * fraction of the link rate.  Optional: every entry point accepts pageable buffers.  NULL when the allocation fails. */
+void* star_gpu_host_alloc(size_t bytes);
+void star_gpu_host_free(void* p);
 
 /* 2nd stage of --outFilterType BySJout (reference source/stitchWindowAligns.cpp:169-177, outputSJ.cpp:139-160): from now on an alignment
  * with an unannotated junction is only kept when the junction (first / last intron base, 0-based genome coordinates) is in this list, which
@@ -343,6 +350,11 @@ typedef struct star_engine_vtbl {
     int (*sa_build)(int device, const uint8_t* G, uint64_t nGenome, uint32_t GstrandBit, uint64_t nSA, uint8_t* SA, uint64_t nSAbyte);
     /* 2nd stage of --outFilterType BySJout (same meaning as star_gpu_set_sj_novel) */
     int (*set_sj_novel)(void* ctx, const uint64_t* sjStart, const uint64_t* sjEnd, uint64_t n);
+    /* optional (may be NULL): page-locked chunk buffers (star_gpu_host_alloc / star_gpu_host_free) and a second fetch of the last
+     * chunk's results after map_chunk reported a too small out->alignsCapacity (star_gpu_download_results) */
+    void* (*host_alloc)(size_t bytes);
+    void (*host_free)(void* p);
+    int (*download_results)(void* ctx, star_align_batch_t* out);
 } star_engine_vtbl_t;
 int star_cli_main_engine(int argc, char** argv, const star_engine_vtbl_t* engine);
 

@@ -10,6 +10,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "star_oracle.h"
 
@@ -24,6 +26,32 @@ int emMerge(void* h, const uint64_t* ind, uint64_t nInd, uint64_t nGsj, uint64_t
     return g_merge((const star_index_view_t*)h, ind, nInd, nGsj, nGsjNew, L, old, SAnew, nByte);
 }
 void emClose(void*) {}
+
+// STAR_CLI_PINNED_EMUL=1: the optional vtable members of the CUDA engine (page-locked buffers, second fetch after a too small
+// out->alignsCapacity) are emulated around the oracle engine so that the driver's use of them is tested without a GPU.
+const star_engine_vtbl_t* g_base;
+std::vector<star_align_t> g_lastAligns;
+std::vector<star_read_result_t> g_lastReads;
+long g_hostAllocs = 0, g_capacityMisses = 0;
+void* pinAlloc(size_t n) { g_hostAllocs++; return malloc(n ? n : 1); }
+void pinFree(void* p) { free(p); }
+int pinDownload(void*, star_align_batch_t* out) {
+    if (g_lastAligns.size() > out->alignsCapacity) { out->nAligns = g_lastAligns.size(); g_capacityMisses++; return STAR_EXIT_RUNTIME; }
+    if (!g_lastReads.empty()) memcpy(out->reads, g_lastReads.data(), g_lastReads.size() * sizeof(star_read_result_t));
+    if (!g_lastAligns.empty()) memcpy(out->aligns, g_lastAligns.data(), g_lastAligns.size() * sizeof(star_align_t));
+    out->nAligns = g_lastAligns.size();
+    return 0;
+}
+int pinMap(void* ctx, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* st) {
+    g_lastReads.assign(in->nReads, star_read_result_t());
+    g_lastAligns.resize((size_t)in->nReads * 64 + 64);
+    star_align_batch_t tmp;
+    tmp.reads = g_lastReads.data(); tmp.aligns = g_lastAligns.data(); tmp.alignsCapacity = g_lastAligns.size(); tmp.nAligns = 0;
+    const int rc = g_base->map_chunk(ctx, in, &tmp, st);
+    if (rc) return rc;
+    g_lastAligns.resize(tmp.nAligns);
+    return pinDownload(ctx, out);
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -40,5 +68,12 @@ int main(int argc, char** argv) {
         if (!sa) { fprintf(stderr, "%s lacks engine_emul_sa_build\n", lib); return 1; }
         vt.sa_build = sa;
     }
-    return star_cli_main_engine(argc, argv, &vt);
+    if (getenv("STAR_CLI_PINNED_EMUL")) {
+        static star_engine_vtbl_t base = vt;
+        g_base = &base;
+        vt.map_chunk = pinMap; vt.host_alloc = pinAlloc; vt.host_free = pinFree; vt.download_results = pinDownload;
+    }
+    const int rc = star_cli_main_engine(argc, argv, &vt);
+    if (getenv("STAR_CLI_PINNED_EMUL")) fprintf(stderr, "pinned emulation: %ld host allocations, %ld capacity misses\n", g_hostAllocs, g_capacityMisses);
+    return rc;
 }

@@ -861,7 +861,7 @@ int star_gpu_map_resident(star_ctx_t* c, star_chunk_stats_t* stats) {
 
 int star_gpu_download_results(star_ctx_t* c, star_align_batch_t* out) {
     CK(cudaSetDevice(c->device));
-    if (c->nAligns > out->alignsCapacity) { g_err = "star_b200: aligns capacity too small"; return STAR_EXIT_RUNTIME; }
+    if (c->nAligns > out->alignsCapacity) { out->nAligns = c->nAligns; g_err = "star_b200: aligns capacity too small"; return STAR_EXIT_RUNTIME; }
     CK(cudaEventRecord(c->ev[0], c->stream));
     if (c->nReads) CK(cudaMemcpyAsync(out->reads, c->d_results, (size_t)c->nReads * sizeof(star_read_result_t), cudaMemcpyDeviceToHost, c->stream));
     if (c->nAligns) CK(cudaMemcpyAsync(out->aligns, c->d_aligns, (size_t)c->nAligns * sizeof(star_align_t), cudaMemcpyDeviceToHost, c->stream));
@@ -875,6 +875,13 @@ int star_gpu_download_results(star_ctx_t* c, star_align_batch_t* out) {
     return 0;
 }
 
+void* star_gpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void star_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int star_gpu_map_chunk(star_ctx_t* c, const star_read_batch_t* in, star_align_batch_t* out, star_chunk_stats_t* stats) {
     memset(&c->last, 0, sizeof(c->last));
     int rc = star_gpu_upload_chunk(c, in);
@@ -885,11 +892,10 @@ int star_gpu_map_chunk(star_ctx_t* c, const star_read_batch_t* in, star_align_ba
     float msH2D = 0;
     if (c->nReads) cudaEventElapsedTime(&msH2D, c->ev[0], c->ev[1]);   // before ev[0] is reused by the download
     rc = star_gpu_download_results(c, out);
-    if (rc) return rc;
     c->last.ms_h2d = msH2D;
     c->last.ms_total += msH2D + c->last.ms_d2h;
-    if (stats) *stats = c->last;
-    return 0;
+    if (stats) *stats = c->last;   // (also when the capacity was too small: the caller may fetch the results again)
+    return rc;
 }
 
 // debug / analysis: copies the per-read ReadInfo records (work counters, flags) of the resident chunk
@@ -931,7 +937,9 @@ static int vt_sjdb_merge(void* h, const uint64_t* indSorted, uint64_t nInd, uint
 }
 static int vt_set_sj_novel(void* c, const uint64_t* a, const uint64_t* b, uint64_t n) { return star_gpu_set_sj_novel((star_ctx_t*)c, a, b, n); }
 static void vt_sjdb_close(void* h) { star_gpu_sjdb_close((star_sjdb_t*)h); }
-static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close, star_gpu_sa_build, vt_set_sj_novel};
+static int vt_download(void* ctx, star_align_batch_t* out) { return star_gpu_download_results((star_ctx_t*)ctx, out); }
+static const star_engine_vtbl_t g_cuda_engine = {vt_init, vt_map, vt_destroy, star_gpu_last_error, vt_sjdb_open, vt_sjdb_search, vt_sjdb_merge, vt_sjdb_close, star_gpu_sa_build, vt_set_sj_novel,
+                                                 star_gpu_host_alloc, star_gpu_host_free, vt_download};
 
 int star_cli_main(int argc, char** argv) { return star_cli_main_engine(argc, argv, &g_cuda_engine); }
 

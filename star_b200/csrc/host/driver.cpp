@@ -287,10 +287,13 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     //   output thread   : SAM / junction / counter formatting on runThreadN threads, ordered writes
     struct Work {
         ReadChunk chunk;
-        std::vector<star_read_result_t> results;
-        // worst case nReads x outFilterMultimapNmax records of 496 B: allocated once, NOT value-initialised (only the part the
-        // engine fills is ever touched, so the untouched pages are never faulted in)
-        std::unique_ptr<star_align_t[]> aligns; uint64_t alignsCap = 0;
+        // result buffers: page-locked when the engine offers such memory (device->host copies to pageable memory run at a fraction of
+        // the link rate), sized for 5/4 records per read and grown when a chunk holds more; otherwise plain memory for the worst case
+        // nReads x outFilterMultimapNmax records of 496 B, allocated once and not initialised (only the part the engine fills is ever
+        // touched, so the untouched pages are never faulted in)
+        star_read_result_t* results = nullptr; uint64_t resultsCap = 0; bool resultsPinned = false;
+        star_align_t* aligns = nullptr; uint64_t alignsCap = 0; bool alignsPinned = false;
+        uint8_t* inPin = nullptr; uint64_t inPinCap = 0;   // page-locked copy of the chunk's sequences + offsets (the reader's strings are pageable)
         star_align_batch_t out;
         long long n = 0;          // reads in the chunk; 0 = end of input; < 0 = -STAR_EXIT_* (err holds the message)
         std::string err;
@@ -300,8 +303,24 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         void push(Work* w) { { std::lock_guard<std::mutex> l(m); q.push_back(w); } cv.notify_one(); }
         Work* pop() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty(); }); Work* w = q.front(); q.pop_front(); return w; }
     };
+    auto hostAlloc = [&](uint64_t bytes, bool pin, bool& pinned) -> void* {
+        void* p = pin ? eng->host_alloc(bytes) : nullptr;
+        pinned = p != nullptr;
+        return p ? p : malloc(bytes ? bytes : 1);
+    };
+    auto hostFree = [&](void* p, bool pinned) { if (!p) return; if (pinned) eng->host_free(p); else free(p); };
     const int NBUF = 3;
     std::vector<Work> bufs(NBUF);
+    struct BufRelease {   // (runs after the three threads were joined: every return below comes after the joins)
+        std::vector<Work>& b; const star_engine_vtbl_t* e;
+        ~BufRelease() {
+            for (Work& w : b) {
+                if (w.results) { if (w.resultsPinned) e->host_free(w.results); else free(w.results); }
+                if (w.aligns) { if (w.alignsPinned) e->host_free(w.aligns); else free(w.aligns); }
+                if (w.inPin) e->host_free(w.inPin);
+            }
+        }
+    } bufRelease{bufs, eng};
     Queue freeQ, mapQ, outQ;
     for (auto& wk : bufs) freeQ.push(&wk);
     // coordinate-sorted BAM: all records stay in host memory (uncompressed, ~0.55 kB per record) until the end of the run
@@ -474,13 +493,57 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         star_read_batch_t in;
         in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
         if (chunk.clipped()) { in.seq = chunk.seqC.data(); in.seqOff = chunk.seqOffC.data(); }   // the engine maps the clipped reads
-        uint64_t cap = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
-        if (wk->alignsCap < cap) { wk->aligns.reset(new star_align_t[cap]); wk->alignsCap = cap; }
-        if (wk->results.size() < chunk.nReads) wk->results.resize(chunk.nReads);
-        wk->out.reads = wk->results.data(); wk->out.aligns = wk->aligns.get(); wk->out.alignsCapacity = wk->alignsCap; wk->out.nAligns = 0;
+        const uint64_t capWorst = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
+        const bool canPin = eng->host_alloc && eng->host_free && eng->download_results;
+        auto growAligns = [&](uint64_t cap) {   // false: out of memory
+            if (wk->alignsCap >= cap) return true;
+            hostFree(wk->aligns, wk->alignsPinned);
+            wk->aligns = (star_align_t*)hostAlloc(cap * sizeof(star_align_t), canPin, wk->alignsPinned);
+            wk->alignsCap = wk->aligns ? cap : 0;
+            return wk->aligns != nullptr;
+        };
+        static const uint64_t pinPct = [] { const char* e = getenv("STAR_B200_PINNED_ALIGNS_PCT"); const long v = e ? atol(e) : 0; return (uint64_t)(v > 0 ? v : 125); }();   // records per 100 reads the first page-locked buffer holds
+        bool memOk = growAligns(canPin ? std::min<uint64_t>(capWorst, (uint64_t)chunk.nReads * pinPct / 100 + 64) : capWorst);
+        if (wk->resultsCap < chunk.nReads) {
+            hostFree(wk->results, wk->resultsPinned);
+            wk->resultsCap = std::max<uint64_t>(chunk.nReads, P.gpuChunkReads);
+            wk->results = (star_read_result_t*)hostAlloc(wk->resultsCap * sizeof(star_read_result_t), canPin, wk->resultsPinned);
+            if (!wk->results) { wk->resultsCap = 0; memOk = false; }
+        }
+        if (canPin && memOk) {   // sequences and offsets through one page-locked block
+            const uint64_t nOff = (uint64_t)in.nReads * in.nMates + 1, seqBytes = in.seqOff[nOff - 1], offAt = (seqBytes + 15) & ~15ULL;
+            const uint64_t need = offAt + nOff * 8;
+            if (wk->inPinCap < need) {
+                eng->host_free(wk->inPin);
+                wk->inPinCap = need + need / 8;
+                wk->inPin = (uint8_t*)eng->host_alloc(wk->inPinCap);
+                if (!wk->inPin) wk->inPinCap = 0;
+            }
+            if (wk->inPin) {
+                memcpy(wk->inPin, in.seq, seqBytes);
+                memcpy(wk->inPin + offAt, in.seqOff, nOff * 8);
+                in.seq = (const char*)wk->inPin; in.seqOff = (const uint64_t*)(wk->inPin + offAt);
+            }
+        }
+        wk->out.reads = wk->results; wk->out.aligns = wk->aligns; wk->out.alignsCapacity = wk->alignsCap; wk->out.nAligns = 0;
         star_chunk_stats_t cs;
         memset(&cs, 0, sizeof(cs));
-        rc = eng->map_chunk(ectx, &in, &wk->out, &cs);
+        rc = memOk ? eng->map_chunk(ectx, &in, &wk->out, &cs) : STAR_EXIT_RUNTIME;
+        if (rc && memOk && canPin && wk->out.nAligns > wk->alignsCap) {   // more records than the page-locked buffer holds: grow it, fetch again
+            const uint64_t needed = wk->out.nAligns;
+            memOk = growAligns(std::min<uint64_t>(capWorst, needed + needed / 4));
+            if (memOk) {
+                wk->out.aligns = wk->aligns; wk->out.alignsCapacity = wk->alignsCap; wk->out.nAligns = 0;
+                rc = eng->download_results(ectx, &wk->out);
+            }
+        }
+        if (!memOk) {
+            runRc = STAR_EXIT_RUNTIME; runErr = "EXITING because of fatal ERROR: not enough memory for the chunk buffers of the mapping pass\n";
+            abortRun.store(true);
+            wk->n = 0;
+            outQ.push(wk);
+            break;
+        }
         if (rc) {
             runRc = rc; runErr = eng->last_error();
             abortRun.store(true);

@@ -94,6 +94,23 @@ def run_sharded(argv, cli=None, backend=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     use_cuda = cli is None
+    if world == 1:   # nothing to shard, gather or merge: the plain command line on this rank's device (it writes the final files itself)
+        t0 = time.time()
+        a = list(argv) + (["--gpuDevice", str(local_rank)] if use_cuda and "--gpuDevice" not in argv else [])
+        if cli is None:
+            import star_b200 as sb
+            lib = sb.load_library()
+            arr = (C.c_char_p * (len(a) + 1))(*([b"STAR"] + [x.encode() for x in a]))
+            rc = lib.star_cli_main(len(a) + 1, arr)
+        else:
+            rc = subprocess.call([cli] + a, stdout=subprocess.DEVNULL)
+        TIMING["map_s"] = TIMING["total_s"] = time.time() - t0
+        TIMING["world"] = 1
+        try:
+            json.dump(TIMING, open(_prefix(argv) + "dist_timing.json", "w"))
+        except OSError:
+            pass
+        return rc
     if backend is None:
         backend = "nccl" if use_cuda else "gloo"
     if use_cuda:

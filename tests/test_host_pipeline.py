@@ -229,3 +229,24 @@ def test_parallel_line_index_of_a_large_file(oracle, golden, tmp_path):
         _cli(os.path.join(golden, "idx"), [f1, f2], out, ["--gpuChunkReads", "9000", "--readMapNumber", "30000"] + extra, threads=thr)
         outs.append(cf.sam_body(out + "Aligned.out.sam"))
     assert len(outs[0]) > 30000 and outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("pct", [125, 40])
+def test_page_locked_chunk_buffers_and_second_fetch(oracle, golden, tmp_path, pct):
+    """With an engine that offers page-locked memory (star_gpu_host_alloc) the driver sizes the record buffer for 5/4 records per read,
+    copies the sequences through a page-locked block, and fetches the results a second time (star_gpu_download_results) into a larger
+    buffer when a chunk holds more records.  The optional vtable members are emulated around the oracle engine (STAR_CLI_PINNED_EMUL);
+    a buffer of 0.4 records per read forces the second fetch in every chunk.  Output = the reference's."""
+    out = str(tmp_path) + "/"
+    env = dict(os.environ, STAR_CLI_PINNED_EMUL="1", STAR_B200_PINNED_ALIGNS_PCT=str(pct))
+    cmd = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
+           "--outFileNamePrefix", out, "--runThreadN", "3", "--gpuChunkReads", "333"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    note = [l for l in r.stderr.split("\n") if l.startswith("pinned emulation:")][0].split()
+    allocs, misses = int(note[2]), int(note[5])
+    assert allocs >= 3 and (misses > 0) == (pct < 100), note
+    ref = os.path.join(golden, "ref_std")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))

@@ -36,6 +36,25 @@ def test_two_rank_sharded_run_equals_reference(oracle, lib, golden, tmp_path):
     assert n0 > 0 and n1 > 0 and n0 + n1 == len(cf.sam_body(out + "Aligned.out.sam"))
 
 
+def test_world_size_one_is_the_plain_run(oracle, lib, golden, tmp_path):
+    """`torchrun --nproc-per-node 1 -m star_b200.dist` (the N=1 point of a scaling run): no shard files, no merge — the final files are
+    the single process' own (found by the 2-GPU measurement of round 2: the N=1 launch looked for shard0.shard.bin)."""
+    out = str(tmp_path) + "/"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1", "--master-port", "29617",
+           "-m", "star_b200.dist", "--cli", oc.ORACLE_CLI, "--",
+           "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
+           "--outFileNamePrefix", out, "--runThreadN", "2"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = os.path.join(golden, "ref_std")
+    assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
+    assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
+    assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+    assert os.path.exists(out + "dist_timing.json")
+
+
 def test_shard_arguments():
     from star_b200 import dist
     a = dist.shard_args(["--genomeDir", "g", "--outFileNamePrefix", "o/x_"], 3, 8, device=3)
