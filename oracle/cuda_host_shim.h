@@ -106,6 +106,7 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     return s;
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicExch(volatile unsigned long long* p, unsigned long long v) { return __atomic_exchange_n((unsigned long long*)p, v, __ATOMIC_SEQ_CST); }

@@ -276,7 +276,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     fast.maxP = std::min<u32>(128, (u32)P.seedPerReadNmax);
     fast.maxW = (std::min<u32>(128, (u32)P.alignWindowsPerReadNmax) + 1) & ~1u;
     fast.maxTr = std::min<u32>(128, (u32)P.alignTranscriptsPerReadNmax);
-    fast.spw = (u32)P.seedPerWindowNmax; fast.nOut = nOut; fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12); fast.arenaBytes = arenaSize(fast);
+    fast.spw = (u32)P.seedPerWindowNmax; fast.nOut = nOut; fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12); fast.binFilter = envU32("STAR_B200_BIN_FILTER", 1); fast.arenaBytes = arenaSize(fast);
     Caps heavy = fast;
     heavy.maxW = (std::min<u32>((u32)P.alignWindowsPerReadNmax, 256) + 1) & ~1u;
     heavy.maxTr = std::min<u32>((u32)P.alignTranscriptsPerReadNmax, 1024);
@@ -391,7 +391,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
             mid.maxP = std::min<u32>((u32)P.seedPerReadNmax, 512);
             mid.maxW = (std::min<u32>((u32)P.alignWindowsPerReadNmax, 1024) + 1) & ~1u;
             mid.maxTr = std::min<u32>((u32)P.alignTranscriptsPerReadNmax, 1024);
-            mid.spw = fast.spw; mid.nOut = nOut; mid.sortMinW = fast.sortMinW; mid.arenaBytes = arenaSize(mid);
+            mid.spw = fast.spw; mid.nOut = nOut; mid.sortMinW = fast.sortMinW; mid.binFilter = fast.binFilter; mid.arenaBytes = arenaSize(mid);
             std::vector<Piece> tp((size_t)list.size() * mid.maxP);
             std::vector<u8> arenaMid((size_t)128 * mid.arenaBytes);
             for (u32 i : list) info[i].flags &= ~1u;

@@ -334,6 +334,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     c->fast.spw = (u32)params->seedPerWindowNmax;
     c->fast.nOut = nOut;
     c->fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12);
+    c->fast.binFilter = envU32("STAR_B200_BIN_FILTER", 1);
     if (c->fast.maxP > params->seedPerReadNmax) c->fast.maxP = (u32)params->seedPerReadNmax;
     if (c->fast.maxW > params->alignWindowsPerReadNmax) c->fast.maxW = (u32)params->alignWindowsPerReadNmax;
     c->fast.maxW = (c->fast.maxW + 1) & ~1u;
@@ -344,14 +345,14 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
         M.caps.maxP = std::min<u32>((u32)params->seedPerReadNmax, envU32("STAR_B200_MID_MAXP", 512));
         M.caps.maxW = (std::min<u32>((u32)params->alignWindowsPerReadNmax, envU32("STAR_B200_MID_MAXW", 2048)) + 1) & ~1u;
         M.caps.maxTr = std::min<u32>((u32)params->alignTranscriptsPerReadNmax, envU32("STAR_B200_MID_MAXTR", 4096));
-        M.caps.spw = c->fast.spw; M.caps.nOut = nOut; M.caps.sortMinW = c->fast.sortMinW;
+        M.caps.spw = c->fast.spw; M.caps.nOut = nOut; M.caps.sortMinW = c->fast.sortMinW; M.caps.binFilter = c->fast.binFilter;
         M.caps.arenaBytes = arenaSize(M.caps);
         M.lanes = envU32("STAR_B200_MID_LANES", 8192); M.batch = envU32("STAR_B200_MID_BATCH", 65536);
         star_ctx::Tier& S = c->tiers[1];
         S.caps.maxP = (u32)params->seedPerReadNmax;
         S.caps.maxW = ((u32)params->alignWindowsPerReadNmax + 1) & ~1u;
         S.caps.maxTr = (u32)params->alignTranscriptsPerReadNmax;
-        S.caps.spw = c->fast.spw; S.caps.nOut = nOut; S.caps.sortMinW = c->fast.sortMinW;
+        S.caps.spw = c->fast.spw; S.caps.nOut = nOut; S.caps.sortMinW = c->fast.sortMinW; S.caps.binFilter = c->fast.binFilter;
         S.caps.arenaBytes = arenaSize(S.caps);
         S.lanes = envU32("STAR_B200_SLOW_LANES", 128); S.batch = envU32("STAR_B200_SLOW_BATCH", 4096);
     }

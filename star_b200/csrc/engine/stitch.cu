@@ -2103,7 +2103,8 @@ __device__ bool coopAssign(const Lane& ln, WarpWin& ww, int iW, u64 a1, u64 aLen
 // memory (swin[0..nWin)), seeds of window w at ln.wa[w*caps.spw ..].
 __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const DevIndex& ix, const star_params_t& P, const ReadInfo& ri, u32 i, u32 slab,
                                                  const Piece* __restrict__ pieces, const u64* __restrict__ heavyOff, const u8* __restrict__ heavyPool,
-                                                 const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason, u32* sortScratch = nullptr) {
+                                                 const Caps& caps, Window* swin, u32 lane, u32& nWin, u32& overReason, u32* sortScratch = nullptr,
+                                                 u32* binFilter = nullptr, u32 filterLog2 = 0) {
     const u32 Lread = ri.Lread;
     bool tooManyAnchors = false;
     u64 saEnum = 0;
@@ -2216,6 +2217,31 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
             for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
             nLive = live;
         }
+        // Almost every locus of a multi-mapping piece falls into no window at all.  One bit per (strand, bin) covered by a live window, hashed
+        // into 2^filterLog2 bits of shared memory, answers "in no window" with one load; only loci that pass are looked up (a bit set by
+        // another bin costs a lookup that finds nothing: the result does not depend on the filter).
+        bool useFilter = binFilter != nullptr && filterLog2 >= 8 && caps.binFilter != 0 && ww.nW > 0;
+        auto filterHash = [&](u32 aStr, u64 bin) -> u32 { return (((u32)bin * 2654435761u) ^ (aStr * 0x7F4A7C15u)) >> (32 - filterLog2); };
+        if (useFilter) {
+            u32 covered = 0;
+            #pragma unroll 1
+            for (u32 w = lane; w < ww.nW; w += 32) { const Window W = swin[w]; if (W.gStart <= W.gEnd) covered += W.gEnd - W.gStart + 1; }
+            for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
+            if ((u64)covered * 4 > (1ULL << filterLog2)) useFilter = false;   // too many bins for this many bits (most loci would pass)
+        }
+        if (useFilter) {
+            #pragma unroll 1
+            for (u32 q = lane; q < (1u << filterLog2) / 32; q += 32) binFilter[q] = 0;
+            __syncwarp();
+            #pragma unroll 1
+            for (u32 w = lane; w < ww.nW; w += 32) {
+                const Window W = swin[w];
+                if (W.gStart > W.gEnd) continue;
+                #pragma unroll 1
+                for (u32 b = W.gStart; b <= W.gEnd; b++) { const u32 h = filterHash(W.Str, b); atomicOr(&binFilter[h >> 5], 1u << (h & 31)); }
+            }
+            __syncwarp();
+        }
         auto findWindow = [&](u32 aStr, u64 bin) -> int {   // index of the live window of strand aStr that holds `bin`, -1 if none
             if (nLive == 0 || bin >= (1ULL << 19)) return -1;
             const u32 target = ((((u32)aStr << 19) | (u32)bin) << 12) | 0xFFFu;
@@ -2260,7 +2286,13 @@ __device__ __forceinline__ void warpBuildWindows(Lane& ln, WarpWin& ww, const De
                         u64 a1D;
                         if (sjAlignSplit(ix, a1, aLength, a1D, aLengthD, a1A, aLengthA, isj)) { a1 = a1D; kind = 2; } else { kind = 0; isj = SJA_NONE; }
                     }
-                    if (kind) {   // window lookup: windows do not change during the assignment phase
+                    bool lookup = kind != 0;
+                    if (kind && useFilter) {
+                        const u32 hD = filterHash(aStr, a1 >> P.winBinNbits);
+                        lookup = (binFilter[hD >> 5] >> (hD & 31)) & 1u;
+                        if (!lookup && kind == 2) { const u32 hA = filterHash(aStr, a1A >> P.winBinNbits); lookup = (binFilter[hA >> 5] >> (hA & 31)) & 1u; }
+                    }
+                    if (lookup) {   // window lookup: windows do not change during the assignment phase
                         const u64 binD = a1 >> P.winBinNbits, binA = a1A >> P.winBinNbits;
                         bool scan = !sortedLookup;
                         if (sortedLookup) {

@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(128, MINB) flat_setup_kernel(const __grid_cons
         __syncwarp();
         u32 nWin = 0;
         u32 overReason = 0;
-        warpBuildWindows(ln, ww, ix, P, ri, i, fa.slabByPos ? k : i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason, taskStart);
+        // (the depth bytes behind the task table are not in use before the windows are final: they hold the bin filter of the assignment phase)
+        warpBuildWindows(ln, ww, ix, P, ri, i, fa.slabByPos ? k : i, pieces, heavyOff, heavyPool, caps, swin, lane, nWin, overReason, taskStart,
+                         (u32*)depthOf, 31u - (u32)__clz((int)(((caps.maxW + 3) & ~3u) * 8u)));
         __syncwarp();
         // ---- task table (lane 0), allocation in the flat pool / task array
         u32 nTasks = 0, nWinC = 0, nSeeds = 0, taskBase = 0;
