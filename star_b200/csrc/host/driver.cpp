@@ -293,7 +293,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         // touched, so the untouched pages are never faulted in)
         star_read_result_t* results = nullptr; uint64_t resultsCap = 0; bool resultsPinned = false;
         star_align_t* aligns = nullptr; uint64_t alignsCap = 0; bool alignsPinned = false;
-        uint8_t* inPin = nullptr; uint64_t inPinCap = 0;   // page-locked copy of the chunk's sequences + offsets (the reader's strings are pageable)
+        uint8_t* inPin = nullptr; uint64_t inPinCap = 0, inOffAt = 0; bool inStaged = false;   // page-locked copy of the chunk's sequences + offsets (the reader's strings are pageable), made by the reader thread
         star_align_batch_t out;
         long long n = 0;          // reads in the chunk; 0 = end of input; < 0 = -STAR_EXIT_* (err holds the message)
         std::string err;
@@ -303,6 +303,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         void push(Work* w) { { std::lock_guard<std::mutex> l(m); q.push_back(w); } cv.notify_one(); }
         Work* pop() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty(); }); Work* w = q.front(); q.pop_front(); return w; }
     };
+    const bool canPin = eng->host_alloc && eng->host_free && eng->download_results;
     auto hostAlloc = [&](uint64_t bytes, bool pin, bool& pinned) -> void* {
         void* p = pin ? eng->host_alloc(bytes) : nullptr;
         pinned = p != nullptr;
@@ -344,6 +345,19 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             if (firstStage) wk->n = reader.next(wk->chunk, P.gpuChunkReads, wk->err);
             else if (heldNext < stage.held.size()) { wk->chunk = std::move(stage.held[heldNext++]); wk->n = wk->chunk.nReads; }
             else wk->n = 0;
+            wk->inStaged = false;
+            if (canPin && wk->n > 0) {   // sequences and offsets of the chunk through one page-locked block (the engine copies from it)
+                const ReadChunk& ch = wk->chunk;
+                const char* sq = ch.clipped() ? ch.seqC.data() : ch.seq.data();                 // the engine maps the clipped reads
+                const uint64_t* so = ch.clipped() ? ch.seqOffC.data() : ch.seqOff.data();
+                const uint64_t nOff = (uint64_t)ch.nReads * ch.nMates + 1, seqBytes = so[nOff - 1], offAt = (seqBytes + 15) & ~15ULL;
+                const uint64_t need = offAt + nOff * 8;
+                if (wk->inPinCap >= need) {   // (the block is allocated / grown by the engine thread, whose current device is the run's)
+                    memcpy(wk->inPin, sq, seqBytes);
+                    memcpy(wk->inPin + offAt, so, nOff * 8);
+                    wk->inOffAt = offAt; wk->inStaged = true;
+                }
+            }
             msRead += msSince(t0);
             const long long n = wk->n;
             mapQ.push(wk);
@@ -494,7 +508,6 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         in.nReads = chunk.nReads; in.nMates = chunk.nMates; in.seq = chunk.seq.data(); in.seqOff = chunk.seqOff.data();
         if (chunk.clipped()) { in.seq = chunk.seqC.data(); in.seqOff = chunk.seqOffC.data(); }   // the engine maps the clipped reads
         const uint64_t capWorst = (uint64_t)chunk.nReads * std::max<uint64_t>(1, P.hp.outFilterMultimapNmax);
-        const bool canPin = eng->host_alloc && eng->host_free && eng->download_results;
         auto growAligns = [&](uint64_t cap) {   // false: out of memory
             if (wk->alignsCap >= cap) return true;
             hostFree(wk->aligns, wk->alignsPinned);
@@ -510,7 +523,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             wk->results = (star_read_result_t*)hostAlloc(wk->resultsCap * sizeof(star_read_result_t), canPin, wk->resultsPinned);
             if (!wk->results) { wk->resultsCap = 0; memOk = false; }
         }
-        if (canPin && memOk) {   // sequences and offsets through one page-locked block
+        if (canPin && !wk->inStaged) {   // first chunk through this buffer, or a chunk larger than all before: (re)allocate the page-locked block here
             const uint64_t nOff = (uint64_t)in.nReads * in.nMates + 1, seqBytes = in.seqOff[nOff - 1], offAt = (seqBytes + 15) & ~15ULL;
             const uint64_t need = offAt + nOff * 8;
             if (wk->inPinCap < need) {
@@ -522,9 +535,10 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
             if (wk->inPin) {
                 memcpy(wk->inPin, in.seq, seqBytes);
                 memcpy(wk->inPin + offAt, in.seqOff, nOff * 8);
-                in.seq = (const char*)wk->inPin; in.seqOff = (const uint64_t*)(wk->inPin + offAt);
+                wk->inOffAt = offAt; wk->inStaged = true;
             }
         }
+        if (wk->inStaged) { in.seq = (const char*)wk->inPin; in.seqOff = (const uint64_t*)(wk->inPin + wk->inOffAt); }   // (normally copied by the reader thread)
         wk->out.reads = wk->results; wk->out.aligns = wk->aligns; wk->out.alignsCapacity = wk->alignsCap; wk->out.nAligns = 0;
         star_chunk_stats_t cs;
         memset(&cs, 0, sizeof(cs));

@@ -195,3 +195,45 @@ def test_init_failure_is_a_clean_error_and_leaves_nothing_behind(lib, oracle, go
     res_o, al_o, _ = oe.map_chunk(seq, off, n, nm)
     oe.close()
     assert not oc.compare_outputs(res_o, al_o, res_g, al_g)
+
+
+def test_page_locked_buffers_and_second_fetch(lib, golden, tiny_index):
+    """star_gpu_host_alloc / star_gpu_host_free hand out page-locked memory the chunk calls accept; a record buffer that is too small makes
+    star_gpu_map_chunk return STAR_EXIT_RUNTIME with out.nAligns = the capacity needed and keeps the results resident, and
+    star_gpu_download_results into a large enough buffer returns what a call with a large buffer returns."""
+    import ctypes as C
+    import star_b200 as sb
+    from star_b200 import capi
+    lib.star_gpu_host_alloc.restype = C.c_void_p
+    lib.star_gpu_host_alloc.argtypes = [C.c_size_t]
+    lib.star_gpu_host_free.argtypes = [C.c_void_p]
+    mates = [cf.read_fastq_seqs(f) for f in _sets(golden)["std"]]
+    seq, off, n, nm = sb.pack_reads(mates)
+    eng = sb.Engine(lib, tiny_index, max_reads=n)
+    res0, al0, _ = eng.map_chunk(seq, off, n, nm)
+    assert al0.shape[0] > 8
+    # sequences, offsets, results and records in page-locked memory
+    sizes = [seq.nbytes, off.nbytes, n * capi.RESULT_DTYPE.itemsize, al0.shape[0] * capi.ALIGN_DTYPE.itemsize]
+    ptrs = [lib.star_gpu_host_alloc(s) for s in sizes]
+    assert all(ptrs)
+    try:
+        C.memmove(ptrs[0], seq.ctypes.data, seq.nbytes)
+        C.memmove(ptrs[1], off.ctypes.data, off.nbytes)
+        b = capi.ReadBatch()
+        b.nReads, b.nMates, b.seq, b.seqOff = n, nm, ptrs[0], ptrs[1]
+        ab = capi.AlignBatch()
+        ab.reads, ab.aligns, ab.alignsCapacity, ab.nAligns = ptrs[2], ptrs[3], 8, 0      # too small on purpose
+        st = capi.ChunkStats()
+        rc = lib.star_gpu_map_chunk(eng.ctx, C.byref(b), C.byref(ab), C.byref(st))
+        assert rc != 0 and ab.nAligns == al0.shape[0]
+        ab.alignsCapacity, ab.nAligns = al0.shape[0], 0
+        assert lib.star_gpu_download_results(eng.ctx, C.byref(ab)) == 0 and ab.nAligns == al0.shape[0]
+        res1 = np.frombuffer((C.c_char * sizes[2]).from_address(ptrs[2]), dtype=capi.RESULT_DTYPE).copy()
+        al1 = np.frombuffer((C.c_char * sizes[3]).from_address(ptrs[3]), dtype=capi.ALIGN_DTYPE).copy()
+        import oracle_capi as oc
+        diffs = oc.compare_outputs(res0, al0, res1, al1)     # field by field (padding bytes are not part of the contract)
+        assert not diffs, "\n".join(diffs[:10])
+    finally:
+        for p in ptrs:
+            lib.star_gpu_host_free(p)
+        eng.close()
