@@ -20,6 +20,8 @@ import csv
 rows=list(csv.reader(open("gpurun_out/g8_g38_seed_raw.csv"))); hdr=rows[0]; vals=rows[2]
 for k in ["gpu__time_duration.sum","dram__bytes_read.sum","dram__bytes_write.sum","smsp__inst_executed.sum","smsp__thread_inst_executed_per_inst_executed.ratio"]: print(k, vals[hdr.index(k)])
 PY
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/g8_g38_launches.csv python bench.py --preset grch38 --steps 2 --warmup 1 --no-cli --no-cpu > gpurun_out/g8_launch_bench.log 2>&1
+el launch list done
 timeout 600 python tools/variants.py grch38 1048576 -- base STAR_B200_BIN_FILTER=0 STAR_B200_L2_FETCH_BYTES=64 STAR_B200_SORTED_LOOKUP_MIN=48 STAR_B200_SORTED_LOOKUP_MIN=4 STAR_B200_FLAT_SETUP_CTAS_PER_SM=4 STAR_B200_FLAT_DFS_CTAS_PER_SM=5 STAR_B200_SEED_KEYED_CTAS_PER_SM=12 STAR_B200_HEAVY_SPLIT=40 base > gpurun_out/g8_variants.jsonl 2> gpurun_out/g8_variants.log; cat gpurun_out/g8_variants.jsonl
 el variants done
 el all done
