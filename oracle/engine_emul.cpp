@@ -276,7 +276,7 @@ int engine_emul_map_chunk(const star_index_view_t* view, const star_params_t* pa
     fast.maxP = std::min<u32>(128, (u32)P.seedPerReadNmax);
     fast.maxW = (std::min<u32>(128, (u32)P.alignWindowsPerReadNmax) + 1) & ~1u;
     fast.maxTr = std::min<u32>(128, (u32)P.alignTranscriptsPerReadNmax);
-    fast.spw = (u32)P.seedPerWindowNmax; fast.nOut = nOut; fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12); fast.binFilter = envU32("STAR_B200_BIN_FILTER", 1); fast.arenaBytes = arenaSize(fast);
+    fast.spw = (u32)P.seedPerWindowNmax; fast.nOut = nOut; fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12); fast.binFilter = envU32("STAR_B200_BIN_FILTER", 0); fast.arenaBytes = arenaSize(fast);
     Caps heavy = fast;
     heavy.maxW = (std::min<u32>((u32)P.alignWindowsPerReadNmax, 256) + 1) & ~1u;
     heavy.maxTr = std::min<u32>((u32)P.alignTranscriptsPerReadNmax, 1024);

@@ -152,7 +152,7 @@ struct Caps {
     u32 maxTr;       // transcript pool per read
     u32 spw;         // seedPerWindowNmax
     u32 nOut;        // staged alignments per read (outFilterMultimapNmax)
-    u32 binFilter = 1;   // setup kernel: hashed (strand, bin) bitmap in front of the window lookup of a locus
+    u32 binFilter = 0;   // setup kernel: hashed (strand, bin) bitmap in front of the window lookup of a locus (STAR_B200_BIN_FILTER=1; measured: no gain)
     u32 sortMinW = 12;   // reads with more windows than this look a locus' window up by bisection (sorted index) instead of a scan
     u64 arenaBytes;
 };

@@ -237,9 +237,11 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->nSM = prop.multiProcessorCount;
-    {   // The path is random 32-byte sector access over an index of tens of GB; with the default 64-byte fill granularity of L2 every miss fetches
-        // a neighbour sector nobody reads (measured: DRAM bytes ~2 x the sectors the kernels request).  A hint: ignored where unsupported.
-        const u32 gran = envU32("STAR_B200_L2_FETCH_BYTES", 32);
+    {   // The path is random 32-byte sector access over an index of tens of GB; with 64-byte fills of L2 every miss fetches a neighbour sector
+        // that is rarely read.  Measured at GRCh38 size (profiles/r02_summary.md, last call): 32-byte fills halve the DRAM bytes of the seed search
+        // (8.2 instead of 17.5 GB per launch) but the kernels are latency-bound, not bandwidth-bound, and the neighbour sector is a free prefetch
+        // for the key / SA / genome reads that do continue: the step is 1.6 % FASTER with 64-byte fills (193.6 vs 196.8 ms).  Default 64.
+        const u32 gran = envU32("STAR_B200_L2_FETCH_BYTES", 64);
         if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
         cudaGetLastError();
     }
@@ -334,7 +336,7 @@ static int initCtx(star_ctx* c, int device, const star_index_view_t* v, const st
     c->fast.spw = (u32)params->seedPerWindowNmax;
     c->fast.nOut = nOut;
     c->fast.sortMinW = envU32("STAR_B200_SORTED_LOOKUP_MIN", 12);
-    c->fast.binFilter = envU32("STAR_B200_BIN_FILTER", 1);
+    c->fast.binFilter = envU32("STAR_B200_BIN_FILTER", 0);   // measured at GRCh38 size: no gain over the bisection (195.9 ms without, 196.6-196.9 ms with): off
     if (c->fast.maxP > params->seedPerReadNmax) c->fast.maxP = (u32)params->seedPerReadNmax;
     if (c->fast.maxW > params->alignWindowsPerReadNmax) c->fast.maxW = (u32)params->alignWindowsPerReadNmax;
     c->fast.maxW = (c->fast.maxW + 1) & ~1u;

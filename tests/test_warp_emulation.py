@@ -121,7 +121,8 @@ def test_emulated_keyed_seed_stage_equals_oracle_pieces(oracle, lib, golden, nam
     ("se", 12, {}),
     ("std", 8, {"STAR_B200_HEAVY_SPLIT": "2", "STAR_B200_FLAT_STORE_ALL": "0"}),           # many prefix sub-trees; leaves replayed by the recording kernel
     ("std", 8, {"ENGINE_EMUL_HOST_RECORD": "1"}),                                          # task kernel + sequential host restatement of the recording
-    ("std", 12, {"STAR_B200_BIN_FILTER": "0"}),                                           # without the hashed (strand, bin) bitmap in front of the window lookup (on in every other case)
+    ("std", 12, {"STAR_B200_BIN_FILTER": "1"}),                                           # with the hashed (strand, bin) bitmap in front of the window lookup (optional: measured no gain)
+    ("hard", 2, {"STAR_B200_BIN_FILTER": "1", "STAR_B200_SORTED_LOOKUP_MIN": "1"}),       # ... in front of the bisection
     ("std", 16, {"STAR_B200_SORTED_LOOKUP_MIN": "1"}),                                    # window of a locus by bisection over the sorted live windows (reads with many windows)
     ("hard", 4, {"STAR_B200_SORTED_LOOKUP_MIN": "1", "STAR_B200_HEAVY_FLAT": "0"}),        # ... in the warp-per-read kernel
     ("std", 12, {"STAR_B200_SEED_RECS_PER_READ": "16"}),                                  # reads flagged by the seed stage: re-seeded by the warp kernel, flat kernels again (overflow tier)
