@@ -462,7 +462,10 @@ def main():
                 eng = None
                 rep = max(1, a.cli_repeat)
                 f1, f2 = ",".join([fq1] * rep), ",".join([fq2] * rep)
-                threads = min(host_cores, 64)
+                # --runThreadN of OUR command line: its reader, formatter and writer stages each use up to that many threads next to the engine thread.
+                # Measured on the 128-core box (profiles/r02g_cli_threads.txt): every stage is faster with 32 than with 64 (engine 121 / 159 ms per
+                # chunk, formatting 145 / 172, reader 115 / 155, writes 77 / 125) and much slower with 112: the stages compete for the cores.
+                threads = max(8, min(32, host_cores // 4))
                 t_base = cli_run(idx, f1, f2, os.path.join(workdir, "cli_base"), threads, ["--readMapNumber", "1"], local_rank)
                 t_full = cli_run(idx, f1, f2, os.path.join(workdir, "cli_run"), threads, [], local_rank)
                 host_lines = []

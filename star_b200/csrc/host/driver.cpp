@@ -327,7 +327,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
     // coordinate-sorted BAM: all records stay in host memory (uncompressed, ~0.55 kB per record) until the end of the run
     std::vector<std::string>& coordBlobs = stage.coordBlobs;
     std::vector<CoordRec>& coordIndex = stage.coordIndex;
-    const int nT = std::max(1, P.runThreadN);
+    const int nT = P.stageThreads();
     double msEngine = 0, msRead = 0, msFormat = 0, msWrite = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     const auto tPass0 = now();

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,14 @@ struct HostParams {
     std::string commandLine, commandLineFull;
     std::string runMode = "alignReads";
     int runThreadN = 1;                     // host threads used for FASTQ parsing / SAM formatting
+    // Threads each host stage of the mapping pass (chunk parsing, record formatting) uses: the stages run concurrently next to the thread that
+    // drives the GPU, so every stage taking --runThreadN threads oversubscribes the cores and starves that thread.  Measured on a 128-core
+    // box (profiles/r02g_cli_threads.txt): with 32 / 64 / 112 threads per stage the engine needs 121 / 159 / 273 ms per chunk of 524 288
+    // pairs, formatting 145 / 172 / 182 ms, the reader 115 / 155 / 155 ms.  Capped at 32 (STAR_B200_HOST_STAGE_THREADS overrides the cap).
+    int stageThreads() const {
+        static const int cap = [] { const char* e = getenv("STAR_B200_HOST_STAGE_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
+        return runThreadN < 1 ? 1 : (runThreadN < cap ? runThreadN : cap);
+    }
     std::string genomeDir = "./GenomeDir/";
     std::string genomeLoad = "NoSharedMemory";
     std::vector<std::string> readFilesIn = {"Read1", "Read2"};

@@ -313,7 +313,7 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     // every mate's lines are found by several threads: the range expected to hold 4*want lines (from the line length seen so far) is cut
     // into slices, each thread collects the newlines of its slice (this is also where the pages of the mapped file are faulted in), the
     // slices are concatenated in order; short of lines, the next range is scanned the same way
-    const int nIdx = (int)std::max(1, std::min(16, std::max(1, P->runThreadN) / (int)nMates));
+    const int nIdx = (int)std::max(1, std::min(16, P->stageThreads() / (int)nMates));
     auto indexMate = [&](unsigned m) {
         const char* base = map[m];
         const size_t size = mapSize[m], off0 = mapOff[m];
@@ -383,7 +383,7 @@ long long ReadsReader::nextFast(ReadChunk& c, uint32_t maxReads, std::string& er
     }
     auto T1 = std::chrono::steady_clock::now();
     // (B) parallel parse
-    const int nT = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, P->runThreadN), nRec / 256 + 1));
+    const int nT = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)P->stageThreads(), nRec / 256 + 1));
     if ((int)parts_.size() < nT) parts_.resize(nT);
     std::vector<ReadChunk>& part = parts_;
     std::vector<std::string> perr(nT);
