@@ -57,6 +57,28 @@ def workload_name(preset, read_len, mm):
     return "%s, 2x%d bp PE, %.1f%% subst" % (g, read_len, mm * 100)
 
 
+def allowed_cpus():
+    """CPUs this process may use: the affinity mask, limited by the cgroup CPU quota (v2 cpu.max, v1 cfs_quota / cfs_period)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, -(-int(q) // int(p))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                n = min(n, max(1, -(-q // p)))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def prepare_genome(workdir, preset, device=0):
     """genome.fa + annot.gtf + idx/ under workdir (built once, cached).  Returns (chrs, trs, idx_dir, build_info)."""
     import synth
@@ -257,6 +279,7 @@ def main():
     os.makedirs(workdir, exist_ok=True)
     workload = workload_name(a.preset, a.read_len, a.mm)
     host_cores = os.cpu_count() or 1
+    cpus_allowed = allowed_cpus()   # cgroup quota: the GPU boxes of round 2 show 128 logical CPUs and allow 16 (cpu.max = 1600000 100000)
     n = a.pairs
     config = {"workload": workload, "fallback": fallback, "pairs_per_gpu_per_step": n, "read_definition": "one 2x%d pair = one read (STAR 'Number of input reads')" % a.read_len,
               "reads": "tools/synth.py make_reads seed 1000 + rank: 50 % from annotated transcripts, 50 % from the genome, fragment 300"}
@@ -292,7 +315,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
                 "config": dict(config, reference_sample_pairs_per_step=rp * rep, threads=host_cores, index_build=build),
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores, "kind": "reference", "sample": sample},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores, "cpus_allowed_by_cgroup": cpus_allowed, "kind": "reference", "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
@@ -451,7 +474,7 @@ def main():
                     dt, wall_ref, _ = rr.run(f1, f2)
                 finally:
                     rr.stop()
-                cpu = {"value": rp * rep / dt, "unit": UNIT, "cores": host_cores, "kind": "reference",
+                cpu = {"value": rp * rep / dt, "unit": UNIT, "cores": host_cores, "cpus_allowed_by_cgroup": cpus_allowed, "kind": "reference",
                        "sample": "%d x the first %d pairs of the step's chunk, oracle/_ref/STAR --runThreadN %d --outSAMtype SAM, %s (%.2f s - %.2f s)"
                                  % (rep, rp, host_cores, rr.describe(), wall_ref, rr.base),
                        "oracle_port_1thread_pairs_per_s": ns / t_oracle}
@@ -486,7 +509,7 @@ def main():
                 t_map = max(t_full - t_base, pass_wall or 0.0, 1e-3)
                 cli = {"value": rp * rep / t_map, "stage_times_from_Log_out": host_lines, "mapping_pass_wall_s": pass_wall,
                        "pairs_per_s_by_wall_minus_startup": rp * rep / max(1e-3, t_full - t_base),
-                       "pairs_per_s_by_mapping_pass_wall": (rp * rep / pass_wall) if pass_wall else None, "unit": UNIT, "pairs": rp * rep, "wall_s": t_full, "startup_and_index_load_s": t_base, "host_threads": threads,
+                       "pairs_per_s_by_mapping_pass_wall": (rp * rep / pass_wall) if pass_wall else None, "unit": UNIT, "pairs": rp * rep, "wall_s": t_full, "startup_and_index_load_s": t_base, "host_threads": threads, "cpus_allowed_by_cgroup": cpus_allowed,
                        "scope": "star_b200/bin/STAR: FASTQ files -> Aligned.out.sam + SJ.out.tab + Log.final.out, wall clock minus a --readMapNumber 1 run (same files and scope as the reference arm)"}
                 # the command line's records for the sample equal the engine's input order: check them against the reference's on a small prefix
                 try:

@@ -588,6 +588,7 @@ static int mapPass(const HostParams& P, const LoadedIndex& idx, const star_engin
         writeSortedBam(P, W, coordBlobs, coordIndex, nT);
     }
     logMain << "star-b200: engine time " << msEngine << " ms over " << nChunks << " chunks; mapping pass wall " << msSince(tPass0) << " ms\n";
+    logMain << "star-b200: host stages used " << nT << " threads each (--runThreadN " << P.runThreadN << ", CPUs allowed to this process " << HostParams::allowedCpus() << ")\n";
     logMain << "star-b200: host time: reads input " << msRead << " ms, SAM/SJ formatting " << msFormat << " ms, output writes " << msWrite << " ms\n";
     return 0;
 }

@@ -23,13 +23,20 @@ struct HostParams {
     std::string commandLine, commandLineFull;
     std::string runMode = "alignReads";
     int runThreadN = 1;                     // host threads used for FASTQ parsing / SAM formatting
-    // Threads each host stage of the mapping pass (chunk parsing, record formatting) uses: the stages run concurrently next to the thread that
-    // drives the GPU, so every stage taking --runThreadN threads oversubscribes the cores and starves that thread.  Measured on a 128-core
-    // box (profiles/r02g_cli_threads.txt): with 32 / 64 / 112 threads per stage the engine needs 121 / 159 / 273 ms per chunk of 524 288
-    // pairs, formatting 145 / 172 / 182 ms, the reader 115 / 155 / 155 ms.  Capped at 32 (STAR_B200_HOST_STAGE_THREADS overrides the cap).
+    // Threads each host stage of the mapping pass (chunk parsing, record formatting) uses.  The stages run concurrently next to the thread that
+    // drives the GPU; what they may use is the CPU time the process is ALLOWED, which in a container is the cgroup quota, not the number
+    // of logical CPUs it sees.  Measured on the round's GPU boxes (128 logical CPUs visible, cpu.max = 16 CPUs; profiles/r02g_cli_threads.txt):
+    // with 32 / 64 / 112 threads per stage the engine needs 121 / 159 / 273 ms per chunk of 524 288 pairs (its kernels take 96 ms), formatting
+    // 145 / 172 / 182 ms, the reader 115 / 155 / 155 ms — the bursts of many runnable threads exhaust the quota of a scheduling period and the
+    // whole process, including the thread that feeds the GPU, is frozen until the next one.  Per stage: --runThreadN, at most 32, at most half
+    // of the allowed CPUs (at least 2).  STAR_B200_HOST_STAGE_THREADS sets the number directly.
+    static int allowedCpus();   // min(logical CPUs of the affinity mask, cgroup CPU quota); params.cpp
     int stageThreads() const {
-        static const int cap = [] { const char* e = getenv("STAR_B200_HOST_STAGE_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
-        return runThreadN < 1 ? 1 : (runThreadN < cap ? runThreadN : cap);
+        static const int fixed = [] { const char* e = getenv("STAR_B200_HOST_STAGE_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+        static const int cap = [] { const int half = allowedCpus() / 2; return half < 2 ? 2 : (half > 32 ? 32 : half); }();
+        const int t = runThreadN < 1 ? 1 : runThreadN;
+        if (fixed) return t < fixed ? t : fixed;
+        return t < cap ? t : cap;
     }
     std::string genomeDir = "./GenomeDir/";
     std::string genomeLoad = "NoSharedMemory";

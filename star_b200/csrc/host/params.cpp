@@ -4,6 +4,9 @@
 // (reference source/Parameters.cpp:19-305 registry, :310-470 input levels, :944-1124 derived values,
 // defaults from source/parametersDefault).  Every other STAR parameter is recognised by name and
 // rejected with a clear message when given: config breadth is outside the hot-path scope.
+#include <cstdio>
+#include <thread>
+#include <sched.h>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -14,6 +17,32 @@
 #include "host.h"
 
 namespace starhost {
+
+int HostParams::allowedCpus() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = CPU_COUNT(&set);
+    // cgroup v2: "<quota> <period>" or "max <period>"; cgroup v1: two files
+    double quota = -1, period = -1;
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64] = {0};
+        double p = 0;
+        if (fscanf(f, "%63s %lf", q, &p) == 2 && strcmp(q, "max") != 0) { quota = atof(q); period = p; }
+        fclose(f);
+    } else {
+        FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+        FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+        if (fq && fp) { if (fscanf(fq, "%lf", &quota) != 1) quota = -1; if (fscanf(fp, "%lf", &period) != 1) period = -1; }
+        if (fq) fclose(fq);
+        if (fp) fclose(fp);
+    }
+    if (quota > 0 && period > 0) {
+        const int q = (int)((quota + period - 1) / period);
+        if (q >= 1 && q < n) n = q;
+    }
+    return n < 1 ? 1 : n;
+}
 
 void paramsDefault(star_params_t* p) {  // source/parametersDefault
     memset(p, 0, sizeof(*p));
