@@ -32,6 +32,26 @@ static inline void putI(std::string& s, long long v) {
     if (v < 0) { s.push_back('-'); putU(s, (uint64_t)(-(v + 1)) + 1); } else putU(s, (uint64_t)v);
 }
 
+static const char* revComplementTable() {   // SequenceFuns.cpp:16-54
+    struct Tab {   // built once, thread-safely (function-local static): the formatting threads call this concurrently
+        char t[256];
+        Tab() {
+            for (int i = 0; i < 256; i++) t[i] = (char)i;
+            const char* a = "ACGTNRYKMSWBDVHacgtnrykmswbdvh";
+            const char* b = "TGCANYRMKSWVHBDtgcanyrmkswvhbd";
+            for (int i = 0; a[i]; i++) t[(unsigned char)a[i]] = b[i];
+        }
+    };
+    static const Tab T;
+    return T.t;
+}
+static void revComplementAppend(const char* in, size_t L, std::string& s) {   // appends the reverse complement to s (no temporary)
+    const char* tab = revComplementTable();
+    const size_t o = s.size();
+    s.resize(o + L);
+    char* d = &s[o];
+    for (size_t j = 0; j < L; j++) d[j] = tab[(unsigned char)in[L - 1 - j]];
+}
 static void revComplement(const char* in, size_t L, std::string& out) {  // SequenceFuns.cpp:16-54
     struct Tab {   // built once, thread-safely (function-local static): the formatting threads call this concurrently
         char t[256];
@@ -201,7 +221,6 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
         if (trimR1 > 0) { putU(cg, trimR1); cg.push_back('S'); }
     }
 
-    std::string rc;
     for (unsigned imate = 0; imate < nMates; imate++) {
         unsigned samFLAG = samFlagCommon;
         uint32_t iEx1 = ex1[imate], iEx2 = ex2[imate];
@@ -232,13 +251,18 @@ void OutputWriter::samMapped(const ReadChunk& c, uint32_t i, const star_read_res
         if (Mate == Str) {
             s.append(c.seq, a, b - a);
         } else {
-            revComplement(c.seq.data() + a, b - a, rc);
-            s += rc;
+            revComplementAppend(c.seq.data() + a, b - a, s);
         }
         s.push_back('\t');
         if (c.fastq && P.outSAMmode != "NoQS") {
             if (Mate == Str) s.append(c.qual, a, b - a);
-            else for (uint64_t k = 0; k < b - a; k++) s.push_back(c.qual[b - 1 - k]);
+            else {   // reversed, written in place (one resize instead of a capacity check per character)
+                const size_t o = s.size(), L = b - a;
+                s.resize(o + L);
+                char* d = &s[o];
+                const char* q = c.qual.data() + a;
+                for (size_t k = 0; k < L; k++) d[k] = q[L - 1 - k];
+            }
         } else {
             s.push_back('*');
         }
