@@ -250,3 +250,29 @@ def test_page_locked_chunk_buffers_and_second_fetch(oracle, golden, tmp_path, pc
     assert cf.sam_body(out + "Aligned.out.sam") == cf.sam_body(os.path.join(ref, "Aligned.out.sam"))
     assert open(out + "SJ.out.tab", "rb").read() == open(os.path.join(ref, "SJ.out.tab"), "rb").read()
     assert cf.log_counters(out + "Log.final.out") == cf.log_counters(os.path.join(ref, "Log.final.out"))
+
+
+def test_host_stage_threads_follow_the_cpu_allowance(oracle, golden, tmp_path):
+    """The reader and the formatter run next to the thread that drives the GPU: each uses min(--runThreadN, 32, CPUs allowed / 2) threads
+    (affinity mask and cgroup quota, not the logical CPUs the process sees), or STAR_B200_HOST_STAGE_THREADS; Log.out reports the number
+    and the output does not depend on it."""
+    import re
+    outs = []
+    for tag, env_extra, thr in (("a", {}, 64), ("b", {"STAR_B200_HOST_STAGE_THREADS": "3"}, 64), ("c", {}, 1)):
+        out = str(tmp_path) + "/" + tag + "/"
+        os.makedirs(out)
+        cmd = [oc.ORACLE_CLI, "--genomeDir", os.path.join(golden, "idx"), "--readFilesIn", os.path.join(golden, "std_1.fq"), os.path.join(golden, "std_2.fq"),
+               "--outFileNamePrefix", out, "--runThreadN", str(thr), "--gpuChunkReads", "700"]
+        subprocess.run(cmd, env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=300, check=True)
+        m = re.search(r"host stages used (\d+) threads each \(--runThreadN (\d+), CPUs allowed to this process (\d+)\)", open(out + "Log.out").read())
+        assert m, "no thread report in Log.out"
+        used, asked, allowed = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        assert asked == thr and 1 <= allowed <= (os.cpu_count() or 1)
+        if tag == "a":
+            assert used == max(2, min(32, allowed // 2, thr)) or used == min(thr, max(2, min(32, allowed // 2)))
+        elif tag == "b":
+            assert used == 3
+        else:
+            assert used == 1
+        outs.append(cf.sam_body(out + "Aligned.out.sam"))
+    assert outs[0] == outs[1] == outs[2]
