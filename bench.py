@@ -449,7 +449,13 @@ def main():
             try:
                 tj = json.load(open(tpath))
                 if int(tj.get("pairs_per_launch", -1)) == n and tj.get("preset") == a.preset and tj.get("read_len", 100) == a.read_len:
-                    traffic = tj.get("dram_bytes_per_launch")
+                    import hashlib
+                    hh = hashlib.sha1()
+                    for fsrc in ("seed_keyed.cuh", "seed_warp.cuh", "seed_types.cuh"):   # the capture is only valid for the kernel sources it was taken from
+                        hh.update(open(os.path.join(ROOT, "star_b200", "csrc", "engine", fsrc), "rb").read())
+                    l2 = int(os.environ.get("STAR_B200_L2_FETCH_BYTES", "64"))
+                    if tj.get("kernel_sources_sha1") == hh.hexdigest() and int(tj.get("l2_fetch_bytes", 64)) == l2:
+                        traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
         roofline = {"bound": "hbm", "kernel": "MMP seed search (all kernels between the prep and the window stage)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
